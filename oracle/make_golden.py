@@ -1,0 +1,171 @@
+"""Generate tests/golden/*.npz by running the REAL reference modules from /root/reference.
+
+TEST INFRASTRUCTURE.  Only runs in the authoring container (needs /root/reference).  The
+reference classes are AST-loaded (oracle/ref_loader.py), never copied; the same seeded weights
+the product uses (vadx.weights.*_random_init) are loaded into them with load_state_dict.
+
+    python -m oracle.make_golden [firered] [postproc] [fsmn] [marblenet] [dfsmn] ...
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader as RL  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _sd_from_numpy(w):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}
+
+
+# ------------------------------------------------------------------------------ FireRed
+def firered_reference(cfg, weights, streaming=False):
+    stft = RL.import_file("FireRedVAD/STFT_Process.py", "STFT_Process")
+    ns = RL.extract("FireRedVAD/Export_FireRedVAD.py", {"STFT_Process": stft.STFT_Process})
+    args = RL.Args(idim=cfg.idim, R=cfg.R, M=cfg.M, H=cfg.H, P=cfg.P, N1=cfg.N1, S1=cfg.S1,
+                   N2=cfg.N2, S2=cfg.S2, odim=cfg.odim)
+    if streaming:
+        dm = ns["DetectModel_Streaming"](args).eval()
+        dm.load_state_dict(_sd_from_numpy(weights), strict=True)
+        return ns["FireRedStreamVAD_ONNX"](dm, cfg.n_fft, cfg.hop, cfg.win_length, cfg.n_mels, 16000,
+                                           cfg.pre_emphasis, cfg.window).eval(), ns
+    dm = ns["DetectModel"](args).eval()
+    dm.load_state_dict(_sd_from_numpy(weights), strict=True)
+    return ns["FireRedVAD_ONNX"](dm, cfg.n_fft, cfg.hop, cfg.win_length, cfg.n_mels, 16000,
+                                 cfg.pre_emphasis, cfg.window).eval(), ns
+
+
+def gen_firered():
+    import vadx  # noqa: F401
+    from vadx import synth, weights as W
+
+    out = {}
+    # (1) default architecture, the reference validation recipe: seed 1234, randint(-8000, 8000)
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, seed=0)
+    ref, ns = firered_reference(cfg, w)
+    np.random.seed(1234)
+    a0 = np.random.randint(-8000, 8000, size=(1, 1, 16000)).astype(np.int16)
+    with torch.inference_mode():
+        out["recipe_probs"] = ref(torch.from_numpy(a0)).numpy()
+    # (2) enveloped synthetic chunks (the bench workload), batch-1 calls like the reference
+    chunks = synth.synth_streams(6, 16000, seed=1234)
+    with torch.inference_mode():
+        out["synth_probs"] = np.stack([ref(torch.from_numpy(c).view(1, 1, -1)).numpy()[0] for c in chunks])
+        # intermediate: log-mel of chunk 0, by replaying the wrapper's frontend
+        x = torch.from_numpy(chunks[0]).view(1, 1, -1).float()
+        x = torch.nn.functional.conv1d(torch.nn.functional.pad(x, (1, 0)), ref.preemph_kernel)
+        re, im = ref.stft(x)
+        pw = re * re + im * im
+        out["synth_power0"] = pw.numpy()[0, :, ::7]
+        mel = torch.clamp(torch.nn.functional.conv1d(pw, ref.fbank_conv), min=1e-7).log()
+        out["synth_logmel0"] = mel.numpy()[0]
+    # (3) ragged length (dynamic axis), 5000 samples -> 29 frames; and minimal 400 -> 1 frame
+    for L in (5000, 400):
+        a = synth.synth_streams(1, L, seed=77)[0]
+        with torch.inference_mode():
+            out[f"len{L}_probs"] = ref(torch.from_numpy(a).view(1, 1, -1)).numpy()
+    # (4) AED head (odim 3) on a small architecture with strides > 1
+    cfg3 = W.FireRedConfig(R=3, H=96, P=64, N1=5, S1=2, N2=3, S2=2, odim=3)
+    w3 = W.firered_random_init(cfg3, seed=3)
+    ref3, _ = firered_reference(cfg3, w3)
+    with torch.inference_mode():
+        out["aed_probs"] = ref3(torch.from_numpy(chunks[1]).view(1, 1, -1)).numpy()
+    # (5) streaming twin: 2560-sample chunks with cache carry over 4 chunks
+    cfgs = W.FireRedConfig(N2=0, S2=0, streaming=True)
+    ws = W.firered_random_init(cfgs, seed=5)
+    refs, _ = firered_reference(cfgs, ws, streaming=True)
+    caches = torch.zeros(cfgs.R, 1, cfgs.P, (cfgs.N1 - 1) * cfgs.S1)
+    pr = []
+    with torch.inference_mode():
+        for i in range(4):
+            p, caches = refs(torch.from_numpy(chunks[2][i * 2560:(i + 1) * 2560].copy()).view(1, 1, -1), caches)
+            pr.append(p.numpy()[0, 0])
+    out["stream_probs"] = np.stack(pr)
+    out["stream_caches_last"] = caches.numpy()[:, 0, ::16, :]
+    np.savez_compressed(os.path.join(GOLD, "firered.npz"), **out)
+    print("firered.npz:", {k: v.shape for k, v in out.items()})
+
+
+# ------------------------------------------------------------------------------ post-processing
+def gen_postproc():
+    ns = RL.extract("FireRedVAD/Inference_FireRed_ONNX.py")
+    nsn = RL.extract("NVIDIA_Frame_VAD_Multilingual_MarbleNet/Inference_NVIDIA_MarbleNet_VAD_ONNX.py")
+    nsf = RL.extract("FSMN/Inference_FSMN_VAD_ONNX.py")
+    rs = np.random.RandomState(99)
+    out = {}
+    cases = []
+    # random-walk probability tracks with plateaus so every state transition fires
+    for i, (n, ws, thr, msp, mxs, msi, mrg, ext) in enumerate([
+            (588, 5, 0.4, 20, 2000, 20, 5, 0),
+            (3000, 3, 0.5, 10, 1000, 10, 3, 0),
+            (4000, 5, 0.4, 20, 300, 20, 5, 0),     # forces max-speech splits
+            (700, 1, 0.5, 0, 2000, 0, 0, 0),       # plain threshold path
+            (900, 4, 0.45, 5, 120, 7, 4, 3),       # extend > 0
+            (3, 5, 0.4, 20, 2000, 20, 5, 0),       # shorter than the smoothing window
+            (1, 5, 0.4, 20, 2000, 20, 5, 0)]):
+        steps = rs.normal(0, 0.08, size=n)
+        lvl = np.clip(0.5 + np.cumsum(steps) * 0.5, 0, 1)
+        gate = (np.sin(np.arange(n) / rs.uniform(15, 60)) > rs.uniform(-0.5, 0.5)).astype(np.float64)
+        p = np.clip(0.15 + 0.7 * gate * lvl + rs.normal(0, 0.05, n), 0, 1).astype(np.float32)
+        if i == 2:
+            p[200:3500] = np.clip(p[200:3500] + 0.5, 0, 1)
+        cases.append((p, (ws, thr, msp, mxs, msi, mrg, ext)))
+    for i, (p, prm) in enumerate(cases):
+        pp = ns["VadPostprocessor"](*prm)
+        dec = pp.process(p.copy())
+        dur = len(p) * 0.01 + 0.012
+        seg = pp.decision_to_segment(dec, dur)
+        out[f"fr{i}_probs"] = p
+        out[f"fr{i}_params"] = np.array(prm, np.float64)
+        out[f"fr{i}_dec"] = dec
+        out[f"fr{i}_seg"] = np.array(seg, np.float64).reshape(-1, 2)
+        out[f"fr{i}_dur"] = np.array(dur)
+        # MarbleNet copy of the class (frame shift argument, open tail without +frame_length)
+        try:
+            ppn = nsn["VadPostprocessor"](*prm, 0.02)
+        except TypeError:
+            ppn = nsn["VadPostprocessor"](*prm)
+        decn = ppn.process(p.copy())
+        segn = ppn.decision_to_segment(decn, len(p) * 0.02 + 0.012)
+        out[f"nv{i}_dec"] = decn
+        out[f"nv{i}_seg"] = np.array(segn, np.float64).reshape(-1, 2)
+    # format_time + timestamp fusing
+    ts = [0.0, 2.28, 2.279999, 36480 / 16000, 59.9996, 3599.9999, 3600.5, 0.001, 1.0005, 12.3456789]
+    out["clock_in"] = np.array(ts)
+    out["clock_out"] = np.array([nsf["format_time"](t) for t in ts])
+    flags = (rs.uniform(size=2000) < 0.5)
+    flags = np.repeat(flags[:200], rs.randint(1, 40, size=200))[:2000]
+    raw = nsf["vad_to_timestamps"](list(flags), 0.01)
+    fused = nsf["process_timestamps"](list(raw), 0.3, 0.2)
+    out["runs_flags"] = flags
+    out["runs_raw"] = np.array(raw, np.float64).reshape(-1, 2)
+    out["runs_fused"] = np.array(fused, np.float64).reshape(-1, 2)
+    out["valid_frames_in"] = np.array([0, 399, 400, 559, 560, 16000, 89431, 960000])
+    out["valid_frames_out"] = np.array([ns["valid_frame_count"](int(v)) for v in out["valid_frames_in"]])
+    np.savez_compressed(os.path.join(GOLD, "postproc.npz"), **out)
+    print("postproc.npz written:", len(out), "arrays")
+
+
+GENERATORS = {"firered": gen_firered, "postproc": gen_postproc}
+
+
+def main(argv):
+    if not RL.reference_available():
+        raise SystemExit("needs /root/reference (authoring container only)")
+    os.makedirs(GOLD, exist_ok=True)
+    todo = argv or list(GENERATORS)
+    for name in todo:
+        GENERATORS[name]()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,117 @@
+"""Weight dictionaries: names/shapes follow the reference modules' state_dict keys, so a
+user holding the pretrained checkpoint can pass `module.state_dict()` (as numpy) straight in.
+
+There is no network in the build environment, so benchmarks and parity tests use
+seeded random-init weights of the named architecture (`random_init`).  The generator is
+numpy's legacy RandomState (bit-stable across numpy versions) so the same weights can be
+regenerated on any box from (model, hyper-parameters, seed).
+
+Reference anchors for the key names:
+  FireRed ... FireRedVAD/Export_FireRedVAD.py:185-326 (DetectModel.state_dict())
+  FSMN ...... FSMN/modeling_modified/encoder.py:159-217 (funasr FSMN encoder)
+"""
+from __future__ import annotations
+
+import dataclasses
+from collections import OrderedDict
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------- FireRed
+@dataclasses.dataclass(frozen=True)
+class FireRedConfig:
+    """DetectModel hyper-parameters (`package["args"]`, FireRedVAD/Export_FireRedVAD.py:310-316)."""
+    idim: int = 80
+    R: int = 8
+    M: int = 1
+    H: int = 256
+    P: int = 128
+    N1: int = 20
+    S1: int = 1
+    N2: int = 20
+    S2: int = 1
+    odim: int = 1
+    # frontend (FireRedVAD/Export_FireRedVAD.py:38-49)
+    n_fft: int = 400
+    win_length: int = 400
+    hop: int = 160
+    n_mels: int = 80
+    window: str = "povey"
+    pre_emphasis: float = 0.97
+    log_floor: float = 1e-7
+    streaming: bool = False      # Stream-VAD twin: lookback only, caches carried
+
+
+def firered_spec(cfg: FireRedConfig) -> "OrderedDict[str, tuple]":
+    s: OrderedDict[str, tuple] = OrderedDict()
+    s["dfsmn.fc1.0.weight"] = (cfg.H, cfg.idim, 1)
+    s["dfsmn.fc1.0.bias"] = (cfg.H,)
+    s["dfsmn.fc2.0.weight"] = (cfg.P, cfg.H, 1)
+    s["dfsmn.fc2.0.bias"] = (cfg.P,)
+    s["dfsmn.fsmn1.lookback_filter.weight"] = (cfg.P, 1, cfg.N1)
+    if cfg.N2 > 0 and not cfg.streaming:
+        s["dfsmn.fsmn1.lookahead_filter.weight"] = (cfg.P, 1, cfg.N2)
+    for i in range(cfg.R - 1):
+        p = f"dfsmn.fsmns.{i}."
+        s[p + "fc1.0.weight"] = (cfg.H, cfg.P, 1)
+        s[p + "fc1.0.bias"] = (cfg.H,)
+        s[p + "fc2.weight"] = (cfg.P, cfg.H, 1)
+        s[p + "fsmn.lookback_filter.weight"] = (cfg.P, 1, cfg.N1)
+        if cfg.N2 > 0 and not cfg.streaming:
+            s[p + "fsmn.lookahead_filter.weight"] = (cfg.P, 1, cfg.N2)
+    s["dfsmn.dnns.0.weight"] = (cfg.H, cfg.P, 1)
+    s["dfsmn.dnns.0.bias"] = (cfg.H,)
+    for j in range(1, cfg.M):
+        s[f"dfsmn.dnns.{2 * j}.weight"] = (cfg.H, cfg.H, 1)
+        s[f"dfsmn.dnns.{2 * j}.bias"] = (cfg.H,)
+    s["out.weight"] = (cfg.odim, cfg.H, 1)
+    s["out.bias"] = (cfg.odim,)
+    return s
+
+
+def _uniform(rs: np.random.RandomState, shape, bound: float) -> np.ndarray:
+    return rs.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+def _fan_in(shape) -> int:
+    if len(shape) == 1:
+        return shape[0]
+    n = 1
+    for d in shape[1:]:
+        n *= d
+    return n
+
+
+def _default_init(rs: np.random.RandomState, spec, gain: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+    """Variance-preserving uniform init: weights U(+-gain*sqrt(3/fan_in)) (unit gain, so a deep
+    random stack neither dies nor explodes), biases U(+-1/sqrt(fan_in of the matching weight))."""
+    out: OrderedDict[str, np.ndarray] = OrderedDict()
+    last_fan = 1
+    for name, shape in spec.items():
+        if name.endswith("bias"):
+            out[name] = _uniform(rs, shape, 1.0 / np.sqrt(last_fan))
+        else:
+            last_fan = _fan_in(shape)
+            out[name] = _uniform(rs, shape, gain * np.sqrt(3.0 / last_fan))
+    return out
+
+
+def firered_random_init(cfg: FireRedConfig = FireRedConfig(), seed: int = 0):
+    """Seeded random weights + a random CMVN folded into the first layer the way
+    DetectModel.from_pretrained does (FireRedVAD/Export_FireRedVAD.py:350-360), so that the
+    fold is non-trivial.  The head is rescaled so frame probabilities spread over (0,1) and the
+    post-processing state machines actually switch."""
+    rs = np.random.RandomState(seed)
+    w = _default_init(rs, firered_spec(cfg))
+    # CMVN stats typical of log-mel of int16-scaled audio
+    means = rs.uniform(13.0, 17.0, size=(cfg.idim,)).astype(np.float32)
+    inv_std = rs.uniform(0.35, 0.65, size=(cfg.idim,)).astype(np.float32)
+    W = w["dfsmn.fc1.0.weight"][:, :, 0].astype(np.float32)
+    b = w["dfsmn.fc1.0.bias"]
+    w["dfsmn.fc1.0.weight"] = (W * inv_std[None, :])[:, :, None].astype(np.float32)
+    w["dfsmn.fc1.0.bias"] = (b - W @ (means * inv_std)).astype(np.float32)
+    # head calibrated (offline, default architecture) so logits straddle the 0.4 threshold
+    w["out.weight"] = (w["out.weight"] * 0.3).astype(np.float32)
+    w["out.bias"] = (w["out.bias"] + 2.9).astype(np.float32)
+    return w
