@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- RTFx (audio-hours/sec) of the B200 VAD hot path, one JSON line on rank 0.
+
+Workload (BASELINE.json configs[3], the config the 1/2/4/8-GPU metric is quoted on):
+FireRedVAD DFSMN, synthetic 16 kHz int16 audio in 16000-sample chunks, 16 chunks per stream.
+A "step" is one pass of the hot path (frontend -> DFSMN -> on-device post-processing to
+segment frame pairs) over one batch of chunks per GPU.  Streams shard across ranks with no
+data-path collective (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks B] [--impl vadx|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`value`  : device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`    : same metric through the public API with pinned HOST buffers, H2D + D2H inside the
+           timed region.
+`roofline`: dominant stage, timed live with CUDA events on the launching stream (per-stage
+           timers inside libvadx), against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference graph (torch-CPU fp32,
+           batch-1 calls like the reference's ORT loop) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK = 16000
+CHUNKS_PER_STREAM = 16
+METRIC = "RTFx (audio-hours/sec)"
+UNIT = "audio-hours/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunks", type=int, default=8192, help="16000-sample chunks per GPU per step")
+    ap.add_argument("--impl", default="vadx", choices=["vadx", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------- CPU legs
+def cpu_reference_leg(seconds_budget: float, steps: int | None = None, warmup: int = 1):
+    """The oracle port of the reference graph on the host cores, batch-1 calls like the reference's
+    per-chunk ORT loop (FireRedVAD/Inference_FireRed_ONNX.py:567-572) + its Python post-processing."""
+    import numpy as np
+    import torch
+    import vadx  # noqa: F401  (weights / synth only; no CUDA involved here)
+    from vadx import synth, weights as W
+    from oracle.firered import FireRedOracle
+    from oracle import postproc as OP
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = W.FireRedConfig()
+    orc = FireRedOracle(W.firered_random_init(cfg, 0), cfg)
+    pool = synth.synth_chunks_fast(256, CHUNK, seed=1234)
+
+    STREAMS_PER_CALL = 4   # 64 chunks per forward call: measured here to be the CPU's best batch size
+
+    def one_call(i0):
+        idx = [(i0 * 64 + j) % 256 for j in range(STREAMS_PER_CALL * CHUNKS_PER_STREAM)]
+        p = orc.forward(pool[idx]).numpy()[:, 0, :].reshape(STREAMS_PER_CALL, -1)
+        out = []
+        for s in range(STREAMS_PER_CALL):
+            dec = OP.frame_decisions(p[s], 5, 0.4, 20, 2000, 20, 5, 0)
+            out.append(OP.segments_from_decisions(dec, 0.01, 0.025, CHUNKS_PER_STREAM * 1.0, True))
+        return out
+
+    calls_per_step = 4     # one CPU "step" = 16 streams = 256 chunks = 256 s of audio
+    for w in range(max(1, warmup)):
+        one_call(w)
+    # the reference's literal loop shape (batch-1 ORT calls) for the record
+    t0 = time.perf_counter()
+    for j in range(16):
+        orc.forward(pool[j][None])
+    batch1 = 16.0 / (time.perf_counter() - t0) / 3600.0
+    per_step = []
+    t_end = time.perf_counter() + seconds_budget
+    done = 0
+    while True:
+        t0 = time.perf_counter()
+        for c in range(calls_per_step):
+            one_call(done * calls_per_step + c)
+        per_step.append(time.perf_counter() - t0)
+        done += 1
+        if steps is not None and done >= steps:
+            break
+        if steps is None and time.perf_counter() >= t_end:
+            break
+    n_streams = done * calls_per_step * STREAMS_PER_CALL
+    audio_s = n_streams * CHUNKS_PER_STREAM * (CHUNK / 16000.0)
+    total = sum(per_step)
+    value = audio_s / total / 3600.0
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_streams} streams x {CHUNKS_PER_STREAM} chunks of {CHUNK} samples in 64-chunk calls "
+                      f"(batch-1 calls like the reference's loop: {batch1:.4f} {UNIT}), torch-CPU fp32 oracle port "
+                      f"on {cores} threads + Python post-processing, {total:.1f} s",
+            "batch1_value": batch1, "ms_per_step": 1e3 * total / done, "steps": done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_leg(args.cpu_seconds, steps=args.steps, warmup=args.warmup)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "FireRedVAD DFSMN, synthetic 16 kHz, 16000-sample chunks (BASELINE configs[3])",
+                       "chunks_per_stream": CHUNKS_PER_STREAM, "step": "16 streams (256 chunks) in 64-chunk calls"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_vadx(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import vadx
+    from vadx import firered_vad, lib, postprocess as PP, synth, weights as W
+
+    L = lib.load()
+    cfg = W.FireRedConfig()
+    sess = vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=CHUNK)
+    B = (args.chunks // CHUNKS_PER_STREAM) * CHUNKS_PER_STREAM
+    S = B // CHUNKS_PER_STREAM
+    T = sess.frames(CHUNK)
+    host = synth.synth_chunks_fast(B, CHUNK, seed=1234 + rank)
+    pinned = torch.from_numpy(host).pin_memory()
+    d_audio = pinned.to(dev)                                   # device-resident copy for `value`
+    lengths = [CHUNKS_PER_STREAM * CHUNK] * S
+    post = firered_vad.POST_DEFAULT
+    stream = torch.cuda.current_stream()
+
+    n_valid = torch.full((S,), min(firered_vad.valid_frame_count(lengths[0]), CHUNKS_PER_STREAM * T),
+                         dtype=torch.int32, device=dev)
+
+    def step_device():
+        return firered_vad.run_vad_streams(sess, d_audio.view(S, CHUNKS_PER_STREAM, CHUNK), lengths, post,
+                                           n_valid=n_valid)
+
+    h_cnt = torch.empty((S,), dtype=torch.int32).pin_memory()
+    max_seg = (CHUNKS_PER_STREAM * T) // 2 + 1
+    h_seg = torch.empty((S, max_seg, 2), dtype=torch.int32).pin_memory()
+    d_in = torch.empty_like(d_audio)
+
+    def step_e2e():
+        d_in.copy_(pinned, non_blocking=True)
+        probs, dec, cnt, seg, _ = firered_vad.run_vad_streams(sess, d_in.view(S, CHUNKS_PER_STREAM, CHUNK),
+                                                                    lengths, post, n_valid=n_valid)
+        h_cnt.copy_(cnt, non_blocking=True)
+        h_seg.copy_(seg, non_blocking=True)
+        return cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    W_ = max(3, args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident, with live per-stage timers
+    lib.profile_enable(True)
+    for _ in range(W_):
+        step_device()
+    torch.cuda.synchronize()
+    lib.profile_collect()                                     # drop warm-up records
+    launches0 = L.vadx_launch_count()
+    ms_total = timed(step_device, args.steps, 0)
+    launches = L.vadx_launch_count() - launches0
+    stages = lib.profile_collect()
+    lib.profile_enable(False)
+    # ---- end to end through the public API with host buffers
+    ms_e2e = timed(step_e2e, args.steps, W_)
+    if rank == 0:
+        sampler.stop()
+    segs_found = int(h_cnt.sum().item())
+
+    audio_s_per_step = world * B * (CHUNK / 16000.0)
+    value = audio_s_per_step * args.steps / (ms_total / 1e3) / 3600.0
+    e2e_value = audio_s_per_step * args.steps / (ms_e2e / 1e3) / 3600.0
+
+    if rank == 0:
+        pk = peaks()
+        rows = B * T
+        # algorithmic work per step per GPU
+        lin_macs_per_row = (cfg.idim * cfg.H + cfg.H * cfg.P + (cfg.R - 1) * (cfg.P * cfg.H + cfg.H * cfg.P)
+                            + cfg.P * cfg.H + (cfg.M - 1) * cfg.H * cfg.H)
+        flops = {"linear": 2.0 * rows * lin_macs_per_row, "stft": 2.0 * rows * cfg.n_fft * 2 * (cfg.n_fft // 2 + 1)}
+        dom = max(stages, key=lambda k: stages[k][0])
+        dom_ms, dom_calls = stages[dom]
+        stage_share = {k: round(v[0] / max(1e-9, sum(x[0] for x in stages.values())), 4) for k, v in stages.items()}
+        if dom in flops:
+            per_launch_flops = flops[dom] * args.steps / max(1, dom_calls)
+            ach = per_launch_flops / (dom_ms / max(1, dom_calls) * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_f32_kernel (" + dom + ")", "achieved": ach,
+                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                    "launches_timed": dom_calls, "avg_launch_ms": dom_ms / max(1, dom_calls),
+                    "note": "fp32 SIMT FFMA path; fp32-grade math on the tensor pipe (3xTF32) tops out at 1/6 of this peak"}
+        else:
+            bytes_per_row = {"memory": 3 * cfg.P * 4, "mel": ((cfg.n_fft // 2 + 2) + cfg.n_mels) * 4,
+                             "prep": 0, "head": cfg.H * 4 + 4, "postproc": 5}.get(dom, 0)
+            per_launch = bytes_per_row * rows * args.steps / max(1, dom_calls)
+            ach = per_launch / (dom_ms / max(1, dom_calls) * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "launches_timed": dom_calls, "avg_launch_ms": dom_ms / max(1, dom_calls)}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_reference_leg(args.cpu_seconds)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "FireRedVAD DFSMN (R8 H256 P128 N20+20), synthetic 16 kHz int16, 16000-sample "
+                                       "chunks, 16 chunks/stream (BASELINE configs[3])",
+                           "chunks_per_gpu_per_step": B, "streams_per_gpu_per_step": S, "frames_per_chunk": T,
+                           "audio_seconds_per_step": audio_s_per_step,
+                           "l2": "inputs (%.0f MB/step/GPU) and activations exceed the 126 MB L2" % (B * CHUNK * 2 / 1e6),
+                           "sharding": "streams split across ranks, no data-path collective"},
+                "rtfx": value * 3600.0,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * CHUNK * 2) * world,
+                        "d2h_bytes_per_step": int(h_cnt.numel() * 4 + h_seg.numel() * 4) * world,
+                        "ms_per_step": ms_e2e / args.steps, "segments_found_last_step": segs_found},
+                "gpu_launches": int(launches),
+                "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+                "stage_share": stage_share,
+                "cpu_baseline": cpu, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_vadx(args)
+
+
+if __name__ == "__main__":
+    main()

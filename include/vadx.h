@@ -1,0 +1,181 @@
+/* vadx.h -- C ABI of libvadx.so, the B200 (sm_100a) batched VAD engine.
+ *
+ * This is the drop-in boundary for the hot path of DakeQQ/Voice-Activity-Detection-VAD-ONNX:
+ * where the reference calls `onnxruntime.InferenceSession.run()` on one chunk of one stream
+ * (FSMN/Inference_FSMN_VAD_ONNX.py:177-187, FireRedVAD/Inference_FireRed_ONNX.py:567-572,
+ * NVIDIA_Frame_VAD_Multilingual_MarbleNet/Inference_NVIDIA_MarbleNet_VAD_ONNX.py:366-377,
+ * DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:229-230,
+ * Silero/modeling_modified/utils_vad.py:114-123) a caller binds `vadx_forward` on S streams at
+ * once, and where the reference runs its Python post-processing loops
+ * (FireRedVAD/Inference_FireRed_ONNX.py:102-305, FSMN/Inference_FSMN_VAD_ONNX.py:188-234) it
+ * binds `vadx_postprocess_*`.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every pointer named `d_*` is a DEVICE pointer owned by the caller; the library borrows it
+ *     for the duration of the (asynchronous) call and never allocates after vadx_create /
+ *     vadx_set_tensor.  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, a negative VADX_E* code otherwise;
+ *     vadx_last_error() returns the message of the calling thread's last failure.
+ *   - activations are TIME-MAJOR: [stream][frame][channel], channel contiguous, fp32.
+ *   - there is no CPU implementation behind this ABI: without a CUDA device every compute entry
+ *     point fails with VADX_ENODEVICE.
+ */
+#ifndef VADX_H_
+#define VADX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VADX_ABI_VERSION 1
+
+enum {
+  VADX_OK = 0,
+  VADX_EINVAL = -1,    /* bad argument / shape (ORT: InvalidArgument) */
+  VADX_ENODEVICE = -2, /* no CUDA device / driver */
+  VADX_ECUDA = -3,     /* a CUDA call or kernel launch failed */
+  VADX_EMISSING = -4,  /* a tensor the model needs was never set */
+  VADX_ENOMEM = -5     /* caller workspace too small */
+};
+
+enum { VADX_DT_I16 = 0, VADX_DT_F32 = 1, VADX_DT_I32 = 2 };
+enum { VADX_ACT_NONE = 0, VADX_ACT_RELU = 1, VADX_ACT_SIGMOID = 2 };
+enum { VADX_FLOOR_CLAMP = 0, VADX_FLOOR_ADD = 1 };
+/* pre-emphasis flavours: NONE; ZERO_HISTORY: y[0]=x[0]-c*0 (pad(1,0)+conv[-c,1],
+ * FireRedVAD/Export_FireRedVAD.py:440, NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:245-246);
+ * KEEP_FIRST: y[0]=x[0] (FSMN/Export_FSMN_VAD.py:78-79, DFSMN Export_DFSMN_VAD.py:338-341) */
+enum { VADX_PREEMPH_NONE = 0, VADX_PREEMPH_ZERO_HISTORY = 1, VADX_PREEMPH_KEEP_FIRST = 2 };
+
+int vadx_abi_version(void);
+const char* vadx_last_error(void);
+/* number of CUDA devices visible (0 when there is none); never fails */
+int vadx_device_count(void);
+/* kernels launched by this library since load (all threads); used by bench.py for gpu_launches */
+uint64_t vadx_launch_count(void);
+
+/* Optional per-stage device timing (used by bench.py for the live roofline numbers): while enabled,
+ * every per-kernel entry point brackets its launches with CUDA events on the caller's stream.
+ * vadx_profile_collect synchronises those events, ADDS the elapsed milliseconds and the number of
+ * calls of each stage into ms[] / calls[] (n_stages entries, indexed by VADX_STAGE_*) and clears
+ * the recorded events. */
+enum {
+  VADX_STAGE_PREP = 0,
+  VADX_STAGE_STFT = 1,
+  VADX_STAGE_MEL = 2,
+  VADX_STAGE_LINEAR = 3,
+  VADX_STAGE_MEMORY = 4,
+  VADX_STAGE_HEAD = 5,
+  VADX_STAGE_POSTPROC = 6,
+  VADX_STAGE_COUNT = 7
+};
+int vadx_profile_enable(int on);
+int vadx_profile_collect(double* ms, uint64_t* calls, int n_stages);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-kernel entry points (also what the unit parity tests and ncu captures call).
+ * ------------------------------------------------------------------------------------------ */
+
+/* a2 -- cast / scale / DC removal / pre-emphasis / zero centre-pad, one pass.
+ * d_audio [S][in_stride] (int16 or fp32) -> d_out [S][out_stride] fp32 with
+ * out[s][pad_left + n] = y[n], zeros in [0,pad_left) and [pad_left+L, out_stride).
+ * remove_dc: subtract the mean over the L samples of the stream's chunk first
+ * (FSMN/Export_FSMN_VAD.py:77). */
+int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_streams, int64_t n_samples,
+                    int64_t in_stride, float scale, int remove_dc, int preemph_mode, float preemph,
+                    int64_t pad_left, float* d_out, int64_t out_stride, void* stream);
+
+/* a1 -- framed real DFT as a GEMM + power: for frame t of stream s
+ *   re/im[f] = sum_k d_sig[s][t*hop + k] * basis[k][2f / 2f+1]   (k < n_taps)
+ *   d_power[(s*T + t)*ld_power + f] = re^2 + im^2
+ * d_basis is [n_taps][ld_basis] with re/im interleaved along the row (ld_basis >= 2*n_bins,
+ * multiple of 4).  Replaces STFT_Process.stft_B_forward (FSMN/STFT_Process.py:144-157,
+ * FireRedVAD/STFT_Process.py:264-278) followed by `real*real + imag*imag`. */
+int vadx_stft_power_f32(const float* d_sig, int64_t sig_stride, int64_t n_streams, int n_frames, int hop,
+                        int n_taps, const float* d_basis, int ld_basis, int n_bins, float* d_power,
+                        int64_t ld_power, void* stream);
+
+/* a3 -- triangular filterbank contraction + floor + ln.  The bank is passed in its sparse form:
+ * filter m covers bins [start[m], start[m]+len[m]) with weights d_w[m*max_len + j].
+ * out[row*ld_out + m] = ln(floor(sum_j w*power)). */
+int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t n_rows, int n_bins, int n_mels,
+                     const int32_t* d_start, const int32_t* d_len, const float* d_w, int max_len,
+                     int floor_mode, float floor_value, float* d_out, int64_t ld_out, void* stream);
+
+/* a8 -- dense layer on [rows][in]: Y = act(X * Wt + bias) (+ residual).
+ * d_wt is the TRANSPOSED weight [in][ldw] (ldw >= out, multiple of 4, zero padded). */
+int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias,
+                    const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
+                    int n_out, int act, void* stream);
+
+/* a5/a6/a7 -- FSMN / DFSMN memory block on time-major activations [S][T][C]:
+ *   out[t] = p[t] + sum_k wl[c][k] * p[t - (n_back-1-k)*stride_back]
+ *                 + sum_k wr[c][k] * p[t + (k+1)*stride_ahead]        (only when T > 1)
+ *                 (+ residual[t])
+ * frames before 0 come from d_cache_in [S][C][(n_back-1)*stride_back] (channel-first, the
+ * reference's cache layout: FSMN/Export_FSMN_VAD.py:116, FireRedVAD/Export_FireRedVAD.py:496-515)
+ * or are zero when it is NULL; frames >= T are zero.  d_cache_out (optional) receives the last
+ * (n_back-1)*stride_back frames of cat(cache, p).  d_wl is [C][n_back], d_wr is [C][n_ahead]. */
+int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* d_wl, int n_back, int stride_back,
+                         const float* d_wr, int n_ahead, int stride_ahead, const float* d_residual,
+                         int64_t ldr, float* d_out, int64_t ldo, int64_t n_streams, int n_frames,
+                         int n_channels, const float* d_cache_in, float* d_cache_out, void* stream);
+
+/* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
+ * that the float32 running sum rounds exactly like np.cumsum
+ * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid
+ * frames per stream (NULL = all n_frames).  Outputs: d_decisions [S][n_frames] int8 (optional),
+ * d_seg_count [S], d_segments [S][max_segments][2] int32 frame indices (start, end-exclusive). */
+typedef struct {
+  int32_t smooth_window;
+  float threshold;
+  int32_t min_speech_frame;
+  int32_t max_speech_frame;
+  int32_t min_silence_frame;
+  int32_t merge_silence_frame;
+  int32_t extend_speech_frame;
+} vadx_post_cfg;
+int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_t* d_n_frames,
+                            int64_t n_streams, int n_frames, const vadx_post_cfg* cfg, int8_t* d_decisions,
+                            int32_t* d_seg_count, int32_t* d_segments, int max_segments, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model-level API: the replacement for InferenceSession(...).run(...)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vadx_model vadx_model;
+
+/* kind: "firered" (more kinds are added as the path widens).  `hparams` is a flat int32 array,
+ * meaning per kind:
+ *   firered: {idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win_length, hop, n_mels}
+ *            (DetectModel args, FireRedVAD/Export_FireRedVAD.py:310-316, frontend :38-49) */
+int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out);
+void vadx_destroy(vadx_model* m);
+
+/* Upload a named constant (weights keep the reference state_dict names, e.g.
+ * "dfsmn.fc1.0.weight"; frontend tables are "frontend.basis", "frontend.mel_start",
+ * "frontend.mel_len", "frontend.mel_w").  h_data is a HOST pointer; the library copies it into
+ * device memory it owns (this is the only place it allocates). dims[] are the logical sizes. */
+int vadx_set_tensor(vadx_model* m, const char* name, const void* h_data, int dtype, const int64_t* dims,
+                    int n_dims);
+int vadx_set_scalar(vadx_model* m, const char* name, double value);
+
+/* bytes of caller-provided device workspace vadx_forward needs for (n_streams, n_samples) */
+int vadx_workspace_bytes(const vadx_model* m, int64_t n_streams, int64_t n_samples, size_t* out_bytes);
+/* frames per stream the model emits for n_samples */
+int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_frames);
+
+/* One pass of the model over S independent chunks.
+ *   firered: inputs[0] = d_audio int16 [S][n_samples]; outputs[0] = d_probs fp32 [S][odim][T]
+ *            (the reference's (1, odim, 98) with the leading 1 generalised to S,
+ *            FireRedVAD/Export_FireRedVAD.py:794-807). state is unused (NULL). */
+int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
+                 int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VADX_H_ */

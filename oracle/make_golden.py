@@ -155,7 +155,18 @@ def gen_postproc():
     print("postproc.npz written:", len(out), "arrays")
 
 
-GENERATORS = {"firered": gen_firered, "postproc": gen_postproc}
+# ------------------------------------------------------------------------------ audio fixture
+def gen_audio():
+    """vad_sample.wav (48 kHz stereo) decoded the way pydub does it (wave -> audioop.tomono ->
+    audioop.ratecv), frozen as 16 kHz mono int16 so GPU-box tests need no /root/reference."""
+    import vadx  # noqa: F401
+    from vadx import audio_io
+    a = audio_io.load_wav_int16(os.path.join(RL.REF_ROOT, "FireRedVAD", "vad_sample.wav"), 16000)
+    np.savez_compressed(os.path.join(GOLD, "vad_sample_16k.npz"), audio=a)
+    print("vad_sample_16k.npz:", a.shape, a.dtype, int(np.abs(a).max()))
+
+
+GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio}
 
 
 def main(argv):

@@ -1,0 +1,138 @@
+"""FireRedVAD end to end on the GPU through the C ABI: frame probabilities against the golden
+outputs of the real reference modules and against the oracle; timestamps bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vadx
+from vadx import firered_vad, postprocess as PP, synth, weights as W
+from oracle import postproc as OP
+from oracle.firered import FireRedOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3  # BASELINE.json north_star: frame-prob max abs err <= 1e-3 in fp32
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "firered.npz"))
+
+
+@pytest.fixture(scope="module")
+def default_session(cuda):
+    cfg = W.FireRedConfig()
+    return vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=16000)
+
+
+def test_reference_recipe_through_run(gold, default_session):
+    np.random.seed(1234)
+    a = np.random.randint(-8000, 8000, size=(1, 1, 16000)).astype(np.int16)
+    name_in = default_session.get_inputs()[0].name
+    name_out = default_session.get_outputs()[0].name
+    p = default_session.run([name_out], {name_in: a})[0]
+    assert p.shape == (1, 1, 98) and p.dtype == np.float32
+    err = np.abs(p - gold["recipe_probs"]).max()
+    print("recipe max abs err", err)
+    assert err <= TOL
+
+
+def test_synthetic_chunks_batched(gold, default_session):
+    chunks = synth.synth_streams(6, 16000, seed=1234)
+    p = default_session.run(None, {"audio": chunks[:, None, :]})[0]
+    err = np.abs(p - gold["synth_probs"]).max()
+    print("synth max abs err", err)
+    assert err <= TOL
+
+
+def test_run_rejects_bad_inputs(default_session):
+    with pytest.raises(ValueError):
+        default_session.run(["probs"], {"audio": np.zeros((1, 1, 16000), np.float32)})
+    with pytest.raises(ValueError):
+        default_session.run(["probs"], {"audio": np.zeros((1, 1, 8000), np.int16)})
+    with pytest.raises(ValueError):
+        default_session.run(["nope"], {"audio": np.zeros((1, 1, 16000), np.int16)})
+    with pytest.raises(ValueError):
+        default_session.run(["probs"], {"wave": np.zeros((1, 1, 16000), np.int16)})
+
+
+@pytest.mark.parametrize("L", [5000, 400])
+def test_dynamic_axis(cuda, gold, L):
+    cfg = W.FireRedConfig()
+    sess = vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=None)
+    a = synth.synth_streams(1, L, seed=77)
+    p = sess.run(None, {"audio": a[:, None, :]})[0]
+    assert p.shape == gold[f"len{L}_probs"].shape
+    assert np.abs(p - gold[f"len{L}_probs"]).max() <= TOL
+
+
+def test_aed_head_with_strides(cuda, gold):
+    cfg = W.FireRedConfig(R=3, H=96, P=64, N1=5, S1=2, N2=3, S2=2, odim=3)
+    sess = vadx.FireRedSession(W.firered_random_init(cfg, 3), cfg)
+    chunks = synth.synth_streams(6, 16000, seed=1234)
+    p = sess.run(None, {"audio": chunks[1:2, None, :]})[0]
+    assert p.shape == (1, 3, 98)
+    assert np.abs(p - gold["aed_probs"]).max() <= TOL
+
+
+def test_large_batch_against_oracle(cuda, default_session):
+    """300 chunks at once (ragged wrt. the 128-row tiles) vs the oracle."""
+    cfg = W.FireRedConfig()
+    chunks = synth.synth_chunks_fast(300, 16000, seed=5)
+    got = default_session.run_batch(torch.from_numpy(chunks).to(cuda)).cpu().numpy()
+    ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks).numpy()
+    err = np.abs(got - ref).max()
+    print("batch-300 max abs err", err)
+    assert err <= TOL
+
+
+def _oracle_timestamps(probs, n_valid, wav_dur, post):
+    dec = OP.frame_decisions(probs[:n_valid], post.smooth_window_size, post.prob_threshold, post.min_speech_frame,
+                             post.max_speech_frame, post.min_silence_frame, post.merge_silence_frame,
+                             post.extend_speech_frame)
+    return dec, OP.segments_from_decisions(dec, 0.01, 0.025, wav_dur, True)
+
+
+def test_vad_sample_timestamps_bit_exact(cuda, golden_dir, default_session, tmp_path):
+    """vad_sample.wav end to end (loader output frozen as a fixture): timestamps must equal the
+    oracle's wherever no smoothed probability lies within TOL of the threshold."""
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    f1, f2 = str(tmp_path / "timestamps_second.txt"), str(tmp_path / "timestamps_indices.txt")
+    r = firered_vad.run_vad(audio, default_session, rng=np.random.RandomState(0), save_timestamps_second=f1,
+                            save_timestamps_indices=f2)
+    cfg = W.FireRedConfig()
+    from vadx import audio_io
+    chunks, n = audio_io.align_non_overlapping(audio, 16000, np.random.RandomState(0))
+    ref_p = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks).numpy().reshape(-1)
+    n_valid = firered_vad.valid_frame_count(n)
+    assert n_valid == 557 and r.probs.shape == (557,)
+    assert np.abs(r.probs - ref_p[:n_valid]).max() <= TOL
+    dec, ts = _oracle_timestamps(ref_p, n_valid, n / 16000, firered_vad.POST_DEFAULT)
+    sm = OP.smooth_probs(ref_p[:n_valid].astype(np.float32), 5)
+    if np.abs(sm - np.float32(0.4)).min() > TOL:
+        assert np.array_equal(r.decisions, dec)
+        assert r.timestamps == ts
+        sec, idx = PP.timestamp_lines(ts)
+        assert open(f1).read() == "".join(sec) and open(f2).read() == "".join(idx)
+    # device post-processing on the device probabilities must in any case equal the oracle run
+    # on those same probabilities (bit-exact state machines)
+    dec2, ts2 = _oracle_timestamps(r.probs, n_valid, n / 16000, firered_vad.POST_DEFAULT)
+    assert np.array_equal(r.decisions, dec2) and r.timestamps == ts2
+
+
+def test_many_streams_timestamps(cuda, default_session):
+    S, n_chunks = 24, 5
+    audio = synth.synth_streams(S, n_chunks * 16000, seed=21)
+    lengths = [n_chunks * 16000 - 137 * s for s in range(S)]
+    d = torch.from_numpy(audio.reshape(S, n_chunks, 16000)).to(cuda)
+    probs, dec, cnt, seg, n_valid = firered_vad.run_vad_streams(default_session, d, lengths)
+    probs, dec, cnt, seg, n_valid = [t.cpu().numpy() for t in (probs, dec, cnt, seg, n_valid)]
+    n_speech = 0
+    for s in range(S):
+        ref_dec, ref_ts = _oracle_timestamps(probs[s], int(n_valid[s]), lengths[s] / 16000, firered_vad.POST_DEFAULT)
+        assert np.array_equal(dec[s, :n_valid[s]], ref_dec)
+        ts = PP.segments_to_seconds(seg[s, :cnt[s]], int(n_valid[s]), firered_vad.POST_DEFAULT, lengths[s] / 16000)
+        assert ts == ref_ts
+        n_speech += len(ts)
+    assert n_speech > 0

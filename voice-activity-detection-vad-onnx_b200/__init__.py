@@ -1,11 +1,12 @@
 """vadx -- B200-native batched voice-activity-detection engine (hot path only).
 
-Raw 16 kHz audio in -> per-frame speech probability -> timestamps, for the five
-model families of DakeQQ/Voice-Activity-Detection-VAD-ONNX, computed by
-hand-written sm_100a CUDA kernels behind the C ABI declared in include/vadx.h
-(csrc/libvadx.so).  There is no CPU fallback: every compute entry point raises
-if the CUDA library is missing.
+Raw 16 kHz audio in -> per-frame speech probability -> timestamps, for the model families of
+DakeQQ/Voice-Activity-Detection-VAD-ONNX, computed by hand-written sm_100a CUDA kernels behind
+the C ABI declared in include/vadx.h (libvadx.so).  There is no CPU fallback: every compute
+entry point raises if the CUDA library or a CUDA device is missing.
 """
 __version__ = "0.1.0"
 
-from . import constants  # noqa: F401
+from . import constants, lib, tables, weights, synth  # noqa: F401
+from .session import InferenceSession, FireRedSession  # noqa: F401
+from .postprocess import FramePostConfig, postprocess_frames  # noqa: F401

@@ -1,0 +1,247 @@
+// elementwise.cu -- the HBM-bound stages: audio preparation (a2), filterbank + log (a3) and the
+// FSMN / DFSMN memory block (a5-a7).
+#include "common.cuh"
+
+namespace vadx {
+
+// ------------------------------------------------------------------------------------------ a2
+template <typename T>
+__device__ __forceinline__ float load_sample(const T* p, int64_t i) {
+  return (float)p[i];
+}
+
+// grid (chunks, S); when remove_dc the launch uses one chunk per stream and the block first
+// reduces the stream's mean.
+template <typename T>
+__global__ void __launch_bounds__(256) prep_audio_kernel(const T* __restrict__ audio, int64_t n_samples,
+                                                         int64_t in_stride, float scale, int remove_dc,
+                                                         int preemph_mode, float c, int64_t pad_left,
+                                                         float* __restrict__ out, int64_t out_stride) {
+  const int64_t s = blockIdx.y;
+  const T* x = audio + s * in_stride;
+  float* y = out + s * out_stride;
+  __shared__ double red[256];
+  float mean = 0.f;
+  if (remove_dc) {
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n_samples; i += blockDim.x) acc += (double)(load_sample(x, i) * scale);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+      __syncthreads();
+    }
+    mean = (float)(red[0] / (double)n_samples);
+  }
+  const int64_t per_block = ceil_div_dev(out_stride, (int64_t)gridDim.x);
+  const int64_t lo = (int64_t)blockIdx.x * per_block;
+  const int64_t hi = min_i64(lo + per_block, out_stride);
+  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const int64_t n = j - pad_left;
+    float v = 0.f;
+    if (n >= 0 && n < n_samples) {
+      float cur = load_sample(x, n) * scale - mean;
+      if (preemph_mode == VADX_PREEMPH_NONE) {
+        v = cur;
+      } else if (n == 0) {
+        v = cur;  // ZERO_HISTORY: x[-1] = 0; KEEP_FIRST: y[0] = x[0]
+      } else {
+        float prev = load_sample(x, n - 1) * scale - mean;
+        v = cur - c * prev;
+      }
+    }
+    y[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a3
+constexpr int kMelRows = 8;
+__global__ void __launch_bounds__(128) mel_log_kernel(const float* __restrict__ power, int64_t ld_power,
+                                                      int64_t n_rows, int n_bins, int n_mels,
+                                                      const int32_t* __restrict__ start,
+                                                      const int32_t* __restrict__ len, const float* __restrict__ w,
+                                                      int max_len, int floor_mode, float floor_value,
+                                                      float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float tile[];  // [kMelRows][n_bins]
+  const int64_t r0 = (int64_t)blockIdx.x * kMelRows;
+  const int rows = (int)min_i64((int64_t)kMelRows, n_rows - r0);
+  for (int i = threadIdx.x; i < rows * n_bins; i += blockDim.x) {
+    int r = i / n_bins, f = i - r * n_bins;
+    tile[r * n_bins + f] = power[(r0 + r) * ld_power + f];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
+    int r = i / n_mels, m = i - r * n_mels;
+    const float* p = tile + r * n_bins + start[m];
+    const float* wm = w + (int64_t)m * max_len;
+    const int L = len[m];
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc = fmaf(wm[j], p[j], acc);
+    acc = (floor_mode == VADX_FLOOR_CLAMP) ? fmaxf(acc, floor_value) : acc + floor_value;
+    out[(r0 + r) * ld_out + m] = logf(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a5-a7
+// One CTA = one stream x a tile of kMemT output frames x all channels.  The tile plus its halo and
+// the transposed taps are staged in shared memory; each thread then produces outputs for one
+// channel (consecutive threads = consecutive channels, so both the global and the shared accesses
+// are unit-stride across a warp).
+constexpr int kMemT = 64;
+__global__ void __launch_bounds__(256) fsmn_memory_kernel(const float* __restrict__ p, int64_t ldp,
+                                                          const float* __restrict__ wl, int n_back, int s_back,
+                                                          const float* __restrict__ wr, int n_ahead, int s_ahead,
+                                                          const float* __restrict__ res, int64_t ldr,
+                                                          float* __restrict__ out, int64_t ldo, int n_frames,
+                                                          int C, const float* __restrict__ cache_in) {
+  extern __shared__ float sm[];
+  const int halo_l = (n_back - 1) * s_back;
+  const int halo_r = (n_frames > 1) ? n_ahead * s_ahead : 0;
+  const int use_ahead = (n_frames > 1) ? n_ahead : 0;
+  const int rows_in = kMemT + halo_l + halo_r;
+  float* tile = sm;                          // [rows_in][C]
+  float* wls = tile + (size_t)rows_in * C;   // [n_back][C]
+  float* wrs = wls + (size_t)n_back * C;     // [use_ahead][C]
+  const int64_t s = blockIdx.y;
+  const int t0 = blockIdx.x * kMemT;
+  const float* ps = p + s * (int64_t)n_frames * ldp;
+
+  for (int i = threadIdx.x; i < rows_in * C; i += blockDim.x) {
+    int r = i / C, c = i - r * C;
+    int t = t0 - halo_l + r;
+    float v = 0.f;
+    if (t >= 0 && t < n_frames) v = ps[(int64_t)t * ldp + c];
+    else if (t < 0 && cache_in) v = cache_in[(s * C + c) * (int64_t)halo_l + (halo_l + t)];
+    tile[i] = v;
+  }
+  for (int i = threadIdx.x; i < n_back * C; i += blockDim.x) {
+    int k = i / C, c = i - k * C;
+    wls[i] = wl[c * n_back + k];
+  }
+  for (int i = threadIdx.x; i < use_ahead * C; i += blockDim.x) {
+    int k = i / C, c = i - k * C;
+    wrs[i] = wr[c * n_ahead + k];
+  }
+  __syncthreads();
+
+  const int t_end = min(kMemT, n_frames - t0);
+  for (int i = threadIdx.x; i < t_end * C; i += blockDim.x) {
+    int tt = i / C, c = i - tt * C;
+    const float* col = tile + (size_t)(tt + halo_l) * C + c;  // p[t]
+    float acc = col[0];
+    // look-back: sum_k wl[k] * p[t - (n_back-1-k)*s_back]
+    const float* src = col - (size_t)halo_l * C;
+    for (int k = 0; k < n_back; ++k) acc = fmaf(wls[k * C + c], src[(size_t)k * s_back * C], acc);
+    // look-ahead: sum_k wr[k] * p[t + (k+1)*s_ahead]
+    for (int k = 0; k < use_ahead; ++k) acc = fmaf(wrs[k * C + c], col[(size_t)(k + 1) * s_ahead * C], acc);
+    const int64_t row = s * (int64_t)n_frames + t0 + tt;
+    if (res) acc += res[row * ldr + c];
+    out[row * ldo + c] = acc;
+  }
+}
+
+// cache_out[s][c][j] = cat(cache_in, p)[T + j] for j in [0, halo): the streaming state hand-over
+__global__ void __launch_bounds__(256) fsmn_cache_out_kernel(const float* __restrict__ p, int64_t ldp,
+                                                             const float* __restrict__ cache_in,
+                                                             float* __restrict__ cache_out, int64_t n_streams,
+                                                             int n_frames, int C, int halo) {
+  const int64_t total = n_streams * C * halo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(i % halo);
+    int64_t sc = i / halo;
+    int c = (int)(sc % C);
+    int64_t s = sc / C;
+    int t = n_frames - halo + j;
+    float v;
+    if (t >= 0) v = p[(s * n_frames + t) * ldp + c];
+    else v = cache_in ? cache_in[sc * halo + (halo + t)] : 0.f;
+    cache_out[i] = v;
+  }
+}
+
+}  // namespace vadx
+
+using namespace vadx;
+
+extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_streams, int64_t n_samples,
+                               int64_t in_stride, float scale, int remove_dc, int preemph_mode, float preemph,
+                               int64_t pad_left, float* d_out, int64_t out_stride, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_audio && d_out, "vadx_prep_audio: null pointer");
+  VADX_REQUIRE(in_dtype == VADX_DT_I16 || in_dtype == VADX_DT_F32, "vadx_prep_audio: dtype %d", in_dtype);
+  VADX_REQUIRE(n_streams >= 0 && n_samples > 0 && in_stride >= n_samples && pad_left >= 0 &&
+                   out_stride >= pad_left + n_samples,
+               "vadx_prep_audio: bad shape S=%lld L=%lld in_stride=%lld pad_left=%lld out_stride=%lld",
+               (long long)n_streams, (long long)n_samples, (long long)in_stride, (long long)pad_left,
+               (long long)out_stride);
+  VADX_REQUIRE(preemph_mode >= 0 && preemph_mode <= 2, "vadx_prep_audio: preemph_mode %d", preemph_mode);
+  VADX_REQUIRE(n_streams <= 65535, "vadx_prep_audio: at most 65535 streams per call (got %lld)", (long long)n_streams);
+  if (n_streams == 0) return VADX_OK;
+  int chunks = remove_dc ? 1 : (int)std::min<int64_t>(ceil_div(out_stride, 256 * 16), 1024);
+  dim3 grid((unsigned)chunks, (unsigned)n_streams);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == VADX_DT_I16)
+    prep_audio_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)d_audio, n_samples, in_stride, scale, remove_dc,
+                                                     preemph_mode, preemph, pad_left, d_out, out_stride);
+  else
+    prep_audio_kernel<float><<<grid, 256, 0, st>>>((const float*)d_audio, n_samples, in_stride, scale, remove_dc,
+                                                   preemph_mode, preemph, pad_left, d_out, out_stride);
+  return after_launch("vadx_prep_audio");
+}
+
+extern "C" int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t n_rows, int n_bins, int n_mels,
+                                const int32_t* d_start, const int32_t* d_len, const float* d_w, int max_len,
+                                int floor_mode, float floor_value, float* d_out, int64_t ld_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  VADX_REQUIRE(d_power && d_start && d_len && d_w && d_out, "vadx_mel_log_f32: null pointer");
+  VADX_REQUIRE(n_rows >= 0 && n_bins > 0 && n_mels > 0 && max_len > 0 && ld_power >= n_bins && ld_out >= n_mels,
+               "vadx_mel_log_f32: bad shape");
+  VADX_REQUIRE(floor_mode == VADX_FLOOR_CLAMP || floor_mode == VADX_FLOOR_ADD, "vadx_mel_log_f32: floor_mode");
+  if (n_rows == 0) return VADX_OK;
+  size_t smem = (size_t)kMelRows * n_bins * sizeof(float);
+  VADX_REQUIRE(smem <= 48 * 1024, "vadx_mel_log_f32: n_bins=%d too large", n_bins);
+  int64_t blocks = ceil_div(n_rows, kMelRows);
+  VADX_REQUIRE(blocks <= 0x7fffffffLL, "vadx_mel_log_f32: too many rows");
+  mel_log_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(d_power, ld_power, n_rows, n_bins, n_mels,
+                                                                        d_start, d_len, d_w, max_len, floor_mode,
+                                                                        floor_value, d_out, ld_out);
+  return after_launch("vadx_mel_log_f32");
+}
+
+extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* d_wl, int n_back, int stride_back,
+                                    const float* d_wr, int n_ahead, int stride_ahead, const float* d_residual,
+                                    int64_t ldr, float* d_out, int64_t ldo, int64_t n_streams, int n_frames,
+                                    int n_channels, const float* d_cache_in, float* d_cache_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  VADX_REQUIRE(d_p && d_wl && d_out, "vadx_fsmn_memory_f32: null pointer");
+  VADX_REQUIRE(n_back >= 1 && stride_back >= 1 && n_ahead >= 0 && (n_ahead == 0 || (d_wr && stride_ahead >= 1)),
+               "vadx_fsmn_memory_f32: bad taps back=%d/%d ahead=%d/%d", n_back, stride_back, n_ahead, stride_ahead);
+  VADX_REQUIRE(n_streams >= 0 && n_frames >= 1 && n_channels >= 1 && ldp >= n_channels && ldo >= n_channels,
+               "vadx_fsmn_memory_f32: bad shape");
+  VADX_REQUIRE(n_streams <= 65535, "vadx_fsmn_memory_f32: at most 65535 streams per call");
+  VADX_REQUIRE(d_p != d_out, "vadx_fsmn_memory_f32: in-place operation is not supported");
+  if (n_streams == 0) return VADX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int halo_l = (n_back - 1) * stride_back;
+  const int halo_r = n_frames > 1 ? n_ahead * stride_ahead : 0;
+  size_t smem = ((size_t)(kMemT + halo_l + halo_r) + n_back + n_ahead) * n_channels * sizeof(float);
+  VADX_REQUIRE(smem <= 200 * 1024, "vadx_fsmn_memory_f32: tile of %zu bytes exceeds shared memory", smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(fsmn_memory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_kernel)");
+    configured = 200 * 1024;
+  }
+  dim3 grid((unsigned)ceil_div(n_frames, kMemT), (unsigned)n_streams);
+  fsmn_memory_kernel<<<grid, 256, smem, st>>>(d_p, ldp, d_wl, n_back, stride_back, d_wr, n_ahead, stride_ahead,
+                                              d_residual, ldr, d_out, ldo, n_frames, n_channels, d_cache_in);
+  VADX_TRY(after_launch("vadx_fsmn_memory_f32"));
+  if (d_cache_out && halo_l > 0) {
+    int64_t total = n_streams * n_channels * halo_l;
+    int64_t blocks = std::min<int64_t>(ceil_div(total, 256), 148 * 8);
+    fsmn_cache_out_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_p, ldp, d_cache_in, d_cache_out, n_streams, n_frames,
+                                                            n_channels, halo_l);
+    VADX_TRY(after_launch("fsmn_cache_out"));
+  }
+  return VADX_OK;
+}

@@ -1,0 +1,342 @@
+// model.cu -- the native runtime behind vadx_create / vadx_set_tensor / vadx_forward: owns the
+// constants of one model, lays the caller's workspace out, and enqueues the kernel sequence of a
+// whole forward pass on the caller's stream (no host synchronisation, no allocation).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vadx {
+int linear_narrow(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias, float* d_y,
+                  int64_t n_rows, int n_in, int n_out, int act, int rows_per_group, int64_t group_stride,
+                  int64_t out_stride, cudaStream_t st);
+
+struct HostTensor {
+  std::vector<char> bytes;
+  std::vector<int64_t> dims;
+  int dtype = VADX_DT_F32;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : dims) n *= d;
+    return n;
+  }
+  const float* f32() const { return reinterpret_cast<const float*>(bytes.data()); }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Workspace {  // bump allocator over the caller's buffer
+  char* base;
+  size_t cap, off = 0;
+  bool dry;  // only measure
+  Workspace(void* b, size_t c, bool d) : base((char*)b), cap(c), dry(d) {}
+  template <typename T>
+  T* take(int64_t n) {
+    size_t bytes = (size_t)round_up((int64_t)(n * sizeof(T)), 256);
+    char* p = dry ? nullptr : base + off;
+    off += bytes;
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+}  // namespace vadx
+
+using namespace vadx;
+
+struct vadx_model {
+  std::string kind;
+  std::vector<int32_t> hp;
+  std::map<std::string, HostTensor> host;
+  std::map<std::string, double> scalars;
+  std::map<std::string, DevBuf> dev;  // derived, device-resident constants
+  bool finalized = false;
+
+  ~vadx_model() { release(); }
+  void release() {
+    for (auto& kv : dev)
+      if (kv.second.p) cudaFree(kv.second.p);
+    dev.clear();
+    finalized = false;
+  }
+  double scalar(const char* name, double dflt) const {
+    auto it = scalars.find(name);
+    return it == scalars.end() ? dflt : it->second;
+  }
+  const HostTensor* find(const std::string& n) const {
+    auto it = host.find(n);
+    return it == host.end() ? nullptr : &it->second;
+  }
+  int upload(const std::string& key, const void* src, size_t bytes) {
+    DevBuf b;
+    b.bytes = bytes;
+    cudaError_t e = cudaMalloc(&b.p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(constant)");
+    e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(b.p);
+      return cuda_fail(e, "cudaMemcpy(constant)");
+    }
+    auto it = dev.find(key);
+    if (it != dev.end() && it->second.p) cudaFree(it->second.p);
+    dev[key] = b;
+    return VADX_OK;
+  }
+  // [out][in](,1) host weight -> device [in][ldw] (ldw = out rounded up to 4, zero padded)
+  int upload_linear(const std::string& name, int n_out, int n_in) {
+    const HostTensor* t = find(name);
+    if (!t) {
+      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
+      return VADX_EMISSING;
+    }
+    if (t->dtype != VADX_DT_F32 || t->numel() != (int64_t)n_out * n_in) {
+      set_error("tensor '%s': expected %d x %d fp32, got %lld elements", name.c_str(), n_out, n_in,
+                (long long)t->numel());
+      return VADX_EINVAL;
+    }
+    int ldw = (int)round_up(n_out, 4);
+    std::vector<float> wt((size_t)n_in * ldw, 0.f);
+    const float* w = t->f32();
+    for (int o = 0; o < n_out; ++o)
+      for (int i = 0; i < n_in; ++i) wt[(size_t)i * ldw + o] = w[(size_t)o * n_in + i];
+    return upload(name + "#T", wt.data(), wt.size() * sizeof(float));
+  }
+  int upload_raw(const std::string& name, int64_t expect_numel, int dtype) {
+    const HostTensor* t = find(name);
+    if (!t) {
+      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
+      return VADX_EMISSING;
+    }
+    if (t->dtype != dtype || (expect_numel >= 0 && t->numel() != expect_numel)) {
+      set_error("tensor '%s': expected %lld elements of dtype %d, got %lld of dtype %d", name.c_str(),
+                (long long)expect_numel, dtype, (long long)t->numel(), t->dtype);
+      return VADX_EINVAL;
+    }
+    return upload(name, t->bytes.data(), t->bytes.size());
+  }
+  template <typename T>
+  const T* d(const std::string& key) const {
+    auto it = dev.find(key);
+    return it == dev.end() ? nullptr : reinterpret_cast<const T*>(it->second.p);
+  }
+  bool has(const std::string& n) const { return host.count(n) != 0; }
+};
+
+// ------------------------------------------------------------------------------------------ FireRed
+namespace {
+
+struct FireRedHP {
+  int idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win, hop, n_mels;
+  int n_taps() const { return win < n_fft ? win : n_fft; }
+  int n_bins() const { return n_fft / 2 + 1; }
+  int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
+  int ld_power() const { return (int)round_up(n_bins(), 2); }
+  int frames(int64_t L) const { return L < n_taps() ? 0 : (int)(1 + (L - n_taps()) / hop); }
+};
+
+int firered_hp(const vadx_model* m, FireRedHP* h) {
+  VADX_REQUIRE(m->hp.size() == 14, "firered: expected 14 hyper-parameters, got %zu", m->hp.size());
+  const int32_t* v = m->hp.data();
+  *h = FireRedHP{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13]};
+  VADX_REQUIRE(h->idim == h->n_mels, "firered: idim (%d) must equal n_mels (%d)", h->idim, h->n_mels);
+  VADX_REQUIRE(h->R >= 1 && h->M >= 1 && h->H >= 1 && h->P >= 1 && h->N1 >= 1 && h->S1 >= 1 && h->N2 >= 0 &&
+                   h->odim >= 1 && h->odim <= 8 && h->hop >= 1 && h->n_fft >= 2,
+               "firered: hyper-parameter out of range");
+  return VADX_OK;
+}
+
+int firered_finalize(vadx_model* m) {
+  FireRedHP h;
+  VADX_TRY(firered_hp(m, &h));
+  VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
+  VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_linear("dfsmn.fc1.0.weight", h.H, h.idim));
+  VADX_TRY(m->upload_raw("dfsmn.fc1.0.bias", h.H, VADX_DT_F32));
+  VADX_TRY(m->upload_linear("dfsmn.fc2.0.weight", h.P, h.H));
+  VADX_TRY(m->upload_raw("dfsmn.fc2.0.bias", h.P, VADX_DT_F32));
+  auto memory = [&](const std::string& pre) -> int {
+    VADX_TRY(m->upload_raw(pre + "lookback_filter.weight", (int64_t)h.P * h.N1, VADX_DT_F32));
+    if (h.N2 > 0) VADX_TRY(m->upload_raw(pre + "lookahead_filter.weight", (int64_t)h.P * h.N2, VADX_DT_F32));
+    return VADX_OK;
+  };
+  VADX_TRY(memory("dfsmn.fsmn1."));
+  for (int i = 0; i < h.R - 1; ++i) {
+    std::string pre = "dfsmn.fsmns." + std::to_string(i) + ".";
+    VADX_TRY(m->upload_linear(pre + "fc1.0.weight", h.H, h.P));
+    VADX_TRY(m->upload_raw(pre + "fc1.0.bias", h.H, VADX_DT_F32));
+    VADX_TRY(m->upload_linear(pre + "fc2.weight", h.P, h.H));
+    VADX_TRY(memory(pre + "fsmn."));
+  }
+  VADX_TRY(m->upload_linear("dfsmn.dnns.0.weight", h.H, h.P));
+  VADX_TRY(m->upload_raw("dfsmn.dnns.0.bias", h.H, VADX_DT_F32));
+  for (int j = 1; j < h.M; ++j) {
+    std::string n = "dfsmn.dnns." + std::to_string(2 * j);
+    VADX_TRY(m->upload_linear(n + ".weight", h.H, h.H));
+    VADX_TRY(m->upload_raw(n + ".bias", h.H, VADX_DT_F32));
+  }
+  VADX_TRY(m->upload_linear("out.weight", h.odim, h.H));
+  VADX_TRY(m->upload_raw("out.bias", h.odim, VADX_DT_F32));
+  return VADX_OK;
+}
+
+// lays out (dry = true) or runs the forward pass
+int firered_run(vadx_model* m, bool dry, const void* d_audio, float* d_probs, float* const* d_state_in,
+                int64_t S, int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+  FireRedHP h;
+  VADX_TRY(firered_hp(m, &h));
+  const int T = h.frames(L);
+  VADX_REQUIRE(T >= 1, "firered: %lld samples are shorter than one %d-sample frame", (long long)L, h.n_taps());
+  const int64_t rows = S * T;
+  const int64_t Lp = round_up(L, 4);
+  Workspace ws(ws_ptr, ws_bytes, dry);
+  float* sig = ws.take<float>(S * Lp);
+  float* power = ws.take<float>(rows * h.ld_power());
+  float* feat = ws.take<float>(rows * h.n_mels);
+  float* bufH = ws.take<float>(rows * h.H);
+  float* bufH2 = h.M > 1 ? ws.take<float>(rows * h.H) : nullptr;
+  float* bufP = ws.take<float>(rows * h.P);
+  float* memA = ws.take<float>(rows * h.P);
+  float* memB = ws.take<float>(rows * h.P);
+  if (need) *need = ws.off;
+  if (dry) return VADX_OK;
+  if (ws.off > ws_bytes) {
+    set_error("firered: workspace of %zu bytes is smaller than the %zu needed", ws_bytes, ws.off);
+    return VADX_ENOMEM;
+  }
+  (void)d_state_in;
+  const float preemph = (float)m->scalar("frontend.preemph", 0.97);
+  const float floor_v = (float)m->scalar("frontend.log_floor", 1e-7);
+  const HostTensor* melw = m->find("frontend.mel_w");
+  const int mel_max = (int)(melw->numel() / h.n_mels);
+
+  // process at most 65535 streams per launch group (grid.y limit of the per-stream kernels)
+  VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0,
+                           preemph, 0, sig, Lp, st));
+  VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                               h.n_bins(), power, h.ld_power(), st));
+  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
+                            m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
+                            VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
+  auto lin = [&](const float* x, int n_in, const std::string& w, const char* b, const float* res, float* y, int n_out,
+                 int act) -> int {
+    return vadx_linear_f32(x, n_in, m->d<float>(w + "#T"), (int)round_up(n_out, 4), b ? m->d<float>(b) : nullptr, res,
+                           n_out, y, n_out, rows, n_in, n_out, act, st);
+  };
+  auto memory = [&](const std::string& pre, const float* p, const float* res, float* out) -> int {
+    return vadx_fsmn_memory_f32(p, h.P, m->d<float>(pre + "lookback_filter.weight"), h.N1, h.S1,
+                                h.N2 > 0 ? m->d<float>(pre + "lookahead_filter.weight") : nullptr, h.N2,
+                                h.N2 > 0 ? h.S2 : 1, res, h.P, out, h.P, S, T, h.P, nullptr, nullptr, st);
+  };
+  VADX_TRY(lin(feat, h.idim, "dfsmn.fc1.0.weight", "dfsmn.fc1.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
+  VADX_TRY(lin(bufH, h.H, "dfsmn.fc2.0.weight", "dfsmn.fc2.0.bias", nullptr, bufP, h.P, VADX_ACT_RELU));
+  VADX_TRY(memory("dfsmn.fsmn1.", bufP, nullptr, memA));
+  for (int i = 0; i < h.R - 1; ++i) {
+    std::string pre = "dfsmn.fsmns." + std::to_string(i) + ".";
+    std::string b1 = pre + "fc1.0.bias";
+    VADX_TRY(lin(memA, h.P, pre + "fc1.0.weight", b1.c_str(), nullptr, bufH, h.H, VADX_ACT_RELU));
+    VADX_TRY(lin(bufH, h.H, pre + "fc2.weight", nullptr, nullptr, bufP, h.P, VADX_ACT_NONE));
+    VADX_TRY(memory(pre + "fsmn.", bufP, memA, memB));
+    std::swap(memA, memB);
+  }
+  VADX_TRY(lin(memA, h.P, "dfsmn.dnns.0.weight", "dfsmn.dnns.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
+  float* hcur = bufH;
+  float* hnext = bufH2;
+  for (int j = 1; j < h.M; ++j) {
+    std::string n = "dfsmn.dnns." + std::to_string(2 * j);
+    std::string b = n + ".bias";
+    VADX_TRY(lin(hcur, h.H, n + ".weight", b.c_str(), nullptr, hnext, h.H, VADX_ACT_RELU));
+    std::swap(hcur, hnext);
+  }
+  // head: [S*T][H] -> probs [S][odim][T]
+  VADX_TRY(linear_narrow(hcur, h.H, m->d<float>("out.weight#T"), (int)round_up(h.odim, 4), m->d<float>("out.bias"),
+                         d_probs, rows, h.H, h.odim, VADX_ACT_SIGMOID, T, (int64_t)h.odim * T, T, st));
+  return VADX_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out) {
+  VADX_REQUIRE(kind && out && (n_hparams == 0 || hparams), "vadx_create: null pointer");
+  VADX_REQUIRE(!strcmp(kind, "firered"), "vadx_create: unknown model kind '%s'", kind);
+  if (vadx_device_count() < 1) {
+    set_error("vadx_create: no CUDA device is visible; libvadx has no CPU path");
+    return VADX_ENODEVICE;
+  }
+  vadx_model* m = new vadx_model();
+  m->kind = kind;
+  m->hp.assign(hparams, hparams + n_hparams);
+  if (m->kind == "firered") {
+    FireRedHP h;
+    int rc = firered_hp(m, &h);
+    if (rc != VADX_OK) {
+      delete m;
+      return rc;
+    }
+  }
+  *out = m;
+  return VADX_OK;
+}
+
+extern "C" void vadx_destroy(vadx_model* m) { delete m; }
+
+extern "C" int vadx_set_tensor(vadx_model* m, const char* name, const void* h_data, int dtype, const int64_t* dims,
+                               int n_dims) {
+  VADX_REQUIRE(m && name && h_data && dims && n_dims >= 1 && n_dims <= 8, "vadx_set_tensor: bad argument");
+  VADX_REQUIRE(dtype == VADX_DT_I16 || dtype == VADX_DT_F32 || dtype == VADX_DT_I32, "vadx_set_tensor: dtype %d", dtype);
+  HostTensor t;
+  t.dtype = dtype;
+  t.dims.assign(dims, dims + n_dims);
+  for (int i = 0; i < n_dims; ++i) VADX_REQUIRE(dims[i] >= 0, "vadx_set_tensor: negative dim");
+  size_t esz = dtype == VADX_DT_I16 ? 2 : 4;
+  t.bytes.resize((size_t)t.numel() * esz);
+  memcpy(t.bytes.data(), h_data, t.bytes.size());
+  m->host[name] = std::move(t);
+  m->finalized = false;
+  return VADX_OK;
+}
+
+extern "C" int vadx_set_scalar(vadx_model* m, const char* name, double value) {
+  VADX_REQUIRE(m && name, "vadx_set_scalar: null pointer");
+  m->scalars[name] = value;
+  return VADX_OK;
+}
+
+extern "C" int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_frames) {
+  VADX_REQUIRE(m && out_frames, "vadx_output_frames: null pointer");
+  FireRedHP h;
+  VADX_TRY(firered_hp(m, &h));
+  *out_frames = h.frames(n_samples);
+  return VADX_OK;
+}
+
+extern "C" int vadx_workspace_bytes(const vadx_model* m, int64_t n_streams, int64_t n_samples, size_t* out_bytes) {
+  VADX_REQUIRE(m && out_bytes && n_streams >= 0 && n_samples >= 0, "vadx_workspace_bytes: bad argument");
+  return firered_run(const_cast<vadx_model*>(m), true, nullptr, nullptr, nullptr, n_streams, n_samples, nullptr, 0,
+                     out_bytes, nullptr);
+}
+
+extern "C" int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
+                            int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
+                            void* stream) {
+  VADX_REQUIRE(m && d_inputs && d_outputs && d_inputs[0] && d_outputs[0], "vadx_forward: null pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_samples > 0, "vadx_forward: bad shape S=%lld L=%lld", (long long)n_streams,
+               (long long)n_samples);
+  VADX_REQUIRE(d_workspace || workspace_bytes == 0, "vadx_forward: null workspace");
+  if (!m->finalized) {
+    m->release();
+    VADX_TRY(firered_finalize(m));
+    m->finalized = true;
+  }
+  if (n_streams == 0) return VADX_OK;
+  (void)d_state;
+  return firered_run(m, false, d_inputs[0], (float*)d_outputs[0], nullptr, n_streams, n_samples, d_workspace,
+                     workspace_bytes, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,117 @@
+"""ctypes binding of libvadx.so (the C ABI in include/vadx.h).
+
+There is NO fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C voice-activity-detection-vad-onnx_b200/csrc``)
+or no CUDA device is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvadx.so")
+
+DT_I16, DT_F32, DT_I32 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+FLOOR_CLAMP, FLOOR_ADD = 0, 1
+PREEMPH_NONE, PREEMPH_ZERO_HISTORY, PREEMPH_KEEP_FIRST = 0, 1, 2
+
+_ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: KeyError, -5: MemoryError}
+
+
+class PostCfg(C.Structure):
+    _fields_ = [("smooth_window", C.c_int32), ("threshold", C.c_float), ("min_speech_frame", C.c_int32),
+                ("max_speech_frame", C.c_int32), ("min_silence_frame", C.c_int32),
+                ("merge_silence_frame", C.c_int32), ("extend_speech_frame", C.c_int32)]
+
+
+_i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/vadx.h declares (tests check this)
+SIGNATURES = {
+    "vadx_abi_version": (C.c_int, []),
+    "vadx_last_error": (C.c_char_p, []),
+    "vadx_device_count": (C.c_int, []),
+    "vadx_launch_count": (C.c_uint64, []),
+    "vadx_profile_enable": (C.c_int, [_i32]),
+    "vadx_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _i32]),
+    "vadx_prep_audio": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _f32, _i32, _i32, _f32, _i64, _vp, _i64, _vp]),
+    "vadx_stft_power_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "vadx_mel_log_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i64, _vp]),
+    "vadx_linear_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "vadx_fsmn_memory_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64,
+                                       _i32, _i32, _vp, _vp, _vp]),
+    "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
+    "vadx_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
+    "vadx_destroy": (None, [_vp]),
+    "vadx_set_tensor": (C.c_int, [_vp, C.c_char_p, _vp, _i32, C.POINTER(_i64), _i32]),
+    "vadx_set_scalar": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "vadx_workspace_bytes": (C.c_int, [_vp, _i64, _i64, C.POINTER(_sz)]),
+    "vadx_output_frames": (C.c_int, [_vp, _i64, C.POINTER(C.c_int32)]),
+    "vadx_forward": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libvadx.so and bind every signature.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(vadx has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vadx_abi_version() != 1:
+        raise RuntimeError(f"libvadx ABI {lib.vadx_abi_version()} != 1; rebuild the library")
+    _lib = lib
+    return lib
+
+
+STAGES = ("prep", "stft", "mel", "linear", "memory", "head", "postproc")
+
+
+def profile_enable(on: bool) -> None:
+    check(load().vadx_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> dict:
+    """-> {stage: (milliseconds, calls)} accumulated since the last collect (synchronises)."""
+    ms = (C.c_double * len(STAGES))()
+    calls = (C.c_uint64 * len(STAGES))()
+    check(load().vadx_profile_collect(ms, calls, len(STAGES)))
+    return {n: (ms[i], int(calls[i])) for i, n in enumerate(STAGES)}
+
+
+def check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = load().vadx_last_error().decode("utf-8", "replace")
+    raise _ERRORS.get(rc, RuntimeError)(f"libvadx: {msg} (code {rc})")
+
+
+def require_device() -> None:
+    if load().vadx_device_count() < 1:
+        raise RuntimeError("libvadx: no CUDA device visible; vadx has no CPU path")
+
+
+def ptr(t) -> int:
+    """Device (or host) address of a torch tensor / numpy array, or 0 for None."""
+    if t is None:
+        return 0
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr(stream=None) -> int:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream

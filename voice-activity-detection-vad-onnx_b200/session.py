@@ -1,0 +1,185 @@
+"""vadx.InferenceSession -- the drop-in for `onnxruntime.InferenceSession` on the VAD hot path.
+
+The reference scripts build a session from an .onnx file and call
+``sess.run([out_name], {in_name: ndarray})`` once per chunk
+(FireRedVAD/Inference_FireRed_ONNX.py:523-572).  Here the session is built from a model kind +
+hyper-parameters + a state_dict of numpy weights, and the same ``run`` call goes to the CUDA
+engine through the C ABI (include/vadx.h).  ``run_batch`` is the B200-native entry: S chunks
+at once, device tensors in and out, asynchronous on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import asdict
+
+import numpy as np
+
+from . import constants, lib, tables, weights as W
+
+
+class NodeArg:
+    """Mirror of onnxruntime.NodeArg: .name, .shape, .type"""
+
+    def __init__(self, name, shape, type_):
+        self.name, self.shape, self.type = name, shape, type_
+
+    def __repr__(self):
+        return f"NodeArg(name='{self.name}', type='{self.type}', shape={self.shape})"
+
+
+class _Engine:
+    """Owns a vadx_model handle and a growable device workspace."""
+
+    def __init__(self, kind: str, hparams):
+        import torch
+        self._torch = torch
+        self._lib = lib.load()
+        lib.require_device()
+        hp = (C.c_int32 * len(hparams))(*[int(v) for v in hparams])
+        h = C.c_void_p()
+        lib.check(self._lib.vadx_create(kind.encode(), hp, len(hparams), C.byref(h)))
+        self._h = h
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vadx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_tensor(self, name: str, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        dt = {np.dtype(np.int16): lib.DT_I16, np.dtype(np.float32): lib.DT_F32, np.dtype(np.int32): lib.DT_I32}[arr.dtype]
+        dims = (C.c_int64 * max(arr.ndim, 1))(*(arr.shape if arr.ndim else (1,)))
+        lib.check(self._lib.vadx_set_tensor(self._h, name.encode(), arr.ctypes.data, dt, dims, max(arr.ndim, 1)))
+
+    def set_scalar(self, name: str, v: float):
+        lib.check(self._lib.vadx_set_scalar(self._h, name.encode(), float(v)))
+
+    def output_frames(self, n_samples: int) -> int:
+        out = C.c_int32()
+        lib.check(self._lib.vadx_output_frames(self._h, n_samples, C.byref(out)))
+        return out.value
+
+    def workspace_bytes(self, n_streams: int, n_samples: int) -> int:
+        out = C.c_size_t()
+        lib.check(self._lib.vadx_workspace_bytes(self._h, n_streams, n_samples, C.byref(out)))
+        return out.value
+
+    def workspace(self, n_bytes: int, device):
+        torch = self._torch
+        if self._ws is None or self._ws.numel() < n_bytes or self._ws.device != device:
+            self._ws = None
+            self._ws = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def forward(self, inputs, outputs, states, n_streams, n_samples, stream=None):
+        dev = inputs[0].device
+        need = self.workspace_bytes(n_streams, n_samples)
+        ws = self.workspace(need, dev)
+        ins = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
+        outs = (C.c_void_p * len(outputs))(*[t.data_ptr() for t in outputs])
+        sts = (C.c_void_p * max(len(states), 1))(*([t.data_ptr() for t in states] or [None]))
+        lib.check(self._lib.vadx_forward(self._h, ins, outs, sts, n_streams, n_samples, ws.data_ptr(), need,
+                                         lib.stream_ptr(stream)))
+
+
+class FireRedSession:
+    """FireRedVAD (non-stream VAD / AED) session.
+
+    I/O contract of the reference graph (FireRedVAD/Export_FireRedVAD.py:794-807):
+    ``audio`` int16 (1, 1, L) -> ``probs`` fp32 (1, odim, T), T = 1 + (L - 400) // 160.
+    """
+    MAX_STREAMS_PER_CALL = 32768
+
+    def __init__(self, weights: dict, cfg: W.FireRedConfig = W.FireRedConfig(), chunk_len: int | None = 16000):
+        self.cfg = cfg
+        self.chunk_len = chunk_len
+        hp = [cfg.idim, cfg.R, cfg.M, cfg.H, cfg.P, cfg.N1, cfg.S1, cfg.N2 if not cfg.streaming else 0, cfg.S2,
+              cfg.odim, cfg.n_fft, cfg.win_length, cfg.hop, cfg.n_mels]
+        self._e = _Engine("firered", hp)
+        basis, first, _ = tables.interleaved_basis(cfg.n_fft, cfg.win_length, cfg.window, "v2")
+        assert first == 0
+        bank = constants.kaldi_like_mel_bank(cfg.n_fft, cfg.n_mels, 16000).numpy()
+        st, ln, w = tables.sparse_bank(bank)
+        self._e.set_tensor("frontend.basis", basis)
+        self._e.set_tensor("frontend.mel_start", st)
+        self._e.set_tensor("frontend.mel_len", ln)
+        self._e.set_tensor("frontend.mel_w", w)
+        self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
+        self._e.set_scalar("frontend.log_floor", cfg.log_floor)
+        spec = W.firered_spec(cfg)
+        for name in spec:
+            if name not in weights:
+                raise KeyError(f"FireRedSession: weight '{name}' missing from the state dict")
+            a = np.asarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(spec[name]):
+                raise ValueError(f"FireRedSession: '{name}' has shape {a.shape}, expected {spec[name]}")
+            self._e.set_tensor(name, a)
+        L = chunk_len if chunk_len else "audio_len"
+        T = self._e.output_frames(chunk_len) if chunk_len else "signal_len"
+        self._inputs_meta = [NodeArg("audio", [1, 1, L], "tensor(int16)")]
+        self._outputs_meta = [NodeArg("probs", [1, cfg.odim, T], "tensor(float)")]
+
+    # ---- onnxruntime.InferenceSession surface --------------------------------------------
+    def get_inputs(self):
+        return list(self._inputs_meta)
+
+    def get_outputs(self):
+        return list(self._outputs_meta)
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
+
+    def run(self, output_names, input_feed: dict):
+        """numpy in / numpy out, like ORT.  Accepts (S, 1, L) as well as the reference's (1, 1, L)."""
+        import torch
+        if output_names is not None and any(n != "probs" for n in output_names):
+            raise ValueError(f"InvalidArgument: unknown output name in {output_names}")
+        if set(input_feed) != {"audio"}:
+            raise ValueError(f"InvalidArgument: expected exactly the input 'audio', got {sorted(input_feed)}")
+        a = input_feed["audio"]
+        if not isinstance(a, np.ndarray) or a.dtype != np.int16:
+            raise ValueError("InvalidArgument: 'audio' must be a numpy int16 array (tensor(int16))")
+        if a.ndim != 3 or a.shape[1] != 1:
+            raise ValueError(f"InvalidArgument: 'audio' must have shape (S, 1, L), got {a.shape}")
+        if self.chunk_len and a.shape[2] != self.chunk_len:
+            raise ValueError(f"InvalidArgument: 'audio' length {a.shape[2]} != static axis {self.chunk_len}")
+        if a.shape[2] < self.cfg.win_length:
+            raise ValueError(f"InvalidArgument: 'audio' length {a.shape[2]} shorter than one frame")
+        d = torch.from_numpy(np.ascontiguousarray(a[:, 0, :])).cuda()
+        p = self.run_batch(d)
+        return [p.cpu().numpy()]
+
+    # ---- B200-native surface ----------------------------------------------------------------
+    def frames(self, n_samples: int) -> int:
+        return self._e.output_frames(n_samples)
+
+    def run_batch(self, audio, out=None, stream=None):
+        """audio: cuda int16 [S, L] -> probs cuda fp32 [S, odim, T]; asynchronous on `stream`."""
+        import torch
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2):
+            raise ValueError("run_batch: audio must be a CUDA int16 tensor of shape [S, L]")
+        if not audio.is_contiguous():
+            raise ValueError("run_batch: audio must be contiguous")
+        S, L = audio.shape
+        T = self.frames(L)
+        if T < 1:
+            raise ValueError(f"run_batch: {L} samples are shorter than one frame")
+        if out is None:
+            out = torch.empty((S, self.cfg.odim, T), dtype=torch.float32, device=audio.device)
+        elif tuple(out.shape) != (S, self.cfg.odim, T) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("run_batch: bad `out` tensor")
+        step = self.MAX_STREAMS_PER_CALL
+        for s0 in range(0, S, step):
+            s1 = min(S, s0 + step)
+            self._e.forward([audio[s0:s1]], [out[s0:s1]], [], s1 - s0, L, stream)
+        return out
+
+
+def InferenceSession(kind: str, weights: dict, config=None, **kw):
+    """Factory with the reference's constructor name; `kind` replaces the .onnx path."""
+    if kind == "firered":
+        return FireRedSession(weights, config or W.FireRedConfig(), **kw)
+    raise ValueError(f"unknown model kind {kind!r}")
