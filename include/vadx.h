@@ -111,6 +111,20 @@ int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt, int ldw, c
                     const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
                     int n_out, int act, void* stream);
 
+/* a8 on the tensor cores (tcgen05.mma, TMEM accumulators): same contract as vadx_linear_f32 but the
+ * weight is passed as the packed operand image built ONCE on the host by vadx_pack_weight_tc
+ * (bf16 hi/lo split, K-major, 128-byte swizzled 64-column tiles).  fp32-grade: both operands are
+ * split into two bf16 terms and three products are accumulated in fp32.
+ * vadx_tc_supported: 1 when (n_in, n_out) fits the weights-stationary kernel (n_out in 9..256 and
+ * the image + two activation stages fit in shared memory).
+ * vadx_pack_weight_tc: h_w is the reference-layout weight [n_out][n_in] on the HOST; call with
+ * h_img = NULL to query *img_bytes. */
+int vadx_tc_supported(int n_in, int n_out);
+int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* h_img, size_t img_capacity, size_t* img_bytes);
+int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
+                       const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
+                       int n_out, int act, void* stream);
+
 /* a5/a6/a7 -- FSMN / DFSMN memory block on time-major activations [S][T][C]:
  *   out[t] = p[t] + sum_k wl[c][k] * p[t - (n_back-1-k)*stride_back]
  *                 + sum_k wr[c][k] * p[t + (k+1)*stride_ahead]        (only when T > 1)

@@ -1,0 +1,79 @@
+"""Tensor-core dense layer (tcgen05 + TMEM, bf16 two-term split) against an fp64 reference and
+against the exact-fp32 SIMT kernel."""
+import numpy as np
+import pytest
+import torch
+
+import vadx
+from vadx import lib, synth, weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_tc(cuda, x, w, b, r, act):
+    l = lib.load()
+    rows, n_in = x.shape
+    n_out = w.shape[0]
+    img = torch.from_numpy(lib.pack_weight_tc(w.numpy())).to(cuda)
+    xd, bd = x.to(cuda), (b.to(cuda) if b is not None else None)
+    rd = r.to(cuda) if r is not None else None
+    y = torch.full((rows, n_out), float("nan"), device=cuda)
+    lib.check(l.vadx_linear_tc_f32(xd.data_ptr(), n_in, img.data_ptr(), lib.ptr(bd), lib.ptr(rd), n_out, y.data_ptr(),
+                                   n_out, rows, n_in, n_out, act, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+@pytest.mark.parametrize("rows,n_in,n_out,act,res,bias", [
+    (128, 64, 16, 0, False, False),       # one tile, one k-chunk, smallest N
+    (128, 128, 256, 1, False, True),      # FireRed fc1
+    (1000, 256, 128, 0, True, False),     # FireRed fc2 (+ residual), ragged last tile
+    (98 * 40, 80, 256, 1, False, True),   # first layer: K = 80 (partial k-chunk)
+    (300000, 128, 256, 1, False, True),   # many tiles per CTA: exercises both ring wrap-arounds
+    (777, 140, 200, 1, False, True),      # odd sizes: K = 140 -> 3 k-chunks, N padded to 208
+    (513, 250, 140, 0, False, True),      # K = 250 -> 4 k-chunks, N padded to 144
+    (64, 128, 128, 2, False, True),       # fewer rows than one tile, sigmoid
+])
+def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):
+    assert lib.load().vadx_tc_supported(n_in, n_out) == 1
+    g = torch.Generator().manual_seed(rows * 7 + n_in)
+    x = torch.randn((rows, n_in), generator=g) * 3.0
+    w = torch.randn((n_out, n_in), generator=g) / np.sqrt(n_in)
+    b = torch.randn((n_out,), generator=g) if bias else None
+    r = torch.randn((rows, n_out), generator=g) if res else None
+    y = _run_tc(cuda, x, w, b, r, act)
+    ref = x.double() @ w.double().T
+    if bias:
+        ref = ref + b.double()
+    ref = torch.relu(ref) if act == 1 else torch.sigmoid(ref) if act == 2 else ref
+    if res:
+        ref = ref + r.double()
+    err = (y.double() - ref).abs().max().item()
+    print(f"tc linear {rows}x{n_in}->{n_out}: max abs err {err:.3e}")
+    assert not torch.isnan(y).any()
+    # two-term bf16 split: <= ~3 * 2^-18 relative per product; bound it by the coherent worst case
+    bound = 1.2e-5 * (x.abs().double() @ w.abs().double().T).max().item() + 1e-6
+    assert err <= bound, (err, bound)
+
+
+def test_unsupported_shapes_are_rejected(cuda):
+    l = lib.load()
+    assert l.vadx_tc_supported(256, 1) == 0      # narrow heads stay on the warp-reduction kernel
+    assert l.vadx_tc_supported(400, 402) == 0    # DFT basis does not fit the stationary-operand budget
+    with pytest.raises(ValueError):
+        lib.pack_weight_tc(np.zeros((402, 400), np.float32))
+
+
+def test_firered_tc_vs_simt_and_oracle(cuda):
+    from oracle.firered import FireRedOracle
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, 0)
+    chunks = synth.synth_chunks_fast(200, 16000, seed=9)
+    d = torch.from_numpy(chunks).to(cuda)
+    p_tc = vadx.FireRedSession(w, cfg, tensor_cores=True).run_batch(d).cpu().numpy()
+    p_simt = vadx.FireRedSession(w, cfg, tensor_cores=False).run_batch(d).cpu().numpy()
+    ref = FireRedOracle(w, cfg).forward(chunks).numpy()
+    e_tc, e_simt = np.abs(p_tc - ref).max(), np.abs(p_simt - ref).max()
+    print(f"FireRed max abs prob err vs oracle: tensor-core {e_tc:.3e}, fp32 SIMT {e_simt:.3e}")
+    assert e_tc <= 1e-3 and e_simt <= 1e-3
+    assert np.abs(p_tc - p_simt).max() <= 1e-3

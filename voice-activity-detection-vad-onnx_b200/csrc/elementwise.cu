@@ -140,6 +140,81 @@ __global__ void __launch_bounds__(256) fsmn_memory_kernel(const float* __restric
   }
 }
 
+
+// Streaming variant for unit strides: thread = (stream, time tile, channel).  The taps and a
+// (R + N1 - 1 + N2)-deep delay line live in registers; every input is read from global memory once
+// per tile (a warp reads 32 consecutive channels of one frame = one 128-byte line), the next R
+// inputs are prefetched while the current R outputs are computed, and no shared memory or barrier
+// is involved, so many independent warps keep loads in flight (HBM-bound by design).
+constexpr int kMemR = 14;
+template <int N1, int N2>
+__global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __restrict__ p, int64_t ldp,
+                                                                 const float* __restrict__ wl,
+                                                                 const float* __restrict__ wr,
+                                                                 const float* __restrict__ res, int64_t ldr,
+                                                                 float* __restrict__ out, int64_t ldo, int n_frames,
+                                                                 int C, const float* __restrict__ cache_in,
+                                                                 int tile_t) {
+  constexpr int HL = N1 - 1, HR = N2, W = kMemR + HL + HR;
+  const int c = blockIdx.z * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t s = blockIdx.y;
+  const int t0 = blockIdx.x * tile_t;
+  const int t1 = min(t0 + tile_t, n_frames);
+  const float* ps = p + s * (int64_t)n_frames * ldp + c;
+  auto load = [&](int t) -> float {
+    if (t >= 0 && t < n_frames) return __ldg(ps + (int64_t)t * ldp);
+    if (t < 0 && cache_in) return cache_in[(s * C + c) * (int64_t)HL + (HL + t)];
+    return 0.f;
+  };
+  float cl[N1], cr[N2 > 0 ? N2 : 1];
+#pragma unroll
+  for (int k = 0; k < N1; ++k) cl[k] = __ldg(wl + c * N1 + k);
+#pragma unroll
+  for (int k = 0; k < N2; ++k) cr[k] = __ldg(wr + c * N2 + k);
+  float w[W];
+#pragma unroll
+  for (int j = 0; j < HL + HR; ++j) w[j] = load(t0 - HL + j);
+  float nxt[kMemR];
+#pragma unroll
+  for (int r = 0; r < kMemR; ++r) nxt[r] = load(t0 + HR + r);
+  for (int tb = t0; tb < t1; tb += kMemR) {
+#pragma unroll
+    for (int r = 0; r < kMemR; ++r) w[HL + HR + r] = nxt[r];
+    if (tb + kMemR < t1) {
+#pragma unroll
+      for (int r = 0; r < kMemR; ++r) nxt[r] = load(tb + kMemR + HR + r);
+    }
+    float rs[kMemR];
+    if (res) {
+#pragma unroll
+      for (int r = 0; r < kMemR; ++r)
+        rs[r] = (tb + r < t1) ? __ldg(res + (s * (int64_t)n_frames + tb + r) * ldr + c) : 0.f;
+    }
+    float acc[kMemR];
+#pragma unroll
+    for (int r = 0; r < kMemR; ++r) acc[r] = w[r + HL];
+#pragma unroll
+    for (int k = 0; k < N1; ++k)
+#pragma unroll
+      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(cl[k], w[r + k], acc[r]);
+#pragma unroll
+    for (int k = 0; k < N2; ++k)
+#pragma unroll
+      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(cr[k], w[r + N1 + k], acc[r]);
+#pragma unroll
+    for (int r = 0; r < kMemR; ++r) {
+      if (tb + r < t1) {
+        float v = acc[r];
+        if (res) v += rs[r];
+        out[(s * (int64_t)n_frames + tb + r) * ldo + c] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HL + HR; ++j) w[j] = w[j + kMemR];
+  }
+}
+
 // cache_out[s][c][j] = cat(cache_in, p)[T + j] for j in [0, halo): the streaming state hand-over
 __global__ void __launch_bounds__(256) fsmn_cache_out_kernel(const float* __restrict__ p, int64_t ldp,
                                                              const float* __restrict__ cache_in,
@@ -232,9 +307,23 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_kernel)");
     configured = 200 * 1024;
   }
-  dim3 grid((unsigned)ceil_div(n_frames, kMemT), (unsigned)n_streams);
-  fsmn_memory_kernel<<<grid, 256, smem, st>>>(d_p, ldp, d_wl, n_back, stride_back, d_wr, n_ahead, stride_ahead,
-                                              d_residual, ldr, d_out, ldo, n_frames, n_channels, d_cache_in);
+  // fast path: unit strides, 20(+20) taps
+  const bool fast = stride_back == 1 && (n_ahead == 0 || stride_ahead == 1) && n_back == 20 &&
+                    (n_ahead == 20 || n_ahead == 0) && n_frames > 1;
+  if (fast) {
+    const int tile_t = (int)std::min<int64_t>(round_up(n_frames, kMemR), 8 * kMemR);
+    dim3 grid2((unsigned)ceil_div(n_frames, tile_t), (unsigned)n_streams, (unsigned)ceil_div(n_channels, 128));
+    if (n_ahead == 20)
+      fsmn_memory_stream_kernel<20, 20><<<grid2, 128, 0, st>>>(d_p, ldp, d_wl, d_wr, d_residual, ldr, d_out, ldo,
+                                                               n_frames, n_channels, d_cache_in, tile_t);
+    else
+      fsmn_memory_stream_kernel<20, 0><<<grid2, 128, 0, st>>>(d_p, ldp, d_wl, d_wr, d_residual, ldr, d_out, ldo,
+                                                              n_frames, n_channels, d_cache_in, tile_t);
+  } else {
+    dim3 grid((unsigned)ceil_div(n_frames, kMemT), (unsigned)n_streams);
+    fsmn_memory_kernel<<<grid, 256, smem, st>>>(d_p, ldp, d_wl, n_back, stride_back, d_wr, n_ahead, stride_ahead,
+                                                d_residual, ldr, d_out, ldo, n_frames, n_channels, d_cache_in);
+  }
   VADX_TRY(after_launch("vadx_fsmn_memory_f32"));
   if (d_cache_out && halo_l > 0) {
     int64_t total = n_streams * n_channels * halo_l;

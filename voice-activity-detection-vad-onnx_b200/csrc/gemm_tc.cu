@@ -1,0 +1,423 @@
+// gemm_tc.cu -- dense layers (a8) on the 5th-generation tensor cores: tcgen05.mma with TMEM
+// accumulators, weights-stationary persistent CTAs, fp32-grade accuracy through a two-term bf16
+// split of both operands.
+//
+//   Y[rows][N] = act(X[rows][K] * W^T + bias) (+ residual)       X, Y fp32 row-major in HBM
+//
+// Numerics: x = xh + xl, w = wh + wl with xh = bf16(x), xl = bf16(x - xh) (same for w).  The tile
+// product is accumulated in fp32 TMEM as  xh*wh + xl*wh + xh*wl ; the dropped xl*wl term and the
+// rounding of the low parts are ~2^-17 relative per product, i.e. fp32-grade for the <=1e-3
+// frame-probability budget (measured: see tests/test_gpu_tc.py).
+//
+// Layout: operands live in shared memory as K-major, 128-byte-swizzled bf16 tiles of 64 k-columns
+// (one swizzle atom wide): element (row r, k) of a tile sits at byte
+//     (r/8)*1024 + (r%8)*128 + (((k/8) ^ (r%8))*16) + (k%8)*2 .
+// The weights are packed into exactly that image ONCE on the host (vadx_pack_weight_tc), so a CTA
+// pulls its whole stationary operand with a handful of 1-D bulk async copies (cp.async.bulk ->
+// mbarrier complete_tx); activations are converted fp32 -> (hi, lo) bf16 by the loader warps.
+//
+// CTA = 9 warps: 0-3 loaders (global fp32 -> split -> swizzled smem), 4-7 epilogue (TMEM -> regs ->
+// bias/act/residual -> global), 8 = TMEM allocator + single-thread MMA issuer.  Two TMEM
+// accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1; a 2-4 deep
+// mbarrier ring decouples the loaders from the MMA issuer.
+#include "common.cuh"
+
+namespace vadx {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;
+constexpr int kTcTileBytes = kTcBM * 128;        // one 128-row x 64-k bf16 tile
+constexpr int kTcStageBytes = 2 * kTcTileBytes;  // hi + lo
+constexpr int kTcThreads = 288;
+constexpr int kTcSmemBudget = 227 * 1024;
+
+struct TcArgs {
+  const float* X;
+  int64_t ldx;
+  const uint8_t* Wimg;
+  const float* bias;
+  const float* res;
+  int64_t ldr;
+  float* Y;
+  int64_t ldy;
+  int64_t M;
+  int K, N, n_pad, kc, n_k16, act, n_stages, n_tiles, tmem_cols, vec_x, vec_y;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (an error the host sees), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8-row atoms are 1024 B apart
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// kind::f16, A = B = bf16, D = fp32, both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// two floats -> packed (hi, lo) bf16x2 words: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));  // upper half <- b, lower half <- a
+  float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  float al = a - ah, bl = b - bh;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(bl), "f"(al));
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (base is 1024-aligned by the launch: dynamic smem starts at a 1024-aligned offset
+  // because the kernel has no static shared memory)
+  uint8_t* w_smem = smem_raw;
+  const int w_bytes = g.kc * 2 * g.n_pad * 128;
+  uint8_t* a_smem = w_smem + w_bytes;
+  float* bias_s = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + g.n_pad);
+  // bars: full[4], empty[4], tmem_full[2], tmem_empty[2], wbar
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (10 + b); };
+  const uint32_t wbar = bar0 + 8u * 12;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < g.n_pad; i += blockDim.x) bias_s[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // stationary operand: the packed weight image, kc*2 tiles of n_pad*128 bytes
+      mbar_expect_tx(wbar, (uint32_t)w_bytes);
+      const uint32_t img_bytes = (uint32_t)g.n_pad * 128u;
+      for (int t = 0; t < g.kc * 2; ++t)
+        bulk_g2s(smem_u32(w_smem) + t * img_bytes, g.Wimg + (size_t)t * img_bytes, img_bytes, wbar);
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_bf16(g.n_pad);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * g.n_pad);
+        for (int c = 0; c < g.kc; ++c) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_smem) + (uint32_t)stage * kTcStageBytes;
+          const uint32_t a_lo = a_hi + kTcTileBytes;
+          const uint32_t w_hi = smem_u32(w_smem) + (uint32_t)(c * 2) * img_bytes;
+          const uint32_t w_lo = w_hi + img_bytes;
+          const int nk = min(4, g.n_k16 - c * 4);
+          for (int j = 0; j < nk; ++j)
+            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w_hi + 32u * j), idesc,
+                      (c | j) ? 1u : 0u);
+          for (int j = 0; j < nk; ++j)
+            umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w_hi + 32u * j), idesc, 1u);
+          for (int j = 0; j < nk; ++j)
+            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w_lo + 32u * j), idesc, 1u);
+          umma_commit(empty_bar(stage));  // frees the activation stage once these MMAs retire
+          if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(b));        // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== loaders: fp32 rows -> (hi, lo) bf16, swizzled =====================
+    const int t = threadIdx.x;   // 0..127
+    const int kq = t & 7;        // 16-byte chunk (8 bf16) within the 64-k atom row
+    const int r_in = t >> 3;     // 0..15
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+      const int64_t row0 = (int64_t)tile * kTcBM;
+      for (int c = 0; c < g.kc; ++c) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
+        uint8_t* st_lo = st_hi + kTcTileBytes;
+        const int k = c * kTcBK + kq * 8;
+        // issue every global load of the stage before touching the data (16 x 16 B in flight per
+        // thread); rows past the end are clamped to a valid row and zeroed afterwards
+        float4 ld[8][2];
+        const bool vec = g.vec_x && (k + 7 < g.K);
+        if (vec) {
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+            const float4* src = reinterpret_cast<const float4*>(g.X + row * g.ldx + k);
+            ld[pass][0] = __ldg(src);
+            ld[pass][1] = __ldg(src + 1);
+          }
+        } else {
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+            const float* src = g.X + row * g.ldx + k;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (k + j < g.K) ? __ldg(src + j) : 0.f;
+            ld[pass][0] = make_float4(v[0], v[1], v[2], v[3]);
+            ld[pass][1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int r = pass * 16 + r_in;
+          float4 p0 = ld[pass][0], p1 = ld[pass][1];
+          if (row0 + r >= g.M) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          uint4 hi, lo;
+          split2(p0.x, p0.y, hi.x, lo.x);
+          split2(p0.z, p0.w, hi.y, lo.y);
+          split2(p1.x, p1.y, hi.z, lo.z);
+          split2(p1.z, p1.w, hi.w, lo.w);
+          const int off = r * 128 + ((kq ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(st_hi + off) = hi;
+          *reinterpret_cast<uint4*>(st_lo + off) = lo;
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(stage));
+        if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp - 4;  // TMEM lane quarter this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tfull_bar(b), use & 1u);
+      tc_fence_after();
+      const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * g.n_pad);
+      for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (!row_ok || c0 >= g.N) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + bias_s[c0 + j], g.act);
+        float* out = g.Y + row * g.ldy + c0;
+        const float* rs = g.res ? g.res + row * g.ldr + c0 : nullptr;
+        if (g.vec_y && c0 + 15 < g.N) {
+          if (rs) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 r4 = __ldg(reinterpret_cast<const float4*>(rs) + j);
+              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < g.N) out[j] = v[j] + (rs ? rs[j] : 0.f);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(b));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static inline uint16_t bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);  // inf / nan
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct TcShape {
+  int n_pad, kc, n_k16, n_stages, tmem_cols;
+  size_t w_bytes, smem_bytes;
+  bool ok;
+};
+TcShape tc_shape(int n_in, int n_out) {
+  TcShape s{};
+  s.n_pad = (int)round_up(n_out, 16);
+  s.kc = (int)ceil_div(n_in, kTcBK);
+  s.n_k16 = (int)ceil_div(n_in, 16);
+  s.w_bytes = (size_t)s.kc * 2 * s.n_pad * 128;
+  const size_t misc = (size_t)s.n_pad * 4 + 13 * 8 + 16;
+  s.ok = s.n_pad <= 256 && n_out > 8;
+  if (s.ok) {
+    size_t left = kTcSmemBudget > s.w_bytes + misc ? kTcSmemBudget - s.w_bytes - misc : 0;
+    s.n_stages = (int)std::min<size_t>(4, left / kTcStageBytes);
+    s.ok = s.n_stages >= 2;
+    s.smem_bytes = s.w_bytes + (size_t)s.n_stages * kTcStageBytes + misc;
+    int cols = 32;
+    while (cols < 2 * s.n_pad) cols *= 2;
+    s.tmem_cols = cols;
+  }
+  return s;
+}
+
+}  // namespace vadx
+
+using namespace vadx;
+
+extern "C" int vadx_tc_supported(int n_in, int n_out) { return tc_shape(n_in, n_out).ok ? 1 : 0; }
+
+extern "C" int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* h_img, size_t img_capacity,
+                                   size_t* img_bytes) {
+  VADX_REQUIRE(h_w && img_bytes && n_out > 0 && n_in > 0, "vadx_pack_weight_tc: bad argument");
+  TcShape s = tc_shape(n_in, n_out);
+  VADX_REQUIRE(s.ok, "vadx_pack_weight_tc: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
+  *img_bytes = s.w_bytes;
+  if (!h_img) return VADX_OK;  // size query
+  VADX_REQUIRE(img_capacity >= s.w_bytes, "vadx_pack_weight_tc: image buffer too small");
+  uint8_t* img = static_cast<uint8_t*>(h_img);
+  memset(img, 0, s.w_bytes);
+  const size_t tile = (size_t)s.n_pad * 128;
+  for (int n = 0; n < n_out; ++n)
+    for (int k = 0; k < n_in; ++k) {
+      float w = h_w[(size_t)n * n_in + k];
+      uint16_t hi = bf16_rn(w);
+      uint16_t lo = bf16_rn(w - bf16_to_f(hi));
+      int c = k / kTcBK, kk = k % kTcBK;
+      size_t off = (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)(((kk / 8) ^ (n % 8)) * 16) + (kk % 8) * 2;
+      memcpy(img + (size_t)(c * 2) * tile + off, &hi, 2);
+      memcpy(img + (size_t)(c * 2 + 1) * tile + off, &lo, 2);
+    }
+  return VADX_OK;
+}
+
+extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
+                                  const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows,
+                                  int n_in, int n_out, int act, void* stream) {
+  StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
+  VADX_REQUIRE(d_x && d_wimg && d_y, "vadx_linear_tc_f32: null pointer");
+  VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
+  TcShape s = tc_shape(n_in, n_out);
+  VADX_REQUIRE(s.ok, "vadx_linear_tc_f32: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
+  VADX_REQUIRE(aligned16(d_wimg), "vadx_linear_tc_f32: weight image must be 16-byte aligned");
+  if (n_rows == 0) return VADX_OK;
+  static int n_sm = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_tc_kernel)");
+    configured = true;
+  }
+  TcArgs g{};
+  g.X = d_x; g.ldx = ldx; g.Wimg = static_cast<const uint8_t*>(d_wimg); g.bias = d_bias; g.res = d_residual;
+  g.ldr = ldr; g.Y = d_y; g.ldy = ldy; g.M = n_rows; g.K = n_in; g.N = n_out; g.n_pad = s.n_pad; g.kc = s.kc;
+  g.n_k16 = s.n_k16; g.act = act; g.n_stages = s.n_stages; g.tmem_cols = s.tmem_cols;
+  int64_t tiles = ceil_div(n_rows, kTcBM);
+  VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_linear_tc_f32: too many rows");
+  g.n_tiles = (int)tiles;
+  g.vec_x = ((ldx & 3) == 0) && aligned16(d_x);
+  g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
+  int grid = (int)std::min<int64_t>(tiles, n_sm > 0 ? n_sm : 148);
+  linear_tc_kernel<<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  return after_launch("vadx_linear_tc_f32");
+}

@@ -104,7 +104,15 @@ struct vadx_model {
     const float* w = t->f32();
     for (int o = 0; o < n_out; ++o)
       for (int i = 0; i < n_in; ++i) wt[(size_t)i * ldw + o] = w[(size_t)o * n_in + i];
-    return upload(name + "#T", wt.data(), wt.size() * sizeof(float));
+    VADX_TRY(upload(name + "#T", wt.data(), wt.size() * sizeof(float)));
+    if (vadx_tc_supported(n_in, n_out)) {
+      size_t bytes = 0;
+      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, nullptr, 0, &bytes));
+      std::vector<uint8_t> img(bytes);
+      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, img.data(), img.size(), &bytes));
+      VADX_TRY(upload(name + "#TC", img.data(), img.size()));
+    }
+    return VADX_OK;
   }
   int upload_raw(const std::string& name, int64_t expect_numel, int dtype) {
     const HostTensor* t = find(name);
@@ -224,8 +232,13 @@ int firered_run(vadx_model* m, bool dry, const void* d_audio, float* d_probs, fl
   VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
                             VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
   auto lin = [&](const float* x, int n_in, const std::string& w, const char* b, const float* res, float* y, int n_out,
                  int act) -> int {
+    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
+    if (img)
+      return vadx_linear_tc_f32(x, n_in, img, b ? m->d<float>(b) : nullptr, res, n_out, y, n_out, rows, n_in, n_out,
+                                act, st);
     return vadx_linear_f32(x, n_in, m->d<float>(w + "#T"), (int)round_up(n_out, 4), b ? m->d<float>(b) : nullptr, res,
                            n_out, y, n_out, rows, n_in, n_out, act, st);
   };

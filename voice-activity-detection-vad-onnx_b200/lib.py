@@ -40,6 +40,9 @@ SIGNATURES = {
     "vadx_stft_power_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "vadx_mel_log_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i64, _vp]),
     "vadx_linear_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "vadx_tc_supported": (C.c_int, [_i32, _i32]),
+    "vadx_pack_weight_tc": (C.c_int, [_vp, _i32, _i32, _vp, _sz, C.POINTER(_sz)]),
+    "vadx_linear_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_fsmn_memory_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64,
                                        _i32, _i32, _vp, _vp, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
@@ -100,6 +103,18 @@ def check(rc: int) -> None:
 def require_device() -> None:
     if load().vadx_device_count() < 1:
         raise RuntimeError("libvadx: no CUDA device visible; vadx has no CPU path")
+
+
+def pack_weight_tc(w):
+    """[n_out, n_in] fp32 numpy weight -> uint8 numpy operand image for vadx_linear_tc_f32."""
+    import numpy as np
+    w = np.ascontiguousarray(w, np.float32)
+    n_out, n_in = w.shape
+    nbytes = C.c_size_t()
+    check(load().vadx_pack_weight_tc(w.ctypes.data, n_out, n_in, None, 0, C.byref(nbytes)))
+    img = np.zeros(nbytes.value, np.uint8)
+    check(load().vadx_pack_weight_tc(w.ctypes.data, n_out, n_in, img.ctypes.data, img.nbytes, C.byref(nbytes)))
+    return img
 
 
 def ptr(t) -> int:

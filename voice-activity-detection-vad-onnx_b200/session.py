@@ -93,7 +93,9 @@ class FireRedSession:
     """
     MAX_STREAMS_PER_CALL = 32768
 
-    def __init__(self, weights: dict, cfg: W.FireRedConfig = W.FireRedConfig(), chunk_len: int | None = 16000):
+    def __init__(self, weights: dict, cfg: W.FireRedConfig = W.FireRedConfig(), chunk_len: int | None = 16000,
+                 tensor_cores: bool = True):
+        """tensor_cores=False keeps every contraction on the exact-fp32 FFMA kernels (debug / A-B)."""
         self.cfg = cfg
         self.chunk_len = chunk_len
         hp = [cfg.idim, cfg.R, cfg.M, cfg.H, cfg.P, cfg.N1, cfg.S1, cfg.N2 if not cfg.streaming else 0, cfg.S2,
@@ -109,6 +111,7 @@ class FireRedSession:
         self._e.set_tensor("frontend.mel_w", w)
         self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
         self._e.set_scalar("frontend.log_floor", cfg.log_floor)
+        self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
         spec = W.firered_spec(cfg)
         for name in spec:
             if name not in weights:
