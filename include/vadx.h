@@ -138,6 +138,44 @@ int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* d_wl, int n
                          int64_t ldr, float* d_out, int64_t ldo, int64_t n_streams, int n_frames,
                          int n_channels, const float* d_cache_in, float* d_cache_out, void* stream);
 
+/* a4 -- FunASR low-frame-rate stacking + CMVN (FSMN/Export_FSMN_VAD.py:65-70,82-86):
+ * out[s][t][j*n_mels + m] = (mel[s][clamp(t + j - (lfr_m-1)/2, 0, T-1)][m] + mean[..]) * var[..]; lfr_n = 1. */
+int vadx_lfr_cmvn_f32(const float* d_mel, int64_t ld_mel, const float* d_mean, const float* d_var, float* d_out,
+                      int64_t ld_out, int64_t n_streams, int n_frames, int n_mels, int lfr_m, int lfr_n, void* stream);
+
+/* a8 head of the FunASR encoder: softmax over n_classes, keep class 0 (= P(silence),
+ * FSMN/modeling_modified/encoder.py:217). */
+int vadx_softmax_class0_f32(const float* d_logits, int64_t ld, int64_t n_rows, int n_classes, float* d_p0,
+                            void* stream);
+
+/* a9 -- frame energy of the prepared signal: out[s][t] = log10(sum_{n<win}(sig[s][offset+t*hop+n]*scale)^2 + eps)
+ * for t < n_energy, the last value replicated up to n_frames (FSMN/Export_FSMN_VAD.py:93-97). */
+int vadx_frame_energy_log10_f32(const float* d_sig, int64_t sig_stride, int64_t offset, int64_t n_streams, int win,
+                                int hop, int n_energy, int n_frames, float scale, float eps, float* d_out,
+                                void* stream);
+
+/* a9 -- gate: score2 = p + (ratio>1 ? p^ratio : ratio<1 ? 1 : p); speech = score2 <= thr && power >= noise[s];
+ * d_score u8 [S][T]; d_noisy_dB[s] = mean(power[~speech]) (NaN when empty) (FSMN/Export_FSMN_VAD.py:87-100). */
+int vadx_fsmn_gate(const float* d_p_sil, const float* d_power_dB, const float* d_noise_avg,
+                   float one_minus_speech_threshold, float speech_2_noise_ratio, int64_t n_streams, int n_frames,
+                   uint8_t* d_score, float* d_noisy_dB, void* stream);
+
+/* a13 -- look-ahead hysteresis of FSMN (mode 0: uint8 flags) and DFSMN (mode 1: fp32 probabilities), one
+ * stream per lane, all stream state on the device: d_silence_state[s] (1 = silence), d_n_saved[s],
+ * d_saved [S][ld_saved] (1 = silence, appended), and, when d_noise_avg/d_noisy_dB are given, the
+ * running background level noise = 0.5*(noise + noisy + snr) if noisy > 0
+ * (FSMN/Inference_FSMN_VAD_ONNX.py:188-234; DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:231-273).
+ * Every call appends n_frames - look_backward decisions; is_final also appends the tail frames. */
+int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_in, int64_t n_streams, int n_frames,
+                              int look_backward, double speaking_score, double silence_score, int is_final,
+                              uint8_t* d_silence_state, int32_t* d_n_saved, uint8_t* d_saved, int64_t ld_saved,
+                              float* d_noise_avg, const float* d_noisy_dB, float snr_threshold, void* stream);
+
+/* a14 -- runs of non-silence flags -> (start, end-exclusive) frame pairs per stream
+ * (vad_to_timestamps, FSMN/Inference_FSMN_VAD_ONNX.py:124-141). */
+int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags, int64_t n_streams,
+                          int32_t* d_seg_count, int32_t* d_segments, int max_segments, void* stream);
+
 /* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
  * that the float32 running sum rounds exactly like np.cumsum
  * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid
@@ -161,10 +199,12 @@ int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_
  * ------------------------------------------------------------------------------------------ */
 typedef struct vadx_model vadx_model;
 
-/* kind: "firered" (more kinds are added as the path widens).  `hparams` is a flat int32 array,
- * meaning per kind:
+/* kind: "firered" | "fsmn".  `hparams` is a flat int32 array, meaning per kind:
  *   firered: {idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win_length, hop, n_mels}
- *            (DetectModel args, FireRedVAD/Export_FireRedVAD.py:310-316, frontend :38-49) */
+ *            (DetectModel args, FireRedVAD/Export_FireRedVAD.py:310-316, frontend :38-49)
+ *   fsmn:    {input_dim, input_affine_dim, fsmn_layers, linear_dim, proj_dim, lorder, rorder, lstride, rstride,
+ *             output_affine_dim, output_dim, n_fft, win_length, hop, n_mels, lfr_m, lfr_n}
+ *            (FunASR FSMN encoder, FSMN/modeling_modified/encoder.py:159-206; frontend FSMN/Export_FSMN_VAD.py:24-34) */
 int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out);
 void vadx_destroy(vadx_model* m);
 
@@ -184,7 +224,12 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
 /* One pass of the model over S independent chunks.
  *   firered: inputs[0] = d_audio int16 [S][n_samples]; outputs[0] = d_probs fp32 [S][odim][T]
  *            (the reference's (1, odim, 98) with the leading 1 generalised to S,
- *            FireRedVAD/Export_FireRedVAD.py:794-807). state is unused (NULL). */
+ *            FireRedVAD/Export_FireRedVAD.py:794-807). state is unused (NULL).
+ *   fsmn:    inputs  = {audio int16 [S][L], noise_average_dB fp32 [S]}
+ *            outputs = {score uint8 [S][T], noisy_dB fp32 [S], P(silence) fp32 [S][T] or NULL,
+ *                       power_dB fp32 [S][T] or NULL}
+ *            state   = {cache_0..3 in, cache_0..3 out}, each fp32 [S][128][19], distinct buffers
+ *            (FSMN/Export_FSMN_VAD.py:122-134); thresholds are scalars set with vadx_set_scalar. */
 int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
                  int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
                  void* stream);

@@ -166,7 +166,88 @@ def gen_audio():
     print("vad_sample_16k.npz:", a.shape, a.dtype, int(np.abs(a).max()))
 
 
-GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio}
+# ------------------------------------------------------------------------------ FSMN
+def fsmn_reference(cfg, weights, input_audio_len):
+    """The reference's own FSMN_VAD wrapper (FSMN/Export_FSMN_VAD.py:56-101) around its own FunASR
+    FSMN encoder (FSMN/modeling_modified/encoder.py:159-217), with our seeded weights."""
+    stft = RL.import_file("FSMN/STFT_Process.py", "STFT_Process")
+    enc = RL.import_file("FSMN/modeling_modified/encoder.py", "fsmn_encoder_ref")
+    ns = RL.extract("FSMN/Export_FSMN_VAD.py", {"STFT_Process": stft.STFT_Process})
+    m = enc.FSMN(cfg.input_dim, cfg.input_affine_dim, cfg.fsmn_layers, cfg.linear_dim, cfg.proj_dim, cfg.lorder,
+                 cfg.rorder, cfg.lstride, cfg.rstride, cfg.output_affine_dim, cfg.output_dim).eval()
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items() if not k.startswith("cmvn")},
+                      strict=True)
+    hop = min(cfg.hop, input_audio_len)
+    T = input_audio_len // cfg.hop + 1
+    custom_stft = stft.STFT_Process(model_type='stft_B', n_fft=cfg.n_fft, hop_len=hop, win_length=cfg.win_length,
+                                    max_frames=0, window_type=cfg.window).eval()
+    means = torch.from_numpy(weights["cmvn_means"]).view(1, 1, -1)
+    vars_ = torch.from_numpy(weights["cmvn_vars"]).view(1, 1, -1)
+    wrap = ns["FSMN_VAD"](m, custom_stft, cfg.n_fft, T, cfg.n_mels, 16000, cfg.pre_emphasis, cfg.lfr_m, cfg.lfr_n,
+                          (T + cfg.lfr_n - 1) // cfg.lfr_n, cfg.speech_2_noise_ratio, input_audio_len, hop, means,
+                          vars_).eval()
+    return wrap, T
+
+
+def fsmn_fake_session(cfg, weights, input_audio_len):
+    from oracle import ref_runner as RR
+    wrap, T = fsmn_reference(cfg, weights, input_audio_len)
+    ins = [RR.NodeArg("audio", [1, 1, input_audio_len], "tensor(int16)")]
+    ins += [RR.NodeArg(f"cache_{i}", [1, 128, 19, 1], "tensor(float)") for i in range(4)]
+    ins += [RR.NodeArg("one_minus_speech_threshold", [1], "tensor(float)"),
+            RR.NodeArg("noise_average_dB", [1], "tensor(float)")]
+    outs = [RR.NodeArg("score", [T], "tensor(uint8)")]
+    outs += [RR.NodeArg(f"cache_{i}_out", [1, 128, 19, 1], "tensor(float)") for i in range(4)]
+    outs += [RR.NodeArg("noisy_dB", [], "tensor(float)")]
+
+    def fn(feed):
+        with torch.inference_mode():
+            r = wrap(torch.from_numpy(feed["audio"]), *[torch.from_numpy(feed[f"cache_{i}"]) for i in range(4)],
+                     torch.from_numpy(feed["one_minus_speech_threshold"]), torch.from_numpy(feed["noise_average_dB"]))
+        return [np.asarray(t.numpy()) for t in r]
+
+    return RR.FakeSession(ins, outs, fn)
+
+
+def gen_fsmn():
+    """Run the reference's UNMODIFIED FSMN/Inference_FSMN_VAD_ONNX.py on vad_sample.wav with its own
+    PyTorch graph behind a fake onnxruntime (oracle/ref_runner.py), for both chunkings."""
+    import vadx  # noqa: F401
+    from vadx import audio_io, weights as W
+    from oracle import ref_runner as RR
+
+    cfg = W.FsmnConfig()
+    w = W.fsmn_random_init(cfg, 0)
+    wav = os.path.join(RL.REF_ROOT, "FSMN", "vad_sample.wav")
+    out = {}
+    for tag, L, lookback in (("c16000", 16000, 0.3), ("c512", 512, 0.0)):
+        sess_box = {}
+
+        def factory(_path, L=L):
+            sess_box["s"] = fsmn_fake_session(cfg, w, L)
+            return sess_box["s"]
+
+        ns, files = RR.run_script("FSMN/Inference_FSMN_VAD_ONNX.py", factory,
+                                  lambda p, sr: audio_io.load_wav_int16(os.path.realpath(p), sr),
+                                  overrides={"LOOK_BACKWARD": lookback}, seed=1234,
+                                  files_to_link={"vad_sample.wav": wav})
+        calls = sess_box["s"].calls
+        out[f"{tag}_saved"] = np.array(ns["saved"], np.bool_)
+        out[f"{tag}_timestamps"] = np.array(ns["timestamps"], np.float64).reshape(-1, 2)
+        out[f"{tag}_file_second"] = np.array(files["timestamps_second.txt"])
+        out[f"{tag}_file_indices"] = np.array(files["timestamps_indices.txt"])
+        out[f"{tag}_aligned_audio"] = ns["audio"].reshape(-1).astype(np.int16)
+        out[f"{tag}_scores"] = np.stack([c[1][0] for c in calls]).astype(np.uint8)
+        out[f"{tag}_noisy_dB"] = np.array([c[1][5] for c in calls], np.float32)
+        out[f"{tag}_noise_avg_in"] = np.array([c[0]["noise_average_dB"][0] for c in calls], np.float32)
+        out[f"{tag}_cache0_last"] = calls[-1][1][1][0, :, :, 0]
+        out[f"{tag}_cache3_last"] = calls[-1][1][4][0, :, :, 0]
+        print(tag, "windows", len(calls), "flags", len(ns["saved"]), "speech frames", int((~out[f'{tag}_saved']).sum()),
+              "segments", out[f"{tag}_timestamps"].tolist())
+    np.savez_compressed(os.path.join(GOLD, "fsmn.npz"), **out)
+
+
+GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn}
 
 
 def main(argv):

@@ -1,0 +1,198 @@
+"""FSMN-VAD on the GPU through the C ABI against the oracle and the golden record of the
+reference's unmodified Inference_FSMN_VAD_ONNX.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vadx
+from vadx import audio_io, fsmn_vad, lib, postprocess as PP, synth, weights as W
+from oracle import fsmn as OFS, postproc as OP
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "fsmn.npz"))
+
+
+@pytest.fixture(scope="module")
+def wts():
+    return W.fsmn_random_init(W.FsmnConfig(), 0)
+
+
+def test_lfr_cmvn_and_softmax_and_energy(cuda, wts):
+    l = lib.load()
+    cfg = W.FsmnConfig()
+    S, T = 3, 101
+    g = torch.Generator().manual_seed(3)
+    mel = torch.randn((S, T, 80), generator=g) * 3 + 12
+    mean, var = torch.from_numpy(wts["cmvn_means"]), torch.from_numpy(wts["cmvn_vars"])
+    out = torch.empty((S, T, 400), device=cuda)
+    d = [t.to(cuda) for t in (mel, mean, var)]
+    lib.check(l.vadx_lfr_cmvn_f32(d[0].data_ptr(), 80, d[1].data_ptr(), d[2].data_ptr(), out.data_ptr(), 400, S, T, 80,
+                                  5, 1, lib.stream_ptr()))
+    padded = torch.cat([mel[:, :1].expand(-1, 2, -1), mel], 1)
+    idx = (torch.arange(T).unsqueeze(1) + torch.arange(5)).clamp(max=T + 1)
+    ref = (padded[:, idx].reshape(S, T, 400) + mean) * var
+    assert torch.equal(out.cpu(), ref)
+    # softmax class 0
+    logits = torch.randn((500, 248), generator=g) * 4
+    ld = 252
+    buf = torch.zeros((500, ld))
+    buf[:, :248] = logits
+    p0 = torch.empty((500,), device=cuda)
+    bd = buf.to(cuda)
+    lib.check(l.vadx_softmax_class0_f32(bd.data_ptr(), ld, 500, 248, p0.data_ptr(), lib.stream_ptr()))
+    assert (p0.cpu() - torch.softmax(logits, -1)[:, 0]).abs().max().item() <= 1e-6
+    # frame energy
+    L = 16000
+    y = torch.randn((S, L + 400), generator=g) * 2000
+    yd = y.to(cuda)
+    e = torch.empty((S, T), device=cuda)
+    scale = float(1.0 / (np.sqrt(L) * 2e-5))
+    lib.check(l.vadx_frame_energy_log10_f32(yd.data_ptr(), L + 400, 200, S, 512, 160, 97, T, scale, 0.00002,
+                                            e.data_ptr(), lib.stream_ptr()))
+    fr = (y[:, 200:200 + L] * scale).unfold(1, 512, 160)
+    ref = torch.log10((fr * fr).sum(-1) + 0.00002)
+    ref = torch.cat([ref, ref[:, -1:].expand(-1, T - 97)], 1)
+    assert (e.cpu() - ref).abs().max().item() <= 1e-5
+
+
+def test_hysteresis_kernel_matches_oracle(cuda):
+    rs = np.random.RandomState(5)
+    S, T, lb, n_chunks = 40, 101, 30, 6
+    flags = (rs.uniform(size=(n_chunks, S, T)) < np.linspace(0.2, 0.8, S)[None, :, None]).astype(np.uint8)
+    flags = np.repeat(flags[:, :, ::4], 4, axis=2)[:, :, :T]          # runs so both transitions happen
+    state = PP.HysteresisState(S, n_chunks * (T - lb) + lb, cuda)
+    for c in range(n_chunks):
+        PP.lookahead_hysteresis(torch.from_numpy(flags[c]).to(cuda), state, lb, 0.5, 0.5, c == n_chunks - 1)
+    cnt, seg = state.segments()
+    saved, n_saved, cnt, seg = [t.cpu().numpy() for t in (state.saved, state.n_saved, cnt, seg)]
+    for s in range(S):
+        ref = OP.lookahead_hysteresis_flags([flags[c, s] for c in range(n_chunks)], lb, 0.5, 0.5)
+        assert n_saved[s] == len(ref)
+        assert np.array_equal(saved[s, :len(ref)].astype(bool), np.array(ref)), s
+        raw = OP.runs_to_timestamps(ref, 0.01)
+        got = PP.runs_to_timestamps(seg[s, :cnt[s]], len(ref), 0.01)
+        assert got == raw
+        assert PP.process_timestamps(got, 0.3, 0.2) == OP.fuse_timestamps(raw, 0.3, 0.2)
+    # look_backward == 0 (the 512-sample chunking): every frame decides alone
+    state0 = PP.HysteresisState(S, n_chunks * T, cuda)
+    for c in range(n_chunks):
+        PP.lookahead_hysteresis(torch.from_numpy(flags[c]).to(cuda), state0, 0, 0.5, 0.5, c == n_chunks - 1)
+    ref0 = OP.lookahead_hysteresis_flags([flags[c, 7] for c in range(n_chunks)], 0, 0.5, 0.5)
+    assert np.array_equal(state0.saved[7, :len(ref0)].cpu().numpy().astype(bool), np.array(ref0))
+
+
+@pytest.mark.parametrize("L", [16000, 512])
+def test_session_run_ort_contract(cuda, wts, L):
+    cfg = W.FsmnConfig()
+    sess = vadx.FsmnSession(wts, cfg, chunk_len=L)
+    orc = OFS.FsmnOracle(wts, cfg, L)
+    names_in = [i.name for i in sess.get_inputs()]
+    names_out = [o.name for o in sess.get_outputs()]
+    assert names_in == ["audio", "cache_0", "cache_1", "cache_2", "cache_3", "one_minus_speech_threshold",
+                        "noise_average_dB"]
+    assert sess.get_outputs()[0].shape == [L // 160 + 1]
+    a = synth.synth_streams(1, 3 * L, seed=31)[0]
+    caches_np = [np.zeros((1, 128, 19, 1), np.float32) for _ in range(4)]
+    caches_t = [torch.zeros(1, 128, 19) for _ in range(4)]
+    for c in range(3):
+        chunk = a[c * L:(c + 1) * L]
+        feed = {"audio": chunk.reshape(1, 1, -1), "one_minus_speech_threshold": np.ones(1, np.float32),
+                "noise_average_dB": np.array([4.0], np.float32)}
+        feed.update({f"cache_{i}": caches_np[i] for i in range(4)})
+        outs = sess.run(names_out, feed)
+        ref = orc.forward(chunk[None], caches_t, 1.0, [4.0])
+        caches_t = ref["caches"]
+        caches_np = outs[1:5]
+        assert outs[0].dtype == np.uint8 and outs[0].shape == (L // 160 + 1,)
+        for i in range(4):
+            assert outs[1 + i].shape == (1, 128, 19, 1)
+            assert np.abs(outs[1 + i][0, :, :, 0] - ref["caches"][i][0].numpy()).max() <= 1e-3
+        # flags may only differ where the decision variables are within tolerance of their thresholds
+        score2 = 2 * ref["p_sil"][0].numpy()
+        margin = np.minimum(np.abs(score2 - 1.0), np.abs(ref["power_dB"][0].numpy() - 4.0))
+        diff = outs[0] != ref["score"][0].numpy()
+        assert not (diff & (margin > TOL)).any()
+        if not diff.any() and not np.isnan(ref["noisy_dB"][0].numpy()):
+            assert abs(float(outs[5]) - float(ref["noisy_dB"][0])) <= 1e-3
+
+
+def test_run_rejects_bad_inputs(cuda, wts):
+    sess = vadx.FsmnSession(wts, W.FsmnConfig(), chunk_len=16000)
+    good = {"audio": np.zeros((1, 1, 16000), np.int16), "one_minus_speech_threshold": np.ones(1, np.float32),
+            "noise_average_dB": np.array([4.0], np.float32)}
+    good.update({f"cache_{i}": np.zeros((1, 128, 19, 1), np.float32) for i in range(4)})
+    bad = dict(good, audio=np.zeros((1, 1, 8000), np.int16))
+    with pytest.raises(ValueError):
+        sess.run(None, bad)
+    bad = dict(good, cache_2=np.zeros((1, 128, 18, 1), np.float32))
+    with pytest.raises(ValueError):
+        sess.run(None, bad)
+    bad = {k: v for k, v in good.items() if k != "noise_average_dB"}
+    with pytest.raises(ValueError):
+        sess.run(None, bad)
+    with pytest.raises(ValueError):
+        vadx.FsmnSession(wts, W.FsmnConfig(), chunk_len=256)
+
+
+@pytest.mark.parametrize("tag,L,lookback", [("c16000", 16000, 0.3), ("c512", 512, 0.0)])
+def test_vad_sample_against_reference_script(cuda, gold, golden_dir, wts, tmp_path, tag, L, lookback):
+    """vad_sample.wav end to end vs the record of the reference's unmodified script (same weights,
+    same tail noise).  Frame probabilities within TOL of the oracle; every flag, timestamp and
+    output file byte identical unless a decision variable sits within TOL of its threshold."""
+    cfg = W.FsmnConfig()
+    sess = vadx.FsmnSession(wts, cfg, chunk_len=L)
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    f1, f2 = str(tmp_path / "timestamps_second.txt"), str(tmp_path / "timestamps_indices.txt")
+    r = fsmn_vad.run_vad(audio, sess, lookback, rng=np.random.RandomState(1234), save_timestamps_second=f1,
+                         save_timestamps_indices=f2, keep_trace=True)
+    orc = OFS.FsmnOracle(wts, cfg, L)
+    a16 = audio_io.normalize_to_int16(audio.astype(np.float32))
+    o = OFS.run_stream(orc, a16, look_backward_s=lookback, noise=np.random.RandomState(1234).normal(size=(20000,)))
+    assert len(o["trace"]) == len(r.p_silence) == gold[f"{tag}_scores"].shape[0]
+    err_p = max(np.abs(r.p_silence[c] - o["trace"][c][0]).max() for c in range(len(o["trace"])))
+    err_e = max(np.abs(r.power_dB[c] - o["trace"][c][1]).max() for c in range(len(o["trace"])))
+    print(f"{tag}: max abs err P(silence) {err_p:.2e}, power_dB {err_e:.2e}")
+    assert err_p <= TOL and err_e <= TOL
+    margin = min(min(np.abs(2 * t[0] - 1.0).min(), np.abs(t[1] - t[2]).min()) for t in o["trace"])
+    if margin > TOL:
+        assert np.array_equal(r.saved, gold[f"{tag}_saved"])
+        assert np.array_equal(np.array(r.timestamps, np.float64).reshape(-1, 2), gold[f"{tag}_timestamps"])
+        assert open(f1).read() == str(gold[f"{tag}_file_second"])
+        assert open(f2).read() == str(gold[f"{tag}_file_indices"])
+    else:
+        # decisions away from the thresholds must still agree
+        print(f"{tag}: a decision variable lies within {margin:.1e} of its threshold; comparing the rest")
+        assert (r.saved != gold[f"{tag}_saved"]).mean() < 0.02
+
+
+def test_many_streams_lockstep(cuda, wts):
+    cfg = W.FsmnConfig()
+    L, S, lb_s = 16000, 12, 0.3
+    sess = vadx.FsmnSession(wts, cfg, chunk_len=L)
+    orc = OFS.FsmnOracle(wts, cfg, L)
+    raw = synth.synth_streams(S, 4 * 16000 + 700, seed=77)
+    noise = np.random.RandomState(9).normal(size=(20000,))
+    aligned = []
+    for s in range(S):
+        a, stride, _ = audio_io.align_overlapping(raw[s], L, 30, 160, np.random.RandomState(9))
+        aligned.append(a)
+    d = torch.from_numpy(np.stack(aligned)).to(cuda)
+    state, _ = fsmn_vad.run_streams(sess, d, stride, lb_s)
+    cnt, seg = state.segments()
+    saved, n_saved = state.saved.cpu().numpy(), state.n_saved.cpu().numpy()
+    agree = 0
+    for s in range(S):
+        o = OFS.run_stream(orc, raw[s], look_backward_s=lb_s, noise=noise)
+        assert n_saved[s] == len(o["saved"])
+        margin = min(min(np.abs(2 * t[0] - 1.0).min(), np.abs(t[1] - t[2]).min()) for t in o["trace"])
+        if margin > TOL:
+            assert np.array_equal(saved[s, :n_saved[s]].astype(bool), np.array(o["saved"])), s
+            agree += 1
+    assert agree >= S // 2

@@ -48,3 +48,36 @@ def align_non_overlapping(audio: np.ndarray, chunk_len: int, rng: np.random.Rand
         noise = (np.sqrt(np.mean(af * af)) * rng.normal(loc=0.0, scale=1.0, size=(chunk_len - n,))).astype(np.int16)
         audio = np.concatenate((audio, noise))
     return audio.reshape(-1, chunk_len), n
+
+
+def normalize_to_int16(audio: np.ndarray) -> np.ndarray:
+    """Peak-normalise to 32767 like the FSMN / DFSMN loaders (FSMN/Inference_FSMN_VAD_ONNX.py:60-63)."""
+    audio = np.asarray(audio, np.float32)
+    max_val = np.max(np.abs(audio))
+    scaling_factor = 32767.0 / max_val if max_val > 0 else 1.0
+    return (audio * float(scaling_factor)).astype(np.int16)
+
+
+def align_overlapping(audio: np.ndarray, chunk_len: int, look_backward_frames: int, frame_len: int,
+                      rng: np.random.RandomState | None = None):
+    """FSMN / DFSMN chunker (FSMN/Inference_FSMN_VAD_ONNX.py:79-99): windows of chunk_len samples that
+    advance by chunk_len - (look_backward+1)*frame_len, tail padded with RMS-matched Gaussian noise
+    cast to int16.  Returns (aligned int16 [n], stride, original_length)."""
+    audio = np.asarray(audio, np.int16).reshape(-1)
+    rng = rng if rng is not None else np.random
+    n = audio.shape[0]
+    stride = chunk_len - (look_backward_frames + 1) * frame_len
+    if stride <= 0:
+        raise ValueError(f"chunk of {chunk_len} samples is too short for a look-backward of {look_backward_frames} frames")
+    pad = 0
+    if n > chunk_len:
+        num = int(np.ceil((n - chunk_len) / stride)) + 1
+        pad = (num - 1) * stride + chunk_len - n
+        tail = audio[-pad:].astype(np.float32)
+    elif n < chunk_len:
+        pad = chunk_len - n
+        tail = audio.astype(np.float32)
+    if pad > 0:
+        noise = (np.sqrt(np.mean(tail * tail)) * rng.normal(loc=0.0, scale=1.0, size=(pad,))).astype(np.int16)
+        audio = np.concatenate((audio, noise))
+    return audio, stride, n

@@ -1,143 +1,9 @@
 // model.cu -- the native runtime behind vadx_create / vadx_set_tensor / vadx_forward: owns the
 // constants of one model, lays the caller's workspace out, and enqueues the kernel sequence of a
 // whole forward pass on the caller's stream (no host synchronisation, no allocation).
-#include <algorithm>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
-
-#include "common.cuh"
-
-namespace vadx {
-int linear_narrow(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias, float* d_y,
-                  int64_t n_rows, int n_in, int n_out, int act, int rows_per_group, int64_t group_stride,
-                  int64_t out_stride, cudaStream_t st);
-
-struct HostTensor {
-  std::vector<char> bytes;
-  std::vector<int64_t> dims;
-  int dtype = VADX_DT_F32;
-  int64_t numel() const {
-    int64_t n = 1;
-    for (auto d : dims) n *= d;
-    return n;
-  }
-  const float* f32() const { return reinterpret_cast<const float*>(bytes.data()); }
-};
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
-struct Workspace {  // bump allocator over the caller's buffer
-  char* base;
-  size_t cap, off = 0;
-  bool dry;  // only measure
-  Workspace(void* b, size_t c, bool d) : base((char*)b), cap(c), dry(d) {}
-  template <typename T>
-  T* take(int64_t n) {
-    size_t bytes = (size_t)round_up((int64_t)(n * sizeof(T)), 256);
-    char* p = dry ? nullptr : base + off;
-    off += bytes;
-    return reinterpret_cast<T*>(p);
-  }
-};
-
-}  // namespace vadx
-
-using namespace vadx;
-
-struct vadx_model {
-  std::string kind;
-  std::vector<int32_t> hp;
-  std::map<std::string, HostTensor> host;
-  std::map<std::string, double> scalars;
-  std::map<std::string, DevBuf> dev;  // derived, device-resident constants
-  bool finalized = false;
-
-  ~vadx_model() { release(); }
-  void release() {
-    for (auto& kv : dev)
-      if (kv.second.p) cudaFree(kv.second.p);
-    dev.clear();
-    finalized = false;
-  }
-  double scalar(const char* name, double dflt) const {
-    auto it = scalars.find(name);
-    return it == scalars.end() ? dflt : it->second;
-  }
-  const HostTensor* find(const std::string& n) const {
-    auto it = host.find(n);
-    return it == host.end() ? nullptr : &it->second;
-  }
-  int upload(const std::string& key, const void* src, size_t bytes) {
-    DevBuf b;
-    b.bytes = bytes;
-    cudaError_t e = cudaMalloc(&b.p, std::max<size_t>(bytes, 16));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(constant)");
-    e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-      cudaFree(b.p);
-      return cuda_fail(e, "cudaMemcpy(constant)");
-    }
-    auto it = dev.find(key);
-    if (it != dev.end() && it->second.p) cudaFree(it->second.p);
-    dev[key] = b;
-    return VADX_OK;
-  }
-  // [out][in](,1) host weight -> device [in][ldw] (ldw = out rounded up to 4, zero padded)
-  int upload_linear(const std::string& name, int n_out, int n_in) {
-    const HostTensor* t = find(name);
-    if (!t) {
-      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
-      return VADX_EMISSING;
-    }
-    if (t->dtype != VADX_DT_F32 || t->numel() != (int64_t)n_out * n_in) {
-      set_error("tensor '%s': expected %d x %d fp32, got %lld elements", name.c_str(), n_out, n_in,
-                (long long)t->numel());
-      return VADX_EINVAL;
-    }
-    int ldw = (int)round_up(n_out, 4);
-    std::vector<float> wt((size_t)n_in * ldw, 0.f);
-    const float* w = t->f32();
-    for (int o = 0; o < n_out; ++o)
-      for (int i = 0; i < n_in; ++i) wt[(size_t)i * ldw + o] = w[(size_t)o * n_in + i];
-    VADX_TRY(upload(name + "#T", wt.data(), wt.size() * sizeof(float)));
-    if (vadx_tc_supported(n_in, n_out)) {
-      size_t bytes = 0;
-      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, nullptr, 0, &bytes));
-      std::vector<uint8_t> img(bytes);
-      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, img.data(), img.size(), &bytes));
-      VADX_TRY(upload(name + "#TC", img.data(), img.size()));
-    }
-    return VADX_OK;
-  }
-  int upload_raw(const std::string& name, int64_t expect_numel, int dtype) {
-    const HostTensor* t = find(name);
-    if (!t) {
-      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
-      return VADX_EMISSING;
-    }
-    if (t->dtype != dtype || (expect_numel >= 0 && t->numel() != expect_numel)) {
-      set_error("tensor '%s': expected %lld elements of dtype %d, got %lld of dtype %d", name.c_str(),
-                (long long)expect_numel, dtype, (long long)t->numel(), t->dtype);
-      return VADX_EINVAL;
-    }
-    return upload(name, t->bytes.data(), t->bytes.size());
-  }
-  template <typename T>
-  const T* d(const std::string& key) const {
-    auto it = dev.find(key);
-    return it == dev.end() ? nullptr : reinterpret_cast<const T*>(it->second.p);
-  }
-  bool has(const std::string& n) const { return host.count(n) != 0; }
-};
+#include "model.hpp"
 
 // ------------------------------------------------------------------------------------------ FireRed
-namespace {
-
 struct FireRedHP {
   int idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win, hop, n_mels;
   int n_taps() const { return win < n_fft ? win : n_fft; }
@@ -147,7 +13,7 @@ struct FireRedHP {
   int frames(int64_t L) const { return L < n_taps() ? 0 : (int)(1 + (L - n_taps()) / hop); }
 };
 
-int firered_hp(const vadx_model* m, FireRedHP* h) {
+static int firered_hp(const vadx_model* m, FireRedHP* h) {
   VADX_REQUIRE(m->hp.size() == 14, "firered: expected 14 hyper-parameters, got %zu", m->hp.size());
   const int32_t* v = m->hp.data();
   *h = FireRedHP{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13]};
@@ -194,11 +60,25 @@ int firered_finalize(vadx_model* m) {
   return VADX_OK;
 }
 
-// lays out (dry = true) or runs the forward pass
-int firered_run(vadx_model* m, bool dry, const void* d_audio, float* d_probs, float* const* d_state_in,
-                int64_t S, int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+int firered_check(const vadx_model* m) {
+  FireRedHP h;
+  return firered_hp(m, &h);
+}
+int firered_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
   FireRedHP h;
   VADX_TRY(firered_hp(m, &h));
+  *out = h.frames(n_samples);
+  return VADX_OK;
+}
+
+// lays out (dry = true) or runs the forward pass
+int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+                int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+  FireRedHP h;
+  VADX_TRY(firered_hp(m, &h));
+  const void* d_audio = dry ? nullptr : in[0];
+  float* d_probs = dry ? nullptr : static_cast<float*>(out[0]);
+  (void)state;
   const int T = h.frames(L);
   VADX_REQUIRE(T >= 1, "firered: %lld samples are shorter than one %d-sample frame", (long long)L, h.n_taps());
   const int64_t rows = S * T;
@@ -218,7 +98,6 @@ int firered_run(vadx_model* m, bool dry, const void* d_audio, float* d_probs, fl
     set_error("firered: workspace of %zu bytes is smaller than the %zu needed", ws_bytes, ws.off);
     return VADX_ENOMEM;
   }
-  (void)d_state_in;
   const float preemph = (float)m->scalar("frontend.preemph", 0.97);
   const float floor_v = (float)m->scalar("frontend.log_floor", 1e-7);
   const HostTensor* melw = m->find("frontend.mel_w");
@@ -273,12 +152,31 @@ int firered_run(vadx_model* m, bool dry, const void* d_audio, float* d_probs, fl
   return VADX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ C ABI
+namespace {
+struct KindOps {
+  const char* name;
+  int (*check)(const vadx_model*);
+  int (*finalize)(vadx_model*);
+  int (*frames)(const vadx_model*, int64_t, int32_t*);
+  int (*run)(vadx_model*, bool, const void* const*, void* const*, void* const*, int64_t, int64_t, void*, size_t,
+             size_t*, cudaStream_t);
+};
+const KindOps kKinds[] = {
+    {"firered", firered_check, firered_finalize, firered_frames, firered_run},
+    {"fsmn", fsmn_check, fsmn_finalize, fsmn_frames, fsmn_run},
+};
+const KindOps* ops_of(const std::string& kind) {
+  for (const auto& k : kKinds)
+    if (kind == k.name) return &k;
+  return nullptr;
+}
 }  // namespace
 
-// ------------------------------------------------------------------------------------------ C ABI
 extern "C" int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out) {
   VADX_REQUIRE(kind && out && (n_hparams == 0 || hparams), "vadx_create: null pointer");
-  VADX_REQUIRE(!strcmp(kind, "firered"), "vadx_create: unknown model kind '%s'", kind);
+  const KindOps* ops = ops_of(kind);
+  VADX_REQUIRE(ops, "vadx_create: unknown model kind '%s'", kind);
   if (vadx_device_count() < 1) {
     set_error("vadx_create: no CUDA device is visible; libvadx has no CPU path");
     return VADX_ENODEVICE;
@@ -286,13 +184,10 @@ extern "C" int vadx_create(const char* kind, const int32_t* hparams, int n_hpara
   vadx_model* m = new vadx_model();
   m->kind = kind;
   m->hp.assign(hparams, hparams + n_hparams);
-  if (m->kind == "firered") {
-    FireRedHP h;
-    int rc = firered_hp(m, &h);
-    if (rc != VADX_OK) {
-      delete m;
-      return rc;
-    }
+  int rc = ops->check(m);
+  if (rc != VADX_OK) {
+    delete m;
+    return rc;
   }
   *out = m;
   return VADX_OK;
@@ -324,16 +219,13 @@ extern "C" int vadx_set_scalar(vadx_model* m, const char* name, double value) {
 
 extern "C" int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_frames) {
   VADX_REQUIRE(m && out_frames, "vadx_output_frames: null pointer");
-  FireRedHP h;
-  VADX_TRY(firered_hp(m, &h));
-  *out_frames = h.frames(n_samples);
-  return VADX_OK;
+  return ops_of(m->kind)->frames(m, n_samples, out_frames);
 }
 
 extern "C" int vadx_workspace_bytes(const vadx_model* m, int64_t n_streams, int64_t n_samples, size_t* out_bytes) {
   VADX_REQUIRE(m && out_bytes && n_streams >= 0 && n_samples >= 0, "vadx_workspace_bytes: bad argument");
-  return firered_run(const_cast<vadx_model*>(m), true, nullptr, nullptr, nullptr, n_streams, n_samples, nullptr, 0,
-                     out_bytes, nullptr);
+  return ops_of(m->kind)->run(const_cast<vadx_model*>(m), true, nullptr, nullptr, nullptr, n_streams, n_samples,
+                              nullptr, 0, out_bytes, nullptr);
 }
 
 extern "C" int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
@@ -343,13 +235,13 @@ extern "C" int vadx_forward(vadx_model* m, const void* const* d_inputs, void* co
   VADX_REQUIRE(n_streams >= 0 && n_samples > 0, "vadx_forward: bad shape S=%lld L=%lld", (long long)n_streams,
                (long long)n_samples);
   VADX_REQUIRE(d_workspace || workspace_bytes == 0, "vadx_forward: null workspace");
+  const KindOps* ops = ops_of(m->kind);
   if (!m->finalized) {
     m->release();
-    VADX_TRY(firered_finalize(m));
+    VADX_TRY(ops->finalize(m));
     m->finalized = true;
   }
   if (n_streams == 0) return VADX_OK;
-  (void)d_state;
-  return firered_run(m, false, d_inputs[0], (float*)d_outputs[0], nullptr, n_streams, n_samples, d_workspace,
-                     workspace_bytes, nullptr, (cudaStream_t)stream);
+  return ops->run(m, false, d_inputs, d_outputs, d_state, n_streams, n_samples, d_workspace, workspace_bytes, nullptr,
+                  (cudaStream_t)stream);
 }

@@ -1,0 +1,148 @@
+// model.hpp -- shared state of the native model runtime (model.cu, model_fsmn.cu, ...).
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vadx {
+int linear_narrow(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias, float* d_y,
+                  int64_t n_rows, int n_in, int n_out, int act, int rows_per_group, int64_t group_stride,
+                  int64_t out_stride, cudaStream_t st);
+
+struct HostTensor {
+  std::vector<char> bytes;
+  std::vector<int64_t> dims;
+  int dtype = VADX_DT_F32;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : dims) n *= d;
+    return n;
+  }
+  const float* f32() const { return reinterpret_cast<const float*>(bytes.data()); }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Workspace {  // bump allocator over the caller's buffer
+  char* base;
+  size_t cap, off = 0;
+  bool dry;  // only measure
+  Workspace(void* b, size_t c, bool d) : base((char*)b), cap(c), dry(d) {}
+  template <typename T>
+  T* take(int64_t n) {
+    size_t bytes = (size_t)round_up((int64_t)(n * sizeof(T)), 256);
+    char* p = dry ? nullptr : base + off;
+    off += bytes;
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+}  // namespace vadx
+
+using namespace vadx;
+
+struct vadx_model {
+  std::string kind;
+  std::vector<int32_t> hp;
+  std::map<std::string, HostTensor> host;
+  std::map<std::string, double> scalars;
+  std::map<std::string, DevBuf> dev;  // derived, device-resident constants
+  bool finalized = false;
+
+  ~vadx_model() { release(); }
+  void release() {
+    for (auto& kv : dev)
+      if (kv.second.p) cudaFree(kv.second.p);
+    dev.clear();
+    finalized = false;
+  }
+  double scalar(const char* name, double dflt) const {
+    auto it = scalars.find(name);
+    return it == scalars.end() ? dflt : it->second;
+  }
+  const HostTensor* find(const std::string& n) const {
+    auto it = host.find(n);
+    return it == host.end() ? nullptr : &it->second;
+  }
+    int upload(const std::string& key, const void* src, size_t bytes) {
+    DevBuf b;
+    b.bytes = bytes;
+    cudaError_t e = cudaMalloc(&b.p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(constant)");
+    e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(b.p);
+      return cuda_fail(e, "cudaMemcpy(constant)");
+    }
+    auto it = dev.find(key);
+    if (it != dev.end() && it->second.p) cudaFree(it->second.p);
+    dev[key] = b;
+    return VADX_OK;
+  }
+  // [out][in](,1) host weight -> device [in][ldw] (ldw = out rounded up to 4, zero padded)
+  int upload_linear(const std::string& name, int n_out, int n_in) {
+    const HostTensor* t = find(name);
+    if (!t) {
+      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
+      return VADX_EMISSING;
+    }
+    if (t->dtype != VADX_DT_F32 || t->numel() != (int64_t)n_out * n_in) {
+      set_error("tensor '%s': expected %d x %d fp32, got %lld elements", name.c_str(), n_out, n_in,
+                (long long)t->numel());
+      return VADX_EINVAL;
+    }
+    int ldw = (int)round_up(n_out, 4);
+    std::vector<float> wt((size_t)n_in * ldw, 0.f);
+    const float* w = t->f32();
+    for (int o = 0; o < n_out; ++o)
+      for (int i = 0; i < n_in; ++i) wt[(size_t)i * ldw + o] = w[(size_t)o * n_in + i];
+    VADX_TRY(upload(name + "#T", wt.data(), wt.size() * sizeof(float)));
+    if (vadx_tc_supported(n_in, n_out)) {
+      size_t bytes = 0;
+      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, nullptr, 0, &bytes));
+      std::vector<uint8_t> img(bytes);
+      VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, img.data(), img.size(), &bytes));
+      VADX_TRY(upload(name + "#TC", img.data(), img.size()));
+    }
+    return VADX_OK;
+  }
+  int upload_raw(const std::string& name, int64_t expect_numel, int dtype) {
+    const HostTensor* t = find(name);
+    if (!t) {
+      set_error("model '%s': tensor '%s' was never set", kind.c_str(), name.c_str());
+      return VADX_EMISSING;
+    }
+    if (t->dtype != dtype || (expect_numel >= 0 && t->numel() != expect_numel)) {
+      set_error("tensor '%s': expected %lld elements of dtype %d, got %lld of dtype %d", name.c_str(),
+                (long long)expect_numel, dtype, (long long)t->numel(), t->dtype);
+      return VADX_EINVAL;
+    }
+    return upload(name, t->bytes.data(), t->bytes.size());
+  }
+  template <typename T>
+  const T* d(const std::string& key) const {
+    auto it = dev.find(key);
+    return it == dev.end() ? nullptr : reinterpret_cast<const T*>(it->second.p);
+  }
+  bool has(const std::string& n) const { return host.count(n) != 0; }
+};
+
+
+// per-kind entry points
+int firered_check(const vadx_model* m);
+int firered_finalize(vadx_model* m);
+int firered_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
+int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+                int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);
+int fsmn_check(const vadx_model* m);
+int fsmn_finalize(vadx_model* m);
+int fsmn_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
+int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+             int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);

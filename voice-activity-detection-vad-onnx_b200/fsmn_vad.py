@@ -1,0 +1,123 @@
+"""FSMN-VAD entry point -- the B200 twin of FSMN/Inference_FSMN_VAD_ONNX.py: raw audio in, speech
+timestamps (seconds + sample indices) out, same two text files.
+
+Per chunk the reference calls the graph (:177-187), walks the look-ahead hysteresis in Python
+(:188-215) and updates the background level (:217-218).  Here all three run on the device for S
+streams in lock-step, the stream state (FSMN caches, silence flag, background level, decisions)
+never leaves HBM, and nothing synchronises with the host until the segments are read back.
+Config names and defaults follow the reference's module-level constants (:15-24).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import audio_io, postprocess as PP, weights as W
+from .session import FsmnSession
+
+SAMPLE_RATE = 16000
+ONE_MINUS_SPEECH_THRESHOLD = 1.0
+SNR_THRESHOLD = 10.0
+BACKGROUND_NOISE_dB_INIT = 30.0
+FUSION_THRESHOLD = 0.3
+MIN_SPEECH_DURATION = 0.2
+SPEAKING_SCORE = 0.5
+SILENCE_SCORE = 0.5
+LOOK_BACKWARD = 0.3
+OUTPUT_FRAME_LENGTH = 160
+
+
+@dataclass
+class FsmnResult:
+    timestamps: list
+    saved: np.ndarray            # bool per emitted frame, True = silence (the reference's `saved`)
+    lines_second: list
+    lines_indices: list
+    p_silence: list              # per chunk [T] (debug / parity)
+    power_dB: list
+    noise_avg_in: list
+
+
+def look_backward_frames(look_backward_s: float) -> int:
+    return int(look_backward_s * SAMPLE_RATE // OUTPUT_FRAME_LENGTH)
+
+
+def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: float = LOOK_BACKWARD,
+                one_minus_speech_threshold: float = ONE_MINUS_SPEECH_THRESHOLD, snr_threshold_db: float = SNR_THRESHOLD,
+                noise_init_db: float = BACKGROUND_NOISE_dB_INIT, speaking_score: float = SPEAKING_SCORE,
+                silence_score: float = SILENCE_SCORE, keep_trace: bool = False, stream=None):
+    """aligned: CUDA int16 [S, n] (already chunk-aligned, see audio_io.align_overlapping).
+    -> (HysteresisState, trace) with every decision of every stream on the device."""
+    import torch
+    S, n = aligned.shape
+    L, T = session.chunk_len, session.T
+    lb = look_backward_frames(look_backward_s)
+    n_windows = (n - L) // stride + 1
+    state = PP.HysteresisState(S, n_windows * (T - lb) + lb, aligned.device,
+                               noise_init=float(np.float32(noise_init_db + snr_threshold_db) * np.float32(0.1)))
+    caches = session.new_caches(S, aligned.device)
+    snr = snr_threshold_db * 0.1
+    trace = []
+    for wdx in range(n_windows):
+        s0 = wdx * stride
+        chunk = aligned[:, s0:s0 + L].contiguous()
+        noise_in = state.noise_avg.clone() if keep_trace else None
+        score, caches, noisy, p_sil, power = session.run_batch(chunk, caches, state.noise_avg,
+                                                               one_minus_speech_threshold, stream)
+        PP.lookahead_hysteresis(score, state, lb, speaking_score, silence_score, is_final=(wdx == n_windows - 1),
+                                noisy_dB=noisy, snr_threshold=snr, stream=stream)
+        if keep_trace:
+            trace.append((score, p_sil, power, noise_in, noisy))
+    return state, trace
+
+
+def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD, rng=None,
+            save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None,
+            fusion_threshold: float = FUSION_THRESHOLD, min_speech_duration: float = MIN_SPEECH_DURATION,
+            normalize: bool = True, keep_trace: bool = False) -> FsmnResult:
+    """One stream, the reference's behaviour: `audio` is a wav path or an int16/float array."""
+    import torch
+    if isinstance(audio, str):
+        audio = audio_io.load_wav_int16(audio, SAMPLE_RATE)
+    a16 = audio_io.normalize_to_int16(np.asarray(audio, np.float32)) if normalize else np.asarray(audio, np.int16)
+    lb = look_backward_frames(look_backward_s)
+    aligned, stride, _n = audio_io.align_overlapping(a16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
+    d = torch.from_numpy(aligned).cuda().unsqueeze(0)
+    state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace)
+    cnt, seg = state.segments()
+    n_flags = int(state.n_saved[0].item())
+    pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
+    frame_d = OUTPUT_FRAME_LENGTH / SAMPLE_RATE
+    ts = PP.process_timestamps(PP.runs_to_timestamps(pairs, n_flags, frame_d), fusion_threshold, min_speech_duration)
+    sec, idx = PP.timestamp_lines(ts, SAMPLE_RATE)
+    if save_timestamps_second and save_timestamps_indices:
+        PP.write_timestamp_files(ts, save_timestamps_second, save_timestamps_indices, SAMPLE_RATE)
+    saved = state.saved[0, :n_flags].cpu().numpy().astype(bool)
+    return FsmnResult(ts, saved, sec, idx, [t[1][0].cpu().numpy() for t in trace],
+                      [t[2][0].cpu().numpy() for t in trace], [float(t[3][0]) for t in trace])
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="FSMN-VAD on B200 (random-init weights unless --weights is given)")
+    ap.add_argument("audio")
+    ap.add_argument("--weights", help=".npz with the FunASR encoder state_dict + cmvn_means/cmvn_vars")
+    ap.add_argument("--chunk", type=int, default=16000)
+    ap.add_argument("--look-backward", type=float, default=LOOK_BACKWARD)
+    ap.add_argument("--out-second", default="./timestamps_second.txt")
+    ap.add_argument("--out-indices", default="./timestamps_indices.txt")
+    a = ap.parse_args(argv)
+    cfg = W.FsmnConfig()
+    w = dict(np.load(a.weights)) if a.weights else W.fsmn_random_init(cfg, 0)
+    sess = FsmnSession(w, cfg, chunk_len=a.chunk)
+    r = run_vad(a.audio, sess, a.look_backward, save_timestamps_second=a.out_second,
+                save_timestamps_indices=a.out_indices)
+    print("\nTimestamps in Second:")
+    print("".join(r.lines_second), end="")
+    print("\nTimestamps in Indices:")
+    print("".join(r.lines_indices), end="")
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,13 @@ SIGNATURES = {
     "vadx_linear_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_fsmn_memory_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64,
                                        _i32, _i32, _vp, _vp, _vp]),
+    "vadx_lfr_cmvn_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "vadx_softmax_class0_f32": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "vadx_frame_energy_log10_f32": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
+    "vadx_fsmn_gate": (C.c_int, [_vp, _vp, _vp, _f32, _f32, _i64, _i32, _vp, _vp, _vp]),
+    "vadx_lookahead_hysteresis": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _i32, C.c_double, C.c_double, _i32, _vp, _vp,
+                                            _vp, _i64, _vp, _vp, _f32, _vp]),
+    "vadx_runs_to_segments": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
     "vadx_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
     "vadx_destroy": (None, [_vp]),

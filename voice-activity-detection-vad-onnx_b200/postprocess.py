@@ -80,6 +80,74 @@ def segments_to_seconds(pairs: np.ndarray, n_frames: int, cfg: FramePostConfig, 
     return [(round(a, 3), round(b, 3)) for a, b in seg.tolist()]
 
 
+def lookahead_hysteresis(values, state, look_backward: int, speaking_score: float, silence_score: float,
+                         is_final: bool, noisy_dB=None, snr_threshold: float = 1.0, stream=None):
+    """One chunk of the FSMN / DFSMN look-ahead state machine for S streams, on the device.
+    values: CUDA uint8 [S,T] flags (FSMN) or fp32 [S,T] probabilities (DFSMN).
+    state: HysteresisState (updated in place)."""
+    import torch
+    mode = 0 if values.dtype == torch.uint8 else 1
+    if values.dtype not in (torch.uint8, torch.float32) or values.dim() != 2 or values.stride(1) != 1:
+        raise ValueError("lookahead_hysteresis: values must be CUDA uint8/fp32 [S, T] with contiguous rows")
+    S, T = values.shape
+    lib.check(lib.load().vadx_lookahead_hysteresis(
+        values.data_ptr(), mode, values.stride(0), S, T, int(look_backward), float(speaking_score),
+        float(silence_score), 1 if is_final else 0, state.silence.data_ptr(), state.n_saved.data_ptr(),
+        state.saved.data_ptr(), state.saved.shape[1], lib.ptr(state.noise_avg) if noisy_dB is not None else None,
+        lib.ptr(noisy_dB), float(snr_threshold), lib.stream_ptr(stream)))
+
+
+class HysteresisState:
+    """Device-resident per-stream state of the look-ahead machine: current silence flag, number of
+    decisions emitted, the decisions themselves (1 = silence) and the running background level."""
+
+    def __init__(self, n_streams: int, capacity: int, device, noise_init: float = 4.0):
+        import torch
+        self.silence = torch.ones((n_streams,), dtype=torch.uint8, device=device)
+        self.n_saved = torch.zeros((n_streams,), dtype=torch.int32, device=device)
+        self.saved = torch.zeros((n_streams, capacity), dtype=torch.uint8, device=device)
+        self.noise_avg = torch.full((n_streams,), float(np.float32(noise_init)), dtype=torch.float32, device=device)
+
+    def segments(self, max_segments: int | None = None, stream=None):
+        """-> (seg_count int32 [S], segments int32 [S, max, 2]) frame pairs (start, end-exclusive)."""
+        import torch
+        S, cap = self.saved.shape
+        max_segments = max_segments or cap // 2 + 1
+        cnt = torch.empty((S,), dtype=torch.int32, device=self.saved.device)
+        seg = torch.empty((S, max_segments, 2), dtype=torch.int32, device=self.saved.device)
+        lib.check(lib.load().vadx_runs_to_segments(self.saved.data_ptr(), cap, self.n_saved.data_ptr(), S,
+                                                   cnt.data_ptr(), seg.data_ptr(), max_segments,
+                                                   lib.stream_ptr(stream)))
+        return cnt, seg
+
+
+def runs_to_timestamps(pairs, n_flags: int, frame_duration: float):
+    """frame pairs of one stream -> [(start_s, end_s)] in Python floats, exactly like vad_to_timestamps
+    (FSMN/Inference_FSMN_VAD_ONNX.py:124-141): a run closed by a silence frame i ends at
+    i*d + d, a run still open at the end of the stream ends at n*d."""
+    out = []
+    for a, b in np.asarray(pairs, np.int64).reshape(-1, 2).tolist():
+        start = a * frame_duration
+        end = b * frame_duration + frame_duration if b < n_flags else n_flags * frame_duration
+        out.append((start, end))
+    return out
+
+
+def process_timestamps(timestamps, fusion_threshold: float = 1.0, min_duration: float = 0.5):
+    """Drop short segments, then fuse neighbours closer than the threshold -- two passes, like the
+    reference (FSMN/Inference_FSMN_VAD_ONNX.py:102-122)."""
+    cur = [(a, b) for a, b in timestamps if (b - a) >= min_duration]
+    for _ in range(2):
+        nxt = []
+        for a, b in cur:
+            if nxt and (a - nxt[-1][1] <= fusion_threshold):
+                nxt[-1] = (nxt[-1][0], b)
+            else:
+                nxt.append((a, b))
+        cur = nxt
+    return cur
+
+
 def format_time(seconds: float) -> str:
     """hh:mm:ss.mmm with truncated milliseconds (FSMN/Inference_FSMN_VAD_ONNX.py:144-153)."""
     td = timedelta(seconds=seconds)

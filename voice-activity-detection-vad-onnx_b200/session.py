@@ -181,8 +181,133 @@ class FireRedSession:
         return out
 
 
+class FsmnSession:
+    """FunASR FSMN-VAD session.
+
+    I/O contract of the reference graph (FSMN/Export_FSMN_VAD.py:122-134), static audio length L:
+      inputs : audio int16 (1,1,L); cache_0..3 fp32 (1,128,19,1); one_minus_speech_threshold fp32 (1,);
+               noise_average_dB fp32 (1,)
+      outputs: score uint8 (T,), T = L//160 + 1; cache_0..3 (new); noisy_dB fp32 ()
+    `run` keeps that contract (numpy, one stream); `run_batch` is the device-resident S-stream form
+    that also returns P(silence) and power_dB (the quantities the uint8 score is thresholded from).
+    """
+    INPUT_NAMES = ["audio", "cache_0", "cache_1", "cache_2", "cache_3", "one_minus_speech_threshold",
+                   "noise_average_dB"]
+    OUTPUT_NAMES = ["score", "cache_0_out", "cache_1_out", "cache_2_out", "cache_3_out", "noisy_dB"]
+
+    def __init__(self, weights: dict, cfg: W.FsmnConfig = W.FsmnConfig(), chunk_len: int = 16000,
+                 tensor_cores: bool = True):
+        self.cfg, self.chunk_len = cfg, int(chunk_len)
+        if self.chunk_len < cfg.n_fft:
+            raise ValueError(f"FsmnSession: chunk_len {chunk_len} is shorter than the {cfg.n_fft}-sample energy frame")
+        hp = [cfg.input_dim, cfg.input_affine_dim, cfg.fsmn_layers, cfg.linear_dim, cfg.proj_dim, cfg.lorder,
+              cfg.rorder, cfg.lstride, cfg.rstride, cfg.output_affine_dim, cfg.output_dim, cfg.n_fft, cfg.win_length,
+              cfg.hop, cfg.n_mels, cfg.lfr_m, cfg.lfr_n]
+        self._e = _Engine("fsmn", hp)
+        basis, _first, _ = tables.interleaved_basis(cfg.n_fft, cfg.win_length, cfg.window, "v1")
+        bank = constants.torchaudio_mel_bank(cfg.n_fft // 2 + 1, 20.0, 8000.0, cfg.n_mels, 16000, None, "htk").numpy()
+        st, ln, w = tables.sparse_bank(bank)
+        self._e.set_tensor("frontend.basis", basis)
+        self._e.set_tensor("frontend.mel_start", st)
+        self._e.set_tensor("frontend.mel_len", ln)
+        self._e.set_tensor("frontend.mel_w", w)
+        self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
+        self._e.set_scalar("frontend.log_floor", cfg.log_floor)
+        self._e.set_scalar("speech_2_noise_ratio", cfg.speech_2_noise_ratio)
+        self._e.set_scalar("one_minus_speech_threshold", 1.0)
+        self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
+        spec = W.fsmn_spec(cfg)
+        for name in spec:
+            if name not in weights:
+                raise KeyError(f"FsmnSession: weight '{name}' missing from the state dict")
+            a = np.asarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(spec[name]):
+                raise ValueError(f"FsmnSession: '{name}' has shape {a.shape}, expected {spec[name]}")
+            self._e.set_tensor(name, a)
+        self.T = self._e.output_frames(self.chunk_len)
+        self.cache_shape = (cfg.proj_dim, (cfg.lorder - 1) * cfg.lstride)
+        cs = [1, cfg.proj_dim, (cfg.lorder - 1) * cfg.lstride, 1]
+        self._inputs_meta = [NodeArg("audio", [1, 1, self.chunk_len], "tensor(int16)")]
+        self._inputs_meta += [NodeArg(f"cache_{i}", cs, "tensor(float)") for i in range(cfg.fsmn_layers)]
+        self._inputs_meta += [NodeArg("one_minus_speech_threshold", [1], "tensor(float)"),
+                              NodeArg("noise_average_dB", [1], "tensor(float)")]
+        self._outputs_meta = [NodeArg("score", [self.T], "tensor(uint8)")]
+        self._outputs_meta += [NodeArg(f"cache_{i}_out", cs, "tensor(float)") for i in range(cfg.fsmn_layers)]
+        self._outputs_meta += [NodeArg("noisy_dB", [], "tensor(float)")]
+        self._thr = 1.0
+
+    def get_inputs(self):
+        return list(self._inputs_meta)
+
+    def get_outputs(self):
+        return list(self._outputs_meta)
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
+
+    def new_caches(self, n_streams: int, device):
+        import torch
+        return [torch.zeros((n_streams,) + self.cache_shape, dtype=torch.float32, device=device)
+                for _ in range(self.cfg.fsmn_layers)]
+
+    def run_batch(self, audio, caches, noise_average_dB, one_minus_speech_threshold: float = 1.0, stream=None):
+        """audio cuda int16 [S, L]; caches: list of cuda fp32 [S,128,19]; noise_average_dB cuda fp32 [S].
+        -> (score u8 [S,T], new_caches, noisy_dB [S], p_silence [S,T], power_dB [S,T]); asynchronous."""
+        import torch
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2
+                and audio.is_contiguous()):
+            raise ValueError("run_batch: audio must be a contiguous CUDA int16 tensor [S, L]")
+        S, L = audio.shape
+        if L != self.chunk_len:
+            raise ValueError(f"InvalidArgument: audio length {L} != static axis {self.chunk_len}")
+        n = self.cfg.fsmn_layers
+        if len(caches) != n or any(tuple(c.shape) != (S,) + self.cache_shape or c.dtype != torch.float32
+                                   or not c.is_cuda or not c.is_contiguous() for c in caches):
+            raise ValueError(f"InvalidArgument: expected {n} contiguous CUDA fp32 caches of shape {(S,) + self.cache_shape}")
+        if tuple(noise_average_dB.shape) != (S,) or noise_average_dB.dtype != torch.float32:
+            raise ValueError("InvalidArgument: noise_average_dB must be fp32 [S]")
+        if float(one_minus_speech_threshold) != self._thr:
+            self._thr = float(one_minus_speech_threshold)
+            self._e.set_scalar("one_minus_speech_threshold", self._thr)
+        dev = audio.device
+        score = torch.empty((S, self.T), dtype=torch.uint8, device=dev)
+        noisy = torch.empty((S,), dtype=torch.float32, device=dev)
+        p_sil = torch.empty((S, self.T), dtype=torch.float32, device=dev)
+        power = torch.empty((S, self.T), dtype=torch.float32, device=dev)
+        new = [torch.empty_like(c) for c in caches]
+        self._e.forward([audio, noise_average_dB], [score, noisy, p_sil, power], list(caches) + new, S, L, stream)
+        return score, new, noisy, p_sil, power
+
+    def run(self, output_names, input_feed: dict):
+        import torch
+        names = [o.name for o in self._outputs_meta]
+        if output_names is not None and any(n not in names for n in output_names):
+            raise ValueError(f"InvalidArgument: unknown output name in {output_names}")
+        if set(input_feed) != set(self.INPUT_NAMES[:1] + [f"cache_{i}" for i in range(self.cfg.fsmn_layers)]
+                                  + self.INPUT_NAMES[-2:]):
+            raise ValueError(f"InvalidArgument: inputs must be {self.INPUT_NAMES}, got {sorted(input_feed)}")
+        a = input_feed["audio"]
+        if not isinstance(a, np.ndarray) or a.dtype != np.int16 or a.shape != (1, 1, self.chunk_len):
+            raise ValueError(f"InvalidArgument: 'audio' must be int16 of shape (1, 1, {self.chunk_len})")
+        caches = []
+        for i in range(self.cfg.fsmn_layers):
+            c = np.asarray(input_feed[f"cache_{i}"])
+            if c.dtype != np.float32 or c.shape != (1,) + self.cache_shape + (1,):
+                raise ValueError(f"InvalidArgument: 'cache_{i}' must be fp32 of shape {(1,) + self.cache_shape + (1,)}")
+            caches.append(torch.from_numpy(np.ascontiguousarray(c[..., 0])).cuda())
+        thr = float(np.asarray(input_feed["one_minus_speech_threshold"], np.float32).reshape(-1)[0])
+        noise = torch.from_numpy(np.asarray(input_feed["noise_average_dB"], np.float32).reshape(1)).cuda()
+        score, new, noisy, _, _ = self.run_batch(torch.from_numpy(a[0]).cuda(), caches, noise, thr)
+        outs = [score[0].cpu().numpy()] + [c.cpu().numpy()[..., None] for c in new] + [noisy[0].cpu().numpy()]
+        if output_names is None:
+            return outs
+        return [outs[names.index(n)] for n in output_names]
+
+
 def InferenceSession(kind: str, weights: dict, config=None, **kw):
     """Factory with the reference's constructor name; `kind` replaces the .onnx path."""
     if kind == "firered":
         return FireRedSession(weights, config or W.FireRedConfig(), **kw)
+    if kind == "fsmn":
+        return FsmnSession(weights, config or W.FsmnConfig(), **kw)
     raise ValueError(f"unknown model kind {kind!r}")

@@ -115,3 +115,72 @@ def firered_random_init(cfg: FireRedConfig = FireRedConfig(), seed: int = 0):
     w["out.weight"] = (w["out.weight"] * 0.3).astype(np.float32)
     w["out.bias"] = (w["out.bias"] + 2.9).astype(np.float32)
     return w
+
+
+# ----------------------------------------------------------------------------- FSMN (FunASR)
+@dataclasses.dataclass(frozen=True)
+class FsmnConfig:
+    """FunASR `speech_fsmn_vad_zh-cn-16k-common` encoder hyper-parameters.  Only proj_dim=128 and
+    lorder=20 are pinned by the reference (cache shape (1,128,19,1), FSMN/Export_FSMN_VAD.py:116);
+    the others follow the public FunASR config."""
+    input_dim: int = 400
+    input_affine_dim: int = 140
+    fsmn_layers: int = 4
+    linear_dim: int = 250
+    proj_dim: int = 128
+    lorder: int = 20
+    rorder: int = 0
+    lstride: int = 1
+    rstride: int = 1
+    output_affine_dim: int = 140
+    output_dim: int = 248
+    # frontend (FSMN/Export_FSMN_VAD.py:24-34)
+    n_fft: int = 512
+    win_length: int = 400
+    hop: int = 160
+    n_mels: int = 80
+    window: str = "hamming"
+    pre_emphasis: float = 0.97
+    log_floor: float = 1e-5
+    lfr_m: int = 5
+    lfr_n: int = 1
+    speech_2_noise_ratio: float = 1.0
+
+
+def fsmn_spec(cfg: FsmnConfig) -> "OrderedDict[str, tuple]":
+    """state_dict keys of FSMN/modeling_modified/encoder.py:159-217 plus the frontend CMVN
+    (`cmvn_means` / `cmvn_vars`, FSMN/Export_FSMN_VAD.py:109-110)."""
+    s: OrderedDict[str, tuple] = OrderedDict()
+    s["in_linear1.linear.weight"] = (cfg.input_affine_dim, cfg.input_dim)
+    s["in_linear1.linear.bias"] = (cfg.input_affine_dim,)
+    s["in_linear2.linear.weight"] = (cfg.linear_dim, cfg.input_affine_dim)
+    s["in_linear2.linear.bias"] = (cfg.linear_dim,)
+    for i in range(cfg.fsmn_layers):
+        p = f"fsmn.{i}."
+        s[p + "linear.linear.weight"] = (cfg.proj_dim, cfg.linear_dim)
+        s[p + "fsmn_block.conv_left.weight"] = (cfg.proj_dim, 1, cfg.lorder, 1)
+        s[p + "affine.linear.weight"] = (cfg.linear_dim, cfg.proj_dim)
+        s[p + "affine.linear.bias"] = (cfg.linear_dim,)
+    s["out_linear1.linear.weight"] = (cfg.output_affine_dim, cfg.linear_dim)
+    s["out_linear1.linear.bias"] = (cfg.output_affine_dim,)
+    s["out_linear2.linear.weight"] = (cfg.output_dim, cfg.output_affine_dim)
+    s["out_linear2.linear.bias"] = (cfg.output_dim,)
+    s["cmvn_means"] = (cfg.n_mels * cfg.lfr_m,)
+    s["cmvn_vars"] = (cfg.n_mels * cfg.lfr_m,)
+    return s
+
+
+def fsmn_random_init(cfg: FsmnConfig = FsmnConfig(), seed: int = 0):
+    """Seeded random weights; CMVN typical of log-mel of peak-normalised int16 audio; the silence
+    class (index 0) of the softmax head is boosted so that 2*P(silence) straddles the default
+    threshold 1.0 and the look-ahead state machine switches."""
+    rs = np.random.RandomState(seed)
+    spec = fsmn_spec(cfg)
+    net = OrderedDict((k, v) for k, v in spec.items() if not k.startswith("cmvn"))
+    w = _default_init(rs, net)
+    d = cfg.n_mels * cfg.lfr_m
+    w["cmvn_means"] = (-rs.uniform(12.0, 17.0, size=(d,))).astype(np.float32)
+    w["cmvn_vars"] = rs.uniform(0.25, 0.45, size=(d,)).astype(np.float32)
+    w["out_linear2.linear.weight"][0] *= 4.0
+    w["out_linear2.linear.bias"][0] += np.float32(np.log(cfg.output_dim - 1.0))
+    return w
