@@ -43,7 +43,10 @@ enum {
 };
 
 enum { VADX_DT_I16 = 0, VADX_DT_F32 = 1, VADX_DT_I32 = 2 };
-enum { VADX_ACT_NONE = 0, VADX_ACT_RELU = 1, VADX_ACT_SIGMOID = 2 };
+/* activation codes; OR VADX_ACT_RES_FIRST in to add the residual BEFORE the activation
+ * (JasperBlock: relu(conv + residual)) instead of after it (DFSMN: act(conv) + residual).
+ * VADX_ACT_SOFTMAX is only valid for narrow heads (n_out <= 8): softmax across the n_out outputs. */
+enum { VADX_ACT_NONE = 0, VADX_ACT_RELU = 1, VADX_ACT_SIGMOID = 2, VADX_ACT_SOFTMAX = 3, VADX_ACT_RES_FIRST = 16 };
 enum { VADX_FLOOR_CLAMP = 0, VADX_FLOOR_ADD = 1 };
 /* pre-emphasis flavours: NONE; ZERO_HISTORY: y[0]=x[0]-c*0 (pad(1,0)+conv[-c,1],
  * FireRedVAD/Export_FireRedVAD.py:440, NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:245-246);
@@ -125,6 +128,12 @@ int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const 
                        const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
                        int n_out, int act, void* stream);
 
+/* a12 -- depthwise conv1d over time on time-major activations [S][T_in][C] (MarbleNet / Jasper separable
+ * blocks): y[s][t][c] = sum_j w[c][j] * x[s][t*stride - pad + j*dilation][c], zeros outside [0, T_in). */
+int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const float* d_w, int kernel, int stride, int dilation,
+                              int pad, float* d_y, int64_t ldy, int64_t n_streams, int t_in, int t_out,
+                              int n_channels, void* stream);
+
 /* a5/a6/a7 -- FSMN / DFSMN memory block on time-major activations [S][T][C]:
  *   out[t] = p[t] + sum_k wl[c][k] * p[t - (n_back-1-k)*stride_back]
  *                 + sum_k wr[c][k] * p[t + (k+1)*stride_ahead]        (only when T > 1)
@@ -199,12 +208,17 @@ int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_
  * ------------------------------------------------------------------------------------------ */
 typedef struct vadx_model vadx_model;
 
-/* kind: "firered" | "fsmn".  `hparams` is a flat int32 array, meaning per kind:
+/* kind: "firered" | "fsmn" | "marblenet".  `hparams` is a flat int32 array, meaning per kind:
  *   firered: {idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win_length, hop, n_mels}
  *            (DetectModel args, FireRedVAD/Export_FireRedVAD.py:310-316, frontend :38-49)
  *   fsmn:    {input_dim, input_affine_dim, fsmn_layers, linear_dim, proj_dim, lorder, rorder, lstride, rstride,
  *             output_affine_dim, output_dim, n_fft, win_length, hop, n_mels, lfr_m, lfr_n}
- *            (FunASR FSMN encoder, FSMN/modeling_modified/encoder.py:159-206; frontend FSMN/Export_FSMN_VAD.py:24-34) */
+ *            (FunASR FSMN encoder, FSMN/modeling_modified/encoder.py:159-206; frontend FSMN/Export_FSMN_VAD.py:24-34)
+ *   marblenet: {feat_in, n_blocks, [filters, repeat, kernel, stride, dilation, residual] x n_blocks,
+ *             num_classes, n_fft, win_length, hop, n_mels}; tensors are the BN-FOLDED layers
+ *             "b{i}.r{j}.dw" [C][k], "b{i}.r{j}.pw" [out][in], "b{i}.r{j}.pw_bias", "b{i}.res", "b{i}.res_bias",
+ *             "decoder.weight", "decoder.bias" (folding: NVIDIA_Frame_VAD_Multilingual_MarbleNet/
+ *             Export_NVIDIA_MarbleNet_VAD.py:58-151) */
 int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out);
 void vadx_destroy(vadx_model* m);
 
@@ -229,7 +243,10 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
  *            outputs = {score uint8 [S][T], noisy_dB fp32 [S], P(silence) fp32 [S][T] or NULL,
  *                       power_dB fp32 [S][T] or NULL}
  *            state   = {cache_0..3 in, cache_0..3 out}, each fp32 [S][128][19], distinct buffers
- *            (FSMN/Export_FSMN_VAD.py:122-134); thresholds are scalars set with vadx_set_scalar. */
+ *            (FSMN/Export_FSMN_VAD.py:122-134); thresholds are scalars set with vadx_set_scalar.
+ *   marblenet: inputs = {audio int16 [S][L]}; outputs = {score_silence fp32 [S][T'], score_active fp32 [S][T']}
+ *            with T' = vadx_output_frames(L); the reference's signal_len output is T' - 1
+ *            (NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:444-457). */
 int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
                  int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
                  void* stream);

@@ -247,7 +247,91 @@ def gen_fsmn():
     np.savez_compressed(os.path.join(GOLD, "fsmn.npz"), **out)
 
 
-GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn}
+# ------------------------------------------------------------------------------ MarbleNet
+def marblenet_reference(cfg, weights, optimized=True):
+    """The reference's OWN wrapper (+ its own BatchNorm folding) around the NeMo-shaped stand-in
+    (oracle/marblenet.py) carrying our seeded weights."""
+    from oracle import marblenet as OM
+    stft = RL.import_file("NVIDIA_Frame_VAD_Multilingual_MarbleNet/STFT_Process.py", "STFT_Process")
+    ns = RL.extract("NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py",
+                    {"STFT_Process": stft.STFT_Process})
+    custom_stft = stft.STFT_Process(model_type='stft_B', n_fft=cfg.n_fft, hop_len=cfg.hop, win_length=cfg.win_length,
+                                    max_frames=0, window_type=cfg.window, center_pad=True, pad_mode='constant').eval()
+    net = OM.StandIn(cfg, weights)
+    cls = ns["NVIDIA_VAD_Optimized"] if optimized else ns["NVIDIA_VAD_Reference"]
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = cls(net, custom_stft, cfg.n_fft, cfg.n_mels, 16000, cfg.pre_emphasis, 16000).eval()
+    return m
+
+
+def marblenet_fake_session(cfg, weights):
+    from oracle import ref_runner as RR
+    m = marblenet_reference(cfg, weights, optimized=True)
+    ins = [RR.NodeArg("audio", [1, 1, "audio_len"], "tensor(int16)")]
+    outs = [RR.NodeArg("score_silence", [1, "signal_len", 1], "tensor(float)"),
+            RR.NodeArg("score_active", [1, "signal_len", 1], "tensor(float)"),
+            RR.NodeArg("signal_len", [1], "tensor(int32)")]
+
+    def fn(feed):
+        with torch.inference_mode():
+            r = m(torch.from_numpy(feed["audio"]))
+        return [np.asarray(t.numpy()) for t in r]
+
+    return RR.FakeSession(ins, outs, fn)
+
+
+def gen_marblenet():
+    import random
+    import vadx  # noqa: F401
+    from vadx import audio_io, synth, weights as W
+    from oracle import ref_runner as RR
+
+    cfg = W.MarbleNetConfig()
+    w = W.marblenet_random_init(cfg, 0)
+    out = {}
+    # (1) the reference's own validation recipe (seed 1234, randint(-32768, 32767), three lengths)
+    ref_m = marblenet_reference(cfg, w, optimized=False)
+    opt_m = marblenet_reference(cfg, w, optimized=True)
+    random.seed(1234); np.random.seed(1234); torch.manual_seed(1234)
+    for L in (16000, 48000, 160000):
+        a = torch.randint(-32768, 32767, (1, 1, L), dtype=torch.int16)
+        with torch.inference_mode():
+            rs, ra, rl = ref_m(a)
+            os_, oa, ol = opt_m(a)
+        assert int(rl) == int(ol)
+        print(f"recipe L={L}: ref-vs-optimized max err {float((ra - oa).abs().max()):.2e}, signal_len {int(ol)}")
+        out[f"recipe{L}_audio"] = a.numpy()[0, 0]
+        out[f"recipe{L}_active"] = oa.numpy()[0, :, 0]
+        out[f"recipe{L}_silence"] = os_.numpy()[0, :, 0]
+        out[f"recipe{L}_active_unfolded"] = ra.numpy()[0, :, 0]
+        out[f"recipe{L}_signal_len"] = np.array(int(ol))
+    # (2) enveloped synthetic clips (the bench workload shape, shortened)
+    clips = synth.synth_streams(3, 10 * 16000, seed=1234)
+    with torch.inference_mode():
+        out["synth_active"] = np.stack([opt_m(torch.from_numpy(c).view(1, 1, -1))[1].numpy()[0, :, 0] for c in clips])
+    # (3) the unmodified inference script on vad_sample.wav
+    wav = os.path.join(RL.REF_ROOT, "NVIDIA_Frame_VAD_Multilingual_MarbleNet", "vad_sample.wav")
+    box = {}
+
+    def factory(_p):
+        box["s"] = marblenet_fake_session(cfg, w)
+        return box["s"]
+
+    ns, files = RR.run_script("NVIDIA_Frame_VAD_Multilingual_MarbleNet/Inference_NVIDIA_MarbleNet_VAD_ONNX.py", factory,
+                              lambda p, sr: audio_io.load_wav_int16(os.path.realpath(p), sr), seed=1234,
+                              files_to_link={"vad_sample.wav": wav})
+    out["sample_probs"] = np.asarray(ns["all_vad_probs"], np.float32)
+    out["sample_decisions"] = np.asarray(ns["vad_decisions"], np.int8)
+    out["sample_timestamps"] = np.array(ns["timestamps"], np.float64).reshape(-1, 2)
+    out["sample_file_second"] = np.array(files["timestamps_second.txt"])
+    out["sample_file_indices"] = np.array(files["timestamps_indices.txt"])
+    print("vad_sample:", out["sample_probs"].shape, out["sample_timestamps"].tolist())
+    np.savez_compressed(os.path.join(GOLD, "marblenet.npz"), **out)
+
+
+GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+              "marblenet": gen_marblenet}
 
 
 def main(argv):

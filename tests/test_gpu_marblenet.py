@@ -1,0 +1,98 @@
+"""MarbleNet on the GPU through the C ABI against the golden record of the reference's wrapper and
+against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vadx
+from vadx import lib, marblenet_vad, postprocess as PP, synth, weights as W
+from oracle import postproc as OP
+from oracle.marblenet import MarbleNetOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "marblenet.npz"))
+
+
+@pytest.fixture(scope="module")
+def session(cuda):
+    cfg = W.MarbleNetConfig()
+    return vadx.MarbleNetSession(W.marblenet_random_init(cfg, 0), cfg)
+
+
+@pytest.mark.parametrize("T,C,k,stride,dil", [(601, 80, 11, 2, 1), (300, 64, 13, 1, 1), (300, 64, 29, 1, 2),
+                                              (50, 128, 1, 1, 1), (33, 128, 17, 1, 1)])
+def test_depthwise_conv(cuda, T, C, k, stride, dil):
+    S = 3
+    g = torch.Generator().manual_seed(T + k)
+    x = torch.randn((S, T, C), generator=g)
+    w = torch.randn((C, k), generator=g)
+    pad = (dil * (k - 1)) // 2
+    ref = F.conv1d(x.permute(0, 2, 1), w.unsqueeze(1), stride=stride, padding=pad, dilation=dil, groups=C).permute(0, 2, 1)
+    t_out = ref.shape[1]
+    y = torch.empty((S, t_out, C), device=cuda)
+    xd, wd = x.to(cuda), w.to(cuda)
+    lib.check(lib.load().vadx_depthwise_conv1d_f32(xd.data_ptr(), C, wd.data_ptr(), k, stride, dil, pad, y.data_ptr(), C,
+                                                   S, T, t_out, C, lib.stream_ptr()))
+    assert (y.cpu() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("L", [16000, 48000, 160000])
+def test_reference_recipe_through_run(gold, session, L):
+    a = gold[f"recipe{L}_audio"].reshape(1, 1, -1)
+    names = [o.name for o in session.get_outputs()]
+    assert names == ["score_silence", "score_active", "signal_len"]
+    sil, act, n = session.run(names, {session.get_inputs()[0].name: a})
+    assert act.shape == (1, L // 320 + 1, 1) and n.dtype == np.int32 and int(n[0]) == int(gold[f"recipe{L}_signal_len"])
+    err = max(np.abs(act[0, :, 0] - gold[f"recipe{L}_active"]).max(), np.abs(sil[0, :, 0] - gold[f"recipe{L}_silence"]).max())
+    print(f"recipe L={L}: max abs err {err:.2e}")
+    assert err <= TOL
+
+
+def test_synthetic_clips_batched_tc_and_simt(cuda, gold):
+    cfg = W.MarbleNetConfig()
+    w = W.marblenet_random_init(cfg, 0)
+    clips = torch.from_numpy(synth.synth_streams(3, 160000, seed=1234)).to(cuda)
+    for tc in (True, False):
+        sc = vadx.MarbleNetSession(w, cfg, tensor_cores=tc).run_batch(clips).cpu().numpy()
+        err = np.abs(sc[1] - gold["synth_active"]).max()
+        print(f"synthetic clips, tensor_cores={tc}: max abs err {err:.2e}")
+        assert err <= TOL
+        assert np.abs(sc[0] + sc[1] - 1.0).max() <= 1e-5
+
+
+def test_vad_sample_timestamps(cuda, gold, golden_dir, session, tmp_path):
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    f1, f2 = str(tmp_path / "s.txt"), str(tmp_path / "i.txt")
+    r = marblenet_vad.run_vad(audio, session, save_timestamps_second=f1, save_timestamps_indices=f2)
+    assert r.probs.shape == gold["sample_probs"].shape
+    assert np.abs(r.probs - gold["sample_probs"]).max() <= TOL
+    sm = OP.smooth_probs(gold["sample_probs"], 3)
+    if np.abs(sm - np.float32(0.5)).min() > TOL:
+        assert np.array_equal(r.decisions, gold["sample_decisions"])
+        assert np.array_equal(np.array(r.timestamps, np.float64).reshape(-1, 2), gold["sample_timestamps"])
+        assert open(f1).read() == str(gold["sample_file_second"]) and open(f2).read() == str(gold["sample_file_indices"])
+
+
+def test_long_clips_batch_against_oracle(cuda, session):
+    """60 s clips (the BASELINE config-3 shape, small batch): 3000 valid frames each."""
+    cfg = W.MarbleNetConfig()
+    clips = synth.synth_streams(4, 960000, seed=8)
+    probs, dec, cnt, seg = marblenet_vad.run_vad_clips(session, torch.from_numpy(clips).to(cuda))
+    assert probs.shape == (4, 3000)
+    _, act, n = MarbleNetOracle(W.marblenet_random_init(cfg, 0), cfg).forward(clips)
+    assert n == 3000
+    err = np.abs(probs.cpu().numpy() - act.numpy()[:, :3000, 0]).max()
+    print(f"60 s clips: max abs err {err:.2e}")
+    assert err <= TOL
+    p = probs.cpu().numpy()
+    for s in range(4):
+        ref = OP.frame_decisions(p[s], 3, 0.5, 10, 1000, 10, 3, 0)
+        assert np.array_equal(dec[s].cpu().numpy(), ref)

@@ -54,6 +54,7 @@ __device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (
 __device__ __forceinline__ int64_t min_i64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
+  act &= 15;
   if (act == VADX_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == VADX_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
   return v;

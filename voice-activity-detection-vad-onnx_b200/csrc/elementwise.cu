@@ -334,3 +334,69 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
   }
   return VADX_OK;
 }
+
+// ------------------------------------------------------------------------------------------ a12
+// Depthwise conv1d over time (Jasper separable blocks), time-major.  One CTA = one stream x a tile of
+// kDwT output frames x all channels; input rows incl. halo and the transposed taps are staged in
+// shared memory, consecutive threads own consecutive channels.
+namespace vadx {
+constexpr int kDwT = 32;
+__global__ void __launch_bounds__(256) depthwise_conv1d_kernel(const float* __restrict__ x, int64_t ldx,
+                                                               const float* __restrict__ w, int K, int stride,
+                                                               int dil, int pad, float* __restrict__ y, int64_t ldy,
+                                                               int t_in, int t_out, int C) {
+  extern __shared__ float sm[];
+  const int rows_in = (kDwT - 1) * stride + (K - 1) * dil + 1;
+  float* tile = sm;                        // [rows_in][C]
+  float* ws = tile + (size_t)rows_in * C;  // [K][C]
+  const int64_t s = blockIdx.y;
+  const int o0 = blockIdx.x * kDwT;
+  const int i0 = o0 * stride - pad;
+  const float* xs = x + s * (int64_t)t_in * ldx;
+  for (int i = threadIdx.x; i < rows_in * C; i += blockDim.x) {
+    int r = i / C, c = i - r * C;
+    int t = i0 + r;
+    tile[i] = (t >= 0 && t < t_in) ? xs[(int64_t)t * ldx + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    int k = i / C, c = i - k * C;
+    ws[i] = w[c * K + k];
+  }
+  __syncthreads();
+  const int n_out = min(kDwT, t_out - o0);
+  for (int i = threadIdx.x; i < n_out * C; i += blockDim.x) {
+    int tt = i / C, c = i - tt * C;
+    const float* src = tile + (size_t)(tt * stride) * C + c;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(ws[k * C + c], src[(size_t)k * dil * C], acc);
+    y[(s * (int64_t)t_out + o0 + tt) * ldy + c] = acc;
+  }
+}
+}  // namespace vadx
+
+extern "C" int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const float* d_w, int kernel, int stride,
+                                         int dilation, int pad, float* d_y, int64_t ldy, int64_t n_streams, int t_in,
+                                         int t_out, int n_channels, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  VADX_REQUIRE(d_x && d_w && d_y && d_x != d_y, "vadx_depthwise_conv1d_f32: null or aliased pointer");
+  VADX_REQUIRE(kernel >= 1 && stride >= 1 && dilation >= 1 && pad >= 0 && n_streams >= 0 && t_in >= 1 && t_out >= 1 &&
+                   n_channels >= 1 && ldx >= n_channels && ldy >= n_channels,
+               "vadx_depthwise_conv1d_f32: bad shape");
+  VADX_REQUIRE((int64_t)(t_out - 1) * stride - pad + (int64_t)(kernel - 1) * dilation < t_in + pad + dilation * kernel,
+               "vadx_depthwise_conv1d_f32: t_out inconsistent with t_in");
+  VADX_REQUIRE(n_streams <= 65535, "vadx_depthwise_conv1d_f32: at most 65535 streams per call");
+  if (n_streams == 0) return VADX_OK;
+  const int rows_in = (kDwT - 1) * stride + (kernel - 1) * dilation + 1;
+  size_t smem = ((size_t)rows_in + kernel) * n_channels * sizeof(float);
+  VADX_REQUIRE(smem <= 200 * 1024, "vadx_depthwise_conv1d_f32: tile of %zu bytes exceeds shared memory", smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(depthwise_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(depthwise_conv1d_kernel)");
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(t_out, kDwT), (unsigned)n_streams);
+  depthwise_conv1d_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, ldx, d_w, kernel, stride, dilation, pad, d_y,
+                                                                     ldy, t_in, t_out, n_channels);
+  return after_launch("vadx_depthwise_conv1d_f32");
+}

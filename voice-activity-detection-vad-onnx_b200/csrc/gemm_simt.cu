@@ -182,8 +182,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_f32_kernel(const GemmArgs g)
           for (int j = 0; j < 4; ++j)
             if (col + j < g.N) v[j] += g.bias[col + j];
         }
+        const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
+        if (!res_first) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
+          for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
+        }
         if (g.res) {
           const float* r = g.res + row * g.ldr + col;
           if (full && g.vec_store) {
@@ -194,6 +197,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_f32_kernel(const GemmArgs g)
             for (int j = 0; j < 4; ++j)
               if (col + j < g.N) v[j] += r[j];
           }
+        }
+        if (res_first) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
         }
         float* out = g.C + row * g.ldc + col;
         if (full && g.vec_store) {
@@ -243,9 +250,22 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const float* __restr
     if (lane == 0) {
       int64_t grp = row / rows_per_group;
       int64_t within = row - grp * rows_per_group;
-      for (int o = 0; o < N; ++o) {
-        float v = acc[o] + (bias ? bias[o] : 0.f);
-        Y[grp * group_stride + o * out_stride + within] = apply_act(v, act);
+      if (act == VADX_ACT_SOFTMAX) {
+        float mx = -INFINITY, sum = 0.f;
+        for (int o = 0; o < N; ++o) {
+          acc[o] += bias ? bias[o] : 0.f;
+          mx = fmaxf(mx, acc[o]);
+        }
+        for (int o = 0; o < N; ++o) {
+          acc[o] = expf(acc[o] - mx);
+          sum += acc[o];
+        }
+        for (int o = 0; o < N; ++o) Y[grp * group_stride + o * out_stride + within] = acc[o] / sum;
+      } else {
+        for (int o = 0; o < N; ++o) {
+          float v = acc[o] + (bias ? bias[o] : 0.f);
+          Y[grp * group_stride + o * out_stride + within] = apply_act(v, act);
+        }
       }
     }
   }

@@ -284,25 +284,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
         float v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         if (!row_ok || c0 >= g.N) continue;
+        const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + bias_s[c0 + j], g.act);
+        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+        if (!res_first) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act);
+        }
         float* out = g.Y + row * g.ldy + c0;
         const float* rs = g.res ? g.res + row * g.ldr + c0 : nullptr;
-        if (g.vec_y && c0 + 15 < g.N) {
-          if (rs) {
+        const bool vec = g.vec_y && c0 + 15 < g.N;
+        if (rs) {
+          if (vec) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 r4 = __ldg(reinterpret_cast<const float4*>(rs) + j);
               v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < g.N) v[j] += rs[j];
           }
+        }
+        if (res_first) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act);
+        }
+        if (vec) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < g.N) out[j] = v[j] + (rs ? rs[j] : 0.f);
+            if (c0 + j < g.N) out[j] = v[j];
         }
       }
       tc_fence_before();

@@ -1,0 +1,177 @@
+// model_marblenet.cu -- NVIDIA Frame-VAD MarbleNet graph (wrapper:
+// NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:222-275; the Jasper encoder
+// itself is NeMo code that the reference does not vendor -- see oracle/marblenet.py) as a kernel
+// sequence: prep -> framed DFT + power -> slaney mel + log -> [depthwise conv -> pointwise GEMM
+// (+folded BN bias, +residual, ReLU)]* -> 2-class softmax head.
+#include "model.hpp"
+
+extern "C" int vadx_depthwise_conv1d_f32(const float*, int64_t, const float*, int, int, int, int, float*, int64_t,
+                                         int64_t, int, int, int, void*);
+
+namespace {
+struct Block {
+  int filters, repeat, kernel, stride, dilation, residual;
+};
+struct MarbleHP {
+  int feat_in;
+  std::vector<Block> blocks;
+  int n_classes, n_fft, win, hop, n_mels;
+  int n_taps() const { return win < n_fft ? win : n_fft; }
+  int first_tap() const { return win < n_fft ? (n_fft - win) / 2 : 0; }
+  int n_bins() const { return n_fft / 2 + 1; }
+  int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
+  int ld_power() const { return (int)round_up(n_bins(), 2); }
+  int pad_left() const { return n_fft / 2 - first_tap(); }
+  int stft_frames(int64_t L) const { return (int)(L / hop + 1); }
+  static int conv_len(int t, int k, int stride, int dil) {
+    int pad = (dil * (k - 1)) / 2;
+    return (t + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  }
+  int out_frames(int64_t L) const {
+    int t = stft_frames(L);
+    for (const auto& b : blocks)
+      for (int r = 0; r < b.repeat; ++r) t = conv_len(t, b.kernel, b.stride, b.dilation);
+    return t;
+  }
+  int max_channels() const {
+    int c = feat_in;
+    for (const auto& b : blocks) c = std::max(c, b.filters);
+    return c;
+  }
+};
+
+int marble_hp(const vadx_model* m, MarbleHP* h) {
+  const auto& v = m->hp;
+  VADX_REQUIRE(v.size() >= 2 && (int)v.size() == 2 + 6 * v[1] + 5, "marblenet: malformed hyper-parameter list (%zu)",
+               v.size());
+  h->feat_in = v[0];
+  h->blocks.clear();
+  for (int b = 0; b < v[1]; ++b) {
+    const int32_t* p = &v[2 + 6 * b];
+    h->blocks.push_back(Block{p[0], p[1], p[2], p[3], p[4], p[5]});
+    VADX_REQUIRE(p[0] >= 1 && p[1] >= 1 && p[2] >= 1 && p[3] >= 1 && p[4] >= 1, "marblenet: block %d out of range", b);
+    VADX_REQUIRE(p[3] == 1 || p[1] == 1, "marblenet: a strided block must have repeat == 1");
+  }
+  const int32_t* t = &v[2 + 6 * v[1]];
+  h->n_classes = t[0]; h->n_fft = t[1]; h->win = t[2]; h->hop = t[3]; h->n_mels = t[4];
+  VADX_REQUIRE(h->n_classes >= 2 && h->n_classes <= 8 && h->feat_in == h->n_mels, "marblenet: head/frontend mismatch");
+  return VADX_OK;
+}
+}  // namespace
+
+int marblenet_check(const vadx_model* m) {
+  MarbleHP h;
+  return marble_hp(m, &h);
+}
+int marblenet_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
+  MarbleHP h;
+  VADX_TRY(marble_hp(m, &h));
+  *out = h.out_frames(n_samples);
+  return VADX_OK;
+}
+
+int marblenet_finalize(vadx_model* m) {
+  MarbleHP h;
+  VADX_TRY(marble_hp(m, &h));
+  VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
+  VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
+  int c_in = h.feat_in;
+  for (size_t b = 0; b < h.blocks.size(); ++b) {
+    const Block& k = h.blocks[b];
+    int c = c_in;
+    for (int r = 0; r < k.repeat; ++r) {
+      std::string p = "b" + std::to_string(b) + ".r" + std::to_string(r) + ".";
+      VADX_TRY(m->upload_raw(p + "dw", (int64_t)c * k.kernel, VADX_DT_F32));
+      VADX_TRY(m->upload_linear(p + "pw", k.filters, c));
+      VADX_TRY(m->upload_raw(p + "pw_bias", k.filters, VADX_DT_F32));
+      c = k.filters;
+    }
+    if (k.residual) {
+      std::string p = "b" + std::to_string(b) + ".";
+      VADX_TRY(m->upload_linear(p + "res", k.filters, c_in));
+      VADX_TRY(m->upload_raw(p + "res_bias", k.filters, VADX_DT_F32));
+    }
+    c_in = k.filters;
+  }
+  VADX_TRY(m->upload_linear("decoder.weight", h.n_classes, c_in));
+  VADX_TRY(m->upload_raw("decoder.bias", h.n_classes, VADX_DT_F32));
+  return VADX_OK;
+}
+
+int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+                  int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+  (void)state;
+  MarbleHP h;
+  VADX_TRY(marble_hp(m, &h));
+  const int T0 = h.stft_frames(L);
+  const int Tout = h.out_frames(L);
+  const int64_t rows0 = S * T0;
+  const int64_t Lp = round_up(h.pad_left() + L + h.n_taps(), 4);
+  const int maxc = h.max_channels();
+  Workspace ws(ws_ptr, ws_bytes, dry);
+  float* sig = ws.take<float>(S * Lp);
+  float* power = ws.take<float>(rows0 * h.ld_power());
+  float* B[5];  // roles: 0 block input, 1 depthwise out, 2/3 pointwise ping-pong, 4 residual branch
+  for (auto& b : B) b = ws.take<float>(rows0 * maxc);
+  if (need) *need = ws.off;
+  if (dry) return VADX_OK;
+  if (ws.off > ws_bytes) {
+    set_error("marblenet: workspace of %zu bytes is smaller than the %zu needed", ws_bytes, ws.off);
+    return VADX_ENOMEM;
+  }
+  VADX_REQUIRE(out[1], "marblenet: outputs are {score_silence, score_active}");
+  VADX_REQUIRE((char*)out[1] == (char*)out[0] + (size_t)S * Tout * sizeof(float),
+               "marblenet: score_active must directly follow score_silence ([2][S][T'] planes)");
+  const float preemph = (float)m->scalar("frontend.preemph", 0.97);
+  const float eps = (float)m->scalar("frontend.log_eps", 1e-7);
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
+
+  VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 0,
+                           preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0, preemph, h.pad_left(), sig, Lp, st));
+  VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T0, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                               h.n_bins(), power, h.ld_power(), st));
+  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows0, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
+                            m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_ADD, eps,
+                            B[0], h.n_mels, st));
+  auto lin = [&](const float* a, int n_in, const std::string& w, const std::string& b, const float* res, float* y,
+                 int n_out, int64_t rows, int act) -> int {
+    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
+    if (img) return vadx_linear_tc_f32(a, n_in, img, m->d<float>(b), res, n_out, y, n_out, rows, n_in, n_out, act, st);
+    return vadx_linear_f32(a, n_in, m->d<float>(w + "#T"), (int)round_up(n_out, 4), m->d<float>(b), res, n_out, y, n_out,
+                           rows, n_in, n_out, act, st);
+  };
+  int c_in = h.feat_in, t = T0;
+  for (size_t bi = 0; bi < h.blocks.size(); ++bi) {
+    const Block& k = h.blocks[bi];
+    const std::string bp = "b" + std::to_string(bi) + ".";
+    if (k.residual)
+      VADX_TRY(lin(B[0], c_in, bp + "res", bp + "res_bias", nullptr, B[4], k.filters, S * (int64_t)t, VADX_ACT_NONE));
+    const float* cur = B[0];
+    int c = c_in, out_slot = 2;
+    for (int rep = 0; rep < k.repeat; ++rep) {
+      const std::string p = bp + "r" + std::to_string(rep) + ".";
+      const int pad = (k.dilation * (k.kernel - 1)) / 2;
+      const int t_next = MarbleHP::conv_len(t, k.kernel, k.stride, k.dilation);
+      VADX_TRY(vadx_depthwise_conv1d_f32(cur, c, m->d<float>(p + "dw"), k.kernel, k.stride, k.dilation, pad, B[1], c, S,
+                                         t, t_next, c, st));
+      t = t_next;
+      out_slot = 2 + (rep & 1);
+      const bool last = rep == k.repeat - 1;
+      const bool add_res = last && k.residual;
+      VADX_TRY(lin(B[1], c, p + "pw", p + "pw_bias", add_res ? B[4] : nullptr, B[out_slot], k.filters, S * (int64_t)t,
+                   VADX_ACT_RELU | (add_res ? VADX_ACT_RES_FIRST : 0)));
+      cur = B[out_slot];
+      c = k.filters;
+    }
+    std::swap(B[0], B[out_slot]);  // the block output becomes the next block's input
+    c_in = k.filters;
+  }
+  VADX_REQUIRE(t == Tout, "marblenet: internal frame-count mismatch (%d vs %d)", t, Tout);
+  // head: [S*T'][C] -> softmax -> planes [2][S*T']
+  return linear_narrow(B[0], c_in, m->d<float>("decoder.weight#T"), (int)round_up(h.n_classes, 4),
+                       m->d<float>("decoder.bias"), static_cast<float*>(out[0]), S * (int64_t)t, c_in, h.n_classes,
+                       VADX_ACT_SOFTMAX, (int)std::min<int64_t>(S * (int64_t)t, 0x7fffffff), 0, S * (int64_t)t, st);
+}

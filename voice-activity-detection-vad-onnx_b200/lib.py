@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvadx.so")
 
 DT_I16, DT_F32, DT_I32 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTMAX, ACT_RES_FIRST = 0, 1, 2, 3, 16
 FLOOR_CLAMP, FLOOR_ADD = 0, 1
 PREEMPH_NONE, PREEMPH_ZERO_HISTORY, PREEMPH_KEEP_FIRST = 0, 1, 2
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "vadx_tc_supported": (C.c_int, [_i32, _i32]),
     "vadx_pack_weight_tc": (C.c_int, [_vp, _i32, _i32, _vp, _sz, C.POINTER(_sz)]),
     "vadx_linear_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "vadx_depthwise_conv1d_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_fsmn_memory_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64,
                                        _i32, _i32, _vp, _vp, _vp]),
     "vadx_lfr_cmvn_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),

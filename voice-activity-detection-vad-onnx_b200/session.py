@@ -304,10 +304,107 @@ class FsmnSession:
         return [outs[names.index(n)] for n in output_names]
 
 
+class MarbleNetSession:
+    """NVIDIA Frame-VAD MarbleNet session.
+
+    I/O contract of the reference graph (NVIDIA_Frame_VAD_Multilingual_MarbleNet/
+    Export_NVIDIA_MarbleNet_VAD.py:444-457), dynamic audio axis:
+      audio int16 (1,1,L) -> score_silence, score_active fp32 (1,T',1); signal_len int32 (1,) = T' - 1.
+    `weights` is the NeMo state dict (un-folded); BatchNorm is folded on the host exactly like the
+    reference's fold_bn_into_conv1d (:58-101).
+    """
+    MAX_STREAMS_PER_CALL = 32768
+
+    def __init__(self, weights: dict, cfg: W.MarbleNetConfig = W.MarbleNetConfig(), tensor_cores: bool = True):
+        self.cfg = cfg
+        hp = [cfg.feat_in, len(cfg.blocks)]
+        for b in cfg.blocks:
+            if not b.separable:
+                raise ValueError("MarbleNetSession: only separable Jasper blocks are supported")
+            hp += [b.filters, b.repeat, b.kernel, b.stride, b.dilation, 1 if b.residual else 0]
+        hp += [cfg.num_classes, cfg.n_fft, cfg.win_length, cfg.hop, cfg.n_mels]
+        self._e = _Engine("marblenet", hp)
+        basis, _first, _ = tables.interleaved_basis(cfg.n_fft, cfg.win_length, cfg.window, "v2")
+        bank = constants.torchaudio_mel_bank(cfg.n_fft // 2 + 1, 0.0, 8000.0, cfg.n_mels, 16000, "slaney", "slaney").numpy()
+        st, ln, w = tables.sparse_bank(bank)
+        self._e.set_tensor("frontend.basis", basis)
+        self._e.set_tensor("frontend.mel_start", st)
+        self._e.set_tensor("frontend.mel_len", ln)
+        self._e.set_tensor("frontend.mel_w", w)
+        self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
+        self._e.set_scalar("frontend.log_eps", cfg.log_eps)
+        self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
+        spec = W.marblenet_spec(cfg)
+        for name in spec:
+            if name not in weights:
+                raise KeyError(f"MarbleNetSession: weight '{name}' missing from the state dict")
+            if tuple(np.shape(weights[name])) != tuple(spec[name]):
+                raise ValueError(f"MarbleNetSession: '{name}' has shape {np.shape(weights[name])}, expected {spec[name]}")
+        for name, arr in W.marblenet_fold(cfg, {k: np.asarray(v, np.float32) for k, v in weights.items()}).items():
+            self._e.set_tensor(name, np.asarray(arr, np.float32))
+        self._inputs_meta = [NodeArg("audio", [1, 1, "audio_len"], "tensor(int16)")]
+        self._outputs_meta = [NodeArg("score_silence", [1, "signal_len", 1], "tensor(float)"),
+                              NodeArg("score_active", [1, "signal_len", 1], "tensor(float)"),
+                              NodeArg("signal_len", [1], "tensor(int32)")]
+
+    def get_inputs(self):
+        return list(self._inputs_meta)
+
+    def get_outputs(self):
+        return list(self._outputs_meta)
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
+
+    def frames(self, n_samples: int) -> int:
+        """T' = frames emitted; the graph's `signal_len` output is T' - 1."""
+        return self._e.output_frames(n_samples)
+
+    def run_batch(self, audio, stream=None):
+        """audio cuda int16 [S, L] -> scores cuda fp32 [2, S, T'] (plane 0 silence, plane 1 active)."""
+        import torch
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2
+                and audio.is_contiguous()):
+            raise ValueError("run_batch: audio must be a contiguous CUDA int16 tensor [S, L]")
+        S, L = audio.shape
+        if L < 1:
+            raise ValueError("InvalidArgument: empty audio")
+        T = self.frames(L)
+        out = torch.empty((2, S, T), dtype=torch.float32, device=audio.device)
+        step = self.MAX_STREAMS_PER_CALL
+        if S <= step:
+            self._e.forward([audio], [out[0], out[1]], [], S, L, stream)
+            return out
+        for s0 in range(0, S, step):
+            s1 = min(S, s0 + step)
+            part = torch.empty((2, s1 - s0, T), dtype=torch.float32, device=audio.device)
+            self._e.forward([audio[s0:s1]], [part[0], part[1]], [], s1 - s0, L, stream)
+            out[:, s0:s1] = part
+        return out
+
+    def run(self, output_names, input_feed: dict):
+        import torch
+        names = [o.name for o in self._outputs_meta]
+        if output_names is not None and any(n not in names for n in output_names):
+            raise ValueError(f"InvalidArgument: unknown output name in {output_names}")
+        if set(input_feed) != {"audio"}:
+            raise ValueError(f"InvalidArgument: expected exactly the input 'audio', got {sorted(input_feed)}")
+        a = input_feed["audio"]
+        if not isinstance(a, np.ndarray) or a.dtype != np.int16 or a.ndim != 3 or a.shape[1] != 1:
+            raise ValueError("InvalidArgument: 'audio' must be a numpy int16 array of shape (S, 1, L)")
+        sc = self.run_batch(torch.from_numpy(np.ascontiguousarray(a[:, 0, :])).cuda()).cpu().numpy()
+        outs = [sc[0][..., None], sc[1][..., None], np.full((a.shape[0],), sc.shape[2] - 1, np.int32)]
+        if output_names is None:
+            return outs
+        return [outs[names.index(n)] for n in output_names]
+
+
 def InferenceSession(kind: str, weights: dict, config=None, **kw):
     """Factory with the reference's constructor name; `kind` replaces the .onnx path."""
     if kind == "firered":
         return FireRedSession(weights, config or W.FireRedConfig(), **kw)
     if kind == "fsmn":
         return FsmnSession(weights, config or W.FsmnConfig(), **kw)
+    if kind == "marblenet":
+        return MarbleNetSession(weights, config or W.MarbleNetConfig(), **kw)
     raise ValueError(f"unknown model kind {kind!r}")

@@ -184,3 +184,135 @@ def fsmn_random_init(cfg: FsmnConfig = FsmnConfig(), seed: int = 0):
     w["out_linear2.linear.weight"][0] *= 4.0
     w["out_linear2.linear.bias"][0] += np.float32(np.log(cfg.output_dim - 1.0))
     return w
+
+
+# ----------------------------------------------------------------------------- MarbleNet (NeMo)
+@dataclasses.dataclass(frozen=True)
+class JasperBlockCfg:
+    filters: int
+    repeat: int
+    kernel: int
+    stride: int = 1
+    dilation: int = 1
+    residual: bool = False
+    separable: bool = True
+
+
+@dataclasses.dataclass(frozen=True)
+class MarbleNetConfig:
+    """NVIDIA Frame-VAD Multilingual MarbleNet v2.0.  The encoder/decoder live in nemo_toolkit, which
+    is NOT part of the reference checkout; this is the public `marblenet_3x2x64_20ms` layout
+     -- a declared assumption, parity for the network arithmetic is unpinned."""
+    feat_in: int = 80
+    blocks: tuple = (
+        JasperBlockCfg(128, 1, 11, stride=2),
+        JasperBlockCfg(64, 2, 13, residual=True),
+        JasperBlockCfg(64, 2, 15, residual=True),
+        JasperBlockCfg(64, 2, 17, residual=True),
+        JasperBlockCfg(128, 1, 29, dilation=2),
+        JasperBlockCfg(128, 1, 1),
+    )
+    num_classes: int = 2
+    bn_eps: float = 1e-3
+    # frontend (NVIDIA_*/Export_NVIDIA_MarbleNet_VAD.py:25-47)
+    n_fft: int = 512
+    win_length: int = 400
+    hop: int = 160
+    n_mels: int = 80
+    window: str = "hann_sym"
+    pre_emphasis: float = 0.97
+    log_eps: float = 1e-7
+
+
+def marblenet_spec(cfg: MarbleNetConfig) -> "OrderedDict[str, tuple]":
+    """NeMo state_dict keys (un-folded): encoder.encoder.{b}.mconv.{i}.conv.weight for MaskedConv1d,
+    .mconv.{i}.{weight,bias,running_mean,running_var} for BatchNorm1d, .res.0.{0,1} for the residual
+    1x1 conv + BN, decoder.layer0.{weight,bias}."""
+    s: OrderedDict[str, tuple] = OrderedDict()
+    c_in = cfg.feat_in
+    for b, blk in enumerate(cfg.blocks):
+        pre = f"encoder.encoder.{b}."
+        idx, cin_r = 0, c_in
+        for r in range(blk.repeat):
+            stride_r = blk.stride if r == 0 else 1  # NeMo applies the stride in every repeat; repeat==1 where stride>1
+            del stride_r
+            if blk.separable:
+                s[pre + f"mconv.{idx}.conv.weight"] = (cin_r, 1, blk.kernel)
+                s[pre + f"mconv.{idx + 1}.conv.weight"] = (blk.filters, cin_r, 1)
+                bn = idx + 2
+            else:
+                s[pre + f"mconv.{idx}.conv.weight"] = (blk.filters, cin_r, blk.kernel)
+                bn = idx + 1
+            for p in ("weight", "bias", "running_mean", "running_var"):
+                s[pre + f"mconv.{bn}.{p}"] = (blk.filters,)
+            idx = bn + 1
+            if r < blk.repeat - 1:
+                idx += 2  # ReLU + Dropout between repeats
+            cin_r = blk.filters
+        if blk.residual:
+            s[pre + "res.0.0.conv.weight"] = (blk.filters, c_in, 1)
+            for p in ("weight", "bias", "running_mean", "running_var"):
+                s[pre + f"res.0.1.{p}"] = (blk.filters,)
+        c_in = blk.filters
+    s["decoder.layer0.weight"] = (cfg.num_classes, c_in)
+    s["decoder.layer0.bias"] = (cfg.num_classes,)
+    return s
+
+
+def marblenet_random_init(cfg: MarbleNetConfig = MarbleNetConfig(), seed: int = 0):
+    """Seeded random weights with non-trivial BatchNorm statistics (so that folding matters)."""
+    rs = np.random.RandomState(seed)
+    w: OrderedDict[str, np.ndarray] = OrderedDict()
+    for name, shape in marblenet_spec(cfg).items():
+        if name.endswith("running_var"):
+            w[name] = rs.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif name.endswith("running_mean"):
+            w[name] = rs.uniform(-0.3, 0.3, size=shape).astype(np.float32)
+        elif name.endswith(".bias") and len(shape) == 1 and "decoder" not in name:
+            w[name] = rs.uniform(-0.2, 0.2, size=shape).astype(np.float32)
+        elif len(shape) == 1 and "decoder" not in name:          # BN gamma
+            w[name] = rs.uniform(0.8, 1.2, size=shape).astype(np.float32)
+        elif len(shape) == 1:
+            w[name] = rs.uniform(-0.1, 0.1, size=shape).astype(np.float32)
+        else:
+            w[name] = _uniform(rs, shape, np.sqrt(3.0 / _fan_in(shape)))
+    # calibrated offline (default layout): centres logit(active) - logit(silence) on the burst/gap mix
+    w["decoder.layer0.bias"] = (w["decoder.layer0.bias"] + np.array([3.6, -3.6], np.float32)[:cfg.num_classes]).astype(np.float32)
+    return w
+
+
+def marblenet_fold(cfg: MarbleNetConfig, w: dict) -> "OrderedDict[str, np.ndarray]":
+    """BatchNorm folding exactly as fold_bn_into_conv1d does it
+    (NVIDIA_*/Export_NVIDIA_MarbleNet_VAD.py:58-101): scale = gamma * rsqrt(var + eps) goes into the
+    conv that precedes the BN (the pointwise conv of a separable pair), bias = -mean*scale + beta.
+    Returns per layer: dw (depthwise [C,k]) / pw ([out,in]) / pw_bias, res / res_bias, decoder."""
+    import torch
+    out: OrderedDict[str, np.ndarray] = OrderedDict()
+    c_in = cfg.feat_in
+
+    def fold(conv_w, pre):
+        g, b = torch.from_numpy(w[pre + "weight"]), torch.from_numpy(w[pre + "bias"])
+        mu, var = torch.from_numpy(w[pre + "running_mean"]), torch.from_numpy(w[pre + "running_var"])
+        scale = g * torch.rsqrt(var + cfg.bn_eps)
+        nw = torch.from_numpy(conv_w) * scale.reshape(-1, 1, 1)
+        nb = (-mu) * scale + b
+        return nw.numpy(), nb.numpy()
+
+    for bi, blk in enumerate(cfg.blocks):
+        pre = f"encoder.encoder.{bi}."
+        idx = 0
+        for r in range(blk.repeat):
+            if not blk.separable:
+                raise NotImplementedError("non-separable Jasper blocks")
+            out[f"b{bi}.r{r}.dw"] = w[pre + f"mconv.{idx}.conv.weight"][:, 0, :].copy()
+            pw, pb = fold(w[pre + f"mconv.{idx + 1}.conv.weight"], pre + f"mconv.{idx + 2}.")
+            out[f"b{bi}.r{r}.pw"], out[f"b{bi}.r{r}.pw_bias"] = pw[:, :, 0].copy(), pb
+            idx += 3 + (2 if r < blk.repeat - 1 else 0)
+        if blk.residual:
+            rw, rb = fold(w[pre + "res.0.0.conv.weight"], pre + "res.0.1.")
+            out[f"b{bi}.res"], out[f"b{bi}.res_bias"] = rw[:, :, 0].copy(), rb
+        c_in = blk.filters
+    out["decoder.weight"] = w["decoder.layer0.weight"]
+    out["decoder.bias"] = w["decoder.layer0.bias"]
+    del c_in
+    return out
