@@ -185,6 +185,26 @@ int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_in, int64_t
 int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags, int64_t n_streams,
                           int32_t* d_seg_count, int32_t* d_segments, int max_segments, void* stream);
 
+/* a11 helpers (Silero): right reflect padding of each row (out[s][n_in + j] = x[s][n_in - 2 - j]), in-place
+ * square root (power -> magnitude) and the LSTM cell update (PyTorch gate order i,f,g,o;
+ * c' = sig(f)*c + sig(i)*tanh(g), h' = sig(o)*tanh(c'); d_h_relu optional = relu(h')). */
+int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_in, int pad, float* d_out,
+                            void* stream);
+int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream);
+int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, float* d_h_out, float* d_c_out, float* d_h_relu,
+                       int64_t n_streams, int hidden, void* stream);
+
+/* a16 -- the trigger / release / max-speech machine of Silero's get_speech_timestamps
+ * (Silero/modeling_modified/utils_vad.py:374-462), one stream per lane: d_probs [S][ld] (one value per
+ * window), d_n_windows[s], d_n_samples[s] (audio length) -> raw (start, end) SAMPLE pairs in
+ * d_segments [S][max_segments][2] (int64) and d_seg_count[s].  Thresholds are doubles because the reference
+ * compares Python floats; speech padding and rounding (:464-482) are per-segment host work. */
+int vadx_silero_timestamps(const float* d_probs, int64_t ld, const int32_t* d_n_windows, const int64_t* d_n_samples,
+                           int64_t n_streams, double threshold, double neg_threshold, double min_speech_samples,
+                           double max_speech_samples, double min_silence_samples,
+                           double min_silence_samples_at_max_speech, int window, int use_max_poss_sil,
+                           int32_t* d_seg_count, int64_t* d_segments, int max_segments, void* stream);
+
 /* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
  * that the float32 running sum rounds exactly like np.cumsum
  * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid
@@ -208,7 +228,7 @@ int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_
  * ------------------------------------------------------------------------------------------ */
 typedef struct vadx_model vadx_model;
 
-/* kind: "firered" | "fsmn" | "marblenet".  `hparams` is a flat int32 array, meaning per kind:
+/* kind: "firered" | "fsmn" | "marblenet" | "silero".  `hparams` is a flat int32 array, meaning per kind:
  *   firered: {idim, R, M, H, P, N1, S1, N2, S2, odim, n_fft, win_length, hop, n_mels}
  *            (DetectModel args, FireRedVAD/Export_FireRedVAD.py:310-316, frontend :38-49)
  *   fsmn:    {input_dim, input_affine_dim, fsmn_layers, linear_dim, proj_dim, lorder, rorder, lstride, rstride,
@@ -218,7 +238,10 @@ typedef struct vadx_model vadx_model;
  *             num_classes, n_fft, win_length, hop, n_mels}; tensors are the BN-FOLDED layers
  *             "b{i}.r{j}.dw" [C][k], "b{i}.r{j}.pw" [out][in], "b{i}.r{j}.pw_bias", "b{i}.res", "b{i}.res_bias",
  *             "decoder.weight", "decoder.bias" (folding: NVIDIA_Frame_VAD_Multilingual_MarbleNet/
- *             Export_NVIDIA_MarbleNet_VAD.py:58-151) */
+ *             Export_NVIDIA_MarbleNet_VAD.py:58-151)
+ *   silero:  {window, context, reflect_pad, n_fft, hop, hidden, n_enc_layers, [out, in] x n_enc_layers}; tensors
+ *             "frontend.basis", "enc.{i}.weight/bias" (dense form of the k=3 conv stack), "rnn.weight_ih",
+ *             "rnn.weight_hh", "rnn.bias" (= bias_ih + bias_hh), "head.weight", "head.bias" */
 int vadx_create(const char* kind, const int32_t* hparams, int n_hparams, vadx_model** out);
 void vadx_destroy(vadx_model* m);
 
@@ -246,7 +269,10 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
  *            (FSMN/Export_FSMN_VAD.py:122-134); thresholds are scalars set with vadx_set_scalar.
  *   marblenet: inputs = {audio int16 [S][L]}; outputs = {score_silence fp32 [S][T'], score_active fp32 [S][T']}
  *            with T' = vadx_output_frames(L); the reference's signal_len output is T' - 1
- *            (NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:444-457). */
+ *            (NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:444-457).
+ *   silero:  inputs = {x fp32 [S][576] = 64-sample context + 512-sample window}; outputs = {out fp32 [S][1]};
+ *            state = {state in fp32 [2][S][128], state out}; n_samples = 576
+ *            (the 'input'/'state' -> 'output'/'stateN' contract of Silero/modeling_modified/utils_vad.py:114-123). */
 int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
                  int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
                  void* stream);

@@ -330,8 +330,104 @@ def gen_marblenet():
     np.savez_compressed(os.path.join(GOLD, "marblenet.npz"), **out)
 
 
+# ------------------------------------------------------------------------------ Silero
+def gen_silero():
+    """(1) the reference's UNMODIFIED Silero/Inference_Silero_VAD_ONNX.py with its own OnnxWrapper and
+    get_speech_timestamps (Silero/modeling_modified/utils_vad.py) -- only the ORT session underneath
+    is replaced by the restated v5 network; (2) get_speech_timestamps on synthetic probability tracks
+    that exercise the max-speech split paths."""
+    import types
+    import vadx  # noqa: F401
+    from vadx import audio_io, synth, weights as W
+    from oracle import ref_runner as RR
+    from oracle.silero import SileroNetOracle
+
+    cfg = W.SileroConfig()
+    w = W.silero_random_init(cfg, 0)
+    net = SileroNetOracle(w, cfg)
+    uv = RL.import_file("Silero/modeling_modified/utils_vad.py", "silero_utils_vad_ref")
+
+    def session_factory(_path):
+        ins = [RR.NodeArg("input", [None, 576], "tensor(float)"), RR.NodeArg("state", [2, None, 128], "tensor(float)"),
+               RR.NodeArg("sr", [], "tensor(int64)")]
+        outs = [RR.NodeArg("output", [None, 1], "tensor(float)"), RR.NodeArg("stateN", [2, None, 128], "tensor(float)")]
+
+        def fn(feed):
+            o, s = net.step(torch.from_numpy(feed["input"]), torch.from_numpy(feed["state"]))
+            return [o.numpy(), s.numpy()]
+
+        return RR.FakeSession(ins, outs, fn)
+
+    fake_ort = RR._fake_onnxruntime(session_factory)
+    sv = types.ModuleType("silero_vad")
+    sv.get_speech_timestamps = uv.get_speech_timestamps
+    box = {}
+
+    def load_silero_vad(onnx=False, opset_version=16, use_cpu=True, path=""):
+        saved = sys.modules.get("onnxruntime")
+        sys.modules["onnxruntime"] = fake_ort
+        try:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                box["m"] = uv.OnnxWrapper(str(path), force_onnx_cpu=use_cpu)
+        finally:
+            if saved is not None:
+                sys.modules["onnxruntime"] = saved
+        return box["m"]
+
+    sv.load_silero_vad = load_silero_vad
+    wav = os.path.join(RL.REF_ROOT, "Silero", "vad_sample.wav")
+    ns, files = RR.run_script("Silero/Inference_Silero_VAD_ONNX.py", session_factory,
+                              lambda p, sr: audio_io.load_wav_int16(os.path.realpath(p), sr), seed=1234,
+                              files_to_link={"vad_sample.wav": wav}, extra_modules={"silero_vad": sv})
+    calls = box["m"].session.calls
+    out = {"sample_probs": np.array([c[1][0][0, 0] for c in calls], np.float32),
+           "sample_state_last": calls[-1][1][1][:, 0, :],
+           "sample_timestamps": np.array(ns["timestamps"], np.float64).reshape(-1, 2),
+           "sample_file_second": np.array(files["timestamps_second.txt"]),
+           "sample_file_indices": np.array(files["timestamps_indices.txt"])}
+    print("silero vad_sample:", len(calls), "windows; probs", float(out["sample_probs"].min()),
+          float(out["sample_probs"].max()), "timestamps", out["sample_timestamps"].tolist())
+
+    # (2) get_speech_timestamps on probability tracks (replay model)
+    class Replay:
+        def __init__(self, probs):
+            self.p, self.i = probs, 0
+
+        def reset_states(self):
+            self.i = 0
+
+        def __call__(self, chunk, sr):
+            v = self.p[self.i]
+            self.i += 1
+            return torch.tensor([[v]])
+
+    rs = np.random.RandomState(7)
+    cases = []
+    for n, max_s, min_sil, use_max in [(400, 20, 250, True), (3000, 6, 250, True), (3000, 6, 100, False),
+                                       (1200, float("inf"), 250, True), (5, 20, 250, True)]:
+        lvl = np.clip(0.5 + np.cumsum(rs.normal(0, 0.06, n)), 0, 1)
+        gate = (np.sin(np.arange(n) / rs.uniform(8, 60)) > rs.uniform(-0.6, 0.3)).astype(np.float64)
+        p = np.clip(0.1 + 0.85 * gate * (0.5 + 0.5 * lvl) + rs.normal(0, 0.04, n), 0, 1).astype(np.float32)
+        cases.append((p, max_s, min_sil, use_max))
+    for i, (p, max_s, min_sil, use_max) in enumerate(cases):
+        n_samples = len(p) * 512 - int(rs.randint(0, 511))
+        audio = torch.zeros(n_samples)
+        for sec in (True, False):
+            r = uv.get_speech_timestamps(audio, Replay([float(v) for v in p]), threshold=0.5,
+                                         max_speech_duration_s=max_s, min_speech_duration_ms=250,
+                                         min_silence_duration_ms=min_sil, return_seconds=sec,
+                                         use_max_poss_sil_at_max_speech=use_max)
+            out[f"ts{i}_{'sec' if sec else 'smp'}"] = np.array([(d["start"], d["end"]) for d in r], np.float64).reshape(-1, 2)
+        out[f"ts{i}_probs"] = p
+        out[f"ts{i}_params"] = np.array([n_samples, max_s if np.isfinite(max_s) else -1, min_sil, 1 if use_max else 0], np.float64)
+        print(f"ts{i}: {len(p)} windows -> {len(out[f'ts{i}_smp'])} segments")
+    np.savez_compressed(os.path.join(GOLD, "silero.npz"), **out)
+
+
 GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
-              "marblenet": gen_marblenet}
+              "marblenet": gen_marblenet, "silero": gen_silero}
 
 
 def main(argv):

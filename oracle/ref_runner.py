@@ -67,6 +67,9 @@ def _fake_onnxruntime(session_factory):
         def add_session_config_entry(self, *_a):
             pass
 
+        def add_run_config_entry(self, *_a):
+            pass
+
     m.SessionOptions = SessionOptions
     m.ExecutionMode = types.SimpleNamespace(ORT_SEQUENTIAL=0, ORT_PARALLEL=1)
     m.GraphOptimizationLevel = types.SimpleNamespace(ORT_ENABLE_ALL=99, ORT_DISABLE_ALL=0, ORT_ENABLE_BASIC=1,

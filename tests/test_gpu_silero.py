@@ -1,0 +1,107 @@
+"""Silero on the GPU through the C ABI: the step graph against the restated network, the wrapper
+contract, and the device trigger machine against the reference's unmodified get_speech_timestamps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vadx
+from vadx import lib, silero_vad, synth, weights as W
+from oracle.silero import OnnxWrapperOracle, SileroNetOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "silero.npz"))
+
+
+@pytest.fixture(scope="module")
+def wts():
+    return W.silero_random_init(W.SileroConfig(), 0)
+
+
+@pytest.fixture(scope="module")
+def session(cuda, wts):
+    return vadx.SileroSession(wts, W.SileroConfig())
+
+
+def test_step_ort_contract(cuda, wts, session):
+    cfg = W.SileroConfig()
+    net = SileroNetOracle(wts, cfg)
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand((7, 576), generator=g) - 0.5) * 0.6
+    st = torch.randn((2, 7, 128), generator=g) * 0.3
+    out, new = session.run(None, {"input": x.numpy(), "state": st.numpy(), "sr": np.array(16000, dtype="int64")})
+    ro, rn = net.step(x, st)
+    assert out.shape == (7, 1) and new.shape == (2, 7, 128)
+    assert np.abs(out - ro.numpy()).max() <= 1e-4 and np.abs(new - rn.numpy()).max() <= 1e-4
+    with pytest.raises(ValueError):
+        session.run(None, {"input": x.numpy()[:, :500], "state": st.numpy(), "sr": np.array(16000)})
+    with pytest.raises(ValueError):
+        session.run(None, {"input": x.numpy(), "state": st.numpy(), "sr": np.array(44100)})
+
+
+def test_wrapper_call_and_state_carry(cuda, wts, session):
+    cfg = W.SileroConfig()
+    ref = OnnxWrapperOracle(SileroNetOracle(wts, cfg))
+    a = torch.from_numpy(synth.synth_streams(5, 512 * 40, seed=12)).float() * 0.000030517578
+    session.reset_states()
+    ref.reset_states()
+    for t in range(40):
+        o = session(a[:, t * 512:(t + 1) * 512], 16000)
+        r = ref(a[:, t * 512:(t + 1) * 512], 16000)
+        assert o.shape == (5, 1)
+        assert (o - r).abs().max().item() <= TOL
+    with pytest.raises(ValueError):
+        session(a[:, :400], 16000)
+    with pytest.raises(ValueError):
+        session(a[:, :512], 22050)
+
+
+def test_vad_sample_against_reference_script(cuda, gold, golden_dir, session, tmp_path):
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    probs = session.audio_forward(torch.from_numpy(audio.astype(np.float32) * 0.000030517578))
+    err = np.abs(probs[0].numpy() - gold["sample_probs"]).max()
+    print(f"vad_sample: max abs prob err {err:.2e}")
+    assert probs.shape == (1, 175) and err <= TOL
+    f1, f2 = str(tmp_path / "s.txt"), str(tmp_path / "i.txt")
+    r = silero_vad.run_vad(audio, session, f1, f2)
+    margin = min(np.abs(gold["sample_probs"] - 0.5).min(), np.abs(gold["sample_probs"] - 0.35).min())
+    if margin > TOL:
+        assert np.array_equal(np.array(r.timestamps, np.float64).reshape(-1, 2), gold["sample_timestamps"])
+        assert open(f1).read() == str(gold["sample_file_second"]) and open(f2).read() == str(gold["sample_file_indices"])
+
+
+def test_trigger_machine_matches_reference_function(cuda, gold):
+    """Probability tracks replayed through the reference's get_speech_timestamps (golden) vs the
+    device machine + host padding, in samples and in seconds, incl. both max-speech split modes."""
+    for i in range(5):
+        p = gold[f"ts{i}_probs"]
+        n_samples, max_s, min_sil, use_max = gold[f"ts{i}_params"]
+        max_s = float("inf") if max_s < 0 else float(max_s)
+        d = torch.from_numpy(p).to(cuda).unsqueeze(0)
+        cnt, seg = silero_vad.raw_segments(d, [int(n_samples)], 0.5, 16000, 250, max_s, int(min_sil), 30, None, 98,
+                                           bool(use_max))
+        pairs = seg[0, :int(cnt[0])].cpu().numpy()
+        smp = silero_vad.pad_and_convert(pairs, int(n_samples), 16000, 30, False)
+        sec = silero_vad.pad_and_convert(pairs, int(n_samples), 16000, 30, True)
+        assert np.array_equal(np.array([(x["start"], x["end"]) for x in smp], np.float64).reshape(-1, 2), gold[f"ts{i}_smp"]), i
+        assert np.array_equal(np.array([(x["start"], x["end"]) for x in sec], np.float64).reshape(-1, 2), gold[f"ts{i}_sec"]), i
+
+
+def test_many_streams_batched(cuda, wts, session):
+    cfg = W.SileroConfig()
+    S, n = 64, 512 * 60 + 123
+    a = torch.from_numpy(synth.synth_streams(S, n, seed=3)).float() * 0.000030517578
+    probs = session.speech_probs(a.to(cuda))
+    ref = OnnxWrapperOracle(SileroNetOracle(wts, cfg)).audio_forward(a)
+    assert probs.shape == ref.shape == (S, 61)
+    err = (probs.cpu() - ref).abs().max().item()
+    print(f"{S} streams x 61 windows: max abs prob err {err:.2e}")
+    assert err <= TOL
+    out = silero_vad.get_speech_timestamps(a, session, return_seconds=True)
+    assert len(out) == S

@@ -8,5 +8,5 @@ entry point raises if the CUDA library or a CUDA device is missing.
 __version__ = "0.1.0"
 
 from . import constants, lib, tables, weights, synth  # noqa: F401
-from .session import InferenceSession, FireRedSession, FsmnSession, MarbleNetSession  # noqa: F401
+from .session import InferenceSession, FireRedSession, FsmnSession, MarbleNetSession, SileroSession  # noqa: F401
 from .postprocess import FramePostConfig, postprocess_frames  # noqa: F401

@@ -165,6 +165,7 @@ struct KindOps {
 const KindOps kKinds[] = {
     {"firered", firered_check, firered_finalize, firered_frames, firered_run},
     {"fsmn", fsmn_check, fsmn_finalize, fsmn_frames, fsmn_run},
+    {"silero", silero_check, silero_finalize, silero_frames, silero_run},
     {"marblenet", marblenet_check, marblenet_finalize, marblenet_frames, marblenet_run},
 };
 const KindOps* ops_of(const std::string& kind) {

@@ -146,6 +146,11 @@ int marblenet_finalize(vadx_model* m);
 int marblenet_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
 int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
                   int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);
+int silero_check(const vadx_model* m);
+int silero_finalize(vadx_model* m);
+int silero_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
+int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+               int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);
 int fsmn_check(const vadx_model* m);
 int fsmn_finalize(vadx_model* m);
 int fsmn_frames(const vadx_model* m, int64_t n_samples, int32_t* out);

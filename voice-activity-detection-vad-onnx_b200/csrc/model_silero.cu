@@ -1,0 +1,131 @@
+// model_silero.cu -- Silero VAD v5 (16 kHz) step: the graph behind OnnxWrapper.__call__
+// (Silero/modeling_modified/utils_vad.py:114-123) for S streams at once.
+//   hparams  {window(512), context(64), reflect_pad(64), n_fft(256), hop(128), hidden(128), n_enc_layers,
+//             [out_dim, in_dim] x n_enc_layers}   (dense re-expression of the k=3 conv stack)
+//   inputs   [0] x fp32 [S][row stride]  (context + window = 576 valid samples per row; the row stride is
+//                the scalar "input.row_stride", default 576, so windows can be strided views of one
+//                long zero-prefixed signal)
+//   outputs  [0] out fp32 [S][1]
+//   state    [0] state in fp32 [2][S][128] (h ; c)   [1] state out (distinct buffer)
+#include "model.hpp"
+
+extern "C" {
+int vadx_reflect_window_f32(const float*, int64_t, int64_t, int, int, float*, void*);
+int vadx_sqrt_inplace_f32(float*, int64_t, void*);
+int vadx_lstm_cell_f32(const float*, const float*, float*, float*, float*, int64_t, int, void*);
+}
+
+namespace {
+struct SileroHP {
+  int window, context, reflect, n_fft, hop, hidden, n_layers;
+  std::vector<std::pair<int, int>> dims;  // (out, in)
+  int n_in() const { return window + context; }
+  int n_bins() const { return n_fft / 2 + 1; }
+  int n_frames() const { return (n_in() + reflect - n_fft) / hop + 1; }
+  int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
+};
+int silero_hp(const vadx_model* m, SileroHP* h) {
+  const auto& v = m->hp;
+  VADX_REQUIRE(v.size() >= 7 && (int)v.size() == 7 + 2 * v[6], "silero: malformed hyper-parameter list (%zu)", v.size());
+  *h = SileroHP{v[0], v[1], v[2], v[3], v[4], v[5], v[6], {}};
+  for (int i = 0; i < h->n_layers; ++i) h->dims.push_back({v[7 + 2 * i], v[8 + 2 * i]});
+  VADX_REQUIRE(h->n_layers >= 1 && h->dims[0].second == h->n_frames() * h->n_bins(),
+               "silero: first dense layer must take n_frames*n_bins = %d inputs", h->n_frames() * h->n_bins());
+  for (int i = 1; i < h->n_layers; ++i)
+    VADX_REQUIRE(h->dims[i].second == h->dims[i - 1].first, "silero: dense layer %d input mismatch", i);
+  VADX_REQUIRE(h->dims.back().first == h->hidden || true, "silero: encoder output");
+  return VADX_OK;
+}
+}  // namespace
+
+int silero_check(const vadx_model* m) {
+  SileroHP h;
+  return silero_hp(m, &h);
+}
+int silero_frames(const vadx_model* m, int64_t, int32_t* out) {
+  (void)m;
+  *out = 1;
+  return VADX_OK;
+}
+int silero_finalize(vadx_model* m) {
+  SileroHP h;
+  VADX_TRY(silero_hp(m, &h));
+  VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_fft * h.ld_basis(), VADX_DT_F32));
+  for (int i = 0; i < h.n_layers; ++i) {
+    std::string p = "enc." + std::to_string(i) + ".";
+    VADX_TRY(m->upload_linear(p + "weight", h.dims[i].first, h.dims[i].second));
+    VADX_TRY(m->upload_raw(p + "bias", h.dims[i].first, VADX_DT_F32));
+  }
+  const int enc_out = h.dims.back().first;
+  VADX_TRY(m->upload_linear("rnn.weight_ih", 4 * h.hidden, enc_out));
+  VADX_TRY(m->upload_linear("rnn.weight_hh", 4 * h.hidden, h.hidden));
+  VADX_TRY(m->upload_raw("rnn.bias", 4 * h.hidden, VADX_DT_F32));
+  VADX_TRY(m->upload_linear("head.weight", 1, h.hidden));
+  VADX_TRY(m->upload_raw("head.bias", 1, VADX_DT_F32));
+  return VADX_OK;
+}
+
+int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
+               int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+  SileroHP h;
+  VADX_TRY(silero_hp(m, &h));
+  const int nwin = h.n_in() + h.reflect;
+  const int T = h.n_frames(), F = h.n_bins();
+  int wide = 4 * h.hidden;
+  for (auto& d : h.dims) wide = std::max(wide, d.first);  // only layer OUTPUTS live in the ping-pong buffers
+  const int ldw = (int)round_up(wide, 4);
+  Workspace ws(ws_ptr, ws_bytes, dry);
+  float* win = ws.take<float>(S * nwin);
+  float* mag = ws.take<float>(S * T * F + 4);
+  float* bufA = ws.take<float>(S * ldw);
+  float* bufB = ws.take<float>(S * ldw);
+  float* hrelu = ws.take<float>(S * h.hidden);
+  if (need) *need = ws.off;
+  if (dry) return VADX_OK;
+  if (ws.off > ws_bytes) {
+    set_error("silero: workspace of %zu bytes is smaller than the %zu needed", ws_bytes, ws.off);
+    return VADX_ENOMEM;
+  }
+  VADX_REQUIRE(L == h.n_in(), "silero: input rows must hold context + window = %d samples, got %lld", h.n_in(),
+               (long long)L);
+  VADX_REQUIRE(state && state[0] && state[1] && state[0] != state[1], "silero: state in/out buffers are required");
+  const int64_t in_stride = (int64_t)m->scalar("input.row_stride", (double)h.n_in());
+  VADX_REQUIRE(in_stride >= 1, "silero: bad input.row_stride");
+  const float* st_in = static_cast<const float*>(state[0]);
+  float* st_out = static_cast<float*>(state[1]);
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
+  auto lin = [&](const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, const float* res,
+                 int64_t ldr, float* y, int64_t ldy, int n_out, int act) -> int {
+    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
+    const float* bias = b ? m->d<float>(b) : nullptr;
+    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, S, n_in, n_out, act, st);
+    return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, S, n_in,
+                           n_out, act, st);
+  };
+  VADX_TRY(vadx_reflect_window_f32(static_cast<const float*>(in[0]), in_stride, S, h.n_in(), h.reflect, win, st));
+  VADX_TRY(vadx_stft_power_f32(win, nwin, S, T, h.hop, h.n_fft, m->d<float>("frontend.basis"), h.ld_basis(), F, mag, F,
+                               st));
+  VADX_TRY(vadx_sqrt_inplace_f32(mag, S * (int64_t)T * F, st));
+  const float* cur = mag;
+  int64_t ldc = (int64_t)T * F;
+  float* pp[2] = {bufA, bufB};
+  for (int i = 0; i < h.n_layers; ++i) {
+    std::string p = "enc." + std::to_string(i) + ".";
+    std::string b = p + "bias";
+    float* dst = pp[i & 1];
+    VADX_TRY(lin(cur, ldc, h.dims[i].second, p + "weight", b.c_str(), nullptr, 0, dst, ldw, h.dims[i].first,
+                 VADX_ACT_RELU));
+    cur = dst;
+    ldc = ldw;
+  }
+  float* g1 = pp[h.n_layers & 1];
+  float* g2 = pp[(h.n_layers + 1) & 1];  // == buffer holding `cur`; safe: cur is consumed by the first GEMM
+  VADX_TRY(lin(cur, ldc, h.dims.back().first, "rnn.weight_ih", "rnn.bias", nullptr, 0, g1, ldw, 4 * h.hidden,
+               VADX_ACT_NONE));
+  VADX_TRY(lin(st_in, h.hidden, h.hidden, "rnn.weight_hh", nullptr, g1, ldw, g2, ldw, 4 * h.hidden, VADX_ACT_NONE));
+  // gates rows have stride ldw; the cell kernel wants them dense [S][4H]: ldw == 4H whenever 4H is the widest layer
+  VADX_REQUIRE(ldw == 4 * h.hidden, "silero: 4*hidden must be the widest layer (got ld %d)", ldw);
+  VADX_TRY(vadx_lstm_cell_f32(g2, st_in + S * h.hidden, st_out, st_out + S * h.hidden, hrelu, S, h.hidden, st));
+  return linear_narrow(hrelu, h.hidden, m->d<float>("head.weight#T"), 4, m->d<float>("head.bias"),
+                       static_cast<float*>(out[0]), S, h.hidden, 1, VADX_ACT_SIGMOID, 1, 1, 1, st);
+}

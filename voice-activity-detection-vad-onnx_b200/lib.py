@@ -53,6 +53,11 @@ SIGNATURES = {
     "vadx_lookahead_hysteresis": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _i32, C.c_double, C.c_double, _i32, _vp, _vp,
                                             _vp, _i64, _vp, _vp, _f32, _vp]),
     "vadx_runs_to_segments": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "vadx_reflect_window_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "vadx_sqrt_inplace_f32": (C.c_int, [_vp, _i64, _vp]),
+    "vadx_lstm_cell_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "vadx_silero_timestamps": (C.c_int, [_vp, _i64, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
     "vadx_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
     "vadx_destroy": (None, [_vp]),

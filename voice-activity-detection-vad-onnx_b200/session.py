@@ -399,6 +399,155 @@ class MarbleNetSession:
         return [outs[names.index(n)] for n in output_names]
 
 
+class SileroSession:
+    """Silero VAD v5 (16 kHz) -- mirrors utils_vad.OnnxWrapper (Silero/modeling_modified/utils_vad.py:10-146):
+    ``model(x, sr)`` on a (B, 512) chunk keeps a 64-sample context and the (2, B, 128) LSTM state between
+    calls, ``reset_states``, ``audio_forward``; plus ``run`` with the raw ORT contract
+    ('input' (B,576), 'state' (2,B,128), 'sr') -> ('output' (B,1), 'stateN') and the device-resident
+    ``speech_probs`` used by the batched entry point."""
+    sample_rates = [16000]
+
+    def __init__(self, weights: dict, cfg: W.SileroConfig = W.SileroConfig(), tensor_cores: bool = True):
+        import torch
+        self.cfg = cfg
+        spec = W.silero_spec(cfg)
+        for name in spec:
+            if name not in weights:
+                raise KeyError(f"SileroSession: weight '{name}' missing from the state dict")
+            if tuple(np.shape(weights[name])) != tuple(spec[name]):
+                raise ValueError(f"SileroSession: '{name}' has shape {np.shape(weights[name])}, expected {spec[name]}")
+        dense = W.silero_dense_layers(cfg, weights)
+        hp = [cfg.window, cfg.context, cfg.reflect_pad, cfg.n_fft, cfg.hop, cfg.hidden, len(dense)]
+        for D, _b in dense:
+            hp += [D.shape[0], D.shape[1]]
+        self._e = _Engine("silero", hp)
+        fb = np.asarray(weights["stft.forward_basis_buffer"], np.float32)[:, 0, :]     # [2F, n_fft]
+        F = cfg.n_bins
+        ld = (2 * F + 3) // 4 * 4
+        basis = np.zeros((cfg.n_fft, ld), np.float32)
+        basis[:, 0:2 * F:2] = fb[:F].T
+        basis[:, 1:2 * F:2] = fb[F:].T
+        self._e.set_tensor("frontend.basis", basis)
+        for i, (D, b) in enumerate(dense):
+            self._e.set_tensor(f"enc.{i}.weight", D)
+            self._e.set_tensor(f"enc.{i}.bias", b)
+        self._e.set_tensor("rnn.weight_ih", np.asarray(weights["decoder.rnn.weight_ih"], np.float32))
+        self._e.set_tensor("rnn.weight_hh", np.asarray(weights["decoder.rnn.weight_hh"], np.float32))
+        self._e.set_tensor("rnn.bias", (np.asarray(weights["decoder.rnn.bias_ih"], np.float32)
+                                        + np.asarray(weights["decoder.rnn.bias_hh"], np.float32)))
+        self._e.set_tensor("head.weight", np.asarray(weights["decoder.decoder.2.weight"], np.float32)[:, :, 0])
+        self._e.set_tensor("head.bias", np.asarray(weights["decoder.decoder.2.bias"], np.float32))
+        self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
+        self._row_stride = None
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+        self.reset_states()
+
+    # ---- raw graph ---------------------------------------------------------------------------
+    def step(self, x, state, row_stride: int | None = None, stream=None):
+        """x: CUDA fp32, S rows of 576 valid samples spaced `row_stride` apart (default: contiguous
+        [S,576]); state CUDA fp32 [2,S,128] -> (out [S,1], new_state)."""
+        import torch
+        n_in = self.cfg.window + self.cfg.context
+        S = state.shape[1]
+        stride = int(row_stride) if row_stride is not None else n_in
+        if stride != self._row_stride:
+            self._e.set_scalar("input.row_stride", float(stride))
+            self._row_stride = stride
+        out = torch.empty((S, 1), dtype=torch.float32, device=state.device)
+        new_state = torch.empty_like(state)
+        self._e.forward([x], [out], [state, new_state], S, n_in, stream)
+        return out, new_state
+
+    def run(self, output_names, input_feed: dict):
+        import torch
+        if set(input_feed) != {"input", "state", "sr"}:
+            raise ValueError(f"InvalidArgument: inputs must be input/state/sr, got {sorted(input_feed)}")
+        x = np.asarray(input_feed["input"])
+        st = np.asarray(input_feed["state"])
+        if int(np.asarray(input_feed["sr"])) != 16000:
+            raise ValueError("Supported sampling rates: [16000]")
+        if x.dtype != np.float32 or x.ndim != 2 or x.shape[1] != self.cfg.window + self.cfg.context:
+            raise ValueError(f"InvalidArgument: 'input' must be fp32 (B, {self.cfg.window + self.cfg.context})")
+        if st.dtype != np.float32 or st.shape != (2, x.shape[0], self.cfg.hidden):
+            raise ValueError(f"InvalidArgument: 'state' must be fp32 (2, {x.shape[0]}, {self.cfg.hidden})")
+        out, new = self.step(torch.from_numpy(np.ascontiguousarray(x)).cuda(), torch.from_numpy(np.ascontiguousarray(st)).cuda())
+        outs = [out.cpu().numpy(), new.cpu().numpy()]
+        names = ["output", "stateN"]
+        if output_names is None:
+            return outs
+        return [outs[names.index(n)] for n in output_names]
+
+    # ---- OnnxWrapper surface -------------------------------------------------------------------
+    def reset_states(self, batch_size=1):
+        import torch
+        self._state = torch.zeros((2, batch_size, self.cfg.hidden), dtype=torch.float32, device=self._dev)
+        self._context = None
+        self._last_sr = 0
+        self._last_batch_size = 0
+
+    def _validate_input(self, x, sr: int):
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() > 2:
+            raise ValueError(f"Too many dimensions for input audio chunk {x.dim()}")
+        if sr != 16000 and (sr % 16000 == 0):
+            x = x[:, ::sr // 16000]
+            sr = 16000
+        if sr not in self.sample_rates:
+            raise ValueError(f"Supported sampling rates: {self.sample_rates} (or multiply of 16000)")
+        if sr / x.shape[1] > 31.25:
+            raise ValueError("Input audio chunk is too short")
+        return x, sr
+
+    def __call__(self, x, sr: int = 16000):
+        import torch
+        x, sr = self._validate_input(x, sr)
+        if x.shape[-1] != self.cfg.window:
+            raise ValueError(f"Provided number of samples is {x.shape[-1]} (Supported values: 256 for 8000 sample rate, 512 for 16000)")
+        b = x.shape[0]
+        if not self._last_batch_size or (self._last_sr and self._last_sr != sr) or self._last_batch_size != b:
+            self.reset_states(b)
+        if self._context is None:
+            self._context = torch.zeros((b, self.cfg.context), dtype=torch.float32, device=self._dev)
+        xd = torch.cat([self._context, x.to(self._dev, torch.float32)], dim=1).contiguous()
+        out, self._state = self.step(xd, self._state)
+        self._context = xd[:, -self.cfg.context:]
+        self._last_sr, self._last_batch_size = sr, b
+        return out.cpu() if not x.is_cuda else out
+
+    def audio_forward(self, x, sr: int = 16000):
+        x, sr = self._validate_input(x, sr)
+        probs = self.speech_probs(x.to(self._dev, dtype=self._state.dtype).contiguous())
+        return probs.cpu()
+
+    # ---- B200-native surface ---------------------------------------------------------------------
+    def speech_probs(self, audio, stream=None):
+        """audio: CUDA fp32 [S, n] (already scaled by 1/32768) -> probs CUDA fp32 [S, ceil(n/512)].
+        One graph step per 32 ms window for all S streams; the context is not copied: every window
+        is a strided view of the zero-prefixed, zero-padded signal; the LSTM state stays in HBM."""
+        import torch
+        c = self.cfg
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.float32 and audio.dim() == 2):
+            raise ValueError("speech_probs: audio must be a CUDA fp32 tensor [S, n]")
+        S, n = audio.shape
+        n_win = (n + c.window - 1) // c.window
+        padded = torch.zeros((S, c.context + n_win * c.window), dtype=torch.float32, device=audio.device)
+        padded[:, c.context:c.context + n] = audio
+        probs = torch.empty((n_win, S, 1), dtype=torch.float32, device=audio.device)
+        state = torch.zeros((2, S, c.hidden), dtype=torch.float32, device=audio.device)
+        stride = padded.shape[1]
+        if stride != self._row_stride:
+            self._e.set_scalar("input.row_stride", float(stride))
+            self._row_stride = stride
+        n_in = c.window + c.context
+        nxt = torch.empty_like(state)
+        for t in range(n_win):
+            self._e.forward([padded[:, t * c.window:]], [probs[t]], [state, nxt], S, n_in, stream)
+            state, nxt = nxt, state
+        self._final_state = state
+        return probs[:, :, 0].transpose(0, 1).contiguous()
+
+
 def InferenceSession(kind: str, weights: dict, config=None, **kw):
     """Factory with the reference's constructor name; `kind` replaces the .onnx path."""
     if kind == "firered":
@@ -407,4 +556,6 @@ def InferenceSession(kind: str, weights: dict, config=None, **kw):
         return FsmnSession(weights, config or W.FsmnConfig(), **kw)
     if kind == "marblenet":
         return MarbleNetSession(weights, config or W.MarbleNetConfig(), **kw)
+    if kind == "silero":
+        return SileroSession(weights, config or W.SileroConfig(), **kw)
     raise ValueError(f"unknown model kind {kind!r}")

@@ -316,3 +316,88 @@ def marblenet_fold(cfg: MarbleNetConfig, w: dict) -> "OrderedDict[str, np.ndarra
     out["decoder.bias"] = w["decoder.layer0.bias"]
     del c_in
     return out
+
+
+# ----------------------------------------------------------------------------- Silero VAD v5 (16 kHz)
+@dataclasses.dataclass(frozen=True)
+class SileroConfig:
+    """Silero VAD v5, 16 kHz branch.  The network ships as an opaque silero_vad.onnx inside the
+    unpinned `silero_vad` pip package (Silero/Export_Silero_VAD.py:91), not in the reference
+    checkout: this layout restates the public v5 graph -- parity for the network is unpinned; the
+    call contract (Silero/modeling_modified/utils_vad.py:93-128) is what the reference pins."""
+    window: int = 512
+    context: int = 64
+    reflect_pad: int = 64
+    n_fft: int = 256
+    hop: int = 128
+    enc_channels: tuple = (128, 64, 64, 128)
+    enc_strides: tuple = (1, 2, 2, 1)
+    enc_kernel: int = 3
+    hidden: int = 128
+
+    @property
+    def n_bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+    @property
+    def n_frames(self) -> int:
+        return (self.context + self.window + self.reflect_pad - self.n_fft) // self.hop + 1
+
+
+def silero_spec(cfg: SileroConfig) -> "OrderedDict[str, tuple]":
+    s: OrderedDict[str, tuple] = OrderedDict()
+    s["stft.forward_basis_buffer"] = (2 * cfg.n_bins, 1, cfg.n_fft)
+    c = cfg.n_bins
+    for i, co in enumerate(cfg.enc_channels):
+        s[f"encoder.{i}.reparam_conv.weight"] = (co, c, cfg.enc_kernel)
+        s[f"encoder.{i}.reparam_conv.bias"] = (co,)
+        c = co
+    s["decoder.rnn.weight_ih"] = (4 * cfg.hidden, c)
+    s["decoder.rnn.weight_hh"] = (4 * cfg.hidden, cfg.hidden)
+    s["decoder.rnn.bias_ih"] = (4 * cfg.hidden,)
+    s["decoder.rnn.bias_hh"] = (4 * cfg.hidden,)
+    s["decoder.decoder.2.weight"] = (1, cfg.hidden, 1)
+    s["decoder.decoder.2.bias"] = (1,)
+    return s
+
+
+def silero_random_init(cfg: SileroConfig = SileroConfig(), seed: int = 0):
+    """Seeded random network; the STFT basis is the real (hann-windowed) DFT basis the model carries."""
+    rs = np.random.RandomState(seed)
+    spec = silero_spec(cfg)
+    w = _default_init(rs, OrderedDict((k, v) for k, v in spec.items() if k != "stft.forward_basis_buffer"))
+    n = np.arange(cfg.n_fft, dtype=np.float64)
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * n / cfg.n_fft)
+    f = np.arange(cfg.n_bins, dtype=np.float64)[:, None]
+    ang = 2 * np.pi * f * n[None, :] / cfg.n_fft
+    basis = np.concatenate([np.cos(ang) * win, -np.sin(ang) * win], 0).astype(np.float32)
+    w["stft.forward_basis_buffer"] = basis[:, None, :]
+    # audio is in [-1, 1): lift the first layer so the stack is alive, and spread the head
+    w["encoder.0.reparam_conv.weight"] = (w["encoder.0.reparam_conv.weight"] * 4.0).astype(np.float32)
+    w["decoder.decoder.2.weight"] = (w["decoder.decoder.2.weight"] * 12.0).astype(np.float32)
+    return w
+
+
+def silero_dense_layers(cfg: SileroConfig, w: dict):
+    """The k=3 conv encoder acts on only 4 -> 4 -> 2 -> 1 -> 1 frames per window, so each layer is
+    re-expressed as ONE dense matrix on the flattened [frame][channel] vector (block-banded, zero
+    where the taps fall outside or on the padding): rows of the batch stay independent and the
+    layer runs on the generic dense kernel.  Returns [(W [out, in], b [out])] for the 4 layers."""
+    out = []
+    t_in, c_in = cfg.n_frames, cfg.n_bins
+    for i, (co, st) in enumerate(zip(cfg.enc_channels, cfg.enc_strides)):
+        k = cfg.enc_kernel
+        pad = k // 2
+        t_out = (t_in + 2 * pad - k) // st + 1
+        Wc = np.asarray(w[f"encoder.{i}.reparam_conv.weight"], np.float32)      # [co, c_in, k]
+        bc = np.asarray(w[f"encoder.{i}.reparam_conv.bias"], np.float32)
+        D = np.zeros((t_out * co, t_in * c_in), np.float32)
+        for to in range(t_out):
+            for j in range(k):
+                ti = to * st - pad + j
+                if 0 <= ti < t_in:
+                    D[to * co:(to + 1) * co, ti * c_in:(ti + 1) * c_in] = Wc[:, :, j]
+        out.append((D, np.tile(bc, t_out)))
+        t_in, c_in = t_out, co
+    assert t_in == 1
+    return out
