@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="vadx", choices=["vadx", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-families", action="store_true", help="skip the short RTFx runs of the other model families")
     return ap.parse_args()
 
 
@@ -176,6 +177,69 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------- other families
+def family_rtfx(dev, world, dist):
+    """Short device-resident RTFx runs of the other model families (BASELINE configs 0-2), same timing
+    rules (3 warm-ups, CUDA events, max over ranks).  Reported next to the headline, not as it."""
+    import numpy as np
+    import torch
+    import vadx
+    from vadx import fsmn_vad, marblenet_vad, silero_vad, synth, weights as W
+
+    def timed(fn, steps=3, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    out = {}
+    # FSMN (config 0 shape, batched): S streams x 4 overlapping 16000-sample windows, state carried on device
+    cfg = W.FsmnConfig()
+    sess = vadx.FsmnSession(W.fsmn_random_init(cfg, 0), cfg, chunk_len=16000)
+    S, stride = 1024, 16000 - 31 * 160
+    n = 16000 + 3 * stride
+    a = torch.from_numpy(synth.synth_chunks_fast(S, n, seed=11)).to(dev)
+    ms = timed(lambda: fsmn_vad.run_streams(sess, a, stride))
+    out["fsmn"] = {"audio_hours_per_sec": world * S * n / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
+                   "config": f"{S} streams/GPU x 4 windows of 16000 samples (stride {stride}), caches + hysteresis on device"}
+    del sess, a
+    # MarbleNet (config 2): 60 s clips
+    cfg = W.MarbleNetConfig()
+    sess = vadx.MarbleNetSession(W.marblenet_random_init(cfg, 0), cfg)
+    B = 64
+    clips = torch.from_numpy(synth.synth_chunks_fast(B, 960000, seed=12)).to(dev)
+    ms = timed(lambda: marblenet_vad.run_vad_clips(sess, clips))
+    out["marblenet"] = {"audio_hours_per_sec": world * B * 60.0 / (ms / 1e3) / 3600, "ms_per_step": ms,
+                        "config": f"{B} clips/GPU x 60 s, post-processing on device"}
+    del sess, clips
+    # Silero (config 1): 4096 streams, 32 ms windows with LSTM state carry
+    cfg = W.SileroConfig()
+    sess = vadx.SileroSession(W.silero_random_init(cfg, 0), cfg)
+    S, n_win = 4096, 32
+    audio = (torch.from_numpy(synth.synth_chunks_fast(S, n_win * 512, seed=13)).to(dev).float() * 0.000030517578)
+    lens = [n_win * 512] * S
+
+    def silero_step():
+        probs = sess.speech_probs(audio)
+        return silero_vad.raw_segments(probs, lens, 0.5, 16000, 250, 20, 250)
+
+    ms = timed(silero_step)
+    out["silero"] = {"audio_hours_per_sec": world * S * n_win * 0.032 / (ms / 1e3) / 3600, "ms_per_step": ms,
+                     "config": f"{S} streams/GPU x {n_win} windows of 512 samples, LSTM state + trigger machine on device"}
+    for v in out.values():
+        v["rtfx"] = v["audio_hours_per_sec"] * 3600
+    return out
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def run_vadx(args):
     import numpy as np
@@ -266,6 +330,11 @@ def run_vadx(args):
     if rank == 0:
         sampler.stop()
     segs_found = int(h_cnt.sum().item())
+    families = None
+    if not args.no_families:
+        del d_in, d_audio
+        torch.cuda.empty_cache()
+        families = family_rtfx(dev, world, dist)
 
     audio_s_per_step = world * B * (CHUNK / 16000.0)
     value = audio_s_per_step * args.steps / (ms_total / 1e3) / 3600.0
@@ -317,7 +386,7 @@ def run_vadx(args):
                 "gpu_launches": int(launches),
                 "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                 "stage_share": stage_share,
-                "cpu_baseline": cpu, "clocks": sampler.summary()}
+                "cpu_baseline": cpu, "clocks": sampler.summary(), "families": families}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
