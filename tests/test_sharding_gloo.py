@@ -48,4 +48,4 @@ def test_two_rank_stream_sharding():
     assert streams == list(range(n_streams))                   # disjoint, complete, ordered
     total = sum(len(part[2]) for part in ret["gathered"])
     assert total == sum(s % 3 for s in range(n_streams))
-    assert list(shard(4, 3, 8)) == [] and list(shard(9, 0, 8)) == [0, 1]
+    assert list(shard(4, 5, 8)) == [] and list(shard(4, 3, 8)) == [3] and list(shard(9, 0, 8)) == [0, 1]

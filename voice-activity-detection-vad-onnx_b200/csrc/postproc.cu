@@ -11,19 +11,29 @@ namespace vadx {
 
 constexpr int kMaxSmooth = 64;
 
-__global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __restrict__ probs, int64_t ld_probs,
-                                                                 const int32_t* __restrict__ n_frames_per_stream,
-                                                                 int64_t n_streams, int n_frames_max,
-                                                                 const vadx_post_cfg cfg, int8_t* __restrict__ dec_all,
-                                                                 int32_t* __restrict__ seg_count,
-                                                                 int32_t* __restrict__ segments, int max_segments) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp = 32 streams.  The decision arrays of the warp's streams live in shared memory
+// (byte-interleaved by lane: dec(t) of lane l at sdec[t*32 + l], conflict-free), so the back-fill,
+// merge, dilation and split passes never touch global memory; probabilities are pulled through the
+// read-only path, decisions are written back once at the end.
+__global__ void __launch_bounds__(32) postprocess_frames_kernel(const float* __restrict__ probs, int64_t ld_probs,
+                                                                const int32_t* __restrict__ n_frames_per_stream,
+                                                                int64_t n_streams, int n_frames_max,
+                                                                const vadx_post_cfg cfg, int8_t* __restrict__ dec_all,
+                                                                int32_t* __restrict__ seg_count,
+                                                                int32_t* __restrict__ segments, int max_segments,
+                                                                int use_smem) {
+  extern __shared__ int8_t sdec[];
+  const int lane = threadIdx.x;
+  const int64_t s = (int64_t)blockIdx.x * 32 + lane;
   if (s >= n_streams) return;
   int n = n_frames_per_stream ? n_frames_per_stream[s] : n_frames_max;
   if (n > n_frames_max) n = n_frames_max;
   if (n < 0) n = 0;
   const float* p = probs + s * ld_probs;
-  int8_t* dec = dec_all + s * (int64_t)n_frames_max;
+  int8_t* gdec = dec_all + s * (int64_t)n_frames_max;
+  // dec(t): shared (stride 32, offset lane) or global (stride 1)
+  int8_t* dec = use_smem ? sdec + lane : gdec;
+  const int ds = use_smem ? 32 : 1;
   const int ws = cfg.smooth_window < 1 ? 1 : cfg.smooth_window;
   const float thr = cfg.threshold;
   const int min_sp = cfg.min_speech_frame, min_si = cfg.min_silence_frame;
@@ -37,17 +47,18 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
   int state = 0, speech_start = 0, silence_start = 0;  // 0 SIL, 1 POSSIBLE_SPEECH, 2 SPEECH, 3 POSSIBLE_SILENCE
   for (int t = 0; t < n; ++t) {
     float sm;
+    const float pt = __ldg(p + t);
     if (ws > 1) {
-      run = __fadd_rn(run, p[t]);           // cumsum[t+1]
+      run = __fadd_rn(run, pt);             // cumsum[t+1]
       ring[(t + 1) % (ws + 1)] = run;
       if (t < ws - 1) sm = __fdiv_rn(run, (float)(t + 1));
       else sm = __fmul_rn(__fsub_rn(run, ring[(t + 1 - ws) % (ws + 1)]), inv_ws);
     } else {
-      sm = p[t];
+      sm = pt;
     }
     const bool hot = sm >= thr;
     if (plain) {
-      dec[t] = hot ? 1 : 0;
+      dec[t * ds] = hot ? 1 : 0;
       continue;
     }
     if (state == 0) {
@@ -56,7 +67,7 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
       if (hot) {
         if (t - speech_start >= min_sp) {
           state = 2;
-          for (int j = speech_start; j < t; ++j) dec[j] = 1;
+          for (int j = speech_start; j < t; ++j) dec[j * ds] = 1;
         }
       } else {
         state = 0;
@@ -70,15 +81,15 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
         state = 2;
       }
     }
-    dec[t] = state >= 2 ? 1 : 0;
+    dec[t * ds] = state >= 2 ? 1 : 0;
   }
 
   // ---- rising edges move left by ws (:235-243) ----
   if (ws > 1) {
     for (int t = 1; t < n; ++t) {
-      if (dec[t] == 1 && dec[t - 1] == 0) {
+      if (dec[t * ds] == 1 && dec[(t - 1) * ds] == 0) {
         int start = t >= ws ? t - ws : 0;
-        for (int j = start; j < t; ++j) dec[j] = 1;
+        for (int j = start; j < t; ++j) dec[j * ds] = 1;
       }
     }
   }
@@ -86,12 +97,12 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
   if (cfg.merge_silence_frame > 0) {
     int gap = -1;
     for (int t = 1; t < n; ++t) {
-      int a = dec[t - 1], b = dec[t];
+      int a = dec[(t - 1) * ds], b = dec[t * ds];
       if (a == 1 && b == 0 && gap < 0) {
         gap = t;
       } else if (a == 0 && b == 1 && gap >= 0) {
         if (t - gap < cfg.merge_silence_frame)
-          for (int j = gap; j < t; ++j) dec[j] = 1;
+          for (int j = gap; j < t; ++j) dec[j * ds] = 1;
         gap = -1;
       }
     }
@@ -101,13 +112,13 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
     const int ext = cfg.extend_speech_frame;
     int dist = ext + 1;
     for (int t = 0; t < n; ++t) {
-      if (dec[t]) dist = 0;
-      else if (++dist <= ext) dec[t] = 1;
+      if (dec[t * ds]) dist = 0;
+      else if (++dist <= ext) dec[t * ds] = 1;
     }
     dist = ext + 1;
     for (int t = n - 1; t >= 0; --t) {
-      if (dec[t]) dist = 0;
-      else if (++dist <= ext) dec[t] = 1;
+      if (dec[t * ds]) dist = 0;
+      else if (++dist <= ext) dec[t * ds] = 1;
     }
   }
   // ---- split over-long runs at the least likely frame of the back half (:279-304) ----
@@ -115,9 +126,9 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
     const int max_sf = cfg.max_speech_frame, half = cfg.max_speech_frame >> 1;
     int t = 0;
     while (t < n) {
-      if (!dec[t]) { ++t; continue; }
+      if (!dec[t * ds]) { ++t; continue; }
       int seg_start = t;
-      while (t < n && dec[t]) ++t;
+      while (t < n && dec[t * ds]) ++t;
       if (t - seg_start > max_sf) {
         int pos = seg_start;
         const int seg_end = t;
@@ -126,21 +137,24 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
           if (b > seg_end) b = seg_end;
           if (a >= b) break;
           int arg = a;
-          float best = p[a];
-          for (int j = a + 1; j < b; ++j)
-            if (p[j] < best) { best = p[j]; arg = j; }
-          dec[arg] = 0;
+          float best = __ldg(p + a);
+          for (int j = a + 1; j < b; ++j) {
+            float v = __ldg(p + j);
+            if (v < best) { best = v; arg = j; }
+          }
+          dec[arg * ds] = 0;
           pos = arg + 1;
         }
       }
     }
   }
-  // ---- edges -> (start, end) frame pairs (decision_to_segment :146-166) ----
+  // ---- edges -> (start, end) frame pairs (decision_to_segment :146-166) + decisions out ----
   int count = 0;
   int32_t* seg = segments ? segments + s * (int64_t)max_segments * 2 : nullptr;
   int prev = 0, start = 0;
   for (int t = 0; t <= n; ++t) {
-    int cur = t < n ? dec[t] : 0;
+    int cur = t < n ? dec[t * ds] : 0;
+    if (use_smem && t < n) gdec[t] = (int8_t)cur;
     if (cur && !prev) start = t;
     if (!cur && prev) {
       if (seg && count < max_segments) { seg[2 * count] = start; seg[2 * count + 1] = t; }
@@ -149,6 +163,164 @@ __global__ void __launch_bounds__(128) postprocess_frames_kernel(const float* __
     prev = cur;
   }
   if (seg_count) seg_count[s] = count;
+}
+
+
+// Warp-per-stream variant (the default whenever a stream's frames fit in shared memory): lanes load
+// the probabilities coalesced, lane 0 forms the float32 running sum in order (the only truly
+// sequential float arithmetic), ALL lanes evaluate the smoothed value and the threshold test for
+// their frames in parallel from that running sum (each is one subtraction + one multiply of
+// already-rounded operands, so the result is bit-identical to numpy's), lane 0 then walks the
+// integer state machines over shared memory, and all lanes write the decisions back coalesced.
+// One stream per warp means no lane divergence in the sequential part.
+constexpr int kPpWarps = 4;
+__global__ void __launch_bounds__(kPpWarps * 32) postprocess_frames_warp_kernel(
+    const float* __restrict__ probs, int64_t ld_probs, const int32_t* __restrict__ n_frames_per_stream,
+    int64_t n_streams, int n_frames_max, const vadx_post_cfg cfg, int8_t* __restrict__ dec_all,
+    int32_t* __restrict__ seg_count, int32_t* __restrict__ segments, int max_segments, int per_warp_floats) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * kPpWarps + warp;
+  if (s >= n_streams) return;
+  int n = n_frames_per_stream ? n_frames_per_stream[s] : n_frames_max;
+  if (n > n_frames_max) n = n_frames_max;
+  if (n < 0) n = 0;
+  float* sp = smem_f + (size_t)warp * per_warp_floats;   // probs [n_frames_max]
+  float* cs = sp + n_frames_max;                          // running sums [n_frames_max + 1]
+  int8_t* dec = reinterpret_cast<int8_t*>(cs + n_frames_max + 1);
+  const float* p = probs + s * ld_probs;
+  int8_t* gdec = dec_all + s * (int64_t)n_frames_max;
+  const int ws = cfg.smooth_window < 1 ? 1 : cfg.smooth_window;
+  const float thr = cfg.threshold;
+  const int min_sp = cfg.min_speech_frame, min_si = cfg.min_silence_frame;
+  const float inv_ws = (float)(1.0 / (double)ws);
+
+  for (int t = lane; t < n; t += 32) sp[t] = __ldg(p + t);
+  __syncwarp();
+  if (ws > 1) {
+    if (lane == 0) {
+      float run = 0.f;
+      cs[0] = 0.f;
+      for (int t = 0; t < n; ++t) {
+        run = __fadd_rn(run, sp[t]);
+        cs[t + 1] = run;
+      }
+    }
+    __syncwarp();
+  }
+  for (int t = lane; t < n; t += 32) {
+    float sm;
+    if (ws > 1) {
+      if (t < ws - 1) sm = __fdiv_rn(cs[t + 1], (float)(t + 1));
+      else sm = __fmul_rn(__fsub_rn(cs[t + 1], cs[t + 1 - ws]), inv_ws);
+    } else {
+      sm = sp[t];
+    }
+    dec[t] = sm >= thr ? 1 : 0;   // "hot" flags; turned into decisions in place below
+  }
+  __syncwarp();
+  int count = 0;
+  if (lane == 0) {
+    if (!(min_sp <= 0 && min_si <= 0)) {
+      int state = 0, speech_start = 0, silence_start = 0;
+      for (int t = 0; t < n; ++t) {
+        const bool hot = dec[t] != 0;
+        if (state == 0) {
+          if (hot) { state = 1; speech_start = t; }
+        } else if (state == 1) {
+          if (hot) {
+            if (t - speech_start >= min_sp) {
+              state = 2;
+              for (int j = speech_start; j < t; ++j) dec[j] = 1;
+            }
+          } else {
+            state = 0;
+          }
+        } else if (state == 2) {
+          if (!hot) { state = 3; silence_start = t; }
+        } else {
+          if (!hot) {
+            if (t - silence_start >= min_si) state = 0;
+          } else {
+            state = 2;
+          }
+        }
+        dec[t] = state >= 2 ? 1 : 0;
+      }
+    }
+    if (ws > 1) {
+      for (int t = 1; t < n; ++t) {
+        if (dec[t] == 1 && dec[t - 1] == 0) {
+          int start = t >= ws ? t - ws : 0;
+          for (int j = start; j < t; ++j) dec[j] = 1;
+        }
+      }
+    }
+    if (cfg.merge_silence_frame > 0) {
+      int gap = -1;
+      for (int t = 1; t < n; ++t) {
+        int a = dec[t - 1], b = dec[t];
+        if (a == 1 && b == 0 && gap < 0) {
+          gap = t;
+        } else if (a == 0 && b == 1 && gap >= 0) {
+          if (t - gap < cfg.merge_silence_frame)
+            for (int j = gap; j < t; ++j) dec[j] = 1;
+          gap = -1;
+        }
+      }
+    }
+    if (cfg.extend_speech_frame > 0) {
+      const int ext = cfg.extend_speech_frame;
+      int dist = ext + 1;
+      for (int t = 0; t < n; ++t) {
+        if (dec[t]) dist = 0;
+        else if (++dist <= ext) dec[t] = 1;
+      }
+      dist = ext + 1;
+      for (int t = n - 1; t >= 0; --t) {
+        if (dec[t]) dist = 0;
+        else if (++dist <= ext) dec[t] = 1;
+      }
+    }
+    {
+      const int max_sf = cfg.max_speech_frame, half = cfg.max_speech_frame >> 1;
+      int t = 0;
+      while (t < n) {
+        if (!dec[t]) { ++t; continue; }
+        int seg_start = t;
+        while (t < n && dec[t]) ++t;
+        if (t - seg_start > max_sf) {
+          int pos = seg_start;
+          const int seg_end = t;
+          while (pos + max_sf < seg_end) {
+            int a = pos + half, b = pos + max_sf;
+            if (b > seg_end) b = seg_end;
+            if (a >= b) break;
+            int arg = a;
+            float best = sp[a];
+            for (int j = a + 1; j < b; ++j)
+              if (sp[j] < best) { best = sp[j]; arg = j; }
+            dec[arg] = 0;
+            pos = arg + 1;
+          }
+        }
+      }
+    }
+    int32_t* seg = segments ? segments + s * (int64_t)max_segments * 2 : nullptr;
+    int prev = 0, start = 0;
+    for (int t = 0; t <= n; ++t) {
+      int cur = t < n ? dec[t] : 0;
+      if (cur && !prev) start = t;
+      if (!cur && prev) {
+        if (seg && count < max_segments) { seg[2 * count] = start; seg[2 * count + 1] = t; }
+        ++count;
+      }
+      prev = cur;
+    }
+    if (seg_count) seg_count[s] = count;
+  }
+  __syncwarp();
+  for (int t = lane; t < n; t += 32) gdec[t] = dec[t];
 }
 
 }  // namespace vadx
@@ -166,8 +338,32 @@ extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, c
                kMaxSmooth);
   VADX_REQUIRE(max_segments >= 0 && (max_segments == 0 || d_segments), "vadx_postprocess_frames: segments buffer");
   if (n_streams == 0) return VADX_OK;
-  int64_t blocks = ceil_div(n_streams, 128);
-  postprocess_frames_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
-      d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments);
+  // warp-per-stream kernel when one stream (probs + running sums + decisions) fits in shared memory
+  const int per_warp_floats = (int)round_up(2 * (int64_t)std::max(n_frames, 1) + 1 + (std::max(n_frames, 1) + 3) / 4, 4);
+  const size_t smem_w = (size_t)per_warp_floats * 4 * kPpWarps;
+  if (smem_w <= 200 * 1024) {
+    static bool cfg_w = false;
+    if (smem_w > 48 * 1024 && !cfg_w) {
+      cudaError_t e = cudaFuncSetAttribute(postprocess_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(postprocess_frames_warp_kernel)");
+      cfg_w = true;
+    }
+    postprocess_frames_warp_kernel<<<(unsigned)ceil_div(n_streams, kPpWarps), kPpWarps * 32, smem_w, (cudaStream_t)stream>>>(
+        d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
+        per_warp_floats);
+    return after_launch("vadx_postprocess_frames");
+  }
+  const int64_t blocks = ceil_div(n_streams, 32);
+  const size_t smem = (size_t)std::max(n_frames, 1) * 32;
+  const int use_smem = smem <= 200 * 1024;
+  static bool configured = false;
+  if (use_smem && smem > 48 * 1024 && !configured) {
+    cudaError_t e = cudaFuncSetAttribute(postprocess_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(postprocess_frames_kernel)");
+    configured = true;
+  }
+  postprocess_frames_kernel<<<(unsigned)blocks, 32, use_smem ? smem : 0, (cudaStream_t)stream>>>(
+      d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
+      use_smem);
   return after_launch("vadx_postprocess_frames");
 }

@@ -60,6 +60,70 @@ def run_vad_streams(session: FireRedSession, chunks, lengths, post: PP.FramePost
     return probs, dec, cnt, seg, n_valid
 
 
+class HostBatchPipeline:
+    """Host-buffer front door for serving: pinned int16 batches in, segment frame pairs back in pinned
+    host memory.  The H2D copy of batch i+1 runs on a copy stream while batch i computes (two device
+    input buffers, event hand-over), so a steady stream of batches costs max(copy, compute) per batch
+    instead of their sum; results (seg_count, segments) are copied back asynchronously."""
+
+    def __init__(self, session: FireRedSession, n_streams: int, n_chunks: int, post: PP.FramePostConfig = POST_DEFAULT,
+                 device=None):
+        import torch
+        self.session, self.post = session, post
+        self.S, self.n_chunks, self.L = n_streams, n_chunks, session.chunk_len
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.T = session.frames(self.L)
+        self.max_seg = (n_chunks * self.T) // 2 + 1
+        self.d_in = [torch.empty((n_streams, n_chunks, self.L), dtype=torch.int16, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.h_cnt = [torch.empty((n_streams,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.h_seg = [torch.empty((n_streams, self.max_seg, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.n_valid = torch.full((n_streams,), min(valid_frame_count(n_chunks * self.L), n_chunks * self.T),
+                                  dtype=torch.int32, device=dev)
+        self._i = 0
+        self._prefetched = False
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.S * self.n_chunks * self.L * 2
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.h_cnt[0].numel() * 4 + self.h_seg[0].numel() * 4
+
+    def prefetch(self, pinned):
+        """enqueue the H2D copy of the NEXT batch (returns immediately)"""
+        import torch
+        b = self._i % 2
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[b])
+            self.d_in[b].copy_(pinned.view(self.S, self.n_chunks, self.L), non_blocking=True)
+            self.copied[b].record(self.copy_stream)
+        self._prefetched = True
+
+    def run(self, pinned, next_pinned=None):
+        """process one batch; if `next_pinned` is given its copy overlaps this batch's compute.
+        Returns the pinned (seg_count, segments) buffers this batch's results are being copied into
+        (valid after the current stream is synchronised)."""
+        import torch
+        if not self._prefetched:
+            self.prefetch(pinned)
+        b = self._i % 2
+        main = torch.cuda.current_stream()
+        main.wait_event(self.copied[b])
+        self._i += 1
+        self._prefetched = False
+        if next_pinned is not None:
+            self.prefetch(next_pinned)
+        _, _, cnt, seg, _ = run_vad_streams(self.session, self.d_in[b], None, self.post, n_valid=self.n_valid)
+        self.consumed[b].record(main)
+        self.h_cnt[b].copy_(cnt, non_blocking=True)
+        self.h_seg[b].copy_(seg, non_blocking=True)
+        return self.h_cnt[b], self.h_seg[b]
+
+
 def run_vad(audio, session: FireRedSession, post: PP.FramePostConfig = POST_DEFAULT, rng=None,
             save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None) -> VadResult:
     """One stream, the reference's behaviour: `audio` is a path to a wav file or an int16 array."""
