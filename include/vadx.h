@@ -101,6 +101,19 @@ int vadx_stft_power_f32(const float* d_sig, int64_t sig_stride, int64_t n_stream
                         int n_taps, const float* d_basis, int ld_basis, int n_bins, float* d_power,
                         int64_t ld_power, void* stream);
 
+/* a1 + a2 on the tensor cores, straight from int16 audio (tcgen05.mma, TMEM accumulators): valid when every
+ * frame lies inside the stream's n_samples and no DC removal is needed (FireRedVAD).  The int16 sample
+ * splits exactly into two bf16 terms; pre-emphasis (y[i] = x[i] - c*x[i-1], x[-1] = 0) and the scale are
+ * folded into the basis, which vadx_pack_stft_basis_tc splits into three bf16 terms and lays out as the
+ * shared-memory operand image (h_basis = the fp32 table of vadx_stft_power_f32; h_img = NULL queries the
+ * size).  Result: d_power[(s*T + t)*ld_power + f] = re^2 + im^2, fp32-grade. */
+int vadx_stft_tc_supported(int n_taps, int n_bins);
+int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph, double scale,
+                            void* h_img, size_t img_capacity, size_t* img_bytes);
+int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                           int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
+                           int64_t ld_power, void* stream);
+
 /* a3 -- triangular filterbank contraction + floor + ln.  The bank is passed in its sparse form:
  * filter m covers bins [start[m], start[m]+len[m]) with weights d_w[m*max_len + j].
  * out[row*ld_out + m] = ln(floor(sum_j w*power)). */

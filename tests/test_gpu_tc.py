@@ -30,7 +30,7 @@ def _run_tc(cuda, x, w, b, r, act):
     (1000, 256, 128, 0, True, False),     # FireRed fc2 (+ residual), ragged last tile
     (98 * 40, 80, 256, 1, False, True),   # first layer: K = 80 (partial k-chunk)
     (300000, 128, 256, 1, False, True),   # many tiles per CTA: exercises both ring wrap-arounds
-    (777, 140, 200, 1, False, True),      # odd sizes: K = 140 -> 3 k-chunks, N padded to 208
+    (777, 140, 170, 1, False, True),      # odd sizes: K = 140 -> 3 k-chunks, N padded to 176
     (513, 250, 140, 0, False, True),      # K = 250 -> 4 k-chunks, N padded to 144
     (64, 128, 128, 2, False, True),       # fewer rows than one tile, sigmoid
 ])
@@ -54,6 +54,36 @@ def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):
     # two-term bf16 split: <= ~3 * 2^-18 relative per product; bound it by the coherent worst case
     bound = 1.2e-5 * (x.abs().double() @ w.abs().double().T).max().item() + 1e-6
     assert err <= bound, (err, bound)
+
+
+@pytest.mark.parametrize("S,L", [(5, 16000), (300, 16000), (3, 5000), (2, 400 + 160 * 7)])
+def test_stft_power_tc_from_int16(cuda, S, L):
+    """Tensor-core DFT straight from int16 (exact sample split, folded pre-emphasis, 3-term basis)
+    against the oracle's conv-STFT of the pre-emphasised signal."""
+    from vadx import tables
+    from oracle import frontend as OF
+    import torch.nn.functional as F
+    l = lib.load()
+    assert l.vadx_stft_tc_supported(400, 201) == 1
+    L8 = L // 8 * 8
+    x = torch.from_numpy(synth.synth_streams(S, L8, seed=S + L))
+    basis, first, nb = tables.interleaved_basis(400, 400, "povey", "v2")
+    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, 1.0)).to(cuda)
+    T = 1 + (L8 - 400) // 160
+    out = torch.full((S * T, 202), float("nan"), device=cuda)
+    xd = x.to(cuda)
+    lib.check(l.vadx_stft_power_tc_i16(xd.data_ptr(), L8, L8, S, T, 160, 400, img.data_ptr(), nb, out.data_ptr(), 202,
+                                       lib.stream_ptr()))
+    torch.cuda.synchronize()
+    y = F.conv1d(F.pad(x.float().unsqueeze(1), (1, 0)), torch.tensor([[[-0.97, 1.0]]]))
+    ref = OF.stft_power(y.double().float(), OF.stft_kernel(400, 400, "povey", "v2"), 160, False)
+    ref = ref.permute(0, 2, 1).reshape(S * T, nb)
+    got = out[:, :nb].cpu()
+    assert not torch.isnan(got).any()
+    rel = ((got - ref).abs() / ref.max(dim=1, keepdim=True).values).max().item()
+    print(f"stft tc S={S} L={L8}: max err relative to the frame's strongest bin {rel:.2e}")
+    # tensor-core fp32 accumulation truncates (chains of ~130 adds): ~1e-5 of the strongest bin
+    assert rel <= 3e-5
 
 
 def test_unsupported_shapes_are_rejected(cuda):

@@ -20,16 +20,13 @@
 // bias/act/residual -> global), 8 = TMEM allocator + single-thread MMA issuer.  Two TMEM
 // accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1; a 2-4 deep
 // mbarrier ring decouples the loaders from the MMA issuer.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace vadx {
 
-constexpr int kTcBM = 128;
-constexpr int kTcBK = 64;
-constexpr int kTcTileBytes = kTcBM * 128;        // one 128-row x 64-k bf16 tile
 constexpr int kTcStageBytes = 2 * kTcTileBytes;  // hi + lo
 constexpr int kTcThreads = 288;
-constexpr int kTcSmemBudget = 227 * 1024;
+constexpr int kTcOutLd = 36;  // floats per staged row: 32 columns + 4 pad (144 B: conflict-free 16-byte accesses)
 
 struct TcArgs {
   const float* X;
@@ -42,91 +39,11 @@ struct TcArgs {
   int64_t ldy;
   int64_t M;
   int K, N, n_pad, kc, n_k16, act, n_stages, n_tiles, tmem_cols, vec_x, vec_y;
+  int debug;  // bit0: skip global stores, bit1: skip global loads (VADX_TC_DEBUG, perf experiments only)
 };
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug becomes a trap (an error the host sees), never a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 20000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8-row atoms are 1024 B apart
-  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
-// kind::f16, A = B = bf16, D = fp32, both K-major, M = 128
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// two floats -> packed (hi, lo) bf16x2 words: hi = rn(x), lo = rn(x - hi)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));  // upper half <- b, lower half <- a
-  float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-  float al = a - ah, bl = b - bh;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(bl), "f"(al));
-}
-
 // ------------------------------------------------------------------------------------------ kernel
+template <int ACT>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
 __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (base is 1024-aligned by the launch: dynamic smem starts at a 1024-aligned offset
@@ -135,7 +52,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
   const int w_bytes = g.kc * 2 * g.n_pad * 128;
   uint8_t* a_smem = w_smem + w_bytes;
   float* bias_s = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + g.n_pad);
+  float* stage_out = bias_s + g.n_pad;  // 4 warps x 32 rows x 36 floats: epilogue transpose buffer
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * kTcOutLd);
   // bars: full[4], empty[4], tmem_full[2], tmem_empty[2], wbar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
@@ -213,60 +131,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     }
   } else if (warp < 4) {
     // ===================== loaders: fp32 rows -> (hi, lo) bf16, swizzled =====================
+    // Software-pipelined: the 16 x 16-byte loads of step i+1 are in flight while step i is split and
+    // stored; rows past the end are clamped to a valid row and zeroed afterwards.
     const int t = threadIdx.x;   // 0..127
     const int kq = t & 7;        // 16-byte chunk (8 bf16) within the 64-k atom row
     const int r_in = t >> 3;     // 0..15
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    auto issue = [&](int tile, int c, float4 (*ld)[2]) {
       const int64_t row0 = (int64_t)tile * kTcBM;
-      for (int c = 0; c < g.kc; ++c) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
-        uint8_t* st_lo = st_hi + kTcTileBytes;
-        const int k = c * kTcBK + kq * 8;
-        // issue every global load of the stage before touching the data (16 x 16 B in flight per
-        // thread); rows past the end are clamped to a valid row and zeroed afterwards
-        float4 ld[8][2];
-        const bool vec = g.vec_x && (k + 7 < g.K);
-        if (vec) {
+      const int k = c * kTcBK + kq * 8;
+      if (g.debug & 2) {
 #pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
-            const float4* src = reinterpret_cast<const float4*>(g.X + row * g.ldx + k);
-            ld[pass][0] = __ldg(src);
-            ld[pass][1] = __ldg(src + 1);
-          }
-        } else {
-#pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
-            const float* src = g.X + row * g.ldx + k;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (k + j < g.K) ? __ldg(src + j) : 0.f;
-            ld[pass][0] = make_float4(v[0], v[1], v[2], v[3]);
-            ld[pass][1] = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        }
+        for (int pass = 0; pass < 8; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
+      } else if (g.vec_x && (k + 7 < g.K)) {
 #pragma unroll
         for (int pass = 0; pass < 8; ++pass) {
-          const int r = pass * 16 + r_in;
-          float4 p0 = ld[pass][0], p1 = ld[pass][1];
-          if (row0 + r >= g.M) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          uint4 hi, lo;
-          split2(p0.x, p0.y, hi.x, lo.x);
-          split2(p0.z, p0.w, hi.y, lo.y);
-          split2(p1.x, p1.y, hi.z, lo.z);
-          split2(p1.z, p1.w, hi.w, lo.w);
-          const int off = r * 128 + ((kq ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(st_hi + off) = hi;
-          *reinterpret_cast<uint4*>(st_lo + off) = lo;
+          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+          const float4* src = reinterpret_cast<const float4*>(g.X + row * g.ldx + k);
+          ld[pass][0] = __ldg(src);
+          ld[pass][1] = __ldg(src + 1);
         }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(full_bar(stage));
-        if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
+      } else {
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+          const float* src = g.X + row * g.ldx + k;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (k + j < g.K) ? __ldg(src + j) : 0.f;
+          ld[pass][0] = make_float4(v[0], v[1], v[2], v[3]);
+          ld[pass][1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float4 cur[8][2], nxt[8][2];
+    int tile = blockIdx.x, c = 0;
+    if (tile < g.n_tiles) issue(tile, 0, cur);
+    while (tile < g.n_tiles) {
+      int tile_n = tile, nc = c + 1;
+      if (nc == g.kc) { nc = 0; tile_n += gridDim.x; }
+      if (tile_n < g.n_tiles) issue(tile_n, nc, nxt);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
+      uint8_t* st_lo = st_hi + kTcTileBytes;
+      const int64_t row0 = (int64_t)tile * kTcBM;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = pass * 16 + r_in;
+        float4 p0 = cur[pass][0], p1 = cur[pass][1];
+        if (row0 + r >= g.M) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 hi, lo;
+        split2(p0.x, p0.y, hi.x, lo.x);
+        split2(p0.z, p0.w, hi.y, lo.y);
+        split2(p1.x, p1.y, hi.z, lo.z);
+        split2(p1.z, p1.w, hi.w, lo.w);
+        const int off = r * 128 + ((kq ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(st_hi + off) = hi;
+        *reinterpret_cast<uint4*>(st_lo + off) = lo;
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(stage));
+      if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        cur[pass][0] = nxt[pass][0];
+        cur[pass][1] = nxt[pass][1];
+      }
+      tile = tile_n;
+      c = nc;
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -280,45 +213,87 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * g.n_pad);
-      for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        if (!row_ok || c0 >= g.N) continue;
-        const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
+      if (!g.res && g.vec_y && !(g.debug & 1) && !(g.debug & 8)) {
+        // coalesced path: each thread stages 32 columns of its row in shared memory, then the warp
+        // writes them out 4 rows x 128 B per instruction (row-per-thread stores would touch 32
+        // different 128-byte lines per instruction and saturate the LSU tag stage)
+        float* my = stage_out + (q * 32) * kTcOutLd;
+        const int64_t tile_row0 = (int64_t)tile * kTcBM + q * 32;
+        for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          if (c0 + 16 < g.n_pad) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
-        if (!res_first) {
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j;
+            v[j] = col < g.n_pad ? apply_act(v[j] + bias_s[col < g.n_pad ? col : 0], ACT) : 0.f;
+          }
+          float4* dst = reinterpret_cast<float4*>(my + lane * kTcOutLd);
+          if (!(g.debug & 16))
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act);
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          if (!(g.debug & 32))
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int r = itr * 4 + (lane >> 3);
+            const int cc = c0 + (lane & 7) * 4;
+            const int64_t grow = tile_row0 + r;
+            if (grow < g.M && cc < g.N && !(g.debug & 4)) {
+              const float4 val = *reinterpret_cast<const float4*>(my + r * kTcOutLd + (lane & 7) * 4);
+              float* out = g.Y + grow * g.ldy + cc;
+              if (cc + 3 < g.N) {
+                *reinterpret_cast<float4*>(out) = val;
+              } else {
+                out[0] = val.x;
+                if (cc + 1 < g.N) out[1] = val.y;
+                if (cc + 2 < g.N) out[2] = val.z;
+              }
+            }
+          }
+          __syncwarp();
         }
-        float* out = g.Y + row * g.ldy + c0;
-        const float* rs = g.res ? g.res + row * g.ldr + c0 : nullptr;
-        const bool vec = g.vec_y && c0 + 15 < g.N;
-        if (rs) {
+      } else {
+      for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          if (!row_ok || c0 >= g.N || (g.debug & 1)) continue;
+          const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+          if (!res_first) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], ACT);
+          }
+          float* out = g.Y + row * g.ldy + c0;
+          const float* rs = g.res ? g.res + row * g.ldr + c0 : nullptr;
+          const bool vec = g.vec_y && c0 + 15 < g.N;
+          if (rs) {
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 r4 = __ldg(reinterpret_cast<const float4*>(rs) + j);
+                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < g.N) v[j] += rs[j];
+            }
+          }
+          if (res_first) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], ACT);
+          }
           if (vec) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 r4 = __ldg(reinterpret_cast<const float4*>(rs) + j);
-              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-            }
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < g.N) v[j] += rs[j];
+              if (c0 + j < g.N) out[j] = v[j];
           }
-        }
-        if (res_first) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], g.act);
-        }
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < g.N) out[j] = v[j];
         }
       }
       tc_fence_before();
@@ -360,7 +335,7 @@ TcShape tc_shape(int n_in, int n_out) {
   s.kc = (int)ceil_div(n_in, kTcBK);
   s.n_k16 = (int)ceil_div(n_in, 16);
   s.w_bytes = (size_t)s.kc * 2 * s.n_pad * 128;
-  const size_t misc = (size_t)s.n_pad * 4 + 13 * 8 + 16;
+  const size_t misc = (size_t)s.n_pad * 4 + (size_t)4 * 32 * kTcOutLd * 4 + 13 * 8 + 16;
   s.ok = s.n_pad <= 256 && n_out > 8;
   if (s.ok) {
     size_t left = kTcSmemBudget > s.w_bytes + misc ? kTcSmemBudget - s.w_bytes - misc : 0;
@@ -420,7 +395,9 @@ extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_w
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_tc_kernel)");
     configured = true;
   }
@@ -431,9 +408,22 @@ extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_w
   int64_t tiles = ceil_div(n_rows, kTcBM);
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_linear_tc_f32: too many rows");
   g.n_tiles = (int)tiles;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("VADX_TC_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    g.debug = dbg;
+  }
   g.vec_x = ((ldx & 3) == 0) && aligned16(d_x);
   g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
   int grid = (int)std::min<int64_t>(tiles, n_sm > 0 ? n_sm : 148);
-  linear_tc_kernel<<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  switch (act & 15) {
+    case VADX_ACT_NONE: linear_tc_kernel<VADX_ACT_NONE><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
+    case VADX_ACT_RELU: linear_tc_kernel<VADX_ACT_RELU><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
+    case VADX_ACT_SIGMOID: linear_tc_kernel<VADX_ACT_SIGMOID><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
+    default: set_error("vadx_linear_tc_f32: activation %d is not supported", act); return VADX_EINVAL;
+  }
   return after_launch("vadx_linear_tc_f32");
 }

@@ -9,7 +9,7 @@ struct FireRedHP {
   int n_taps() const { return win < n_fft ? win : n_fft; }
   int n_bins() const { return n_fft / 2 + 1; }
   int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
-  int ld_power() const { return (int)round_up(n_bins(), 2); }
+  int ld_power() const { return (int)round_up(n_bins(), 4); }
   int frames(int64_t L) const { return L < n_taps() ? 0 : (int)(1 + (L - n_taps()) / hop); }
 };
 
@@ -28,6 +28,16 @@ int firered_finalize(vadx_model* m) {
   FireRedHP h;
   VADX_TRY(firered_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
+  if (vadx_stft_tc_supported(h.n_taps(), h.n_bins())) {
+    // tensor-core DFT image: pre-emphasis folded into the 3-term bf16 basis (stft_tc.cu)
+    const double preemph = m->scalar("frontend.preemph", 0.97);
+    size_t bytes = 0;
+    const float* hb = m->find("frontend.basis")->f32();
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, nullptr, 0, &bytes));
+    std::vector<uint8_t> img(bytes);
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, img.data(), img.size(), &bytes));
+    VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
+  }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
@@ -103,11 +113,18 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   const HostTensor* melw = m->find("frontend.mel_w");
   const int mel_max = (int)(melw->numel() / h.n_mels);
 
-  // process at most 65535 streams per launch group (grid.y limit of the per-stream kernels)
-  VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0,
-                           preemph, 0, sig, Lp, st));
-  VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
-                               h.n_bins(), power, h.ld_power(), st));
+  const bool use_tc_all = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const uint8_t* stft_img = use_tc_all ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
+  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
+    // int16 audio -> power in one tensor-core kernel (exact sample split, folded pre-emphasis)
+    VADX_TRY(vadx_stft_power_tc_i16(static_cast<const int16_t*>(d_audio), L, L, S, T, h.hop, h.n_taps(), stft_img,
+                                    h.n_bins(), power, h.ld_power(), st));
+  } else {
+    VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0,
+                             preemph, 0, sig, Lp, st));
+    VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                                 h.n_bins(), power, h.ld_power(), st));
+  }
   VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
                             VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
@@ -215,6 +232,7 @@ extern "C" int vadx_set_tensor(vadx_model* m, const char* name, const void* h_da
 
 extern "C" int vadx_set_scalar(vadx_model* m, const char* name, double value) {
   VADX_REQUIRE(m && name, "vadx_set_scalar: null pointer");
+  if (!strncmp(name, "frontend.", 9)) m->finalized = false;  // folded into device-side constants
   m->scalars[name] = value;
   return VADX_OK;
 }

@@ -1,0 +1,360 @@
+// stft_tc.cu -- framed real DFT + power (a1 + a2) on the tensor cores, straight from int16 audio.
+//
+//   power[(s*T + t)][f] = | sum_n y[s][t*hop + n] * w[n] e^{-i 2 pi f n / n_fft} |^2 ,
+//   y[i] = scale * (x[i] - c * x[i-1])            (x int16, x[-1] = 0: the reference's pad(1,0)+conv)
+//
+// as ONE bf16 tensor-core GEMM with fp32-grade accuracy and no prepared-signal round trip:
+//   * an int16 sample splits EXACTLY into two bf16 terms, x = 256*(x >> 8) + (x & 255);
+//   * pre-emphasis and the int16 scale are folded into the basis on the host, in double:
+//       B'[k][col] = scale * (b[k-8][col] - c * b[k-7][col])      (k-8 = tap index; 8 leading zero
+//     rows keep every 8-sample group of a frame 16-byte aligned and make room for the x[i-1] tap);
+//   * B' is split into THREE bf16 terms (24 bits), and x_hi*b0 + x_lo*b0 + x_hi*b1 + x_lo*b1 + x_hi*b2
+//     is accumulated in fp32 TMEM -- the dropped x_lo*b2 is < 2^-23 of full scale.
+// Valid when every frame lies inside [0, L) and no DC removal is requested (FireRedVAD); the
+// centre-padded / DC-removed frontends keep the fp32 kernel.
+//
+// Work decomposition: the (re, im)-interleaved output columns are cut into N-tiles of 48; a CTA keeps
+// the 3-term basis image of ITS N-tile resident in shared memory (129 KB, fetched once with
+// cp.async.bulk) and streams 128-frame row tiles through a 3-deep mbarrier ring.  Same warp roles
+// as gemm_tc.cu: 4 loader warps (int16 -> (hi, lo) bf16, swizzled), 1 MMA issuer, 4 epilogue warps
+// (TMEM -> re^2+im^2 -> global), two TMEM accumulators in ping-pong.
+#include "tc_ptx.cuh"
+
+namespace vadx {
+
+constexpr int kStNPad = 48;                          // columns per N-tile (24 bins)
+constexpr int kStLead = 8;                           // leading zero rows of the folded basis
+constexpr int kStStageBytes = 2 * kTcTileBytes;      // x_hi + x_lo
+constexpr int kStStages = 3;
+constexpr int kStThreads = 288;
+
+struct StftTcArgs {
+  const int16_t* X;
+  int64_t in_stride;   // samples between streams
+  int64_t L;           // valid samples per stream
+  int n_frames, hop;
+  const uint8_t* Wimg;  // [n_ntiles][kc][3][kStNPad*128]
+  float* P;
+  int64_t ldp;
+  int64_t M;           // S * n_frames
+  int n_bins, kc, n_k16, n_tiles, vec_p;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16_pair_from_ints(int a, int b) {
+  // integers with <= 8 significant bits are exact in bf16
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"((float)b), "f"((float)a));
+  return r;
+}
+
+__global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const StftTcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* w_smem = smem_raw;
+  const uint32_t img_bytes = kStNPad * 128u;
+  const int w_bytes = g.kc * 3 * (int)img_bytes;
+  uint8_t* a_smem = w_smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)kStStages * kStStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (10 + b); };
+  const uint32_t wbar = bar0 + 8u * 12;
+  constexpr uint32_t kTmemCols = 128;  // 2 x 48 accumulator columns
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ntile = blockIdx.y;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)w_bytes);
+      const uint8_t* src = g.Wimg + (size_t)ntile * w_bytes;
+      for (int t = 0; t < g.kc * 3; ++t) bulk_g2s(smem_u32(w_smem) + t * img_bytes, src + (size_t)t * img_bytes, img_bytes, wbar);
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma_idesc_bf16(kStNPad);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * kStNPad);
+        for (int c = 0; c < g.kc; ++c) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_smem) + (uint32_t)stage * kStStageBytes;
+          const uint32_t a_lo = a_hi + kTcTileBytes;
+          const uint32_t w0 = smem_u32(w_smem) + (uint32_t)(c * 3) * img_bytes;
+          const uint32_t w1 = w0 + img_bytes, w2 = w1 + img_bytes;
+          const int nk = min(4, g.n_k16 - c * 4);
+          // smallest contributions first would be numerically nicer, but the first MMA of a tile must
+          // overwrite the accumulator; the order below keeps that one the dominant x_hi * b0 term
+          for (int j = 0; j < nk; ++j)
+            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, (c | j) ? 1u : 0u);
+          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, 1u);
+          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
+          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
+          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w2 + 32u * j), idesc, 1u);
+          umma_commit(empty_bar(stage));
+          if (++stage == kStStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(b));
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== loaders: int16 frames -> exact (hi, lo) bf16 =====================
+    // Software-pipelined: the 8 x 16-byte loads of step i+1 are in flight while step i is converted
+    // and stored, so the L2/HBM latency is paid once per CTA, not once per stage.
+    const int t = threadIdx.x;
+    const int kq = t & 7;      // group of 8 consecutive samples
+    const int r_in = t >> 3;   // 0..15
+    // frame origins of this thread's 8 rows in the tile being PREFETCHED (recomputed once per tile:
+    // the 64-bit divisions must not sit on the per-stage path)
+    const int16_t* xs_n[8];
+    int forig_n[8];
+    int tile_cached = -1;
+    auto issue = [&](int tile, int c, uint4* raw) {
+      if (tile != tile_cached) {
+        const int64_t row0 = (int64_t)tile * kTcBM;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+          const int64_t s = row / g.n_frames;
+          const int fr = (int)(row - s * g.n_frames);
+          xs_n[pass] = g.X + s * g.in_stride;
+          forig_n[pass] = fr * g.hop - kStLead;
+        }
+        tile_cached = tile;
+      }
+      const int k = c * kTcBK + kq * 8;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int16_t* xs = xs_n[pass];
+        const int i0 = forig_n[pass] + k;  // first of 8 consecutive samples (stream-relative)
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 >= 0 && i0 + 7 < g.L) {
+          v = __ldg(reinterpret_cast<const uint4*>(xs + i0));
+        } else if (i0 + 7 >= 0 && i0 < g.L) {
+          uint16_t tmp[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int i = i0 + j;
+            tmp[j] = (i >= 0 && i < g.L) ? (uint16_t)__ldg(xs + i) : (uint16_t)0;
+          }
+          v.x = tmp[0] | ((uint32_t)tmp[1] << 16);
+          v.y = tmp[2] | ((uint32_t)tmp[3] << 16);
+          v.z = tmp[4] | ((uint32_t)tmp[5] << 16);
+          v.w = tmp[6] | ((uint32_t)tmp[7] << 16);
+        }
+        raw[pass] = v;
+      }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    uint4 cur[8], nxt[8];
+    int tile = blockIdx.x, c = 0;
+    if (tile < g.n_tiles) issue(tile, 0, cur);
+    while (tile < g.n_tiles) {
+      int tile_n = tile, nc = c + 1;
+      if (nc == g.kc) { nc = 0; tile_n += gridDim.x; }
+      if (tile_n < g.n_tiles) issue(tile_n, nc, nxt);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
+      uint8_t* st_lo = st_hi + kTcTileBytes;
+      const int64_t row0 = (int64_t)tile * kTcBM;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = pass * 16 + r_in;
+        const uint32_t wds[4] = {cur[pass].x, cur[pass].y, cur[pass].z, cur[pass].w};
+        uint32_t hi[4], lo[4];
+        const bool live = row0 + r < g.M;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int a = live ? (int)(int16_t)(wds[j] & 0xffffu) : 0;
+          const int b = live ? (int)(int16_t)(wds[j] >> 16) : 0;
+          hi[j] = pack_bf16_pair_from_ints((a >> 8) * 256, (b >> 8) * 256);  // multiples of 256 up to 2^15: exact
+          lo[j] = pack_bf16_pair_from_ints(a & 255, b & 255);
+        }
+        const int off = r * 128 + ((kq ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(stage));
+      if (++stage == kStStages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) cur[pass] = nxt[pass];
+      tile = tile_n;
+      c = nc;
+    }
+  } else {
+    // ===================== epilogue: re^2 + im^2 =====================
+    const int q = warp - 4;
+    int it = 0;
+    const int f0 = ntile * (kStNPad / 2);
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tfull_bar(b), use & 1u);
+      tc_fence_after();
+      const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * kStNPad);
+#pragma unroll
+      for (int c0 = 0; c0 < kStNPad; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (!row_ok) continue;
+        float* out = g.P + row * g.ldp + f0 + c0 / 2;
+        float pw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pw[j] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+        const int fb = f0 + c0 / 2;
+        if (g.vec_p && fb + 7 < g.n_bins) {
+          reinterpret_cast<float4*>(out)[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+          reinterpret_cast<float4*>(out)[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (fb + j < g.n_bins) out[j] = pw[j];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(b));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+struct StftTcShape {
+  int kc, n_k16, n_ntiles;
+  size_t tile_bytes, img_bytes, smem_bytes;
+  bool ok;
+};
+StftTcShape stft_tc_shape(int n_taps, int n_bins) {
+  StftTcShape s{};
+  const int k_used = n_taps + kStLead;
+  s.kc = (int)ceil_div(k_used, kTcBK);
+  s.n_k16 = (int)ceil_div(k_used, 16);
+  s.n_ntiles = (int)ceil_div(2 * n_bins, kStNPad);
+  s.tile_bytes = (size_t)s.kc * 3 * kStNPad * 128;
+  s.img_bytes = s.tile_bytes * s.n_ntiles;
+  s.smem_bytes = s.tile_bytes + (size_t)kStStages * kStStageBytes + 13 * 8 + 16;
+  s.ok = s.smem_bytes <= (size_t)kTcSmemBudget;
+  return s;
+}
+
+}  // namespace vadx
+
+using namespace vadx;
+
+extern "C" int vadx_stft_tc_supported(int n_taps, int n_bins) { return stft_tc_shape(n_taps, n_bins).ok ? 1 : 0; }
+
+// h_basis: the fp32 table of vadx_stft_power_f32 ([n_taps][ld_basis], re/im interleaved).  The loader
+// feeds the operand pair (256*(x >> 8), x & 255) -- both exact in bf16 -- so one image per basis term
+// serves both halves of the sample.
+extern "C" int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph,
+                                       double scale, void* h_img, size_t img_capacity, size_t* img_bytes) {
+  VADX_REQUIRE(h_basis && img_bytes && n_taps > 0 && n_bins > 0 && ld_basis >= 2 * n_bins,
+               "vadx_pack_stft_basis_tc: bad argument");
+  StftTcShape s = stft_tc_shape(n_taps, n_bins);
+  VADX_REQUIRE(s.ok, "vadx_pack_stft_basis_tc: %d taps x %d bins does not fit the tensor-core DFT", n_taps, n_bins);
+  *img_bytes = s.img_bytes;
+  if (!h_img) return VADX_OK;
+  VADX_REQUIRE(img_capacity >= s.img_bytes, "vadx_pack_stft_basis_tc: image buffer too small");
+  uint8_t* img = static_cast<uint8_t*>(h_img);
+  memset(img, 0, s.img_bytes);
+  const int n_cols = 2 * n_bins;
+  const size_t term = (size_t)kStNPad * 128;
+  for (int col = 0; col < n_cols; ++col) {
+    const int nt = col / kStNPad, r = col % kStNPad;
+    for (int k = 0; k < n_taps + kStLead; ++k) {
+      const int n0 = k - kStLead, n1 = k - kStLead + 1;  // y[n0] uses x[i] (+1), y[n1] uses x[i] (-c)
+      double v = 0.0;
+      if (n0 >= 0 && n0 < n_taps) v += (double)h_basis[(size_t)n0 * ld_basis + col];
+      if (n1 >= 0 && n1 < n_taps) v -= preemph * (double)h_basis[(size_t)n1 * ld_basis + col];
+      v *= scale;
+      const float f = (float)v;
+      const uint16_t b0 = bf16_rn_host(f);
+      const float r1 = (float)(v - (double)bf16_to_f_host(b0));
+      const uint16_t b1 = bf16_rn_host(r1);
+      const float r2 = (float)(v - (double)bf16_to_f_host(b0) - (double)bf16_to_f_host(b1));
+      const uint16_t b2 = bf16_rn_host(r2);
+      const int c = k / kTcBK, kk = k % kTcBK;
+      uint8_t* base = img + (size_t)nt * s.tile_bytes + (size_t)(c * 3) * term + sw128_offset(r, kk);
+      memcpy(base, &b0, 2);
+      memcpy(base + term, &b1, 2);
+      memcpy(base + 2 * term, &b2, 2);
+    }
+  }
+  return VADX_OK;
+}
+
+extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                                      int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
+                                      int64_t ld_power, void* stream) {
+  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
+  VADX_REQUIRE(d_audio && d_img && d_power, "vadx_stft_power_tc_i16: null pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0 && ld_power >= n_bins,
+               "vadx_stft_power_tc_i16: bad shape");
+  VADX_REQUIRE((int64_t)(n_frames - 1) * hop + n_taps <= n_samples && in_stride >= n_samples,
+               "vadx_stft_power_tc_i16: frames must lie inside the %lld samples of a stream", (long long)n_samples);
+  VADX_REQUIRE((in_stride % 8) == 0 && (hop % 8) == 0 && aligned16(d_audio) && aligned16(d_img),
+               "vadx_stft_power_tc_i16: stream stride and hop must be multiples of 8 samples, pointers 16-byte aligned");
+  StftTcShape s = stft_tc_shape(n_taps, n_bins);
+  VADX_REQUIRE(s.ok, "vadx_stft_power_tc_i16: shape not supported");
+  if (n_streams == 0) return VADX_OK;
+  static int n_sm = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_power_tc_kernel)");
+    configured = true;
+  }
+  StftTcArgs g{};
+  g.X = d_audio; g.in_stride = in_stride; g.L = n_samples; g.n_frames = n_frames; g.hop = hop;
+  g.Wimg = static_cast<const uint8_t*>(d_img); g.P = d_power; g.ldp = ld_power; g.M = n_streams * n_frames;
+  g.n_bins = n_bins; g.kc = s.kc; g.n_k16 = s.n_k16;
+  g.vec_p = ((ld_power & 3) == 0) && aligned16(d_power);
+  int64_t tiles = ceil_div(g.M, kTcBM);
+  VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_stft_power_tc_i16: too many rows");
+  g.n_tiles = (int)tiles;
+  int per = std::max(1, (n_sm > 0 ? n_sm : 148) / s.n_ntiles);
+  dim3 grid((unsigned)std::min<int64_t>(tiles, per), (unsigned)s.n_ntiles);
+  stft_power_tc_kernel<<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  return after_launch("vadx_stft_power_tc_i16");
+}

@@ -38,6 +38,9 @@ SIGNATURES = {
     "vadx_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _i32]),
     "vadx_prep_audio": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _f32, _i32, _i32, _f32, _i64, _vp, _i64, _vp]),
     "vadx_stft_power_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "vadx_stft_tc_supported": (C.c_int, [_i32, _i32]),
+    "vadx_pack_stft_basis_tc": (C.c_int, [_vp, _i32, _i32, _i32, C.c_double, C.c_double, _vp, _sz, C.POINTER(_sz)]),
+    "vadx_stft_power_tc_i16": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "vadx_mel_log_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i64, _vp]),
     "vadx_linear_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_tc_supported": (C.c_int, [_i32, _i32]),
@@ -127,6 +130,19 @@ def pack_weight_tc(w):
     check(load().vadx_pack_weight_tc(w.ctypes.data, n_out, n_in, None, 0, C.byref(nbytes)))
     img = np.zeros(nbytes.value, np.uint8)
     check(load().vadx_pack_weight_tc(w.ctypes.data, n_out, n_in, img.ctypes.data, img.nbytes, C.byref(nbytes)))
+    return img
+
+
+def pack_stft_basis_tc(basis, n_bins: int, preemph: float, scale: float):
+    """[n_taps, ld] fp32 interleaved basis table -> uint8 operand image for vadx_stft_power_tc_i16."""
+    import numpy as np
+    basis = np.ascontiguousarray(basis, np.float32)
+    n_taps, ld = basis.shape
+    nbytes = C.c_size_t()
+    check(load().vadx_pack_stft_basis_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, None, 0, C.byref(nbytes)))
+    img = np.zeros(nbytes.value, np.uint8)
+    check(load().vadx_pack_stft_basis_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, img.ctypes.data,
+                                         img.nbytes, C.byref(nbytes)))
     return img
 
 
