@@ -67,12 +67,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), 4);     // one elected lane per loader warp
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), 4);   // one elected lane per epilogue warp
     }
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
         *reinterpret_cast<uint4*>(st_lo + off) = lo;
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(full_bar(stage));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) {
@@ -297,7 +298,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(b));
     }
   }
   tc_fence_before();

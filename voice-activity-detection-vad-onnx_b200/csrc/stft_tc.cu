@@ -22,10 +22,11 @@
 
 namespace vadx {
 
-constexpr int kStNPad = 48;                          // columns per N-tile (24 bins)
+constexpr int kStNPad = 80;                          // columns per N-tile (40 bins)
+constexpr int kStTerms = 2;                          // bf16 terms of the folded basis
 constexpr int kStLead = 8;                           // leading zero rows of the folded basis
 constexpr int kStStageBytes = 2 * kTcTileBytes;      // x_hi + x_lo
-constexpr int kStStages = 3;
+constexpr int kStStages = 2;
 constexpr int kStThreads = 288;
 
 struct StftTcArgs {
@@ -38,20 +39,32 @@ struct StftTcArgs {
   int64_t ldp;
   int64_t M;           // S * n_frames
   int n_bins, kc, n_k16, n_tiles, vec_p;
+  int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
-__device__ __forceinline__ uint32_t pack_bf16_pair_from_ints(int a, int b) {
-  // integers with <= 8 significant bits are exact in bf16
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"((float)b), "f"((float)a));
-  return r;
+// Exact int -> bf16 without the (quarter-rate) conversion pipe: for 0 <= v < 2^23,
+// as_float(0x4B000000 | v) == 8388608 + v, so one FADD/FFMA yields float(v); integers with <= 8
+// significant bits are exact in bf16, i.e. the bf16 word is just the upper half of the fp32 word.
+__device__ __forceinline__ uint32_t bf16x2_lo(uint32_t w) {
+  // (w & 0xff) and ((w >> 16) & 0xff): the low bytes of the two packed int16 samples, both in [0, 255]
+  const float a = __uint_as_float(0x4B000000u | (w & 0xffu)) - 8388608.0f;
+  const float b = __uint_as_float(0x4B000000u | ((w >> 16) & 0xffu)) - 8388608.0f;
+  return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+__device__ __forceinline__ uint32_t bf16x2_hi(uint32_t w) {
+  // 256 * (x >> 8) for the two packed int16 samples: ((x >> 8) + 128) is in [0, 255]
+  const uint32_t ha = (((w >> 8) & 0xffu) ^ 0x80u);          // (x_a >> 8) + 128 (two's complement high byte)
+  const uint32_t hb = (((w >> 24) & 0xffu) ^ 0x80u);
+  const float a = fmaf(__uint_as_float(0x4B000000u | ha), 256.0f, -(8388608.0f + 128.0f) * 256.0f);
+  const float b = fmaf(__uint_as_float(0x4B000000u | hb), 256.0f, -(8388608.0f + 128.0f) * 256.0f);
+  return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
 }
 
 __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const StftTcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* w_smem = smem_raw;
   const uint32_t img_bytes = kStNPad * 128u;
-  const int w_bytes = g.kc * 3 * (int)img_bytes;
+  const int w_bytes = g.kc * kStTerms * (int)img_bytes;
   uint8_t* a_smem = w_smem + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)kStStages * kStStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
@@ -63,16 +76,16 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
   auto tfull_bar = [&](int b) { return bar0 + 8u * (8 + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (10 + b); };
   const uint32_t wbar = bar0 + 8u * 12;
-  constexpr uint32_t kTmemCols = 128;  // 2 x 48 accumulator columns
+  constexpr uint32_t kTmemCols = 256;  // 2 x 80 accumulator columns
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), 4);     // one elected lane per loader warp
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), 4);   // one elected lane per epilogue warp
     }
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -93,7 +106,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     if (lane == 0) {
       mbar_expect_tx(wbar, (uint32_t)w_bytes);
       const uint8_t* src = g.Wimg + (size_t)ntile * w_bytes;
-      for (int t = 0; t < g.kc * 3; ++t) bulk_g2s(smem_u32(w_smem) + t * img_bytes, src + (size_t)t * img_bytes, img_bytes, wbar);
+      for (int t = 0; t < g.kc * kStTerms; ++t) bulk_g2s(smem_u32(w_smem) + t * img_bytes, src + (size_t)t * img_bytes, img_bytes, wbar);
       mbar_wait(wbar, 0);
       const uint32_t idesc = umma_idesc_bf16(kStNPad);
       int stage = 0;
@@ -110,17 +123,18 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
           tc_fence_after();
           const uint32_t a_hi = smem_u32(a_smem) + (uint32_t)stage * kStStageBytes;
           const uint32_t a_lo = a_hi + kTcTileBytes;
-          const uint32_t w0 = smem_u32(w_smem) + (uint32_t)(c * 3) * img_bytes;
-          const uint32_t w1 = w0 + img_bytes, w2 = w1 + img_bytes;
+          const uint32_t w0 = smem_u32(w_smem) + (uint32_t)(c * kStTerms) * img_bytes;
+          const uint32_t w1 = w0 + img_bytes;
           const int nk = min(4, g.n_k16 - c * 4);
           // smallest contributions first would be numerically nicer, but the first MMA of a tile must
           // overwrite the accumulator; the order below keeps that one the dominant x_hi * b0 term
           for (int j = 0; j < nk; ++j)
             umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, (c | j) ? 1u : 0u);
+          if (!(g.debug & 4)) {
           for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, 1u);
           for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
           for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
-          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w2 + 32u * j), idesc, 1u);
+          }
           umma_commit(empty_bar(stage));
           if (++stage == kStStages) { stage = 0; phase ^= 1u; }
         }
@@ -158,7 +172,9 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         const int16_t* xs = xs_n[pass];
         const int i0 = forig_n[pass] + k;  // first of 8 consecutive samples (stream-relative)
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (i0 >= 0 && i0 + 7 < g.L) {
+        if (g.debug & 2) {
+          v = make_uint4(0x00010002u, 0x00030004u, 0x00050006u, 0x00070008u);
+        } else if (i0 >= 0 && i0 + 7 < g.L) {
           v = __ldg(reinterpret_cast<const uint4*>(xs + i0));
         } else if (i0 + 7 >= 0 && i0 < g.L) {
           uint16_t tmp[8];
@@ -188,6 +204,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
       const int64_t row0 = (int64_t)tile * kTcBM;
+      if (!(g.debug & 8))
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) {
         const int r = pass * 16 + r_in;
@@ -196,17 +213,17 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         const bool live = row0 + r < g.M;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int a = live ? (int)(int16_t)(wds[j] & 0xffffu) : 0;
-          const int b = live ? (int)(int16_t)(wds[j] >> 16) : 0;
-          hi[j] = pack_bf16_pair_from_ints((a >> 8) * 256, (b >> 8) * 256);  // multiples of 256 up to 2^15: exact
-          lo[j] = pack_bf16_pair_from_ints(a & 255, b & 255);
+          const uint32_t w = live ? wds[j] : 0u;
+          hi[j] = bf16x2_hi(w);
+          lo[j] = bf16x2_lo(w);
         }
         const int off = r * 128 + ((kq ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      fence_proxy_async();
-      mbar_arrive(full_bar(stage));
+      if (!(g.debug & 16)) fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == kStStages) { stage = 0; phase ^= 1u; }
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) cur[pass] = nxt[pass];
@@ -230,7 +247,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       for (int c0 = 0; c0 < kStNPad; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
-        if (!row_ok) continue;
+        if (!row_ok || (g.debug & 1)) continue;
         float* out = g.P + row * g.ldp + f0 + c0 / 2;
         float pw[8];
 #pragma unroll
@@ -246,7 +263,8 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(b));
     }
   }
   tc_fence_before();
@@ -268,7 +286,7 @@ StftTcShape stft_tc_shape(int n_taps, int n_bins) {
   s.kc = (int)ceil_div(k_used, kTcBK);
   s.n_k16 = (int)ceil_div(k_used, 16);
   s.n_ntiles = (int)ceil_div(2 * n_bins, kStNPad);
-  s.tile_bytes = (size_t)s.kc * 3 * kStNPad * 128;
+  s.tile_bytes = (size_t)s.kc * kStTerms * kStNPad * 128;
   s.img_bytes = s.tile_bytes * s.n_ntiles;
   s.smem_bytes = s.tile_bytes + (size_t)kStStages * kStStageBytes + 13 * 8 + 16;
   s.ok = s.smem_bytes <= (size_t)kTcSmemBudget;
@@ -309,13 +327,10 @@ extern "C" int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n
       const uint16_t b0 = bf16_rn_host(f);
       const float r1 = (float)(v - (double)bf16_to_f_host(b0));
       const uint16_t b1 = bf16_rn_host(r1);
-      const float r2 = (float)(v - (double)bf16_to_f_host(b0) - (double)bf16_to_f_host(b1));
-      const uint16_t b2 = bf16_rn_host(r2);
       const int c = k / kTcBK, kk = k % kTcBK;
-      uint8_t* base = img + (size_t)nt * s.tile_bytes + (size_t)(c * 3) * term + sw128_offset(r, kk);
+      uint8_t* base = img + (size_t)nt * s.tile_bytes + (size_t)(c * kStTerms) * term + sw128_offset(r, kk);
       memcpy(base, &b0, 2);
       memcpy(base + term, &b1, 2);
-      memcpy(base + 2 * term, &b2, 2);
     }
   }
   return VADX_OK;
@@ -350,6 +365,14 @@ extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride,
   g.Wimg = static_cast<const uint8_t*>(d_img); g.P = d_power; g.ldp = ld_power; g.M = n_streams * n_frames;
   g.n_bins = n_bins; g.kc = s.kc; g.n_k16 = s.n_k16;
   g.vec_p = ((ld_power & 3) == 0) && aligned16(d_power);
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("VADX_TC_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    g.debug = dbg;
+  }
   int64_t tiles = ceil_div(g.M, kTcBM);
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_stft_power_tc_i16: too many rows");
   g.n_tiles = (int)tiles;
