@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
   const int t0 = blockIdx.x * tile_t;
   const int t1 = min(t0 + tile_t, n_frames);
   const float* ps = p + s * (int64_t)n_frames * ldp + c;
+  const float* rs = res ? res + s * (int64_t)n_frames * ldr + c : nullptr;
+  float* os = out + s * (int64_t)n_frames * ldo + c;
   auto load = [&](int t) -> float {
     if (t >= 0 && t < n_frames) return __ldg(ps + (int64_t)t * ldp);
     if (t < 0 && cache_in) return cache_in[(s * C + c) * (int64_t)HL + (HL + t)];
@@ -175,21 +177,35 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
   float w[W];
 #pragma unroll
   for (int j = 0; j < HL + HR; ++j) w[j] = load(t0 - HL + j);
-  float nxt[kMemR];
+  float nxt[kMemR], rv[kMemR];
 #pragma unroll
   for (int r = 0; r < kMemR; ++r) nxt[r] = load(t0 + HR + r);
   for (int tb = t0; tb < t1; tb += kMemR) {
 #pragma unroll
     for (int r = 0; r < kMemR; ++r) w[HL + HR + r] = nxt[r];
+    // prefetch the next group and this group's residual; groups whose reads cannot leave
+    // [0, n_frames) (all but the edges of the stream) take the unguarded path
+    const int tn = tb + kMemR + HR;  // first frame of the next group's new inputs
     if (tb + kMemR < t1) {
+      if (tn + kMemR <= n_frames) {
+        const float* q = ps + (int64_t)tn * ldp;
 #pragma unroll
-      for (int r = 0; r < kMemR; ++r) nxt[r] = load(tb + kMemR + HR + r);
+        for (int r = 0; r < kMemR; ++r) nxt[r] = __ldg(q + (int64_t)r * ldp);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMemR; ++r) nxt[r] = load(tn + r);
+      }
     }
-    float rs[kMemR];
-    if (res) {
+    const bool full = tb + kMemR <= t1;
+    if (rs) {
+      const float* q = rs + (int64_t)tb * ldr;
+      if (full) {
 #pragma unroll
-      for (int r = 0; r < kMemR; ++r)
-        rs[r] = (tb + r < t1) ? __ldg(res + (s * (int64_t)n_frames + tb + r) * ldr + c) : 0.f;
+        for (int r = 0; r < kMemR; ++r) rv[r] = __ldg(q + (int64_t)r * ldr);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMemR; ++r) rv[r] = (tb + r < t1) ? __ldg(q + (int64_t)r * ldr) : 0.f;
+      }
     }
     float acc[kMemR];
 #pragma unroll
@@ -202,13 +218,14 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
     for (int k = 0; k < N2; ++k)
 #pragma unroll
       for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(cr[k], w[r + N1 + k], acc[r]);
+    float* o = os + (int64_t)tb * ldo;
+    if (full) {
 #pragma unroll
-    for (int r = 0; r < kMemR; ++r) {
-      if (tb + r < t1) {
-        float v = acc[r];
-        if (res) v += rs[r];
-        out[(s * (int64_t)n_frames + tb + r) * ldo + c] = v;
-      }
+      for (int r = 0; r < kMemR; ++r) o[(int64_t)r * ldo] = rs ? acc[r] + rv[r] : acc[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < kMemR; ++r)
+        if (tb + r < t1) o[(int64_t)r * ldo] = rs ? acc[r] + rv[r] : acc[r];
     }
 #pragma unroll
     for (int j = 0; j < HL + HR; ++j) w[j] = w[j + kMemR];
