@@ -50,6 +50,23 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic_bytes(kernel_substr):
+    """DRAM bytes per launch of the named kernel from the committed ncu capture (None when absent)."""
+    import re
+    p = os.path.join(ROOT, "profiles", "r01_top_kernels.txt")
+    if not os.path.exists(p):
+        return None
+    vals = []
+    for line in open(p):
+        if kernel_substr in line.split(";")[0]:
+            rd = re.search(r"dram__bytes_read\.sum=([0-9.]+) (\w+)", line)
+            wr = re.search(r"dram__bytes_write\.sum=([0-9.]+) (\w+)", line)
+            if rd and wr:
+                mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                vals.append(float(rd.group(1)) * mul[rd.group(2)] + float(wr.group(1)) * mul[wr.group(2)])
+    return sum(vals) / len(vals) if vals else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -60,45 +77,46 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, through NVML (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints, B200_PROFILING.md),
+    sampled every 5 ms so that even a 100 ms timed region gets a median."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self._stop_evt, self.max_mhz = index, [], threading.Event(), None
+        self.active = threading.Event()
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return
         while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+            if self.active.is_set():
+                try:
+                    self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                      int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                except Exception:
+                    pass
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            bits |= r[1]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, v in self.REASONS.items() if bits & v), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------- CPU legs
@@ -292,23 +310,26 @@ def run_vadx(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active.set()
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
         barrier()
+        sampler.active.clear()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
     W_ = max(3, args.warmup)
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # ---- device-resident, with live per-stage timers
@@ -369,6 +390,10 @@ def run_vadx(args):
                 "peak_source": pk["source"] + " STREAM-style copy (MEASURED_PEAKS.json hbm_gbs)",
                 "launches_timed": dom_calls, "avg_launch_ms": dom_ms / max(1, dom_calls),
                 "algorithmic_bytes_per_launch": per_launch_bytes}
+        roof["traffic"] = ncu_traffic_bytes({"linear": "linear_tc_kernel", "memory": "fsmn_memory_stream_kernel",
+                                             "stft": "stft_power_tc_kernel", "mel": "mel_log_kernel"}.get(dom, dom))
+        if roof["traffic"] is not None:
+            roof["traffic_source"] = "profiles/r01_top_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches at this bench size)"
         if dom in stage_flops:
             tf = stage_flops[dom] * args.steps / (dom_ms * 1e-3) / 1e12
             roof["tensor"] = {"achieved_tflops_fp32_equiv": tf, "mma_products_per_fp32_product": 3 if dom == "linear" else 4,

@@ -401,3 +401,135 @@ def silero_dense_layers(cfg: SileroConfig, w: dict):
         t_in, c_in = t_out, co
     assert t_in == 1
     return out
+
+
+# ----------------------------------------------------------------------------- DFSMN AEC-VAD (dual input)
+@dataclasses.dataclass(frozen=True)
+class DfsmnAecConfig:
+    """DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py: SDAEC AlphaPredictor + ICCRN echo estimator
+    (architecture vendored in the Export script, :65-284) followed by the modelscope
+    `speech_dfsmn_aec_psm_16k` mask-net (linear1 -> relu -> deepfsmn -> linear3, :350-353).  The
+    mask-net's sizes are not in the reference (modelscope is un-vendored): hidden 128, 9 UniDeepFsmn
+    layers (128 -> 256 -> 128, lorder 20) is a declared assumption."""
+    channels: int = 20
+    n_fft_b: int = 319
+    hop_b: int = 160
+    alpha_k: int = 10
+    n_fft_a: int = 1024
+    win_a: int = 640
+    hop_a: int = 320
+    n_mels: int = 80
+    pre_emphasis: float = 0.97
+    echo_factor: float = 1.15
+    log_floor: float = 1e-6
+    mask_hidden: int = 128
+    mask_layers: int = 9
+    mask_inner: int = 256
+    mask_lorder: int = 20
+    max_frames: int = 200
+
+    @property
+    def n_bins_b(self) -> int:
+        return self.n_fft_b // 2 + 1   # 160
+
+    @property
+    def ceps_bins(self) -> int:
+        return self.n_bins_b // 2 + 1  # 81
+
+
+def _lstm_spec(s, prefix, n_in, hidden, layers=1, bi=False):
+    for l in range(layers):
+        for suf in ([""] + (["_reverse"] if bi else [])):
+            i = n_in if l == 0 else hidden * (2 if bi else 1)
+            s[f"{prefix}.weight_ih_l{l}{suf}"] = (4 * hidden, i)
+            s[f"{prefix}.weight_hh_l{l}{suf}"] = (4 * hidden, hidden)
+            s[f"{prefix}.bias_ih_l{l}{suf}"] = (4 * hidden,)
+            s[f"{prefix}.bias_hh_l{l}{suf}"] = (4 * hidden,)
+
+
+def dfsmn_aec_spec(cfg: DfsmnAecConfig) -> "OrderedDict[str, tuple]":
+    """Learnable tensors: `iccrn.*` = NET.state_dict() parameter names (Export_DFSMN_VAD.py:170-249),
+    `alpha.*` = AlphaPredictor, `mask.*` = the mask-net shell, `shift` / `scale` = preprocessor.feature."""
+    c, F, cb = cfg.channels, cfg.n_bins_b, cfg.ceps_bins
+    s: OrderedDict[str, tuple] = OrderedDict()
+    _lstm_spec(s, "iccrn.in_ch_lstm.lstm2", 4, c, bi=True)
+    s["iccrn.in_ch_lstm.linear.weight"] = (c, 2 * c)
+    s["iccrn.in_ch_lstm.linear.bias"] = (c,)
+    s["iccrn.in_conv.weight"] = (c, 4 + c, 1, 1)
+    s["iccrn.in_conv.bias"] = (c,)
+
+    def cfb(name, cin):
+        p = f"iccrn.{name}."
+        for conv, shape in (("conv_gate", (c, cin, 1, 1)), ("conv_input", (c, cin, 1, 1)), ("conv", (c, c, 3, 1))):
+            s[p + conv + ".weight"] = shape
+            s[p + conv + ".bias"] = (c,)
+        _lstm_spec(s, p + "ceps_unit.ch_lstm_f.lstm2", 2 * c, c, bi=True)
+        s[p + "ceps_unit.ch_lstm_f.linear.weight"] = (2 * c, 2 * c)
+        s[p + "ceps_unit.ch_lstm_f.linear.bias"] = (2 * c,)
+        s[p + "ceps_unit.LN.w"] = (1, 2 * c, cb, 1)
+        s[p + "ceps_unit.LN.b"] = (1, 2 * c, cb, 1)
+        for ln, ch in (("LN0", cin), ("LN1", c), ("LN2", c)):
+            s[p + ln + ".w"] = (1, ch, F, 1)
+            s[p + ln + ".b"] = (1, ch, F, 1)
+
+    for i in range(1, 6):
+        cfb(f"cfb_e{i}", c)
+    s["iccrn.ln.w"] = (1, c, F, 1)
+    s["iccrn.ln.b"] = (1, c, F, 1)
+    _lstm_spec(s, "iccrn.ch_lstm.lstm2", c, 2 * c, layers=2)
+    s["iccrn.ch_lstm.linear.weight"] = (c, 2 * c)
+    s["iccrn.ch_lstm.linear.bias"] = (c,)
+    cfb("cfb_d5", c)
+    for i in (4, 3, 2, 1):
+        cfb(f"cfb_d{i}", 2 * c)
+    _lstm_spec(s, "iccrn.out_ch_lstm.lstm2", 2 * c, c)
+    s["iccrn.out_ch_lstm.linear.weight"] = (2 * c, c)
+    s["iccrn.out_ch_lstm.linear.bias"] = (2 * c,)
+    s["iccrn.out_conv.weight"] = (2, 3 * c, 1, 1)
+    s["iccrn.out_conv.bias"] = (2,)
+    s["alpha.linear1.weight"] = (1, 2)
+    s["alpha.linear1.bias"] = (1,)
+    s["alpha.linear2.weight"] = (1, cfg.alpha_k)
+    s["alpha.linear2.bias"] = (1,)
+    H = cfg.mask_hidden
+    s["mask.linear1.weight"] = (H, 3 * cfg.n_mels)
+    s["mask.linear1.bias"] = (H,)
+    for i in range(cfg.mask_layers):
+        s[f"mask.deepfsmn.{i}.linear.weight"] = (cfg.mask_inner, H)
+        s[f"mask.deepfsmn.{i}.linear.bias"] = (cfg.mask_inner,)
+        s[f"mask.deepfsmn.{i}.project.weight"] = (H, cfg.mask_inner)
+        s[f"mask.deepfsmn.{i}.conv1.weight"] = (H, 1, cfg.mask_lorder, 1)
+    s["mask.linear3.weight"] = (1, H)
+    s["mask.linear3.bias"] = (1,)
+    s["shift"] = (3 * cfg.n_mels,)
+    s["scale"] = (3 * cfg.n_mels,)
+    return s
+
+
+def dfsmn_aec_random_init(cfg: DfsmnAecConfig = DfsmnAecConfig(), seed: int = 0):
+    rs = np.random.RandomState(seed)
+    spec = dfsmn_aec_spec(cfg)
+    w: OrderedDict[str, np.ndarray] = OrderedDict()
+    last_fan = 1
+    for name, shape in spec.items():
+        if name in ("shift", "scale"):
+            continue
+        if name.endswith(".w"):                      # LayerNorm gain (reference init: ones)
+            w[name] = rs.uniform(0.8, 1.2, size=shape).astype(np.float32)
+        elif name.endswith(".b") and len(shape) == 4:  # LayerNorm bias (reference init: rand * 1e-4)
+            w[name] = (rs.uniform(0, 1, size=shape) * 1e-1).astype(np.float32)
+        elif "bias" in name:
+            w[name] = _uniform(rs, shape, 1.0 / np.sqrt(max(last_fan, 1)))
+        else:
+            last_fan = _fan_in(shape)
+            w[name] = _uniform(rs, shape, np.sqrt(3.0 / last_fan))
+    # log-mel of 1/32768-scaled audio sits around -20..-5; shift already includes + ln(32768^2) in the
+    # reference wrapper (Export_DFSMN_VAD.py:291), so `shift` here is the raw preprocessor value
+    w["shift"] = (-rs.uniform(2.0, 6.0, size=(3 * cfg.n_mels,))).astype(np.float32)
+    w["scale"] = rs.uniform(0.2, 0.4, size=(3 * cfg.n_mels,)).astype(np.float32)
+    w["alpha.linear1.weight"] = np.array([[0.6, 0.4]], np.float32)
+    w["alpha.linear1.bias"] = np.array([0.05], np.float32)
+    w["alpha.linear2.weight"] = (rs.uniform(0.02, 0.2, size=(1, cfg.alpha_k))).astype(np.float32)
+    w["alpha.linear2.bias"] = np.array([0.3], np.float32)
+    w["mask.linear3.weight"] = (w["mask.linear3.weight"] * 3.0).astype(np.float32)
+    return w
