@@ -426,8 +426,90 @@ def gen_silero():
     np.savez_compressed(os.path.join(GOLD, "silero.npz"), **out)
 
 
+# ------------------------------------------------------------------------------ DFSMN AEC-VAD
+def dfsmn_aec_reference(cfg, weights):
+    """The reference's own DFSMN_VAD wrapper around its own NET / AlphaPredictor / UniDeepFsmn modules."""
+    import importlib.util
+    import types
+    stft = RL.import_file("DFSMN/near_and_far_end_audio/STFT_Process.py", "STFT_Process")
+    pkg = types.ModuleType("dfsmn_ref_pkg")
+    pkg.__path__ = []
+    sys.modules["dfsmn_ref_pkg"] = pkg
+    lb = types.ModuleType("dfsmn_ref_pkg.layer_base")
+
+    class LayerBase(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+
+    lb.LayerBase = LayerBase
+    lb.to_kaldi_matrix = lb.expect_kaldi_matrix = lb.expect_token_number = lambda *a, **k: None
+    sys.modules["dfsmn_ref_pkg.layer_base"] = lb
+    spec = importlib.util.spec_from_file_location(
+        "dfsmn_ref_pkg.uni_deep_fsmn",
+        os.path.join(RL.REF_ROOT, "DFSMN/near_and_far_end_audio/modeling_modified/uni_deep_fsmn.py"))
+    udf = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = udf
+    spec.loader.exec_module(udf)
+    ns = RL.extract("DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py", {"STFT_Process": stft.STFT_Process})
+    tw = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    net = ns["NET"](max_frames=cfg.max_frames)
+    missing, unexpected = net.load_state_dict({k[6:]: v for k, v in tw.items() if k.startswith("iccrn.")}, strict=False)
+    assert not unexpected and all(("kernel" in m or "basis" in m or "window_sum" in m) for m in missing), (missing, unexpected)
+    net = net.float().eval()
+    ap = ns["AlphaPredictor"](cfg.alpha_k)
+    ap.load_state_dict({k[6:]: v for k, v in tw.items() if k.startswith("alpha.")}, strict=True)
+
+    class MaskNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear1 = torch.nn.Linear(3 * cfg.n_mels, cfg.mask_hidden)
+            self.relu = torch.nn.ReLU()
+            self.deepfsmn = torch.nn.Sequential(*[udf.UniDeepFsmn(cfg.mask_hidden, cfg.mask_hidden, cfg.mask_lorder,
+                                                                  cfg.mask_inner) for _ in range(cfg.mask_layers)])
+            self.linear3 = torch.nn.Linear(cfg.mask_hidden, 1)
+
+    mask = MaskNet()
+    mask.load_state_dict({k[5:]: v for k, v in tw.items() if k.startswith("mask.")}, strict=True)
+    feature = types.SimpleNamespace(shift=tw["shift"], scale=tw["scale"])
+    pipe = types.SimpleNamespace(model=mask.eval(), preprocessor=types.SimpleNamespace(feature=feature))
+    mk = lambda n, w_, h: stft.STFT_Process(model_type='stft_B', n_fft=n, hop_len=h, win_length=w_, max_frames=0,
+                                            window_type='hamming').eval()
+    wrap = ns["DFSMN_VAD"](pipe, net, ap.float().eval(), mk(cfg.n_fft_a, cfg.win_a, cfg.hop_a), mk(640, cfg.win_a, cfg.hop_a),
+                           mk(cfg.n_fft_b, cfg.n_fft_b, cfg.hop_b), cfg.n_fft_a, cfg.n_fft_b, cfg.alpha_k, cfg.max_frames,
+                           cfg.pre_emphasis, 16000, cfg.n_mels).eval()
+    return wrap, net
+
+
+def gen_dfsmn_aec():
+    import vadx  # noqa: F401
+    from vadx import synth, weights as W
+    cfg = W.DfsmnAecConfig()
+    w = W.dfsmn_aec_random_init(cfg, 0)
+    wrap, net = dfsmn_aec_reference(cfg, w)
+    L = 31841
+    rs = np.random.RandomState(5)
+    far = synth.synth_streams(2, L, seed=41)
+    near_clean = synth.synth_streams(2, L, seed=42)
+    # near = own speech bursts + a delayed, attenuated copy of the far end (echo)
+    near = np.clip(near_clean.astype(np.float32) + 0.5 * np.roll(far, 240, axis=1).astype(np.float32), -32768, 32767).astype(np.int16)
+    out = {"near": near, "far": far}
+    for s in range(2):
+        with torch.inference_mode():
+            p = wrap(torch.from_numpy(near[s]).view(1, 1, -1), torch.from_numpy(far[s]).view(1, 1, -1))
+        out[f"probs{s}"] = p.numpy()
+        print(f"stream {s}: probs", p.shape, float(p.min()), float(p.max()))
+    # ICCRN alone on a seeded input (stage-level pin)
+    torch.manual_seed(3)
+    x = torch.randn(1, 4, 160, 24) * 0.05
+    with torch.inference_mode():
+        y, n = net(x)
+    out["iccrn_in"] = x.numpy()
+    out["iccrn_out"] = y.numpy()[0, 0]
+    np.savez_compressed(os.path.join(GOLD, "dfsmn_aec.npz"), **out)
+
+
 GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
-              "marblenet": gen_marblenet, "silero": gen_silero}
+              "marblenet": gen_marblenet, "silero": gen_silero, "dfsmn_aec": gen_dfsmn_aec}
 
 
 def main(argv):

@@ -525,11 +525,14 @@ def dfsmn_aec_random_init(cfg: DfsmnAecConfig = DfsmnAecConfig(), seed: int = 0)
             w[name] = _uniform(rs, shape, np.sqrt(3.0 / last_fan))
     # log-mel of 1/32768-scaled audio sits around -20..-5; shift already includes + ln(32768^2) in the
     # reference wrapper (Export_DFSMN_VAD.py:291), so `shift` here is the raw preprocessor value
-    w["shift"] = (-rs.uniform(2.0, 6.0, size=(3 * cfg.n_mels,))).astype(np.float32)
+    w["shift"] = (-rs.uniform(19.0, 23.0, size=(3 * cfg.n_mels,))).astype(np.float32)
     w["scale"] = rs.uniform(0.2, 0.4, size=(3 * cfg.n_mels,)).astype(np.float32)
     w["alpha.linear1.weight"] = np.array([[0.6, 0.4]], np.float32)
     w["alpha.linear1.bias"] = np.array([0.05], np.float32)
     w["alpha.linear2.weight"] = (rs.uniform(0.02, 0.2, size=(1, cfg.alpha_k))).astype(np.float32)
     w["alpha.linear2.bias"] = np.array([0.3], np.float32)
-    w["mask.linear3.weight"] = (w["mask.linear3.weight"] * 3.0).astype(np.float32)
+    for i in range(cfg.mask_layers):      # keep the 9-deep residual stack from blowing up under random init
+        w[f"mask.deepfsmn.{i}.project.weight"] = (w[f"mask.deepfsmn.{i}.project.weight"] * 0.35).astype(np.float32)
+    w["mask.linear3.weight"] = (w["mask.linear3.weight"] * 2.0).astype(np.float32)
+    w["mask.linear3.bias"] = (w["mask.linear3.bias"] - 1.1).astype(np.float32)
     return w
