@@ -218,6 +218,40 @@ int vadx_silero_timestamps(const float* d_probs, int64_t ld, const int32_t* d_n_
                            double min_silence_samples_at_max_speech, int window, int use_max_poss_sil,
                            int32_t* d_seg_count, int64_t* d_segments, int max_segments, void* stream);
 
+/* a10 -- building blocks of the SDAEC / ICCRN echo estimator (DFSMN/near_and_far_end_audio/
+ * Export_DFSMN_VAD.py:65-354) on [stream][frame][bin][channel] fp32 activations.
+ *  vadx_stft_complex_f32: like vadx_stft_power_f32 but keeps (re, im) interleaved: out[(s*T+t)*ld_out + 2f / 2f+1].
+ *  vadx_permute4_f32: out dims = (n[p0], n[p1], n[p2], n[p3]); out[i0][i1][i2][i3] = in[j], j[p_k] = i_k.
+ *  vadx_layernorm_f32: per row of row_len contiguous values: (x - mean) / (std_unbiased + eps) * w[d] + b[d]
+ *      (LayerNorm over (C, F), :163-167).
+ *  vadx_lstm_seq_f32: n_seq independent LSTM sequences (PyTorch gate order, zero initial state); sequence
+ *      q = o*n_inner + i starts at d_x + o*x_outer + i*x_inner, steps are x_step floats apart (same for d_y,
+ *      which receives the hidden state of every step); reverse = 1 walks the sequence backwards.
+ *  vadx_ew2_f32: op 0 a+b, 1 a*b, 2 a - scalar*b, 3 copy a, 4 gate (out = a*b, out2 = b - a*b), row-strided.
+ *  vadx_ceps_cmul_f32: complex product of [rows][re(C) | im(C)] tensors (CepsUnit, :145-146).
+ *  vadx_im2col_f3_f32: out[(blk,f)][j*C + c] = x[(blk, f+j-1)][c] (zero padded) for the (3,1) frequency conv.
+ *  vadx_alpha_x4_f32: AlphaPredictor (:326-336) + assembly of the 4-channel ICCRN input.
+ *  vadx_istft_ola_f32: overlap-add + crop + window-sum normalisation of NET.istft (:226-230). */
+int vadx_stft_complex_f32(const float* d_sig, int64_t sig_stride, int64_t n_streams, int n_frames, int hop, int n_taps,
+                          const float* d_basis, int ld_basis, int n_bins, float* d_out, int64_t ld_out, void* stream);
+int vadx_permute4_f32(const float* d_in, float* d_out, int64_t n0, int64_t n1, int64_t n2, int64_t n3, int p0, int p1,
+                      int p2, int p3, void* stream);
+int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len, const float* d_w, const float* d_b, float eps,
+                       float* d_out, void* stream);
+int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y, int64_t y_outer,
+                      int64_t y_inner, int64_t y_step, const float* d_w_ih, const float* d_w_hh, const float* d_b_ih,
+                      const float* d_b_hh, int64_t n_seq, int n_inner, int seq_len, int n_in, int hidden, int reverse,
+                      void* stream);
+int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_out, int64_t ldo,
+                 float* d_out2, int64_t ldo2, int64_t n_rows, int n_cols, float scalar, void* stream);
+int vadx_ceps_cmul_f32(const float* d_q, const float* d_p, float* d_out, int64_t n_rows, int n_channels, void* stream);
+int vadx_im2col_f3_f32(const float* d_x, float* d_out, int64_t n_blocks, int n_bins, int n_channels, void* stream);
+int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, int64_t n_streams, int n_frames, int n_bins, int k,
+                      float w1_far, float w1_mix, float b1, const float* d_w2, float b2, float* d_x4, float* d_alpha,
+                      void* stream);
+int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,
+                       const float* d_wsum_inv, int n_out, float* d_y, int64_t ldy, void* stream);
+
 /* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
  * that the float32 running sum rounds exactly like np.cumsum
  * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid

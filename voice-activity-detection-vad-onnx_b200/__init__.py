@@ -10,3 +10,4 @@ __version__ = "0.1.0"
 from . import constants, lib, tables, weights, synth  # noqa: F401
 from .session import InferenceSession, FireRedSession, FsmnSession, MarbleNetSession, SileroSession  # noqa: F401
 from .postprocess import FramePostConfig, postprocess_frames  # noqa: F401
+from .dfsmn_aec import DfsmnAecSession  # noqa: F401,E402

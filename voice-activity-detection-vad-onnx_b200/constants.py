@@ -155,3 +155,35 @@ def torchaudio_mel_bank(n_freqs: int, f_min: float, f_max: float, n_mels: int,
         enorm = 2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])
         fb = fb * enorm.unsqueeze(0)
     return fb.transpose(0, 1).contiguous()
+
+
+def ceps_bases(n_fft: int):
+    """CepsUnit tables (DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py:104-131): rectangular-window DFT
+    kernels [n_fft//2+1, n_fft] (cos, -sin) and the pinv inverse basis [2*(n_fft//2+1), n_fft]."""
+    half = n_fft // 2
+    t = torch.arange(n_fft, dtype=_F32).unsqueeze(0)
+    f = torch.arange(half + 1, dtype=_F32).unsqueeze(1)
+    omega = 2 * torch.pi * f * t / n_fft
+    fb = torch.fft.fft(torch.eye(n_fft, dtype=_F32))
+    fb_ri = torch.vstack([torch.real(fb[:half + 1]), torch.imag(fb[:half + 1])]).float()
+    return torch.cos(omega), -torch.sin(omega), torch.linalg.pinv(fb_ri).T.contiguous()
+
+
+def istft_tables(n_fft: int, hop: int, max_frames: int):
+    """NET tables (:186-209): windowed pinv synthesis basis [2*(n_fft//2+1), n_fft] and the inverse
+    overlap-add window sum."""
+    half = n_fft // 2
+    window = torch.hamming_window(n_fft)
+    fb = torch.fft.fft(torch.eye(n_fft, dtype=_F32))
+    fb_ri = torch.vstack([torch.real(fb[:half + 1]), torch.imag(fb[:half + 1])]).float()
+    inv = (torch.linalg.pinv((fb_ri * n_fft) / hop).T * window.view(1, -1)).contiguous()
+    out_len = (max_frames - 1) * hop + n_fft
+    wsum = torch.zeros(out_len, dtype=_F32)
+    wsq = window ** 2
+    for i in range(max_frames):
+        s = i * hop
+        n = min(n_fft, out_len - s)
+        if n <= 0:
+            break
+        wsum[s:s + n] += wsq[:n]
+    return inv, n_fft / (wsum * hop + 1e-6)

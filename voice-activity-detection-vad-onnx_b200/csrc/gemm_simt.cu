@@ -347,3 +347,20 @@ extern "C" int vadx_stft_power_f32(const float* d_sig, int64_t sig_stride, int64
   g.vec_store = ((ld_power & 1) == 0) && ((reinterpret_cast<uintptr_t>(d_power) & 7u) == 0);
   return launch_gemm<1, 1>(g, 2 * n_bins, (cudaStream_t)stream, "vadx_stft_power_f32");
 }
+
+extern "C" int vadx_stft_complex_f32(const float* d_sig, int64_t sig_stride, int64_t n_streams, int n_frames, int hop,
+                                     int n_taps, const float* d_basis, int ld_basis, int n_bins, float* d_out,
+                                     int64_t ld_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
+  VADX_REQUIRE(d_sig && d_basis && d_out, "vadx_stft_complex_f32: null pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0, "vadx_stft_complex_f32: bad shape");
+  VADX_REQUIRE(ld_basis >= 2 * n_bins && (ld_basis & 3) == 0 && aligned16(d_basis) && ld_out >= 2 * n_bins,
+               "vadx_stft_complex_f32: ld_basis must be >= 2*n_bins and a multiple of 4, ld_out >= 2*n_bins");
+  VADX_REQUIRE(sig_stride >= (int64_t)(n_frames - 1) * hop + n_taps, "vadx_stft_complex_f32: signal stride too short");
+  GemmArgs g{};
+  g.A = d_sig; g.lda = sig_stride; g.n_frames = n_frames; g.hop = hop;
+  g.B = d_basis; g.ldb = ld_basis; g.M = n_streams * n_frames; g.N = 2 * n_bins; g.K = n_taps;
+  g.C = d_out; g.ldc = ld_out; g.act = 0;
+  g.vec_store = ((ld_out & 3) == 0) && aligned16(d_out);
+  return launch_gemm<1, 0>(g, 2 * n_bins, (cudaStream_t)stream, "vadx_stft_complex_f32");
+}

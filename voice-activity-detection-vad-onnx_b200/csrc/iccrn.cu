@@ -1,0 +1,367 @@
+// iccrn.cu -- building blocks of the SDAEC / ICCRN echo estimator (a10) on [stream][frame][bin][channel]
+// activations: 4-D permute, (C,F)-LayerNorm with unbiased std, batched LSTM sequences, gated
+// element-wise ops, 3-tap frequency im2col, the AlphaPredictor scaling and the ISTFT overlap-add.
+// Reference: DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py:65-354.
+#include "common.cuh"
+
+namespace vadx {
+
+// ---------------------------------------------------------------------------------- permute
+// out dims = (n[p0], n[p1], n[p2], n[p3]); out[i0][i1][i2][i3] = in[j0][j1][j2][j3] with j[p_k] = i_k
+__global__ void __launch_bounds__(256) permute4_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                       int64_t n0, int64_t n1, int64_t n2, int64_t n3, int p0, int p1,
+                                                       int p2, int p3) {
+  const int64_t n[4] = {n0, n1, n2, n3};
+  const int64_t st[4] = {n1 * n2 * n3, n2 * n3, n3, 1};
+  const int p[4] = {p0, p1, p2, p3};
+  const int64_t o1 = n[p[1]], o2 = n[p[2]], o3 = n[p[3]];
+  const int64_t total = n0 * n1 * n2 * n3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int64_t i3 = r % o3; r /= o3;
+    const int64_t i2 = r % o2; r /= o2;
+    const int64_t i1 = r % o1; r /= o1;
+    const int64_t i0 = r;
+    out[i] = in[i0 * st[p[0]] + i1 * st[p[1]] + i2 * st[p[2]] + i3 * st[p[3]]];
+  }
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm (unbiased std)
+// one CTA per row of D contiguous elements: (x - mean) / (std + eps) * w[d] + b[d]
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t n_rows, int D,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float eps, float* __restrict__ out) {
+  __shared__ float red[256];
+  __shared__ float s_mean, s_inv;
+  const int64_t row = blockIdx.x;
+  const float* xr = x + row * D;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) acc += xr[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_mean = red[0] / (float)D;
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float d = xr[i] - mean;
+    acc = fmaf(d, d, acc);
+  }
+  __syncthreads();
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_inv = 1.0f / (sqrtf(red[0] / (float)(D - 1)) + eps);
+  __syncthreads();
+  const float inv = s_inv;
+  float* o = out + row * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) o[i] = (xr[i] - mean) * inv * w[i] + b[i];
+}
+
+// ---------------------------------------------------------------------------------- LSTM sequences
+// Thread = one sequence; weights, the thread's x / h / c / gate columns live in shared memory
+// ([k][thread]: conflict-free), gate order i,f,g,o (PyTorch).  Sequence q = o*n_inner + i starts at
+// x + o*x_outer + i*x_inner, steps are x_step apart (same decomposition for the output).
+struct LstmArgs {
+  const float* x;
+  int64_t x_outer, x_inner, x_step;
+  float* y;
+  int64_t y_outer, y_inner, y_step;
+  const float* w_ih;
+  const float* w_hh;
+  const float* b_ih;
+  const float* b_hh;
+  int64_t n_seq;
+  int n_inner, L, n_in, H, reverse;
+};
+constexpr int kLstmThreads = 64;
+__global__ void __launch_bounds__(kLstmThreads) lstm_seq_kernel(const LstmArgs a) {
+  extern __shared__ float sm[];
+  const int IN = a.n_in, H = a.H, G = 4 * a.H;
+  float* wih = sm;                       // [G][IN]
+  float* whh = wih + G * IN;             // [G][H]
+  float* bias = whh + G * H;             // [G]
+  float* xs = bias + G;                  // [IN][T]
+  float* hs = xs + IN * kLstmThreads;    // [H][T]
+  float* cs = hs + H * kLstmThreads;     // [H][T]
+  float* gs = cs + H * kLstmThreads;     // [G][T]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < G * IN; i += kLstmThreads) wih[i] = a.w_ih[i];
+  for (int i = tid; i < G * H; i += kLstmThreads) whh[i] = a.w_hh[i];
+  for (int i = tid; i < G; i += kLstmThreads) bias[i] = a.b_ih[i] + a.b_hh[i];
+  for (int k = 0; k < H; ++k) {
+    hs[k * kLstmThreads + tid] = 0.f;
+    cs[k * kLstmThreads + tid] = 0.f;
+  }
+  __syncthreads();
+  const int64_t q = (int64_t)blockIdx.x * kLstmThreads + tid;
+  if (q >= a.n_seq) return;
+  const int64_t qo = q / a.n_inner, qi = q - qo * a.n_inner;
+  const float* xq = a.x + qo * a.x_outer + qi * a.x_inner;
+  float* yq = a.y + qo * a.y_outer + qi * a.y_inner;
+  for (int step = 0; step < a.L; ++step) {
+    const int t = a.reverse ? a.L - 1 - step : step;
+    const float* xt = xq + (int64_t)t * a.x_step;
+    for (int k = 0; k < IN; ++k) xs[k * kLstmThreads + tid] = xt[k];
+    for (int j = 0; j < H; ++j) {
+      float gi = bias[j], gf = bias[H + j], gg = bias[2 * H + j], go = bias[3 * H + j];
+      const float* wi0 = wih + j * IN;
+      const float* wi1 = wih + (H + j) * IN;
+      const float* wi2 = wih + (2 * H + j) * IN;
+      const float* wi3 = wih + (3 * H + j) * IN;
+      for (int k = 0; k < IN; ++k) {
+        const float v = xs[k * kLstmThreads + tid];
+        gi = fmaf(wi0[k], v, gi); gf = fmaf(wi1[k], v, gf); gg = fmaf(wi2[k], v, gg); go = fmaf(wi3[k], v, go);
+      }
+      const float* wh0 = whh + j * H;
+      const float* wh1 = whh + (H + j) * H;
+      const float* wh2 = whh + (2 * H + j) * H;
+      const float* wh3 = whh + (3 * H + j) * H;
+      for (int k = 0; k < H; ++k) {
+        const float v = hs[k * kLstmThreads + tid];
+        gi = fmaf(wh0[k], v, gi); gf = fmaf(wh1[k], v, gf); gg = fmaf(wh2[k], v, gg); go = fmaf(wh3[k], v, go);
+      }
+      gs[j * kLstmThreads + tid] = gi;
+      gs[(H + j) * kLstmThreads + tid] = gf;
+      gs[(2 * H + j) * kLstmThreads + tid] = gg;
+      gs[(3 * H + j) * kLstmThreads + tid] = go;
+    }
+    float* yt = yq + (int64_t)t * a.y_step;
+    for (int j = 0; j < H; ++j) {
+      const float ig = 1.0f / (1.0f + expf(-gs[j * kLstmThreads + tid]));
+      const float fg = 1.0f / (1.0f + expf(-gs[(H + j) * kLstmThreads + tid]));
+      const float gg = tanhf(gs[(2 * H + j) * kLstmThreads + tid]);
+      const float og = 1.0f / (1.0f + expf(-gs[(3 * H + j) * kLstmThreads + tid]));
+      const float c = fg * cs[j * kLstmThreads + tid] + ig * gg;
+      const float h = og * tanhf(c);
+      cs[j * kLstmThreads + tid] = c;
+      hs[j * kLstmThreads + tid] = h;
+      yt[j] = h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- element-wise
+// op 0: out = a + b; 1: out = a * b; 2: out = a - s*b; 3: out = a (copy); 4: gate: out = a*b, out2 = b - a*b
+__global__ void __launch_bounds__(256) ew2_kernel(int op, const float* __restrict__ a, int64_t lda,
+                                                  const float* __restrict__ b, int64_t ldb, float* __restrict__ out,
+                                                  int64_t ldo, float* __restrict__ out2, int64_t ldo2, int64_t rows,
+                                                  int cols, float s) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float av = a[r * lda + c];
+    const float bv = b ? b[r * ldb + c] : 0.f;
+    float v;
+    if (op == 0) v = av + bv;
+    else if (op == 1) v = av * bv;
+    else if (op == 2) v = av - s * bv;
+    else if (op == 3) v = av;
+    else {
+      v = av * bv;
+      out2[r * ldo2 + c] = bv - v;
+    }
+    out[r * ldo + c] = v;
+  }
+}
+
+// CepsUnit complex product on [rows = (blk, bin)][2C]: q = LSTM output (re | im), p = spectrum (re | im)
+__global__ void __launch_bounds__(256) cmul_kernel(const float* __restrict__ q, const float* __restrict__ p,
+                                                   float* __restrict__ out, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float qr = q[r * 2 * C + c], qi = q[r * 2 * C + C + c];
+    const float pr = p[r * 2 * C + c], pi = p[r * 2 * C + C + c];
+    out[r * 2 * C + c] = qr * pr - qi * pi;
+    out[r * 2 * C + C + c] = qr * pi + qi * pr;
+  }
+}
+
+// 3-tap frequency im2col: out[(blk, f)][j*C + c] = x[(blk, f + j - 1)][c], zero outside [0, F)
+__global__ void __launch_bounds__(256) im2col_f3_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                        int64_t n_blk, int F, int C) {
+  const int64_t total = n_blk * F * 3 * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int j = (int)(r % 3);
+    r /= 3;
+    const int f = (int)(r % F);
+    const int64_t blk = r / F;
+    const int fs = f + j - 1;
+    out[i] = (fs >= 0 && fs < F) ? x[(blk * F + fs) * C + c] : 0.f;
+  }
+}
+
+// AlphaPredictor + input assembly: near/far complex spectra [S*T][2F] (re, im interleaved) ->
+// x4 [S*T*F][4] = (near_re, near_im, far_re*|alpha|, far_im*|alpha|), alpha per (t, f) from the
+// last k frames' powers (zero history): Export_DFSMN_VAD.py:326-336.
+__global__ void __launch_bounds__(256) alpha_x4_kernel(const float* __restrict__ near_ri, const float* __restrict__ far_ri,
+                                                       int64_t n_streams, int T, int F, int k, float w1_far, float w1_mix,
+                                                       float b1, const float* __restrict__ w2, float b2,
+                                                       float* __restrict__ x4, float* __restrict__ alpha_out) {
+  const int64_t total = n_streams * T * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const int64_t st = i / F;
+    const int t = (int)(st % T);
+    float acc = b2;
+    for (int j = 0; j < k; ++j) {
+      const int tt = t - (k - 1) + j;
+      float pm = 0.f, pf = 0.f;
+      if (tt >= 0) {
+        const int64_t row = st - t + tt;
+        const float nr = near_ri[row * 2 * F + 2 * f], ni = near_ri[row * 2 * F + 2 * f + 1];
+        const float fr = far_ri[row * 2 * F + 2 * f], fi = far_ri[row * 2 * F + 2 * f + 1];
+        pm = nr * nr + ni * ni;
+        pf = fr * fr + fi * fi;
+      }
+      acc = fmaf(w2[j], fmaf(w1_far, pf, fmaf(w1_mix, pm, b1)), acc);
+    }
+    const float aa = fabsf(acc);
+    x4[i * 4 + 0] = near_ri[st * 2 * F + 2 * f];
+    x4[i * 4 + 1] = near_ri[st * 2 * F + 2 * f + 1];
+    x4[i * 4 + 2] = far_ri[st * 2 * F + 2 * f] * aa;
+    x4[i * 4 + 3] = far_ri[st * 2 * F + 2 * f + 1] * aa;
+    if (alpha_out) alpha_out[i] = acc;
+  }
+}
+
+// ISTFT overlap-add (NET.istft :226-230): frames [S*T][ld] (n_fft valid) -> y[s][i] = window_sum_inv[i + half] *
+// sum_t frames[t][i + half - t*hop]
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, int64_t ld, int64_t n_streams,
+                                                        int T, int n_fft, int hop, const float* __restrict__ wsum_inv,
+                                                        int n_out, float* __restrict__ y, int64_t ldy) {
+  const int half = n_fft / 2;
+  const int64_t total = n_streams * n_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / n_out;
+    const int n = (int)(i - s * n_out) + half;
+    float acc = 0.f;
+    int t_hi = n / hop;
+    if (t_hi > T - 1) t_hi = T - 1;
+    for (int t = t_hi; t >= 0 && n - t * hop < n_fft; --t) acc += frames[(s * T + t) * ld + (n - t * hop)];
+    y[s * ldy + (n - half)] = acc * wsum_inv[n];
+  }
+}
+
+}  // namespace vadx
+
+using namespace vadx;
+
+static inline unsigned g1(int64_t items) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 256), 148 * 32));
+}
+
+extern "C" int vadx_permute4_f32(const float* d_in, float* d_out, int64_t n0, int64_t n1, int64_t n2, int64_t n3, int p0,
+                                 int p1, int p2, int p3, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_in && d_out && d_in != d_out && n0 >= 0 && n1 >= 1 && n2 >= 1 && n3 >= 1, "vadx_permute4_f32: bad argument");
+  int seen = 0;
+  for (int p : {p0, p1, p2, p3}) {
+    VADX_REQUIRE(p >= 0 && p < 4, "vadx_permute4_f32: bad permutation");
+    seen |= 1 << p;
+  }
+  VADX_REQUIRE(seen == 15, "vadx_permute4_f32: not a permutation");
+  if (n0 == 0) return VADX_OK;
+  permute4_kernel<<<g1(n0 * n1 * n2 * n3), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n0, n1, n2, n3, p0, p1, p2, p3);
+  return after_launch("vadx_permute4_f32");
+}
+
+extern "C" int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len, const float* d_w, const float* d_b,
+                                  float eps, float* d_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  VADX_REQUIRE(d_x && d_w && d_b && d_out && n_rows >= 0 && row_len >= 2, "vadx_layernorm_f32: bad argument");
+  VADX_REQUIRE(n_rows <= 0x7fffffffLL, "vadx_layernorm_f32: too many rows");
+  if (n_rows == 0) return VADX_OK;
+  layernorm_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(d_x, n_rows, row_len, d_w, d_b, eps, d_out);
+  return after_launch("vadx_layernorm_f32");
+}
+
+extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y,
+                                 int64_t y_outer, int64_t y_inner, int64_t y_step, const float* d_w_ih,
+                                 const float* d_w_hh, const float* d_b_ih, const float* d_b_hh, int64_t n_seq,
+                                 int n_inner, int seq_len, int n_in, int hidden, int reverse, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  VADX_REQUIRE(d_x && d_y && d_w_ih && d_w_hh && d_b_ih && d_b_hh, "vadx_lstm_seq_f32: null pointer");
+  VADX_REQUIRE(n_seq >= 0 && n_inner >= 1 && seq_len >= 1 && n_in >= 1 && hidden >= 1, "vadx_lstm_seq_f32: bad shape");
+  if (n_seq == 0) return VADX_OK;
+  const size_t G = 4 * (size_t)hidden;
+  const size_t smem = (G * n_in + G * hidden + G + (size_t)kLstmThreads * (n_in + 2 * hidden + G)) * sizeof(float);
+  VADX_REQUIRE(smem <= 200 * 1024, "vadx_lstm_seq_f32: in=%d hidden=%d needs %zu bytes of shared memory", n_in, hidden, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && configured == 0) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lstm_seq_kernel)");
+    configured = 1;
+  }
+  LstmArgs a{d_x, x_outer, x_inner, x_step, d_y, y_outer, y_inner, y_step, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
+             n_seq, n_inner, seq_len, n_in, hidden, reverse};
+  lstm_seq_kernel<<<(unsigned)ceil_div(n_seq, kLstmThreads), kLstmThreads, smem, (cudaStream_t)stream>>>(a);
+  return after_launch("vadx_lstm_seq_f32");
+}
+
+extern "C" int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_out,
+                            int64_t ldo, float* d_out2, int64_t ldo2, int64_t n_rows, int n_cols, float scalar,
+                            void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  VADX_REQUIRE(d_a && d_out && op >= 0 && op <= 4 && (op == 3 || d_b) && (op != 4 || d_out2) && n_rows >= 0 && n_cols >= 1,
+               "vadx_ew2_f32: bad argument");
+  if (n_rows == 0) return VADX_OK;
+  ew2_kernel<<<g1(n_rows * n_cols), 256, 0, (cudaStream_t)stream>>>(op, d_a, lda, d_b, ldb, d_out, ldo, d_out2, ldo2,
+                                                                    n_rows, n_cols, scalar);
+  return after_launch("vadx_ew2_f32");
+}
+
+extern "C" int vadx_ceps_cmul_f32(const float* d_q, const float* d_p, float* d_out, int64_t n_rows, int n_channels,
+                                  void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  VADX_REQUIRE(d_q && d_p && d_out && n_rows >= 0 && n_channels >= 1, "vadx_ceps_cmul_f32: bad argument");
+  if (n_rows == 0) return VADX_OK;
+  cmul_kernel<<<g1(n_rows * n_channels), 256, 0, (cudaStream_t)stream>>>(d_q, d_p, d_out, n_rows, n_channels);
+  return after_launch("vadx_ceps_cmul_f32");
+}
+
+extern "C" int vadx_im2col_f3_f32(const float* d_x, float* d_out, int64_t n_blocks, int n_bins, int n_channels,
+                                  void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_x && d_out && n_blocks >= 0 && n_bins >= 1 && n_channels >= 1, "vadx_im2col_f3_f32: bad argument");
+  if (n_blocks == 0) return VADX_OK;
+  im2col_f3_kernel<<<g1(n_blocks * n_bins * 3 * n_channels), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n_blocks, n_bins,
+                                                                                         n_channels);
+  return after_launch("vadx_im2col_f3_f32");
+}
+
+extern "C" int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, int64_t n_streams, int n_frames,
+                                 int n_bins, int k, float w1_far, float w1_mix, float b1, const float* d_w2, float b2,
+                                 float* d_x4, float* d_alpha, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_near_ri && d_far_ri && d_w2 && d_x4 && n_streams >= 0 && n_frames >= 1 && n_bins >= 1 && k >= 1,
+               "vadx_alpha_x4_f32: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  alpha_x4_kernel<<<g1(n_streams * n_frames * n_bins), 256, 0, (cudaStream_t)stream>>>(
+      d_near_ri, d_far_ri, n_streams, n_frames, n_bins, k, w1_far, w1_mix, b1, d_w2, b2, d_x4, d_alpha);
+  return after_launch("vadx_alpha_x4_f32");
+}
+
+extern "C" int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,
+                                  const float* d_wsum_inv, int n_out, float* d_y, int64_t ldy, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_frames && d_wsum_inv && d_y && n_streams >= 0 && n_frames >= 1 && n_fft >= 2 && hop >= 1 && ld >= n_fft &&
+                   n_out >= 1 && n_out <= (n_frames - 1) * hop + n_fft - 2 * (n_fft / 2) && ldy >= n_out,
+               "vadx_istft_ola_f32: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  istft_ola_kernel<<<g1(n_streams * n_out), 256, 0, (cudaStream_t)stream>>>(d_frames, ld, n_streams, n_frames, n_fft, hop,
+                                                                            d_wsum_inv, n_out, d_y, ldy);
+  return after_launch("vadx_istft_ola_f32");
+}

@@ -61,6 +61,16 @@ SIGNATURES = {
     "vadx_lstm_cell_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "vadx_silero_timestamps": (C.c_int, [_vp, _i64, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_double, C.c_double, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "vadx_stft_complex_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "vadx_permute4_f32": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "vadx_layernorm_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "vadx_lstm_seq_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                    _i32, _i32, _i32, _vp]),
+    "vadx_ew2_f32": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp]),
+    "vadx_ceps_cmul_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "vadx_im2col_f3_f32": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "vadx_alpha_x4_f32": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _f32, _vp, _vp, _vp]),
+    "vadx_istft_ola_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
     "vadx_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
     "vadx_destroy": (None, [_vp]),
