@@ -202,7 +202,7 @@ def family_rtfx(dev, world, dist):
     import numpy as np
     import torch
     import vadx
-    from vadx import fsmn_vad, marblenet_vad, silero_vad, synth, weights as W
+    from vadx import fsmn_vad, marblenet_vad, postprocess as PP, silero_vad, synth, weights as W
 
     def timed(fn, steps=3, warm=3):
         for _ in range(warm):
@@ -253,6 +253,25 @@ def family_rtfx(dev, world, dist):
     ms = timed(silero_step)
     out["silero"] = {"audio_hours_per_sec": world * S * n_win * 0.032 / (ms / 1e3) / 3600, "ms_per_step": ms,
                      "config": f"{S} streams/GPU x {n_win} windows of 512 samples, LSTM state + trigger machine on device"}
+    del sess, audio
+    # DFSMN AEC-VAD (config 4): near + far end, 31841-sample chunks
+    from vadx import dfsmn_aec
+    cfg = W.DfsmnAecConfig()
+    sess = vadx.DfsmnAecSession(W.dfsmn_aec_random_init(cfg, 0), cfg, chunk_len=31841)
+    S = 32
+    far = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=14)).to(dev)
+    near = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=15)).to(dev)
+    state = PP.HysteresisState(S, 100, dev)
+
+    def aec_step():
+        probs = sess.run_batch(near, far)
+        state.n_saved.zero_()
+        PP.lookahead_hysteresis(probs, state, 15, 0.5, 0.5, is_final=True)
+
+    ms = timed(aec_step, steps=2, warm=2)
+    out["dfsmn_aec"] = {"audio_hours_per_sec": world * S * 31841 / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
+                        "config": f"{S} near+far stream pairs/GPU x one 31841-sample chunk, echo estimator on fp32 FFMA "
+                                  "kernels, mask-net on tcgen05, hysteresis on device"}
     for v in out.values():
         v["rtfx"] = v["audio_hours_per_sec"] * 3600
     return out

@@ -148,6 +148,71 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_seq_kernel(const LstmArgs a
   }
 }
 
+// Gate-parallel variant: one thread per (sequence, gate row).  The thread keeps its row of
+// [W_ih | W_hh] in registers for the whole sequence (compile-time IN, H), x_t and h_{t-1} of the
+// sequence sit in shared memory (broadcast reads), the cell state lives in a register of the
+// thread that owns hidden unit j.  Two barriers per time step.
+template <int IN, int H, int NSEQ>
+__global__ void __launch_bounds__(4 * H * NSEQ) lstm_seq_gates_kernel(const LstmArgs a) {
+  constexpr int G = 4 * H;
+  __shared__ float xs[NSEQ][IN];
+  __shared__ float hs[NSEQ][H];
+  __shared__ float gs[NSEQ][G];
+  const int g = threadIdx.x % G;       // gate row (i: 0..H-1, f: H.., g: 2H.., o: 3H..)
+  const int ql = threadIdx.x / G;      // local sequence
+  const int64_t q = (int64_t)blockIdx.x * NSEQ + ql;
+  const bool live = q < a.n_seq;
+  const int64_t qc = live ? q : 0;
+  const int64_t qo = qc / a.n_inner, qi = qc - qo * a.n_inner;
+  const float* xq = a.x + qo * a.x_outer + qi * a.x_inner;
+  float* yq = a.y + qo * a.y_outer + qi * a.y_inner;
+  float wi[IN], wh[H];
+#pragma unroll
+  for (int k = 0; k < IN; ++k) wi[k] = a.w_ih[g * IN + k];
+#pragma unroll
+  for (int k = 0; k < H; ++k) wh[k] = a.w_hh[g * H + k];
+  const float bias = a.b_ih[g] + a.b_hh[g];
+  float c = 0.f;
+  if (g < H) hs[ql][g] = 0.f;
+  {
+    const int t0 = a.reverse ? a.L - 1 : 0;
+    if (g < IN) xs[ql][g] = live ? xq[(int64_t)t0 * a.x_step + g] : 0.f;
+  }
+  __syncthreads();
+  for (int step = 0; step < a.L; ++step) {
+    const int t = a.reverse ? a.L - 1 - step : step;
+    float acc = bias;
+#pragma unroll
+    for (int k = 0; k < IN; ++k) acc = fmaf(wi[k], xs[ql][k], acc);
+#pragma unroll
+    for (int k = 0; k < H; ++k) acc = fmaf(wh[k], hs[ql][k], acc);
+    gs[ql][g] = acc;
+    __syncthreads();
+    if (g < H) {
+      const float ig = 1.0f / (1.0f + expf(-gs[ql][g]));
+      const float fg = 1.0f / (1.0f + expf(-gs[ql][H + g]));
+      const float gg = tanhf(gs[ql][2 * H + g]);
+      const float og = 1.0f / (1.0f + expf(-gs[ql][3 * H + g]));
+      c = fg * c + ig * gg;
+      const float h = og * tanhf(c);
+      hs[ql][g] = h;
+      if (live) yq[(int64_t)t * a.y_step + g] = h;
+    } else if (g - H < IN && step + 1 < a.L) {
+      // the other threads fetch the next step's input meanwhile
+      const int tn = a.reverse ? a.L - 2 - step : step + 1;
+      xs[ql][g - H] = live ? xq[(int64_t)tn * a.x_step + (g - H)] : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+template <int IN, int H, int NSEQ>
+static int launch_lstm_gates(const LstmArgs& a, cudaStream_t st) {
+  static_assert(IN <= 3 * H, "the threads of gate rows H..4H-1 prefetch x: need IN <= 3H");
+  lstm_seq_gates_kernel<IN, H, NSEQ><<<(unsigned)ceil_div(a.n_seq, NSEQ), 4 * H * NSEQ, 0, st>>>(a);
+  return after_launch("vadx_lstm_seq_f32");
+}
+
 // ---------------------------------------------------------------------------------- element-wise
 // op 0: out = a + b; 1: out = a * b; 2: out = a - s*b; 3: out = a (copy); 4: gate: out = a*b, out2 = b - a*b
 __global__ void __launch_bounds__(256) ew2_kernel(int op, const float* __restrict__ a, int64_t lda,
@@ -296,6 +361,15 @@ extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_in
   VADX_REQUIRE(d_x && d_y && d_w_ih && d_w_hh && d_b_ih && d_b_hh, "vadx_lstm_seq_f32: null pointer");
   VADX_REQUIRE(n_seq >= 0 && n_inner >= 1 && seq_len >= 1 && n_in >= 1 && hidden >= 1, "vadx_lstm_seq_f32: bad shape");
   if (n_seq == 0) return VADX_OK;
+  {
+    LstmArgs a{d_x, x_outer, x_inner, x_step, d_y, y_outer, y_inner, y_step, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
+               n_seq, n_inner, seq_len, n_in, hidden, reverse};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_in == 4 && hidden == 20) return launch_lstm_gates<4, 20, 4>(a, st);
+    if (n_in == 40 && hidden == 20) return launch_lstm_gates<40, 20, 4>(a, st);
+    if (n_in == 20 && hidden == 40) return launch_lstm_gates<20, 40, 2>(a, st);
+    if (n_in == 40 && hidden == 40) return launch_lstm_gates<40, 40, 2>(a, st);
+  }
   const size_t G = 4 * (size_t)hidden;
   const size_t smem = (G * n_in + G * hidden + G + (size_t)kLstmThreads * (n_in + 2 * hidden + G)) * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_lstm_seq_f32: in=%d hidden=%d needs %zu bytes of shared memory", n_in, hidden, smem);
