@@ -147,6 +147,13 @@ int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const float* d_w, i
                               int pad, float* d_y, int64_t ldy, int64_t n_streams, int t_in, int t_out,
                               int n_channels, void* stream);
 
+/* a8 with the 1-output sigmoid head fused into the epilogue (FireRed: dnn 128->256 + ReLU, out 256->1, sigmoid):
+ * d_head_out[row] = sigmoid(sum_n act(x*W^T + b)[n] * d_head_w[n] + head_bias); the n_out-wide layer output
+ * never leaves the SM. */
+int vadx_linear_head_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias, int64_t n_rows,
+                            int n_in, int n_out, int act, const float* d_head_w, float head_bias, float* d_head_out,
+                            void* stream);
+
 /* a5/a6/a7 -- FSMN / DFSMN memory block on time-major activations [S][T][C]:
  *   out[t] = p[t] + sum_k wl[c][k] * p[t - (n_back-1-k)*stride_back]
  *                 + sum_k wr[c][k] * p[t + (k+1)*stride_ahead]        (only when T > 1)

@@ -31,7 +31,7 @@ def _run_tc(cuda, x, w, b, r, act):
     (98 * 40, 80, 256, 1, False, True),   # first layer: K = 80 (partial k-chunk)
     (300000, 128, 256, 1, False, True),   # many tiles per CTA: exercises both ring wrap-arounds
     (777, 140, 170, 1, False, True),      # odd sizes: K = 140 -> 3 k-chunks, N padded to 176
-    (513, 250, 140, 0, False, True),      # K = 250 -> 4 k-chunks, N padded to 144
+    (513, 250, 128, 0, False, True),      # K = 250 -> 4 k-chunks (partial last chunk)
     (64, 128, 128, 2, False, True),       # fewer rows than one tile, sigmoid
 ])
 def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):

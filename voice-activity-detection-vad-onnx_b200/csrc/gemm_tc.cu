@@ -39,6 +39,9 @@ struct TcArgs {
   int64_t ldy;
   int64_t M;
   int K, N, n_pad, kc, n_k16, act, n_stages, n_tiles, tmem_cols, vec_x, vec_y;
+  const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
+  float head_b;
+  float* head_out;       // [rows]; when set the N-wide output itself is not written
   int debug;  // bit0: skip global stores, bit1: skip global loads (VADX_TC_DEBUG, perf experiments only)
 };
 
@@ -53,7 +56,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
   uint8_t* a_smem = w_smem + w_bytes;
   float* bias_s = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);
   float* stage_out = bias_s + g.n_pad;  // 4 warps x 32 rows x 36 floats: epilogue transpose buffer
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * kTcOutLd);
+  float* head_s = stage_out + 4 * 32 * kTcOutLd;  // [n_pad] fused-head weights (zeros when unused)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + g.n_pad);
   // bars: full[4], empty[4], tmem_full[2], tmem_empty[2], wbar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
@@ -77,7 +81,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < g.n_pad; i += blockDim.x) bias_s[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < g.n_pad; i += blockDim.x) {
+    bias_s[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
+    head_s[i] = (g.head_w && i < g.N) ? g.head_w[i] : 0.f;
+  }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)g.tmem_cols)
@@ -214,7 +221,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * g.n_pad);
-      if (!g.res && g.vec_y && !(g.debug & 1) && !(g.debug & 8)) {
+      if (g.head_out) {
+        // fused narrow head: the row's N activations never leave the SM
+        float acc = 0.f;
+        for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc = fmaf(apply_act(v[j] + bias_s[c0 + j], ACT), head_s[c0 + j], acc);
+        }
+        if (row_ok) g.head_out[row] = 1.0f / (1.0f + expf(-(acc + g.head_b)));
+      } else if (!g.res && g.vec_y && !(g.debug & 1) && !(g.debug & 8)) {
         // coalesced path: each thread stages 32 columns of its row in shared memory, then the warp
         // writes them out 4 rows x 128 B per instruction (row-per-thread stores would touch 32
         // different 128-byte lines per instruction and saturate the LSU tag stage)
@@ -337,7 +354,7 @@ TcShape tc_shape(int n_in, int n_out) {
   s.kc = (int)ceil_div(n_in, kTcBK);
   s.n_k16 = (int)ceil_div(n_in, 16);
   s.w_bytes = (size_t)s.kc * 2 * s.n_pad * 128;
-  const size_t misc = (size_t)s.n_pad * 4 + (size_t)4 * 32 * kTcOutLd * 4 + 13 * 8 + 16;
+  const size_t misc = (size_t)s.n_pad * 8 + (size_t)4 * 32 * kTcOutLd * 4 + 13 * 8 + 16;
   s.ok = s.n_pad <= 256 && n_out > 8;
   if (s.ok) {
     size_t left = kTcSmemBudget > s.w_bytes + misc ? kTcSmemBudget - s.w_bytes - misc : 0;
@@ -381,11 +398,31 @@ extern "C" int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* 
   return VADX_OK;
 }
 
+static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
+                            const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
+                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream);
+
 extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                                   const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows,
                                   int n_in, int n_out, int act, void* stream) {
+  VADX_REQUIRE(d_y, "vadx_linear_tc_f32: null pointer");
+  return linear_tc_launch(d_x, ldx, d_wimg, d_bias, d_residual, ldr, d_y, ldy, n_rows, n_in, n_out, act, nullptr, 0.f,
+                          nullptr, stream);
+}
+
+extern "C" int vadx_linear_head_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
+                                       int64_t n_rows, int n_in, int n_out, int act, const float* d_head_w,
+                                       float head_bias, float* d_head_out, void* stream) {
+  VADX_REQUIRE(d_head_w && d_head_out, "vadx_linear_head_tc_f32: null pointer");
+  return linear_tc_launch(d_x, ldx, d_wimg, d_bias, nullptr, 0, nullptr, n_out, n_rows, n_in, n_out, act, d_head_w,
+                          head_bias, d_head_out, stream);
+}
+
+static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
+                            const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
+                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream) {
   StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
-  VADX_REQUIRE(d_x && d_wimg && d_y, "vadx_linear_tc_f32: null pointer");
+  VADX_REQUIRE(d_x && d_wimg, "vadx_linear_tc_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
   TcShape s = tc_shape(n_in, n_out);
   VADX_REQUIRE(s.ok, "vadx_linear_tc_f32: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
@@ -407,6 +444,7 @@ extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_w
   g.X = d_x; g.ldx = ldx; g.Wimg = static_cast<const uint8_t*>(d_wimg); g.bias = d_bias; g.res = d_residual;
   g.ldr = ldr; g.Y = d_y; g.ldy = ldy; g.M = n_rows; g.K = n_in; g.N = n_out; g.n_pad = s.n_pad; g.kc = s.kc;
   g.n_k16 = s.n_k16; g.act = act; g.n_stages = s.n_stages; g.tmem_cols = s.tmem_cols;
+  g.head_w = d_head_w; g.head_b = head_b; g.head_out = d_head_out;
   int64_t tiles = ceil_div(n_rows, kTcBM);
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_linear_tc_f32: too many rows");
   g.n_tiles = (int)tiles;

@@ -66,6 +66,7 @@ int firered_finalize(vadx_model* m) {
     VADX_TRY(m->upload_raw(n + ".bias", h.H, VADX_DT_F32));
   }
   VADX_TRY(m->upload_linear("out.weight", h.odim, h.H));
+  VADX_TRY(m->upload_raw("out.weight", (int64_t)h.odim * h.H, VADX_DT_F32));
   VADX_TRY(m->upload_raw("out.bias", h.odim, VADX_DT_F32));
   return VADX_OK;
 }
@@ -153,6 +154,12 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     VADX_TRY(lin(bufH, h.H, pre + "fc2.weight", nullptr, nullptr, bufP, h.P, VADX_ACT_NONE));
     VADX_TRY(memory(pre + "fsmn.", bufP, memA, memB));
     std::swap(memA, memB);
+  }
+  if (use_tc && h.M == 1 && h.odim == 1 && m->d<uint8_t>("dfsmn.dnns.0.weight#TC")) {
+    // last dense layer + 1-output sigmoid head in one tensor-core kernel: [S*T][1] == [S][1][T]
+    const HostTensor* ob = m->find("out.bias");
+    return vadx_linear_head_tc_f32(memA, h.P, m->d<uint8_t>("dfsmn.dnns.0.weight#TC"), m->d<float>("dfsmn.dnns.0.bias"),
+                                   rows, h.P, h.H, VADX_ACT_RELU, m->d<float>("out.weight"), ob->f32()[0], d_probs, st);
   }
   VADX_TRY(lin(memA, h.P, "dfsmn.dnns.0.weight", "dfsmn.dnns.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
   float* hcur = bufH;
