@@ -55,14 +55,22 @@ __global__ void __launch_bounds__(256) prep_audio_kernel(const T* __restrict__ a
 }
 
 // ------------------------------------------------------------------------------------------ a3
-constexpr int kMelRows = 8;
-__global__ void __launch_bounds__(128) mel_log_kernel(const float* __restrict__ power, int64_t ld_power,
+constexpr int kMelRows = 32;
+__global__ void __launch_bounds__(256) mel_log_kernel(const float* __restrict__ power, int64_t ld_power,
                                                       int64_t n_rows, int n_bins, int n_mels,
                                                       const int32_t* __restrict__ start,
                                                       const int32_t* __restrict__ len, const float* __restrict__ w,
                                                       int max_len, int floor_mode, float floor_value,
                                                       float* __restrict__ out, int64_t ld_out) {
-  extern __shared__ float tile[];  // [kMelRows][n_bins]
+  extern __shared__ float tile[];  // [kMelRows][n_bins] | w [n_mels][max_len] | start, len [n_mels]
+  float* ws = tile + kMelRows * n_bins;
+  int* ss = reinterpret_cast<int*>(ws + n_mels * max_len);
+  int* ls = ss + n_mels;
+  for (int i = threadIdx.x; i < n_mels * max_len; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
+    ss[i] = start[i];
+    ls[i] = len[i];
+  }
   const int64_t r0 = (int64_t)blockIdx.x * kMelRows;
   const int rows = (int)min_i64((int64_t)kMelRows, n_rows - r0);
   for (int i = threadIdx.x; i < rows * n_bins; i += blockDim.x) {
@@ -72,9 +80,9 @@ __global__ void __launch_bounds__(128) mel_log_kernel(const float* __restrict__ 
   __syncthreads();
   for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
     int r = i / n_mels, m = i - r * n_mels;
-    const float* p = tile + r * n_bins + start[m];
-    const float* wm = w + (int64_t)m * max_len;
-    const int L = len[m];
+    const float* p = tile + r * n_bins + ss[m];
+    const float* wm = ws + m * max_len;
+    const int L = ls[m];
     float acc = 0.f;
     for (int j = 0; j < L; ++j) acc = fmaf(wm[j], p[j], acc);
     acc = (floor_mode == VADX_FLOOR_CLAMP) ? fmaxf(acc, floor_value) : acc + floor_value;
@@ -290,11 +298,17 @@ extern "C" int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t 
                "vadx_mel_log_f32: bad shape");
   VADX_REQUIRE(floor_mode == VADX_FLOOR_CLAMP || floor_mode == VADX_FLOOR_ADD, "vadx_mel_log_f32: floor_mode");
   if (n_rows == 0) return VADX_OK;
-  size_t smem = (size_t)kMelRows * n_bins * sizeof(float);
-  VADX_REQUIRE(smem <= 48 * 1024, "vadx_mel_log_f32: n_bins=%d too large", n_bins);
+  size_t smem = ((size_t)kMelRows * n_bins + (size_t)n_mels * max_len + 2 * (size_t)n_mels) * sizeof(float);
+  VADX_REQUIRE(smem <= 200 * 1024, "vadx_mel_log_f32: n_bins=%d too large", n_bins);
+  static bool mel_cfg = false;
+  if (smem > 48 * 1024 && !mel_cfg) {
+    cudaError_t e = cudaFuncSetAttribute(mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mel_log_kernel)");
+    mel_cfg = true;
+  }
   int64_t blocks = ceil_div(n_rows, kMelRows);
   VADX_REQUIRE(blocks <= 0x7fffffffLL, "vadx_mel_log_f32: too many rows");
-  mel_log_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(d_power, ld_power, n_rows, n_bins, n_mels,
+  mel_log_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_power, ld_power, n_rows, n_bins, n_mels,
                                                                         d_start, d_len, d_w, max_len, floor_mode,
                                                                         floor_value, d_out, ld_out);
   return after_launch("vadx_mel_log_f32");

@@ -28,14 +28,30 @@ int firered_finalize(vadx_model* m) {
   FireRedHP h;
   VADX_TRY(firered_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
-  if (vadx_stft_tc_supported(h.n_taps(), h.n_bins())) {
-    // tensor-core DFT image: pre-emphasis folded into the 3-term bf16 basis (stft_tc.cu)
+  // bins the filterbank actually reads: the Kaldi-style bank gives zero weight to DC and Nyquist, so the
+  // DFT only has to produce bins [0, bins_used) (FireRed: 200 of 201 -> 400 columns = exactly five 80-wide tiles)
+  int bins_used = 1;
+  {
+    const HostTensor* ms = m->find("frontend.mel_start");
+    const HostTensor* ml = m->find("frontend.mel_len");
+    if (ms && ml && ms->dtype == VADX_DT_I32 && ml->dtype == VADX_DT_I32 && ms->numel() == h.n_mels && ml->numel() == h.n_mels) {
+      const int32_t* a = reinterpret_cast<const int32_t*>(ms->bytes.data());
+      const int32_t* b = reinterpret_cast<const int32_t*>(ml->bytes.data());
+      for (int i = 0; i < h.n_mels; ++i) bins_used = std::max(bins_used, a[i] + b[i]);
+    } else {
+      bins_used = h.n_bins();
+    }
+    bins_used = std::min(bins_used, h.n_bins());
+    m->scalars["derived.bins_used"] = bins_used;
+  }
+  if (vadx_stft_tc_supported(h.n_taps(), bins_used)) {
+    // tensor-core DFT image: pre-emphasis folded into the 2-term bf16 basis (stft_tc.cu)
     const double preemph = m->scalar("frontend.preemph", 0.97);
     size_t bytes = 0;
     const float* hb = m->find("frontend.basis")->f32();
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, nullptr, 0, &bytes));
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, nullptr, 0, &bytes));
     std::vector<uint8_t> img(bytes);
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, img.data(), img.size(), &bytes));
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, img.data(), img.size(), &bytes));
     VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
   }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
@@ -115,18 +131,19 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   const int mel_max = (int)(melw->numel() / h.n_mels);
 
   const bool use_tc_all = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const int nb_used = (int)m->scalar("derived.bins_used", (double)h.n_bins());
   const uint8_t* stft_img = use_tc_all ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
   if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
     // int16 audio -> power in one tensor-core kernel (exact sample split, folded pre-emphasis)
     VADX_TRY(vadx_stft_power_tc_i16(static_cast<const int16_t*>(d_audio), L, L, S, T, h.hop, h.n_taps(), stft_img,
-                                    h.n_bins(), power, h.ld_power(), st));
+                                    nb_used, power, h.ld_power(), st));
   } else {
     VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0,
                              preemph, 0, sig, Lp, st));
     VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
-                                 h.n_bins(), power, h.ld_power(), st));
+                                 nb_used, power, h.ld_power(), st));
   }
-  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
+  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, nb_used, h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
                             VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
   const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
