@@ -196,3 +196,13 @@ def test_many_streams_lockstep(cuda, wts):
             assert np.array_equal(saved[s, :n_saved[s]].astype(bool), np.array(o["saved"])), s
             agree += 1
     assert agree >= S // 2
+
+
+def test_cuda_graph_replay_is_bit_identical(cuda, wts, golden_dir):
+    """512-sample chunking of vad_sample.wav (254 windows): eager vs one captured window replayed."""
+    cfg = W.FsmnConfig()
+    sess = vadx.FsmnSession(wts, cfg, chunk_len=512)
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    a = fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1234))
+    b = fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1234), graph=True)
+    assert np.array_equal(a.saved, b.saved) and a.timestamps == b.timestamps

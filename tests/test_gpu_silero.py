@@ -105,3 +105,10 @@ def test_many_streams_batched(cuda, wts, session):
     assert err <= TOL
     out = silero_vad.get_speech_timestamps(a, session, return_seconds=True)
     assert len(out) == S
+
+
+def test_cuda_graph_replay_is_bit_identical(cuda, session):
+    a = torch.from_numpy(synth.synth_streams(16, 512 * 20 + 5, seed=6)).float().to(cuda) * 0.000030517578
+    p0 = session.speech_probs(a)
+    p1 = session.speech_probs_graph(a)
+    assert torch.equal(p0, p1)

@@ -46,10 +46,16 @@ def look_backward_frames(look_backward_s: float) -> int:
 def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: float = LOOK_BACKWARD,
                 one_minus_speech_threshold: float = ONE_MINUS_SPEECH_THRESHOLD, snr_threshold_db: float = SNR_THRESHOLD,
                 noise_init_db: float = BACKGROUND_NOISE_dB_INIT, speaking_score: float = SPEAKING_SCORE,
-                silence_score: float = SILENCE_SCORE, keep_trace: bool = False, stream=None):
+                silence_score: float = SILENCE_SCORE, keep_trace: bool = False, stream=None, graph: bool = False):
     """aligned: CUDA int16 [S, n] (already chunk-aligned, see audio_io.align_overlapping).
-    -> (HysteresisState, trace) with every decision of every stream on the device."""
+    -> (HysteresisState, trace) with every decision of every stream on the device.
+    graph=True captures one window (forward + hysteresis + cache hand-over, ~30 kernels) into a CUDA
+    graph and replays it per window: the per-window cost drops from ~30 launches to one, which is
+    what matters for few streams and short chunks (the reference's 512-sample configuration)."""
     import torch
+    if graph and not keep_trace:
+        return _run_streams_graph(session, aligned, stride, look_backward_s, one_minus_speech_threshold,
+                                  snr_threshold_db, noise_init_db, speaking_score, silence_score), []
     S, n = aligned.shape
     L, T = session.chunk_len, session.T
     lb = look_backward_frames(look_backward_s)
@@ -72,10 +78,46 @@ def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: flo
     return state, trace
 
 
+def _run_streams_graph(session, aligned, stride, look_backward_s, thr, snr_threshold_db, noise_init_db, speaking_score,
+                       silence_score):
+    import torch
+    S, n = aligned.shape
+    L, T = session.chunk_len, session.T
+    lb = look_backward_frames(look_backward_s)
+    n_windows = (n - L) // stride + 1
+    state = PP.HysteresisState(S, n_windows * (T - lb) + lb, aligned.device,
+                               noise_init=float(np.float32(noise_init_db + snr_threshold_db) * np.float32(0.1)))
+    caches = session.new_caches(S, aligned.device)
+    chunk = torch.empty((S, L), dtype=torch.int16, device=aligned.device)
+    snr = snr_threshold_db * 0.1
+
+    def window(is_final):
+        score, new, noisy, _, _ = session.run_batch(chunk, caches, state.noise_avg, thr)
+        PP.lookahead_hysteresis(score, state, lb, speaking_score, silence_score, is_final=is_final, noisy_dB=noisy,
+                                snr_threshold=snr)
+        for c, nw in zip(caches, new):
+            c.copy_(nw)
+
+    g = None
+    for wdx in range(n_windows):
+        chunk.copy_(aligned[:, wdx * stride:wdx * stride + L])
+        last = wdx == n_windows - 1
+        if wdx == 0 or last:
+            window(last)                      # eager: warms constants / allocator, and the final-window variant
+            continue
+        if g is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                window(False)
+        g.replay()
+    return state
+
+
 def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD, rng=None,
             save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None,
             fusion_threshold: float = FUSION_THRESHOLD, min_speech_duration: float = MIN_SPEECH_DURATION,
-            normalize: bool = True, keep_trace: bool = False) -> FsmnResult:
+            normalize: bool = True, keep_trace: bool = False, graph: bool = False) -> FsmnResult:
     """One stream, the reference's behaviour: `audio` is a wav path or an int16/float array."""
     import torch
     if isinstance(audio, str):
@@ -84,7 +126,7 @@ def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD,
     lb = look_backward_frames(look_backward_s)
     aligned, stride, _n = audio_io.align_overlapping(a16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
     d = torch.from_numpy(aligned).cuda().unsqueeze(0)
-    state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace)
+    state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace, graph=graph)
     cnt, seg = state.segments()
     n_flags = int(state.n_saved[0].item())
     pairs = seg[0, :int(cnt[0].item())].cpu().numpy()

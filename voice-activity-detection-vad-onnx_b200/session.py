@@ -521,6 +521,47 @@ class SileroSession:
         return probs.cpu()
 
     # ---- B200-native surface ---------------------------------------------------------------------
+    def speech_probs_graph(self, audio):
+        """speech_probs with the per-window kernel sequence (10 launches) captured once into a CUDA graph:
+        each window costs one strided copy into a static buffer, one graph replay and one copy out."""
+        import torch
+        c = self.cfg
+        S, n = audio.shape
+        n_win = (n + c.window - 1) // c.window
+        if n_win < 3:
+            return self.speech_probs(audio)
+        padded = torch.zeros((S, c.context + n_win * c.window), dtype=torch.float32, device=audio.device)
+        padded[:, c.context:c.context + n] = audio
+        n_in = c.window + c.context
+        x = torch.empty((S, n_in), dtype=torch.float32, device=audio.device)
+        state = torch.zeros((2, S, c.hidden), dtype=torch.float32, device=audio.device)
+        probs = torch.empty((n_win, S, 1), dtype=torch.float32, device=audio.device)
+        out = torch.empty((S, 1), dtype=torch.float32, device=audio.device)
+        nxt = torch.empty_like(state)
+        if self._row_stride != n_in:
+            self._e.set_scalar("input.row_stride", float(n_in))
+            self._row_stride = n_in
+
+        def step():
+            self._e.forward([x], [out], [state, nxt], S, n_in, None)
+            state.copy_(nxt)
+
+        g = None
+        for t in range(n_win):
+            x.copy_(padded[:, t * c.window:t * c.window + n_in])
+            if t == 0:
+                step()
+            else:
+                if g is None:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        step()
+                g.replay()
+            probs[t].copy_(out)
+        self._final_state = state
+        return probs[:, :, 0].transpose(0, 1).contiguous()
+
     def speech_probs(self, audio, stream=None):
         """audio: CUDA fp32 [S, n] (already scaled by 1/32768) -> probs CUDA fp32 [S, ceil(n/512)].
         One graph step per 32 ms window for all S streams; the context is not copied: every window
