@@ -277,6 +277,30 @@ int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_
                             int64_t n_streams, int n_frames, const vadx_post_cfg* cfg, int8_t* d_decisions,
                             int32_t* d_seg_count, int32_t* d_segments, int max_segments, void* stream);
 
+/* next-1 -- FireRed StreamVadPostprocessor on device, one stream per lane, state carried between calls
+ * (FireRedVAD/Inference_FireRed_ONNX.py:307-490: ring-buffer mean in float32, 1-based frame counter,
+ * pad_start, max-speech re-arm).  d_state is [S][vadx_stream_post_state_words(smooth_window)] int32;
+ * all-zero bytes are the reset state (the reference's reset(), :335-346).  Each call consumes
+ * d_n_frames[s] (NULL = n_frames) frames of d_probs [S][ld_probs] and APPENDS the segments closed in
+ * this call to d_segments [S][max_segments][2] at index d_seg_count[s] (the caller zeroes the counts
+ * when a stream starts); a count may exceed max_segments, the overflow is not stored.  Segments are
+ * 0-based frame pairs (start, end), both as the reference emits them before the multiplication by
+ * 1/frames-per-second.  d_open [S][2] receives the segment still open after the call, as
+ * (start, last frame seen), or (-1, -1): the reference reports it at the end of every process_batch
+ * call (:470-474). */
+typedef struct {
+  int32_t smooth_window;
+  float threshold;
+  int32_t pad_start_frame;
+  int32_t min_speech_frame;
+  int32_t max_speech_frame;
+  int32_t min_silence_frame;
+} vadx_stream_post_cfg;
+int vadx_stream_post_state_words(int smooth_window);
+int vadx_stream_postprocess(const float* d_probs, int64_t ld_probs, const int32_t* d_n_frames, int64_t n_streams,
+                            int n_frames, const vadx_stream_post_cfg* cfg, int32_t* d_state, int32_t* d_seg_count,
+                            int32_t* d_segments, int max_segments, int32_t* d_open, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Model-level API: the replacement for InferenceSession(...).run(...)
  * ------------------------------------------------------------------------------------------ */
@@ -315,7 +339,10 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
 /* One pass of the model over S independent chunks.
  *   firered: inputs[0] = d_audio int16 [S][n_samples]; outputs[0] = d_probs fp32 [S][odim][T]
  *            (the reference's (1, odim, 98) with the leading 1 generalised to S,
- *            FireRedVAD/Export_FireRedVAD.py:794-807). state is unused (NULL).
+ *            FireRedVAD/Export_FireRedVAD.py:794-807). state = NULL for the static graphs;
+ *            Stream-VAD twin (N2 = 0): state = {caches_in, caches_out}, each fp32
+ *            [R][S][P][(N1-1)*S1], distinct buffers (the reference's (R,1,P,Lb),
+ *            FireRedVAD/Export_FireRedVAD.py:863-876, Inference_FireRed_ONNX.py:758-803).
  *   fsmn:    inputs  = {audio int16 [S][L], noise_average_dB fp32 [S]}
  *            outputs = {score uint8 [S][T], noisy_dB fp32 [S], P(silence) fp32 [S][T] or NULL,
  *                       power_dB fp32 [S][T] or NULL}

@@ -95,6 +95,99 @@ def gen_firered():
     print("firered.npz:", {k: v.shape for k, v in out.items()})
 
 
+# ------------------------------------------------------------------------------ FireRed: whole script
+def gen_firered_script():
+    """The reference's UNMODIFIED FireRedVAD/Inference_FireRed_ONNX.py on vad_sample.wav with all three
+    sections on (VAD, AED, Stream-VAD), its own PyTorch wrappers behind a fake onnxruntime; plus the
+    StreamVadPostprocessor class on synthetic probability tracks, one call and chunked calls."""
+    import vadx  # noqa: F401
+    from vadx import audio_io, weights as W
+    from oracle import ref_runner as RR
+
+    cfg_v = W.FireRedConfig()
+    cfg_a = W.FireRedConfig(odim=3)
+    cfg_s = W.FireRedConfig(N2=0, S2=0, streaming=True)
+    w_v, w_a, w_s = W.firered_random_init(cfg_v, 0), W.firered_random_init(cfg_a, 2), W.firered_random_init(cfg_s, 5)
+    ref_v, _ = firered_reference(cfg_v, w_v)
+    ref_a, _ = firered_reference(cfg_a, w_a)
+    ref_s, _ = firered_reference(cfg_s, w_s, streaming=True)
+    Lb = (cfg_s.N1 - 1) * cfg_s.S1
+
+    def static(ref, odim):
+        def fn(feed):
+            with torch.inference_mode():
+                return [ref(torch.from_numpy(feed["audio"])).numpy()]
+        return RR.FakeSession([RR.NodeArg("audio", [1, 1, 16000], "tensor(int16)")],
+                              [RR.NodeArg("probs", [1, odim, 98], "tensor(float)")], fn)
+
+    def streaming():
+        def fn(feed):
+            with torch.inference_mode():
+                p, c = ref_s(torch.from_numpy(feed["audio"]), torch.from_numpy(feed["caches_in"]))
+            return [p.numpy(), c.numpy()]
+        return RR.FakeSession([RR.NodeArg("audio", [1, 1, "audio_len"], "tensor(int16)"),
+                               RR.NodeArg("caches_in", [cfg_s.R, 1, cfg_s.P, Lb], "tensor(float)")],
+                              [RR.NodeArg("probs", [1, 1, "T"], "tensor(float)"),
+                               RR.NodeArg("caches_out", [cfg_s.R, 1, cfg_s.P, Lb], "tensor(float)")], fn)
+
+    def factory(path):
+        if path.endswith("FireRedVAD.onnx"):
+            return static(ref_v, 1)
+        if path.endswith("FireRedAED.onnx"):
+            return static(ref_a, 3)
+        return streaming()
+
+    wav = os.path.join(RL.REF_ROOT, "FireRedVAD", "vad_sample.wav")
+    ns, files = RR.run_script("FireRedVAD/Inference_FireRed_ONNX.py", factory,
+                              lambda p, sr: audio_io.load_wav_int16(os.path.realpath(p), sr), seed=1234,
+                              files_to_link={"vad_sample.wav": wav})
+    out = {}
+    out["vad_probs"] = np.asarray(ns["all_vad_probs"], np.float32)
+    out["vad_timestamps"] = np.array(ns["timestamps"], np.float64).reshape(-1, 2)
+    out["vad_file_second"] = np.array(files["timestamps_second.txt"])
+    out["vad_file_indices"] = np.array(files["timestamps_indices.txt"])
+    out["aed_probs"] = np.asarray(ns["all_probs"], np.float32)
+    for ev in ("speech", "singing", "music"):
+        out[f"aed_{ev}_timestamps"] = np.array(ns["event2timestamps"][ev], np.float64).reshape(-1, 2)
+        out[f"aed_{ev}_ratio"] = np.array(ns["event2ratio"][ev], np.float64)
+    out["stream_probs"] = np.asarray(ns["all_stream_probs"], np.float32)
+    out["stream_timestamps"] = np.array(ns["stream_timestamps"], np.float64).reshape(-1, 2)
+    out["stream_caches_last"] = np.asarray(ns["caches"], np.float32)[:, 0, ::16, :]
+    print("script: vad", out["vad_probs"].shape, out["vad_timestamps"].tolist())
+    print("        aed", out["aed_probs"].shape, {ev: out[f"aed_{ev}_timestamps"].shape[0] for ev in ("speech", "singing", "music")})
+    print("        stream", out["stream_probs"].shape, out["stream_timestamps"].tolist())
+
+    # StreamVadPostprocessor on synthetic tracks: (ws, thr, pad_start, min_speech, max_speech, min_silence, split)
+    cls = RL.extract("FireRedVAD/Inference_FireRed_ONNX.py")["StreamVadPostprocessor"]
+    rs = np.random.RandomState(7)
+    for i, (n, prm, split) in enumerate([
+            (1400, (5, 0.4, 5, 8, 2000, 20), 14),
+            (3000, (5, 0.4, 5, 8, 150, 20), 14),      # max-speech re-arm
+            (900, (1, 0.5, 0, 1, 2000, 1), 7),        # no smoothing, immediate transitions
+            (2000, (3, 0.45, 9, 4, 90, 6), 0),        # pad_start > window, one call
+            (40, (5, 0.4, 5, 8, 2000, 20), 14),       # ends inside a segment
+            (2, (5, 0.4, 5, 8, 2000, 20), 0)]):
+        steps = rs.normal(0, 0.08, size=n)
+        lvl = np.clip(0.5 + np.cumsum(steps) * 0.5, 0, 1)
+        gate = (np.sin(np.arange(n) / rs.uniform(15, 60)) > rs.uniform(-0.5, 0.5)).astype(np.float64)
+        p = np.clip(0.12 + 0.75 * gate * (0.35 + 0.65 * lvl) + rs.normal(0, 0.06, n), 0, 1).astype(np.float32)
+        if i == 1:
+            p[100:2500] = np.clip(p[100:2500] + 0.5, 0, 1)
+        if i == 4:
+            p[10:] = 0.9
+        whole = cls(*prm).process_batch(p.copy())
+        out[f"sp{i}_probs"] = p
+        out[f"sp{i}_params"] = np.array(prm + (split,), np.float64)
+        out[f"sp{i}_whole"] = np.array(whole, np.float64).reshape(-1, 2)
+        if split:
+            pp = cls(*prm)
+            per_call = [pp.process_batch(p[j:j + split].copy()) for j in range(0, n, split)]
+            out[f"sp{i}_chunked"] = np.array([t for c in per_call for t in c], np.float64).reshape(-1, 2)
+            out[f"sp{i}_chunked_counts"] = np.array([len(c) for c in per_call], np.int32)
+        print(f"sp{i}: n={n} segments {len(whole)}" + (f", chunked total {len(out[f'sp{i}_chunked'])}" if split else ""))
+    np.savez_compressed(os.path.join(GOLD, "firered_script.npz"), **out)
+
+
 # ------------------------------------------------------------------------------ post-processing
 def gen_postproc():
     ns = RL.extract("FireRedVAD/Inference_FireRed_ONNX.py")
@@ -508,7 +601,7 @@ def gen_dfsmn_aec():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_aec.npz"), **out)
 
 
-GENERATORS = {"firered": gen_firered, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+GENERATORS = {"firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "dfsmn_aec": gen_dfsmn_aec}
 
 

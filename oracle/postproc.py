@@ -12,6 +12,9 @@ Follows:
   runs_to_timestamps / fuse_timestamps ........ FSMN/Inference_FSMN_VAD_ONNX.py:102-141
   clock_string ................................ FSMN/Inference_FSMN_VAD_ONNX.py:144-153
   valid_frames ................................ FireRedVAD/Inference_FireRed_ONNX.py:84-89
+  StreamPost .................................. FireRedVAD/Inference_FireRed_ONNX.py:307-490
+        (StreamVadPostprocessor: ring-buffer mean, 1-based frame counter, pad_start, max-speech re-arm,
+         the open segment re-reported at the end of every call)
 """
 from __future__ import annotations
 
@@ -213,3 +216,98 @@ def clock_string(seconds: float) -> str:
     whole = int(tot)
     ms = int((tot - whole) * 1000)
     return f"{whole // 3600:02}:{(whole % 3600) // 60:02}:{whole % 60:02}.{ms:03}"
+
+
+class StreamPost:
+    """Call-by-call streaming segmenter (FireRedVAD/Inference_FireRed_ONNX.py:307-490), pinned by
+    tests/golden/firered_script.npz.  `feed(probs)` returns the (start_s, end_s) pairs of that call:
+    every segment closed inside the call, then -- if a segment is open when the call ends -- that open
+    segment up to the last frame seen (so a chunked caller sees it again, longer, on the next call)."""
+
+    SIL, MAYBE_SP, SP, MAYBE_SIL = 0, 1, 2, 3
+
+    def __init__(self, ws, thr, pad_start, min_speech, max_speech, min_silence, fps=100):
+        self.ws = max(1, int(ws))
+        self.thr = f32(thr)
+        self.pad = max(self.ws, int(pad_start))
+        self.min_sp, self.max_sp, self.min_si = int(min_speech), int(max_speech), int(min_silence)
+        self.inv_fps = 1.0 / fps
+        self.ring = np.zeros(self.ws, f32)
+        self.acc = f32(0.0)
+        self.head = 0
+        self.fill = 0
+        self.frame = 0           # 1-based index of the last frame consumed
+        self.mode = self.SIL
+        self.n_sp = 0
+        self.n_si = 0
+        self.rearm = False       # the previous frame hit max_speech: a new segment starts on this one
+        self.open_from = -1      # 1-based first frame of the open segment, -1 when none
+        self.closed_at = -1      # 1-based last frame of the latest closed segment
+
+    def _mean(self, p):
+        if self.ws <= 1:
+            return p
+        gone = self.ring[self.head]
+        self.ring[self.head] = p
+        self.acc = f32(self.acc + f32(p - gone))
+        self.head = (self.head + 1) % self.ws
+        self.fill = min(self.fill + 1, self.ws)
+        return f32(self.acc / f32(self.fill))
+
+    def feed(self, probs):
+        probs = np.asarray(probs, f32)
+        if probs.shape[0] == 0:
+            return []
+        out = []
+        for p in probs:
+            self.frame += 1
+            k = self.frame
+            speech = bool(self._mean(p) >= self.thr)
+            begin = end = -1
+            if self.rearm:
+                begin = self.open_from = k
+                self.rearm = False
+            force_close = False
+            if self.mode == self.SIL:
+                if speech:
+                    self.mode, self.n_sp = self.MAYBE_SP, 1
+                else:
+                    self.n_si += 1
+                    self.n_sp = 0
+            elif self.mode == self.MAYBE_SP:
+                if speech:
+                    self.n_sp += 1
+                    if self.n_sp >= self.min_sp:
+                        self.mode = self.SP
+                        begin = self.open_from = max(1, k - self.n_sp + 1 - self.pad, self.closed_at + 1)
+                        self.n_si = 0
+                else:
+                    self.mode, self.n_si, self.n_sp = self.SIL, 1, 0
+            elif self.mode == self.SP:
+                self.n_sp += 1
+                if speech:
+                    self.n_si = 0
+                    force_close = self.n_sp >= self.max_sp
+                else:
+                    self.mode, self.n_si = self.MAYBE_SIL, 1
+            else:
+                self.n_sp += 1
+                if speech:
+                    self.mode, self.n_si = self.SP, 0
+                    force_close = self.n_sp >= self.max_sp
+                else:
+                    self.n_si += 1
+                    if self.n_si >= self.min_si:
+                        self.mode = self.SIL
+                        begin, end = self.open_from, k
+                        self.open_from, self.closed_at, self.n_sp = -1, k, 0
+            if force_close:
+                self.rearm = True
+                self.n_sp = 0
+                begin, end = self.open_from, k
+                self.open_from, self.closed_at = -1, k
+            if begin > 0 and end > 0:
+                out.append((max(0, begin - 1) * self.inv_fps, max(0, end - 1) * self.inv_fps))
+        if self.open_from > 0:
+            out.append((max(0, self.open_from - 1) * self.inv_fps, (self.frame - 1) * self.inv_fps))
+        return out

@@ -67,3 +67,54 @@ def test_streaming_twin_cache_carry(gold):
         p, caches = o.forward(chunks[2][i * 2560:(i + 1) * 2560][None], caches)
         assert np.abs(p.numpy()[0, 0] - gold["stream_probs"][i]).max() <= TOL
     assert np.abs(caches.numpy()[:, 0, ::16, :] - gold["stream_caches_last"]).max() <= 1e-4
+
+
+# ---- the UNMODIFIED Inference_FireRed_ONNX.py on vad_sample.wav (tests/golden/firered_script.npz) ----
+@pytest.fixture(scope="module")
+def gold_script(golden_dir):
+    return np.load(os.path.join(golden_dir, "firered_script.npz"))
+
+
+def test_script_vad_and_aed_sections(gold_script, golden_dir, oracle):
+    """VAD then AED, as the script runs them: both tails are padded from the same global numpy stream."""
+    from vadx import audio_io
+    from oracle import postproc as OP
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    rng = np.random.RandomState(1234)
+    chunks, n = audio_io.align_non_overlapping(audio, 16000, rng)
+    nv = OP.valid_frames(n)
+    p = oracle.forward(chunks).numpy().reshape(-1)[:nv]
+    assert np.abs(p - gold_script["vad_probs"]).max() <= TOL
+    dec = OP.frame_decisions(gold_script["vad_probs"], 5, 0.4, 20, 2000, 20, 5, 0)
+    ts = OP.segments_from_decisions(dec, 0.01, 0.025, n / 16000, True)
+    assert np.array_equal(np.array(ts, np.float64).reshape(-1, 2), gold_script["vad_timestamps"])
+    # AED
+    cfg = W.FireRedConfig(odim=3)
+    aed = FireRedOracle(W.firered_random_init(cfg, 2), cfg)
+    chunks2, _ = audio_io.align_non_overlapping(audio, 16000, rng)
+    pa = aed.forward(chunks2).numpy()                       # [n_chunks, 3, 98]
+    pa = np.concatenate(list(pa), axis=1)[:, :nv]
+    assert np.abs(pa - gold_script["aed_probs"]).max() <= TOL
+    for e, (ev, thr) in enumerate((("speech", 0.4), ("singing", 0.5), ("music", 0.5))):
+        d = OP.frame_decisions(gold_script["aed_probs"][e], 5, thr, 20, 2000, 20, 5, 0)
+        t = OP.segments_from_decisions(d, 0.01, 0.025, n / 16000, True)
+        assert np.array_equal(np.array(t, np.float64).reshape(-1, 2), gold_script[f"aed_{ev}_timestamps"])
+        assert round(float(np.mean(gold_script["aed_probs"][e] >= thr)), 3) == float(gold_script[f"aed_{ev}_ratio"])
+
+
+def test_script_stream_section(gold_script, golden_dir):
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    cfg = W.FireRedConfig(N2=0, S2=0, streaming=True)
+    o = FireRedOracle(W.firered_random_init(cfg, 5), cfg)
+    caches = torch.zeros(cfg.R, 1, cfg.P, (cfg.N1 - 1) * cfg.S1)
+    out = []
+    for pos in range(0, len(audio), 2560):
+        c = audio[pos:pos + 2560]
+        if len(c) < 400:
+            c = np.pad(c, (0, 400 - len(c)))
+        p, caches = o.forward(torch.from_numpy(np.ascontiguousarray(c)).view(1, 1, -1), caches)
+        out.append(p.numpy()[0, 0])
+    p = np.concatenate(out)[:557]
+    assert p.shape == gold_script["stream_probs"].shape
+    assert np.abs(p - gold_script["stream_probs"]).max() <= TOL
+    assert np.abs(caches.numpy()[:, 0, ::16, :] - gold_script["stream_caches_last"]).max() <= 1e-4

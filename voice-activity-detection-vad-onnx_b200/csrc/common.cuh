@@ -11,6 +11,10 @@
 
 namespace vadx {
 
+// at or below this many rows the exact-fp32 skinny kernel (gemm_simt.cu) beats a tensor-core launch
+constexpr int kSkinnyMaxRows = 16;
+
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

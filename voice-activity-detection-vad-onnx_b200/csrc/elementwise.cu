@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
                                                                  const float* __restrict__ res, int64_t ldr,
                                                                  float* __restrict__ out, int64_t ldo, int n_frames,
                                                                  int C, const float* __restrict__ cache_in,
-                                                                 int tile_t) {
+                                                                 float* __restrict__ cache_out, int tile_t) {
   constexpr int HL = N1 - 1, HR = N2, W = kMemR + HL + HR;
   const int c = blockIdx.z * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -237,6 +237,12 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
     }
 #pragma unroll
     for (int j = 0; j < HL + HR; ++j) w[j] = w[j + kMemR];
+  }
+  // streaming hand-over: the last HL frames of cat(cache_in, p), written by the stream's last tile
+  if (cache_out && t1 == n_frames) {
+    float* co = cache_out + (s * C + c) * (int64_t)HL;
+#pragma unroll
+    for (int j = 0; j < HL; ++j) co[j] = load(n_frames - HL + j);
   }
 }
 
@@ -326,6 +332,7 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
                "vadx_fsmn_memory_f32: bad shape");
   VADX_REQUIRE(n_streams <= 65535, "vadx_fsmn_memory_f32: at most 65535 streams per call");
   VADX_REQUIRE(d_p != d_out, "vadx_fsmn_memory_f32: in-place operation is not supported");
+  VADX_REQUIRE(!d_cache_out || d_cache_out != d_cache_in, "vadx_fsmn_memory_f32: cache_out must not alias cache_in");
   if (n_streams == 0) return VADX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int halo_l = (n_back - 1) * stride_back;
@@ -346,17 +353,17 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
     dim3 grid2((unsigned)ceil_div(n_frames, tile_t), (unsigned)n_streams, (unsigned)ceil_div(n_channels, 128));
     if (n_ahead == 20)
       fsmn_memory_stream_kernel<20, 20><<<grid2, 128, 0, st>>>(d_p, ldp, d_wl, d_wr, d_residual, ldr, d_out, ldo,
-                                                               n_frames, n_channels, d_cache_in, tile_t);
+                                                               n_frames, n_channels, d_cache_in, d_cache_out, tile_t);
     else
       fsmn_memory_stream_kernel<20, 0><<<grid2, 128, 0, st>>>(d_p, ldp, d_wl, d_wr, d_residual, ldr, d_out, ldo,
-                                                              n_frames, n_channels, d_cache_in, tile_t);
+                                                              n_frames, n_channels, d_cache_in, d_cache_out, tile_t);
   } else {
     dim3 grid((unsigned)ceil_div(n_frames, kMemT), (unsigned)n_streams);
     fsmn_memory_kernel<<<grid, 256, smem, st>>>(d_p, ldp, d_wl, n_back, stride_back, d_wr, n_ahead, stride_ahead,
                                                 d_residual, ldr, d_out, ldo, n_frames, n_channels, d_cache_in);
   }
   VADX_TRY(after_launch("vadx_fsmn_memory_f32"));
-  if (d_cache_out && halo_l > 0) {
+  if (d_cache_out && halo_l > 0 && !fast) {
     int64_t total = n_streams * n_channels * halo_l;
     int64_t blocks = std::min<int64_t>(ceil_div(total, 256), 148 * 8);
     fsmn_cache_out_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_p, ldp, d_cache_in, d_cache_out, n_streams, n_frames,

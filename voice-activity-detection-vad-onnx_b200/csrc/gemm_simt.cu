@@ -271,9 +271,110 @@ __global__ void __launch_bounds__(256) linear_narrow_kernel(const float* __restr
   }
 }
 
+// Skinny problems (M <= 16 rows: one stream, one short window): the 128-row tile above would run the
+// whole K loop in ONE CTA (~25 us of serial latency).  Here the rows sit in shared memory, a CTA owns 32
+// output columns (lane = column, so every weight row is one coalesced 128 B read), its 16 warps split K,
+// and the partial sums meet in shared memory.  Still exact fp32 FFMA.
+constexpr int kSkinnyRows = kSkinnyMaxRows;
+constexpr int kSkinnyWarps = 16;
+constexpr int kSkinnySmem = 48 * 1024;
+
+template <int ROWS, int ALOAD, int EPI>
+__global__ void __launch_bounds__(kSkinnyWarps * 32) gemm_skinny_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) float sm[];   // phase 1: xs[K][ROWS]; phase 2: red[warp][ROWS][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = (int)g.M, K = g.K;
+  for (int idx = tid; idx < ROWS * K; idx += kSkinnyWarps * 32) {
+    const int r = idx / K, k = idx - r * K;
+    sm[k * ROWS + r] = r < M ? a_row_ptr<ALOAD>(g, r)[k] : 0.f;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * 32 + lane;
+  const bool col_ok = col < g.ldb;
+  const float* b = g.B + (col_ok ? col : 0);
+  float acc[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+  constexpr int U = 4;
+  int k = warp;
+  for (; k + (U - 1) * kSkinnyWarps < K; k += U * kSkinnyWarps) {
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) w[u] = __ldg(b + (int64_t)(k + u * kSkinnyWarps) * g.ldb);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4* x4 = reinterpret_cast<const float4*>(sm + (k + u * kSkinnyWarps) * ROWS);
+#pragma unroll
+      for (int q = 0; q < ROWS / 4; ++q) {
+        const float4 x = x4[q];
+        acc[4 * q + 0] = fmaf(x.x, w[u], acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(x.y, w[u], acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(x.z, w[u], acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(x.w, w[u], acc[4 * q + 3]);
+      }
+    }
+  }
+  for (; k < K; k += kSkinnyWarps) {
+    const float w = __ldg(b + (int64_t)k * g.ldb);
+    const float4* x4 = reinterpret_cast<const float4*>(sm + k * ROWS);
+#pragma unroll
+    for (int q = 0; q < ROWS / 4; ++q) {
+      const float4 x = x4[q];
+      acc[4 * q + 0] = fmaf(x.x, w, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(x.y, w, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(x.z, w, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(x.w, w, acc[4 * q + 3]);
+    }
+  }
+  __syncthreads();   // xs is dead from here on
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) sm[(warp * ROWS + r) * 32 + lane] = acc[r];
+  __syncthreads();
+  // warp r finishes row r (ROWS <= kSkinnyWarps)
+  if (warp >= ROWS || warp >= M) return;
+  const int row = warp;
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < kSkinnyWarps; ++w) v += sm[(w * ROWS + row) * 32 + lane];
+  if (EPI == 1) {
+    // lanes (2j, 2j+1) hold (re, im) of bin col/2
+    const float sq = v * v;
+    const float p = sq + __shfl_xor_sync(0xffffffffu, sq, 1);
+    const int f = col >> 1;
+    if ((lane & 1) == 0 && f < g.N) g.C[(int64_t)row * g.ldc + f] = p;
+  } else {
+    if (col >= g.N) return;
+    if (g.bias) v += g.bias[col];
+    const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
+    if (!res_first) v = apply_act(v, g.act);
+    if (g.res) v += g.res[(int64_t)row * g.ldr + col];
+    if (res_first) v = apply_act(v, g.act);
+    g.C[(int64_t)row * g.ldc + col] = v;
+  }
+}
+
+template <int ALOAD, int EPI>
+static bool skinny_fits(const GemmArgs& g) {
+  if (g.M > kSkinnyRows) return false;
+  const int rows = g.M <= 4 ? 4 : (g.M <= 8 ? 8 : 16);
+  return (size_t)rows * g.K * 4 <= (size_t)kSkinnySmem;
+}
+
+template <int ALOAD, int EPI>
+static int launch_skinny(const GemmArgs& g, int n_cols, cudaStream_t st, const char* what) {
+  const unsigned grid = (unsigned)ceil_div(n_cols, 32);
+  const int rows = g.M <= 4 ? 4 : (g.M <= 8 ? 8 : 16);
+  const size_t smem = std::max((size_t)rows * g.K * 4, (size_t)kSkinnyWarps * rows * 32 * 4);
+  if (rows == 4) gemm_skinny_kernel<4, ALOAD, EPI><<<grid, kSkinnyWarps * 32, smem, st>>>(g);
+  else if (rows == 8) gemm_skinny_kernel<8, ALOAD, EPI><<<grid, kSkinnyWarps * 32, smem, st>>>(g);
+  else gemm_skinny_kernel<16, ALOAD, EPI><<<grid, kSkinnyWarps * 32, smem, st>>>(g);
+  return after_launch(what);
+}
+
 template <int ALOAD, int EPI>
 static int launch_gemm(const GemmArgs& g, int n_cols, cudaStream_t st, const char* what) {
   if (g.M == 0) return VADX_OK;
+  if (skinny_fits<ALOAD, EPI>(g)) return launch_skinny<ALOAD, EPI>(g, n_cols, st, what);
   // pick the column tile that wastes fewer padded columns
   int waste128 = (int)(round_up(n_cols, 128) - n_cols), waste64 = (int)(round_up(n_cols, 64) - n_cols);
   bool use64 = waste64 < waste128;

@@ -105,7 +105,15 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   VADX_TRY(firered_hp(m, &h));
   const void* d_audio = dry ? nullptr : in[0];
   float* d_probs = dry ? nullptr : static_cast<float*>(out[0]);
-  (void)state;
+  // Stream-VAD twin (Export_FireRedVAD.py:496-622): state[0] = caches_in, state[1] = caches_out, both
+  // [R][S][P][(N1-1)*S1] -- the reference's (R,1,P,Lb) with the unit axis generalised to S streams
+  const float* cin = (!dry && state && state[0]) ? static_cast<const float*>(state[0]) : nullptr;
+  float* cout = (!dry && state && state[0]) ? static_cast<float*>(state[1]) : nullptr;
+  if (cin) {
+    VADX_REQUIRE(h.N2 == 0, "firered: the streaming graph has no look-ahead taps (N2 must be 0, got %d)", h.N2);
+    VADX_REQUIRE(cout && cout != cin, "firered: streaming needs a caches_out buffer distinct from caches_in");
+  }
+  const int64_t cache_layer = S * (int64_t)h.P * (h.N1 - 1) * h.S1;
   const int T = h.frames(L);
   VADX_REQUIRE(T >= 1, "firered: %lld samples are shorter than one %d-sample frame", (long long)L, h.n_taps());
   const int64_t rows = S * T;
@@ -130,7 +138,7 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   const HostTensor* melw = m->find("frontend.mel_w");
   const int mel_max = (int)(melw->numel() / h.n_mels);
 
-  const bool use_tc_all = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const bool use_tc_all = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
   const int nb_used = (int)m->scalar("derived.bins_used", (double)h.n_bins());
   const uint8_t* stft_img = use_tc_all ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
   if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
@@ -146,7 +154,7 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, nb_used, h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
                             VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
-  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const bool use_tc = use_tc_all;
   auto lin = [&](const float* x, int n_in, const std::string& w, const char* b, const float* res, float* y, int n_out,
                  int act) -> int {
     const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
@@ -156,20 +164,21 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     return vadx_linear_f32(x, n_in, m->d<float>(w + "#T"), (int)round_up(n_out, 4), b ? m->d<float>(b) : nullptr, res,
                            n_out, y, n_out, rows, n_in, n_out, act, st);
   };
-  auto memory = [&](const std::string& pre, const float* p, const float* res, float* out) -> int {
+  auto memory = [&](int layer, const std::string& pre, const float* p, const float* res, float* out) -> int {
     return vadx_fsmn_memory_f32(p, h.P, m->d<float>(pre + "lookback_filter.weight"), h.N1, h.S1,
                                 h.N2 > 0 ? m->d<float>(pre + "lookahead_filter.weight") : nullptr, h.N2,
-                                h.N2 > 0 ? h.S2 : 1, res, h.P, out, h.P, S, T, h.P, nullptr, nullptr, st);
+                                h.N2 > 0 ? h.S2 : 1, res, h.P, out, h.P, S, T, h.P,
+                                cin ? cin + layer * cache_layer : nullptr, cin ? cout + layer * cache_layer : nullptr, st);
   };
   VADX_TRY(lin(feat, h.idim, "dfsmn.fc1.0.weight", "dfsmn.fc1.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
   VADX_TRY(lin(bufH, h.H, "dfsmn.fc2.0.weight", "dfsmn.fc2.0.bias", nullptr, bufP, h.P, VADX_ACT_RELU));
-  VADX_TRY(memory("dfsmn.fsmn1.", bufP, nullptr, memA));
+  VADX_TRY(memory(0, "dfsmn.fsmn1.", bufP, nullptr, memA));
   for (int i = 0; i < h.R - 1; ++i) {
     std::string pre = "dfsmn.fsmns." + std::to_string(i) + ".";
     std::string b1 = pre + "fc1.0.bias";
     VADX_TRY(lin(memA, h.P, pre + "fc1.0.weight", b1.c_str(), nullptr, bufH, h.H, VADX_ACT_RELU));
     VADX_TRY(lin(bufH, h.H, pre + "fc2.weight", nullptr, nullptr, bufP, h.P, VADX_ACT_NONE));
-    VADX_TRY(memory(pre + "fsmn.", bufP, memA, memB));
+    VADX_TRY(memory(i + 1, pre + "fsmn.", bufP, memA, memB));
     std::swap(memA, memB);
   }
   if (use_tc && h.M == 1 && h.odim == 1 && m->d<uint8_t>("dfsmn.dnns.0.weight#TC")) {

@@ -126,7 +126,7 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   const float floor_v = (float)m->scalar("frontend.log_floor", 1e-5);
   const float thr = (float)m->scalar("one_minus_speech_threshold", 1.0);
   const float ratio = (float)m->scalar("speech_2_noise_ratio", 1.0);
-  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
   const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
 
   VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,

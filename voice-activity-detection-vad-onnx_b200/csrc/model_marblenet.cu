@@ -138,7 +138,7 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
                             B[0], h.n_mels, st));
   auto lin = [&](const float* a, int n_in, const std::string& w, const std::string& b, const float* res, float* y,
                  int n_out, int64_t rows, int act) -> int {
-    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
+    const uint8_t* img = use_tc && rows > kSkinnyMaxRows ? m->d<uint8_t>(w + "#TC") : nullptr;
     if (img) return vadx_linear_tc_f32(a, n_in, img, m->d<float>(b), res, n_out, y, n_out, rows, n_in, n_out, act, st);
     return vadx_linear_f32(a, n_in, m->d<float>(w + "#T"), (int)round_up(n_out, 4), m->d<float>(b), res, n_out, y, n_out,
                            rows, n_in, n_out, act, st);

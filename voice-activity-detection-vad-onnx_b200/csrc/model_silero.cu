@@ -93,7 +93,7 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
   VADX_REQUIRE(in_stride >= 1, "silero: bad input.row_stride");
   const float* st_in = static_cast<const float*>(state[0]);
   float* st_out = static_cast<float*>(state[1]);
-  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && S > kSkinnyMaxRows;
   auto lin = [&](const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, const float* res,
                  int64_t ldr, float* y, int64_t ldy, int n_out, int act) -> int {
     const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;

@@ -323,9 +323,123 @@ __global__ void __launch_bounds__(kPpWarps * 32) postprocess_frames_warp_kernel(
   for (int t = lane; t < n; t += 32) gdec[t] = dec[t];
 }
 
+// ---- Stream-VAD segmenter (FireRedVAD/Inference_FireRed_ONNX.py:307-490) ----
+// state words per stream: 0 head, 1 fill, 2 frame (1-based, last consumed), 3 mode, 4 speech run, 5 silence run,
+// 6 re-arm flag, 7 first frame of the open segment (0 = none), 8 last frame of the latest closed segment
+// (0 = none), 9 ring sum (float bits), 10..15 spare, 16.. ring of smooth_window floats.
+constexpr int kSpHeader = 16;
+
+__global__ void __launch_bounds__(128) stream_post_kernel(const float* __restrict__ probs, int64_t ld_probs,
+                                                          const int32_t* __restrict__ n_frames_per_stream,
+                                                          int64_t n_streams, int n_frames_max,
+                                                          const vadx_stream_post_cfg cfg, int32_t* __restrict__ state,
+                                                          int32_t* __restrict__ seg_count,
+                                                          int32_t* __restrict__ segments, int max_segments,
+                                                          int32_t* __restrict__ open_seg) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  int n = n_frames_per_stream ? n_frames_per_stream[s] : n_frames_max;
+  n = n < 0 ? 0 : (n > n_frames_max ? n_frames_max : n);
+  const int ws = cfg.smooth_window < 1 ? 1 : cfg.smooth_window;
+  const int pad = cfg.pad_start_frame > ws ? cfg.pad_start_frame : ws;
+  int32_t* st = state + s * (int64_t)(kSpHeader + ws);
+  float ring[kMaxSmooth];
+  for (int i = 0; i < ws; ++i) ring[i] = __int_as_float(st[kSpHeader + i]);
+  int head = st[0], fill = st[1], frame = st[2], mode = st[3], n_sp = st[4], n_si = st[5];
+  bool rearm = st[6] != 0;
+  int open_from = st[7], closed_at = st[8];
+  float acc = __int_as_float(st[9]);
+  int count = seg_count ? seg_count[s] : 0;
+  int32_t* seg = segments ? segments + s * (int64_t)max_segments * 2 : nullptr;
+  const float* p = probs + s * ld_probs;
+  for (int t = 0; t < n; ++t) {
+    const float pt = __ldg(p + t);
+    ++frame;
+    float sm = pt;
+    if (ws > 1) {
+      const float gone = ring[head];
+      ring[head] = pt;
+      acc = __fadd_rn(acc, __fsub_rn(pt, gone));
+      head = head + 1 == ws ? 0 : head + 1;
+      if (fill < ws) ++fill;
+      sm = __fdiv_rn(acc, (float)fill);
+    }
+    const bool speech = sm >= cfg.threshold;
+    int begin = 0, end = 0;  // 1-based, 0 = not set
+    bool force_close = false;
+    if (rearm) { begin = open_from = frame; rearm = false; }
+    if (mode == 0) {
+      if (speech) { mode = 1; n_sp = 1; }
+      else { ++n_si; n_sp = 0; }
+    } else if (mode == 1) {
+      if (speech) {
+        if (++n_sp >= cfg.min_speech_frame) {
+          mode = 2;
+          int b = frame - n_sp + 1 - pad;
+          if (b < 1) b = 1;
+          if (b < closed_at + 1) b = closed_at + 1;
+          begin = open_from = b;
+          n_si = 0;
+        }
+      } else { mode = 0; n_si = 1; n_sp = 0; }
+    } else if (mode == 2) {
+      ++n_sp;
+      if (speech) { n_si = 0; force_close = n_sp >= cfg.max_speech_frame; }
+      else { mode = 3; n_si = 1; }
+    } else {
+      ++n_sp;
+      if (speech) { mode = 2; n_si = 0; force_close = n_sp >= cfg.max_speech_frame; }
+      else if (++n_si >= cfg.min_silence_frame) {
+        mode = 0;
+        begin = open_from; end = frame;
+        open_from = 0; closed_at = frame; n_sp = 0;
+      }
+    }
+    if (force_close) {
+      rearm = true;
+      n_sp = 0;
+      begin = open_from; end = frame;
+      open_from = 0; closed_at = frame;
+    }
+    if (begin > 0 && end > 0) {
+      if (seg && count < max_segments) { seg[2 * count] = begin - 1; seg[2 * count + 1] = end - 1; }
+      ++count;
+    }
+  }
+  st[0] = head; st[1] = fill; st[2] = frame; st[3] = mode; st[4] = n_sp; st[5] = n_si; st[6] = rearm ? 1 : 0;
+  st[7] = open_from; st[8] = closed_at; st[9] = __float_as_int(acc);
+  for (int i = 0; i < ws; ++i) st[kSpHeader + i] = __float_as_int(ring[i]);
+  if (seg_count) seg_count[s] = count;
+  if (open_seg) {
+    open_seg[2 * s] = open_from > 0 ? open_from - 1 : -1;
+    open_seg[2 * s + 1] = open_from > 0 ? frame - 1 : -1;
+  }
+}
+
 }  // namespace vadx
 
 using namespace vadx;
+
+extern "C" int vadx_stream_post_state_words(int smooth_window) {
+  return kSpHeader + (smooth_window < 1 ? 1 : smooth_window);
+}
+
+extern "C" int vadx_stream_postprocess(const float* d_probs, int64_t ld_probs, const int32_t* d_n_frames,
+                                       int64_t n_streams, int n_frames, const vadx_stream_post_cfg* cfg,
+                                       int32_t* d_state, int32_t* d_seg_count, int32_t* d_segments, int max_segments,
+                                       int32_t* d_open, void* stream) {
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  VADX_REQUIRE(d_probs && cfg && d_state, "vadx_stream_postprocess: null pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_frames >= 0 && ld_probs >= n_frames, "vadx_stream_postprocess: bad shape");
+  VADX_REQUIRE(cfg->smooth_window <= kMaxSmooth, "vadx_stream_postprocess: smooth_window %d > %d", cfg->smooth_window,
+               kMaxSmooth);
+  VADX_REQUIRE(max_segments >= 0 && (max_segments == 0 || (d_segments && d_seg_count)),
+               "vadx_stream_postprocess: segments buffer without counts");
+  if (n_streams == 0) return VADX_OK;
+  stream_post_kernel<<<(unsigned)ceil_div(n_streams, 128), 128, 0, (cudaStream_t)stream>>>(
+      d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_state, d_seg_count, d_segments, max_segments, d_open);
+  return after_launch("vadx_stream_postprocess");
+}
 
 extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, const int32_t* d_n_frames,
                                        int64_t n_streams, int n_frames, const vadx_post_cfg* cfg,

@@ -1,5 +1,7 @@
-"""FireRedVAD entry point -- the B200 twin of FireRedVAD/Inference_FireRed_ONNX.py (RUN_VAD section,
-:523-613): raw audio in, speech timestamps (seconds + sample indices) out, same two text files.
+"""FireRedVAD entry point -- the B200 twin of FireRedVAD/Inference_FireRed_ONNX.py: raw audio in, speech
+timestamps (seconds + sample indices) out, same two text files.  run_vad = the RUN_VAD section (:523-613),
+run_aed = RUN_AED (:620-738, three event tracks), run_stream_vad = RUN_STREAM_VAD (:745-839, 160 ms chunks
+with cache carry and the streaming segmenter).
 
 Config names and defaults follow the reference's module-level constants (:26-53).
 """
@@ -10,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import audio_io, postprocess as PP, weights as W
-from .session import FireRedSession
+from .session import FireRedSession, FireRedStreamSession
 
 IN_SAMPLE_RATE = 16000
 INPUT_AUDIO_LENGTH = 16000           # static export axis of the reference graph
@@ -21,6 +23,22 @@ MAX_SPEECH_FRAME = 2000
 MIN_SILENCE_FRAME = 20
 MERGE_SILENCE_FRAME = 5
 EXTEND_SPEECH_FRAME = 0
+
+# AED (:55-58) and Stream-VAD (:36-37, :60-66) settings
+MIN_EVENT_FRAME = 20
+MAX_EVENT_FRAME = 2000
+SINGING_THRESHOLD = 0.5
+MUSIC_THRESHOLD = 0.5
+IDX2EVENT = {0: "speech", 1: "singing", 2: "music"}
+STREAM_CHUNK_MS = 160
+STREAM_CHUNK_SAMPLES = int(IN_SAMPLE_RATE * STREAM_CHUNK_MS / 1000)
+WINDOW_LENGTH = 400
+HOP_LENGTH = 160
+STREAM_VAD_THRESHOLD = 0.4
+PAD_START_FRAME = 5
+MIN_SPEECH_FRAME_STREAM = 8
+MAX_SPEECH_FRAME_STREAM = 2000
+MIN_SILENCE_FRAME_STREAM = 20
 
 POST_DEFAULT = PP.FramePostConfig(SMOOTH_WINDOW_SIZE, SPEAKING_SCORE, MIN_SPEECH_FRAME, MAX_SPEECH_FRAME,
                                   MIN_SILENCE_FRAME, MERGE_SILENCE_FRAME, EXTEND_SPEECH_FRAME, 0.01, 0.025, True)
@@ -142,6 +160,139 @@ def run_vad(audio, session: FireRedSession, post: PP.FramePostConfig = POST_DEFA
     if save_timestamps_second and save_timestamps_indices:
         PP.write_timestamp_files(ts, save_timestamps_second, save_timestamps_indices, IN_SAMPLE_RATE)
     return VadResult(ts, probs[0, :n].cpu().numpy(), dec[0, :n].cpu().numpy(), sec, idx)
+
+
+@dataclass
+class AedResult:
+    event2timestamps: dict      # event -> [(start_s, end_s)]
+    event2ratio: dict           # event -> fraction of frames at or above the event threshold, round(, 3)
+    probs: np.ndarray           # [3, valid frames]
+
+
+def run_aed_streams(session: FireRedSession, chunks, lengths, thresholds=None, stream=None):
+    """Batched AED core: chunks CUDA int16 [S, n_chunks, L] -> probs [S, odim, n_chunks*T] and, per event,
+    (decisions, seg_count, segments) from the device post-processor with that event's threshold."""
+    import torch
+    S, n_chunks, L = chunks.shape
+    T = session.frames(L)
+    odim = session.cfg.odim
+    thresholds = thresholds or [SPEAKING_SCORE, SINGING_THRESHOLD, MUSIC_THRESHOLD][:odim]
+    p = session.run_batch(chunks.reshape(S * n_chunks, L), stream=stream)               # [S*n_chunks, odim, T]
+    probs = p.view(S, n_chunks, odim, T).permute(0, 2, 1, 3).reshape(S, odim, n_chunks * T)
+    n_valid = torch.tensor([min(valid_frame_count(int(n)), n_chunks * T) for n in lengths], dtype=torch.int32,
+                           device=chunks.device)
+    per_event = []
+    for e in range(odim):
+        post = PP.FramePostConfig(SMOOTH_WINDOW_SIZE, thresholds[e], MIN_EVENT_FRAME, MAX_EVENT_FRAME, MIN_SILENCE_FRAME,
+                                  MERGE_SILENCE_FRAME, EXTEND_SPEECH_FRAME, 0.01, 0.025, True)
+        per_event.append((post,) + tuple(PP.postprocess_frames(probs[:, e, :], post, n_valid, stream=stream)))
+    return probs, per_event, n_valid
+
+
+def run_aed(audio, session: FireRedSession, rng=None) -> AedResult:
+    """One stream, the reference's RUN_AED section (:620-738)."""
+    import torch
+    if isinstance(audio, str):
+        audio = audio_io.load_wav_int16(audio, IN_SAMPLE_RATE)
+    chunk_len = session.chunk_len or min(IN_SAMPLE_RATE * 3600, len(audio))
+    chunks, audio_len = audio_io.align_non_overlapping(audio, chunk_len, rng)
+    d = torch.from_numpy(chunks).cuda().unsqueeze(0)
+    probs, per_event, n_valid = run_aed_streams(session, d, [audio_len])
+    n = int(n_valid[0].item())
+    host = probs[0, :, :n].cpu().numpy()
+    ts, ratio = {}, {}
+    for e, (post, _dec, cnt, seg) in enumerate(per_event):
+        name = IDX2EVENT.get(e, str(e))
+        pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
+        ts[name] = PP.segments_to_seconds(pairs, n, post, audio_len / IN_SAMPLE_RATE)
+        ratio[name] = round(float(np.mean(host[e] >= post.prob_threshold)) if n > 0 else 0.0, 3)
+    return AedResult(ts, ratio, host)
+
+
+@dataclass
+class StreamVadResult:
+    timestamps: list            # [(start_s, end_s)]
+    probs: np.ndarray           # frame probabilities (valid_frame_count of them at most)
+    caches: object              # final caches (CUDA tensor [R, 1, P, Lb])
+
+
+def stream_frame_plan(lengths, chunk_samples: int = STREAM_CHUNK_SAMPLES):
+    """Frames each stream contributes per call when S streams advance in lock-step (int32 [n_calls, S]).
+    Per stream this is what the reference loop produces (:786-811): full chunks give 1 + (c-400)//160
+    frames, the last partial chunk its own count (one frame if it had to be zero-padded to 400 samples),
+    and the concatenation is cut at valid_frame_count(len)."""
+    lengths = [int(n) for n in lengths]
+    n_calls = max(1, max((n + chunk_samples - 1) // chunk_samples for n in lengths)) if lengths else 0
+    plan = np.zeros((n_calls, len(lengths)), np.int32)
+    for s, n in enumerate(lengths):
+        left = valid_frame_count(n)
+        for k in range(n_calls):
+            l = min(max(n - k * chunk_samples, 0), chunk_samples)
+            f = 0 if l == 0 else (1 if l < WINDOW_LENGTH else 1 + (l - WINDOW_LENGTH) // HOP_LENGTH)
+            f = min(f, left)
+            left -= f
+            plan[k, s] = f
+    return plan
+
+
+def run_stream_vad_streams(session: FireRedStreamSession, audio, lengths, chunk_samples: int = STREAM_CHUNK_SAMPLES,
+                           post: PP.StreamVadPostprocessor | None = None, caches=None, stream=None):
+    """S streams in lock-step: audio CUDA int16 [S, n_calls*chunk_samples] (zero-padded), `lengths` the true
+    sample counts.  Per call: model forward with cache hand-over, then the streaming segmenter, all on the
+    device.  Returns (probs [S, n_calls*T] cuda, post, caches, plan)."""
+    import torch
+    S, n = audio.shape
+    plan = stream_frame_plan(lengths, chunk_samples)
+    n_calls = plan.shape[0]
+    if n != n_calls * chunk_samples:
+        raise ValueError(f"run_stream_vad_streams: audio must be zero-padded to {n_calls * chunk_samples} samples, got {n}")
+    T = session.frames(chunk_samples)
+    post = post or PP.StreamVadPostprocessor(SMOOTH_WINDOW_SIZE, STREAM_VAD_THRESHOLD, PAD_START_FRAME,
+                                             MIN_SPEECH_FRAME_STREAM, MAX_SPEECH_FRAME_STREAM,
+                                             MIN_SILENCE_FRAME_STREAM, n_streams=S, device=audio.device)
+    d_plan = torch.from_numpy(plan).to(audio.device)
+    a = caches if caches is not None else session.new_caches(S, audio.device)
+    b = torch.empty_like(a)
+    probs = torch.empty((S, n_calls, T), dtype=torch.float32, device=audio.device)
+    chunk = torch.empty((S, chunk_samples), dtype=torch.int16, device=audio.device)
+    out = torch.empty((S, 1, T), dtype=torch.float32, device=audio.device)
+    for k in range(n_calls):
+        chunk.copy_(audio[:, k * chunk_samples:(k + 1) * chunk_samples])
+        session.run_batch(chunk, a, out=out, caches_out=b, stream=stream)
+        post.feed(out[:, 0, :], d_plan[k], stream=stream)
+        probs[:, k, :].copy_(out[:, 0, :])
+        a, b = b, a
+    return probs.reshape(S, n_calls * T), post, a, plan
+
+
+def run_stream_vad(audio, session: FireRedStreamSession, chunk_samples: int = STREAM_CHUNK_SAMPLES) -> StreamVadResult:
+    """One stream, the reference's RUN_STREAM_VAD section (:745-839): full chunks in lock-step with
+    themselves, the last partial chunk at its own length (zero-padded to one frame if shorter), so the
+    final caches equal the reference's too."""
+    import torch
+    if isinstance(audio, str):
+        audio = audio_io.load_wav_int16(audio, IN_SAMPLE_RATE)
+    a16 = np.ascontiguousarray(np.asarray(audio, np.int16).reshape(-1))
+    n = len(a16)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = torch.from_numpy(a16).to(dev)
+    post = PP.StreamVadPostprocessor(SMOOTH_WINDOW_SIZE, STREAM_VAD_THRESHOLD, PAD_START_FRAME, MIN_SPEECH_FRAME_STREAM,
+                                     MAX_SPEECH_FRAME_STREAM, MIN_SILENCE_FRAME_STREAM, n_streams=1, device=dev)
+    caches = session.new_caches(1, dev)
+    left = valid_frame_count(n)
+    kept = []
+    for pos in range(0, n, chunk_samples):
+        chunk = d[pos:pos + chunk_samples]
+        if chunk.numel() < WINDOW_LENGTH:
+            chunk = torch.nn.functional.pad(chunk, (0, WINDOW_LENGTH - chunk.numel()))
+        p, caches = session.run_batch(chunk.reshape(1, -1).contiguous(), caches)
+        p = p[:, 0, :min(p.shape[2], left)]
+        left -= p.shape[1]
+        if p.shape[1]:
+            post.feed(p.contiguous())
+            kept.append(p[0])
+    probs = torch.cat(kept).cpu().numpy() if kept else np.zeros((0,), np.float32)
+    return StreamVadResult(post.timestamps()[0], probs, caches)
 
 
 def main(argv=None):

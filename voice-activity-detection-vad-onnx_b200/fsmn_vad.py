@@ -78,40 +78,72 @@ def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: flo
     return state, trace
 
 
+class _GraphRunner:
+    """Static buffers + one captured window (forward, hysteresis, cache hand-over) for a fixed
+    (streams, chunk length, thresholds) configuration; kept on the session and reused across calls, so
+    a steady caller pays the capture once."""
+
+    def __init__(self, session, S, lb, capacity, device, thr, snr, speaking_score, silence_score):
+        import torch
+        self.session, self.S, self.lb, self.capacity = session, S, lb, capacity
+        self.thr, self.snr, self.speaking, self.silence = thr, snr, speaking_score, silence_score
+        self.state = PP.HysteresisState(S, capacity, device)
+        self.caches = session.new_caches(S, device)
+        self.chunk = torch.empty((S, session.chunk_len), dtype=torch.int16, device=device)
+        self.graph = None
+
+    def reset(self, noise_init: float):
+        s = self.state
+        s.silence.fill_(1)
+        s.n_saved.zero_()
+        s.noise_avg.fill_(float(np.float32(noise_init)))
+        for c in self.caches:
+            c.zero_()
+
+    def window(self, is_final: bool):
+        score, new, noisy, _, _ = self.session.run_batch(self.chunk, self.caches, self.state.noise_avg, self.thr)
+        PP.lookahead_hysteresis(score, self.state, self.lb, self.speaking, self.silence, is_final=is_final, noisy_dB=noisy,
+                                snr_threshold=self.snr)
+        for c, nw in zip(self.caches, new):
+            c.copy_(nw)
+
+    def replay(self):
+        import torch
+        if self.graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.window(False)
+            self.graph = g
+        self.graph.replay()
+
+
 def _run_streams_graph(session, aligned, stride, look_backward_s, thr, snr_threshold_db, noise_init_db, speaking_score,
                        silence_score):
-    import torch
+    """NOTE: the returned HysteresisState belongs to the cached runner and is overwritten by the next
+    graph-mode call on this session with the same configuration; read the segments before that."""
     S, n = aligned.shape
     L, T = session.chunk_len, session.T
     lb = look_backward_frames(look_backward_s)
     n_windows = (n - L) // stride + 1
-    state = PP.HysteresisState(S, n_windows * (T - lb) + lb, aligned.device,
-                               noise_init=float(np.float32(noise_init_db + snr_threshold_db) * np.float32(0.1)))
-    caches = session.new_caches(S, aligned.device)
-    chunk = torch.empty((S, L), dtype=torch.int16, device=aligned.device)
-    snr = snr_threshold_db * 0.1
-
-    def window(is_final):
-        score, new, noisy, _, _ = session.run_batch(chunk, caches, state.noise_avg, thr)
-        PP.lookahead_hysteresis(score, state, lb, speaking_score, silence_score, is_final=is_final, noisy_dB=noisy,
-                                snr_threshold=snr)
-        for c, nw in zip(caches, new):
-            c.copy_(nw)
-
-    g = None
+    need = n_windows * (T - lb) + lb
+    runners = session.__dict__.setdefault("_graph_runners", {})
+    key = (S, L, lb, float(thr), float(snr_threshold_db), float(speaking_score), float(silence_score), str(aligned.device))
+    r = runners.get(key)
+    if r is None or r.capacity < need:
+        r = _GraphRunner(session, S, lb, max(need, 1 << 15), aligned.device, thr, snr_threshold_db * 0.1, speaking_score,
+                         silence_score)
+        runners[key] = r
+    r.reset(float(np.float32(noise_init_db + snr_threshold_db) * np.float32(0.1)))
     for wdx in range(n_windows):
-        chunk.copy_(aligned[:, wdx * stride:wdx * stride + L])
-        last = wdx == n_windows - 1
-        if wdx == 0 or last:
-            window(last)                      # eager: warms constants / allocator, and the final-window variant
-            continue
-        if g is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                window(False)
-        g.replay()
-    return state
+        r.chunk.copy_(aligned[:, wdx * stride:wdx * stride + L])
+        if wdx == n_windows - 1:
+            r.window(True)        # the final-window variant flushes the look-ahead buffer: eager
+        elif wdx == 0 and r.graph is None:
+            r.window(False)       # first ever window eager: uploads constants, warms the allocator
+        else:
+            r.replay()
+    return r.state
 
 
 def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD, rng=None,

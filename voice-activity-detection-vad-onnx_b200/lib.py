@@ -26,6 +26,11 @@ class PostCfg(C.Structure):
                 ("merge_silence_frame", C.c_int32), ("extend_speech_frame", C.c_int32)]
 
 
+class StreamPostCfg(C.Structure):
+    _fields_ = [("smooth_window", C.c_int32), ("threshold", C.c_float), ("pad_start_frame", C.c_int32),
+                ("min_speech_frame", C.c_int32), ("max_speech_frame", C.c_int32), ("min_silence_frame", C.c_int32)]
+
+
 _i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/vadx.h declares (tests check this)
@@ -73,6 +78,9 @@ SIGNATURES = {
     "vadx_alpha_x4_f32": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _f32, _vp, _vp, _vp]),
     "vadx_istft_ola_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
+    "vadx_stream_post_state_words": (C.c_int, [_i32]),
+    "vadx_stream_postprocess": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(StreamPostCfg), _vp, _vp, _vp, _i32, _vp,
+                                          _vp]),
     "vadx_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
     "vadx_destroy": (None, [_vp]),
     "vadx_set_tensor": (C.c_int, [_vp, C.c_char_p, _vp, _i32, C.POINTER(_i64), _i32]),

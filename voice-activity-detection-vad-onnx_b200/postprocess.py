@@ -172,3 +172,78 @@ def write_timestamp_files(timestamps, path_second: str, path_indices: str, sampl
         f.writelines(sec)
     with open(path_indices, "w", encoding="UTF-8") as f:
         f.writelines(idx)
+
+
+class StreamVadPostprocessor:
+    """Device twin of the reference's StreamVadPostprocessor (FireRedVAD/Inference_FireRed_ONNX.py:307-490)
+    for S streams in lock-step.  Same constructor arguments; `process_batch(probs)` keeps the reference's
+    meaning per stream (segments closed in this call, then the still-open segment up to the last frame
+    seen) and the state -- ring buffer, counters, open segment -- stays in HBM between calls."""
+
+    def __init__(self, smooth_window_size, speech_threshold, pad_start_frame, min_speech_frame, max_speech_frame,
+                 min_silence_frame, n_streams: int = 1, max_segments: int = 256, device=None,
+                 frames_per_second: int = 100):
+        import torch
+        self.cfg = lib.StreamPostCfg(max(1, int(smooth_window_size)), float(np.float32(speech_threshold)),
+                                     int(pad_start_frame), int(min_speech_frame), int(max_speech_frame),
+                                     int(min_silence_frame))
+        self.S, self.max_segments = int(n_streams), int(max_segments)
+        self.inv_fps = 1.0 / frames_per_second
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        words = lib.load().vadx_stream_post_state_words(self.cfg.smooth_window)
+        self.state = torch.zeros((self.S, words), dtype=torch.int32, device=dev)
+        self.seg_count = torch.zeros((self.S,), dtype=torch.int32, device=dev)
+        self.segments = torch.empty((self.S, self.max_segments, 2), dtype=torch.int32, device=dev)
+        self.open = torch.full((self.S, 2), -1, dtype=torch.int32, device=dev)
+
+    def reset(self):
+        self.state.zero_()
+        self.seg_count.zero_()
+        self.open.fill_(-1)
+
+    def feed(self, probs, n_frames=None, stream=None):
+        """probs CUDA fp32 [S, T] (this call's frames), n_frames optional CUDA int32 [S].  Asynchronous;
+        closed segments accumulate in self.segments / self.seg_count, the open one lands in self.open."""
+        import torch
+        if not (torch.is_tensor(probs) and probs.is_cuda and probs.dtype == torch.float32 and probs.dim() == 2
+                and probs.shape[0] == self.S and probs.stride(1) == 1):
+            raise ValueError(f"StreamVadPostprocessor.feed: probs must be CUDA fp32 [{self.S}, T] with contiguous rows")
+        if n_frames is not None and not (n_frames.is_cuda and n_frames.dtype == torch.int32 and n_frames.numel() == self.S):
+            raise ValueError("StreamVadPostprocessor.feed: n_frames must be a CUDA int32 tensor [S]")
+        T = probs.shape[1]
+        lib.check(lib.load().vadx_stream_postprocess(probs.data_ptr(), probs.stride(0) if T else 0, lib.ptr(n_frames), self.S,
+                                                     T, C.byref(self.cfg), self.state.data_ptr(),
+                                                     self.seg_count.data_ptr(), self.segments.data_ptr(),
+                                                     self.max_segments, self.open.data_ptr(), lib.stream_ptr(stream)))
+
+    def timestamps(self, first_segment=None):
+        """Per stream [(start_s, end_s)]: the closed segments from index first_segment[s] on, then the
+        open one.  float64 products frame * (1.0 / fps), as the reference (:352, :465-474)."""
+        cnt = self.seg_count.cpu().numpy()
+        if int(cnt.max(initial=0)) > self.max_segments:
+            raise RuntimeError(f"StreamVadPostprocessor: a stream closed {int(cnt.max())} segments, more than "
+                               f"max_segments={self.max_segments}")
+        seg = self.segments.cpu().numpy()
+        opn = self.open.cpu().numpy()
+        out = []
+        for s in range(self.S):
+            k0 = 0 if first_segment is None else int(first_segment[s])
+            ts = [(int(a) * self.inv_fps, int(b) * self.inv_fps) for a, b in seg[s, k0:cnt[s]]]
+            if opn[s, 0] >= 0:
+                ts.append((int(opn[s, 0]) * self.inv_fps, int(opn[s, 1]) * self.inv_fps))
+            out.append(ts)
+        return out
+
+    def process_batch(self, raw_probs):
+        """The reference's call for ONE stream (numpy or CUDA [T]) or S streams ([S, T]); returns the
+        list(s) of (start_s, end_s) this call reports."""
+        import torch
+        p = raw_probs if torch.is_tensor(raw_probs) else torch.from_numpy(np.ascontiguousarray(raw_probs, np.float32))
+        single = p.dim() == 1
+        p = p.reshape(1, -1) if single else p
+        if p.shape[1] == 0:
+            return [] if single else [[] for _ in range(self.S)]
+        before = self.seg_count.cpu().numpy().copy()
+        self.feed(p.to(self.state.device, torch.float32).contiguous())
+        ts = self.timestamps(before)
+        return ts[0] if single else ts

@@ -40,6 +40,7 @@ class _Engine:
         lib.check(self._lib.vadx_create(kind.encode(), hp, len(hparams), C.byref(h)))
         self._h = h
         self._ws = None
+        self._captured_ws = []
 
     def close(self):
         if getattr(self, "_h", None):
@@ -78,6 +79,8 @@ class _Engine:
         dev = inputs[0].device
         need = self.workspace_bytes(n_streams, n_samples)
         ws = self.workspace(need, dev)
+        if self._torch.cuda.is_current_stream_capturing() and not any(ws is k for k in self._captured_ws):
+            self._captured_ws.append(ws)   # a CUDA graph now holds this address: never free it (growth allocates anew)
         ins = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
         outs = (C.c_void_p * len(outputs))(*[t.data_ptr() for t in outputs])
         sts = (C.c_void_p * max(len(states), 1))(*([t.data_ptr() for t in states] or [None]))
@@ -179,6 +182,75 @@ class FireRedSession:
             s1 = min(S, s0 + step)
             self._e.forward([audio[s0:s1]], [out[s0:s1]], [], s1 - s0, L, stream)
         return out
+
+
+class FireRedStreamSession(FireRedSession):
+    """FireRed Stream-VAD session: lookback-only DFSMN with explicit caches.
+
+    I/O contract of the reference graph (FireRedVAD/Export_FireRedVAD.py:863-876; call site
+    Inference_FireRed_ONNX.py:794-799): ``audio`` int16 (1, 1, L), ``caches_in`` fp32 (R, 1, P, (N1-1)*S1)
+    -> ``probs`` fp32 (1, 1, T), ``caches_out``.  The unit axes generalise to S streams in lock-step."""
+
+    def __init__(self, weights: dict, cfg: W.FireRedConfig | None = None, tensor_cores: bool = True):
+        cfg = cfg or W.FireRedConfig(N2=0, S2=0, streaming=True)
+        if not cfg.streaming:
+            raise ValueError("FireRedStreamSession needs a streaming config (FireRedConfig(N2=0, streaming=True))")
+        super().__init__(weights, cfg, chunk_len=None, tensor_cores=tensor_cores)
+        self.lookback = (cfg.N1 - 1) * cfg.S1
+        self._inputs_meta = [NodeArg("audio", [1, 1, "audio_len"], "tensor(int16)"),
+                             NodeArg("caches_in", [cfg.R, 1, cfg.P, self.lookback], "tensor(float)")]
+        self._outputs_meta = [NodeArg("probs", [1, cfg.odim, "T"], "tensor(float)"),
+                              NodeArg("caches_out", [cfg.R, 1, cfg.P, self.lookback], "tensor(float)")]
+
+    def new_caches(self, n_streams: int, device):
+        import torch
+        return torch.zeros((self.cfg.R, n_streams, self.cfg.P, self.lookback), dtype=torch.float32, device=device)
+
+    def run_batch(self, audio, caches_in, out=None, caches_out=None, stream=None):
+        """audio cuda int16 [S, L], caches_in cuda fp32 [R, S, P, Lb] -> (probs [S, odim, T], caches_out)."""
+        import torch
+        if not (torch.is_tensor(audio) and audio.is_cuda and audio.dtype == torch.int16 and audio.dim() == 2
+                and audio.is_contiguous()):
+            raise ValueError("run_batch: audio must be a contiguous CUDA int16 tensor of shape [S, L]")
+        S, L = audio.shape
+        shape = (self.cfg.R, S, self.cfg.P, self.lookback)
+        if not (torch.is_tensor(caches_in) and caches_in.is_cuda and caches_in.dtype == torch.float32
+                and tuple(caches_in.shape) == shape and caches_in.is_contiguous()):
+            raise ValueError(f"run_batch: caches_in must be a contiguous CUDA fp32 tensor of shape {shape}")
+        if S > self.MAX_STREAMS_PER_CALL:
+            raise ValueError(f"run_batch: at most {self.MAX_STREAMS_PER_CALL} streams per call")
+        T = self.frames(L)
+        if T < 1:
+            raise ValueError(f"run_batch: {L} samples are shorter than one frame")
+        if out is None:
+            out = torch.empty((S, self.cfg.odim, T), dtype=torch.float32, device=audio.device)
+        if caches_out is None:
+            caches_out = torch.empty_like(caches_in)
+        elif caches_out.data_ptr() == caches_in.data_ptr() or tuple(caches_out.shape) != shape:
+            raise ValueError("run_batch: caches_out must be a distinct tensor of the caches_in shape")
+        self._e.forward([audio], [out], [caches_in, caches_out], S, L, stream)
+        return out, caches_out
+
+    def run(self, output_names, input_feed: dict):
+        import torch
+        names = [o.name for o in self._outputs_meta]
+        if output_names is not None and any(n not in names for n in output_names):
+            raise ValueError(f"InvalidArgument: unknown output name in {output_names}")
+        if set(input_feed) != {"audio", "caches_in"}:
+            raise ValueError(f"InvalidArgument: expected the inputs 'audio' and 'caches_in', got {sorted(input_feed)}")
+        a, c = input_feed["audio"], input_feed["caches_in"]
+        if not isinstance(a, np.ndarray) or a.dtype != np.int16 or a.ndim != 3 or a.shape[1] != 1:
+            raise ValueError("InvalidArgument: 'audio' must be a numpy int16 array of shape (S, 1, L)")
+        if a.shape[2] < self.cfg.win_length:
+            raise ValueError(f"InvalidArgument: 'audio' length {a.shape[2]} shorter than one frame")
+        S = a.shape[0]
+        want = (self.cfg.R, S, self.cfg.P, self.lookback)
+        if not isinstance(c, np.ndarray) or c.dtype != np.float32 or tuple(c.shape) != want:
+            raise ValueError(f"InvalidArgument: 'caches_in' must be a numpy float32 array of shape {want}")
+        d = torch.from_numpy(np.ascontiguousarray(a[:, 0, :])).cuda()
+        p, co = self.run_batch(d, torch.from_numpy(np.ascontiguousarray(c)).cuda())
+        res = {"probs": p, "caches_out": co}
+        return [res[n].cpu().numpy() for n in (output_names or names)]
 
 
 class FsmnSession:
@@ -523,7 +595,8 @@ class SileroSession:
     # ---- B200-native surface ---------------------------------------------------------------------
     def speech_probs_graph(self, audio):
         """speech_probs with the per-window kernel sequence (10 launches) captured once into a CUDA graph:
-        each window costs one strided copy into a static buffer, one graph replay and one copy out."""
+        each window costs one strided copy into a static buffer, one graph replay and one copy out.
+        The static buffers and the graph are kept per (streams, device) and reused across calls."""
         import torch
         c = self.cfg
         S, n = audio.shape
@@ -533,11 +606,17 @@ class SileroSession:
         padded = torch.zeros((S, c.context + n_win * c.window), dtype=torch.float32, device=audio.device)
         padded[:, c.context:c.context + n] = audio
         n_in = c.window + c.context
-        x = torch.empty((S, n_in), dtype=torch.float32, device=audio.device)
-        state = torch.zeros((2, S, c.hidden), dtype=torch.float32, device=audio.device)
         probs = torch.empty((n_win, S, 1), dtype=torch.float32, device=audio.device)
-        out = torch.empty((S, 1), dtype=torch.float32, device=audio.device)
-        nxt = torch.empty_like(state)
+        runners = self.__dict__.setdefault("_graph_runners", {})
+        r = runners.get((S, str(audio.device)))
+        if r is None:
+            r = {"x": torch.empty((S, n_in), dtype=torch.float32, device=audio.device),
+                 "state": torch.zeros((2, S, c.hidden), dtype=torch.float32, device=audio.device),
+                 "nxt": torch.empty((2, S, c.hidden), dtype=torch.float32, device=audio.device),
+                 "out": torch.empty((S, 1), dtype=torch.float32, device=audio.device), "graph": None}
+            runners[(S, str(audio.device))] = r
+        x, state, nxt, out = r["x"], r["state"], r["nxt"], r["out"]
+        state.zero_()
         if self._row_stride != n_in:
             self._e.set_scalar("input.row_stride", float(n_in))
             self._row_stride = n_in
@@ -546,20 +625,20 @@ class SileroSession:
             self._e.forward([x], [out], [state, nxt], S, n_in, None)
             state.copy_(nxt)
 
-        g = None
         for t in range(n_win):
             x.copy_(padded[:, t * c.window:t * c.window + n_in])
-            if t == 0:
-                step()
+            if r["graph"] is None and t == 0:
+                step()                      # first ever window eager: uploads constants, sizes the workspace
             else:
-                if g is None:
+                if r["graph"] is None:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         step()
-                g.replay()
+                    r["graph"] = g
+                r["graph"].replay()
             probs[t].copy_(out)
-        self._final_state = state
+        self._final_state = state.clone()
         return probs[:, :, 0].transpose(0, 1).contiguous()
 
     def speech_probs(self, audio, stream=None):
@@ -593,6 +672,8 @@ def InferenceSession(kind: str, weights: dict, config=None, **kw):
     """Factory with the reference's constructor name; `kind` replaces the .onnx path."""
     if kind == "firered":
         return FireRedSession(weights, config or W.FireRedConfig(), **kw)
+    if kind == "firered_stream":
+        return FireRedStreamSession(weights, config, **kw)
     if kind == "fsmn":
         return FsmnSession(weights, config or W.FsmnConfig(), **kw)
     if kind == "marblenet":
