@@ -272,8 +272,42 @@ def family_rtfx(dev, world, dist):
     out["dfsmn_aec"] = {"audio_hours_per_sec": world * S * 31841 / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
                         "config": f"{S} near+far stream pairs/GPU x one 31841-sample chunk, echo estimator on fp32 FFMA "
                                   "kernels, mask-net on tcgen05, hysteresis on device"}
+    del sess, near, far
+    # FireRed Stream-VAD: 4096 streams in lock-step, 160 ms chunks (14 frames) with cache carry + streaming segmenter
+    from vadx import firered_vad
+    cfg = W.FireRedConfig(N2=0, S2=0, streaming=True)
+    sess = vadx.FireRedStreamSession(W.firered_random_init(cfg, 5), cfg)
+    S, n_calls = 4096, 25
+    a = torch.from_numpy(synth.synth_chunks_fast(S, n_calls * 2560, seed=16)).to(dev)
+    lens = [n_calls * 2560] * S
+    ms = timed(lambda: firered_vad.run_stream_vad_streams(sess, a, lens), steps=2, warm=2)
+    out["firered_stream"] = {"audio_hours_per_sec": world * S * n_calls * 0.16 / (ms / 1e3) / 3600, "ms_per_step": ms,
+                             "ms_per_160ms_chunk": ms / n_calls,
+                             "config": f"{S} streams/GPU x {n_calls} chunks of 2560 samples, caches + streaming segmenter on device"}
+    del sess, a
     for v in out.values():
         v["rtfx"] = v["audio_hours_per_sec"] * 3600
+    # BASELINE configs[0] as the reference runs it: ONE stream, 512-sample chunks, batch 1 (latency-bound; the
+    # reference publishes RTF 0.0047 for it on an i3-12300).  Wall clock around the whole entry point.
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "vad_sample_16k.npz")
+    if os.path.exists(gold):
+        import time
+        audio = np.load(gold)["audio"].astype(np.int16)
+        cfg = W.FsmnConfig()
+        sess = vadx.FsmnSession(W.fsmn_random_init(cfg, 0), cfg, chunk_len=512)
+        for graph in (False, True):
+            for _ in range(2):
+                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), graph=graph)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), graph=graph)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            out["fsmn_c1_single_stream" + ("_graph" if graph else "")] = {
+                "rtf": dt / (len(audio) / 16000.0), "rtfx": (len(audio) / 16000.0) / dt, "seconds": dt,
+                "config": "vad_sample.wav (5.59 s), one stream, 512-sample chunks, 254 windows, wall clock of run_vad"
+                          + (", one CUDA-graph replay per window" if graph else ", eager launches")}
     return out
 
 

@@ -519,6 +519,45 @@ def gen_silero():
     np.savez_compressed(os.path.join(GOLD, "silero.npz"), **out)
 
 
+def gen_silero_iterator():
+    """The reference's VADIterator (Silero/modeling_modified/utils_vad.py:494-585) driven window by window
+    with replayed probabilities: the online start/end events, in samples and in seconds."""
+    uv = RL.import_file("Silero/modeling_modified/utils_vad.py", "silero_utils_vad_ref")
+
+    class Replay:
+        def __init__(self, probs):
+            self.p, self.i = probs, 0
+
+        def reset_states(self):
+            self.i = 0
+
+        def __call__(self, chunk, sr):
+            v = self.p[self.i]
+            self.i += 1
+            return torch.tensor([[v]])
+
+    rs = np.random.RandomState(11)
+    out = {}
+    for i, (n, thr, min_sil, pad) in enumerate([(600, 0.5, 100, 30), (900, 0.4, 250, 0), (300, 0.6, 32, 100)]):
+        lvl = np.clip(0.5 + np.cumsum(rs.normal(0, 0.06, n)), 0, 1)
+        gate = (np.sin(np.arange(n) / rs.uniform(8, 40)) > rs.uniform(-0.6, 0.3)).astype(np.float64)
+        p = np.clip(0.1 + 0.85 * gate * (0.5 + 0.5 * lvl) + rs.normal(0, 0.05, n), 0, 1).astype(np.float32)
+        for sec in (False, True):
+            it = uv.VADIterator(Replay([float(v) for v in p]), threshold=thr, sampling_rate=16000,
+                                min_silence_duration_ms=min_sil, speech_pad_ms=pad)
+            ev = []
+            for w in range(n):
+                r = it(torch.zeros(512), return_seconds=sec, time_resolution=2)
+                if r is not None:
+                    (k, v), = r.items()
+                    ev.append((w, 0 if k == "start" else 1, v))
+            out[f"it{i}_{'sec' if sec else 'smp'}"] = np.array(ev, np.float64).reshape(-1, 3)
+        out[f"it{i}_probs"] = p
+        out[f"it{i}_params"] = np.array([thr, min_sil, pad], np.float64)
+        print(f"it{i}: {n} windows -> {len(ev)} events")
+    np.savez_compressed(os.path.join(GOLD, "silero_iter.npz"), **out)
+
+
 # ------------------------------------------------------------------------------ DFSMN AEC-VAD
 def dfsmn_aec_reference(cfg, weights):
     """The reference's own DFSMN_VAD wrapper around its own NET / AlphaPredictor / UniDeepFsmn modules."""
@@ -602,7 +641,7 @@ def gen_dfsmn_aec():
 
 
 GENERATORS = {"firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
-              "marblenet": gen_marblenet, "silero": gen_silero, "dfsmn_aec": gen_dfsmn_aec}
+              "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 
 def main(argv):

@@ -35,3 +35,36 @@ def test_pad_and_convert_matches_reference(gold):
         n_samples = int(gold[f"ts{i}_params"][0])
         conv = [(max(round(a / 16000, 1), 0), min(round(b / 16000, 1), n_samples / 16000)) for a, b in smp.tolist()]
         assert np.array_equal(np.array(conv, np.float64).reshape(-1, 2), sec)
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_vad_iterator_events_match_reference_class(golden_dir, i):
+    """host logic only (replayed probabilities): start/end events of the reference's VADIterator"""
+    import torch
+    from vadx.silero_vad import VADIterator
+    g = np.load(os.path.join(golden_dir, "silero_iter.npz"))
+    p = g[f"it{i}_probs"]
+    thr, min_sil, pad = g[f"it{i}_params"]
+
+    class Replay:
+        def __init__(self):
+            self.i = 0
+
+        def reset_states(self):
+            self.i = 0
+
+        def __call__(self, chunk, sr):
+            self.i += 1
+            return torch.tensor([[float(p[self.i - 1])]])
+
+    for sec in (False, True):
+        it = VADIterator(Replay(), threshold=float(thr), min_silence_duration_ms=int(min_sil), speech_pad_ms=int(pad))
+        ev = []
+        for w in range(len(p)):
+            r = it(torch.zeros(512), return_seconds=sec, time_resolution=2)
+            if r is not None:
+                (k, v), = r.items()
+                ev.append((w, 0 if k == "start" else 1, v))
+        assert np.array_equal(np.array(ev, np.float64).reshape(-1, 3), g[f"it{i}_{'sec' if sec else 'smp'}"])
+    with pytest.raises(ValueError):
+        VADIterator(Replay(), sampling_rate=44100)

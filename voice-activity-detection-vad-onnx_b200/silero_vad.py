@@ -129,6 +129,58 @@ def get_speech_timestamps(audio, model: SileroSession, threshold: float = 0.5, s
     return out[0] if single else out
 
 
+class VADIterator:
+    """Online start/end events for one stream, window by window -- the twin of the reference's VADIterator
+    (Silero/modeling_modified/utils_vad.py:494-585) with the same constructor, reset_states() and call.
+    `model` is anything with the OnnxWrapper surface (`model(x, sr)` -> [[p]], `reset_states()`), normally a
+    vadx.SileroSession, whose LSTM state stays on the device between windows."""
+
+    def __init__(self, model, threshold: float = 0.5, sampling_rate: int = 16000, min_silence_duration_ms: int = 100,
+                 speech_pad_ms: int = 30):
+        if sampling_rate not in (8000, 16000):
+            raise ValueError("VADIterator does not support sampling rates other than [8000, 16000]")
+        self.model, self.threshold, self.sampling_rate = model, threshold, sampling_rate
+        self.min_silence_samples = sampling_rate * min_silence_duration_ms / 1000
+        self.speech_pad_samples = sampling_rate * speech_pad_ms / 1000
+        self.reset_states()
+
+    def reset_states(self):
+        self.model.reset_states()
+        self.triggered = False
+        self.temp_end = 0          # sample position where the current below-threshold stretch began (0 = none)
+        self.current_sample = 0
+
+    def _fmt(self, samples, return_seconds, time_resolution):
+        return round(samples / self.sampling_rate, time_resolution) if return_seconds else int(samples)
+
+    def __call__(self, x, return_seconds: bool = False, time_resolution: int = 1):
+        import torch
+        if not torch.is_tensor(x):
+            try:
+                x = torch.Tensor(x)
+            except Exception:
+                raise TypeError("Audio cannot be casted to tensor. Cast it manually")
+        n_win = x.shape[-1]
+        self.current_sample += n_win
+        p = float(self.model(x, self.sampling_rate).item())
+        hot = p >= self.threshold
+        if hot:
+            self.temp_end = 0
+            if not self.triggered:
+                self.triggered = True
+                start = max(0, self.current_sample - self.speech_pad_samples - n_win)
+                return {"start": self._fmt(start, return_seconds, time_resolution)}
+            return None
+        if self.triggered and p < self.threshold - 0.15:
+            if not self.temp_end:
+                self.temp_end = self.current_sample
+            if self.current_sample - self.temp_end >= self.min_silence_samples:
+                end = self.temp_end + self.speech_pad_samples - n_win
+                self.temp_end, self.triggered = 0, False
+                return {"end": self._fmt(end, return_seconds, time_resolution)}
+        return None
+
+
 def run_vad(audio, model: SileroSession, save_timestamps_second: str | None = None,
             save_timestamps_indices: str | None = None) -> VadResult:
     """One stream, like the reference script: wav path or int16 array in, fused timestamps out."""
