@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) fsmn_memory_kernel(const float* __restric
 // is involved, so many independent warps keep loads in flight (HBM-bound by design).
 constexpr int kMemR = 14;
 template <int N1, int N2>
-__global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __restrict__ p, int64_t ldp,
+__global__ void __launch_bounds__(128, 4) fsmn_memory_stream_kernel(const float* __restrict__ p, int64_t ldp,
                                                                  const float* __restrict__ wl,
                                                                  const float* __restrict__ wr,
                                                                  const float* __restrict__ res, int64_t ldr,
@@ -177,11 +177,13 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
     if (t < 0 && cache_in) return cache_in[(s * C + c) * (int64_t)HL + (HL + t)];
     return 0.f;
   };
-  float cl[N1], cr[N2 > 0 ? N2 : 1];
+  // taps in shared memory, one private column per thread (written and read by the same thread, so no
+  // barrier): frees 40 registers -> 4 CTAs per SM instead of 3, i.e. a third more loads in flight
+  __shared__ float taps[N1 + N2][128];
 #pragma unroll
-  for (int k = 0; k < N1; ++k) cl[k] = __ldg(wl + c * N1 + k);
+  for (int k = 0; k < N1; ++k) taps[k][threadIdx.x] = __ldg(wl + c * N1 + k);
 #pragma unroll
-  for (int k = 0; k < N2; ++k) cr[k] = __ldg(wr + c * N2 + k);
+  for (int k = 0; k < N2; ++k) taps[N1 + k][threadIdx.x] = __ldg(wr + c * N2 + k);
   float w[W];
 #pragma unroll
   for (int j = 0; j < HL + HR; ++j) w[j] = load(t0 - HL + j);
@@ -219,13 +221,17 @@ __global__ void __launch_bounds__(128) fsmn_memory_stream_kernel(const float* __
 #pragma unroll
     for (int r = 0; r < kMemR; ++r) acc[r] = w[r + HL];
 #pragma unroll
-    for (int k = 0; k < N1; ++k)
+    for (int k = 0; k < N1; ++k) {
+      const float ck = taps[k][threadIdx.x];
 #pragma unroll
-      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(cl[k], w[r + k], acc[r]);
+      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(ck, w[r + k], acc[r]);
+    }
 #pragma unroll
-    for (int k = 0; k < N2; ++k)
+    for (int k = 0; k < N2; ++k) {
+      const float ck = taps[N1 + k][threadIdx.x];
 #pragma unroll
-      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(cr[k], w[r + N1 + k], acc[r]);
+      for (int r = 0; r < kMemR; ++r) acc[r] = fmaf(ck, w[r + N1 + k], acc[r]);
+    }
     float* o = os + (int64_t)tb * ldo;
     if (full) {
 #pragma unroll

@@ -16,16 +16,21 @@
 // pulls its whole stationary operand with a handful of 1-D bulk async copies (cp.async.bulk ->
 // mbarrier complete_tx); activations are converted fp32 -> (hi, lo) bf16 by the loader warps.
 //
-// CTA = 9 warps: 0-3 loaders (global fp32 -> split -> swizzled smem), 4-7 epilogue (TMEM -> regs ->
-// bias/act/residual -> global), 8 = TMEM allocator + single-thread MMA issuer.  Two TMEM
+// CTA = 13 warps: 0-7 loaders (global fp32 -> split -> swizzled smem), 8-11 epilogue (TMEM -> regs ->
+// bias/act/residual -> global), 12 = TMEM allocator + single-thread MMA issuer.  Two TMEM
 // accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1; a 2-4 deep
-// mbarrier ring decouples the loaders from the MMA issuer.
+// mbarrier ring decouples the loaders from the MMA issuer.  The loaders keep TWO 32 KB stages of
+// global loads in flight per SM (three register buffers per thread): with one stage in flight the
+// kernel sat at Little's-law bandwidth (~32 KB / ~1.3 us per SM = 0.57 of the HBM peak).
 #include "tc_ptx.cuh"
 
 namespace vadx {
 
 constexpr int kTcStageBytes = 2 * kTcTileBytes;  // hi + lo
-constexpr int kTcThreads = 288;
+constexpr int kTcLoaderWarps = 8;
+constexpr int kTcEpiWarp0 = kTcLoaderWarps;       // 8..11: (warp & 3) = TMEM lane quarter
+constexpr int kTcMmaWarp = kTcLoaderWarps + 4;
+constexpr int kTcThreads = (kTcLoaderWarps + 5) * 32;
 constexpr int kTcOutLd = 36;  // floats per staged row: 32 columns + 4 pad (144 B: conflict-free 16-byte accesses)
 
 struct TcArgs {
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), 4);     // one elected lane per loader warp
+      mbar_init(full_bar(s), kTcLoaderWarps);     // one elected lane per loader warp
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     bias_s[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
     head_s[i] = (g.head_w && i < g.N) ? g.head_w[i] : 0.f;
   }
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)g.tmem_cols)
                  : "memory");
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       // stationary operand: the packed weight image, kc*2 tiles of n_pad*128 bytes
@@ -136,31 +141,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
         umma_commit(tfull_bar(b));        // accumulator complete -> epilogue
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < kTcLoaderWarps) {
     // ===================== loaders: fp32 rows -> (hi, lo) bf16, swizzled =====================
-    // Software-pipelined: the 16 x 16-byte loads of step i+1 are in flight while step i is split and
-    // stored; rows past the end are clamped to a valid row and zeroed afterwards.
-    const int t = threadIdx.x;   // 0..127
+    // 256 threads: thread = (16-byte k chunk, row mod 32), 4 rows per stage.  Three register buffers
+    // rotate (issue for step i+2, convert step i), so two stages of loads are always in flight;
+    // rows past the end are clamped to a valid row and zeroed afterwards.
+    constexpr int kPasses = kTcBM / (kTcLoaderWarps * 4);   // 4
+    const int t = threadIdx.x;   // 0..255
     const int kq = t & 7;        // 16-byte chunk (8 bf16) within the 64-k atom row
-    const int r_in = t >> 3;     // 0..15
-    auto issue = [&](int tile, int c, float4 (*ld)[2]) {
-      const int64_t row0 = (int64_t)tile * kTcBM;
-      const int k = c * kTcBK + kq * 8;
+    const int r_in = t >> 3;     // 0..31
+    struct Seq { int tile, c; };
+    auto valid = [&](const Seq& q) { return q.tile < g.n_tiles; };
+    auto advance = [&](Seq& q) { if (++q.c == g.kc) { q.c = 0; q.tile += gridDim.x; } };
+    auto issue = [&](const Seq& q, float4 (*ld)[2]) {
+      const int64_t row0 = (int64_t)q.tile * kTcBM;
+      const int k = q.c * kTcBK + kq * 8;
       if (g.debug & 2) {
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
+        for (int pass = 0; pass < kPasses; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
       } else if (g.vec_x && (k + 7 < g.K)) {
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
           const float4* src = reinterpret_cast<const float4*>(g.X + row * g.ldx + k);
           ld[pass][0] = __ldg(src);
           ld[pass][1] = __ldg(src + 1);
         }
       } else {
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
           const float* src = g.X + row * g.ldx + k;
           float v[8];
 #pragma unroll
@@ -172,21 +182,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     };
     int stage = 0;
     uint32_t phase = 0;
-    float4 cur[8][2], nxt[8][2];
-    int tile = blockIdx.x, c = 0;
-    if (tile < g.n_tiles) issue(tile, 0, cur);
-    while (tile < g.n_tiles) {
-      int tile_n = tile, nc = c + 1;
-      if (nc == g.kc) { nc = 0; tile_n += gridDim.x; }
-      if (tile_n < g.n_tiles) issue(tile_n, nc, nxt);
+    auto consume = [&](const Seq& q, float4 (*ld)[2]) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
-      const int64_t row0 = (int64_t)tile * kTcBM;
+      const int64_t row0 = (int64_t)q.tile * kTcBM;
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = pass * 16 + r_in;
-        float4 p0 = cur[pass][0], p1 = cur[pass][1];
+      for (int pass = 0; pass < kPasses; ++pass) {
+        const int r = pass * 32 + r_in;
+        float4 p0 = ld[pass][0], p1 = ld[pass][1];
         if (row0 + r >= g.M) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
         uint4 hi, lo;
         split2(p0.x, p0.y, hi.x, lo.x);
@@ -201,17 +205,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        cur[pass][0] = nxt[pass][0];
-        cur[pass][1] = nxt[pass][1];
-      }
-      tile = tile_n;
-      c = nc;
+    };
+    float4 b0[kPasses][2], b1[kPasses][2], b2[kPasses][2];
+    Seq nxt{(int)blockIdx.x, 0}, cur{(int)blockIdx.x, 0};
+    if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
+    if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+    while (valid(cur)) {
+      if (valid(nxt)) { issue(nxt, b2); advance(nxt); }
+      consume(cur, b0); advance(cur);
+      if (!valid(cur)) break;
+      if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
+      consume(cur, b1); advance(cur);
+      if (!valid(cur)) break;
+      if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+      consume(cur, b2); advance(cur);
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp - 4;  // TMEM lane quarter this warp may touch
+    const int q = warp - kTcEpiWarp0;  // TMEM lane quarter this warp may touch (== warp % 4)
     int it = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
                  : "memory");
