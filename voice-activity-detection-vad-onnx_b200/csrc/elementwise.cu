@@ -55,38 +55,64 @@ __global__ void __launch_bounds__(256) prep_audio_kernel(const T* __restrict__ a
 }
 
 // ------------------------------------------------------------------------------------------ a3
+// Persistent CTAs: the sparse filterbank (weights, start, length per mel) is staged in shared memory ONCE
+// per CTA, then 32-row tiles of the power spectrum stream through: a tile is copied as one contiguous
+// block of float4 (rows are ld_power apart, so 32 rows are 32*ld_power consecutive floats), each warp
+// owns 4 rows and its lanes walk the mels (lane, lane+32, lane+64), so the log-mel row leaves as
+// coalesced 128-byte stores.  No integer division anywhere on the per-element path.
 constexpr int kMelRows = 32;
 __global__ void __launch_bounds__(256) mel_log_kernel(const float* __restrict__ power, int64_t ld_power,
                                                       int64_t n_rows, int n_bins, int n_mels,
                                                       const int32_t* __restrict__ start,
                                                       const int32_t* __restrict__ len, const float* __restrict__ w,
                                                       int max_len, int floor_mode, float floor_value,
-                                                      float* __restrict__ out, int64_t ld_out) {
-  extern __shared__ float tile[];  // [kMelRows][n_bins] | w [n_mels][max_len] | start, len [n_mels]
-  float* ws = tile + kMelRows * n_bins;
-  int* ss = reinterpret_cast<int*>(ws + n_mels * max_len);
+                                                      float* __restrict__ out, int64_t ld_out, int vec_ok) {
+  extern __shared__ __align__(16) float tile[];  // [kMelRows][ldt] | w [n_mels][wl] | start, len [n_mels]
+  const int ldt = (int)ld_power;                 // tile rows keep the global pitch (one block copy)
+  const int wl = max_len | 1;                    // odd pitch: lanes (consecutive mels) hit different banks
+  float* ws = tile + kMelRows * ldt;
+  int* ss = reinterpret_cast<int*>(ws + n_mels * wl);
   int* ls = ss + n_mels;
-  for (int i = threadIdx.x; i < n_mels * max_len; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < n_mels * max_len; i += blockDim.x) {
+    const int m = i / max_len;
+    ws[m * wl + (i - m * max_len)] = w[i];
+  }
   for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
     ss[i] = start[i];
     ls[i] = len[i];
   }
-  const int64_t r0 = (int64_t)blockIdx.x * kMelRows;
-  const int rows = (int)min_i64((int64_t)kMelRows, n_rows - r0);
-  for (int i = threadIdx.x; i < rows * n_bins; i += blockDim.x) {
-    int r = i / n_bins, f = i - r * n_bins;
-    tile[r * n_bins + f] = power[(r0 + r) * ld_power + f];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < rows * n_mels; i += blockDim.x) {
-    int r = i / n_mels, m = i - r * n_mels;
-    const float* p = tile + r * n_bins + ss[m];
-    const float* wm = ws + m * max_len;
-    const int L = ls[m];
-    float acc = 0.f;
-    for (int j = 0; j < L; ++j) acc = fmaf(wm[j], p[j], acc);
-    acc = (floor_mode == VADX_FLOOR_CLAMP) ? fmaxf(acc, floor_value) : acc + floor_value;
-    out[(r0 + r) * ld_out + m] = logf(acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n_rows + kMelRows - 1) / kMelRows;
+  for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const int64_t r0 = tl * kMelRows;
+    const int rows = (int)min_i64((int64_t)kMelRows, n_rows - r0);
+    __syncthreads();  // previous tile fully consumed (and the tables visible on the first pass)
+    const float* src = power + r0 * ld_power;
+    if (vec_ok) {
+      const int n4 = rows * ldt / 4;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) t4[i] = __ldg(s4 + i);
+    } else {
+      for (int i = threadIdx.x; i < rows * ldt; i += blockDim.x) tile[i] = src[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kMelRows / 8; ++rr) {
+      const int r = warp * (kMelRows / 8) + rr;
+      if (r >= rows) break;
+      const float* prow = tile + r * ldt;
+      float* orow = out + (r0 + r) * ld_out;
+      for (int m = lane; m < n_mels; m += 32) {
+        const float* p = prow + ss[m];
+        const float* wm = ws + m * wl;
+        const int L = ls[m];
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(wm[j], p[j], acc);
+        acc = (floor_mode == VADX_FLOOR_CLAMP) ? fmaxf(acc, floor_value) : acc + floor_value;
+        orow[m] = logf(acc);
+      }
+    }
   }
 }
 
@@ -310,19 +336,25 @@ extern "C" int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t 
                "vadx_mel_log_f32: bad shape");
   VADX_REQUIRE(floor_mode == VADX_FLOOR_CLAMP || floor_mode == VADX_FLOOR_ADD, "vadx_mel_log_f32: floor_mode");
   if (n_rows == 0) return VADX_OK;
-  size_t smem = ((size_t)kMelRows * n_bins + (size_t)n_mels * max_len + 2 * (size_t)n_mels) * sizeof(float);
-  VADX_REQUIRE(smem <= 200 * 1024, "vadx_mel_log_f32: n_bins=%d too large", n_bins);
+  size_t smem = ((size_t)kMelRows * ld_power + (size_t)n_mels * (max_len | 1) + 2 * (size_t)n_mels) * sizeof(float);
+  VADX_REQUIRE(smem <= 200 * 1024, "vadx_mel_log_f32: ld_power=%lld too large", (long long)ld_power);
   static bool mel_cfg = false;
-  if (smem > 48 * 1024 && !mel_cfg) {
+  static int n_sm = 148;
+  if (!mel_cfg) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mel_log_kernel)");
     mel_cfg = true;
   }
-  int64_t blocks = ceil_div(n_rows, kMelRows);
-  VADX_REQUIRE(blocks <= 0x7fffffffLL, "vadx_mel_log_f32: too many rows");
+  const int64_t tiles = ceil_div(n_rows, kMelRows);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));   // resident CTAs per SM
+  const int64_t blocks = std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
+  const int vec_ok = ((ld_power & 3) == 0) && aligned16(d_power);
   mel_log_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_power, ld_power, n_rows, n_bins, n_mels,
                                                                         d_start, d_len, d_w, max_len, floor_mode,
-                                                                        floor_value, d_out, ld_out);
+                                                                        floor_value, d_out, ld_out, vec_ok);
   return after_launch("vadx_mel_log_f32");
 }
 

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     int stage = 0;
     uint32_t phase = 0;
     auto consume = [&](const Seq& q, float4 (*ld)[2]) {
-      mbar_wait(empty_bar(stage), phase ^ 1u);
+      mbar_wait(empty_bar(stage), phase ^ 1u, 64);
       uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
       const int64_t row0 = (int64_t)q.tile * kTcBM;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(b), use & 1u);
+      mbar_wait(tfull_bar(b), use & 1u, 64);
       tc_fence_after();
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -248,7 +248,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
         // different 128-byte lines per instruction and saturate the LSU tag stage)
         float* my = stage_out + (q * 32) * kTcOutLd;
         const int64_t tile_row0 = (int64_t)tile * kTcBM + q * 32;
+        const bool rows_full = tile_row0 + 32 <= g.M && !g.debug;
+        float4* const st_dst = reinterpret_cast<float4*>(my + lane * kTcOutLd);
+        const float* const ld_src = my + (lane >> 3) * kTcOutLd + (lane & 7) * 4;
+        float* const out0 = g.Y + (tile_row0 + (lane >> 3)) * g.ldy + (lane & 7) * 4;
+        const int64_t ld4 = 4 * g.ldy;
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+          if (rows_full && c0 + 32 <= g.N) {
+            // interior round (all 32 rows and 32 columns valid): no per-element guards, bias as float4,
+            // the eight staged rows-of-four are read back before the first store is issued
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              st_dst[j] = make_float4(apply_act(v[4 * j] + b.x, ACT), apply_act(v[4 * j + 1] + b.y, ACT),
+                                      apply_act(v[4 * j + 2] + b.z, ACT), apply_act(v[4 * j + 3] + b.w, ACT));
+            }
+            __syncwarp();
+            float4 val[8];
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) val[itr] = *reinterpret_cast<const float4*>(ld_src + itr * 4 * kTcOutLd);
+            float* o = out0 + c0;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) *reinterpret_cast<float4*>(o + itr * ld4) = val[itr];
+            __syncwarp();
+            continue;
+          }
           float v[32];
           tmem_ld16(taddr + (uint32_t)c0, v);
           if (c0 + 16 < g.n_pad) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);

@@ -15,9 +15,10 @@
 //
 // Work decomposition: the (re, im)-interleaved output columns are cut into N-tiles of 48; a CTA keeps
 // the 3-term basis image of ITS N-tile resident in shared memory (129 KB, fetched once with
-// cp.async.bulk) and streams 128-frame row tiles through a 3-deep mbarrier ring.  Same warp roles
-// as gemm_tc.cu: 4 loader warps (int16 -> (hi, lo) bf16, swizzled), 1 MMA issuer, 4 epilogue warps
-// (TMEM -> re^2+im^2 -> global), two TMEM accumulators in ping-pong.
+// cp.async.bulk) and streams 128-frame row tiles through a 2-deep mbarrier ring.  Same warp roles
+// as gemm_tc.cu: 8 loader warps (int16 -> (hi, lo) bf16, swizzled; three register buffers, i.e. the
+// loads of two stages in flight), 4 epilogue warps (TMEM -> re^2+im^2 -> global), 1 MMA issuer, two
+// TMEM accumulators in ping-pong.
 #include "tc_ptx.cuh"
 
 namespace vadx {
@@ -27,7 +28,10 @@ constexpr int kStTerms = 2;                          // bf16 terms of the folded
 constexpr int kStLead = 8;                           // leading zero rows of the folded basis
 constexpr int kStStageBytes = 2 * kTcTileBytes;      // x_hi + x_lo
 constexpr int kStStages = 2;
-constexpr int kStThreads = 288;
+constexpr int kStLoaderWarps = 8;
+constexpr int kStEpiWarp0 = kStLoaderWarps;          // 8..11: (warp & 3) = TMEM lane quarter
+constexpr int kStMmaWarp = kStLoaderWarps + 4;
+constexpr int kStThreads = (kStLoaderWarps + 5) * 32;
 
 struct StftTcArgs {
   const int16_t* X;
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), 4);     // one elected lane per loader warp
+      mbar_init(full_bar(s), kStLoaderWarps);     // one elected lane per loader warp
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kStMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTmemCols)
                  : "memory");
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
   const uint32_t tmem_base = *tmem_slot;
   const int ntile = blockIdx.y;
 
-  if (warp == 8) {
+  if (warp == kStMmaWarp) {
     if (lane == 0) {
       mbar_expect_tx(wbar, (uint32_t)w_bytes);
       const uint8_t* src = g.Wimg + (size_t)ntile * w_bytes;
@@ -141,34 +145,39 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         umma_commit(tfull_bar(b));
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < kStLoaderWarps) {
     // ===================== loaders: int16 frames -> exact (hi, lo) bf16 =====================
-    // Software-pipelined: the 8 x 16-byte loads of step i+1 are in flight while step i is converted
-    // and stored, so the L2/HBM latency is paid once per CTA, not once per stage.
+    // 256 threads: thread = (group of 8 samples, row mod 32), 4 rows per stage.  Three register buffers
+    // rotate (issue for step i+2, convert step i): the loads of two stages are always in flight, so the
+    // L2/HBM latency is hidden instead of being paid once per stage.
+    constexpr int kPasses = kTcBM / (kStLoaderWarps * 4);   // 4
     const int t = threadIdx.x;
     const int kq = t & 7;      // group of 8 consecutive samples
-    const int r_in = t >> 3;   // 0..15
-    // frame origins of this thread's 8 rows in the tile being PREFETCHED (recomputed once per tile:
+    const int r_in = t >> 3;   // 0..31
+    // frame origins of this thread's rows in the tile being PREFETCHED (recomputed once per tile:
     // the 64-bit divisions must not sit on the per-stage path)
-    const int16_t* xs_n[8];
-    int forig_n[8];
+    const int16_t* xs_n[kPasses];
+    int forig_n[kPasses];
     int tile_cached = -1;
-    auto issue = [&](int tile, int c, uint4* raw) {
-      if (tile != tile_cached) {
-        const int64_t row0 = (int64_t)tile * kTcBM;
+    struct Seq { int tile, c; };
+    auto valid = [&](const Seq& q) { return q.tile < g.n_tiles; };
+    auto advance = [&](Seq& q) { if (++q.c == g.kc) { q.c = 0; q.tile += gridDim.x; } };
+    auto issue = [&](const Seq& q, uint4* raw) {
+      if (q.tile != tile_cached) {
+        const int64_t row0 = (int64_t)q.tile * kTcBM;
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 16 + r_in, g.M - 1);
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
           const int64_t s = row / g.n_frames;
           const int fr = (int)(row - s * g.n_frames);
           xs_n[pass] = g.X + s * g.in_stride;
           forig_n[pass] = fr * g.hop - kStLead;
         }
-        tile_cached = tile;
+        tile_cached = q.tile;
       }
-      const int k = c * kTcBK + kq * 8;
+      const int k = q.c * kTcBK + kq * 8;
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
+      for (int pass = 0; pass < kPasses; ++pass) {
         const int16_t* xs = xs_n[pass];
         const int i0 = forig_n[pass] + k;  // first of 8 consecutive samples (stream-relative)
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -193,22 +202,16 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     };
     int stage = 0;
     uint32_t phase = 0;
-    uint4 cur[8], nxt[8];
-    int tile = blockIdx.x, c = 0;
-    if (tile < g.n_tiles) issue(tile, 0, cur);
-    while (tile < g.n_tiles) {
-      int tile_n = tile, nc = c + 1;
-      if (nc == g.kc) { nc = 0; tile_n += gridDim.x; }
-      if (tile_n < g.n_tiles) issue(tile_n, nc, nxt);
-      mbar_wait(empty_bar(stage), phase ^ 1u);
+    auto consume = [&](const Seq& q, const uint4* raw) {
+      mbar_wait(empty_bar(stage), phase ^ 1u, 64);
       uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
-      const int64_t row0 = (int64_t)tile * kTcBM;
+      const int64_t row0 = (int64_t)q.tile * kTcBM;
       if (!(g.debug & 8))
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = pass * 16 + r_in;
-        const uint32_t wds[4] = {cur[pass].x, cur[pass].y, cur[pass].z, cur[pass].w};
+      for (int pass = 0; pass < kPasses; ++pass) {
+        const int r = pass * 32 + r_in;
+        const uint32_t wds[4] = {raw[pass].x, raw[pass].y, raw[pass].z, raw[pass].w};
         uint32_t hi[4], lo[4];
         const bool live = row0 + r < g.M;
 #pragma unroll
@@ -225,20 +228,30 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == kStStages) { stage = 0; phase ^= 1u; }
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) cur[pass] = nxt[pass];
-      tile = tile_n;
-      c = nc;
+    };
+    uint4 b0[kPasses], b1[kPasses], b2[kPasses];
+    Seq nxt{(int)blockIdx.x, 0}, cur{(int)blockIdx.x, 0};
+    if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
+    if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+    while (valid(cur)) {
+      if (valid(nxt)) { issue(nxt, b2); advance(nxt); }
+      consume(cur, b0); advance(cur);
+      if (!valid(cur)) break;
+      if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
+      consume(cur, b1); advance(cur);
+      if (!valid(cur)) break;
+      if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+      consume(cur, b2); advance(cur);
     }
   } else {
     // ===================== epilogue: re^2 + im^2 =====================
-    const int q = warp - 4;
+    const int q = warp - kStEpiWarp0;
     int it = 0;
     const int f0 = ntile * (kStNPad / 2);
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(b), use & 1u);
+      mbar_wait(tfull_bar(b), use & 1u, 64);
       tc_fence_after();
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kStMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
