@@ -46,7 +46,10 @@ enum { VADX_DT_I16 = 0, VADX_DT_F32 = 1, VADX_DT_I32 = 2 };
 /* activation codes; OR VADX_ACT_RES_FIRST in to add the residual BEFORE the activation
  * (JasperBlock: relu(conv + residual)) instead of after it (DFSMN: act(conv) + residual).
  * VADX_ACT_SOFTMAX is only valid for narrow heads (n_out <= 8): softmax across the n_out outputs. */
-enum { VADX_ACT_NONE = 0, VADX_ACT_RELU = 1, VADX_ACT_SIGMOID = 2, VADX_ACT_SOFTMAX = 3, VADX_ACT_RES_FIRST = 16 };
+enum { VADX_ACT_NONE = 0, VADX_ACT_RELU = 1, VADX_ACT_SIGMOID = 2, VADX_ACT_SOFTMAX = 3,
+       /* tensor-core path only (the log-mel contraction as a dense layer): y = log(x.W + bias), and
+        * y = log(max(x.W, bias)) with the bias vector holding the per-column floor */
+       VADX_ACT_LOG = 4, VADX_ACT_LOG_CLAMP = 5, VADX_ACT_RES_FIRST = 16 };
 enum { VADX_FLOOR_CLAMP = 0, VADX_FLOOR_ADD = 1 };
 /* pre-emphasis flavours: NONE; ZERO_HISTORY: y[0]=x[0]-c*0 (pad(1,0)+conv[-c,1],
  * FireRedVAD/Export_FireRedVAD.py:440, NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:245-246);

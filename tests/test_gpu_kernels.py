@@ -183,3 +183,34 @@ def test_postprocess_frames_batch_ragged(cuda):
         d = np.diff(padded)
         pairs = np.stack([np.flatnonzero(d == 1), np.flatnonzero(d == -1)], 1)
         assert cnt[s] == len(pairs) and np.array_equal(seg[s, :cnt[s]], pairs), s
+
+
+@pytest.mark.parametrize("cfg_t", [
+    (5, 0.4, 20, 2000, 20, 5, 0), (3, 0.5, 10, 1000, 10, 3, 0), (5, 0.4, 20, 120, 20, 5, 0), (1, 0.5, 0, 2000, 0, 0, 0),
+    (4, 0.45, 5, 60, 7, 4, 3), (1, 0.5, 3, 50, 0, 0, 2), (7, 0.35, 0, 33, 4, 9, 1), (2, 0.6, 1, 2000, 1, 1, 0),
+    (5, 0.4, 1, 7, 1, 0, 0), (64, 0.4, 30, 500, 30, 5, 0)])
+def test_postprocess_frames_run_based_matches_sequential_oracle(cuda, cfg_t):
+    """The run-based state machines (find-first-set over the flag mask) against the frame-by-frame
+    oracle on lively tracks, for window / min-speech / min-silence / merge / extend / split settings
+    including the degenerate ones; every length from 0 up."""
+    rs = np.random.RandomState(hash(cfg_t) % (2 ** 31))
+    S, T = 160, 700
+    lvl = np.clip(0.5 + np.cumsum(rs.normal(0, 0.07, size=(S, T)), 1), 0, 1)
+    gate = (np.sin(np.arange(T)[None] / rs.uniform(3, 60, size=(S, 1)) + rs.uniform(0, 6, size=(S, 1))) > rs.uniform(-0.7, 0.7, size=(S, 1)))
+    p = np.clip(0.1 + 0.8 * gate * lvl + rs.normal(0, 0.08, (S, T)), 0, 1).astype(np.float32)
+    p[5] = 0.9                                   # one unbroken segment: exercises the split chain
+    p[6, ::2] = 0.9; p[6, 1::2] = 0.1            # alternating flags
+    n = rs.randint(0, T + 1, size=S).astype(np.int32)
+    n[:8] = [0, 1, 2, T, 31, T, T, 33]
+    cfg = PP.FramePostConfig(*cfg_t)
+    dec, cnt, seg = PP.postprocess_frames(torch.from_numpy(p).to(cuda), cfg, torch.from_numpy(n).to(cuda))
+    dec, cnt, seg = dec.cpu().numpy(), cnt.cpu().numpy(), seg.cpu().numpy()
+    n_seg = 0
+    for s in range(S):
+        ref = OP.frame_decisions(p[s, :n[s]], *cfg_t)
+        assert np.array_equal(dec[s, :n[s]], ref), (s, int(n[s]))
+        d = np.diff(np.concatenate(([0], ref, [0])).astype(np.int8))
+        pairs = np.stack([np.flatnonzero(d == 1), np.flatnonzero(d == -1)], 1)
+        assert cnt[s] == len(pairs) and np.array_equal(seg[s, :cnt[s]], pairs), s
+        n_seg += len(pairs)
+    assert n_seg > S // 4

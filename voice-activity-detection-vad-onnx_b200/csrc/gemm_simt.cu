@@ -417,6 +417,7 @@ extern "C" int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt,
   VADX_REQUIRE(ldw >= n_out && (ldw & 3) == 0 && aligned16(d_wt),
                "vadx_linear_f32: ldw=%d must be >= n_out=%d, a multiple of 4, and d_wt 16B aligned", ldw, n_out);
   VADX_REQUIRE(ldx >= n_in && ldy >= n_out, "vadx_linear_f32: row strides smaller than the row");
+  VADX_REQUIRE((act & 15) <= VADX_ACT_SOFTMAX, "vadx_linear_f32: activation %d exists on the tensor-core path only", act);
   cudaStream_t st = (cudaStream_t)stream;
   if (n_out <= 8 && !d_residual)
     return linear_narrow(d_x, ldx, d_wt, ldw, d_bias, d_y, n_rows, n_in, n_out, act, 1, ldy, 1, st);

@@ -50,6 +50,14 @@ struct TcArgs {
   int debug;  // bit0: skip global stores, bit1: skip global loads (VADX_TC_DEBUG, perf experiments only)
 };
 
+// bias + activation of one accumulator value; LOG_CLAMP reads the bias slot as the floor
+template <int ACT>
+__device__ __forceinline__ float bias_act(float v, float b) {
+  if (ACT == VADX_ACT_LOG_CLAMP) return logf(fmaxf(v, b));
+  if (ACT == VADX_ACT_LOG) return logf(v + b);
+  return apply_act(v + b, ACT);
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 template <int ACT>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
 __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g) {
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
           float v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc = fmaf(apply_act(v[j] + bias_s[c0 + j], ACT), head_s[c0 + j], acc);
+          for (int j = 0; j < 16; ++j) acc = fmaf(bias_act<ACT>(v[j], bias_s[c0 + j]), head_s[c0 + j], acc);
         }
         if (row_ok) g.head_out[row] = 1.0f / (1.0f + expf(-(acc + g.head_b)));
       } else if (!g.res && g.vec_y && !(g.debug & 1) && !(g.debug & 8)) {
@@ -263,8 +271,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = b4[j];
-              st_dst[j] = make_float4(apply_act(v[4 * j] + b.x, ACT), apply_act(v[4 * j + 1] + b.y, ACT),
-                                      apply_act(v[4 * j + 2] + b.z, ACT), apply_act(v[4 * j + 3] + b.w, ACT));
+              st_dst[j] = make_float4(bias_act<ACT>(v[4 * j], b.x), bias_act<ACT>(v[4 * j + 1], b.y),
+                                      bias_act<ACT>(v[4 * j + 2], b.z), bias_act<ACT>(v[4 * j + 3], b.w));
             }
             __syncwarp();
             float4 val[8];
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = c0 + j;
-            v[j] = col < g.n_pad ? apply_act(v[j] + bias_s[col < g.n_pad ? col : 0], ACT) : 0.f;
+            v[j] = col < g.n_pad ? bias_act<ACT>(v[j], bias_s[col < g.n_pad ? col : 0]) : 0.f;
           }
           float4* dst = reinterpret_cast<float4*>(my + lane * kTcOutLd);
           if (!(g.debug & 16))
@@ -315,9 +323,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
           tmem_ld16(taddr + (uint32_t)c0, v);
           if (!row_ok || c0 >= g.N || (g.debug & 1)) continue;
           const bool res_first = (g.act & VADX_ACT_RES_FIRST) != 0;
+          if (ACT == VADX_ACT_LOG || ACT == VADX_ACT_LOG_CLAMP) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
-          if (!res_first) {
+            for (int j = 0; j < 16; ++j) v[j] = bias_act<ACT>(v[j], bias_s[c0 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += bias_s[c0 + j];
+          }
+          if (!res_first && ACT != VADX_ACT_LOG && ACT != VADX_ACT_LOG_CLAMP) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], ACT);
           }
@@ -475,6 +488,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_LOG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_tc_kernel)");
     configured = true;
   }
@@ -501,6 +516,12 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     case VADX_ACT_NONE: linear_tc_kernel<VADX_ACT_NONE><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
     case VADX_ACT_RELU: linear_tc_kernel<VADX_ACT_RELU><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
     case VADX_ACT_SIGMOID: linear_tc_kernel<VADX_ACT_SIGMOID><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
+    case VADX_ACT_LOG:
+    case VADX_ACT_LOG_CLAMP:
+      VADX_REQUIRE(!d_residual && !d_head_out && d_bias, "vadx_linear_tc_f32: the log epilogues need a bias/floor vector and take no residual or head");
+      if ((act & 15) == VADX_ACT_LOG) linear_tc_kernel<VADX_ACT_LOG><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+      else linear_tc_kernel<VADX_ACT_LOG_CLAMP><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+      break;
     default: set_error("vadx_linear_tc_f32: activation %d is not supported", act); return VADX_EINVAL;
   }
   return after_launch("vadx_linear_tc_f32");

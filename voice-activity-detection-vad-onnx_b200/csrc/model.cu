@@ -57,6 +57,27 @@ int firered_finalize(vadx_model* m) {
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
+  {
+    // the filterbank as a dense [n_mels][bins_used] layer for the tensor-core path (log + floor in the epilogue)
+    const HostTensor* ms = m->find("frontend.mel_start");
+    const HostTensor* ml = m->find("frontend.mel_len");
+    const HostTensor* mw = m->find("frontend.mel_w");
+    if (ms && ml && mw && ms->numel() == h.n_mels && ml->numel() == h.n_mels && vadx_tc_supported(bins_used, h.n_mels)) {
+      const int max_len = (int)(mw->numel() / h.n_mels);
+      const int32_t* a = reinterpret_cast<const int32_t*>(ms->bytes.data());
+      const int32_t* b = reinterpret_cast<const int32_t*>(ml->bytes.data());
+      std::vector<float> dense((size_t)h.n_mels * bins_used, 0.f);
+      for (int i = 0; i < h.n_mels; ++i)
+        for (int j = 0; j < b[i] && a[i] + j < bins_used; ++j) dense[(size_t)i * bins_used + a[i] + j] = mw->f32()[(size_t)i * max_len + j];
+      size_t bytes = 0;
+      VADX_TRY(vadx_pack_weight_tc(dense.data(), h.n_mels, bins_used, nullptr, 0, &bytes));
+      std::vector<uint8_t> img(bytes);
+      VADX_TRY(vadx_pack_weight_tc(dense.data(), h.n_mels, bins_used, img.data(), img.size(), &bytes));
+      VADX_TRY(m->upload("frontend.mel#TC", img.data(), img.size()));
+      std::vector<float> floor_v((size_t)h.n_mels, (float)m->scalar("frontend.log_floor", 1e-7));
+      VADX_TRY(m->upload("frontend.mel_floor", floor_v.data(), floor_v.size() * sizeof(float)));
+    }
+  }
   VADX_TRY(m->upload_linear("dfsmn.fc1.0.weight", h.H, h.idim));
   VADX_TRY(m->upload_raw("dfsmn.fc1.0.bias", h.H, VADX_DT_F32));
   VADX_TRY(m->upload_linear("dfsmn.fc2.0.weight", h.P, h.H));
@@ -172,9 +193,15 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
       VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
                                    nb_used, power, h.ld_power(), st));
     }
-    VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, nb_used, h.n_mels, m->d<int32_t>("frontend.mel_start"),
-                              m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
-                              VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
+    if (use_tc && m->d<uint8_t>("frontend.mel#TC")) {
+      // log-mel as a dense tensor-core layer: [rows][bins] x [bins][n_mels], log(max(., floor)) in the epilogue
+      VADX_TRY(vadx_linear_tc_f32(power, h.ld_power(), m->d<uint8_t>("frontend.mel#TC"), m->d<float>("frontend.mel_floor"),
+                                  nullptr, 0, feat, h.n_mels, rows, nb_used, h.n_mels, VADX_ACT_LOG_CLAMP, st));
+    } else {
+      VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, nb_used, h.n_mels, m->d<int32_t>("frontend.mel_start"),
+                                m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max,
+                                VADX_FLOOR_CLAMP, floor_v, feat, h.n_mels, st));
+    }
     auto lin = [&](const float* x, int n_in, const std::string& w, const char* b, const float* res, float* y, int n_out,
                    int act) -> int {
       const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;

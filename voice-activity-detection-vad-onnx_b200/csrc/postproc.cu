@@ -323,6 +323,209 @@ __global__ void __launch_bounds__(kPpWarps * 32) postprocess_frames_warp_kernel(
   for (int t = lane; t < n; t += 32) gdec[t] = dec[t];
 }
 
+// ---- run-based variant of the warp-per-stream kernel ----
+// Same results, different cost model: after the (inherently sequential) float32 running sum, the frame
+// flags become a bit mask (__ballot_sync) and the state machines advance from run to run with
+// find-first-set instead of frame by frame.  The 4-state machine, the window extension of rising edges,
+// the gap merge and the dilation are closed-form on (start, end) pairs:
+//   * a speech segment opens at the first frame a of a run of flags that stays set through frame
+//     a + max(min_speech, 1) (the reference back-fills to a, :196-204);
+//   * it closes at e = b + max(min_silence, 1), b the first cleared frame after which the flags stay
+//     clear through e (possible-silence frames count as speech, :209-221), or at the end of the stream;
+//   * every segment that does not start at frame 0 grows left by the smoothing window (:235-243),
+//     gaps shorter than merge_silence close (:245-257), extend_speech dilates both ways (:259-277);
+//   * max_speech splitting at the first minimum of the raw probabilities in the second half of the
+//     window (:279-304) is done while the final pairs are emitted, the arg-min by all lanes.
+// Every lane executes the same control flow on the same shared data (no divergence), lane 0 writes.
+__device__ __forceinline__ int pp_next_set(const uint32_t* w, int t, int n) {
+  if (t >= n) return n;
+  const int nw = (n + 31) >> 5;
+  int wi = t >> 5;
+  uint32_t cur = w[wi] & (0xffffffffu << (t & 31));
+  while (!cur) {
+    if (++wi >= nw) return n;
+    cur = w[wi];
+  }
+  const int r = (wi << 5) + __ffs(cur) - 1;
+  return r < n ? r : n;
+}
+__device__ __forceinline__ int pp_next_clear(const uint32_t* w, int t, int n) {
+  if (t >= n) return n;
+  const int nw = (n + 31) >> 5;
+  int wi = t >> 5;
+  uint32_t cur = ~w[wi] & (0xffffffffu << (t & 31));
+  while (!cur) {
+    if (++wi >= nw) return n;
+    cur = ~w[wi];
+  }
+  const int r = (wi << 5) + __ffs(cur) - 1;
+  return r < n ? r : n;
+}
+
+__global__ void __launch_bounds__(kPpWarps * 32) postprocess_frames_runs_kernel(
+    const float* __restrict__ probs, int64_t ld_probs, const int32_t* __restrict__ n_frames_per_stream,
+    int64_t n_streams, int n_frames_max, const vadx_post_cfg cfg, int8_t* __restrict__ dec_all,
+    int32_t* __restrict__ seg_count, int32_t* __restrict__ segments, int max_segments, int per_warp_floats) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * kPpWarps + warp;
+  if (s >= n_streams) return;
+  int n = n_frames_per_stream ? n_frames_per_stream[s] : n_frames_max;
+  if (n > n_frames_max) n = n_frames_max;
+  if (n < 0) n = 0;
+  float* sp = smem_f + (size_t)warp * per_warp_floats;     // probs [n_frames_max]
+  float* cs = sp + n_frames_max;                            // running sums [n_frames_max + 1], then the pairs
+  int* pairs = reinterpret_cast<int*>(cs);                  // (start, end) x up to (n + 1) / 2
+  int8_t* dec = reinterpret_cast<int8_t*>(cs + n_frames_max + 1);
+  uint32_t* hot = reinterpret_cast<uint32_t*>(dec + ((n_frames_max + 3) & ~3));
+  const float* p = probs + s * ld_probs;
+  int8_t* gdec = dec_all + s * (int64_t)n_frames_max;
+  const int ws = cfg.smooth_window < 1 ? 1 : cfg.smooth_window;
+  const float thr = cfg.threshold;
+  const int min_sp = cfg.min_speech_frame, min_si = cfg.min_silence_frame;
+  const float inv_ws = (float)(1.0 / (double)ws);
+
+  for (int t = lane; t < n; t += 32) sp[t] = __ldg(p + t);
+  __syncwarp();
+  if (ws > 1) {
+    if (lane == 0) {
+      float run = 0.f;
+      cs[0] = 0.f;
+      int t = 0;
+      for (; t + 4 <= n; t += 4) {   // four independent loads per trip; the additions stay in order
+        const float a = sp[t], b = sp[t + 1], c = sp[t + 2], d = sp[t + 3];
+        run = __fadd_rn(run, a); cs[t + 1] = run;
+        run = __fadd_rn(run, b); cs[t + 2] = run;
+        run = __fadd_rn(run, c); cs[t + 3] = run;
+        run = __fadd_rn(run, d); cs[t + 4] = run;
+      }
+      for (; t < n; ++t) { run = __fadd_rn(run, sp[t]); cs[t + 1] = run; }
+    }
+    __syncwarp();
+  }
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int t = t0 + lane;
+    bool h = false;
+    if (t < n) {
+      float sm;
+      if (ws > 1) {
+        if (t < ws - 1) sm = __fdiv_rn(cs[t + 1], (float)(t + 1));
+        else sm = __fmul_rn(__fsub_rn(cs[t + 1], cs[t + 1 - ws]), inv_ws);
+      } else {
+        sm = sp[t];
+      }
+      h = sm >= thr;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) hot[t0 >> 5] = word;
+    if (t < n) dec[t] = 0;
+  }
+  __syncwarp();   // cs is dead from here: its storage becomes the pair list
+
+  // ---- pass A: flags -> speech segments (all lanes, same control flow) ----
+  int ns = 0;
+  auto push = [&](int a, int e) {
+    if (lane == 0) { pairs[2 * ns] = a; pairs[2 * ns + 1] = e; }
+    ++ns;
+  };
+  if (min_sp <= 0 && min_si <= 0) {
+    int t = 0;
+    while (t < n) {
+      const int a = pp_next_set(hot, t, n);
+      if (a >= n) break;
+      const int e = pp_next_clear(hot, a + 1, n);
+      push(a, e);
+      t = e;
+    }
+  } else {
+    const int need_sp = min_sp > 1 ? min_sp : 1, need_si = min_si > 1 ? min_si : 1;
+    int t = 0;
+    while (t < n) {
+      const int a = pp_next_set(hot, t, n);
+      if (a >= n) break;
+      const int b = pp_next_clear(hot, a + 1, n);
+      if (a + need_sp >= b) { t = b; continue; }          // the run ends before speech is confirmed
+      int cur = b, e;
+      while (true) {
+        if (cur >= n) { e = n; break; }
+        const int c = pp_next_set(hot, cur + 1, n);
+        const int lim = cur + need_si;
+        if (lim < c && lim < n) { e = lim; break; }        // silence confirmed at frame lim
+        if (c >= n) { e = n; break; }                      // the stream ends inside possible silence
+        cur = pp_next_clear(hot, c + 1, n);
+      }
+      push(a, e);
+      t = e;
+    }
+  }
+  __syncwarp();
+  // ---- passes B-D on the pair list, in place (each pass only ever shrinks the list) ----
+  auto sweep = [&](int grow_left, int grow_left_skip0, int grow_right, int merge_below) {
+    // grow every pair, then fuse pairs that touch/overlap or whose gap is < merge_below
+    int m = 0, pa = 0, pe = 0;
+    for (int k = 0; k < ns; ++k) {
+      int a = pairs[2 * k], e = pairs[2 * k + 1];
+      if (!(grow_left_skip0 && a == 0)) a = a - grow_left < 0 ? 0 : a - grow_left;
+      e = e + grow_right > n ? n : e + grow_right;
+      if (m > 0 && (a <= pe || a - pe < merge_below)) {
+        if (e > pe) pe = e;
+      } else {
+        if (m > 0) {
+          __syncwarp();
+          if (lane == 0) { pairs[2 * (m - 1)] = pa; pairs[2 * (m - 1) + 1] = pe; }
+        }
+        pa = a; pe = e; ++m;
+      }
+    }
+    __syncwarp();
+    if (m > 0 && lane == 0) { pairs[2 * (m - 1)] = pa; pairs[2 * (m - 1) + 1] = pe; }
+    __syncwarp();
+    ns = m;
+  };
+  if (ws > 1) sweep(ws, 1, 0, 0);
+  if (cfg.merge_silence_frame > 0) sweep(0, 0, 0, cfg.merge_silence_frame);
+  if (cfg.extend_speech_frame > 0) sweep(cfg.extend_speech_frame, 0, cfg.extend_speech_frame, 0);
+
+  // ---- pass E + emission: split long segments, write pairs, rasterise the decisions ----
+  int count = 0;
+  int32_t* seg = segments ? segments + s * (int64_t)max_segments * 2 : nullptr;
+  auto emit = [&](int a, int e) {
+    if (e <= a) return;
+    if (lane == 0 && seg && count < max_segments) { seg[2 * count] = a; seg[2 * count + 1] = e; }
+    ++count;
+    for (int t = a + lane; t < e; t += 32) dec[t] = 1;
+  };
+  const int max_sf = cfg.max_speech_frame, half = cfg.max_speech_frame >> 1;
+  for (int k = 0; k < ns; ++k) {
+    const int a0 = pairs[2 * k], e0 = pairs[2 * k + 1];
+    int pos = a0;
+    if (e0 - a0 > max_sf) {
+      while (pos + max_sf < e0) {
+        const int lo = pos + half, hi = pos + max_sf;     // hi < e0
+        if (lo >= hi) break;
+        float best = INFINITY;
+        int arg = 0x7fffffff;
+        for (int j = lo + lane; j < hi; j += 32) {
+          const float v = sp[j];
+          if (v < best) { best = v; arg = j; }            // strided scan keeps the lowest index per lane
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+          if (ov < best || (ov == best && oa < arg)) { best = ov; arg = oa; }
+        }
+        emit(pos, arg);
+        pos = arg + 1;
+      }
+    }
+    emit(pos, e0);
+  }
+  if (lane == 0 && seg_count) seg_count[s] = count;
+  __syncwarp();
+  for (int t = lane; t < n; t += 32) gdec[t] = dec[t];
+}
+
 // ---- Stream-VAD segmenter (FireRedVAD/Inference_FireRed_ONNX.py:307-490) ----
 // state words per stream: 0 head, 1 fill, 2 frame (1-based, last consumed), 3 mode, 4 speech run, 5 silence run,
 // 6 re-arm flag, 7 first frame of the open segment (0 = none), 8 last frame of the latest closed segment
@@ -453,18 +656,31 @@ extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, c
   VADX_REQUIRE(max_segments >= 0 && (max_segments == 0 || d_segments), "vadx_postprocess_frames: segments buffer");
   if (n_streams == 0) return VADX_OK;
   // warp-per-stream kernel when one stream (probs + running sums + decisions) fits in shared memory
-  const int per_warp_floats = (int)round_up(2 * (int64_t)std::max(n_frames, 1) + 1 + (std::max(n_frames, 1) + 3) / 4, 4);
+  const int per_warp_floats = (int)round_up(2 * (int64_t)std::max(n_frames, 1) + 1 + (std::max(n_frames, 1) + 3) / 4 +
+                                               (std::max(n_frames, 1) + 31) / 32 + 1, 4);
   const size_t smem_w = (size_t)per_warp_floats * 4 * kPpWarps;
   if (smem_w <= 200 * 1024) {
     static bool cfg_w = false;
     if (smem_w > 48 * 1024 && !cfg_w) {
       cudaError_t e = cudaFuncSetAttribute(postprocess_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(postprocess_frames_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(postprocess_frames_warp_kernel)");
       cfg_w = true;
     }
-    postprocess_frames_warp_kernel<<<(unsigned)ceil_div(n_streams, kPpWarps), kPpWarps * 32, smem_w, (cudaStream_t)stream>>>(
-        d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
-        per_warp_floats);
+    static int legacy = -1;   // VADX_PP_LEGACY=1: the frame-by-frame kernel (kept as the cross-check of the run-based one)
+    if (legacy < 0) {
+      const char* e = getenv("VADX_PP_LEGACY");
+      legacy = e ? atoi(e) : 0;
+    }
+    if (legacy)
+      postprocess_frames_warp_kernel<<<(unsigned)ceil_div(n_streams, kPpWarps), kPpWarps * 32, smem_w, (cudaStream_t)stream>>>(
+          d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
+          per_warp_floats);
+    else
+      postprocess_frames_runs_kernel<<<(unsigned)ceil_div(n_streams, kPpWarps), kPpWarps * 32, smem_w, (cudaStream_t)stream>>>(
+          d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
+          per_warp_floats);
     return after_launch("vadx_postprocess_frames");
   }
   const int64_t blocks = ceil_div(n_streams, 32);
