@@ -214,3 +214,29 @@ def test_postprocess_frames_run_based_matches_sequential_oracle(cuda, cfg_t):
         assert cnt[s] == len(pairs) and np.array_equal(seg[s, :cnt[s]], pairs), s
         n_seg += len(pairs)
     assert n_seg > S // 4
+
+
+@pytest.mark.parametrize("T,n2,with_res,S", [(98, 20, True, 333), (98, 20, False, 40), (98, 0, True, 149), (57, 20, True, 64),
+                                             (2, 20, True, 32), (131, 0, False, 33)])
+def test_fsmn_memory_whole_chunk_kernel(cuda, T, n2, with_res, S):
+    """The persistent shared-memory kernel (>= 32 streams, 128 channels, no cache): every stream slot of the
+    two-deep ring is reused many times (S >> SM count for the first case)."""
+    l = lib.load()
+    C, n1 = 128, 20
+    g = torch.Generator().manual_seed(T * 7 + n2 + S)
+    p = torch.randn((S, T, C), generator=g)
+    res = torch.randn((S, T, C), generator=g) if with_res else None
+    wl = torch.randn((C, 1, n1), generator=g) * 0.2
+    wr = torch.randn((C, 1, max(n2, 1)), generator=g) * 0.2
+    x = p.permute(0, 2, 1)
+    ref = x + F.conv1d(F.pad(x, (n1 - 1, 0)), wl, groups=C)
+    if n2 > 0:
+        ref = ref + F.conv1d(F.pad(x, (0, n2)), wr, groups=C)[:, :, 1:]
+    ref = ref.permute(0, 2, 1)
+    if with_res:
+        ref = ref + res
+    out = torch.full((S, T, C), float("nan"), device=cuda)
+    d = [t.to(cuda) if t is not None else None for t in (p, wl.reshape(C, n1), wr.reshape(C, -1), res)]
+    lib.check(l.vadx_fsmn_memory_f32(d[0].data_ptr(), C, d[1].data_ptr(), n1, 1, d[2].data_ptr() if n2 else None, n2, 1,
+                                     lib.ptr(d[3]), C, out.data_ptr(), C, S, T, C, None, None, _st()))
+    assert (out.cpu() - ref).abs().max().item() <= 2e-5

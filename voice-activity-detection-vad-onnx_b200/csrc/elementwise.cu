@@ -299,6 +299,14 @@ __global__ void __launch_bounds__(256) fsmn_cache_out_kernel(const float* __rest
 
 }  // namespace vadx
 
+namespace vadx {
+bool memory_bulk_fits(int n_back, int stride_back, int n_ahead, int stride_ahead, int n_frames, int n_channels,
+                      int64_t ldp, int64_t ldr, int64_t ldo, const float* p, const float* res, const float* out,
+                      const float* cache_in, const float* cache_out, size_t* smem_out);
+int memory_bulk_launch(const float* p, const float* wl, const float* wr, int n_ahead, const float* res, float* out,
+                       int64_t n_streams, int n_frames, size_t smem, cudaStream_t st);
+}  // namespace vadx
+
 using namespace vadx;
 
 extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_streams, int64_t n_samples,
@@ -382,6 +390,19 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
     cudaError_t e = cudaFuncSetAttribute(fsmn_memory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_kernel)");
     configured = 200 * 1024;
+  }
+  // whole-chunk shared-memory kernel (memory_bulk.cu) when the stream's tile fits: FireRed's [98][128]
+  {
+    size_t smem_b = 0;
+    static int no_bulk = -1;
+    if (no_bulk < 0) {
+      const char* e = getenv("VADX_MEM_NO_BULK");
+      no_bulk = e ? atoi(e) : 0;
+    }
+    if (!no_bulk && n_streams >= 32 &&
+        memory_bulk_fits(n_back, stride_back, n_ahead, stride_ahead, n_frames, n_channels, ldp, ldr, ldo, d_p, d_residual,
+                         d_out, d_cache_in, d_cache_out, &smem_b))
+      return memory_bulk_launch(d_p, d_wl, d_wr, n_ahead, d_residual, d_out, n_streams, n_frames, smem_b, st);
   }
   // fast path: unit strides, 20(+20) taps
   const bool fast = stride_back == 1 && (n_ahead == 0 || stride_ahead == 1) && n_back == 20 &&
