@@ -262,6 +262,21 @@ int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, int64_t n_s
 int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,
                        const float* d_wsum_inv, int n_out, float* d_y, int64_t ldy, void* stream);
 
+/* next-3 -- real-audio ingest on device: interleaved int16 PCM (1 or 2 channels, any rate) -> mono int16 at
+ * out_rate, bit-identical to the reference loader's pydub chain
+ * `AudioSegment.from_file(p).set_channels(1).set_frame_rate(sr)` (FSMN/Inference_FSMN_VAD_ONNX.py:68), i.e.
+ * audioop.tomono(0.5, 0.5) = floor((l + r) / 2) followed by audioop.ratecv with default weights, whose
+ * sequential recurrence has the closed form  out[k] = floor((prev*d + cur*(b - d)) / b),
+ * n = ceil(k*a/b) + 1, cur = x[n-1], prev = x[n-2] (0 before the start), d = (n-1)*b - k*a,
+ * a/b = in_rate/out_rate in lowest terms.  d_pcm [S][in_stride] int16 (n_channels interleaved),
+ * d_n_in [S] frames per stream (NULL = n_frames_in); d_out [S][out_stride], entries past a stream's
+ * own output count are zero; d_n_out [S] (optional) receives the counts.
+ * vadx_ingest_out_frames: output frames for n_in input frames (what ratecv returns). */
+int64_t vadx_ingest_out_frames(int64_t n_frames_in, int in_rate, int out_rate);
+int vadx_ingest_pcm16(const int16_t* d_pcm, int64_t in_stride, const int64_t* d_n_in, int64_t n_streams,
+                      int64_t n_frames_in, int n_channels, int in_rate, int out_rate, int16_t* d_out,
+                      int64_t out_stride, int64_t* d_n_out, void* stream);
+
 /* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
  * that the float32 running sum rounds exactly like np.cumsum
  * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid

@@ -257,6 +257,21 @@ def gen_audio():
     a = audio_io.load_wav_int16(os.path.join(RL.REF_ROOT, "FireRedVAD", "vad_sample.wav"), 16000)
     np.savez_compressed(os.path.join(GOLD, "vad_sample_16k.npz"), audio=a)
     print("vad_sample_16k.npz:", a.shape, a.dtype, int(np.abs(a).max()))
+    # the raw PCM of the first 1.5 s (48 kHz stereo, interleaved) with the loader's output for it: the
+    # fixture of the on-device ingest (audioop.tomono + audioop.ratecv)
+    import audioop
+    import wave
+    with wave.open(os.path.join(RL.REF_ROOT, "FireRedVAD", "vad_sample.wav"), "rb") as w:
+        ch, width, sr = w.getnchannels(), w.getsampwidth(), w.getframerate()
+        w.setpos(int(0.5 * sr))
+        raw = w.readframes(int(1.5 * sr))
+    assert width == 2
+    mono = audioop.tomono(raw, 2, 0.5, 0.5) if ch == 2 else raw
+    out = {"pcm": np.frombuffer(raw, np.int16), "channels": np.array(ch), "rate": np.array(sr)}
+    for r in (16000, 8000, 22050):
+        out[f"mono_{r}"] = np.frombuffer(audioop.ratecv(mono, 2, 1, sr, r, None)[0], np.int16)
+    np.savez_compressed(os.path.join(GOLD, "vad_sample_pcm_head.npz"), **out)
+    print("vad_sample_pcm_head.npz:", {k: v.shape for k, v in out.items()})
 
 
 # ------------------------------------------------------------------------------ FSMN

@@ -28,6 +28,44 @@ def load_wav_int16(path: str, sample_rate: int = 16000) -> np.ndarray:
     return np.frombuffer(raw, dtype=np.int16).copy()
 
 
+def ingest_pcm16_device(pcm, n_channels: int, in_rate: int, out_rate: int = 16000, n_frames=None, stream=None):
+    """Device twin of the loader's down-mix + resample: `pcm` CUDA int16 [S, n_frames * n_channels]
+    (interleaved; a 1-D tensor is one stream), `n_frames` optional CUDA int64 [S] valid frames per stream.
+    -> (mono CUDA int16 [S, n_out], counts CUDA int64 [S]); bit-identical to audioop.tomono + ratecv."""
+    import torch
+    from . import lib
+    if not (torch.is_tensor(pcm) and pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() in (1, 2)):
+        raise ValueError("ingest_pcm16_device: pcm must be a CUDA int16 tensor [S, n_frames * n_channels]")
+    x = (pcm.reshape(1, -1) if pcm.dim() == 1 else pcm).contiguous()
+    S, width = x.shape
+    if width % n_channels:
+        raise ValueError(f"ingest_pcm16_device: row length {width} is not a multiple of {n_channels} channels")
+    n_in = width // n_channels
+    L = lib.load()
+    n_out = int(L.vadx_ingest_out_frames(n_in, in_rate, out_rate))
+    out = torch.empty((S, n_out), dtype=torch.int16, device=x.device)
+    cnt = torch.empty((S,), dtype=torch.int64, device=x.device)
+    if n_frames is not None and not (n_frames.is_cuda and n_frames.dtype == torch.int64 and n_frames.numel() == S):
+        raise ValueError("ingest_pcm16_device: n_frames must be a CUDA int64 tensor [S]")
+    lib.check(L.vadx_ingest_pcm16(x.data_ptr(), width, lib.ptr(n_frames), S, n_in, n_channels, in_rate, out_rate,
+                                  out.data_ptr(), max(n_out, 0), cnt.data_ptr(), lib.stream_ptr(stream)))
+    return out, cnt
+
+
+def load_wav_int16_device(path: str, sample_rate: int = 16000):
+    """load_wav_int16 with the down-mix and the rate conversion on the GPU: only the raw PCM crosses PCIe.
+    -> CUDA int16 [n]"""
+    import torch
+    with wave.open(path, "rb") as w:
+        ch, width, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n)
+    if width != 2:
+        raise ValueError(f"{path}: {8 * width}-bit PCM is not supported by the device loader (use load_wav_int16)")
+    pcm = torch.frombuffer(bytearray(raw), dtype=torch.int16).cuda()
+    mono, _ = ingest_pcm16_device(pcm, ch, sr, sample_rate)
+    return mono[0]
+
+
 def align_non_overlapping(audio: np.ndarray, chunk_len: int, rng: np.random.RandomState | None = None):
     """FireRed / MarbleNet static-axis chunker (FireRedVAD/Inference_FireRed_ONNX.py:547-559):
     non-overlapping windows, the tail padded with RMS-matched Gaussian noise cast to int16.
