@@ -259,6 +259,11 @@ int vadx_im2col_f3_f32(const float* d_x, float* d_out, int64_t n_blocks, int n_b
 int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, int64_t n_streams, int n_frames, int n_bins, int k,
                       float w1_far, float w1_mix, float b1, const float* d_w2, float b2, float* d_x4, float* d_alpha,
                       void* stream);
+/* near-end-only graph (DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:319-335): as vadx_alpha_x4_f32 with the far
+ * end's power window and spectrum given as the graph's constants d_pow_far [F][t_max][k], d_far_comp [2][F][t_max] */
+int vadx_alpha_x4_const_f32(const float* d_near_ri, const float* d_pow_far, const float* d_far_comp, int t_max,
+                            int64_t n_streams, int n_frames, int n_bins, int k, float w1_far, float w1_mix, float b1,
+                            const float* d_w2, float b2, float* d_x4, float* d_alpha, void* stream);
 int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,
                        const float* d_wsum_inv, int n_out, float* d_y, int64_t ldy, void* stream);
 

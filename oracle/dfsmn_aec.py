@@ -156,28 +156,35 @@ class DfsmnAecOracle:
         return y[:, :nb], y[:, nb:]
 
     @torch.inference_mode()
-    def forward(self, near_i16, far_i16, trace=None):
-        """near/far int16 [L] (one stream) -> vad probabilities [T_A]"""
+    def forward(self, near_i16, far_i16=None, trace=None, far_noise=None):
+        """near/far int16 [L] (one stream) -> vad probabilities [T_A].
+        Near-end-only variant (DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:319-352): far_i16 is None and
+        far_noise = (pow_far [160, max_len, k], far_comp [2, 160, max_len]) -- the two constant white-noise
+        buffers the wrapper draws at construction (:309-310) stand in for the far end's power and spectrum."""
         cfg, w = self.cfg, self.w
         near = torch.as_tensor(near_i16).view(1, 1, -1).float() * float(1.0 / 32768.0)
-        far = torch.as_tensor(far_i16).view(1, 1, -1).float() * float(1.0 / 32768.0)
         near = near - near.mean()
-        far = far - far.mean()
         nre, nim = self._stft_ri(near, self.kernel_b, cfg.hop_b)
-        fre, fim = self._stft_ri(far, self.kernel_b, cfg.hop_b)
         mix = torch.cat([nre, nim], 0).unsqueeze(0)                    # [1,2,160,T]
-        farc = torch.cat([fre, fim], 0).unsqueeze(0)
         k = cfg.alpha_k
         T = mix.shape[-1]
         idx = torch.arange(T).unsqueeze(1) + torch.arange(k).unsqueeze(0)
         pad = torch.zeros(1, 2, cfg.n_bins_b, k - 1)
         pm = (torch.cat([pad, mix], -1)[..., idx] ** 2).sum(1, keepdim=True)
-        pf = (torch.cat([pad, farc], -1)[..., idx] ** 2).sum(1, keepdim=True)
+        if far_i16 is None:
+            pf = torch.as_tensor(far_noise[0]).float()[:, :T].view(1, 1, cfg.n_bins_b, T, k)
+            farc = torch.as_tensor(far_noise[1]).float()[..., :T].view(1, 1, 2, cfg.n_bins_b, T)
+        else:
+            far = torch.as_tensor(far_i16).view(1, 1, -1).float() * float(1.0 / 32768.0)
+            far = far - far.mean()
+            fre, fim = self._stft_ri(far, self.kernel_b, cfg.hop_b)
+            farc = torch.cat([fre, fim], 0).unsqueeze(0)
+            pf = (torch.cat([pad, farc], -1)[..., idx] ** 2).sum(1, keepdim=True)
         ci = torch.stack([pf, pm], -1).unsqueeze(1)
         a = F.linear(ci.sum(2, keepdim=True), w["alpha.linear1.weight"], w["alpha.linear1.bias"]).squeeze(-1)
         a = F.linear(a, w["alpha.linear2.weight"], w["alpha.linear2.bias"]).squeeze(-1)
         farc = farc * torch.abs(a)
-        x = torch.cat([mix, farc.squeeze(1)], 1)
+        x = torch.cat([mix, farc.squeeze(1) if farc.dim() == 5 else farc], 1)
         if trace is not None:
             trace.update(x4=x, alpha=a)
         aec, n = self.iccrn(x, trace)

@@ -574,11 +574,12 @@ def gen_silero_iterator():
 
 
 # ------------------------------------------------------------------------------ DFSMN AEC-VAD
-def dfsmn_aec_reference(cfg, weights):
-    """The reference's own DFSMN_VAD wrapper around its own NET / AlphaPredictor / UniDeepFsmn modules."""
+def dfsmn_aec_reference(cfg, weights, variant="near_and_far_end_audio"):
+    """The reference's own DFSMN_VAD wrapper around its own NET / AlphaPredictor / UniDeepFsmn modules
+    (variant = the DFSMN sub-directory: near_and_far_end_audio or only_near_end_audio)."""
     import importlib.util
     import types
-    stft = RL.import_file("DFSMN/near_and_far_end_audio/STFT_Process.py", "STFT_Process")
+    stft = RL.import_file(f"DFSMN/{variant}/STFT_Process.py", "STFT_Process")
     pkg = types.ModuleType("dfsmn_ref_pkg")
     pkg.__path__ = []
     sys.modules["dfsmn_ref_pkg"] = pkg
@@ -593,11 +594,11 @@ def dfsmn_aec_reference(cfg, weights):
     sys.modules["dfsmn_ref_pkg.layer_base"] = lb
     spec = importlib.util.spec_from_file_location(
         "dfsmn_ref_pkg.uni_deep_fsmn",
-        os.path.join(RL.REF_ROOT, "DFSMN/near_and_far_end_audio/modeling_modified/uni_deep_fsmn.py"))
+        os.path.join(RL.REF_ROOT, f"DFSMN/{variant}/modeling_modified/uni_deep_fsmn.py"))
     udf = importlib.util.module_from_spec(spec)
     sys.modules[spec.name] = udf
     spec.loader.exec_module(udf)
-    ns = RL.extract("DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py", {"STFT_Process": stft.STFT_Process})
+    ns = RL.extract(f"DFSMN/{variant}/Export_DFSMN_VAD.py", {"STFT_Process": stft.STFT_Process})
     tw = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
     net = ns["NET"](max_frames=cfg.max_frames)
     missing, unexpected = net.load_state_dict({k[6:]: v for k, v in tw.items() if k.startswith("iccrn.")}, strict=False)
@@ -655,7 +656,37 @@ def gen_dfsmn_aec():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_aec.npz"), **out)
 
 
-GENERATORS = {"firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+def gen_dfsmn_near():
+    """Near-end-only variant (DFSMN/only_near_end_audio): the wrapper's two white-noise buffers are drawn under
+    a fixed seed and frozen with the probabilities -- they are constants of the exported graph."""
+    import vadx  # noqa: F401
+    from vadx import synth, weights as W
+    cfg = W.DfsmnAecConfig()
+    w = W.dfsmn_aec_random_init(cfg, 0)
+    torch.manual_seed(77)
+    wrap, _ = dfsmn_aec_reference(cfg, w, variant="only_near_end_audio")
+    L = 31841
+    near = synth.synth_streams(2, L, seed=43)
+    # the wrapper draws its two constant noise buffers with torch.randn at construction (:309-310); replace them
+    # by buffers of the same shape / dtype / distribution from a numpy seed, so tests can rebuild them without a
+    # megabyte fixture (vadx.weights.dfsmn_near_noise)
+    pow_far, far_comp = W.dfsmn_near_noise(cfg, seed=77)
+    assert wrap.pow_far_white_noise.shape[2:] == pow_far.shape and wrap.far_comp_white_noise.shape[2:] == far_comp.shape
+    wrap.pow_far_white_noise = torch.from_numpy(pow_far).view(wrap.pow_far_white_noise.shape)
+    wrap.far_comp_white_noise = torch.from_numpy(far_comp).view(wrap.far_comp_white_noise.shape)
+    out = {"near": near, "pow_far_head": pow_far[:2, :3].astype(np.float32), "far_comp_head": far_comp[:, :2, :3].astype(np.float32)}
+    # the wrapper's forward only runs under tracing (it calls .unsqueeze on a shape element, :322), which is
+    # how the reference itself executes it (torch.onnx.export): trace it, then run the traced module
+    with torch.no_grad():
+        traced = torch.jit.trace(wrap, (torch.from_numpy(near[0]).view(1, 1, -1),), check_trace=False)
+        for s in range(2):
+            p = traced(torch.from_numpy(near[s]).view(1, 1, -1))
+            out[f"probs{s}"] = p.numpy()
+            print(f"near-only stream {s}: probs", p.shape, float(p.min()), float(p.max()))
+    np.savez_compressed(os.path.join(GOLD, "dfsmn_near.npz"), **out)
+
+
+GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 

@@ -137,3 +137,29 @@ def test_stream_loop_and_hysteresis(cuda, wts):
         silence = (not pr[i] >= 0.5) if silence else (pr[i] <= 0.5)
         flags.append(silence)
     assert np.array_equal(r.saved, np.array(flags))
+
+
+def test_near_end_only_variant(cuda, golden_dir, wts):
+    """DFSMN/only_near_end_audio: one input, the far end replaced by the graph's constant noise buffers."""
+    g = np.load(os.path.join(golden_dir, "dfsmn_near.npz"))
+    cfg = W.DfsmnAecConfig()
+    sess = vadx.DfsmnAecSession(wts, cfg, chunk_len=31841, far_noise=W.dfsmn_near_noise(cfg, seed=77))
+    assert [i.name for i in sess.get_inputs()] == ["audio"]
+    near = torch.from_numpy(g["near"]).to(cuda)
+    p = sess.run_batch(near).cpu().numpy()
+    assert p.shape == (2, 100)
+    for s in range(2):
+        err = np.abs(p[s] - g[f"probs{s}"]).max()
+        print(f"near-only stream {s}: max abs prob err {err:.2e}")
+        assert err <= TOL
+    out = sess.run(["vad_results"], {"audio": g["near"][:1, None, :]})[0]
+    assert out.shape == (100,) and np.abs(out - g["probs0"]).max() <= TOL
+    with pytest.raises(ValueError):
+        sess.run(None, {"near_end_audio": g["near"][:1, None, :], "far_end_audio": g["near"][:1, None, :]})
+    with pytest.raises(ValueError):
+        sess.run_batch(near, near)
+    with pytest.raises(ValueError):
+        vadx.DfsmnAecSession(wts, cfg, chunk_len=31841, far_noise=(np.zeros((3, 3, 3)), np.zeros((2, 3, 3))))
+    # the whole single-recording script loop (overlapping windows, hysteresis, timestamps) runs
+    r = dfsmn_aec.run_vad(g["near"][0], None, sess, rng=np.random.RandomState(1))
+    assert len(r.saved) > 0

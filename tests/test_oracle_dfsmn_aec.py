@@ -34,3 +34,15 @@ def test_whole_graph_matches_reference_wrapper(gold, oracle):
     assert p.shape == (100,)
     assert np.abs(p - gold["probs0"]).max() <= 1e-4
     assert gold["probs0"].max() - gold["probs0"].min() > 0.3
+
+
+def test_near_end_only_variant_matches_reference_wrapper(golden_dir, oracle):
+    """DFSMN/only_near_end_audio: the far end replaced by the graph's constant noise buffers (seeded, rebuilt here)."""
+    g = np.load(os.path.join(golden_dir, "dfsmn_near.npz"))
+    cfg = W.DfsmnAecConfig()
+    pow_far, far_comp = W.dfsmn_near_noise(cfg, seed=77)
+    assert np.array_equal(pow_far[:2, :3].astype(np.float32), g["pow_far_head"])
+    assert np.array_equal(far_comp[:, :2, :3].astype(np.float32), g["far_comp_head"])
+    p = oracle.forward(g["near"][0], None, far_noise=(pow_far, far_comp)).numpy()
+    assert p.shape == (100,)
+    assert np.abs(p - g["probs0"]).max() <= 1e-4

@@ -302,6 +302,40 @@ __global__ void __launch_bounds__(256) alpha_x4_kernel(const float* __restrict__
   }
 }
 
+// Near-end-only variant (DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:319-335): the far end's k-frame power
+// window and its spectrum are constants of the graph, pow_far [F][Tmax][k] and far_comp [2][F][Tmax].
+__global__ void __launch_bounds__(256) alpha_x4_const_kernel(const float* __restrict__ near_ri,
+                                                             const float* __restrict__ pow_far,
+                                                             const float* __restrict__ far_comp, int t_max,
+                                                             int64_t n_streams, int T, int F, int k, float w1_far,
+                                                             float w1_mix, float b1, const float* __restrict__ w2, float b2,
+                                                             float* __restrict__ x4, float* __restrict__ alpha_out) {
+  const int64_t total = n_streams * T * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const int64_t st = i / F;
+    const int t = (int)(st % T);
+    float acc = b2;
+    for (int j = 0; j < k; ++j) {
+      const int tt = t - (k - 1) + j;
+      float pm = 0.f;
+      if (tt >= 0) {
+        const int64_t row = st - t + tt;
+        const float nr = near_ri[row * 2 * F + 2 * f], ni = near_ri[row * 2 * F + 2 * f + 1];
+        pm = nr * nr + ni * ni;
+      }
+      const float pf = pow_far[((int64_t)f * t_max + t) * k + j];
+      acc = fmaf(w2[j], fmaf(w1_far, pf, fmaf(w1_mix, pm, b1)), acc);
+    }
+    const float aa = fabsf(acc);
+    x4[i * 4 + 0] = near_ri[st * 2 * F + 2 * f];
+    x4[i * 4 + 1] = near_ri[st * 2 * F + 2 * f + 1];
+    x4[i * 4 + 2] = far_comp[(int64_t)f * t_max + t] * aa;
+    x4[i * 4 + 3] = far_comp[((int64_t)F + f) * t_max + t] * aa;
+    if (alpha_out) alpha_out[i] = acc;
+  }
+}
+
 // ISTFT overlap-add (NET.istft :226-230): frames [S*T][ld] (n_fft valid) -> y[s][i] = window_sum_inv[i + half] *
 // sum_t frames[t][i + half - t*hop]
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, int64_t ld, int64_t n_streams,
@@ -426,6 +460,20 @@ extern "C" int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, 
   alpha_x4_kernel<<<g1(n_streams * n_frames * n_bins), 256, 0, (cudaStream_t)stream>>>(
       d_near_ri, d_far_ri, n_streams, n_frames, n_bins, k, w1_far, w1_mix, b1, d_w2, b2, d_x4, d_alpha);
   return after_launch("vadx_alpha_x4_f32");
+}
+
+extern "C" int vadx_alpha_x4_const_f32(const float* d_near_ri, const float* d_pow_far, const float* d_far_comp,
+                                       int t_max, int64_t n_streams, int n_frames, int n_bins, int k, float w1_far,
+                                       float w1_mix, float b1, const float* d_w2, float b2, float* d_x4, float* d_alpha,
+                                       void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_near_ri && d_pow_far && d_far_comp && d_w2 && d_x4 && n_streams >= 0 && n_frames >= 1 && n_bins >= 1 &&
+                   k >= 1 && t_max >= n_frames,
+               "vadx_alpha_x4_const_f32: bad argument (t_max %d must cover n_frames %d)", t_max, n_frames);
+  if (n_streams == 0) return VADX_OK;
+  alpha_x4_const_kernel<<<g1(n_streams * n_frames * n_bins), 256, 0, (cudaStream_t)stream>>>(
+      d_near_ri, d_pow_far, d_far_comp, t_max, n_streams, n_frames, n_bins, k, w1_far, w1_mix, b1, d_w2, b2, d_x4, d_alpha);
+  return after_launch("vadx_alpha_x4_const_f32");
 }
 
 extern "C" int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,

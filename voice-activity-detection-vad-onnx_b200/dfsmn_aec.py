@@ -40,7 +40,10 @@ class DfsmnAecSession:
     int16 (1,1,L) -> vad_results fp32 (T,), T = L // 320 + 1 (100 for L = 31841)."""
 
     def __init__(self, weights: dict, cfg: W.DfsmnAecConfig = W.DfsmnAecConfig(), chunk_len: int = 31841,
-                 tensor_cores: bool = True):
+                 tensor_cores: bool = True, far_noise=None):
+        """far_noise = (pow_far [F, max_frames, k], far_comp [2, F, max_frames]) selects the near-end-only graph
+        (DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:291-352): one input `audio`, the far end replaced by those
+        two constant buffers (see weights.dfsmn_near_noise)."""
         import torch
         self._torch = torch
         self._l = lib.load()
@@ -66,8 +69,18 @@ class DfsmnAecSession:
         self.tc_everywhere = False
         self._c = {}
         self._build_constants({k: _t(v) for k, v in weights.items()})
-        self._inputs_meta = [NodeArg("near_end_audio", [1, 1, self.chunk_len], "tensor(int16)"),
-                             NodeArg("far_end_audio", [1, 1, self.chunk_len], "tensor(int16)")]
+        self.near_only = far_noise is not None
+        if self.near_only:
+            pf, fc = (np.ascontiguousarray(np.asarray(a, np.float32)) for a in far_noise)
+            want_pf, want_fc = (cfg.n_bins_b, cfg.max_frames, cfg.alpha_k), (2, cfg.n_bins_b, cfg.max_frames)
+            if pf.shape != want_pf or fc.shape != want_fc:
+                raise ValueError(f"DfsmnAecSession: far_noise shapes {pf.shape}, {fc.shape}; expected {want_pf}, {want_fc}")
+            self._c["far.pow"] = torch.from_numpy(pf).to(self.dev)
+            self._c["far.comp"] = torch.from_numpy(fc).to(self.dev)
+            self._inputs_meta = [NodeArg("audio", [1, 1, self.chunk_len], "tensor(int16)")]
+        else:
+            self._inputs_meta = [NodeArg("near_end_audio", [1, 1, self.chunk_len], "tensor(int16)"),
+                                 NodeArg("far_end_audio", [1, 1, self.chunk_len], "tensor(int16)")]
         self._outputs_meta = [NodeArg("vad_results", [self.T], "tensor(float)")]
 
     # ------------------------------------------------------------------ constants
@@ -254,7 +267,7 @@ class DfsmnAecSession:
         half = cfg.n_fft_b // 2
         Lp = (half + L + half + cfg.n_fft_b + 3) // 4 * 4
         ri = []
-        for a in (near, far):
+        for a in ((near,) if self.near_only else (near, far)):
             sig = self._new(S, Lp)
             lib.check(l.vadx_prep_audio(a.data_ptr(), lib.DT_I16, S, L, L, 1.0 / 32768.0, 1, 0, 0.0, half, sig.data_ptr(),
                                         Lp, self._s()))
@@ -264,8 +277,13 @@ class DfsmnAecSession:
             ri.append(o)
         x4 = self._new(R, 4)
         w1f, w1m, b1, b2 = self.alpha
-        lib.check(l.vadx_alpha_x4_f32(ri[0].data_ptr(), ri[1].data_ptr(), S, T, F, cfg.alpha_k, w1f, w1m, b1,
-                                      self._c["alpha.w2"].data_ptr(), b2, x4.data_ptr(), None, self._s()))
+        if self.near_only:
+            lib.check(l.vadx_alpha_x4_const_f32(ri[0].data_ptr(), self._c["far.pow"].data_ptr(), self._c["far.comp"].data_ptr(),
+                                                cfg.max_frames, S, T, F, cfg.alpha_k, w1f, w1m, b1,
+                                                self._c["alpha.w2"].data_ptr(), b2, x4.data_ptr(), None, self._s()))
+        else:
+            lib.check(l.vadx_alpha_x4_f32(ri[0].data_ptr(), ri[1].data_ptr(), S, T, F, cfg.alpha_k, w1f, w1m, b1,
+                                          self._c["alpha.w2"].data_ptr(), b2, x4.data_ptr(), None, self._s()))
         if x4_override is not None:
             x4 = x4_override
         h = self._bilstm_rows("in_lstm", x4, B, F, 4, c)                                           # [R][2c]
@@ -303,13 +321,15 @@ class DfsmnAecSession:
         return aec
 
     # ------------------------------------------------------------------ whole graph
-    def run_batch(self, near, far, trace=None):
-        """near, far: CUDA int16 [S, L] -> probabilities CUDA fp32 [S, T]"""
+    def run_batch(self, near, far=None, trace=None):
+        """near, far: CUDA int16 [S, L] -> probabilities CUDA fp32 [S, T] (far is None for the near-end-only graph)"""
         torch, cfg, l = self._torch, self.cfg, self._l
-        for a in (near, far):
+        if self.near_only != (far is None):
+            raise ValueError("run_batch: the near-end-only graph takes one input, the near+far graph two")
+        for a in ((near,) if far is None else (near, far)):
             if not (torch.is_tensor(a) and a.is_cuda and a.dtype == torch.int16 and a.dim() == 2 and a.is_contiguous()):
                 raise ValueError("run_batch: near/far must be contiguous CUDA int16 tensors [S, L]")
-        if near.shape != far.shape or near.shape[1] != self.chunk_len:
+        if (far is not None and near.shape != far.shape) or near.shape[1] != self.chunk_len:
             raise ValueError(f"InvalidArgument: inputs must both have shape [S, {self.chunk_len}]")
         S, L = near.shape
         aec = self.echo_estimate(near, far, trace)
@@ -366,15 +386,16 @@ class DfsmnAecSession:
         torch = self._torch
         if output_names is not None and any(n != "vad_results" for n in output_names):
             raise ValueError(f"InvalidArgument: unknown output name in {output_names}")
-        if set(input_feed) != {"near_end_audio", "far_end_audio"}:
-            raise ValueError(f"InvalidArgument: inputs must be near_end_audio and far_end_audio, got {sorted(input_feed)}")
+        names = [i.name for i in self._inputs_meta]
+        if set(input_feed) != set(names):
+            raise ValueError(f"InvalidArgument: inputs must be {' and '.join(names)}, got {sorted(input_feed)}")
         arrs = []
-        for k in ("near_end_audio", "far_end_audio"):
+        for k in names:
             a = input_feed[k]
             if not isinstance(a, np.ndarray) or a.dtype != np.int16 or a.shape != (1, 1, self.chunk_len):
                 raise ValueError(f"InvalidArgument: '{k}' must be int16 of shape (1, 1, {self.chunk_len})")
             arrs.append(torch.from_numpy(np.ascontiguousarray(a[0])).cuda())
-        return [self.run_batch(arrs[0], arrs[1])[0].cpu().numpy()]
+        return [self.run_batch(arrs[0], arrs[1] if len(arrs) > 1 else None)[0].cpu().numpy()]
 
 
 @dataclass
@@ -398,7 +419,8 @@ def run_streams(session: DfsmnAecSession, near_aligned, far_aligned, stride: int
     trace = []
     for wdx in range(n_windows):
         s0 = wdx * stride
-        probs = session.run_batch(near_aligned[:, s0:s0 + L].contiguous(), far_aligned[:, s0:s0 + L].contiguous())
+        probs = session.run_batch(near_aligned[:, s0:s0 + L].contiguous(),
+                                  None if far_aligned is None else far_aligned[:, s0:s0 + L].contiguous())
         PP.lookahead_hysteresis(probs, state, lb, speaking_score, silence_score, is_final=(wdx == n_windows - 1))
         if keep_trace:
             trace.append(probs)
@@ -409,20 +431,25 @@ def run_vad(near, far, session: DfsmnAecSession, look_backward_s: float = LOOK_B
             save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None,
             keep_trace: bool = False) -> AecVadResult:
     """One near/far pair like the reference script (:124-163,229-298): truncate to the common length,
-    peak-normalise each, overlapping windows with RMS-noise tail padding, hysteresis, timestamps."""
+    peak-normalise each, overlapping windows with RMS-noise tail padding, hysteresis, timestamps.
+    far=None with a near-end-only session follows DFSMN/only_near_end_audio/Inference_DFSMN_VAD_ONNX.py
+    (:120-145,210-214): the same loop over one recording."""
     import torch
     if isinstance(near, str):
         near = audio_io.load_wav_int16(near, SAMPLE_RATE)
     if isinstance(far, str):
         far = audio_io.load_wav_int16(far, SAMPLE_RATE)
-    n = min(len(near), len(far))
+    n = len(near) if far is None else min(len(near), len(far))
     near16 = audio_io.normalize_to_int16(np.asarray(near[:n], np.float32))
-    far16 = audio_io.normalize_to_int16(np.asarray(far[:n], np.float32))
     lb = int(look_backward_s * SAMPLE_RATE // OUTPUT_FRAME_LENGTH)
     na, stride, _ = audio_io.align_overlapping(near16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
-    fa, _, _ = audio_io.align_overlapping(far16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
-    state, trace = run_streams(session, torch.from_numpy(na).cuda().unsqueeze(0), torch.from_numpy(fa).cuda().unsqueeze(0),
-                               stride, look_backward_s, keep_trace=keep_trace)
+    d_far = None
+    if far is not None:
+        far16 = audio_io.normalize_to_int16(np.asarray(far[:n], np.float32))
+        fa, _, _ = audio_io.align_overlapping(far16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
+        d_far = torch.from_numpy(fa).cuda().unsqueeze(0)
+    state, trace = run_streams(session, torch.from_numpy(na).cuda().unsqueeze(0), d_far, stride, look_backward_s,
+                               keep_trace=keep_trace)
     cnt, seg = state.segments()
     n_flags = int(state.n_saved[0].item())
     pairs = seg[0, :int(cnt[0].item())].cpu().numpy()

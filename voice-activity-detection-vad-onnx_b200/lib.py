@@ -76,6 +76,8 @@ SIGNATURES = {
     "vadx_ceps_cmul_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "vadx_im2col_f3_f32": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "vadx_alpha_x4_f32": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _f32, _vp, _vp, _vp]),
+    "vadx_alpha_x4_const_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _f32, _vp, _vp,
+                                          _vp]),
     "vadx_istft_ola_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
     "vadx_ingest_out_frames": (C.c_int64, [_i64, _i32, _i32]),

@@ -536,3 +536,14 @@ def dfsmn_aec_random_init(cfg: DfsmnAecConfig = DfsmnAecConfig(), seed: int = 0)
     w["mask.linear3.weight"] = (w["mask.linear3.weight"] * 2.0).astype(np.float32)
     w["mask.linear3.bias"] = (w["mask.linear3.bias"] - 1.1).astype(np.float32)
     return w
+
+
+def dfsmn_near_noise(cfg: DfsmnAecConfig = DfsmnAecConfig(), seed: int = 77):
+    """The two constant white-noise buffers of the near-end-only DFSMN graph
+    (DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:309-310): pow_far = randn(n_bins, max_frames, k).half() ** 2 and
+    far_comp = randn(2, n_bins, max_frames).half().  The reference draws them unseeded at export time, so they are
+    model constants like the weights; here they come from a numpy seed.  -> (float16 [F, max_len, k], float16 [2, F, max_len])"""
+    rs = np.random.RandomState(seed)
+    a = rs.standard_normal((cfg.n_bins_b, cfg.max_frames, cfg.alpha_k)).astype(np.float16)
+    b = rs.standard_normal((2, cfg.n_bins_b, cfg.max_frames)).astype(np.float16)
+    return (a * a).astype(np.float16), b
