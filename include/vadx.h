@@ -282,6 +282,15 @@ int vadx_ingest_pcm16(const int16_t* d_pcm, int64_t in_stride, const int64_t* d_
                       int64_t n_frames_in, int n_channels, int in_rate, int out_rate, int16_t* d_out,
                       int64_t out_stride, int64_t* d_n_out, void* stream);
 
+/* next-3 -- the in-graph resampler of the FireRed / MarbleNet wrappers for IN_SAMPLE_RATE != 16000
+ * (FireRedVAD/Export_FireRedVAD.py:431-449): F.interpolate(x, scale_factor, mode='linear', align_corners=False),
+ * out[i] = (1-w)*x[i0] + w*x[min(i0+1, n_in-1)], src = max(0, (float)(1/scale)*(i+0.5) - 0.5), i0 = floor(src),
+ * w = src - i0, n_out = floor(n_in * scale).  d_in [S][in_stride] -> d_out [S][out_stride], written at column
+ * out_offset (room for the STFT's centre pad); vadx_resample_out_len returns n_out. */
+int64_t vadx_resample_out_len(int64_t n_in, double scale);
+int vadx_resample_linear_f32(const float* d_in, int64_t in_stride, int64_t n_in, int64_t n_streams, double scale,
+                             float* d_out, int64_t out_stride, int64_t out_offset, void* stream);
+
 /* a15 -- FireRed / MarbleNet VadPostprocessor on device, one stream per lane, sequential in time so
  * that the float32 running sum rounds exactly like np.cumsum
  * (FireRedVAD/Inference_FireRed_ONNX.py:181-304).  d_probs [S][ld_probs]; d_n_frames [S] valid
@@ -366,6 +375,8 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
  *            Stream-VAD twin (N2 = 0): state = {caches_in, caches_out}, each fp32
  *            [R][S][P][(N1-1)*S1], distinct buffers (the reference's (R,1,P,Lb),
  *            FireRedVAD/Export_FireRedVAD.py:863-876, Inference_FireRed_ONNX.py:758-803).
+ *            Scalar "frontend.in_sample_rate" (default 16000) selects the wrapper's in-graph linear
+ *            resampler (Export_FireRedVAD.py:389-393,431-449); T then follows the resampled length.
  *   fsmn:    inputs  = {audio int16 [S][L], noise_average_dB fp32 [S]}
  *            outputs = {score uint8 [S][T], noisy_dB fp32 [S], P(silence) fp32 [S][T] or NULL,
  *                       power_dB fp32 [S][T] or NULL}

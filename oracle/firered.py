@@ -26,8 +26,10 @@ def _t(a):
 
 
 class FireRedOracle:
-    def __init__(self, weights: dict, cfg):
+    def __init__(self, weights: dict, cfg, in_sample_rate: int = 16000):
         self.cfg = cfg
+        # in-graph resampler of the wrapper (:389-393): down before the pre-emphasis, up after it
+        self.rate_scale = 1.0 / (in_sample_rate / 16000.0)
         self.w = {k: _t(np.asarray(v, np.float32)) for k, v in weights.items()}
         self.kernel = fe.stft_kernel(cfg.n_fft, cfg.win_length, cfg.window, "v2")
         self.bank = _t(fe.kaldi_like_bank(cfg.n_fft, cfg.n_mels, 16000)).unsqueeze(-1)
@@ -37,7 +39,11 @@ class FireRedOracle:
     def logmel(self, audio_i16: torch.Tensor) -> torch.Tensor:
         """[N,1,L] int16 -> [N,n_mels,T] log-mel."""
         x = audio_i16.float()
+        if self.rate_scale < 1.0:
+            x = F.interpolate(x, scale_factor=self.rate_scale, mode="linear", align_corners=False)
         x = F.conv1d(F.pad(x, (1, 0)), self.pre)
+        if self.rate_scale > 1.0:
+            x = F.interpolate(x, scale_factor=self.rate_scale, mode="linear", align_corners=False)
         p = fe.stft_power(x, self.kernel, self.cfg.hop, center_pad=False)
         m = F.conv1d(p, self.bank)
         return torch.clamp(m, min=self.cfg.log_floor).log()

@@ -27,7 +27,7 @@ def _sd_from_numpy(w):
 
 
 # ------------------------------------------------------------------------------ FireRed
-def firered_reference(cfg, weights, streaming=False):
+def firered_reference(cfg, weights, streaming=False, in_sample_rate=16000):
     stft = RL.import_file("FireRedVAD/STFT_Process.py", "STFT_Process")
     ns = RL.extract("FireRedVAD/Export_FireRedVAD.py", {"STFT_Process": stft.STFT_Process})
     args = RL.Args(idim=cfg.idim, R=cfg.R, M=cfg.M, H=cfg.H, P=cfg.P, N1=cfg.N1, S1=cfg.S1,
@@ -40,7 +40,7 @@ def firered_reference(cfg, weights, streaming=False):
     dm = ns["DetectModel"](args).eval()
     dm.load_state_dict(_sd_from_numpy(weights), strict=True)
     return ns["FireRedVAD_ONNX"](dm, cfg.n_fft, cfg.hop, cfg.win_length, cfg.n_mels, 16000,
-                                 cfg.pre_emphasis, cfg.window).eval(), ns
+                                 cfg.pre_emphasis, cfg.window, in_sample_rate).eval(), ns
 
 
 def gen_firered():
@@ -93,6 +93,23 @@ def gen_firered():
     out["stream_caches_last"] = caches.numpy()[:, 0, ::16, :]
     np.savez_compressed(os.path.join(GOLD, "firered.npz"), **out)
     print("firered.npz:", {k: v.shape for k, v in out.items()})
+
+
+def gen_firered_rates():
+    """IN_SAMPLE_RATE != 16000: the wrapper's in-graph linear resampler (Export_FireRedVAD.py:389-393,431-449)
+    for a lower, a higher and a non-integer-ratio input rate."""
+    import vadx  # noqa: F401
+    from vadx import synth, weights as W
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, seed=0)
+    out = {}
+    for rate in (8000, 48000, 22050):
+        ref, _ = firered_reference(cfg, w, in_sample_rate=rate)
+        a = synth.synth_streams(2, rate, seed=rate)          # one second at the input rate
+        with torch.inference_mode():
+            out[f"r{rate}_probs"] = np.stack([ref(torch.from_numpy(c).view(1, 1, -1)).numpy()[0] for c in a])
+        print(rate, out[f"r{rate}_probs"].shape)
+    np.savez_compressed(os.path.join(GOLD, "firered_rates.npz"), **out)
 
 
 # ------------------------------------------------------------------------------ FireRed: whole script
@@ -686,7 +703,7 @@ def gen_dfsmn_near():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_near.npz"), **out)
 
 
-GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 

@@ -136,3 +136,37 @@ def test_many_streams_timestamps(cuda, default_session):
         assert ts == ref_ts
         n_speech += len(ts)
     assert n_speech > 0
+
+
+@pytest.mark.parametrize("rate", [8000, 48000, 22050])
+def test_in_graph_resampler(cuda, golden_dir, rate):
+    """IN_SAMPLE_RATE != 16000: the wrapper's linear resampler around the pre-emphasis
+    (FireRedVAD/Export_FireRedVAD.py:389-393,431-449), golden from the reference wrapper built with that rate."""
+    g = np.load(os.path.join(golden_dir, "firered_rates.npz"))
+    cfg = W.FireRedConfig()
+    sess = vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=rate, in_sample_rate=rate)
+    a = synth.synth_streams(2, rate, seed=rate)
+    p = sess.run([sess.get_outputs()[0].name], {"audio": a[:, None, :]})[0]
+    assert p.shape == g[f"r{rate}_probs"].shape == (2, 1, 98)
+    err = np.abs(p - g[f"r{rate}_probs"]).max()
+    print(f"in_sample_rate {rate}: max abs err {err:.2e}")
+    assert err <= TOL
+    big = torch.from_numpy(synth.synth_streams(40, rate, seed=3)).to(cuda)     # tensor-core layers after the fp32 frontend
+    ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg, in_sample_rate=rate).forward(big.cpu().numpy()).numpy()
+    assert np.abs(sess.run_batch(big).cpu().numpy() - ref).max() <= TOL
+
+
+def test_resample_linear_kernel_matches_torch(cuda):
+    from vadx import lib
+    L = lib.load()
+    g = torch.Generator().manual_seed(0)
+    for n_in, scale in ((1000, 0.5), (1000, 1.0 / 3.0), (777, 16000 / 22050), (500, 2.0), (33, 16000 / 11025), (1, 2.0)):
+        x = torch.randn((3, n_in), generator=g)
+        ref = torch.nn.functional.interpolate(x[:, None, :], scale_factor=scale, mode="linear", align_corners=False)[:, 0]
+        n_out = int(L.vadx_resample_out_len(n_in, scale))
+        assert n_out == ref.shape[1]
+        out = torch.zeros((3, n_out + 5), device=cuda)
+        d = x.to(cuda)
+        lib.check(L.vadx_resample_linear_f32(d.data_ptr(), n_in, n_in, 3, scale, out.data_ptr(), n_out + 5, 2, None))
+        assert (out[:, 2:2 + n_out].cpu() - ref).abs().max().item() <= 1e-6
+        assert out[:, :2].abs().max().item() == 0 and out[:, 2 + n_out:].abs().max().item() == 0

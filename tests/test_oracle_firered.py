@@ -118,3 +118,17 @@ def test_script_stream_section(gold_script, golden_dir):
     assert p.shape == gold_script["stream_probs"].shape
     assert np.abs(p - gold_script["stream_probs"]).max() <= TOL
     assert np.abs(caches.numpy()[:, 0, ::16, :] - gold_script["stream_caches_last"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("rate", [8000, 48000, 22050])
+def test_in_graph_resampler(golden_dir, rate):
+    """IN_SAMPLE_RATE != 16000 (tests/golden/firered_rates.npz: the reference wrapper built with that rate)"""
+    g = np.load(os.path.join(golden_dir, "firered_rates.npz"))
+    cfg = W.FireRedConfig()
+    o = FireRedOracle(W.firered_random_init(cfg, 0), cfg, in_sample_rate=rate)
+    a = synth.synth_streams(2, rate, seed=rate)
+    p = o.forward(a).numpy()
+    assert p.shape == g[f"r{rate}_probs"].shape
+    # 1e-4: an upsampled signal has almost no energy in the upper mel bands, so the log amplifies fp32
+    # summation-order differences between this batch-of-2 call and the reference's batch-1 calls
+    assert np.abs(p - g[f"r{rate}_probs"]).max() <= 1e-4

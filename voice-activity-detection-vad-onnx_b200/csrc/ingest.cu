@@ -51,9 +51,47 @@ __global__ void __launch_bounds__(256) ingest_pcm16_kernel(const int16_t* __rest
   out[s * out_stride + k] = v;
 }
 
+// F.interpolate(mode='linear', align_corners=False) with a given scale_factor (ATen UpSampleLinear1d: the
+// reciprocal scale is formed in double and cast to float, coordinates and weights are float)
+__global__ void __launch_bounds__(256) resample_linear_kernel(const float* __restrict__ in, int64_t in_stride, int64_t n_in,
+                                                              float rscale, float* __restrict__ out, int64_t out_stride,
+                                                              int64_t out_offset, int64_t n_out) {
+  const int64_t s = blockIdx.y;
+  const float* x = in + s * in_stride;
+  float* y = out + s * out_stride + out_offset;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
+    float src = __fsub_rn(__fmul_rn(rscale, __fadd_rn((float)i, 0.5f)), 0.5f);
+    if (src < 0.f) src = 0.f;
+    const int64_t i0 = (int64_t)src;
+    const int64_t i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    const float w1 = __fsub_rn(src, (float)i0), w0 = __fsub_rn(1.0f, w1);
+    y[i] = __fadd_rn(__fmul_rn(w0, __ldg(x + i0)), __fmul_rn(w1, __ldg(x + i1)));
+  }
+}
+
 }  // namespace vadx
 
 using namespace vadx;
+
+extern "C" int64_t vadx_resample_out_len(int64_t n_in, double scale) {
+  if (n_in <= 0 || !(scale > 0.0)) return 0;
+  return (int64_t)floor((double)n_in * scale);
+}
+
+extern "C" int vadx_resample_linear_f32(const float* d_in, int64_t in_stride, int64_t n_in, int64_t n_streams, double scale,
+                                        float* d_out, int64_t out_stride, int64_t out_offset, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_in && d_out && scale > 0.0, "vadx_resample_linear_f32: bad argument");
+  const int64_t n_out = vadx_resample_out_len(n_in, scale);
+  VADX_REQUIRE(n_streams >= 0 && n_streams <= 65535 && n_in >= 1 && in_stride >= n_in && out_offset >= 0 &&
+                   out_stride >= out_offset + n_out,
+               "vadx_resample_linear_f32: bad shape");
+  if (n_streams == 0 || n_out == 0) return VADX_OK;
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(n_out, 256), 4096), (unsigned)n_streams);
+  resample_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, in_stride, n_in, (float)(1.0 / scale), d_out,
+                                                                 out_stride, out_offset, n_out);
+  return after_launch("vadx_resample_linear_f32");
+}
 
 extern "C" int64_t vadx_ingest_out_frames(int64_t n_frames_in, int in_rate, int out_rate) {
   if (n_frames_in <= 0 || in_rate <= 0 || out_rate <= 0) return 0;

@@ -112,10 +112,17 @@ int firered_check(const vadx_model* m) {
   FireRedHP h;
   return firered_hp(m, &h);
 }
+// IN_SAMPLE_RATE != 16000 (Export_FireRedVAD.py:389-393): scale = 1 / (in_rate / 16000), samples after the
+// in-graph linear resampler = floor(L * scale)
+static double firered_rate_scale(const vadx_model* m) {
+  const double in_rate = m->scalar("frontend.in_sample_rate", 16000.0);
+  return in_rate == 16000.0 ? 1.0 : 1.0 / (in_rate / 16000.0);
+}
 int firered_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
   FireRedHP h;
   VADX_TRY(firered_hp(m, &h));
-  *out = h.frames(n_samples);
+  const double sc = firered_rate_scale(m);
+  *out = h.frames(sc == 1.0 ? n_samples : vadx_resample_out_len(n_samples, sc));
   return VADX_OK;
 }
 
@@ -147,13 +154,16 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   }
   const int64_t cache_stream = (int64_t)h.P * (h.N1 - 1) * h.S1;
   const int64_t cache_layer = S_all * cache_stream;
-  const int T = h.frames(L);
-  VADX_REQUIRE(T >= 1, "firered: %lld samples are shorter than one %d-sample frame", (long long)L, h.n_taps());
+  const double rate_scale = firered_rate_scale(m);
+  const int64_t L16 = rate_scale == 1.0 ? L : vadx_resample_out_len(L, rate_scale);   // samples at the model's 16 kHz
+  const int T = h.frames(L16);
+  VADX_REQUIRE(T >= 1, "firered: %lld samples are shorter than one %d-sample frame", (long long)L16, h.n_taps());
   const int64_t slab = firered_slab(m, S_all);
   const int64_t slab_rows = slab * T;
-  const int64_t Lp = round_up(L, 4);
+  const int64_t Lp = round_up(std::max(L, L16), 4);
   Workspace ws(ws_ptr, ws_bytes, dry);
   float* sig = ws.take<float>(slab * Lp);
+  float* sig2 = rate_scale == 1.0 ? nullptr : ws.take<float>(slab * Lp);
   float* power = ws.take<float>(slab_rows * h.ld_power());
   float* feat = ws.take<float>(slab_rows * h.n_mels);
   float* bufH = ws.take<float>(slab_rows * h.H);
@@ -184,7 +194,20 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     float* memB = memB0;
     const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
     const uint8_t* stft_img = use_tc ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
-    if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
+    if (rate_scale != 1.0) {
+      // in-graph resampler: downsample before the pre-emphasis, upsample after it (Export_FireRedVAD.py:431-449)
+      const int pre = preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0;
+      if (rate_scale < 1.0) {
+        VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, 0, 0.f, 0, sig2, Lp, st));
+        VADX_TRY(vadx_resample_linear_f32(sig2, Lp, L, S, rate_scale, sig, Lp, 0, st));
+        VADX_TRY(vadx_prep_audio(sig, VADX_DT_F32, S, L16, Lp, 1.0f, 0, pre, preemph, 0, sig2, Lp, st));
+      } else {
+        VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, pre, preemph, 0, sig, Lp, st));
+        VADX_TRY(vadx_resample_linear_f32(sig, Lp, L, S, rate_scale, sig2, Lp, 0, st));
+      }
+      VADX_TRY(vadx_stft_power_f32(sig2, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                                   nb_used, power, h.ld_power(), st));
+    } else if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
       // int16 audio -> power in one tensor-core kernel (exact sample split, folded pre-emphasis)
       VADX_TRY(vadx_stft_power_tc_i16(d_audio, L, L, S, T, h.hop, h.n_taps(), stft_img, nb_used, power, h.ld_power(), st));
     } else {

@@ -80,6 +80,8 @@ SIGNATURES = {
                                           _vp]),
     "vadx_istft_ola_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "vadx_postprocess_frames": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(PostCfg), _vp, _vp, _vp, _i32, _vp]),
+    "vadx_resample_out_len": (C.c_int64, [_i64, C.c_double]),
+    "vadx_resample_linear_f32": (C.c_int, [_vp, _i64, _i64, _i64, C.c_double, _vp, _i64, _i64, _vp]),
     "vadx_ingest_out_frames": (C.c_int64, [_i64, _i32, _i32]),
     "vadx_ingest_pcm16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "vadx_stream_post_state_words": (C.c_int, [_i32]),

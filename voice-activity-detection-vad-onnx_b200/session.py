@@ -97,10 +97,13 @@ class FireRedSession:
     MAX_STREAMS_PER_CALL = 32768
 
     def __init__(self, weights: dict, cfg: W.FireRedConfig = W.FireRedConfig(), chunk_len: int | None = 16000,
-                 tensor_cores: bool = True):
-        """tensor_cores=False keeps every contraction on the exact-fp32 FFMA kernels (debug / A-B)."""
+                 tensor_cores: bool = True, in_sample_rate: int = 16000):
+        """tensor_cores=False keeps every contraction on the exact-fp32 FFMA kernels (debug / A-B).
+        in_sample_rate != 16000 enables the wrapper's in-graph linear resampler (IN_SAMPLE_RATE,
+        FireRedVAD/Export_FireRedVAD.py:389-393,431-449); chunk_len is then counted at that rate."""
         self.cfg = cfg
         self.chunk_len = chunk_len
+        self.in_sample_rate = int(in_sample_rate)
         hp = [cfg.idim, cfg.R, cfg.M, cfg.H, cfg.P, cfg.N1, cfg.S1, cfg.N2 if not cfg.streaming else 0, cfg.S2,
               cfg.odim, cfg.n_fft, cfg.win_length, cfg.hop, cfg.n_mels]
         self._e = _Engine("firered", hp)
@@ -115,6 +118,7 @@ class FireRedSession:
         self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
         self._e.set_scalar("frontend.log_floor", cfg.log_floor)
         self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
+        self._e.set_scalar("frontend.in_sample_rate", float(self.in_sample_rate))
         spec = W.firered_spec(cfg)
         for name in spec:
             if name not in weights:
@@ -152,7 +156,7 @@ class FireRedSession:
             raise ValueError(f"InvalidArgument: 'audio' must have shape (S, 1, L), got {a.shape}")
         if self.chunk_len and a.shape[2] != self.chunk_len:
             raise ValueError(f"InvalidArgument: 'audio' length {a.shape[2]} != static axis {self.chunk_len}")
-        if a.shape[2] < self.cfg.win_length:
+        if self.frames(a.shape[2]) < 1:
             raise ValueError(f"InvalidArgument: 'audio' length {a.shape[2]} shorter than one frame")
         d = torch.from_numpy(np.ascontiguousarray(a[:, 0, :])).cuda()
         p = self.run_batch(d)
