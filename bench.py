@@ -264,14 +264,14 @@ def family_rtfx(dev, world, dist):
     state = PP.HysteresisState(S, 100, dev)
 
     def aec_step():
-        probs = sess.run_batch(near, far)
+        probs = sess.run_batch_graph(near, far)
         state.n_saved.zero_()
         PP.lookahead_hysteresis(probs, state, 15, 0.5, 0.5, is_final=True)
 
     ms = timed(aec_step, steps=2, warm=2)
     out["dfsmn_aec"] = {"audio_hours_per_sec": world * S * 31841 / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
                         "config": f"{S} near+far stream pairs/GPU x one 31841-sample chunk, echo estimator on fp32 FFMA "
-                                  "kernels, mask-net on tcgen05, hysteresis on device"}
+                                  "kernels, mask-net on tcgen05, whole call replayed as one CUDA graph, hysteresis on device"}
     del sess, near, far
     # FireRed Stream-VAD: 4096 streams in lock-step, 160 ms chunks (14 frames) with cache carry + streaming segmenter
     from vadx import firered_vad
@@ -418,6 +418,10 @@ def run_vadx(args):
         # algorithmic work per step per GPU
         lin_layers = ([(cfg.idim, cfg.H), (cfg.H, cfg.P)] + [(cfg.P, cfg.H), (cfg.H, cfg.P)] * (cfg.R - 1)
                       + [(cfg.P, cfg.H)] + [(cfg.H, cfg.H)] * (cfg.M - 1))
+        if stages.get("mel", (0, 0))[0] == 0:
+            # the log-mel contraction runs as a tcgen05 dense layer (bins the filterbank reads -> n_mels) and is
+            # timed with the linear stage
+            lin_layers = [(cfg.n_fft // 2, cfg.n_mels)] + lin_layers
         stage_bytes = {"linear": 4.0 * rows * sum(k + n for k, n in lin_layers),           # fp32 rows in + out
                        "memory": 4.0 * rows * cfg.P * (2 + (cfg.R - 1) * 3),               # p (+ residual) in, out
                        "stft": B * CHUNK * 2.0 + 4.0 * rows * (cfg.n_fft // 2 + 1),        # int16 audio in, power out
@@ -429,9 +433,9 @@ def run_vadx(args):
         dom = max(stages, key=lambda k: stages[k][0])
         dom_ms, dom_calls = stages[dom]
         stage_share = {k: round(v[0] / total_ms, 4) for k, v in stages.items()}
-        kernel_names = {"linear": "linear_tc_kernel (tcgen05, bf16 2-term split)", "memory": "fsmn_memory_stream_kernel",
+        kernel_names = {"linear": "linear_tc_kernel (tcgen05, bf16 2-term split)", "memory": "fsmn_memory_bulk_kernel (cp.async.bulk ring, fp32x2 FMA)",
                         "stft": "stft_power_tc_kernel (tcgen05, int16 exact split)", "mel": "mel_log_kernel",
-                        "head": "linear_narrow_kernel", "postproc": "postprocess_frames_warp_kernel",
+                        "head": "linear_narrow_kernel", "postproc": "postprocess_frames_runs_kernel",
                         "prep": "prep_audio_kernel"}
         # every stage of this path is limited by HBM traffic today (the tensor pipe is <25 % busy in the
         # tcgen05 kernels, see profiles/): report the dominant stage against the measured copy bandwidth,
@@ -443,7 +447,7 @@ def run_vadx(args):
                 "peak_source": pk["source"] + " STREAM-style copy (MEASURED_PEAKS.json hbm_gbs)",
                 "launches_timed": dom_calls, "avg_launch_ms": dom_ms / max(1, dom_calls),
                 "algorithmic_bytes_per_launch": per_launch_bytes}
-        roof["traffic"] = ncu_traffic_bytes({"linear": "linear_tc_kernel", "memory": "fsmn_memory_stream_kernel",
+        roof["traffic"] = ncu_traffic_bytes({"linear": "linear_tc_kernel", "memory": "fsmn_memory_bulk_kernel",
                                              "stft": "stft_power_tc_kernel", "mel": "mel_log_kernel"}.get(dom, dom))
         if roof["traffic"] is not None:
             roof["traffic_source"] = "profiles/r01_top_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches at this bench size)"

@@ -163,3 +163,14 @@ def test_near_end_only_variant(cuda, golden_dir, wts):
     # the whole single-recording script loop (overlapping windows, hysteresis, timestamps) runs
     r = dfsmn_aec.run_vad(g["near"][0], None, sess, rng=np.random.RandomState(1))
     assert len(r.saved) > 0
+
+
+def test_cuda_graph_replay_is_bit_identical(cuda, gold, wts):
+    cfg = W.DfsmnAecConfig()
+    sess = vadx.DfsmnAecSession(wts, cfg, chunk_len=31841)
+    near, far = torch.from_numpy(gold["near"]).to(cuda), torch.from_numpy(gold["far"]).to(cuda)
+    a = sess.run_batch(near, far).clone()
+    b = sess.run_batch_graph(near, far).clone()
+    c = sess.run_batch_graph(far, near).clone()           # second replay, different data
+    d = sess.run_batch(far, near)
+    assert torch.equal(a, b) and torch.equal(c, d)
