@@ -116,6 +116,22 @@ int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n_taps, int 
 int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
                            int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
                            int64_t ld_power, void* stream);
+/* Centre-padded and / or DC-removed frontends (FSMN, MarbleNet) on the same kernel: frame t starts pad_left
+ * samples before t*hop (zeros outside [0, n_samples)); with the mean given (vadx_stream_mean_i16 splits it into
+ * its nearest integer and the remainder) it is removed BEFORE the pre-emphasis, as FSMN/Export_FSMN_VAD.py:76-79
+ * does: the integer part exactly, from the samples in the loaders, the remainder in the frequency domain,
+ * X(x - m) = X(x) - m * D_t, D_t the folded basis applied to the mean's coefficient pattern
+ * (vadx_pack_stft_dc_tc: one row for interior frames, one per frame touching the pad, then the tail rows that
+ * undo the folded pre-emphasis' spill past the end of the stream). */
+int vadx_pack_stft_dc_tc(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph, double scale,
+                         int64_t n_samples, int hop, int pad_left, int n_frames, float* h_tables, size_t capacity_floats,
+                         size_t* n_floats, int* n_edge_lo, int* t_edge_hi);
+int vadx_stream_mean_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                         float* d_mean_frac, int32_t* d_mean_int, void* stream);
+int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                              int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
+                              int64_t ld_power, int pad_left, const float* d_mean_frac, const int32_t* d_mean_int,
+                              const float* d_dc_tables, int n_edge_lo, int t_edge_hi, void* stream);
 
 /* a3 -- triangular filterbank contraction + floor + ln.  The bank is passed in its sparse form:
  * filter m covers bins [start[m], start[m]+len[m]) with weights d_w[m*max_len + j].

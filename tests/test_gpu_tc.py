@@ -86,6 +86,54 @@ def test_stft_power_tc_from_int16(cuda, S, L):
     assert rel <= 3e-5
 
 
+@pytest.mark.parametrize("mode", ["fsmn", "marblenet"])
+@pytest.mark.parametrize("S,L", [(3, 16000), (9, 512), (2, 4800)])
+def test_stft_power_tc_centre_padded_frontends(cuda, mode, S, L):
+    """The generalised tensor-core DFT (centre pad; DC removal in the frequency domain) against the fp32 chain
+    prep_audio -> framed DFT that the FSMN / MarbleNet runtimes used before (itself checked against torch)."""
+    from vadx import tables
+    l = lib.load()
+    n_fft, win, hop = 512, 400, 160
+    basis, first, nb = tables.interleaved_basis(n_fft, win, "hamming" if mode == "fsmn" else "hann", "v2")
+    pad_left = n_fft // 2 - first
+    T = L // hop + 1
+    x = synth.synth_streams(S, L, seed=S * L)
+    x = (x.astype(np.int32) + (np.arange(S)[:, None] * 900 - 1500)).clip(-32768, 32767).astype(np.int16)   # DC offsets
+    xd = torch.from_numpy(x).to(cuda)
+    scale = 1.0 if mode == "fsmn" else 1.0 / 32768.0
+    dc = 1 if mode == "fsmn" else 0
+    pre_mode = lib.PREEMPH_KEEP_FIRST if mode == "fsmn" else lib.PREEMPH_ZERO_HISTORY
+    Lp = (pad_left + L + win + 3) // 4 * 4
+    sig = torch.zeros((S, Lp), device=cuda)
+    lib.check(l.vadx_prep_audio(xd.data_ptr(), lib.DT_I16, S, L, L, scale, dc, pre_mode, 0.97, pad_left, sig.data_ptr(), Lp,
+                                lib.stream_ptr()))
+    bd = torch.from_numpy(basis).to(cuda)
+    ref = torch.zeros((S * T, 258), device=cuda)
+    lib.check(l.vadx_stft_power_f32(sig.data_ptr(), Lp, S, T, hop, win, bd.data_ptr(), basis.shape[1], nb, ref.data_ptr(), 258,
+                                    lib.stream_ptr()))
+    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, scale)).to(cuda)
+    out = torch.full((S * T, 258), float("nan"), device=cuda)
+    mean = None
+    t, lo, hi = lib.pack_stft_dc_tc(basis, nb, 0.97, scale, L, hop, pad_left, T)
+    tab = torch.from_numpy(t).to(cuda)
+    assert lo >= 1 and hi <= T - 1
+    mean_i = None
+    if dc:
+        mean, mean_i = torch.empty((S,), device=cuda), torch.empty((S,), dtype=torch.int32, device=cuda)
+        lib.check(l.vadx_stream_mean_i16(xd.data_ptr(), L, L, S, mean.data_ptr(), mean_i.data_ptr(), lib.stream_ptr()))
+        tot = mean.cpu().double() + mean_i.cpu().double()
+        assert (tot - torch.from_numpy(x.astype(np.float64).mean(1))).abs().max().item() <= 1e-6
+        assert mean.abs().max().item() <= 0.5
+    lib.check(l.vadx_stft_power_tc_i16_ex(xd.data_ptr(), L, L, S, T, hop, win, img.data_ptr(), nb, out.data_ptr(), 258,
+                                          pad_left, lib.ptr(mean), lib.ptr(mean_i), lib.ptr(tab), lo, hi, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got, want = out[:, :nb].cpu(), ref[:, :nb].cpu()
+    assert not torch.isnan(got).any()
+    rel = ((got - want).abs() / want.max(dim=1, keepdim=True).values.clamp_min(1e-30)).max().item()
+    print(f"stft tc {mode} S={S} L={L}: max err relative to the frame's strongest bin {rel:.2e}")
+    assert rel <= 3e-5
+
+
 def test_unsupported_shapes_are_rejected(cuda):
     l = lib.load()
     assert l.vadx_tc_supported(256, 1) == 0      # narrow heads stay on the warp-reduction kernel

@@ -64,6 +64,17 @@ int fsmn_finalize(vadx_model* m) {
   FsmnHP h;
   VADX_TRY(fsmn_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
+  if (vadx_stft_tc_supported(h.n_taps(), h.n_bins())) {
+    // tensor-core DFT image: pre-emphasis folded into the 2-term bf16 basis; the DC removal is applied in the
+    // frequency domain by the kernel's epilogue (tables built per chunk length at first use)
+    const double preemph = m->scalar("frontend.preemph", 0.97);
+    const float* hb = m->find("frontend.basis")->f32();
+    size_t bytes = 0;
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, nullptr, 0, &bytes));
+    std::vector<uint8_t> img(bytes);
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, img.data(), img.size(), &bytes));
+    VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
+  }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
@@ -107,6 +118,8 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   float* bufM = ws.take<float>(rows * h.proj);
   float* p_sil_ws = ws.take<float>(rows);
   float* power_db_ws = ws.take<float>(rows);
+  float* mean_ws = ws.take<float>(S);
+  int32_t* mean_int_ws = ws.take<int32_t>(S);
   if (need) *need = ws.off;
   if (dry) return VADX_OK;
   if (ws.off > ws_bytes) {
@@ -131,8 +144,32 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
 
   VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,
                            h.pad_left(), sig, Lp, st));
-  VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
-                               h.n_bins(), power, h.ld_power(), st));
+  const uint8_t* stft_img = use_tc ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
+  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
+    // framed DFT on the tensor cores straight from the int16 samples; the mean is removed in the epilogue
+    const std::string key = "frontend.dc#" + std::to_string((long long)L);
+    const std::string k_lo = key + ".lo", k_hi = key + ".hi";
+    if (!m->d<float>(key)) {
+      size_t n = 0;
+      int lo = 0, hi = 0;
+      const float* hb = m->find("frontend.basis")->f32();
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, L, h.hop, h.pad_left(), T, nullptr,
+                                    0, &n, &lo, &hi));
+      std::vector<float> tab(n);
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, L, h.hop, h.pad_left(), T,
+                                    tab.data(), tab.size(), &n, &lo, &hi));
+      VADX_TRY(m->upload(key, tab.data(), tab.size() * sizeof(float)));
+      m->scalars[k_lo] = lo;
+      m->scalars[k_hi] = hi;
+    }
+    VADX_TRY(vadx_stream_mean_i16(static_cast<const int16_t*>(in[0]), L, L, S, mean_ws, mean_int_ws, st));
+    VADX_TRY(vadx_stft_power_tc_i16_ex(static_cast<const int16_t*>(in[0]), L, L, S, T, h.hop, h.n_taps(), stft_img, h.n_bins(),
+                                       power, h.ld_power(), h.pad_left(), mean_ws, mean_int_ws, m->d<float>(key),
+                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T), st));
+  } else {
+    VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                                 h.n_bins(), power, h.ld_power(), st));
+  }
   VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_CLAMP,
                             floor_v, mel, h.n_mels, st));

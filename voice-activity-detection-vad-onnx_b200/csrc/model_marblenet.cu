@@ -74,6 +74,17 @@ int marblenet_finalize(vadx_model* m) {
   MarbleHP h;
   VADX_TRY(marble_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
+  if (vadx_stft_tc_supported(h.n_taps(), h.n_bins())) {
+    // tensor-core DFT image: 1/32768 and the pre-emphasis folded into the 2-term bf16 basis
+    const double preemph = m->scalar("frontend.preemph", 0.97);
+    const float* hb = m->find("frontend.basis")->f32();
+    size_t bytes = 0;
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, nullptr, 0, &bytes));
+    std::vector<uint8_t> img(bytes);
+    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, img.data(), img.size(),
+                                     &bytes));
+    VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
+  }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
@@ -129,10 +140,33 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
   const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0;
   const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
 
-  VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 0,
-                           preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0, preemph, h.pad_left(), sig, Lp, st));
-  VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T0, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
-                               h.n_bins(), power, h.ld_power(), st));
+  const uint8_t* stft_img = use_tc && rows0 > kSkinnyMaxRows ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
+  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
+    // centre-padded framed DFT on the tensor cores straight from the int16 samples (zeros outside the clip)
+    const std::string key = "frontend.dc#" + std::to_string((long long)L);
+    const std::string k_lo = key + ".lo", k_hi = key + ".hi";
+    if (!m->d<float>(key)) {
+      size_t n = 0;
+      int lo = 0, hi = 0;
+      const float* hb = m->find("frontend.basis")->f32();
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, L, h.hop, h.pad_left(), T0,
+                                    nullptr, 0, &n, &lo, &hi));
+      std::vector<float> tab(n);
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, L, h.hop, h.pad_left(), T0,
+                                    tab.data(), tab.size(), &n, &lo, &hi));
+      VADX_TRY(m->upload(key, tab.data(), tab.size() * sizeof(float)));
+      m->scalars[k_lo] = lo;
+      m->scalars[k_hi] = hi;
+    }
+    VADX_TRY(vadx_stft_power_tc_i16_ex(static_cast<const int16_t*>(in[0]), L, L, S, T0, h.hop, h.n_taps(), stft_img, h.n_bins(),
+                                       power, h.ld_power(), h.pad_left(), nullptr, nullptr, m->d<float>(key),
+                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T0), st));
+  } else {
+    VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 0,
+                             preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0, preemph, h.pad_left(), sig, Lp, st));
+    VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T0, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                                 h.n_bins(), power, h.ld_power(), st));
+  }
   VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows0, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
                             m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_ADD, eps,
                             B[0], h.n_mels, st));

@@ -43,6 +43,14 @@ struct StftTcArgs {
   int64_t ldp;
   int64_t M;           // S * n_frames
   int n_bins, kc, n_k16, n_tiles, vec_p;
+  int pad_left;          // zero samples before sample 0 (centre pad minus the window's dead taps); multiple of 8
+  const float* mean;     // [S] FRACTIONAL part of the per-stream mean (removed in the epilogue), or null
+  const int* mean_int;   // [S] integer part of the mean, subtracted from the samples by the loaders (exact: the
+                         // 17-bit difference still splits into two bf16-exact terms)
+  const float* dc;       // [(1 + n_edge) + n_edge_hi][n_ntiles * kStNPad]: the folded basis applied to the mean's
+                         // coefficient pattern -- row 0 for interior frames, one row per frame that touches the zero
+                         // pad -- then one tail row per frame that runs past the end of the stream
+  int n_edge_lo, t_edge_hi;   // frames t < n_edge_lo and t >= t_edge_hi are edge frames
   int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
@@ -64,6 +72,15 @@ __device__ __forceinline__ uint32_t bf16x2_hi(uint32_t w) {
   return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
 }
 
+// same trick for a sample with an integer offset removed: d in [-65535, 65535] -> (256 * (d >> 8), d & 255)
+__device__ __forceinline__ void split17(int d, float& hi, float& lo) {
+  lo = __uint_as_float(0x4B000000u | (uint32_t)(d & 255)) - 8388608.0f;
+  const uint32_t h = (uint32_t)((d >> 8) + 256);   // [0, 511]
+  hi = fmaf(__uint_as_float(0x4B000000u | h), 256.0f, -(8388608.0f + 256.0f) * 256.0f);
+}
+
+// EX = false: every frame inside the stream, no DC removal (FireRed) -- the padded / mean-removing code is compiled out
+template <bool EX>
 __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const StftTcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* w_smem = smem_raw;
@@ -162,7 +179,8 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     struct Seq { int tile, c; };
     auto valid = [&](const Seq& q) { return q.tile < g.n_tiles; };
     auto advance = [&](Seq& q) { if (++q.c == g.kc) { q.c = 0; q.tile += gridDim.x; } };
-    auto issue = [&](const Seq& q, uint4* raw) {
+    auto issue = [&](const Seq& q, uint4* raw, uint32_t& msk) {
+      msk = 0u;
       if (q.tile != tile_cached) {
         const int64_t row0 = (int64_t)q.tile * kTcBM;
 #pragma unroll
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
           const int64_t s = row / g.n_frames;
           const int fr = (int)(row - s * g.n_frames);
           xs_n[pass] = g.X + s * g.in_stride;
-          forig_n[pass] = fr * g.hop - kStLead;
+          forig_n[pass] = fr * g.hop - (EX ? g.pad_left : 0) - kStLead;
         }
         tile_cached = q.tile;
       }
@@ -185,12 +203,15 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
           v = make_uint4(0x00010002u, 0x00030004u, 0x00050006u, 0x00070008u);
         } else if (i0 >= 0 && i0 + 7 < g.L) {
           v = __ldg(reinterpret_cast<const uint4*>(xs + i0));
+          if (EX) msk |= 0xffu << (8 * pass);
         } else if (i0 + 7 >= 0 && i0 < g.L) {
           uint16_t tmp[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             int i = i0 + j;
-            tmp[j] = (i >= 0 && i < g.L) ? (uint16_t)__ldg(xs + i) : (uint16_t)0;
+            const bool in = i >= 0 && i < g.L;
+            tmp[j] = in ? (uint16_t)__ldg(xs + i) : (uint16_t)0;
+            if (EX && in) msk |= 1u << (8 * pass + j);
           }
           v.x = tmp[0] | ((uint32_t)tmp[1] << 16);
           v.y = tmp[2] | ((uint32_t)tmp[3] << 16);
@@ -202,11 +223,21 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     };
     int stage = 0;
     uint32_t phase = 0;
-    auto consume = [&](const Seq& q, const uint4* raw) {
+    int mi_c[kPasses];        // integer mean of each row's stream, for the tile being CONSUMED
+    int tile_cached_c = -1;
+    auto consume = [&](const Seq& q, const uint4* raw, uint32_t msk) {
+      const int64_t row0 = (int64_t)q.tile * kTcBM;
+      if (EX && g.mean_int && q.tile != tile_cached_c) {
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
+          mi_c[pass] = __ldg(g.mean_int + row / g.n_frames);
+        }
+        tile_cached_c = q.tile;
+      }
       mbar_wait(empty_bar(stage), phase ^ 1u, 64);
       uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
-      const int64_t row0 = (int64_t)q.tile * kTcBM;
       if (!(g.debug & 8))
 #pragma unroll
       for (int pass = 0; pass < kPasses; ++pass) {
@@ -214,11 +245,28 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         const uint32_t wds[4] = {raw[pass].x, raw[pass].y, raw[pass].z, raw[pass].w};
         uint32_t hi[4], lo[4];
         const bool live = row0 + r < g.M;
+        if (EX && g.mean_int) {
+          // integer part of the stream's mean removed from the real samples only (the zero pad stays zero)
+          const int mi = mi_c[pass];
+          const uint32_t vm = (msk >> (8 * pass)) & 0xffu;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w = live ? wds[j] : 0u;
+            const int a = (live && ((vm >> (2 * j)) & 1u)) ? ((int)(w << 16) >> 16) - mi : 0;
+            const int b = (live && ((vm >> (2 * j + 1)) & 1u)) ? ((int)w >> 16) - mi : 0;
+            float ah, al, bh, bl;
+            split17(a, ah, al);
+            split17(b, bh, bl);
+            hi[j] = __byte_perm(__float_as_uint(ah), __float_as_uint(bh), 0x7632);
+            lo[j] = __byte_perm(__float_as_uint(al), __float_as_uint(bl), 0x7632);
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t w = live ? wds[j] : 0u;
           hi[j] = bf16x2_hi(w);
           lo[j] = bf16x2_lo(w);
+        }
         }
         const int off = r * 128 + ((kq ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -230,18 +278,19 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       if (++stage == kStStages) { stage = 0; phase ^= 1u; }
     };
     uint4 b0[kPasses], b1[kPasses], b2[kPasses];
+    uint32_t m0 = 0, m1 = 0, m2 = 0;   // validity masks of the buffered samples (8 bits per pass)
     Seq nxt{(int)blockIdx.x, 0}, cur{(int)blockIdx.x, 0};
-    if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
-    if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+    if (valid(nxt)) { issue(nxt, b0, m0); advance(nxt); }
+    if (valid(nxt)) { issue(nxt, b1, m1); advance(nxt); }
     while (valid(cur)) {
-      if (valid(nxt)) { issue(nxt, b2); advance(nxt); }
-      consume(cur, b0); advance(cur);
+      if (valid(nxt)) { issue(nxt, b2, m2); advance(nxt); }
+      consume(cur, b0, m0); advance(cur);
       if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
-      consume(cur, b1); advance(cur);
+      if (valid(nxt)) { issue(nxt, b0, m0); advance(nxt); }
+      consume(cur, b1, m1); advance(cur);
       if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
-      consume(cur, b2); advance(cur);
+      if (valid(nxt)) { issue(nxt, b1, m1); advance(nxt); }
+      consume(cur, b2, m2); advance(cur);
     }
   } else {
     // ===================== epilogue: re^2 + im^2 =====================
@@ -256,11 +305,40 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * kStNPad);
+      // DC removal in the frequency domain: X(x - m) = X(x) - m * (folded basis applied to the mean's
+      // coefficient pattern), exact in fp32; only frames touching the zero pad need their own row of the table
+      // Frames that run past the end of the stream: the reference pads the PRE-EMPHASISED signal with zeros, the
+      // folded basis sees y[L] = 0 - c*x[L-1] there; the tail table (c * b[L - origin(t)][col]) puts it back.
+      float m_row = 0.f, x_last = 0.f;
+      const float* dc_row = nullptr;
+      const float* tail_row = nullptr;
+      if (EX && g.dc && row_ok) {
+        const int64_t sidx = row / g.n_frames;
+        const int t = (int)(row - sidx * g.n_frames);
+        const int n_edge = g.n_edge_lo + (g.n_frames - g.t_edge_hi);
+        if (g.mean) {
+          m_row = __ldg(g.mean + sidx);
+          const int e = t < g.n_edge_lo ? 1 + t : (t >= g.t_edge_hi ? 1 + g.n_edge_lo + (t - g.t_edge_hi) : 0);
+          dc_row = g.dc + ((size_t)e * gridDim.y + ntile) * kStNPad;
+        }
+        if (t >= g.t_edge_hi) {
+          x_last = (float)((int)__ldg(g.X + sidx * g.in_stride + (g.L - 1)) - (g.mean_int ? __ldg(g.mean_int + sidx) : 0));
+          tail_row = g.dc + ((size_t)(1 + n_edge + (t - g.t_edge_hi)) * gridDim.y + ntile) * kStNPad;
+        }
+      }
 #pragma unroll
       for (int c0 = 0; c0 < kStNPad; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         if (!row_ok || (g.debug & 1)) continue;
+        if (EX && dc_row) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(-m_row, __ldg(dc_row + c0 + j), v[j]);
+        }
+        if (EX && tail_row) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(x_last, __ldg(tail_row + c0 + j), v[j]);
+        }
         float* out = g.P + row * g.ldp + f0 + c0 / 2;
         float pw[8];
 #pragma unroll
@@ -349,15 +427,113 @@ extern "C" int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n
   return VADX_OK;
 }
 
+// Folded-basis response to the DC term of a centre-padded, DC-removed frontend: with y[0] = x[0] - m and
+// y[i] = (x[i] - m) - c (x[i-1] - m) = x[i] - c x[i-1] - (1 - c) m for 1 <= i < L, frame t of the mean alone is
+// sum_n coef(t*hop - pad_left + n) * b[n][col], coef(0) = 1, coef(i) = 1 - c inside, 0 in the pad.
+extern "C" int vadx_pack_stft_dc_tc(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph, double scale,
+                                    int64_t n_samples, int hop, int pad_left, int n_frames, float* h_tables,
+                                    size_t capacity_floats, size_t* n_floats, int* n_edge_lo, int* t_edge_hi) {
+  VADX_REQUIRE(h_basis && n_floats && n_edge_lo && t_edge_hi && n_taps > 0 && n_bins > 0 && hop > 0 && pad_left >= 0 &&
+                   n_frames > 0 && ld_basis >= 2 * n_bins,
+               "vadx_pack_stft_dc_tc: bad argument");
+  StftTcShape s = stft_tc_shape(n_taps, n_bins);
+  VADX_REQUIRE(s.ok, "vadx_pack_stft_dc_tc: shape not supported");
+  // frame t is interior when every tap index lies in [1, n_samples)
+  int lo = 0;
+  while (lo < n_frames && (int64_t)lo * hop - pad_left < 1) ++lo;
+  int hi = n_frames;
+  while (hi > lo && (int64_t)(hi - 1) * hop - pad_left + n_taps - 1 >= n_samples) --hi;
+  *n_edge_lo = lo;
+  *t_edge_hi = hi;
+  const int n_edge = lo + (n_frames - hi);
+  const size_t ncp = (size_t)s.n_ntiles * kStNPad;
+  *n_floats = (size_t)(1 + n_edge + (n_frames - hi)) * ncp;   // DC rows, then one tail row per right-edge frame
+  if (!h_tables) return VADX_OK;
+  VADX_REQUIRE(capacity_floats >= *n_floats, "vadx_pack_stft_dc_tc: table buffer too small");
+  memset(h_tables, 0, *n_floats * sizeof(float));
+  auto fill = [&](float* row, int64_t origin, bool interior) {
+    for (int col = 0; col < 2 * n_bins; ++col) {
+      double acc = 0.0;
+      for (int n = 0; n < n_taps; ++n) {
+        const int64_t i = origin + n;
+        double coef = interior ? 1.0 - preemph : (i < 0 || i >= n_samples ? 0.0 : (i == 0 ? 1.0 : 1.0 - preemph));
+        acc += coef * (double)h_basis[(size_t)n * ld_basis + col];
+      }
+      row[col] = (float)(acc * scale);
+    }
+  };
+  fill(h_tables, 0, true);
+  int e = 1;
+  for (int t = 0; t < lo; ++t, ++e) fill(h_tables + (size_t)e * ncp, (int64_t)t * hop - pad_left, false);
+  for (int t = hi; t < n_frames; ++t, ++e) fill(h_tables + (size_t)e * ncp, (int64_t)t * hop - pad_left, false);
+  // tail rows: c * scale * b[n_L][col], n_L = tap index of sample L in frame t (zero row when outside the window)
+  for (int t = hi; t < n_frames; ++t, ++e) {
+    const int64_t n_l = n_samples - ((int64_t)t * hop - pad_left);
+    if (n_l < 0 || n_l >= n_taps) continue;
+    float* row = h_tables + (size_t)e * ncp;
+    for (int col = 0; col < 2 * n_bins; ++col) row[col] = (float)(preemph * scale * (double)h_basis[(size_t)n_l * ld_basis + col]);
+  }
+  return VADX_OK;
+}
+
+namespace vadx {
+__global__ void __launch_bounds__(256) stream_mean_i16_kernel(const int16_t* __restrict__ x, int64_t in_stride, int64_t n,
+                                                              float* __restrict__ mean_frac, int* __restrict__ mean_int) {
+  const int64_t s = blockIdx.x;
+  const int16_t* p = x + s * in_stride;
+  long long acc = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (long long)__ldg(p + i);
+  __shared__ long long part[8];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    const double m = (double)t / (double)n;
+    const int mi = (int)llrint(m);
+    mean_int[s] = mi;
+    mean_frac[s] = (float)(m - (double)mi);
+  }
+}
+}  // namespace vadx
+
+extern "C" int vadx_stream_mean_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                                    float* d_mean_frac, int32_t* d_mean_int, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  VADX_REQUIRE(d_audio && d_mean_frac && d_mean_int && n_samples > 0 && in_stride >= n_samples && n_streams >= 0,
+               "vadx_stream_mean_i16: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  stream_mean_i16_kernel<<<(unsigned)n_streams, 256, 0, (cudaStream_t)stream>>>(d_audio, in_stride, n_samples, d_mean_frac,
+                                                                                d_mean_int);
+  return after_launch("vadx_stream_mean_i16");
+}
+
 extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
                                       int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
                                       int64_t ld_power, void* stream) {
+  VADX_REQUIRE((int64_t)(n_frames - 1) * hop + n_taps <= n_samples,
+               "vadx_stft_power_tc_i16: frames must lie inside the %lld samples of a stream", (long long)n_samples);
+  return vadx_stft_power_tc_i16_ex(d_audio, in_stride, n_samples, n_streams, n_frames, hop, n_taps, d_img, n_bins, d_power,
+                                   ld_power, 0, nullptr, nullptr, nullptr, 0, n_frames, stream);
+}
+
+extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
+                                         int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
+                                         int64_t ld_power, int pad_left, const float* d_mean_frac, const int32_t* d_mean_int,
+                                         const float* d_dc_tables, int n_edge_lo, int t_edge_hi, void* stream) {
+  const float* d_mean = d_mean_frac;
+  VADX_REQUIRE((d_mean_frac == nullptr) == (d_mean_int == nullptr), "vadx_stft_power_tc_i16: mean needs both its parts");
   StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
   VADX_REQUIRE(d_audio && d_img && d_power, "vadx_stft_power_tc_i16: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0 && ld_power >= n_bins,
                "vadx_stft_power_tc_i16: bad shape");
-  VADX_REQUIRE((int64_t)(n_frames - 1) * hop + n_taps <= n_samples && in_stride >= n_samples,
-               "vadx_stft_power_tc_i16: frames must lie inside the %lld samples of a stream", (long long)n_samples);
+  VADX_REQUIRE(in_stride >= n_samples && pad_left >= 0 && (pad_left % 8) == 0,
+               "vadx_stft_power_tc_i16: stride shorter than the stream, or pad_left not a multiple of 8");
+  const bool leaves_stream = pad_left > 0 || (int64_t)(n_frames - 1) * hop - pad_left + n_taps > n_samples;
+  VADX_REQUIRE(!(d_mean || leaves_stream) || (d_dc_tables && n_edge_lo >= 0 && t_edge_hi >= n_edge_lo && t_edge_hi <= n_frames),
+               "vadx_stft_power_tc_i16: padded frames / DC removal need the tables of vadx_pack_stft_dc_tc");
   VADX_REQUIRE((in_stride % 8) == 0 && (hop % 8) == 0 && aligned16(d_audio) && aligned16(d_img),
                "vadx_stft_power_tc_i16: stream stride and hop must be multiples of 8 samples, pointers 16-byte aligned");
   StftTcShape s = stft_tc_shape(n_taps, n_bins);
@@ -369,7 +545,9 @@ extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride,
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stft_power_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_power_tc_kernel)");
     configured = true;
   }
@@ -377,6 +555,7 @@ extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride,
   g.X = d_audio; g.in_stride = in_stride; g.L = n_samples; g.n_frames = n_frames; g.hop = hop;
   g.Wimg = static_cast<const uint8_t*>(d_img); g.P = d_power; g.ldp = ld_power; g.M = n_streams * n_frames;
   g.n_bins = n_bins; g.kc = s.kc; g.n_k16 = s.n_k16;
+  g.pad_left = pad_left; g.mean = d_mean; g.mean_int = d_mean_int; g.dc = d_dc_tables; g.n_edge_lo = n_edge_lo; g.t_edge_hi = t_edge_hi;
   g.vec_p = ((ld_power & 3) == 0) && aligned16(d_power);
   {
     static int dbg = -1;
@@ -391,6 +570,9 @@ extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride,
   g.n_tiles = (int)tiles;
   int per = std::max(1, (n_sm > 0 ? n_sm : 148) / s.n_ntiles);
   dim3 grid((unsigned)std::min<int64_t>(tiles, per), (unsigned)s.n_ntiles);
-  stft_power_tc_kernel<<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  if (leaves_stream || d_mean)
+    stft_power_tc_kernel<true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  else
+    stft_power_tc_kernel<false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
   return after_launch("vadx_stft_power_tc_i16");
 }

@@ -46,6 +46,11 @@ SIGNATURES = {
     "vadx_stft_tc_supported": (C.c_int, [_i32, _i32]),
     "vadx_pack_stft_basis_tc": (C.c_int, [_vp, _i32, _i32, _i32, C.c_double, C.c_double, _vp, _sz, C.POINTER(_sz)]),
     "vadx_stft_power_tc_i16": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
+    "vadx_pack_stft_dc_tc": (C.c_int, [_vp, _i32, _i32, _i32, C.c_double, C.c_double, _i64, _i32, _i32, _i32, _vp, _sz,
+                                       C.POINTER(_sz), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vadx_stream_mean_i16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "vadx_stft_power_tc_i16_ex": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp,
+                                            _i32, _i32, _vp]),
     "vadx_mel_log_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i64, _vp]),
     "vadx_linear_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_tc_supported": (C.c_int, [_i32, _i32]),
@@ -169,6 +174,21 @@ def pack_stft_basis_tc(basis, n_bins: int, preemph: float, scale: float):
     check(load().vadx_pack_stft_basis_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, img.ctypes.data,
                                          img.nbytes, C.byref(nbytes)))
     return img
+
+
+def pack_stft_dc_tc(basis, n_bins: int, preemph: float, scale: float, n_samples: int, hop: int, pad_left: int,
+                    n_frames: int):
+    """DC-response tables for vadx_stft_power_tc_i16_ex -> (float32 array, n_edge_lo, t_edge_hi)"""
+    import numpy as np
+    basis = np.ascontiguousarray(basis, np.float32)
+    n_taps, ld = basis.shape
+    n, lo, hi = C.c_size_t(), C.c_int(), C.c_int()
+    check(load().vadx_pack_stft_dc_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, n_samples, hop, pad_left,
+                                      n_frames, None, 0, C.byref(n), C.byref(lo), C.byref(hi)))
+    tab = np.zeros(n.value, np.float32)
+    check(load().vadx_pack_stft_dc_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, n_samples, hop, pad_left,
+                                      n_frames, tab.ctypes.data, tab.size, C.byref(n), C.byref(lo), C.byref(hi)))
+    return tab, lo.value, hi.value
 
 
 def ptr(t) -> int:
