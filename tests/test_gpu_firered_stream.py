@@ -205,3 +205,20 @@ def test_vad_sample_vad_and_aed_sections(cuda, gold_script, golden_dir):
             assert np.array_equal(_pairs(ra.event2timestamps[ev]), g[f"aed_{ev}_timestamps"]), ev
         if np.abs(g["aed_probs"][e] - np.float32(thr)).min() > TOL:
             assert ra.event2ratio[ev] == float(g[f"aed_{ev}_ratio"])
+
+
+def test_stream_cuda_graph_replay_is_bit_identical(cuda, stream_session):
+    """Eager lock-step run vs the two captured steps replayed; twice, so the second call reuses the cached graphs."""
+    S, c, n_calls = 40, 2560, 7
+    lengths = [c * n_calls - 97 * s for s in range(S)]
+    raw = synth.synth_streams(S, c * n_calls, seed=8)
+    padded = np.zeros((S, c * n_calls), np.int16)
+    for s in range(S):
+        padded[s, :lengths[s]] = raw[s, :lengths[s]]
+    d = torch.from_numpy(padded).to(cuda)
+    p0, post0, c0, _ = firered_vad.run_stream_vad_streams(stream_session, d, lengths)
+    ts0 = post0.timestamps()
+    for _ in range(2):
+        p1, post1, c1, _ = firered_vad.run_stream_vad_streams(stream_session, d, lengths, graph=True)
+        assert torch.equal(p0, p1) and torch.equal(c0, c1)
+        assert post1.timestamps() == ts0

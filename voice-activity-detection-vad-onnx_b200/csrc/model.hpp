@@ -110,8 +110,43 @@ struct vadx_model {
       std::vector<uint8_t> img(bytes);
       VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, img.data(), img.size(), &bytes));
       VADX_TRY(upload(name + "#TC", img.data(), img.size()));
+    } else if (n_in > 256 && n_out > 8 && vadx_tc_supported(256, n_out) && vadx_tc_supported(n_in - 256, n_out)) {
+      // K too long for one stationary operand image (e.g. FSMN 400 -> 140): two images over K = [0, 256) and
+      // [256, n_in); the second launch accumulates onto the first through the residual input
+      for (int part = 0; part < 2; ++part) {
+        const int k0 = part ? 256 : 0, kn = part ? n_in - 256 : 256;
+        std::vector<float> sub((size_t)n_out * kn);
+        for (int o = 0; o < n_out; ++o)
+          for (int i = 0; i < kn; ++i) sub[(size_t)o * kn + i] = w[(size_t)o * n_in + k0 + i];
+        size_t bytes = 0;
+        VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, nullptr, 0, &bytes));
+        std::vector<uint8_t> img(bytes);
+        VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, img.data(), img.size(), &bytes));
+        VADX_TRY(upload(name + (part ? "#TC1" : "#TC0"), img.data(), img.size()));
+      }
     }
     return VADX_OK;
+  }
+  // the sparse filterbank (frontend.mel_start / mel_len / mel_w) as a dense [n_mels][n_bins] tensor-core layer image
+  // ("frontend.mel#TC") plus its per-column floor / epsilon vector ("frontend.mel_floor"); no-op when it does not fit
+  int upload_mel_dense_tc(int n_mels, int n_bins, float floor_value) {
+    const HostTensor* ms = find("frontend.mel_start");
+    const HostTensor* ml = find("frontend.mel_len");
+    const HostTensor* mw = find("frontend.mel_w");
+    if (!ms || !ml || !mw || ms->numel() != n_mels || ml->numel() != n_mels || !vadx_tc_supported(n_bins, n_mels)) return VADX_OK;
+    const int max_len = (int)(mw->numel() / n_mels);
+    const int32_t* a = reinterpret_cast<const int32_t*>(ms->bytes.data());
+    const int32_t* b = reinterpret_cast<const int32_t*>(ml->bytes.data());
+    std::vector<float> dense((size_t)n_mels * n_bins, 0.f);
+    for (int i = 0; i < n_mels; ++i)
+      for (int j = 0; j < b[i] && a[i] + j < n_bins; ++j) dense[(size_t)i * n_bins + a[i] + j] = mw->f32()[(size_t)i * max_len + j];
+    size_t bytes = 0;
+    VADX_TRY(vadx_pack_weight_tc(dense.data(), n_mels, n_bins, nullptr, 0, &bytes));
+    std::vector<uint8_t> img(bytes);
+    VADX_TRY(vadx_pack_weight_tc(dense.data(), n_mels, n_bins, img.data(), img.size(), &bytes));
+    VADX_TRY(upload("frontend.mel#TC", img.data(), img.size()));
+    std::vector<float> fl((size_t)n_mels, floor_value);
+    return upload("frontend.mel_floor", fl.data(), fl.size() * sizeof(float));
   }
   int upload_raw(const std::string& name, int64_t expect_numel, int dtype) {
     const HostTensor* t = find(name);

@@ -31,7 +31,7 @@ struct FsmnHP {
   int first_tap() const { return win < n_fft ? (n_fft - win) / 2 : 0; }
   int n_bins() const { return n_fft / 2 + 1; }
   int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
-  int ld_power() const { return (int)round_up(n_bins(), 2); }
+  int ld_power() const { return (int)round_up(n_bins(), 4); }
   int pad_left() const { return n_fft / 2 - first_tap(); }
   int frames(int64_t L) const { return (int)(L / hop + 1); }
 };
@@ -78,6 +78,7 @@ int fsmn_finalize(vadx_model* m) {
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_mel_dense_tc(h.n_mels, h.n_bins(), (float)m->scalar("frontend.log_floor", 1e-5)));
   VADX_TRY(m->upload_raw("cmvn_means", h.input_dim, VADX_DT_F32));
   VADX_TRY(m->upload_raw("cmvn_vars", h.input_dim, VADX_DT_F32));
   VADX_TRY(m->upload_linear("in_linear1.linear.weight", h.affine, h.input_dim));
@@ -170,9 +171,15 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
     VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
                                  h.n_bins(), power, h.ld_power(), st));
   }
-  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
-                            m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_CLAMP,
-                            floor_v, mel, h.n_mels, st));
+  if (use_tc && m->d<uint8_t>("frontend.mel#TC")) {
+    // log-mel as a dense tensor-core layer, log(max(., floor)) in the epilogue
+    VADX_TRY(vadx_linear_tc_f32(power, h.ld_power(), m->d<uint8_t>("frontend.mel#TC"), m->d<float>("frontend.mel_floor"),
+                                nullptr, 0, mel, h.n_mels, rows, h.n_bins(), h.n_mels, VADX_ACT_LOG_CLAMP, st));
+  } else {
+    VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
+                              m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_CLAMP,
+                              floor_v, mel, h.n_mels, st));
+  }
   VADX_TRY(vadx_lfr_cmvn_f32(mel, h.n_mels, m->d<float>("cmvn_means"), m->d<float>("cmvn_vars"), feat, h.input_dim, S,
                              T, h.n_mels, h.lfr_m, h.lfr_n, st));
   auto lin = [&](const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, float* y, int64_t ldy,
@@ -180,6 +187,13 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
     const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
     const float* bias = b ? m->d<float>(b) : nullptr;
     if (img) return vadx_linear_tc_f32(x, ldx, img, bias, nullptr, 0, y, ldy, rows, n_in, n_out, act, st);
+    const uint8_t* img0 = use_tc ? m->d<uint8_t>(w + "#TC0") : nullptr;
+    if (img0 && (act & 15) == VADX_ACT_NONE) {
+      // long K split over two stationary images: y = x[:, :256] W0^T + b, then y += x[:, 256:] W1^T
+      VADX_TRY(vadx_linear_tc_f32(x, ldx, img0, bias, nullptr, 0, y, ldy, rows, 256, n_out, VADX_ACT_NONE, st));
+      return vadx_linear_tc_f32(x + 256, ldx, m->d<uint8_t>(w + "#TC1"), nullptr, y, ldy, y, ldy, rows, n_in - 256, n_out,
+                                VADX_ACT_NONE, st);
+    }
     return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, nullptr, 0, y, ldy, rows, n_in,
                            n_out, act, st);
   };

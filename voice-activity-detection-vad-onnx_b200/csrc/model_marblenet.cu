@@ -20,7 +20,7 @@ struct MarbleHP {
   int first_tap() const { return win < n_fft ? (n_fft - win) / 2 : 0; }
   int n_bins() const { return n_fft / 2 + 1; }
   int ld_basis() const { return (int)round_up(2 * n_bins(), 4); }
-  int ld_power() const { return (int)round_up(n_bins(), 2); }
+  int ld_power() const { return (int)round_up(n_bins(), 4); }
   int pad_left() const { return n_fft / 2 - first_tap(); }
   int stft_frames(int64_t L) const { return (int)(L / hop + 1); }
   static int conv_len(int t, int k, int stride, int dil) {
@@ -88,6 +88,7 @@ int marblenet_finalize(vadx_model* m) {
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_len", h.n_mels, VADX_DT_I32));
   VADX_TRY(m->upload_raw("frontend.mel_w", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_mel_dense_tc(h.n_mels, h.n_bins(), (float)m->scalar("frontend.log_eps", 1e-7)));
   int c_in = h.feat_in;
   for (size_t b = 0; b < h.blocks.size(); ++b) {
     const Block& k = h.blocks[b];
@@ -167,9 +168,15 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
     VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T0, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
                                  h.n_bins(), power, h.ld_power(), st));
   }
-  VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows0, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
-                            m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_ADD, eps,
-                            B[0], h.n_mels, st));
+  if (use_tc && rows0 > kSkinnyMaxRows && m->d<uint8_t>("frontend.mel#TC")) {
+    // log-mel as a dense tensor-core layer, log(. + eps) in the epilogue (the bias slot carries eps)
+    VADX_TRY(vadx_linear_tc_f32(power, h.ld_power(), m->d<uint8_t>("frontend.mel#TC"), m->d<float>("frontend.mel_floor"),
+                                nullptr, 0, B[0], h.n_mels, rows0, h.n_bins(), h.n_mels, VADX_ACT_LOG, st));
+  } else {
+    VADX_TRY(vadx_mel_log_f32(power, h.ld_power(), rows0, h.n_bins(), h.n_mels, m->d<int32_t>("frontend.mel_start"),
+                              m->d<int32_t>("frontend.mel_len"), m->d<float>("frontend.mel_w"), mel_max, VADX_FLOOR_ADD, eps,
+                              B[0], h.n_mels, st));
+  }
   auto lin = [&](const float* a, int n_in, const std::string& w, const std::string& b, const float* res, float* y,
                  int n_out, int64_t rows, int act) -> int {
     const uint8_t* img = use_tc && rows > kSkinnyMaxRows ? m->d<uint8_t>(w + "#TC") : nullptr;

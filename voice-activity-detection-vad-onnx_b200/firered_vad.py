@@ -221,26 +221,83 @@ def stream_frame_plan(lengths, chunk_samples: int = STREAM_CHUNK_SAMPLES):
     Per stream this is what the reference loop produces (:786-811): full chunks give 1 + (c-400)//160
     frames, the last partial chunk its own count (one frame if it had to be zero-padded to 400 samples),
     and the concatenation is cut at valid_frame_count(len)."""
-    lengths = [int(n) for n in lengths]
-    n_calls = max(1, max((n + chunk_samples - 1) // chunk_samples for n in lengths)) if lengths else 0
-    plan = np.zeros((n_calls, len(lengths)), np.int32)
-    for s, n in enumerate(lengths):
-        left = valid_frame_count(n)
-        for k in range(n_calls):
-            l = min(max(n - k * chunk_samples, 0), chunk_samples)
-            f = 0 if l == 0 else (1 if l < WINDOW_LENGTH else 1 + (l - WINDOW_LENGTH) // HOP_LENGTH)
-            f = min(f, left)
-            left -= f
-            plan[k, s] = f
-    return plan
+    n = np.asarray([int(v) for v in lengths], np.int64)
+    n_calls = int(max(1, ((n + chunk_samples - 1) // chunk_samples).max())) if n.size else 0
+    k = np.arange(n_calls, dtype=np.int64)[:, None]
+    l = np.clip(n[None, :] - k * chunk_samples, 0, chunk_samples)                       # samples of call k, per stream
+    f = np.where(l == 0, 0, np.where(l < WINDOW_LENGTH, 1, 1 + (l - WINDOW_LENGTH) // HOP_LENGTH))
+    valid = np.where(n < WINDOW_LENGTH, 0, 1 + (n - WINDOW_LENGTH) // HOP_LENGTH)       # valid_frame_count per stream
+    before = np.cumsum(f, axis=0) - f
+    return np.clip(np.minimum(f, valid[None, :] - before), 0, None).astype(np.int32)
+
+
+class _StreamGraphRunner:
+    """Two captured steps (caches a -> b and b -> a) over static buffers for one (streams, chunk) shape: a 160 ms
+    step is ~30 small launches, so eager execution is bound by host launch cost; replay costs two copies and
+    one graph launch."""
+
+    def __init__(self, session, S, chunk_samples, device, post):
+        import torch
+        self.session, self.post = session, post
+        T = session.frames(chunk_samples)
+        self.chunk = torch.empty((S, chunk_samples), dtype=torch.int16, device=device)
+        self.out = torch.empty((S, 1, T), dtype=torch.float32, device=device)
+        self.n_frames = torch.zeros((S,), dtype=torch.int32, device=device)
+        self.caches = [session.new_caches(S, device), session.new_caches(S, device)]
+        self.graphs = [None, None]
+
+    def step(self, k: int):
+        """caches[k & 1] -> caches[1 - (k & 1)]"""
+        import torch
+        i = k & 1
+
+        def body():
+            self.session.run_batch(self.chunk, self.caches[i], out=self.out, caches_out=self.caches[1 - i])
+            self.post.feed(self.out[:, 0, :], self.n_frames)
+
+        if self.graphs[i] is None:
+            body()                                   # this step runs eagerly (constants, workspace) ...
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                # ... and is recorded (not executed) for the later ones
+                body()
+            self.graphs[i] = g
+        else:
+            self.graphs[i].replay()
 
 
 def run_stream_vad_streams(session: FireRedStreamSession, audio, lengths, chunk_samples: int = STREAM_CHUNK_SAMPLES,
-                           post: PP.StreamVadPostprocessor | None = None, caches=None, stream=None):
+                           post: PP.StreamVadPostprocessor | None = None, caches=None, stream=None, graph: bool = False):
     """S streams in lock-step: audio CUDA int16 [S, n_calls*chunk_samples] (zero-padded), `lengths` the true
     sample counts.  Per call: model forward with cache hand-over, then the streaming segmenter, all on the
-    device.  Returns (probs [S, n_calls*T] cuda, post, caches, plan)."""
+    device.  Returns (probs [S, n_calls*T] cuda, post, caches, plan).
+    graph=True replays each step as one CUDA graph (runner cached on the session; its post-processor and caches
+    are reset per call and returned -- read them before the next graph-mode call)."""
     import torch
+    if graph:
+        S, n = audio.shape
+        plan = stream_frame_plan(lengths, chunk_samples)
+        n_calls = plan.shape[0]
+        if n != n_calls * chunk_samples:
+            raise ValueError(f"run_stream_vad_streams: audio must be zero-padded to {n_calls * chunk_samples} samples, got {n}")
+        runners = session.__dict__.setdefault("_graph_runners", {})
+        key = (S, chunk_samples, str(audio.device))
+        r = runners.get(key)
+        if r is None:
+            p = PP.StreamVadPostprocessor(SMOOTH_WINDOW_SIZE, STREAM_VAD_THRESHOLD, PAD_START_FRAME, MIN_SPEECH_FRAME_STREAM,
+                                          MAX_SPEECH_FRAME_STREAM, MIN_SILENCE_FRAME_STREAM, n_streams=S, device=audio.device)
+            r = runners[key] = _StreamGraphRunner(session, S, chunk_samples, audio.device, p)
+        r.post.reset()
+        r.caches[0].zero_()
+        T = session.frames(chunk_samples)
+        d_plan = torch.from_numpy(plan).to(audio.device)
+        probs = torch.empty((S, n_calls, T), dtype=torch.float32, device=audio.device)
+        for k in range(n_calls):
+            r.chunk.copy_(audio[:, k * chunk_samples:(k + 1) * chunk_samples])
+            r.n_frames.copy_(d_plan[k])
+            r.step(k)
+            probs[:, k, :].copy_(r.out[:, 0, :])
+        return probs.reshape(S, n_calls * T), r.post, r.caches[n_calls & 1], plan
     S, n = audio.shape
     plan = stream_frame_plan(lengths, chunk_samples)
     n_calls = plan.shape[0]
