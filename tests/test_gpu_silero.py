@@ -109,6 +109,35 @@ def test_many_streams_batched(cuda, wts, session):
 
 def test_cuda_graph_replay_is_bit_identical(cuda, session):
     a = torch.from_numpy(synth.synth_streams(16, 512 * 20 + 5, seed=6)).float().to(cuda) * 0.000030517578
-    p0 = session.speech_probs(a)
+    old = session.MAX_ROWS_PER_CALL
+    try:
+        session.MAX_ROWS_PER_CALL = 16           # one window per call: the same kernels the captured step runs
+        p0 = session.speech_probs(a).clone()
+    finally:
+        session.MAX_ROWS_PER_CALL = old
     p1 = session.speech_probs_graph(a)
     assert torch.equal(p0, p1)
+    # the batched-windows path puts the same rows through the tensor-core kernels (16 streams per window stay on the
+    # exact-fp32 skinny path): equal within the tensor-core split error
+    assert (session.speech_probs(a) - p1).abs().max().item() <= 2e-4
+
+
+def test_window_blocks_equal_single_window_steps(cuda, session):
+    """The multi-window forward (state-free part batched over windows) against one forward per window, for a block
+    size that does not divide the window count."""
+    S, n = 33, 512 * 23 + 77
+    a = (torch.from_numpy(synth.synth_streams(S, n, seed=5)).float() * 0.000030517578).to(cuda)
+    old = session.MAX_ROWS_PER_CALL
+    try:
+        session.MAX_ROWS_PER_CALL = S            # one window per call: the per-window path
+        p1 = session.speech_probs(a).clone()
+        s1 = session._final_state.clone()
+        session.MAX_ROWS_PER_CALL = S * 5        # blocks of 5 windows (24 = 4 x 5 + 4)
+        p5 = session.speech_probs(a).clone()
+        s5 = session._final_state.clone()
+        session.MAX_ROWS_PER_CALL = old          # everything in one call
+        pa = session.speech_probs(a)
+    finally:
+        session.MAX_ROWS_PER_CALL = old
+    assert (p1 - p5).abs().max().item() <= 2e-6 and (p1 - pa).abs().max().item() <= 2e-6
+    assert (s1 - s5).abs().max().item() <= 1e-5

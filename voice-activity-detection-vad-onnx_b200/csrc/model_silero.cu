@@ -65,21 +65,30 @@ int silero_finalize(vadx_model* m) {
   return VADX_OK;
 }
 
+// "input.n_windows" = W > 1 (offline / batched use): in[0] rows are strided views of a long signal and the call
+// covers W consecutive windows of every stream.  Everything that does not depend on the LSTM state (reflect pad,
+// STFT, encoder, the input half of the gates) runs ONCE over S*W rows; only the recurrent half of the gates, the
+// cell and the head run per window (3 launches instead of 10).  out[0] is then [W][S][1], state in -> state out
+// spans all W windows.
 int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
                int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
   SileroHP h;
   VADX_TRY(silero_hp(m, &h));
+  const int W = std::max(1, (int)m->scalar("input.n_windows", 1.0));
+  const int64_t rows = S * W;
   const int nwin = h.n_in() + h.reflect;
   const int T = h.n_frames(), F = h.n_bins();
   int wide = 4 * h.hidden;
   for (auto& d : h.dims) wide = std::max(wide, d.first);  // only layer OUTPUTS live in the ping-pong buffers
   const int ldw = (int)round_up(wide, 4);
   Workspace ws(ws_ptr, ws_bytes, dry);
-  float* win = ws.take<float>(S * nwin);
-  float* mag = ws.take<float>(S * T * F + 4);
-  float* bufA = ws.take<float>(S * ldw);
-  float* bufB = ws.take<float>(S * ldw);
+  float* win = ws.take<float>(rows * nwin);
+  float* mag = ws.take<float>(rows * T * F + 4);
+  float* bufA = ws.take<float>(rows * ldw);
+  float* bufB = ws.take<float>(rows * ldw);
+  float* gates = ws.take<float>(S * ldw);
   float* hrelu = ws.take<float>(S * h.hidden);
+  float* tmp_state[2] = {W > 1 ? ws.take<float>(2 * S * h.hidden) : nullptr, W > 2 ? ws.take<float>(2 * S * h.hidden) : nullptr};
   if (need) *need = ws.off;
   if (dry) return VADX_OK;
   if (ws.off > ws_bytes) {
@@ -90,22 +99,26 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
                (long long)L);
   VADX_REQUIRE(state && state[0] && state[1] && state[0] != state[1], "silero: state in/out buffers are required");
   const int64_t in_stride = (int64_t)m->scalar("input.row_stride", (double)h.n_in());
-  VADX_REQUIRE(in_stride >= 1, "silero: bad input.row_stride");
+  VADX_REQUIRE(in_stride >= 1 && (W == 1 || in_stride >= (int64_t)(W - 1) * h.window + h.n_in()),
+               "silero: input.row_stride %lld does not hold %d windows", (long long)in_stride, W);
   const float* st_in = static_cast<const float*>(state[0]);
   float* st_out = static_cast<float*>(state[1]);
-  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && S > kSkinnyMaxRows;
-  auto lin = [&](const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, const float* res,
+  const bool tc_ok = m->scalar("engine.use_tc", 1.0) != 0.0;
+  auto lin = [&](int64_t n_rows, const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, const float* res,
                  int64_t ldr, float* y, int64_t ldy, int n_out, int act) -> int {
-    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
+    const uint8_t* img = tc_ok && n_rows > kSkinnyMaxRows ? m->d<uint8_t>(w + "#TC") : nullptr;
     const float* bias = b ? m->d<float>(b) : nullptr;
-    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, S, n_in, n_out, act, st);
-    return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, S, n_in,
+    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, st);
+    return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, n_rows, n_in,
                            n_out, act, st);
   };
-  VADX_TRY(vadx_reflect_window_f32(static_cast<const float*>(in[0]), in_stride, S, h.n_in(), h.reflect, win, st));
-  VADX_TRY(vadx_stft_power_f32(win, nwin, S, T, h.hop, h.n_fft, m->d<float>("frontend.basis"), h.ld_basis(), F, mag, F,
+  // rows are ordered [window][stream] so that one window's gates are contiguous for the recurrence
+  for (int w = 0; w < W; ++w)
+    VADX_TRY(vadx_reflect_window_f32(static_cast<const float*>(in[0]) + (int64_t)w * h.window, in_stride, S, h.n_in(),
+                                     h.reflect, win + (int64_t)w * S * nwin, st));
+  VADX_TRY(vadx_stft_power_f32(win, nwin, rows, T, h.hop, h.n_fft, m->d<float>("frontend.basis"), h.ld_basis(), F, mag, F,
                                st));
-  VADX_TRY(vadx_sqrt_inplace_f32(mag, S * (int64_t)T * F, st));
+  VADX_TRY(vadx_sqrt_inplace_f32(mag, rows * (int64_t)T * F, st));
   const float* cur = mag;
   int64_t ldc = (int64_t)T * F;
   float* pp[2] = {bufA, bufB};
@@ -113,19 +126,25 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
     std::string p = "enc." + std::to_string(i) + ".";
     std::string b = p + "bias";
     float* dst = pp[i & 1];
-    VADX_TRY(lin(cur, ldc, h.dims[i].second, p + "weight", b.c_str(), nullptr, 0, dst, ldw, h.dims[i].first,
+    VADX_TRY(lin(rows, cur, ldc, h.dims[i].second, p + "weight", b.c_str(), nullptr, 0, dst, ldw, h.dims[i].first,
                  VADX_ACT_RELU));
     cur = dst;
     ldc = ldw;
   }
   float* g1 = pp[h.n_layers & 1];
-  float* g2 = pp[(h.n_layers + 1) & 1];  // == buffer holding `cur`; safe: cur is consumed by the first GEMM
-  VADX_TRY(lin(cur, ldc, h.dims.back().first, "rnn.weight_ih", "rnn.bias", nullptr, 0, g1, ldw, 4 * h.hidden,
+  VADX_TRY(lin(rows, cur, ldc, h.dims.back().first, "rnn.weight_ih", "rnn.bias", nullptr, 0, g1, ldw, 4 * h.hidden,
                VADX_ACT_NONE));
-  VADX_TRY(lin(st_in, h.hidden, h.hidden, "rnn.weight_hh", nullptr, g1, ldw, g2, ldw, 4 * h.hidden, VADX_ACT_NONE));
   // gates rows have stride ldw; the cell kernel wants them dense [S][4H]: ldw == 4H whenever 4H is the widest layer
   VADX_REQUIRE(ldw == 4 * h.hidden, "silero: 4*hidden must be the widest layer (got ld %d)", ldw);
-  VADX_TRY(vadx_lstm_cell_f32(g2, st_in + S * h.hidden, st_out, st_out + S * h.hidden, hrelu, S, h.hidden, st));
-  return linear_narrow(hrelu, h.hidden, m->d<float>("head.weight#T"), 4, m->d<float>("head.bias"),
-                       static_cast<float*>(out[0]), S, h.hidden, 1, VADX_ACT_SIGMOID, 1, 1, 1, st);
+  float* probs = static_cast<float*>(out[0]);
+  for (int w = 0; w < W; ++w) {
+    const float* src = w == 0 ? st_in : tmp_state[(w - 1) & 1];
+    float* dst = w == W - 1 ? st_out : tmp_state[w & 1];
+    VADX_TRY(lin(S, src, h.hidden, h.hidden, "rnn.weight_hh", nullptr, g1 + (int64_t)w * S * ldw, ldw, gates, ldw, 4 * h.hidden,
+                 VADX_ACT_NONE));
+    VADX_TRY(vadx_lstm_cell_f32(gates, src + S * h.hidden, dst, dst + S * h.hidden, hrelu, S, h.hidden, st));
+    VADX_TRY(linear_narrow(hrelu, h.hidden, m->d<float>("head.weight#T"), 4, m->d<float>("head.bias"), probs + (int64_t)w * S, S,
+                           h.hidden, 1, VADX_ACT_SIGMOID, 1, 1, 1, st));
+  }
+  return VADX_OK;
 }

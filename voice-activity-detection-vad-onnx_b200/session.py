@@ -483,6 +483,8 @@ class SileroSession:
     ``speech_probs`` used by the batched entry point."""
     sample_rates = [16000]
 
+    MAX_ROWS_PER_CALL = 262144      # streams x windows handled by one batched forward (bounds the workspace)
+
     def __init__(self, weights: dict, cfg: W.SileroConfig = W.SileroConfig(), tensor_cores: bool = True):
         import torch
         self.cfg = cfg
@@ -665,9 +667,19 @@ class SileroSession:
             self._row_stride = stride
         n_in = c.window + c.context
         nxt = torch.empty_like(state)
-        for t in range(n_win):
-            self._e.forward([padded[:, t * c.window:]], [probs[t]], [state, nxt], S, n_in, stream)
-            state, nxt = nxt, state
+        # blocks of windows per call: the state-free part of the graph (STFT, encoder, input half of the gates)
+        # runs once over streams x windows rows, only the recurrence runs per window (input.n_windows)
+        block = max(1, min(n_win, self.MAX_ROWS_PER_CALL // max(S, 1)))
+        t = 0
+        try:
+            while t < n_win:
+                wb = min(block, n_win - t)
+                self._e.set_scalar("input.n_windows", float(wb))
+                self._e.forward([padded[:, t * c.window:]], [probs[t:t + wb]], [state, nxt], S, n_in, stream)
+                state, nxt = nxt, state
+                t += wb
+        finally:
+            self._e.set_scalar("input.n_windows", 1.0)
         self._final_state = state
         return probs[:, :, 0].transpose(0, 1).contiguous()
 
