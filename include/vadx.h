@@ -403,7 +403,11 @@ int vadx_output_frames(const vadx_model* m, int64_t n_samples, int32_t* out_fram
  *            (NVIDIA_Frame_VAD_Multilingual_MarbleNet/Export_NVIDIA_MarbleNet_VAD.py:444-457).
  *   silero:  inputs = {x fp32 [S][576] = 64-sample context + 512-sample window}; outputs = {out fp32 [S][1]};
  *            state = {state in fp32 [2][S][128], state out}; n_samples = 576
- *            (the 'input'/'state' -> 'output'/'stateN' contract of Silero/modeling_modified/utils_vad.py:114-123). */
+ *            (the 'input'/'state' -> 'output'/'stateN' contract of Silero/modeling_modified/utils_vad.py:114-123).
+ *            Scalars: "input.row_stride" (default 576: rows may be strided views of one long signal) and
+ *            "input.n_windows" = W (default 1): one call covers W consecutive 512-sample windows of every stream,
+ *            outputs[0] is then fp32 [W][S][1] and the state spans all W windows; everything that does not
+ *            depend on the LSTM state runs once over S*W rows, the recurrence runs per window. */
 int vadx_forward(vadx_model* m, const void* const* d_inputs, void* const* d_outputs, void* const* d_state,
                  int64_t n_streams, int64_t n_samples, void* d_workspace, size_t workspace_bytes,
                  void* stream);
