@@ -373,7 +373,7 @@ def gen_fsmn():
 
 
 # ------------------------------------------------------------------------------ MarbleNet
-def marblenet_reference(cfg, weights, optimized=True):
+def marblenet_reference(cfg, weights, optimized=True, in_sample_rate=16000):
     """The reference's OWN wrapper (+ its own BatchNorm folding) around the NeMo-shaped stand-in
     (oracle/marblenet.py) carrying our seeded weights."""
     from oracle import marblenet as OM
@@ -386,7 +386,7 @@ def marblenet_reference(cfg, weights, optimized=True):
     cls = ns["NVIDIA_VAD_Optimized"] if optimized else ns["NVIDIA_VAD_Reference"]
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        m = cls(net, custom_stft, cfg.n_fft, cfg.n_mels, 16000, cfg.pre_emphasis, 16000).eval()
+        m = cls(net, custom_stft, cfg.n_fft, cfg.n_mels, 16000, cfg.pre_emphasis, in_sample_rate).eval()
     return m
 
 
@@ -404,6 +404,24 @@ def marblenet_fake_session(cfg, weights):
         return [np.asarray(t.numpy()) for t in r]
 
     return RR.FakeSession(ins, outs, fn)
+
+
+def gen_marblenet_rates():
+    """IN_SAMPLE_RATE != 16000: the MarbleNet wrapper's in-graph linear resampler (BN-folded wrapper)."""
+    import vadx  # noqa: F401
+    from vadx import synth, weights as W
+    cfg = W.MarbleNetConfig()
+    w = W.marblenet_random_init(cfg, 0)
+    out = {}
+    for rate in (8000, 48000):
+        ref = marblenet_reference(cfg, w, optimized=True, in_sample_rate=rate)
+        a = synth.synth_streams(2, 2 * rate, seed=rate + 1)          # two seconds at the input rate
+        with torch.inference_mode():
+            r = [ref(torch.from_numpy(c).view(1, 1, -1)) for c in a]
+        out[f"r{rate}_active"] = np.stack([x[1].numpy()[0, :, 0] for x in r])
+        out[f"r{rate}_signal_len"] = np.array(int(r[0][2]))
+        print(rate, out[f"r{rate}_active"].shape, int(r[0][2]))
+    np.savez_compressed(os.path.join(GOLD, "marblenet_rates.npz"), **out)
 
 
 def gen_marblenet():
@@ -703,7 +721,7 @@ def gen_dfsmn_near():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_near.npz"), **out)
 
 
-GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "marblenet_rates": gen_marblenet_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 

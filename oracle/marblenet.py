@@ -117,8 +117,9 @@ class StandIn(nn.Module):
 class MarbleNetOracle:
     """Restated wrapper graph (NVIDIA_VAD_Reference.forward, :312-335) on the un-folded stand-in."""
 
-    def __init__(self, weights, cfg):
+    def __init__(self, weights, cfg, in_sample_rate: int = 16000):
         self.cfg = cfg
+        self.rate_scale = 1.0 / (in_sample_rate / 16000.0)   # in-graph resampler (:180-183, :308-330)
         self.net = StandIn(cfg, weights)
         for b in self.net.encoder.encoder:
             for l in b.mconv:
@@ -134,8 +135,13 @@ class MarbleNetOracle:
         """[S,L] int16 -> (score_silence [S,T',1], score_active [S,T',1], signal_len int)"""
         a = audio_i16 if torch.is_tensor(audio_i16) else torch.from_numpy(audio_i16)
         c = self.cfg
-        x = a.float() * float(1.0 / 32768.0)
+        x = a.float()
+        if self.rate_scale < 1.0:
+            x = torch.nn.functional.interpolate(x.unsqueeze(1), scale_factor=self.rate_scale, mode="linear", align_corners=False)[:, 0]
+        x = x * float(1.0 / 32768.0)
         x = torch.cat([x[:, :1], x[:, 1:] - c.pre_emphasis * x[:, :-1]], dim=1)
+        if self.rate_scale > 1.0:
+            x = torch.nn.functional.interpolate(x.unsqueeze(1), scale_factor=self.rate_scale, mode="linear", align_corners=False)[:, 0]
         p = fe.stft_power(x.unsqueeze(1), self.kernel, c.hop, center_pad=True)
         mel = (torch.matmul(self.bank.unsqueeze(0), p) + c.log_eps).log()
         enc, lens = self.net.encoder(([mel], torch.tensor([mel.shape[-1]] * a.shape[0], dtype=torch.long)))

@@ -96,3 +96,17 @@ def test_long_clips_batch_against_oracle(cuda, session):
     for s in range(4):
         ref = OP.frame_decisions(p[s], 3, 0.5, 10, 1000, 10, 3, 0)
         assert np.array_equal(dec[s].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("rate", [8000, 48000])
+def test_in_graph_resampler(cuda, golden_dir, rate):
+    """IN_SAMPLE_RATE != 16000: golden from the reference's BN-folded wrapper built with that rate."""
+    g = np.load(os.path.join(golden_dir, "marblenet_rates.npz"))
+    cfg = W.MarbleNetConfig()
+    sess = vadx.MarbleNetSession(W.marblenet_random_init(cfg, 0), cfg, in_sample_rate=rate)
+    a = synth.synth_streams(2, 2 * rate, seed=rate + 1)
+    sil, act, n = sess.run(None, {"audio": a[:, None, :]})
+    assert int(n[0]) == int(g[f"r{rate}_signal_len"])
+    err = np.abs(act[:, :, 0] - g[f"r{rate}_active"]).max()
+    print(f"marblenet in_sample_rate {rate}: max abs err {err:.2e}")
+    assert err <= TOL

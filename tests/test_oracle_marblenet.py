@@ -54,3 +54,17 @@ def test_vad_sample_script_record(gold, oracle, golden_dir):
     assert np.array_equal(dec, gold["sample_decisions"])
     seg = OP.segments_from_decisions(dec, 0.02, 0.025, len(audio) / 16000, False)
     assert np.array_equal(np.array(seg, np.float64).reshape(-1, 2), gold["sample_timestamps"])
+
+
+@pytest.mark.parametrize("rate", [8000, 48000])
+def test_in_graph_resampler(golden_dir, rate):
+    """IN_SAMPLE_RATE != 16000 (tests/golden/marblenet_rates.npz: the reference's BN-folded wrapper built with that rate)"""
+    from vadx import synth
+    from oracle.marblenet import MarbleNetOracle
+    g = np.load(os.path.join(golden_dir, "marblenet_rates.npz"))
+    cfg = W.MarbleNetConfig()
+    o = MarbleNetOracle(W.marblenet_random_init(cfg, 0), cfg, in_sample_rate=rate)
+    a = synth.synth_streams(2, 2 * rate, seed=rate + 1)
+    sil, act, n = o.forward(a)
+    assert n == int(g[f"r{rate}_signal_len"])
+    assert np.abs(act.numpy()[:, :, 0] - g[f"r{rate}_active"]).max() <= 1e-4

@@ -63,10 +63,17 @@ int marblenet_check(const vadx_model* m) {
   MarbleHP h;
   return marble_hp(m, &h);
 }
+// IN_SAMPLE_RATE != 16000 (Export_NVIDIA_MarbleNet_VAD.py:180-183): scale = 1 / (in_rate / 16000), the in-graph
+// linear resampler leaves floor(L * scale) samples at the model's 16 kHz
+static double marble_rate_scale(const vadx_model* m) {
+  const double in_rate = m->scalar("frontend.in_sample_rate", 16000.0);
+  return in_rate == 16000.0 ? 1.0 : 1.0 / (in_rate / 16000.0);
+}
 int marblenet_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
   MarbleHP h;
   VADX_TRY(marble_hp(m, &h));
-  *out = h.out_frames(n_samples);
+  const double sc = marble_rate_scale(m);
+  *out = h.out_frames(sc == 1.0 ? n_samples : vadx_resample_out_len(n_samples, sc));
   return VADX_OK;
 }
 
@@ -117,13 +124,17 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
   (void)state;
   MarbleHP h;
   VADX_TRY(marble_hp(m, &h));
+  const double rate_scale = marble_rate_scale(m);
+  const int64_t L_in = L;
+  if (rate_scale != 1.0) L = vadx_resample_out_len(L_in, rate_scale);   // from here on L counts 16 kHz samples
   const int T0 = h.stft_frames(L);
   const int Tout = h.out_frames(L);
   const int64_t rows0 = S * T0;
-  const int64_t Lp = round_up(h.pad_left() + L + h.n_taps(), 4);
+  const int64_t Lp = round_up(h.pad_left() + std::max(L, L_in) + h.n_taps(), 4);
   const int maxc = h.max_channels();
   Workspace ws(ws_ptr, ws_bytes, dry);
   float* sig = ws.take<float>(S * Lp);
+  float* sig2 = rate_scale == 1.0 ? nullptr : ws.take<float>(S * Lp);
   float* power = ws.take<float>(rows0 * h.ld_power());
   float* B[5];  // roles: 0 block input, 1 depthwise out, 2/3 pointwise ping-pong, 4 residual branch
   for (auto& b : B) b = ws.take<float>(rows0 * maxc);
@@ -142,7 +153,22 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
   const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
 
   const uint8_t* stft_img = use_tc && rows0 > kSkinnyMaxRows ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
-  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
+  if (rate_scale != 1.0) {
+    // in-graph resampler (Export_NVIDIA_MarbleNet_VAD.py:236-254): down before the scale + pre-emphasis conv, up after it
+    const int pre = preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0;
+    if (rate_scale < 1.0) {
+      VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L_in, L_in, 1.0f, 0, 0, 0.f, 0, sig2, Lp, st));
+      VADX_TRY(vadx_resample_linear_f32(sig2, Lp, L_in, S, rate_scale, sig, Lp, 0, st));
+      VADX_TRY(vadx_prep_audio(sig, VADX_DT_F32, S, L, Lp, 1.0f / 32768.0f, 0, pre, preemph, h.pad_left(), sig2, Lp, st));
+    } else {
+      VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L_in, L_in, 1.0f / 32768.0f, 0, pre, preemph, 0, sig, Lp, st));
+      cudaError_t e = cudaMemsetAsync(sig2, 0, (size_t)S * Lp * sizeof(float), st);   // centre pad around the resampled signal
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(marblenet centre pad)");
+      VADX_TRY(vadx_resample_linear_f32(sig, Lp, L_in, S, rate_scale, sig2, Lp, h.pad_left(), st));
+    }
+    VADX_TRY(vadx_stft_power_f32(sig2, Lp, S, T0, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
+                                 h.n_bins(), power, h.ld_power(), st));
+  } else if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
     // centre-padded framed DFT on the tensor cores straight from the int16 samples (zeros outside the clip)
     const std::string key = "frontend.dc#" + std::to_string((long long)L);
     const std::string k_lo = key + ".lo", k_hi = key + ".hi";

@@ -391,7 +391,8 @@ class MarbleNetSession:
     """
     MAX_STREAMS_PER_CALL = 32768
 
-    def __init__(self, weights: dict, cfg: W.MarbleNetConfig = W.MarbleNetConfig(), tensor_cores: bool = True):
+    def __init__(self, weights: dict, cfg: W.MarbleNetConfig = W.MarbleNetConfig(), tensor_cores: bool = True,
+                 in_sample_rate: int = 16000):
         self.cfg = cfg
         hp = [cfg.feat_in, len(cfg.blocks)]
         for b in cfg.blocks:
@@ -410,6 +411,9 @@ class MarbleNetSession:
         self._e.set_scalar("frontend.preemph", cfg.pre_emphasis)
         self._e.set_scalar("frontend.log_eps", cfg.log_eps)
         self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
+        # IN_SAMPLE_RATE != 16000: the wrapper's in-graph linear resampler (Export_NVIDIA_MarbleNet_VAD.py:180-183,236-254)
+        self.in_sample_rate = int(in_sample_rate)
+        self._e.set_scalar("frontend.in_sample_rate", float(self.in_sample_rate))
         spec = W.marblenet_spec(cfg)
         for name in spec:
             if name not in weights:
