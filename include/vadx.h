@@ -131,7 +131,15 @@ int vadx_stream_mean_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_sa
 int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
                               int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
                               int64_t ld_power, int pad_left, const float* d_mean_frac, const int32_t* d_mean_int,
-                              const float* d_dc_tables, int n_edge_lo, int t_edge_hi, void* stream);
+                              const float* d_dc_tables, int n_edge_lo, int t_edge_hi, float power_scale,
+                              int operand_format, void* stream);
+/* Operand format of a DFT basis image and of the samples the loaders build to match it: bf16 (the default of
+ * vadx_pack_stft_basis_tc) or fp16 -- fp16 makes the exact int16 split three half2 operations per pair of
+ * samples and gives the two-term basis 22 bits; it cannot carry the 17-bit mean-removed samples, and a scale
+ * such as 1/32768 must stay out of the basis (pass scale = 1 and power_scale = scale^2 to the kernel). */
+enum { VADX_TC_FMT_BF16 = 0, VADX_TC_FMT_F16 = 1 };
+int vadx_pack_stft_basis_tc_fmt(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph, double scale,
+                                int operand_format, void* h_img, size_t img_capacity, size_t* img_bytes);
 
 /* a3 -- triangular filterbank contraction + floor + ln.  The bank is passed in its sparse form:
  * filter m covers bins [start[m], start[m]+len[m]) with weights d_w[m*max_len + j].

@@ -57,7 +57,8 @@ def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):
 
 
 @pytest.mark.parametrize("S,L", [(5, 16000), (300, 16000), (3, 5000), (2, 400 + 160 * 7)])
-def test_stft_power_tc_from_int16(cuda, S, L):
+@pytest.mark.parametrize("fmt", [lib.TC_FMT_BF16, lib.TC_FMT_F16])
+def test_stft_power_tc_from_int16(cuda, S, L, fmt):
     """Tensor-core DFT straight from int16 (exact sample split, folded pre-emphasis, 3-term basis)
     against the oracle's conv-STFT of the pre-emphasised signal."""
     from vadx import tables
@@ -68,12 +69,12 @@ def test_stft_power_tc_from_int16(cuda, S, L):
     L8 = L // 8 * 8
     x = torch.from_numpy(synth.synth_streams(S, L8, seed=S + L))
     basis, first, nb = tables.interleaved_basis(400, 400, "povey", "v2")
-    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, 1.0)).to(cuda)
+    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, 1.0, fmt)).to(cuda)
     T = 1 + (L8 - 400) // 160
     out = torch.full((S * T, 202), float("nan"), device=cuda)
     xd = x.to(cuda)
-    lib.check(l.vadx_stft_power_tc_i16(xd.data_ptr(), L8, L8, S, T, 160, 400, img.data_ptr(), nb, out.data_ptr(), 202,
-                                       lib.stream_ptr()))
+    lib.check(l.vadx_stft_power_tc_i16_ex(xd.data_ptr(), L8, L8, S, T, 160, 400, img.data_ptr(), nb, out.data_ptr(), 202,
+                                          0, None, None, None, 0, T, 1.0, fmt, lib.stream_ptr()))
     torch.cuda.synchronize()
     y = F.conv1d(F.pad(x.float().unsqueeze(1), (1, 0)), torch.tensor([[[-0.97, 1.0]]]))
     ref = OF.stft_power(y.double().float(), OF.stft_kernel(400, 400, "povey", "v2"), 160, False)
@@ -81,7 +82,7 @@ def test_stft_power_tc_from_int16(cuda, S, L):
     got = out[:, :nb].cpu()
     assert not torch.isnan(got).any()
     rel = ((got - ref).abs() / ref.max(dim=1, keepdim=True).values).max().item()
-    print(f"stft tc S={S} L={L8}: max err relative to the frame's strongest bin {rel:.2e}")
+    print(f"stft tc fmt={fmt} S={S} L={L8}: max err relative to the frame's strongest bin {rel:.2e}")
     # tensor-core fp32 accumulation truncates (chains of ~130 adds): ~1e-5 of the strongest bin
     assert rel <= 3e-5
 
@@ -111,10 +112,12 @@ def test_stft_power_tc_centre_padded_frontends(cuda, mode, S, L):
     ref = torch.zeros((S * T, 258), device=cuda)
     lib.check(l.vadx_stft_power_f32(sig.data_ptr(), Lp, S, T, hop, win, bd.data_ptr(), basis.shape[1], nb, ref.data_ptr(), 258,
                                     lib.stream_ptr()))
-    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, scale)).to(cuda)
+    # FSMN: bf16 operands (17-bit mean-removed samples); MarbleNet: fp16 operands, the 1/32768 kept out of the basis
+    fmt = lib.TC_FMT_BF16 if mode == "fsmn" else lib.TC_FMT_F16
+    img = torch.from_numpy(lib.pack_stft_basis_tc(basis, nb, 0.97, 1.0, fmt)).to(cuda)
     out = torch.full((S * T, 258), float("nan"), device=cuda)
     mean = None
-    t, lo, hi = lib.pack_stft_dc_tc(basis, nb, 0.97, scale, L, hop, pad_left, T)
+    t, lo, hi = lib.pack_stft_dc_tc(basis, nb, 0.97, 1.0, L, hop, pad_left, T)
     tab = torch.from_numpy(t).to(cuda)
     assert lo >= 1 and hi <= T - 1
     mean_i = None
@@ -125,7 +128,7 @@ def test_stft_power_tc_centre_padded_frontends(cuda, mode, S, L):
         assert (tot - torch.from_numpy(x.astype(np.float64).mean(1))).abs().max().item() <= 1e-6
         assert mean.abs().max().item() <= 0.5
     lib.check(l.vadx_stft_power_tc_i16_ex(xd.data_ptr(), L, L, S, T, hop, win, img.data_ptr(), nb, out.data_ptr(), 258,
-                                          pad_left, lib.ptr(mean), lib.ptr(mean_i), lib.ptr(tab), lo, hi, lib.stream_ptr()))
+                                          pad_left, lib.ptr(mean), lib.ptr(mean_i), lib.ptr(tab), lo, hi, scale * scale, fmt, lib.stream_ptr()))
     torch.cuda.synchronize()
     got, want = out[:, :nb].cpu(), ref[:, :nb].cpu()
     assert not torch.isnan(got).any()

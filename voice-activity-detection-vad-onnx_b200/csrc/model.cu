@@ -45,13 +45,14 @@ int firered_finalize(vadx_model* m) {
     m->scalars["derived.bins_used"] = bins_used;
   }
   if (vadx_stft_tc_supported(h.n_taps(), bins_used)) {
-    // tensor-core DFT image: pre-emphasis folded into the 2-term bf16 basis (stft_tc.cu)
+    // tensor-core DFT image: pre-emphasis folded into the 2-term fp16 basis (stft_tc.cu)
     const double preemph = m->scalar("frontend.preemph", 0.97);
     size_t bytes = 0;
     const float* hb = m->find("frontend.basis")->f32();
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, nullptr, 0, &bytes));
+    VADX_TRY(vadx_pack_stft_basis_tc_fmt(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, VADX_TC_FMT_F16, nullptr, 0, &bytes));
     std::vector<uint8_t> img(bytes);
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, img.data(), img.size(), &bytes));
+    VADX_TRY(vadx_pack_stft_basis_tc_fmt(hb, h.ld_basis(), h.n_taps(), bins_used, preemph, 1.0, VADX_TC_FMT_F16, img.data(),
+                                         img.size(), &bytes));
     VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
   }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
@@ -209,7 +210,8 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                                    nb_used, power, h.ld_power(), st));
     } else if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && aligned16(d_audio)) {
       // int16 audio -> power in one tensor-core kernel (exact sample split, folded pre-emphasis)
-      VADX_TRY(vadx_stft_power_tc_i16(d_audio, L, L, S, T, h.hop, h.n_taps(), stft_img, nb_used, power, h.ld_power(), st));
+      VADX_TRY(vadx_stft_power_tc_i16_ex(d_audio, L, L, S, T, h.hop, h.n_taps(), stft_img, nb_used, power, h.ld_power(), 0,
+                                         nullptr, nullptr, nullptr, 0, T, 1.0f, VADX_TC_FMT_F16, st));
     } else {
       VADX_TRY(vadx_prep_audio(d_audio, VADX_DT_I16, S, L, L, 1.0f, 0, preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0,
                                preemph, 0, sig, Lp, st));

@@ -166,7 +166,8 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
     VADX_TRY(vadx_stream_mean_i16(static_cast<const int16_t*>(in[0]), L, L, S, mean_ws, mean_int_ws, st));
     VADX_TRY(vadx_stft_power_tc_i16_ex(static_cast<const int16_t*>(in[0]), L, L, S, T, h.hop, h.n_taps(), stft_img, h.n_bins(),
                                        power, h.ld_power(), h.pad_left(), mean_ws, mean_int_ws, m->d<float>(key),
-                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T), st));
+                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T), 1.0f,
+                                       VADX_TC_FMT_BF16, st));
   } else {
     VADX_TRY(vadx_stft_power_f32(sig, Lp, S, T, h.hop, h.n_taps(), m->d<float>("frontend.basis"), h.ld_basis(),
                                  h.n_bins(), power, h.ld_power(), st));

@@ -82,14 +82,16 @@ int marblenet_finalize(vadx_model* m) {
   VADX_TRY(marble_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_taps() * h.ld_basis(), VADX_DT_F32));
   if (vadx_stft_tc_supported(h.n_taps(), h.n_bins())) {
-    // tensor-core DFT image: 1/32768 and the pre-emphasis folded into the 2-term bf16 basis
+    // tensor-core DFT image: the pre-emphasis folded into the 2-term basis
     const double preemph = m->scalar("frontend.preemph", 0.97);
     const float* hb = m->find("frontend.basis")->f32();
     size_t bytes = 0;
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, nullptr, 0, &bytes));
+    // fp16 operands; the 1/32768 stays out of the basis (fp16 range) and multiplies the power instead
+    VADX_TRY(vadx_pack_stft_basis_tc_fmt(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, VADX_TC_FMT_F16, nullptr, 0,
+                                         &bytes));
     std::vector<uint8_t> img(bytes);
-    VADX_TRY(vadx_pack_stft_basis_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, img.data(), img.size(),
-                                     &bytes));
+    VADX_TRY(vadx_pack_stft_basis_tc_fmt(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, VADX_TC_FMT_F16, img.data(),
+                                         img.size(), &bytes));
     VADX_TRY(m->upload("frontend.basis#TC", img.data(), img.size()));
   }
   VADX_TRY(m->upload_raw("frontend.mel_start", h.n_mels, VADX_DT_I32));
@@ -176,10 +178,10 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
       size_t n = 0;
       int lo = 0, hi = 0;
       const float* hb = m->find("frontend.basis")->f32();
-      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, L, h.hop, h.pad_left(), T0,
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, L, h.hop, h.pad_left(), T0,
                                     nullptr, 0, &n, &lo, &hi));
       std::vector<float> tab(n);
-      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0 / 32768.0, L, h.hop, h.pad_left(), T0,
+      VADX_TRY(vadx_pack_stft_dc_tc(hb, h.ld_basis(), h.n_taps(), h.n_bins(), preemph, 1.0, L, h.hop, h.pad_left(), T0,
                                     tab.data(), tab.size(), &n, &lo, &hi));
       VADX_TRY(m->upload(key, tab.data(), tab.size() * sizeof(float)));
       m->scalars[k_lo] = lo;
@@ -187,7 +189,8 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
     }
     VADX_TRY(vadx_stft_power_tc_i16_ex(static_cast<const int16_t*>(in[0]), L, L, S, T0, h.hop, h.n_taps(), stft_img, h.n_bins(),
                                        power, h.ld_power(), h.pad_left(), nullptr, nullptr, m->d<float>(key),
-                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T0), st));
+                                       (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T0),
+                                       (float)(1.0 / (32768.0 * 32768.0)), VADX_TC_FMT_F16, st));
   } else {
     VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 0,
                              preemph > 0.f ? VADX_PREEMPH_ZERO_HISTORY : 0, preemph, h.pad_left(), sig, Lp, st));

@@ -51,6 +51,7 @@ struct StftTcArgs {
                          // coefficient pattern -- row 0 for interior frames, one row per frame that touches the zero
                          // pad -- then one tail row per frame that runs past the end of the stream
   int n_edge_lo, t_edge_hi;   // frames t < n_edge_lo and t >= t_edge_hi are edge frames
+  float power_scale;     // multiplies re^2 + im^2 (a scale kept out of an fp16 basis, e.g. (1/32768)^2)
   int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
@@ -72,6 +73,23 @@ __device__ __forceinline__ uint32_t bf16x2_hi(uint32_t w) {
   return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
 }
 
+// fp16 operands: the same exact split in three half2 operations per pair of samples.  as_half(0x6400 | v) is
+// 1024 + v for 0 <= v < 1024, so (w & 0x00ff00ff) | 0x64006400 minus 1024 is the pair of low bytes, and the
+// sign-flipped high bytes minus (1024 + 128), times 256, is the pair 256 * (x >> 8) (|.| <= 32768 fits fp16).
+__device__ __forceinline__ uint32_t f16x2_lo(uint32_t w) {
+  const uint32_t m = (w & 0x00ff00ffu) | 0x64006400u;
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(0x64006400u));
+  return r;
+}
+__device__ __forceinline__ uint32_t f16x2_hi(uint32_t w) {
+  const uint32_t m = (((w >> 8) & 0x00ff00ffu) ^ 0x00800080u) | 0x64006400u;
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(0x64806480u));      // 1024 + 128
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x5c005c00u));      // x 256
+  return r;
+}
+
 // same trick for a sample with an integer offset removed: d in [-65535, 65535] -> (256 * (d >> 8), d & 255)
 __device__ __forceinline__ void split17(int d, float& hi, float& lo) {
   lo = __uint_as_float(0x4B000000u | (uint32_t)(d & 255)) - 8388608.0f;
@@ -80,7 +98,8 @@ __device__ __forceinline__ void split17(int d, float& hi, float& lo) {
 }
 
 // EX = false: every frame inside the stream, no DC removal (FireRed) -- the padded / mean-removing code is compiled out
-template <bool EX>
+// F16 = true: fp16 operands (cheaper exact conversion; not with the 17-bit mean-removed samples)
+template <bool EX, bool F16>
 __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const StftTcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* w_smem = smem_raw;
@@ -129,7 +148,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       const uint8_t* src = g.Wimg + (size_t)ntile * w_bytes;
       for (int t = 0; t < g.kc * kStTerms; ++t) bulk_g2s(smem_u32(w_smem) + t * img_bytes, src + (size_t)t * img_bytes, img_bytes, wbar);
       mbar_wait(wbar, 0);
-      const uint32_t idesc = umma_idesc_bf16(kStNPad);
+      const uint32_t idesc = F16 ? umma_idesc_f16(kStNPad) : umma_idesc_bf16(kStNPad);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -264,8 +283,8 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t w = live ? wds[j] : 0u;
-          hi[j] = bf16x2_hi(w);
-          lo[j] = bf16x2_lo(w);
+          hi[j] = F16 ? f16x2_hi(w) : bf16x2_hi(w);
+          lo[j] = F16 ? f16x2_lo(w) : bf16x2_lo(w);
         }
         }
         const int off = r * 128 + ((kq ^ (r & 7)) << 4);
@@ -342,7 +361,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         float* out = g.P + row * g.ldp + f0 + c0 / 2;
         float pw[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pw[j] = v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+        for (int j = 0; j < 8; ++j) pw[j] = (v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1]) * g.power_scale;
         const int fb = f0 + c0 / 2;
         if (g.vec_p && fb + 7 < g.n_bins) {
           reinterpret_cast<float4*>(out)[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
@@ -395,8 +414,18 @@ extern "C" int vadx_stft_tc_supported(int n_taps, int n_bins) { return stft_tc_s
 // serves both halves of the sample.
 extern "C" int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph,
                                        double scale, void* h_img, size_t img_capacity, size_t* img_bytes) {
+  return vadx_pack_stft_basis_tc_fmt(h_basis, ld_basis, n_taps, n_bins, preemph, scale, VADX_TC_FMT_BF16, h_img, img_capacity,
+                                     img_bytes);
+}
+
+extern "C" int vadx_pack_stft_basis_tc_fmt(const float* h_basis, int ld_basis, int n_taps, int n_bins, double preemph,
+                                           double scale, int operand_format, void* h_img, size_t img_capacity,
+                                           size_t* img_bytes) {
   VADX_REQUIRE(h_basis && img_bytes && n_taps > 0 && n_bins > 0 && ld_basis >= 2 * n_bins,
                "vadx_pack_stft_basis_tc: bad argument");
+  VADX_REQUIRE(operand_format == VADX_TC_FMT_BF16 || operand_format == VADX_TC_FMT_F16, "vadx_pack_stft_basis_tc: operand format %d",
+               operand_format);
+  const bool f16 = operand_format == VADX_TC_FMT_F16;
   StftTcShape s = stft_tc_shape(n_taps, n_bins);
   VADX_REQUIRE(s.ok, "vadx_pack_stft_basis_tc: %d taps x %d bins does not fit the tensor-core DFT", n_taps, n_bins);
   *img_bytes = s.img_bytes;
@@ -415,9 +444,9 @@ extern "C" int vadx_pack_stft_basis_tc(const float* h_basis, int ld_basis, int n
       if (n1 >= 0 && n1 < n_taps) v -= preemph * (double)h_basis[(size_t)n1 * ld_basis + col];
       v *= scale;
       const float f = (float)v;
-      const uint16_t b0 = bf16_rn_host(f);
-      const float r1 = (float)(v - (double)bf16_to_f_host(b0));
-      const uint16_t b1 = bf16_rn_host(r1);
+      const uint16_t b0 = f16 ? f16_rn_host(f) : bf16_rn_host(f);
+      const float r1 = (float)(v - (double)(f16 ? f16_to_f_host(b0) : bf16_to_f_host(b0)));
+      const uint16_t b1 = f16 ? f16_rn_host(r1) : bf16_rn_host(r1);
       const int c = k / kTcBK, kk = k % kTcBK;
       uint8_t* base = img + (size_t)nt * s.tile_bytes + (size_t)(c * kStTerms) * term + sw128_offset(r, kk);
       memcpy(base, &b0, 2);
@@ -516,14 +545,17 @@ extern "C" int vadx_stft_power_tc_i16(const int16_t* d_audio, int64_t in_stride,
   VADX_REQUIRE((int64_t)(n_frames - 1) * hop + n_taps <= n_samples,
                "vadx_stft_power_tc_i16: frames must lie inside the %lld samples of a stream", (long long)n_samples);
   return vadx_stft_power_tc_i16_ex(d_audio, in_stride, n_samples, n_streams, n_frames, hop, n_taps, d_img, n_bins, d_power,
-                                   ld_power, 0, nullptr, nullptr, nullptr, 0, n_frames, stream);
+                                   ld_power, 0, nullptr, nullptr, nullptr, 0, n_frames, 1.0f, VADX_TC_FMT_BF16, stream);
 }
 
 extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
                                          int n_frames, int hop, int n_taps, const void* d_img, int n_bins, float* d_power,
                                          int64_t ld_power, int pad_left, const float* d_mean_frac, const int32_t* d_mean_int,
-                                         const float* d_dc_tables, int n_edge_lo, int t_edge_hi, void* stream) {
+                                         const float* d_dc_tables, int n_edge_lo, int t_edge_hi, float power_scale,
+                                         int operand_format, void* stream) {
   const float* d_mean = d_mean_frac;
+  VADX_REQUIRE(operand_format == VADX_TC_FMT_BF16 || (operand_format == VADX_TC_FMT_F16 && !d_mean_frac),
+               "vadx_stft_power_tc_i16: fp16 operands cannot carry the mean-removed (17-bit) samples");
   VADX_REQUIRE((d_mean_frac == nullptr) == (d_mean_int == nullptr), "vadx_stft_power_tc_i16: mean needs both its parts");
   StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
   VADX_REQUIRE(d_audio && d_img && d_power, "vadx_stft_power_tc_i16: null pointer");
@@ -545,9 +577,13 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stft_power_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+      e = cudaFuncSetAttribute(stft_power_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stft_power_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stft_power_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_power_tc_kernel)");
     configured = true;
   }
@@ -555,7 +591,7 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   g.X = d_audio; g.in_stride = in_stride; g.L = n_samples; g.n_frames = n_frames; g.hop = hop;
   g.Wimg = static_cast<const uint8_t*>(d_img); g.P = d_power; g.ldp = ld_power; g.M = n_streams * n_frames;
   g.n_bins = n_bins; g.kc = s.kc; g.n_k16 = s.n_k16;
-  g.pad_left = pad_left; g.mean = d_mean; g.mean_int = d_mean_int; g.dc = d_dc_tables; g.n_edge_lo = n_edge_lo; g.t_edge_hi = t_edge_hi;
+  g.pad_left = pad_left; g.mean = d_mean; g.mean_int = d_mean_int; g.dc = d_dc_tables; g.power_scale = power_scale; g.n_edge_lo = n_edge_lo; g.t_edge_hi = t_edge_hi;
   g.vec_p = ((ld_power & 3) == 0) && aligned16(d_power);
   {
     static int dbg = -1;
@@ -570,9 +606,10 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   g.n_tiles = (int)tiles;
   int per = std::max(1, (n_sm > 0 ? n_sm : 148) / s.n_ntiles);
   dim3 grid((unsigned)std::min<int64_t>(tiles, per), (unsigned)s.n_ntiles);
-  if (leaves_stream || d_mean)
-    stft_power_tc_kernel<true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
-  else
-    stft_power_tc_kernel<false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  const bool ex = leaves_stream || d_mean, f16 = operand_format == VADX_TC_FMT_F16;
+  if (ex && f16) stft_power_tc_kernel<true, true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  else if (ex) stft_power_tc_kernel<true, false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  else if (f16) stft_power_tc_kernel<false, true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  else stft_power_tc_kernel<false, false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
   return after_launch("vadx_stft_power_tc_i16");
 }

@@ -64,6 +64,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
+// kind::f16, A = B = fp16, D = fp32
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -122,6 +126,45 @@ static inline uint16_t bf16_rn_host(float f) {
 static inline float bf16_to_f_host(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// IEEE half, round to nearest even (subnormals included)
+static inline uint16_t f16_rn_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const int32_t exp = (int32_t)((u >> 23) & 0xffu) - 127 + 15;
+  uint32_t man = u & 0x7fffffu;
+  if (((u >> 23) & 0xffu) == 0xffu) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0u));
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    man |= 0x800000u;
+    const int shift = 14 - exp;                       // 14..24
+    uint32_t h = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+  const uint32_t rem = man & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;   // may carry into the exponent: still correct
+  return (uint16_t)(sign | h);
+}
+static inline float f16_to_f_host(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+  float f;
+  if (exp == 0) {
+    f = ldexpf((float)man, -24);
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u |= sign;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  const uint32_t u = exp == 31 ? (sign | 0x7f800000u | (man << 13)) : (sign | ((exp - 15 + 127) << 23) | (man << 13));
   memcpy(&f, &u, 4);
   return f;
 }

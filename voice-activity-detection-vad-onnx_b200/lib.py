@@ -50,7 +50,8 @@ SIGNATURES = {
                                        C.POINTER(_sz), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vadx_stream_mean_i16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "vadx_stft_power_tc_i16_ex": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp,
-                                            _i32, _i32, _vp]),
+                                            _i32, _i32, _f32, _i32, _vp]),
+    "vadx_pack_stft_basis_tc_fmt": (C.c_int, [_vp, _i32, _i32, _i32, C.c_double, C.c_double, _i32, _vp, _sz, C.POINTER(_sz)]),
     "vadx_mel_log_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _i64, _vp]),
     "vadx_linear_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_tc_supported": (C.c_int, [_i32, _i32]),
@@ -163,16 +164,20 @@ def pack_weight_tc(w):
     return img
 
 
-def pack_stft_basis_tc(basis, n_bins: int, preemph: float, scale: float):
-    """[n_taps, ld] fp32 interleaved basis table -> uint8 operand image for vadx_stft_power_tc_i16."""
+TC_FMT_BF16, TC_FMT_F16 = 0, 1
+
+
+def pack_stft_basis_tc(basis, n_bins: int, preemph: float, scale: float, fmt: int = TC_FMT_BF16):
+    """[n_taps, ld] fp32 interleaved basis table -> uint8 operand image for vadx_stft_power_tc_i16(_ex)."""
     import numpy as np
     basis = np.ascontiguousarray(basis, np.float32)
     n_taps, ld = basis.shape
     nbytes = C.c_size_t()
-    check(load().vadx_pack_stft_basis_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, None, 0, C.byref(nbytes)))
+    check(load().vadx_pack_stft_basis_tc_fmt(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, fmt, None, 0,
+                                             C.byref(nbytes)))
     img = np.zeros(nbytes.value, np.uint8)
-    check(load().vadx_pack_stft_basis_tc(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, img.ctypes.data,
-                                         img.nbytes, C.byref(nbytes)))
+    check(load().vadx_pack_stft_basis_tc_fmt(basis.ctypes.data, ld, n_taps, n_bins, preemph, scale, fmt, img.ctypes.data,
+                                             img.nbytes, C.byref(nbytes)))
     return img
 
 
