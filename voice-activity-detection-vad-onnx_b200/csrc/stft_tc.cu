@@ -296,20 +296,25 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == kStStages) { stage = 0; phase ^= 1u; }
     };
-    uint4 b0[kPasses], b1[kPasses], b2[kPasses];
-    uint32_t m0 = 0, m1 = 0, m2 = 0;   // validity masks of the buffered samples (8 bits per pass)
+    // kStBufs register buffers rotate: the loads of kStBufs - 1 stages are in flight while one is converted
+    // (the padded / mean-removing variant carries more live state per thread and keeps one buffer fewer)
+    constexpr int kStBufs = EX ? 4 : 5;
+    uint4 bufs[kStBufs][kPasses];
+    uint32_t msks[kStBufs];
+#pragma unroll
+    for (int i = 0; i < kStBufs; ++i) msks[i] = 0u;
     Seq nxt{(int)blockIdx.x, 0}, cur{(int)blockIdx.x, 0};
-    if (valid(nxt)) { issue(nxt, b0, m0); advance(nxt); }
-    if (valid(nxt)) { issue(nxt, b1, m1); advance(nxt); }
+#pragma unroll
+    for (int i = 0; i < kStBufs - 1; ++i)
+      if (valid(nxt)) { issue(nxt, bufs[i], msks[i]); advance(nxt); }
     while (valid(cur)) {
-      if (valid(nxt)) { issue(nxt, b2, m2); advance(nxt); }
-      consume(cur, b0, m0); advance(cur);
-      if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b0, m0); advance(nxt); }
-      consume(cur, b1, m1); advance(cur);
-      if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b1, m1); advance(nxt); }
-      consume(cur, b2, m2); advance(cur);
+#pragma unroll
+      for (int i = 0; i < kStBufs; ++i) {
+        constexpr int kPrev = kStBufs - 1;
+        if (valid(nxt)) { issue(nxt, bufs[(i + kPrev) % kStBufs], msks[(i + kPrev) % kStBufs]); advance(nxt); }
+        consume(cur, bufs[i], msks[i]); advance(cur);
+        if (!valid(cur)) break;
+      }
     }
   } else {
     // ===================== epilogue: re^2 + im^2 =====================
