@@ -181,11 +181,13 @@ __global__ void __launch_bounds__(4 * H * NSEQ) lstm_seq_gates_kernel(const Lstm
   __syncthreads();
   for (int step = 0; step < a.L; ++step) {
     const int t = a.reverse ? a.L - 1 - step : step;
-    float acc = bias;
+    // four independent partial sums: the (IN + H)-long dependent FMA chain is the latency of a step
+    float a4[4] = {bias, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < IN; ++k) acc = fmaf(wi[k], xs[ql][k], acc);
+    for (int k = 0; k < IN; ++k) a4[k & 3] = fmaf(wi[k], xs[ql][k], a4[k & 3]);
 #pragma unroll
-    for (int k = 0; k < H; ++k) acc = fmaf(wh[k], hs[ql][k], acc);
+    for (int k = 0; k < H; ++k) a4[(IN + k) & 3] = fmaf(wh[k], hs[ql][k], a4[(IN + k) & 3]);
+    const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     gs[ql][g] = acc;
     __syncthreads();
     if (g < H) {
