@@ -170,3 +170,15 @@ def test_resample_linear_kernel_matches_torch(cuda):
         lib.check(L.vadx_resample_linear_f32(d.data_ptr(), n_in, n_in, 3, scale, out.data_ptr(), n_out + 5, 2, None))
         assert (out[:, 2:2 + n_out].cpu() - ref).abs().max().item() <= 1e-6
         assert out[:, :2].abs().max().item() == 0 and out[:, 2 + n_out:].abs().max().item() == 0
+
+
+def test_opt_in_fused_block_path_matches_default(cuda):
+    """engine.fuse_block = 1 routes fc2 + memory block through block_tc.cu: same probabilities as the default path."""
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, 0)
+    d = torch.from_numpy(synth.synth_chunks_fast(70, 16000, seed=4)).to(cuda)
+    a = vadx.FireRedSession(w, cfg)
+    b = vadx.FireRedSession(w, cfg)
+    b._e.set_scalar("engine.fuse_block", 1.0)
+    pa, pb = a.run_batch(d), b.run_batch(d)
+    assert (pa - pb).abs().max().item() <= 2e-5

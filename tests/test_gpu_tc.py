@@ -158,3 +158,52 @@ def test_firered_tc_vs_simt_and_oracle(cuda):
     print(f"FireRed max abs prob err vs oracle: tensor-core {e_tc:.3e}, fp32 SIMT {e_simt:.3e}")
     assert e_tc <= 1e-3 and e_simt <= 1e-3
     assert np.abs(p_tc - p_simt).max() <= 1e-3
+
+
+@pytest.mark.parametrize("T,n2,with_res,act,S,K", [(98, 20, True, 0, 333, 256), (98, 20, False, 1, 150, 256), (98, 0, True, 0, 40, 256),
+                                                 (57, 20, True, 1, 64, 256), (2, 20, True, 0, 5, 256), (113, 0, False, 0, 9, 128),
+                                                 (98, 20, True, 0, 1, 200)])
+def test_fused_dense_plus_memory_block(cuda, T, n2, with_res, act, S, K):
+    """fc2 + memory block in one kernel against the two-kernel composition (tensor-core dense layer, then the memory
+    kernel) through the C ABI, and against float64."""
+    import torch.nn.functional as F
+    l = lib.load()
+    C, n1 = 128, 20
+    assert l.vadx_fc2_memory_tc_supported(K, C, T, n1, 1, n2, 1) == 1
+    g = torch.Generator().manual_seed(T * 31 + n2 + S + K)
+    x = torch.randn((S * T, K), generator=g)
+    w = torch.randn((C, K), generator=g) / K ** 0.5
+    b = torch.randn((C,), generator=g) * 0.1
+    wl = torch.randn((C, n1), generator=g) * 0.2
+    wr = torch.randn((C, max(n2, 1)), generator=g) * 0.2
+    res = torch.randn((S * T, C), generator=g) if with_res else None
+    img = torch.from_numpy(lib.pack_weight_tc(w.numpy())).to(cuda)
+    d = {k: (v.to(cuda) if v is not None else None) for k, v in dict(x=x, b=b, wl=wl, wr=wr, res=res).items()}
+    out = torch.full((S * T, C), float("nan"), device=cuda)
+    lib.check(l.vadx_fc2_memory_tc_f32(d["x"].data_ptr(), K, img.data_ptr(), d["b"].data_ptr(), act, d["wl"].data_ptr(), n1,
+                                       d["wr"].data_ptr() if n2 else None, n2, lib.ptr(d["res"]), out.data_ptr(), S, T, K,
+                                       lib.stream_ptr()))
+    # two-kernel composition
+    p = torch.empty((S * T, C), device=cuda)
+    lib.check(l.vadx_linear_tc_f32(d["x"].data_ptr(), K, img.data_ptr(), d["b"].data_ptr(), None, 0, p.data_ptr(), C, S * T, K, C,
+                                   act, lib.stream_ptr()))
+    two = torch.empty((S * T, C), device=cuda)
+    lib.check(l.vadx_fsmn_memory_f32(p.data_ptr(), C, d["wl"].data_ptr(), n1, 1, d["wr"].data_ptr() if n2 else None, n2, 1,
+                                     lib.ptr(d["res"]), C, two.data_ptr(), C, S, T, C, None, None, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert (out - two).abs().max().item() <= 1e-5
+    # float64
+    pr = x.double() @ w.double().t() + b.double()
+    if act == 1:
+        pr = torch.relu(pr)
+    xr = pr.reshape(S, T, C).permute(0, 2, 1)
+    ref = xr + F.conv1d(F.pad(xr, (n1 - 1, 0)), wl.double().unsqueeze(1), groups=C)
+    if n2 > 0 and T > 1:
+        ref = ref + F.conv1d(F.pad(xr, (0, n2)), wr.double().unsqueeze(1), groups=C)[:, :, 1:]
+    ref = ref.permute(0, 2, 1).reshape(S * T, C)
+    if with_res:
+        ref = ref + res.double()
+    err = (out.cpu().double() - ref).abs().max().item()
+    print(f"fused block T={T} n2={n2} S={S} K={K}: max abs err vs float64 {err:.2e}")
+    assert err <= 5e-4

@@ -243,15 +243,30 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                                   cin ? cin + layer * cache_layer : nullptr, cin ? cout + layer * cache_layer : nullptr,
                                   st);
     };
+    // second dense layer + memory block (+ residual) of every DFSMN block in one kernel when a chunk is one row tile
+    // (block_tc.cu): p never reaches HBM.  Opt-in ("engine.fuse_block" = 1): correct, but on B200 the FIR phase on
+    // the few warps the register file leaves next to the loaders is slower than the two streaming kernels
+    // (8192 chunks: 10.8 ms with a dedicated MMA warp / 18.7 ms in the 12-warp layout vs 8.97 ms unfused).
+    const bool fuse_block = use_tc && !cin && m->scalar("engine.fuse_block", 0.0) != 0.0 &&
+                            vadx_fc2_memory_tc_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1);
+    auto block_tail = [&](const std::string& w, const char* b, int act, const std::string& mem_pre, int layer, const float* res,
+                          float* o) -> int {
+      const uint8_t* img = fuse_block ? m->d<uint8_t>(w + "#TC") : nullptr;
+      if (img)
+        return vadx_fc2_memory_tc_f32(bufH, h.H, img, b ? m->d<float>(b) : nullptr, act,
+                                      m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,
+                                      h.N2 > 0 ? m->d<float>(mem_pre + "lookahead_filter.weight") : nullptr, h.N2, res, o, S, T,
+                                      h.H, st);
+      VADX_TRY(lin(bufH, h.H, w, b, nullptr, bufP, h.P, act));
+      return memory(layer, mem_pre, bufP, res, o);
+    };
     VADX_TRY(lin(feat, h.idim, "dfsmn.fc1.0.weight", "dfsmn.fc1.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
-    VADX_TRY(lin(bufH, h.H, "dfsmn.fc2.0.weight", "dfsmn.fc2.0.bias", nullptr, bufP, h.P, VADX_ACT_RELU));
-    VADX_TRY(memory(0, "dfsmn.fsmn1.", bufP, nullptr, memA));
+    VADX_TRY(block_tail("dfsmn.fc2.0.weight", "dfsmn.fc2.0.bias", VADX_ACT_RELU, "dfsmn.fsmn1.", 0, nullptr, memA));
     for (int i = 0; i < h.R - 1; ++i) {
       std::string pre = "dfsmn.fsmns." + std::to_string(i) + ".";
       std::string b1 = pre + "fc1.0.bias";
       VADX_TRY(lin(memA, h.P, pre + "fc1.0.weight", b1.c_str(), nullptr, bufH, h.H, VADX_ACT_RELU));
-      VADX_TRY(lin(bufH, h.H, pre + "fc2.weight", nullptr, nullptr, bufP, h.P, VADX_ACT_NONE));
-      VADX_TRY(memory(i + 1, pre + "fsmn.", bufP, memA, memB));
+      VADX_TRY(block_tail(pre + "fc2.weight", nullptr, VADX_ACT_NONE, pre + "fsmn.", i + 1, memA, memB));
       std::swap(memA, memB);
     }
     if (use_tc && h.M == 1 && h.odim == 1 && m->d<uint8_t>("dfsmn.dnns.0.weight#TC")) {
