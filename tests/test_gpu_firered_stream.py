@@ -222,3 +222,25 @@ def test_stream_cuda_graph_replay_is_bit_identical(cuda, stream_session):
         p1, post1, c1, _ = firered_vad.run_stream_vad_streams(stream_session, d, lengths, graph=True)
         assert torch.equal(p0, p1) and torch.equal(c0, c1)
         assert post1.timestamps() == ts0
+
+
+def test_aed_many_streams_against_oracle(cuda):
+    """run_aed_streams: S streams x 3 chunks, three event tracks, each post-processed on the device with its own threshold."""
+    cfg = W.FireRedConfig(odim=3)
+    wts = W.firered_random_init(cfg, 2)
+    sess = vadx.FireRedSession(wts, cfg, chunk_len=16000)
+    S, n_chunks = 20, 3
+    audio = synth.synth_streams(S, n_chunks * 16000, seed=61)
+    lengths = [n_chunks * 16000 - 211 * s for s in range(S)]
+    d = torch.from_numpy(audio.reshape(S, n_chunks, 16000)).to(cuda)
+    probs, per_event, n_valid = firered_vad.run_aed_streams(sess, d, lengths)
+    ref = FireRedOracle(wts, cfg).forward(audio.reshape(S * n_chunks, 16000)).numpy().reshape(S, n_chunks, 3, 98)
+    ref = ref.transpose(0, 2, 1, 3).reshape(S, 3, n_chunks * 98)
+    assert np.abs(probs.cpu().numpy() - ref).max() <= TOL
+    nv = n_valid.cpu().numpy()
+    p_host = probs.cpu().numpy()
+    for e, (post, dec, cnt, seg) in enumerate(per_event):
+        dec = dec.cpu().numpy()
+        for s in range(0, S, 4):
+            want = OP.frame_decisions(p_host[s, e, :nv[s]], 5, post.prob_threshold, 20, 2000, 20, 5, 0)
+            assert np.array_equal(dec[s, :nv[s]], want), (e, s)

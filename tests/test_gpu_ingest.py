@@ -57,3 +57,19 @@ def test_ingest_rejects_bad_arguments(cuda):
         audio_io.ingest_pcm16_device(x[:9], 2, 48000, 16000)
     with pytest.raises(ValueError):
         audio_io.ingest_pcm16_device(x.float(), 1, 48000, 16000)
+
+
+def test_device_wav_loader_equals_host_loader(cuda, tmp_path):
+    """load_wav_int16_device (raw PCM to the GPU, down-mix + rate conversion there) == load_wav_int16 (wave + audioop)."""
+    import wave
+    rs = np.random.RandomState(3)
+    pcm = (rs.randint(-20000, 20000, size=44100 * 2 * 2)).astype(np.int16)     # 2 s, stereo, 44.1 kHz
+    path = str(tmp_path / "x.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(pcm.tobytes())
+    host = audio_io.load_wav_int16(path, 16000)
+    dev = audio_io.load_wav_int16_device(path, 16000).cpu().numpy()
+    assert np.array_equal(host, dev)

@@ -141,3 +141,32 @@ def test_window_blocks_equal_single_window_steps(cuda, session):
         session.MAX_ROWS_PER_CALL = old
     assert (p1 - p5).abs().max().item() <= 2e-6 and (p1 - pa).abs().max().item() <= 2e-6
     assert (s1 - s5).abs().max().item() <= 1e-5
+
+
+def test_vad_iterator_online_events(cuda, session):
+    """VADIterator over a SileroSession window by window (state on the device) == the same iterator replaying the
+    probabilities of the offline path."""
+    audio = torch.from_numpy(synth.synth_streams(1, 512 * 90, seed=12)[0]).float() * 0.000030517578
+    probs = session.audio_forward(audio.unsqueeze(0))[0].numpy()
+
+    class Replay:
+        def __init__(self):
+            self.i = 0
+
+        def reset_states(self):
+            self.i = 0
+
+        def __call__(self, chunk, sr):
+            self.i += 1
+            return torch.tensor([[float(probs[self.i - 1])]])
+
+    live, replay = silero_vad.VADIterator(session), silero_vad.VADIterator(Replay())
+    ev_live, ev_replay = [], []
+    for w in range(90):
+        chunk = audio[w * 512:(w + 1) * 512]
+        ev_live.append(live(chunk))
+        ev_replay.append(replay(chunk))
+    margin = min(np.abs(probs - 0.5).min(), np.abs(probs - 0.35).min())
+    if margin > 1e-4:
+        assert ev_live == ev_replay
+    assert any(e is not None for e in ev_live)
