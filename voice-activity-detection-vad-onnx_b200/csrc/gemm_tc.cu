@@ -136,13 +136,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
           const uint32_t w_hi = smem_u32(w_smem) + (uint32_t)(c * 2) * img_bytes;
           const uint32_t w_lo = w_hi + img_bytes;
           const int nk = min(4, g.n_k16 - c * 4);
-          for (int j = 0; j < nk; ++j)
-            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w_hi + 32u * j), idesc,
-                      (c | j) ? 1u : 0u);
-          for (int j = 0; j < nk; ++j)
-            umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w_hi + 32u * j), idesc, 1u);
-          for (int j = 0; j < nk; ++j)
-            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w_lo + 32u * j), idesc, 1u);
+          const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_lo);
+          const uint64_t dw_hi = umma_desc_sw128(w_hi), dw_lo = umma_desc_sw128(w_lo);
+          umma_k64(d_tmem, da_hi, dw_hi, idesc, c ? 1u : 0u, nk);
+          umma_k64(d_tmem, da_lo, dw_hi, idesc, 1u, nk);
+          umma_k64(d_tmem, da_hi, dw_lo, idesc, 1u, nk);
           umma_commit(empty_bar(stage));  // frees the activation stage once these MMAs retire
           if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
         }

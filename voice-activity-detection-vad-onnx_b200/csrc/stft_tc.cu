@@ -168,12 +168,13 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
           const int nk = min(4, g.n_k16 - c * 4);
           // smallest contributions first would be numerically nicer, but the first MMA of a tile must
           // overwrite the accumulator; the order below keeps that one the dominant x_hi * b0 term
-          for (int j = 0; j < nk; ++j)
-            umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, (c | j) ? 1u : 0u);
+          const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_lo);
+          const uint64_t dw0 = umma_desc_sw128(w0), dw1 = umma_desc_sw128(w1);
+          umma_k64(d_tmem, da_hi, dw0, idesc, c ? 1u : 0u, nk);
           if (!(g.debug & 4)) {
-          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w0 + 32u * j), idesc, 1u);
-          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_hi + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
-          for (int j = 0; j < nk; ++j) umma_bf16(d_tmem, umma_desc_sw128(a_lo + 32u * j), umma_desc_sw128(w1 + 32u * j), idesc, 1u);
+            umma_k64(d_tmem, da_lo, dw0, idesc, 1u, nk);
+            umma_k64(d_tmem, da_hi, dw1, idesc, 1u, nk);
+            umma_k64(d_tmem, da_lo, dw1, idesc, 1u, nk);
           }
           umma_commit(empty_bar(stage));
           if (++stage == kStStages) { stage = 0; phase ^= 1u; }

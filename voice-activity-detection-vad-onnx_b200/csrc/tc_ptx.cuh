@@ -75,6 +75,35 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Up to four K=16 steps of one 64-wide K chunk in a single asm block: the operand descriptors advance by 32 bytes
+// (2 in the descriptors' 16-byte address units) per step, the accumulate predicate is built once.  The issuing
+// thread spends ~12 instructions per chunk instead of ~10 per MMA -- with N = 80 an MMA occupies the tensor core for
+// only 40 cycles, so the issue rate of that one thread matters.
+__device__ __forceinline__ void umma_k64(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate_first, int n_steps) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p0, pt, q1, q2, q3;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+      "setp.ne.b32 p0, %4, 0;\n"
+      "setp.eq.b32 pt, 0, 0;\n"
+      "setp.gt.s32 q1, %5, 1;\n"
+      "setp.gt.s32 q2, %5, 2;\n"
+      "setp.gt.s32 q3, %5, 3;\n"
+      "add.u64 a1, %1, 2;\n"
+      "add.u64 a2, %1, 4;\n"
+      "add.u64 a3, %1, 6;\n"
+      "add.u64 b1, %2, 2;\n"
+      "add.u64 b2, %2, 4;\n"
+      "add.u64 b3, %2, 6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p0;\n"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(n_steps)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
