@@ -218,25 +218,12 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       for (int pass = 0; pass < kPasses; ++pass) {
         const int16_t* xs = xs_n[pass];
         const int i0 = forig_n[pass] + k;  // first of 8 consecutive samples (stream-relative)
+        // hop, pad_left, the lead (8) and the stream length are all multiples of 8 samples, so an 8-sample group lies
+        // either entirely inside [0, L) or entirely outside it (zero pad): no element-wise edge path
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (g.debug & 2) {
-          v = make_uint4(0x00010002u, 0x00030004u, 0x00050006u, 0x00070008u);
-        } else if (i0 >= 0 && i0 + 7 < g.L) {
+        if (i0 >= 0 && i0 + 7 < g.L) {
           v = __ldg(reinterpret_cast<const uint4*>(xs + i0));
           if (EX) msk |= 0xffu << (8 * pass);
-        } else if (i0 + 7 >= 0 && i0 < g.L) {
-          uint16_t tmp[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            int i = i0 + j;
-            const bool in = i >= 0 && i < g.L;
-            tmp[j] = in ? (uint16_t)__ldg(xs + i) : (uint16_t)0;
-            if (EX && in) msk |= 1u << (8 * pass + j);
-          }
-          v.x = tmp[0] | ((uint32_t)tmp[1] << 16);
-          v.y = tmp[2] | ((uint32_t)tmp[3] << 16);
-          v.z = tmp[4] | ((uint32_t)tmp[5] << 16);
-          v.w = tmp[6] | ((uint32_t)tmp[7] << 16);
         }
         raw[pass] = v;
       }
@@ -567,8 +554,8 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   VADX_REQUIRE(d_audio && d_img && d_power, "vadx_stft_power_tc_i16: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0 && ld_power >= n_bins,
                "vadx_stft_power_tc_i16: bad shape");
-  VADX_REQUIRE(in_stride >= n_samples && pad_left >= 0 && (pad_left % 8) == 0,
-               "vadx_stft_power_tc_i16: stride shorter than the stream, or pad_left not a multiple of 8");
+  VADX_REQUIRE(in_stride >= n_samples && pad_left >= 0 && (pad_left % 8) == 0 && (n_samples % 8) == 0,
+               "vadx_stft_power_tc_i16: stride shorter than the stream, or pad_left / n_samples not a multiple of 8");
   const bool leaves_stream = pad_left > 0 || (int64_t)(n_frames - 1) * hop - pad_left + n_taps > n_samples;
   VADX_REQUIRE(!(d_mean || leaves_stream) || (d_dc_tables && n_edge_lo >= 0 && t_edge_hi >= n_edge_lo && t_edge_hi <= n_frames),
                "vadx_stft_power_tc_i16: padded frames / DC removal need the tables of vadx_pack_stft_dc_tc");
