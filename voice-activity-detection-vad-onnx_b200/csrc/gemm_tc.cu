@@ -27,10 +27,7 @@
 namespace vadx {
 
 constexpr int kTcStageBytes = 2 * kTcTileBytes;  // hi + lo
-constexpr int kTcLoaderWarps = 8;
-constexpr int kTcEpiWarp0 = kTcLoaderWarps;       // 8..11: (warp & 3) = TMEM lane quarter
-constexpr int kTcMmaWarp = kTcLoaderWarps + 4;
-constexpr int kTcThreads = (kTcLoaderWarps + 5) * 32;
+// loader warps LW (8 or 16, a template parameter): epilogue warps LW..LW+3 ((warp & 3) = TMEM lane quarter), MMA warp LW+4
 constexpr int kTcOutLd = 36;  // floats per staged row: 32 columns + 4 pad (144 B: conflict-free 16-byte accesses)
 
 struct TcArgs {
@@ -59,8 +56,9 @@ __device__ __forceinline__ float bias_act(float v, float b) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int ACT>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
-__global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g) {
+template <int ACT, int LW, int NB = 3>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
+__global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArgs g) {
+  constexpr int kTcLoaderWarps = LW, kTcEpiWarp0 = LW, kTcMmaWarp = LW + 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (base is 1024-aligned by the launch: dynamic smem starts at a 1024-aligned offset
   // because the kernel has no static shared memory)
@@ -165,10 +163,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       if (g.debug & 2) {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
+      } else if (g.vec_x == 2 && (k + 7 < g.K)) {
+        // one 256-bit load per row chunk: the eight lanes of a row read 256 contiguous bytes, every 32-byte sector
+        // of the request is fully used (two 128-bit loads at a 32-byte lane stride touch each sector twice and cost
+        // twice the L1 data-stage wavefronts -- the stage this kernel saturates)
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int64_t row = min_i64(row0 + pass * (kTcLoaderWarps * 4) + r_in, g.M - 1);
+          ldg256_nc(g.X + row * g.ldx + k, ld[pass][0], ld[pass][1]);
+        }
       } else if (g.vec_x && (k + 7 < g.K)) {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
+          const int64_t row = min_i64(row0 + pass * (kTcLoaderWarps * 4) + r_in, g.M - 1);
           const float4* src = reinterpret_cast<const float4*>(g.X + row * g.ldx + k);
           ld[pass][0] = __ldg(src);
           ld[pass][1] = __ldg(src + 1);
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       } else {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
+          const int64_t row = min_i64(row0 + pass * (kTcLoaderWarps * 4) + r_in, g.M - 1);
           const float* src = g.X + row * g.ldx + k;
           float v[8];
 #pragma unroll
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       const int64_t row0 = (int64_t)q.tile * kTcBM;
 #pragma unroll
       for (int pass = 0; pass < kPasses; ++pass) {
-        const int r = pass * 32 + r_in;
+        const int r = pass * (kTcLoaderWarps * 4) + r_in;
         float4 p0 = ld[pass][0], p1 = ld[pass][1];
         if (row0 + r >= g.M) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
         uint4 hi, lo;
@@ -212,19 +219,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) linear_tc_kernel(const TcArgs g
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
     };
-    float4 b0[kPasses][2], b1[kPasses][2], b2[kPasses][2];
+    // kBufs register buffers rotate: the loads of kBufs - 1 stages are in flight while one is converted
+    constexpr int kBufs = NB;
+    float4 bufs[kBufs][kPasses][2];
     Seq nxt{(int)blockIdx.x, 0}, cur{(int)blockIdx.x, 0};
-    if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
-    if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
+#pragma unroll
+    for (int i = 0; i < kBufs - 1; ++i)
+      if (valid(nxt)) { issue(nxt, bufs[i]); advance(nxt); }
     while (valid(cur)) {
-      if (valid(nxt)) { issue(nxt, b2); advance(nxt); }
-      consume(cur, b0); advance(cur);
-      if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b0); advance(nxt); }
-      consume(cur, b1); advance(cur);
-      if (!valid(cur)) break;
-      if (valid(nxt)) { issue(nxt, b1); advance(nxt); }
-      consume(cur, b2); advance(cur);
+#pragma unroll
+      for (int i = 0; i < kBufs; ++i) {
+        if (valid(nxt)) { issue(nxt, bufs[(i + kBufs - 1) % kBufs]); advance(nxt); }
+        consume(cur, bufs[i]); advance(cur);
+        if (!valid(cur)) break;
+      }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -483,11 +491,15 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc_kernel<VADX_ACT_LOG_CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](auto kern) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    };
+    opt_in(linear_tc_kernel<VADX_ACT_NONE, 8>);       opt_in(linear_tc_kernel<VADX_ACT_NONE, 16>); opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 4>);
+    opt_in(linear_tc_kernel<VADX_ACT_RELU, 8>);       opt_in(linear_tc_kernel<VADX_ACT_RELU, 16>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 4>);
+    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 8>);    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16>); opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16, 4>);
+    opt_in(linear_tc_kernel<VADX_ACT_LOG, 8>);        opt_in(linear_tc_kernel<VADX_ACT_LOG, 16>); opt_in(linear_tc_kernel<VADX_ACT_LOG, 16, 4>);
+    opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 8>);  opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 16>); opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 16, 4>);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_tc_kernel)");
     configured = true;
   }
@@ -508,19 +520,31 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     g.debug = dbg;
   }
   g.vec_x = ((ldx & 3) == 0) && aligned16(d_x);
+  {
+    static const bool no256 = getenv("VADX_LIN_NO_LDG256") != nullptr;
+    if (g.vec_x && !no256 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 31u) == 0) g.vec_x = 2;
+  }
   g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
   int grid = (int)std::min<int64_t>(tiles, n_sm > 0 ? n_sm : 148);
+  static const int lw = [] { const char* e = getenv("VADX_LIN_LOADERS"); const int v = e ? atoi(e) : 16; return v == 8 || v == 164 ? v : 16; }();
+#define VADX_LIN_LAUNCH(A)                                                                                \
+  do {                                                                                                    \
+    if (lw == 8) linear_tc_kernel<A, 8><<<grid, 13 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);        \
+    else if (lw == 16) linear_tc_kernel<A, 16><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g); \
+    else linear_tc_kernel<A, 16, 4><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);            \
+  } while (0)
   switch (act & 15) {
-    case VADX_ACT_NONE: linear_tc_kernel<VADX_ACT_NONE><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
-    case VADX_ACT_RELU: linear_tc_kernel<VADX_ACT_RELU><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
-    case VADX_ACT_SIGMOID: linear_tc_kernel<VADX_ACT_SIGMOID><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g); break;
+    case VADX_ACT_NONE: VADX_LIN_LAUNCH(VADX_ACT_NONE); break;
+    case VADX_ACT_RELU: VADX_LIN_LAUNCH(VADX_ACT_RELU); break;
+    case VADX_ACT_SIGMOID: VADX_LIN_LAUNCH(VADX_ACT_SIGMOID); break;
     case VADX_ACT_LOG:
     case VADX_ACT_LOG_CLAMP:
       VADX_REQUIRE(!d_residual && !d_head_out && d_bias, "vadx_linear_tc_f32: the log epilogues need a bias/floor vector and take no residual or head");
-      if ((act & 15) == VADX_ACT_LOG) linear_tc_kernel<VADX_ACT_LOG><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
-      else linear_tc_kernel<VADX_ACT_LOG_CLAMP><<<grid, kTcThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+      if ((act & 15) == VADX_ACT_LOG) VADX_LIN_LAUNCH(VADX_ACT_LOG);
+      else VADX_LIN_LAUNCH(VADX_ACT_LOG_CLAMP);
       break;
     default: set_error("vadx_linear_tc_f32: activation %d is not supported", act); return VADX_EINVAL;
   }
+#undef VADX_LIN_LAUNCH
   return after_launch("vadx_linear_tc_f32");
 }

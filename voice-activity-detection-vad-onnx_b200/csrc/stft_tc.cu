@@ -28,10 +28,8 @@ constexpr int kStTerms = 2;                          // bf16 terms of the folded
 constexpr int kStLead = 8;                           // leading zero rows of the folded basis
 constexpr int kStStageBytes = 2 * kTcTileBytes;      // x_hi + x_lo
 constexpr int kStStages = 2;
-constexpr int kStLoaderWarps = 8;
-constexpr int kStEpiWarp0 = kStLoaderWarps;          // 8..11: (warp & 3) = TMEM lane quarter
-constexpr int kStMmaWarp = kStLoaderWarps + 4;
-constexpr int kStThreads = (kStLoaderWarps + 5) * 32;
+constexpr int kStOutLd = 44;                         // floats per staged output row (40 used; 44 keeps float4 stores conflict-free)
+// loader warps LW (8 or 16, a template parameter): epilogue warps LW..LW+3 ((warp & 3) = TMEM lane quarter), MMA warp LW+4
 
 struct StftTcArgs {
   const int16_t* X;
@@ -52,6 +50,8 @@ struct StftTcArgs {
                          // pad -- then one tail row per frame that runs past the end of the stream
   int n_edge_lo, t_edge_hi;   // frames t < n_edge_lo and t >= t_edge_hi are edge frames
   float power_scale;     // multiplies re^2 + im^2 (a scale kept out of an fp16 basis, e.g. (1/32768)^2)
+  int stack;       // 1: both basis terms as one N = 160 operand (two MMAs per K step, each sample term read once)
+  int stage_out;   // 1: the epilogue transposes each warp's 32 x 40 powers through shared memory (coalesced stores)
   int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
@@ -99,8 +99,9 @@ __device__ __forceinline__ void split17(int d, float& hi, float& lo) {
 
 // EX = false: every frame inside the stream, no DC removal (FireRed) -- the padded / mean-removing code is compiled out
 // F16 = true: fp16 operands (cheaper exact conversion; not with the 17-bit mean-removed samples)
-template <bool EX, bool F16>
-__global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const StftTcArgs g) {
+template <bool EX, bool F16, int LW>
+__global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const StftTcArgs g) {
+  constexpr int kStLoaderWarps = LW, kStEpiWarp0 = LW, kStMmaWarp = LW + 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* w_smem = smem_raw;
   const uint32_t img_bytes = kStNPad * 128u;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
   uint8_t* a_smem = w_smem + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)kStStages * kStStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* out_stage = reinterpret_cast<float*>(bars + 16);   // [4 warps][32 rows][kStOutLd], only when g.stage_out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
   auto tfull_bar = [&](int b) { return bar0 + 8u * (8 + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (10 + b); };
   const uint32_t wbar = bar0 + 8u * 12;
-  constexpr uint32_t kTmemCols = 256;  // 2 x 80 accumulator columns
+  constexpr uint32_t kTmemCols = 512;  // 2 accumulators of 80 (or, stacked, 160) columns
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       const uint8_t* src = g.Wimg + (size_t)ntile * w_bytes;
       for (int t = 0; t < g.kc * kStTerms; ++t) bulk_g2s(smem_u32(w_smem) + t * img_bytes, src + (size_t)t * img_bytes, img_bytes, wbar);
       mbar_wait(wbar, 0);
-      const uint32_t idesc = F16 ? umma_idesc_f16(kStNPad) : umma_idesc_bf16(kStNPad);
+      const int acc_n = g.stack ? 2 * kStNPad : kStNPad;
+      const uint32_t idesc = F16 ? umma_idesc_f16(acc_n) : umma_idesc_bf16(acc_n);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * kStNPad);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * acc_n);
         for (int c = 0; c < g.kc; ++c) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -171,7 +174,11 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
           const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_lo);
           const uint64_t dw0 = umma_desc_sw128(w0), dw1 = umma_desc_sw128(w1);
           umma_k64(d_tmem, da_hi, dw0, idesc, c ? 1u : 0u, nk);
-          if (!(g.debug & 4)) {
+          if (g.stack) {
+            // the two basis terms sit back to back in shared memory: as one 160-row operand they give x_hi*b0 | x_hi*b1
+            // in two column blocks of the accumulator (the epilogue adds them) and every sample term is read once
+            umma_k64(d_tmem, da_lo, dw0, idesc, 1u, nk);
+          } else if (!(g.debug & 4)) {
             umma_k64(d_tmem, da_lo, dw0, idesc, 1u, nk);
             umma_k64(d_tmem, da_hi, dw1, idesc, 1u, nk);
             umma_k64(d_tmem, da_lo, dw1, idesc, 1u, nk);
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         const int64_t row0 = (int64_t)q.tile * kTcBM;
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
+          const int64_t row = min_i64(row0 + pass * (kStLoaderWarps * 4) + r_in, g.M - 1);
           const int64_t s = row / g.n_frames;
           const int fr = (int)(row - s * g.n_frames);
           xs_n[pass] = g.X + s * g.in_stride;
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       if (EX && g.mean_int && q.tile != tile_cached_c) {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          const int64_t row = min_i64(row0 + pass * 32 + r_in, g.M - 1);
+          const int64_t row = min_i64(row0 + pass * (kStLoaderWarps * 4) + r_in, g.M - 1);
           mi_c[pass] = __ldg(g.mean_int + row / g.n_frames);
         }
         tile_cached_c = q.tile;
@@ -248,19 +255,18 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       if (!(g.debug & 8))
 #pragma unroll
       for (int pass = 0; pass < kPasses; ++pass) {
-        const int r = pass * 32 + r_in;
+        const int r = pass * (kStLoaderWarps * 4) + r_in;
         const uint32_t wds[4] = {raw[pass].x, raw[pass].y, raw[pass].z, raw[pass].w};
         uint32_t hi[4], lo[4];
-        const bool live = row0 + r < g.M;
         if (EX && g.mean_int) {
           // integer part of the stream's mean removed from the real samples only (the zero pad stays zero)
           const int mi = mi_c[pass];
           const uint32_t vm = (msk >> (8 * pass)) & 0xffu;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t w = live ? wds[j] : 0u;
-            const int a = (live && ((vm >> (2 * j)) & 1u)) ? ((int)(w << 16) >> 16) - mi : 0;
-            const int b = (live && ((vm >> (2 * j + 1)) & 1u)) ? ((int)w >> 16) - mi : 0;
+            const uint32_t w = wds[j];   // rows past M repeat row M-1 and are never stored
+            const int a = ((vm >> (2 * j)) & 1u) ? ((int)(w << 16) >> 16) - mi : 0;
+            const int b = ((vm >> (2 * j + 1)) & 1u) ? ((int)w >> 16) - mi : 0;
             float ah, al, bh, bl;
             split17(a, ah, al);
             split17(b, bh, bl);
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
         } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t w = live ? wds[j] : 0u;
+          const uint32_t w = wds[j];   // rows past M repeat row M-1 and are never stored
           hi[j] = F16 ? f16x2_hi(w) : bf16x2_hi(w);
           lo[j] = F16 ? f16x2_lo(w) : bf16x2_lo(w);
         }
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     };
     // kStBufs register buffers rotate: the loads of kStBufs - 1 stages are in flight while one is converted
     // (the padded / mean-removing variant carries more live state per thread and keeps one buffer fewer)
-    constexpr int kStBufs = EX ? 4 : 5;
+    constexpr int kStBufs = EX ? 4 : (LW > 8 ? 6 : 5);
     uint4 bufs[kStBufs][kPasses];
     uint32_t msks[kStBufs];
 #pragma unroll
@@ -312,11 +318,12 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(b), use & 1u, 64);
+      mbar_wait(tfull_bar(b), use & 1u, 256);   // a tile takes microseconds: poll rarely, the spin competes with the loaders for issue slots
       tc_fence_after();
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * kStNPad);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * (g.stack ? 2 * kStNPad : kStNPad));
+      float* const my_out = out_stage + (size_t)q * 32 * kStOutLd;
       // DC removal in the frequency domain: X(x - m) = X(x) - m * (folded basis applied to the mean's
       // coefficient pattern), exact in fp32; only frames touching the zero pad need their own row of the table
       // Frames that run past the end of the stream: the reference pads the PRE-EMPHASISED signal with zeros, the
@@ -342,6 +349,12 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       for (int c0 = 0; c0 < kStNPad; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
+        if (g.stack) {
+          float v2[16];
+          tmem_ld16(taddr + (uint32_t)(kStNPad + c0), v2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += v2[j];
+        }
         if (!row_ok || (g.debug & 1)) continue;
         if (EX && dc_row) {
 #pragma unroll
@@ -356,7 +369,11 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
 #pragma unroll
         for (int j = 0; j < 8; ++j) pw[j] = (v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1]) * g.power_scale;
         const int fb = f0 + c0 / 2;
-        if (g.vec_p && fb + 7 < g.n_bins) {
+        if (g.stage_out) {
+          float4* d4 = reinterpret_cast<float4*>(my_out + lane * kStOutLd + c0 / 2);
+          d4[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+          d4[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+        } else if (g.vec_p && fb + 7 < g.n_bins) {
           reinterpret_cast<float4*>(out)[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
           reinterpret_cast<float4*>(out)[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
         } else {
@@ -367,7 +384,32 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(b));
+      if (lane == 0) mbar_arrive(tempty_bar(b));   // the accumulator is free; the staged rows still have to go out
+      if (g.stage_out && !(g.debug & 1)) {
+        // 32 rows x 40 powers, written 16 bytes per lane with consecutive lanes on consecutive columns: a row's 160 bytes
+        // leave in one piece instead of as ten 16-byte stores scattered over ten instructions
+        const int64_t row0 = (int64_t)tile * kTcBM + q * 32;
+        constexpr int kC4 = kStNPad / 8;   // 10 float4 per row
+#pragma unroll
+        for (int itr = 0; itr < kC4; ++itr) {
+          const int idx = itr * 32 + lane;
+          const int r = idx / kC4, c4 = idx - r * kC4;
+          const int64_t grow = row0 + r;
+          const int fbin = f0 + c4 * 4;
+          if (grow < g.M && fbin < g.n_bins) {
+            const float4 val = *reinterpret_cast<const float4*>(my_out + r * kStOutLd + c4 * 4);
+            float* out = g.P + grow * g.ldp + fbin;
+            if (fbin + 3 < g.n_bins) {
+              *reinterpret_cast<float4*>(out) = val;
+            } else {
+              out[0] = val.x;
+              if (fbin + 1 < g.n_bins) out[1] = val.y;
+              if (fbin + 2 < g.n_bins) out[2] = val.z;
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
@@ -380,7 +422,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stft_power_tc_kernel(const Stft
 
 struct StftTcShape {
   int kc, n_k16, n_ntiles;
-  size_t tile_bytes, img_bytes, smem_bytes;
+  size_t tile_bytes, img_bytes, smem_bytes, stage_bytes;   // stage_bytes: optional output staging on top of smem_bytes
   bool ok;
 };
 StftTcShape stft_tc_shape(int n_taps, int n_bins) {
@@ -391,7 +433,8 @@ StftTcShape stft_tc_shape(int n_taps, int n_bins) {
   s.n_ntiles = (int)ceil_div(2 * n_bins, kStNPad);
   s.tile_bytes = (size_t)s.kc * kStTerms * kStNPad * 128;
   s.img_bytes = s.tile_bytes * s.n_ntiles;
-  s.smem_bytes = s.tile_bytes + (size_t)kStStages * kStStageBytes + 13 * 8 + 16;
+  s.smem_bytes = s.tile_bytes + (size_t)kStStages * kStStageBytes + 16 * 8;
+  s.stage_bytes = (size_t)4 * 32 * kStOutLd * sizeof(float);
   s.ok = s.smem_bytes <= (size_t)kTcSmemBudget;
   return s;
 }
@@ -570,13 +613,14 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(stft_power_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stft_power_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stft_power_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stft_power_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](auto kern) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    };
+    opt_in(stft_power_tc_kernel<false, false, 8>);  opt_in(stft_power_tc_kernel<false, false, 16>);
+    opt_in(stft_power_tc_kernel<true, false, 8>);   opt_in(stft_power_tc_kernel<true, false, 16>);
+    opt_in(stft_power_tc_kernel<false, true, 8>);   opt_in(stft_power_tc_kernel<false, true, 16>);
+    opt_in(stft_power_tc_kernel<true, true, 8>);    opt_in(stft_power_tc_kernel<true, true, 16>);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_power_tc_kernel)");
     configured = true;
   }
@@ -594,15 +638,26 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     }
     g.debug = dbg;
   }
+  static const int opt = [] { const char* e = getenv("VADX_ST_OPT"); return e ? atoi(e) : 3; }();   // bit 0 stack, bit 1 staged output
+  g.stack = (opt & 1) ? 1 : 0;
+  g.stage_out = ((opt & 2) && g.vec_p && s.smem_bytes + s.stage_bytes <= (size_t)kTcSmemBudget) ? 1 : 0;
+  const size_t smem = s.smem_bytes + (g.stage_out ? s.stage_bytes : 0);
   int64_t tiles = ceil_div(g.M, kTcBM);
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_stft_power_tc_i16: too many rows");
   g.n_tiles = (int)tiles;
   int per = std::max(1, (n_sm > 0 ? n_sm : 148) / s.n_ntiles);
   dim3 grid((unsigned)std::min<int64_t>(tiles, per), (unsigned)s.n_ntiles);
   const bool ex = leaves_stream || d_mean, f16 = operand_format == VADX_TC_FMT_F16;
-  if (ex && f16) stft_power_tc_kernel<true, true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
-  else if (ex) stft_power_tc_kernel<true, false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
-  else if (f16) stft_power_tc_kernel<false, true><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
-  else stft_power_tc_kernel<false, false><<<grid, kStThreads, s.smem_bytes, (cudaStream_t)stream>>>(g);
+  static const int lw = [] { const char* e = getenv("VADX_ST_LOADERS"); return e && atoi(e) == 8 ? 8 : 16; }();
+#define VADX_ST_LAUNCH(EXV, F16V)                                                                                   \
+  do {                                                                                                              \
+    if (lw == 8) stft_power_tc_kernel<EXV, F16V, 8><<<grid, 13 * 32, smem, (cudaStream_t)stream>>>(g);              \
+    else stft_power_tc_kernel<EXV, F16V, 16><<<grid, 21 * 32, smem, (cudaStream_t)stream>>>(g);                     \
+  } while (0)
+  if (ex && f16) VADX_ST_LAUNCH(true, true);
+  else if (ex) VADX_ST_LAUNCH(true, false);
+  else if (f16) VADX_ST_LAUNCH(false, true);
+  else VADX_ST_LAUNCH(false, false);
+#undef VADX_ST_LAUNCH
   return after_launch("vadx_stft_power_tc_i16");
 }

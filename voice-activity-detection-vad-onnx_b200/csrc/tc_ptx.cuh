@@ -120,6 +120,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // 32 consecutive fp32 columns of this thread's TMEM lane, one wait for both halves
+// 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256_nc(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
