@@ -41,6 +41,9 @@ struct TcArgs {
   int64_t ldy;
   int64_t M;
   int K, N, n_pad, kc, n_k16, act, n_stages, n_tiles, tmem_cols, vec_x, vec_y;
+  unsigned backoff_ld, backoff_epi;   // nanoseconds between mbarrier probes of the loader / epilogue warps
+  int pf_tiles;   // L2 prefetch distance in row tiles of this CTA (0 = off)
+  int pf_spread, pf_at;   // pf_at: the K step of the current tile at which the prefetch is issued
   const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
   float head_b;
   float* head_out;       // [rows]; when set the N-wide output itself is not written
@@ -54,6 +57,12 @@ __device__ __forceinline__ float bias_act(float v, float b) {
   if (ACT == VADX_ACT_LOG) return logf(v + b);
   return apply_act(v + b, ACT);
 }
+
+static int lin_loader_warps() {
+  static const int lw = [] { const char* e = getenv("VADX_LIN_LOADERS"); const int v = e ? atoi(e) : 16; return v == 8 || v == 164 ? v : 16; }();
+  return lw;
+}
+static bool lw_is16() { return lin_loader_warps() != 8; }
 
 // ------------------------------------------------------------------------------------------ kernel
 template <int ACT, int LW, int NB = 3>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
@@ -160,6 +169,22 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
     auto issue = [&](const Seq& q, float4 (*ld)[2]) {
       const int64_t row0 = (int64_t)q.tile * kTcBM;
       const int k = q.c * kTcBK + kq * 8;
+      if (g.pf_tiles && lane == 0 && (g.pf_spread || q.c == g.pf_at)) {
+        // ask L2 for the rows of a later tile of this CTA: the register buffers only keep two stages of loads in
+        // flight, and at HBM latency that is not enough bytes per SM; a prefetched row is an L2 hit when its turn comes.
+        // pf_spread: each K step of the current tile asks for 1/kc of this warp's rows instead of all of them at once
+        constexpr int kRows = kTcBM / kTcLoaderWarps;
+        const int per = g.pf_spread ? kRows / g.kc : kRows;
+        const int64_t pr0 = ((int64_t)q.tile + (int64_t)g.pf_tiles * gridDim.x) * kTcBM + warp * kRows + (g.pf_spread ? q.c * per : 0);
+        const int64_t n = min_i64((int64_t)per, g.M - pr0);
+        if (n > 0) {
+          if (g.ldx == g.K) {
+            l2_prefetch(g.X + pr0 * g.ldx, (uint32_t)(n * g.K * 4));
+          } else {
+            for (int i = 0; i < (int)n; ++i) l2_prefetch(g.X + (pr0 + i) * g.ldx, (uint32_t)(g.K * 4));
+          }
+        }
+      }
       if (g.debug & 2) {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
@@ -196,7 +221,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
     int stage = 0;
     uint32_t phase = 0;
     auto consume = [&](const Seq& q, float4 (*ld)[2]) {
-      mbar_wait(empty_bar(stage), phase ^ 1u, 64);
+      mbar_wait(empty_bar(stage), phase ^ 1u, g.backoff_ld);
       uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
       const int64_t row0 = (int64_t)q.tile * kTcBM;
@@ -241,7 +266,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(b), use & 1u, 64);
+      mbar_wait(tfull_bar(b), use & 1u, g.backoff_epi);
       tc_fence_after();
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -521,12 +546,23 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   }
   g.vec_x = ((ldx & 3) == 0) && aligned16(d_x);
   {
+    static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
+    static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 64; }();
+    g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
+    static const int pf = [] { const char* e = getenv("VADX_LIN_PF"); return e ? atoi(e) : 1; }();
+    g.pf_tiles = (g.vec_x && (n_in & 3) == 0) ? pf : 0;   // bulk prefetch wants 16-byte aligned addresses and sizes
+    static const int spread = [] { const char* e = getenv("VADX_LIN_PF_SPREAD"); return e ? atoi(e) : 0; }();
+    static const int at = [] { const char* e = getenv("VADX_LIN_PF_AT"); return e ? atoi(e) : 0; }();
+    g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
+    g.pf_spread = (spread && s.kc <= 8 && ((kTcBM / 16) % s.kc) == 0 && lw_is16()) ? 1 : 0;
+  }
+  {
     static const bool no256 = getenv("VADX_LIN_NO_LDG256") != nullptr;
     if (g.vec_x && !no256 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 31u) == 0) g.vec_x = 2;
   }
   g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
   int grid = (int)std::min<int64_t>(tiles, n_sm > 0 ? n_sm : 148);
-  static const int lw = [] { const char* e = getenv("VADX_LIN_LOADERS"); const int v = e ? atoi(e) : 16; return v == 8 || v == 164 ? v : 16; }();
+  const int lw = lin_loader_warps();
 #define VADX_LIN_LAUNCH(A)                                                                                \
   do {                                                                                                    \
     if (lw == 8) linear_tc_kernel<A, 8><<<grid, 13 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);        \

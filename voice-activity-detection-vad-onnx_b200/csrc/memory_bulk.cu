@@ -45,6 +45,7 @@ struct MemBulkArgs {
   float* out;
   int64_t n_streams;
   int T;
+  int pf;   // L2 prefetch distance, in streams of this CTA beyond the one being copied to shared memory (0 = off)
 };
 
 template <int N1, int N2>
@@ -88,6 +89,15 @@ __global__ void __launch_bounds__(kMbThreads, 1) fsmn_memory_bulk_kernel(const M
     for (uint32_t off = 0; off < tile_bytes; off += 16384u) {
       const uint32_t nb = tile_bytes - off < 16384u ? tile_bytes - off : 16384u;
       bulk_g2s(smem_u32(dst) + off, src_p + off, nb, full_bar(slot));
+    }
+    // one stream's tiles in flight do not cover the HBM latency: ask L2 for a later stream's now
+    const int64_t s_pf = s + (int64_t)g.pf * gridDim.x;
+    if (g.pf && s_pf < g.n_streams) {
+      for (uint32_t off = 0; off < tile_bytes; off += 16384u) {
+        const uint32_t nb = tile_bytes - off < 16384u ? tile_bytes - off : 16384u;
+        l2_prefetch(reinterpret_cast<const uint8_t*>(g.p) + (size_t)s_pf * tile_bytes + off, nb);
+        if (g.res) l2_prefetch(reinterpret_cast<const uint8_t*>(g.res) + (size_t)s_pf * tile_bytes + off, nb);
+      }
     }
     if (g.res) {
       const uint8_t* src_r = reinterpret_cast<const uint8_t*>(g.res) + (size_t)s * tile_bytes;
@@ -186,7 +196,8 @@ int memory_bulk_launch(const float* p, const float* wl, const float* wr, int n_a
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_bulk_kernel)");
     configured = true;
   }
-  MemBulkArgs g{p, res, wl, wr, out, n_streams, n_frames};
+  static const int pf = [] { const char* e = getenv("VADX_MEM_PF"); return e ? atoi(e) : 0; }();   // measured slower on B200 (2.17 -> 2.5 ms per step): off
+  MemBulkArgs g{p, res, wl, wr, out, n_streams, n_frames, pf};
   const int grid = (int)std::min<int64_t>(n_streams, n_sm > 0 ? n_sm : 148);
   if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20><<<grid, kMbThreads, smem, st>>>(g);
   else fsmn_memory_bulk_kernel<20, 0><<<grid, kMbThreads, smem, st>>>(g);

@@ -52,6 +52,7 @@ struct StftTcArgs {
   float power_scale;     // multiplies re^2 + im^2 (a scale kept out of an fp16 basis, e.g. (1/32768)^2)
   int stack;       // 1: both basis terms as one N = 160 operand (two MMAs per K step, each sample term read once)
   int stage_out;   // 1: the epilogue transposes each warp's 32 x 40 powers through shared memory (coalesced stores)
+  unsigned backoff_ld, backoff_epi;   // nanoseconds between mbarrier probes of the loader / epilogue warps
   int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const S
         }
         tile_cached_c = q.tile;
       }
-      mbar_wait(empty_bar(stage), phase ^ 1u, 64);
+      mbar_wait(empty_bar(stage), phase ^ 1u, g.backoff_ld);
       uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
       if (!(g.debug & 8))
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const S
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(b), use & 1u, 256);   // a tile takes microseconds: poll rarely, the spin competes with the loaders for issue slots
+      mbar_wait(tfull_bar(b), use & 1u, g.backoff_epi);   // a tile takes microseconds: poll rarely
       tc_fence_after();
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -639,6 +640,11 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     g.debug = dbg;
   }
   static const int opt = [] { const char* e = getenv("VADX_ST_OPT"); return e ? atoi(e) : 3; }();   // bit 0 stack, bit 1 staged output
+  {
+    static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
+    static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 256; }();
+    g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
+  }
   g.stack = (opt & 1) ? 1 : 0;
   g.stage_out = ((opt & 2) && g.vec_p && s.smem_bytes + s.stage_bytes <= (size_t)kTcSmemBudget) ? 1 : 0;
   const size_t smem = s.smem_bytes + (g.stage_out ? s.stage_bytes : 0);

@@ -120,6 +120,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // 32 consecutive fp32 columns of this thread's TMEM lane, one wait for both halves
+// bulk L2 prefetch (no destination, no completion): p 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
 __device__ __forceinline__ void ldg256_nc(const float* p, float4& a, float4& b) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
