@@ -56,6 +56,62 @@ def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):
     assert err <= bound, (err, bound)
 
 
+@pytest.mark.parametrize("rows,n_in,ldx,col0", [
+    (5000, 128, 256, 0),      # rows of a wider tensor: per-row L2 prefetch, 256-bit loads (ldx % 8 == 0)
+    (5000, 128, 256, 64),     # ... starting at a 256-byte column offset
+    (3000, 200, 204, 0),      # ldx % 8 != 0: 128-bit loads; K = 200 leaves a partial k-chunk (the mel layer's shape)
+    (3000, 128, 132, 4),      # base pointer only 16-byte aligned
+    (1500, 100, 101, 0),      # ldx % 4 != 0: scalar loads, no prefetch
+    (40000, 256, 256, 0),     # dense, several tiles per CTA: the tile-ahead prefetch runs past the last tile
+])
+def test_linear_tc_strided_input(cuda, rows, n_in, ldx, col0):
+    """x is a column window of a wider row-major tensor (ldx > K); every loader path must give the dense result."""
+    l = lib.load()
+    n_out = 128
+    g = torch.Generator().manual_seed(rows + ldx)
+    wide = torch.randn((rows, ldx + col0), generator=g) * 2.0
+    w = torch.randn((n_out, n_in), generator=g) / np.sqrt(n_in)
+    b = torch.randn((n_out,), generator=g)
+    wd = wide.to(cuda)
+    xv = wd[:, col0:col0 + n_in]
+    img = torch.from_numpy(lib.pack_weight_tc(w.numpy())).to(cuda)
+    bd = b.to(cuda)
+    y = torch.full((rows, n_out), float("nan"), device=cuda)
+    lib.check(l.vadx_linear_tc_f32(xv.data_ptr(), wd.stride(0), img.data_ptr(), bd.data_ptr(), None, n_out, y.data_ptr(), n_out,
+                                   rows, n_in, n_out, 1, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    x = wide[:, col0:col0 + n_in]
+    ref = torch.relu(x.double() @ w.double().T + b.double())
+    err = (y.cpu().double() - ref).abs().max().item()
+    bound = 1.2e-5 * (x.abs().double() @ w.abs().double().T).max().item() + 1e-6
+    assert not torch.isnan(y).any()
+    assert err <= bound, (err, bound)
+
+
+@pytest.mark.parametrize("act", [4, 5])
+def test_linear_tc_log_epilogues(cuda, act):
+    """VADX_ACT_LOG (ln(v + eps)) and VADX_ACT_LOG_CLAMP (ln(max(v, floor))): the bias slot carries eps / floor.
+    The epilogue uses lg2.approx * ln 2; tolerance 2e-5 absolute on |ln| < 30 plus the operand split's share."""
+    l = lib.load()
+    rows, n_in, n_out = 4000, 200, 80
+    g = torch.Generator().manual_seed(act)
+    x = torch.rand((rows, n_in), generator=g) * 1e6          # power-spectrum-like, non-negative
+    x[::7] = 0.0                                             # silent rows hit the floor
+    w = torch.rand((n_out, n_in), generator=g) * (torch.rand((n_out, n_in), generator=g) < 0.1)   # sparse triangles
+    floor = torch.full((n_out,), 1e-7 if act == 4 else 1e-5)
+    img = torch.from_numpy(lib.pack_weight_tc(w.numpy())).to(cuda)
+    xd, fd = x.to(cuda), floor.to(cuda)
+    y = torch.full((rows, n_out), float("nan"), device=cuda)
+    lib.check(l.vadx_linear_tc_f32(xd.data_ptr(), n_in, img.data_ptr(), fd.data_ptr(), None, n_out, y.data_ptr(), n_out,
+                                   rows, n_in, n_out, act, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    v = x.double() @ w.double().T
+    ref = torch.log(v + floor.double()) if act == 4 else torch.log(torch.clamp(v, min=floor.double()[0].item()))
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert not torch.isnan(y).any()
+    assert err <= 5e-5, err
+
+
 @pytest.mark.parametrize("S,L", [(5, 16000), (300, 16000), (3, 5000), (2, 400 + 160 * 7)])
 @pytest.mark.parametrize("fmt", [lib.TC_FMT_BF16, lib.TC_FMT_F16])
 def test_stft_power_tc_from_int16(cuda, S, L, fmt):

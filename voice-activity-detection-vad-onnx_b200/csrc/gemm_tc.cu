@@ -43,6 +43,7 @@ struct TcArgs {
   int K, N, n_pad, kc, n_k16, act, n_stages, n_tiles, tmem_cols, vec_x, vec_y;
   unsigned backoff_ld, backoff_epi;   // nanoseconds between mbarrier probes of the loader / epilogue warps
   int pf_tiles;   // L2 prefetch distance in row tiles of this CTA (0 = off)
+  int k_live;     // columns < k_live are read by the MMA (n_k16 * 16)
   int pf_spread, pf_at;   // pf_at: the K step of the current tile at which the prefetch is issued
   const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
   float head_b;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
     struct Seq { int tile, c; };
     auto valid = [&](const Seq& q) { return q.tile < g.n_tiles; };
     auto advance = [&](Seq& q) { if (++q.c == g.kc) { q.c = 0; q.tile += gridDim.x; } };
+    const int k_live = g.k_live;
     auto issue = [&](const Seq& q, float4 (*ld)[2]) {
       const int64_t row0 = (int64_t)q.tile * kTcBM;
       const int k = q.c * kTcBK + kq * 8;
@@ -188,7 +190,10 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
           }
         }
       }
-      if (g.debug & 2) {
+      if (k >= k_live) {
+        // columns beyond the last K16 step the MMA issues (K = 80 or 200 in a 64-wide chunk): never read, so neither
+        // loaded nor stored
+      } else if (g.debug & 2) {
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) ld[pass][0] = ld[pass][1] = make_float4(1.f, 2.f, 3.f, 4.f);
       } else if (g.vec_x == 2 && (k + 7 < g.K)) {
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
       uint8_t* st_hi = a_smem + (size_t)stage * kTcStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
       const int64_t row0 = (int64_t)q.tile * kTcBM;
+      if (q.c * kTcBK + kq * 8 < k_live)
 #pragma unroll
       for (int pass = 0; pass < kPasses; ++pass) {
         const int r = pass * (kTcLoaderWarps * 4) + r_in;
@@ -552,6 +558,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
     static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 64; }();
     g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
+    static const bool all_cols = getenv("VADX_TC_ALLCOLS") != nullptr;
+    g.k_live = all_cols ? s.kc * kTcBK : s.n_k16 * 16;
     static const int pf = [] { const char* e = getenv("VADX_LIN_PF"); return e ? atoi(e) : 1; }();
     g.pf_tiles = (g.vec_x && (n_in & 3) == 0) ? pf : 0;   // bulk prefetch wants 16-byte aligned addresses and sizes
     static const int spread = [] { const char* e = getenv("VADX_LIN_PF_SPREAD"); return e ? atoi(e) : 0; }();

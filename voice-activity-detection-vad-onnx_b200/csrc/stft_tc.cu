@@ -53,6 +53,7 @@ struct StftTcArgs {
   int stack;       // 1: both basis terms as one N = 160 operand (two MMAs per K step, each sample term read once)
   int stage_out;   // 1: the epilogue transposes each warp's 32 x 40 powers through shared memory (coalesced stores)
   unsigned backoff_ld, backoff_epi;   // nanoseconds between mbarrier probes of the loader / epilogue warps
+  int k_live;      // columns < k_live are read by the MMA (n_k16 * 16)
   int debug;  // VADX_TC_DEBUG perf experiments: 1 no stores, 2 no loads, 4 one product only
 };
 
@@ -207,6 +208,9 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const S
     struct Seq { int tile, c; };
     auto valid = [&](const Seq& q) { return q.tile < g.n_tiles; };
     auto advance = [&](Seq& q) { if (++q.c == g.kc) { q.c = 0; q.tile += gridDim.x; } };
+    // columns at and beyond the last K16 step the MMA issues are never read: neither load nor store them (the last
+    // 64-wide chunk of a 408-tap frame has 32 such columns, 7 % of the loader's traffic)
+    const int k_live = g.k_live;
     auto issue = [&](const Seq& q, uint4* raw, uint32_t& msk) {
       msk = 0u;
       if (q.tile != tile_cached) {
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const S
         // hop, pad_left, the lead (8) and the stream length are all multiples of 8 samples, so an 8-sample group lies
         // either entirely inside [0, L) or entirely outside it (zero pad): no element-wise edge path
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (i0 >= 0 && i0 + 7 < g.L) {
+        if (i0 >= 0 && i0 + 7 < g.L && k < k_live) {
           v = __ldg(reinterpret_cast<const uint4*>(xs + i0));
           if (EX) msk |= 0xffu << (8 * pass);
         }
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) stft_power_tc_kernel(const S
       mbar_wait(empty_bar(stage), phase ^ 1u, g.backoff_ld);
       uint8_t* st_hi = a_smem + (size_t)stage * kStStageBytes;
       uint8_t* st_lo = st_hi + kTcTileBytes;
-      if (!(g.debug & 8))
+      if (!(g.debug & 8) && q.c * kTcBK + kq * 8 < k_live)
 #pragma unroll
       for (int pass = 0; pass < kPasses; ++pass) {
         const int r = pass * (kStLoaderWarps * 4) + r_in;
@@ -644,6 +648,8 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
     static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 256; }();
     g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
+    static const bool all_cols = getenv("VADX_TC_ALLCOLS") != nullptr;
+    g.k_live = all_cols ? s.kc * kTcBK : s.n_k16 * 16;
   }
   g.stack = (opt & 1) ? 1 : 0;
   g.stage_out = ((opt & 2) && g.vec_p && s.smem_bytes + s.stage_bytes <= (size_t)kTcSmemBudget) ? 1 : 0;
