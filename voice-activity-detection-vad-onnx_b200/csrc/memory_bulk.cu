@@ -20,8 +20,9 @@
 namespace vadx {
 
 constexpr int kMbC = 128;           // channels (consumer threads = 2 * kMbC)
-constexpr int kMbR = 7;             // outputs per register group
-constexpr int kMbGroups = 4;         // register groups per thread: a thread owns <= kMbGroups * kMbR frames (T <= 112)
+// outputs per register group R and groups per thread G are template parameters: a thread owns <= G * R frames; R independent
+// FFMA2 chains, the taps are re-read once per group
+constexpr int kMbMaxOwn = 26;        // frames per thread every (R, G) variant can hold (T <= 104)
 constexpr int kMbConsumers = 2 * kMbC;
 constexpr int kMbThreads = kMbConsumers;   // no separate producer warp: 9 warps would be allocated as 12 (register file)
 
@@ -48,7 +49,7 @@ struct MemBulkArgs {
   int pf;   // L2 prefetch distance, in streams of this CTA beyond the one being copied to shared memory (0 = off)
 };
 
-template <int N1, int N2>
+template <int N1, int N2, int kMbR, int kMbGroups>
 __global__ void __launch_bounds__(kMbThreads, 1) fsmn_memory_bulk_kernel(const MemBulkArgs g) {
   constexpr int HL = N1 - 1, HR = N2;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -173,7 +174,7 @@ bool memory_bulk_fits(int n_back, int stride_back, int n_ahead, int stride_ahead
   if (cache_in || cache_out) return false;
   if (n_channels != kMbC || ldp != kMbC || ldo != kMbC || (res && ldr != kMbC)) return false;
   if (stride_back != 1 || n_back != 20 || !(n_ahead == 0 || (n_ahead == 20 && stride_ahead == 1))) return false;
-  if (n_frames < 2 || (n_frames + 3) / 4 > kMbGroups * kMbR) return false;
+  if (n_frames < 2 || (n_frames + 3) / 4 > kMbMaxOwn) return false;
   if (!aligned16(p) || !aligned16(out) || (res && !aligned16(res))) return false;
   const size_t tile = (size_t)n_frames * kMbC * 4;
   const size_t smem = (size_t)(n_back + n_ahead) * kMbC * 4 + 2 * (res ? 2 : 1) * tile + 4 * 8 + 16;
@@ -190,17 +191,30 @@ int memory_bulk_launch(const float* p, const float* wl, const float* wr, int n_a
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(fsmn_memory_bulk_kernel<20, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fsmn_memory_bulk_kernel<20, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](auto kern) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+    };
+    opt_in(fsmn_memory_bulk_kernel<20, 20, 7, 4>);  opt_in(fsmn_memory_bulk_kernel<20, 0, 7, 4>);
+    opt_in(fsmn_memory_bulk_kernel<20, 20, 13, 2>); opt_in(fsmn_memory_bulk_kernel<20, 0, 13, 2>);
+    opt_in(fsmn_memory_bulk_kernel<20, 20, 26, 1>); opt_in(fsmn_memory_bulk_kernel<20, 0, 26, 1>);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_bulk_kernel)");
     configured = true;
   }
   static const int pf = [] { const char* e = getenv("VADX_MEM_PF"); return e ? atoi(e) : 0; }();   // measured slower on B200 (2.17 -> 2.5 ms per step): off
   MemBulkArgs g{p, res, wl, wr, out, n_streams, n_frames, pf};
   const int grid = (int)std::min<int64_t>(n_streams, n_sm > 0 ? n_sm : 148);
-  if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20><<<grid, kMbThreads, smem, st>>>(g);
-  else fsmn_memory_bulk_kernel<20, 0><<<grid, kMbThreads, smem, st>>>(g);
+  static const int rg = [] { const char* e = getenv("VADX_MEM_RG"); return e ? atoi(e) : 13; }();
+  if (rg == 7) {
+    if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20, 7, 4><<<grid, kMbThreads, smem, st>>>(g);
+    else fsmn_memory_bulk_kernel<20, 0, 7, 4><<<grid, kMbThreads, smem, st>>>(g);
+  } else if (rg == 26) {
+    if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20, 26, 1><<<grid, kMbThreads, smem, st>>>(g);
+    else fsmn_memory_bulk_kernel<20, 0, 26, 1><<<grid, kMbThreads, smem, st>>>(g);
+  } else {
+    if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20, 13, 2><<<grid, kMbThreads, smem, st>>>(g);
+    else fsmn_memory_bulk_kernel<20, 0, 13, 2><<<grid, kMbThreads, smem, st>>>(g);
+  }
   return after_launch("vadx_fsmn_memory_f32(bulk)");
 }
 
