@@ -87,6 +87,28 @@ def test_large_batch_against_oracle(cuda, default_session):
     assert err <= TOL
 
 
+def test_full_step_is_batch_independent(cuda, default_session):
+    """BASELINE.json's step size (8192 chunks = 802 816 frame rows, 6272 row tiles, 42-43 tiles per CTA: ring and
+    accumulator wrap-arounds, the tile-ahead L2 prefetch past the last tile).  The oracle cannot run this size in
+    seconds; the size-independent property is that a chunk's probabilities do not depend on what else is in the batch:
+    every chunk of the big call must equal, bit for bit, the same chunk run in a 64-chunk call, and a sample of them
+    is checked against the oracle."""
+    cfg = W.FireRedConfig()
+    n = 8192
+    chunks = synth.synth_chunks_fast(n, 16000, seed=11)
+    d = torch.from_numpy(chunks).to(cuda)
+    big = default_session.run_batch(d).cpu().numpy()
+    assert big.shape[0] == n and np.isfinite(big).all()
+    for lo in (0, 4032, n - 64):                      # first, middle (straddles CTA boundaries), last
+        small = default_session.run_batch(d[lo:lo + 64].contiguous()).cpu().numpy()
+        assert np.array_equal(big[lo:lo + 64], small), f"chunks {lo}..{lo + 63} depend on the batch"
+    idx = np.array([0, 1, 97, 4095, 4096, n - 2, n - 1])
+    ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks[idx]).numpy()
+    err = np.abs(big[idx] - ref).max()
+    print("full-step sample max abs err", err)
+    assert err <= TOL
+
+
 def _oracle_timestamps(probs, n_valid, wav_dur, post):
     dec = OP.frame_decisions(probs[:n_valid], post.smooth_window_size, post.prob_threshold, post.min_speech_frame,
                              post.max_speech_frame, post.min_silence_frame, post.merge_silence_frame,
@@ -182,3 +204,19 @@ def test_opt_in_fused_block_path_matches_default(cuda):
     b._e.set_scalar("engine.fuse_block", 1.0)
     pa, pb = a.run_batch(d), b.run_batch(d)
     assert (pa - pb).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("n", [70, 3, 333])
+def test_staged_hidden_handover_matches_fp32_rows(cuda, n):
+    """engine.split_hidden (default on): fc1 writes relu(h) as the two-term bf16 operand stages fc2's MMA reads.  The split
+    of h is the same arithmetic the fc2 loader would do, so the probabilities must be IDENTICAL to the fp32-row path
+    (ragged last row tile included: n * 98 rows is not a multiple of 128)."""
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, 0)
+    d = torch.from_numpy(synth.synth_chunks_fast(n, 16000, seed=6)).to(cuda)
+    a = vadx.FireRedSession(w, cfg)
+    b = vadx.FireRedSession(w, cfg)
+    b._e.set_scalar("engine.split_hidden", 0.0)
+    pa, pb = a.run_batch(d), b.run_batch(d)
+    assert torch.isfinite(pa).all()
+    assert torch.equal(pa, pb)

@@ -44,6 +44,9 @@ struct TcArgs {
   unsigned backoff_ld, backoff_epi;   // nanoseconds between mbarrier probes of the loader / epilogue warps
   int pf_tiles;   // L2 prefetch distance in row tiles of this CTA (0 = off)
   int k_live;     // columns < k_live are read by the MMA (n_k16 * 16)
+  int x_split;    // 1: X is a sequence of ready-made operand stages [tile][k chunk][hi | lo] (16 KB swizzled bf16 images
+                  //    written by a y_split producer): one thread streams them in with cp.async.bulk, no loader warps
+  int y_split;    // 1: Y is written as such stages for a consumer with K = N (N % 64 == 0), rows padded to whole tiles
   int pf_spread, pf_at;   // pf_at: the K step of the current tile at which the prefetch is issued
   const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
   float head_b;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), kTcLoaderWarps);     // one elected lane per loader warp
+      mbar_init(full_bar(s), g.x_split ? 1 : kTcLoaderWarps);     // one elected lane per loader warp / the bulk-copy thread
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -156,6 +159,24 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
           if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(b));        // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < kTcLoaderWarps && g.x_split) {
+    // ===================== ready-made operand stages: one thread, one 32 KB bulk copy pair per stage =====================
+    if (threadIdx.x == 0) {
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(g.X);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < g.kc; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, g.backoff_ld);
+          mbar_expect_tx(full_bar(stage), (uint32_t)kTcStageBytes);
+          const uint8_t* src = img + ((size_t)tile * g.kc + c) * kTcStageBytes;
+          const uint32_t dst = smem_u32(a_smem) + (uint32_t)stage * kTcStageBytes;
+          bulk_g2s(dst, src, kTcTileBytes, full_bar(stage));
+          bulk_g2s(dst + kTcTileBytes, src + kTcTileBytes, kTcTileBytes, full_bar(stage));
+          if (++stage == g.n_stages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp < kTcLoaderWarps) {
@@ -290,6 +311,44 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
           for (int j = 0; j < 16; ++j) acc = fmaf(bias_act<ACT>(v[j], bias_s[c0 + j]), head_s[c0 + j], acc);
         }
         if (row_ok) g.head_out[row] = 1.0f / (1.0f + expf(-(acc + g.head_b)));
+      } else if (g.y_split) {
+        // output as the next layer's operand stages: bias/activation, the two-term bf16 split, and the swizzled 16 KB
+        // images [tile][N/64][hi | lo] -- the consumer streams them with bulk copies and converts nothing.
+        // Staged per warp as 32 rows x (16 hi words | 16 lo words); eight lanes write one row's four hi and four lo chunks.
+        uint32_t* my = reinterpret_cast<uint32_t*>(stage_out + (q * 32) * kTcOutLd);
+        uint8_t* yimg = reinterpret_cast<uint8_t*>(g.Y) + (size_t)tile * (g.N / kTcBK) * kTcStageBytes;
+        for (int c0 = 0; c0 < g.N; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            split2(bias_act<ACT>(v[4 * j], b.x), bias_act<ACT>(v[4 * j + 1], b.y), hi[2 * j], lo[2 * j]);
+            split2(bias_act<ACT>(v[4 * j + 2], b.z), bias_act<ACT>(v[4 * j + 3], b.w), hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(my + lane * kTcOutLd);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            d4[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          __syncwarp();
+          const int piece = lane & 7, half = piece >> 2, ch = piece & 3;
+          uint8_t* base = yimg + (size_t)(c0 / kTcBK) * kTcStageBytes + (size_t)half * kTcTileBytes;
+          const int jj = ((c0 % kTcBK) >> 3) + ch;   // 16-byte chunk of the 128-byte image row
+          uint4 val[8];
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr)
+            val[itr] = *reinterpret_cast<const uint4*>(my + (itr * 4 + (lane >> 3)) * kTcOutLd + half * 16 + ch * 4);
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int r = q * 32 + itr * 4 + (lane >> 3);
+            *reinterpret_cast<uint4*>(base + r * 128 + ((jj ^ (r & 7)) << 4)) = val[itr];
+          }
+          __syncwarp();
+        }
       } else if (!g.res && g.vec_y && !(g.debug & 1) && !(g.debug & 8)) {
         // coalesced path: each thread stages 32 columns of its row in shared memory, then the warp
         // writes them out 4 rows x 128 B per instruction (row-per-thread stores would touch 32
@@ -491,7 +550,18 @@ extern "C" int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* 
 
 static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                             const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
-                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream);
+                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
+                            int x_split = 0, int y_split = 0);
+
+// Internal (model.cu): the same layer with its input and/or output in the operand-stage format (TcArgs::x_split / y_split).
+int linear_tc_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows, int n_in,
+                         int n_out, int act, int x_split, int y_split, void* stream) {
+  VADX_REQUIRE(d_y, "linear_tc_stages_f32: null pointer");
+  VADX_REQUIRE(!x_split || n_in % kTcBK == 0, "linear_tc_stages_f32: a staged input needs K %% 64 == 0 (got %d)", n_in);
+  VADX_REQUIRE(!y_split || n_out % kTcBK == 0, "linear_tc_stages_f32: a staged output needs N %% 64 == 0 (got %d)", n_out);
+  return linear_tc_launch(d_x, n_in, d_wimg, d_bias, nullptr, 0, d_y, n_out, n_rows, n_in, n_out, act, nullptr, 0.f, nullptr,
+                          stream, x_split, y_split);
+}
 
 extern "C" int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                                   const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows,
@@ -511,7 +581,8 @@ extern "C" int vadx_linear_head_tc_f32(const float* d_x, int64_t ldx, const void
 
 static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                             const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
-                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream) {
+                            int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
+                            int x_split, int y_split) {
   StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
   VADX_REQUIRE(d_x && d_wimg, "vadx_linear_tc_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
@@ -565,6 +636,9 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     static const int spread = [] { const char* e = getenv("VADX_LIN_PF_SPREAD"); return e ? atoi(e) : 0; }();
     static const int at = [] { const char* e = getenv("VADX_LIN_PF_AT"); return e ? atoi(e) : 0; }();
     g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
+    g.x_split = x_split; g.y_split = y_split;
+    if (x_split) { g.pf_tiles = 0; VADX_REQUIRE(aligned16(d_x), "linear_tc: staged input must be 16-byte aligned"); }
+    if (y_split) VADX_REQUIRE(aligned16(d_y), "linear_tc: staged output must be 16-byte aligned");
     g.pf_spread = (spread && s.kc <= 8 && ((kTcBM / 16) % s.kc) == 0 && lw_is16()) ? 1 : 0;
   }
   {

@@ -167,7 +167,7 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   float* sig2 = rate_scale == 1.0 ? nullptr : ws.take<float>(slab * Lp);
   float* power = ws.take<float>(slab_rows * h.ld_power());
   float* feat = ws.take<float>(slab_rows * h.n_mels);
-  float* bufH = ws.take<float>(slab_rows * h.H);
+  float* bufH = ws.take<float>(round_up(slab_rows, 128) * h.H);   // whole row tiles: it may hold operand stages (split_hidden)
   float* bufH2 = h.M > 1 ? ws.take<float>(slab_rows * h.H) : nullptr;
   float* bufP = ws.take<float>(slab_rows * h.P);
   float* memA0 = ws.take<float>(slab_rows * h.P);
@@ -249,6 +249,16 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     // (8192 chunks: 10.8 ms with a dedicated MMA warp / 18.7 ms in the 12-warp layout vs 8.97 ms unfused).
     const bool fuse_block = use_tc && !cin && m->scalar("engine.fuse_block", 0.0) != 0.0 &&
                             vadx_fc2_memory_tc_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1);
+    // fc1 -> fc2 hand-over in the tensor-core operand format: fc1's epilogue writes relu(h) already split into the two bf16
+    // terms and swizzled into the 16 KB stage images fc2's MMA reads, fc2 streams them in with bulk copies (same bytes in
+    // HBM as fp32 rows; fc2 loses its load/convert/store loader, the stage the L1 data pipe was saturated by)
+    const bool split_hidden = use_tc && !fuse_block && (h.H % 64) == 0 && m->scalar("engine.split_hidden", 1.0) != 0.0 &&
+                              !getenv("VADX_NO_SPLIT_HIDDEN");
+    auto fc1 = [&](const float* x, int n_in, const std::string& w, const char* b) -> int {
+      const uint8_t* img = split_hidden ? m->d<uint8_t>(w + "#TC") : nullptr;
+      if (img) return linear_tc_stages_f32(x, img, b ? m->d<float>(b) : nullptr, bufH, rows, n_in, h.H, VADX_ACT_RELU, 0, 1, st);
+      return lin(x, n_in, w, b, nullptr, bufH, h.H, VADX_ACT_RELU);
+    };
     auto block_tail = [&](const std::string& w, const char* b, int act, const std::string& mem_pre, int layer, const float* res,
                           float* o) -> int {
       const uint8_t* img = fuse_block ? m->d<uint8_t>(w + "#TC") : nullptr;
@@ -257,15 +267,17 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                                       m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,
                                       h.N2 > 0 ? m->d<float>(mem_pre + "lookahead_filter.weight") : nullptr, h.N2, res, o, S, T,
                                       h.H, st);
-      VADX_TRY(lin(bufH, h.H, w, b, nullptr, bufP, h.P, act));
+      const uint8_t* simg = split_hidden ? m->d<uint8_t>(w + "#TC") : nullptr;
+      if (simg) VADX_TRY(linear_tc_stages_f32(bufH, simg, b ? m->d<float>(b) : nullptr, bufP, rows, h.H, h.P, act, 1, 0, st));
+      else VADX_TRY(lin(bufH, h.H, w, b, nullptr, bufP, h.P, act));
       return memory(layer, mem_pre, bufP, res, o);
     };
-    VADX_TRY(lin(feat, h.idim, "dfsmn.fc1.0.weight", "dfsmn.fc1.0.bias", nullptr, bufH, h.H, VADX_ACT_RELU));
+    VADX_TRY(fc1(feat, h.idim, "dfsmn.fc1.0.weight", "dfsmn.fc1.0.bias"));
     VADX_TRY(block_tail("dfsmn.fc2.0.weight", "dfsmn.fc2.0.bias", VADX_ACT_RELU, "dfsmn.fsmn1.", 0, nullptr, memA));
     for (int i = 0; i < h.R - 1; ++i) {
       std::string pre = "dfsmn.fsmns." + std::to_string(i) + ".";
       std::string b1 = pre + "fc1.0.bias";
-      VADX_TRY(lin(memA, h.P, pre + "fc1.0.weight", b1.c_str(), nullptr, bufH, h.H, VADX_ACT_RELU));
+      VADX_TRY(fc1(memA, h.P, pre + "fc1.0.weight", b1.c_str()));
       VADX_TRY(block_tail(pre + "fc2.weight", nullptr, VADX_ACT_NONE, pre + "fsmn.", i + 1, memA, memB));
       std::swap(memA, memB);
     }

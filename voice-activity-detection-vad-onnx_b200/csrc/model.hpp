@@ -46,6 +46,11 @@ struct Workspace {  // bump allocator over the caller's buffer
 
 }  // namespace vadx
 
+// gemm_tc.cu: dense layer whose input and/or output is in the tensor-core operand-stage format ([row tile][K chunk][hi | lo]
+// 16 KB swizzled bf16 images, rows padded to whole 128-row tiles) instead of fp32 rows
+int linear_tc_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows, int n_in,
+                         int n_out, int act, int x_split, int y_split, void* stream);
+
 using namespace vadx;
 
 struct vadx_model {
