@@ -215,8 +215,27 @@ def test_staged_hidden_handover_matches_fp32_rows(cuda, n):
     w = W.firered_random_init(cfg, 0)
     d = torch.from_numpy(synth.synth_chunks_fast(n, 16000, seed=6)).to(cuda)
     a = vadx.FireRedSession(w, cfg)
+    a._e.set_scalar("engine.fuse_stages", 0.0)      # the staged hand-over alone, two-kernel block tail
     b = vadx.FireRedSession(w, cfg)
-    b._e.set_scalar("engine.split_hidden", 0.0)
+    b._e.set_scalar("engine.split_hidden", 0.0)     # fp32 rows everywhere (also switches the fused tail off)
     pa, pb = a.run_batch(d), b.run_batch(d)
     assert torch.isfinite(pa).all()
     assert torch.equal(pa, pb)
+
+
+@pytest.mark.parametrize("n", [70, 1, 300])
+def test_fused_block_from_stages_matches_default(cuda, n):
+    """engine.fuse_stages (default on): fc1 writes per-stream operand stages, block_stages.cu runs fc2 (transposed tcgen05 product,
+    accumulator = p^T) and the memory block's FIR straight out of tensor memory.  Same products and the same tap order
+    as the two-kernel path: probabilities within 2e-5 of it."""
+    cfg = W.FireRedConfig()
+    w = W.firered_random_init(cfg, 0)
+    d = torch.from_numpy(synth.synth_chunks_fast(n, 16000, seed=8)).to(cuda)
+    a = vadx.FireRedSession(w, cfg)
+    a._e.set_scalar("engine.fuse_stages", 0.0)      # two-kernel block tail
+    b = vadx.FireRedSession(w, cfg)                 # default: fused
+    pa, pb = a.run_batch(d), b.run_batch(d)
+    assert torch.isfinite(pb).all()
+    err = (pa - pb).abs().max().item()
+    print("fused-from-stages vs default max abs diff", err)
+    assert err <= 2e-5

@@ -47,6 +47,9 @@ struct TcArgs {
   int x_split;    // 1: X is a sequence of ready-made operand stages [tile][k chunk][hi | lo] (16 KB swizzled bf16 images
                   //    written by a y_split producer): one thread streams them in with cp.async.bulk, no loader warps
   int y_split;    // 1: Y is written as such stages for a consumer with K = N (N % 64 == 0), rows padded to whole tiles
+                  // 2: the same, but one image set per STREAM of ys_T rows ([stream][N/64][hi | lo], images of ys_img
+                  //    bytes = round_up(ys_T, 16) rows): the fused fc2 + memory kernel's operand (block_stages.cu)
+  int ys_T, ys_img;
   int pf_spread, pf_at;   // pf_at: the K step of the current tile at which the prefetch is issued
   const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
   float head_b;
@@ -316,7 +319,25 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
         // images [tile][N/64][hi | lo] -- the consumer streams them with bulk copies and converts nothing.
         // Staged per warp as 32 rows x (16 hi words | 16 lo words); eight lanes write one row's four hi and four lo chunks.
         uint32_t* my = reinterpret_cast<uint32_t*>(stage_out + (q * 32) * kTcOutLd);
-        uint8_t* yimg = reinterpret_cast<uint8_t*>(g.Y) + (size_t)tile * (g.N / kTcBK) * kTcStageBytes;
+        uint8_t* yimg = reinterpret_cast<uint8_t*>(g.Y) + (g.y_split == 1 ? (size_t)tile * (g.N / kTcBK) * kTcStageBytes : 0);
+        // per-stream images: byte offset of each of this lane's eight rows (stream base + row in the image), ~0 = past M
+        uint32_t roff[8];
+        if (g.y_split == 2) {
+          // one division per tile and lane; the lane's rows are 4 apart and a stream has more than 4 rows, so the
+          // (stream, row in stream) pair of the next row is an add and at most one wrap (eight 64-bit divisions here
+          // made the N = 256 epilogue, already the busiest warps of the kernel, 40 % slower)
+          const int64_t grow0 = (int64_t)tile * kTcBM + q * 32 + (lane >> 3);
+          int64_t sidx = grow0 / g.ys_T;
+          int t = (int)(grow0 - sidx * g.ys_T);
+          const uint32_t stream_bytes = (uint32_t)((g.N / kTcBK) * 2 * g.ys_img);
+          uint32_t sbase = (uint32_t)sidx * stream_bytes;
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            roff[itr] = grow0 + itr * 4 < g.M ? sbase + (uint32_t)t * 128u : 0xffffffffu;
+            t += 4;
+            if (t >= g.ys_T) { t -= g.ys_T; sbase += stream_bytes; }
+          }
+        }
         for (int c0 = 0; c0 < g.N; c0 += 32) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
@@ -336,16 +357,24 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
           }
           __syncwarp();
           const int piece = lane & 7, half = piece >> 2, ch = piece & 3;
-          uint8_t* base = yimg + (size_t)(c0 / kTcBK) * kTcStageBytes + (size_t)half * kTcTileBytes;
           const int jj = ((c0 % kTcBK) >> 3) + ch;   // 16-byte chunk of the 128-byte image row
           uint4 val[8];
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr)
             val[itr] = *reinterpret_cast<const uint4*>(my + (itr * 4 + (lane >> 3)) * kTcOutLd + half * 16 + ch * 4);
+          if (g.y_split == 1) {
+            uint8_t* base = yimg + (size_t)(c0 / kTcBK) * kTcStageBytes + (size_t)half * kTcTileBytes;
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int r = q * 32 + itr * 4 + (lane >> 3);
-            *reinterpret_cast<uint4*>(base + r * 128 + ((jj ^ (r & 7)) << 4)) = val[itr];
+            for (int itr = 0; itr < 8; ++itr) {
+              const int r = q * 32 + itr * 4 + (lane >> 3);
+              *reinterpret_cast<uint4*>(base + r * 128 + ((jj ^ (r & 7)) << 4)) = val[itr];
+            }
+          } else {
+            uint8_t* base = yimg + (size_t)((c0 / kTcBK) * 2 + half) * g.ys_img;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr)
+              if (roff[itr] != 0xffffffffu)
+                *reinterpret_cast<uint4*>(base + roff[itr] + ((jj ^ ((roff[itr] >> 7) & 7)) << 4)) = val[itr];
           }
           __syncwarp();
         }
@@ -522,6 +551,10 @@ TcShape tc_shape(int n_in, int n_out) {
 
 using namespace vadx;
 
+// fc1 with its output as per-stream operand stages (rows_per_stream rows per image set)
+int linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows,
+                                int rows_per_stream, int n_in, int n_out, int act, void* stream);
+
 extern "C" int vadx_tc_supported(int n_in, int n_out) { return tc_shape(n_in, n_out).ok ? 1 : 0; }
 
 extern "C" int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* h_img, size_t img_capacity,
@@ -554,6 +587,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
                             int x_split = 0, int y_split = 0);
 
 // Internal (model.cu): the same layer with its input and/or output in the operand-stage format (TcArgs::x_split / y_split).
+static int g_ys_T = 0;   // rows per stream of the next y_split == 2 launch (set by linear_tc_stream_stages_f32)
+
 int linear_tc_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows, int n_in,
                          int n_out, int act, int x_split, int y_split, void* stream) {
   VADX_REQUIRE(d_y, "linear_tc_stages_f32: null pointer");
@@ -637,6 +672,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     static const int at = [] { const char* e = getenv("VADX_LIN_PF_AT"); return e ? atoi(e) : 0; }();
     g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
     g.x_split = x_split; g.y_split = y_split;
+    g.ys_T = g_ys_T; g.ys_img = (int)round_up(g_ys_T, 16) * 128;
+    if (y_split == 2) VADX_REQUIRE(g_ys_T > 4 && (round_up(g_ys_T, 16) * 128) % 1024 == 0, "linear_tc: per-stream stages need round_up(T, 16) %% 8 == 0");
     if (x_split) { g.pf_tiles = 0; VADX_REQUIRE(aligned16(d_x), "linear_tc: staged input must be 16-byte aligned"); }
     if (y_split) VADX_REQUIRE(aligned16(d_y), "linear_tc: staged output must be 16-byte aligned");
     g.pf_spread = (spread && s.kc <= 8 && ((kTcBM / 16) % s.kc) == 0 && lw_is16()) ? 1 : 0;
@@ -668,4 +705,12 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   }
 #undef VADX_LIN_LAUNCH
   return after_launch("vadx_linear_tc_f32");
+}
+
+int linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows,
+                                int rows_per_stream, int n_in, int n_out, int act, void* stream) {
+  g_ys_T = rows_per_stream;
+  const int rc = linear_tc_stages_f32(d_x, d_wimg, d_bias, d_y, n_rows, n_in, n_out, act, 0, 2, stream);
+  g_ys_T = 0;
+  return rc;
 }

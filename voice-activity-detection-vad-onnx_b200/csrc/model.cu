@@ -167,7 +167,10 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
   float* sig2 = rate_scale == 1.0 ? nullptr : ws.take<float>(slab * Lp);
   float* power = ws.take<float>(slab_rows * h.ld_power());
   float* feat = ws.take<float>(slab_rows * h.n_mels);
-  float* bufH = ws.take<float>(round_up(slab_rows, 128) * h.H);   // whole row tiles: it may hold operand stages (split_hidden)
+  // whole row tiles / per-stream image sets: bufH may hold operand stages instead of fp32 rows (split_hidden, fuse_stages)
+  const int64_t bufH_floats = std::max<int64_t>(round_up(slab_rows, 128) * h.H,
+                                                (h.H % 64) == 0 ? slab * (int64_t)(fc2_memory_stages_stream_bytes(h.H, T) / 4) : 0);
+  float* bufH = ws.take<float>(bufH_floats);
   float* bufH2 = h.M > 1 ? ws.take<float>(slab_rows * h.H) : nullptr;
   float* bufP = ws.take<float>(slab_rows * h.P);
   float* memA0 = ws.take<float>(slab_rows * h.P);
@@ -254,7 +257,13 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     // HBM as fp32 rows; fc2 loses its load/convert/store loader, the stage the L1 data pipe was saturated by)
     const bool split_hidden = use_tc && !fuse_block && (h.H % 64) == 0 && m->scalar("engine.split_hidden", 1.0) != 0.0 &&
                               !getenv("VADX_NO_SPLIT_HIDDEN");
+    // fc2 + memory block + residual in one kernel fed by per-stream stages (block_stages.cu): p never reaches HBM
+    const bool fuse_stages = split_hidden && !cin && fc2_memory_stages_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1) &&
+                             m->scalar("engine.fuse_stages", 1.0) != 0.0 && !getenv("VADX_NO_FUSE_STAGES");
     auto fc1 = [&](const float* x, int n_in, const std::string& w, const char* b) -> int {
+      if (fuse_stages)
+        return linear_tc_stream_stages_f32(x, m->d<uint8_t>(w + "#TC"), b ? m->d<float>(b) : nullptr, bufH, rows, T, n_in, h.H,
+                                           VADX_ACT_RELU, st);
       const uint8_t* img = split_hidden ? m->d<uint8_t>(w + "#TC") : nullptr;
       if (img) return linear_tc_stages_f32(x, img, b ? m->d<float>(b) : nullptr, bufH, rows, n_in, h.H, VADX_ACT_RELU, 0, 1, st);
       return lin(x, n_in, w, b, nullptr, bufH, h.H, VADX_ACT_RELU);
@@ -267,6 +276,10 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                                       m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,
                                       h.N2 > 0 ? m->d<float>(mem_pre + "lookahead_filter.weight") : nullptr, h.N2, res, o, S, T,
                                       h.H, st);
+      if (fuse_stages)
+        return fc2_memory_stages_f32(bufH, h.H, m->d<uint8_t>(w + "#TC"), b ? m->d<float>(b) : nullptr, act,
+                                     m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,
+                                     m->d<float>(mem_pre + "lookahead_filter.weight"), h.N2, res, o, S, T, st);
       const uint8_t* simg = split_hidden ? m->d<uint8_t>(w + "#TC") : nullptr;
       if (simg) VADX_TRY(linear_tc_stages_f32(bufH, simg, b ? m->d<float>(b) : nullptr, bufP, rows, h.H, h.P, act, 1, 0, st));
       else VADX_TRY(lin(bufH, h.H, w, b, nullptr, bufP, h.P, act));

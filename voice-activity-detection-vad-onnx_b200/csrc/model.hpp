@@ -51,6 +51,15 @@ struct Workspace {  // bump allocator over the caller's buffer
 int linear_tc_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows, int n_in,
                          int n_out, int act, int x_split, int y_split, void* stream);
 
+// gemm_tc.cu / block_stages.cu: fc1 writing per-stream operand stages, and the fused fc2 + memory block that consumes them
+int linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows,
+                                int rows_per_stream, int n_in, int n_out, int act, void* stream);
+size_t fc2_memory_stages_stream_bytes(int n_in, int n_frames);
+bool fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, int stride_back, int n_ahead, int stride_ahead);
+int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, const float* d_bias, int act, const float* d_wl,
+                          int n_back, const float* d_wr, int n_ahead, const float* d_res, float* d_out, int64_t n_streams,
+                          int n_frames, void* stream);
+
 using namespace vadx;
 
 struct vadx_model {
