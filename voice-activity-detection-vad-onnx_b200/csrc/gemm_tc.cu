@@ -673,6 +673,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
     g.x_split = x_split; g.y_split = y_split;
     g.ys_T = g_ys_T; g.ys_img = (int)round_up(g_ys_T, 16) * 128;
+    if (y_split == 2) VADX_REQUIRE(ceil_div(n_rows, (int64_t)std::max(1, g_ys_T)) * (int64_t)(n_out / kTcBK) * 2 * (round_up(g_ys_T, 16) * 128) < (1LL << 32),
+                                   "linear_tc: per-stream stages of %lld rows exceed the 32-bit image offsets", (long long)n_rows);
     if (y_split == 2) VADX_REQUIRE(g_ys_T > 4 && (round_up(g_ys_T, 16) * 128) % 1024 == 0, "linear_tc: per-stream stages need round_up(T, 16) %% 8 == 0");
     if (x_split) { g.pf_tiles = 0; VADX_REQUIRE(aligned16(d_x), "linear_tc: staged input must be 16-byte aligned"); }
     if (y_split) VADX_REQUIRE(aligned16(d_y), "linear_tc: staged output must be 16-byte aligned");

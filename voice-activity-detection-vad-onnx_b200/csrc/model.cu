@@ -259,7 +259,9 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                               !getenv("VADX_NO_SPLIT_HIDDEN");
     // fc2 + memory block + residual in one kernel fed by per-stream stages (block_stages.cu): p never reaches HBM
     const bool fuse_stages = split_hidden && !cin && fc2_memory_stages_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1) &&
-                             m->scalar("engine.fuse_stages", 1.0) != 0.0 && !getenv("VADX_NO_FUSE_STAGES");
+                             m->scalar("engine.fuse_stages", 1.0) != 0.0 && !getenv("VADX_NO_FUSE_STAGES") &&
+                             // fc1's epilogue addresses a stream's image set with 32-bit byte offsets
+                             S * (int64_t)fc2_memory_stages_stream_bytes(h.H, T) < (1LL << 32);
     auto fc1 = [&](const float* x, int n_in, const std::string& w, const char* b) -> int {
       if (fuse_stages)
         return linear_tc_stream_stages_f32(x, m->d<uint8_t>(w + "#TC"), b ? m->d<float>(b) : nullptr, bufH, rows, T, n_in, h.H,
