@@ -36,9 +36,10 @@ struct BsArgs {
   int64_t n_streams;
   int kc, n_k16;
   int pf;   // L2 prefetch distance in streams of this CTA (0 = off)
+  int mirror;   // 1: both halves run one shared body, the second in reversed time (needs NP == 2, T even, N1 == N2)
 };
 
-template <int ACT, int T, int N1, int N2, int NP, int kBsR>   // NP time parts, kBsR FIR outputs per register group
+template <int ACT, int T, int N1, int N2, int NP, int kBsR, bool MIRROR>   // NP time parts, kBsR FIR outputs per register group
 __global__ void __launch_bounds__(NP == 2 ? 384 : 512, 1) fc2_memory_stages_kernel(const BsArgs g) {
   constexpr int kBsFirWarps = 4 * NP;
   constexpr int TP = (T + 15) / 16 * 16;     // accumulator columns = N of the MMA
@@ -155,10 +156,26 @@ __global__ void __launch_bounds__(NP == 2 ? 384 : 512, 1) fc2_memory_stages_kern
     // the channel's taps are loop invariants: in registers for the whole kernel (a shared-memory read per tap and group
     // put ~30 cycles of latency in front of every seven FMAs)
     float tw[N1 + N2];
+    if (!MIRROR) {
 #pragma unroll
-    for (int k = 0; k < N1; ++k) tw[k] = __ldg(g.wl + c * N1 + k);
+      for (int k = 0; k < N1; ++k) tw[k] = __ldg(g.wl + c * N1 + k);
 #pragma unroll
-    for (int k = 0; k < N2; ++k) tw[N1 + k] = __ldg(g.wr + c * N2 + k);
+      for (int k = 0; k < N2; ++k) tw[N1 + k] = __ldg(g.wr + c * N2 + k);
+    }
+    // Mirrored form (g.mirror, T even, two parts, N2 == N1): the second half of the frames is processed in REVERSED time, which
+    // turns its right edge into a left edge -- both halves then run the SAME unrolled code (one 49-output body instead of
+    // two: half the instruction footprint of a kernel that is instruction-fetch bound).  Canonical time u = t (first half)
+    // or T-1-t (second half); canonical taps over offsets d = -N2 .. +N2: forward c_d = wl[N1-1+d] (d <= 0) | wr[d-1] (d > 0),
+    // mirrored c'_d = c_{-d}; the one offset a half does not have (d = -N2 forward, +N2 mirrored) is a zero tap.
+    constexpr int kD = N2;                       // canonical offsets -kD .. +kD
+    float tc[2 * kD + 1];
+    if (MIRROR) {
+#pragma unroll
+      for (int i = 0; i < 2 * kD + 1; ++i) {
+        const int d = part == 0 ? i - kD : kD - i;                 // the physical offset this canonical tap applies to
+        tc[i] = d == -kD ? 0.f : (d <= 0 ? __ldg(g.wl + c * N1 + (N1 - 1 + d)) : __ldg(g.wr + c * N2 + (d - 1)));
+      }
+    }
     int it = 0;
     for (int64_t s = blockIdx.x; s < g.n_streams; s += gridDim.x, ++it) {
       const int b = it & 1;
@@ -167,6 +184,65 @@ __global__ void __launch_bounds__(NP == 2 ? 384 : 512, 1) fc2_memory_stages_kern
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 128);
       const float* rs = g.res ? g.res + (size_t)s * T * kBsC + c : nullptr;
       float* os = g.out + (size_t)s * T * kBsC + c;
+      if (MIRROR) {
+        constexpr int kOut = T / 2;                      // outputs per half
+        constexpr int kWin = kOut + kD;                  // canonical window: P[0 .. kOut-1+kD], P[u] = p[u] or p[T-1-u]
+        constexpr int kLd = (kWin + 7) / 8 * 8;
+        float win[kLd];
+        if (part == 0) {
+#pragma unroll
+          for (int i = 0; i < kLd / 8; ++i) tmem_ld8(taddr + (uint32_t)(8 * i), win + 8 * i);
+        } else {
+          // columns T-1-u for u = 0 .. kWin-1, i.e. [T-kWin, T): loaded ascending from an 8-column boundary, renamed reversed
+          constexpr int c_lo = (T - kWin) / 8 * 8;
+          constexpr int n_ld = (T - c_lo + 7) / 8;
+          static_assert(c_lo + 8 * n_ld <= TP, "mirrored window load runs past the accumulator");
+#pragma unroll
+          for (int i = 0; i < n_ld; ++i) {
+            float tmp[8];
+            tmem_ld8(taddr + (uint32_t)(c_lo + 8 * i), tmp);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int u = T - 1 - (c_lo + 8 * i + j);
+              if (u >= 0 && u < kLd) win[u] = tmp[j];
+            }
+          }
+#pragma unroll
+          for (int u = T - c_lo; u < kLd; ++u) win[u] = 0.f;    // (not reached by the loads; never used either)
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(b));      // the accumulator is free for the stream after next
+#pragma unroll
+        for (int j = 0; j < kLd; ++j) win[j] = apply_act(win[j] + bias_c, ACT);
+        constexpr int kGroups = (kOut + kBsR - 1) / kBsR;
+#pragma unroll
+        for (int gi = 0; gi < kGroups; ++gi) {
+          const int u0 = gi * kBsR;
+          float rv[kBsR], acc[kBsR];
+#pragma unroll
+          for (int r = 0; r < kBsR; ++r) {
+            const int t = part == 0 ? u0 + r : T - 1 - (u0 + r);
+            rv[r] = (rs && u0 + r < kOut) ? __ldg(rs + (size_t)t * kBsC) : 0.f;
+          }
+#pragma unroll
+          for (int r = 0; r < kBsR; ++r) acc[r] = u0 + r < kOut ? win[u0 + r] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 2 * kD + 1; ++i) {
+#pragma unroll
+            for (int r = 0; r < kBsR; ++r) {
+              const int col = u0 + r + i - kD;
+              if (u0 + r < kOut && col >= 0) acc[r] = fmaf(tc[i], win[col], acc[r]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kBsR; ++r) {
+            const int t = part == 0 ? u0 + r : T - 1 - (u0 + r);
+            if (u0 + r < kOut) os[(size_t)t * kBsC] = acc[r] + rv[r];
+          }
+        }
+        continue;
+      }
       // Both parts fully unrolled with compile-time window indices and edge tests.  (A looped variant -- one 8-output
       // group body, the window shifted by 8 registers and refilled from TMEM between groups -- is 15 times less code
       // but measured 60 % slower; this one is instruction-fetch bound, ncu: 60 % of stall samples "no instruction".)
@@ -216,7 +292,8 @@ __global__ void __launch_bounds__(NP == 2 ? 384 : 512, 1) fc2_memory_stages_kern
             if (t0 + r < hb) os[(size_t)(t0 + r) * kBsC] = acc[r] + rv[r];
         }
       };
-      if (part == 0) fir(std::integral_constant<int, 0>{});
+      if (MIRROR) {
+      } else if (part == 0) fir(std::integral_constant<int, 0>{});
       else if (part == 1) fir(std::integral_constant<int, 1>{});
       else if (NP > 2) fir(std::integral_constant<int, (NP > 2 ? 2 : 0)>{});
     }
@@ -250,6 +327,11 @@ bool fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, 
   return bs_smem_bytes(n_in / kTcBK, n_frames, n_back, n_ahead) <= (size_t)kTcSmemBudget;
 }
 
+static int parts_env() {
+  static const int parts = [] { const char* e = getenv("VADX_BS_PARTS"); return e && atoi(e) == 3 ? 3 : 2; }();
+  return parts;
+}
+
 int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, const float* d_bias, int act, const float* d_wl,
                           int n_back, const float* d_wr, int n_ahead, const float* d_res, float* d_out, int64_t n_streams,
                           int n_frames, void* stream) {
@@ -269,8 +351,9 @@ int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, cons
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     };
-    opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7>);  opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7>);
-    opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7>); opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 3, 7>);
+    opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, false>);  opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, false>);
+    opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, true>);   opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, true>);
+    opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7, false>); opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 3, 7, false>);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fc2_memory_stages_kernel)");
     configured = true;
   }
@@ -280,16 +363,21 @@ int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, cons
   g.kc = n_in / kTcBK; g.n_k16 = n_in / 16;
   static const int pf = [] { const char* e = getenv("VADX_BS_PF"); return e ? atoi(e) : 0; }();   // measured slower on B200: off
   g.pf = pf;
+  static const int mirror = [] { const char* e = getenv("VADX_BS_MIRROR"); return e ? atoi(e) : 1; }();
+  g.mirror = (mirror && parts_env() == 2) ? 1 : 0;
   const size_t smem = bs_smem_bytes(g.kc, n_frames, n_back, n_ahead);
   const int grid = (int)std::min<int64_t>(n_streams, n_sm > 0 ? n_sm : 148);
-  static const int parts = [] { const char* e = getenv("VADX_BS_PARTS"); return e && atoi(e) == 3 ? 3 : 2; }();
+  const int parts = parts_env();
   cudaStream_t cs = (cudaStream_t)stream;
   if (parts == 2) {
-    if (act == VADX_ACT_RELU) fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7><<<grid, 10 * 32, smem, cs>>>(g);
-    else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7><<<grid, 10 * 32, smem, cs>>>(g);
+    if (g.mirror) {
+      if (act == VADX_ACT_RELU) fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, true><<<grid, 10 * 32, smem, cs>>>(g);
+      else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, true><<<grid, 10 * 32, smem, cs>>>(g);
+    } else if (act == VADX_ACT_RELU) fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, false><<<grid, 10 * 32, smem, cs>>>(g);
+    else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, false><<<grid, 10 * 32, smem, cs>>>(g);
   } else {
-    if (act == VADX_ACT_RELU) fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 3, 7><<<grid, 14 * 32, smem, cs>>>(g);
-    else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7><<<grid, 14 * 32, smem, cs>>>(g);
+    if (act == VADX_ACT_RELU) fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 3, 7, false><<<grid, 14 * 32, smem, cs>>>(g);
+    else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7, false><<<grid, 14 * 32, smem, cs>>>(g);
   }
   return after_launch("fc2_memory_stages_f32");
 }
