@@ -190,22 +190,28 @@ __global__ void __launch_bounds__(NP == 2 ? 384 : 512, 1) fc2_memory_stages_kern
         constexpr int kLd = (kWin + 7) / 8 * 8;
         float win[kLd];
         if (part == 0) {
+          // all loads issued, then collected: one TMEM latency per stream instead of nine
+          uint32_t raw[kLd];
 #pragma unroll
-          for (int i = 0; i < kLd / 8; ++i) tmem_ld8(taddr + (uint32_t)(8 * i), win + 8 * i);
+          for (int i = 0; i < kLd / 8; ++i) tmem_ld8_issue(taddr + (uint32_t)(8 * i), raw + 8 * i);
+#pragma unroll
+          for (int i = 0; i < kLd / 8; ++i) tmem_ld8_finish(raw + 8 * i);
+#pragma unroll
+          for (int j = 0; j < kLd; ++j) win[j] = __uint_as_float(raw[j]);
         } else {
           // columns T-1-u for u = 0 .. kWin-1, i.e. [T-kWin, T): loaded ascending from an 8-column boundary, renamed reversed
           constexpr int c_lo = (T - kWin) / 8 * 8;
           constexpr int n_ld = (T - c_lo + 7) / 8;
           static_assert(c_lo + 8 * n_ld <= TP, "mirrored window load runs past the accumulator");
+          uint32_t raw[8 * n_ld];
 #pragma unroll
-          for (int i = 0; i < n_ld; ++i) {
-            float tmp[8];
-            tmem_ld8(taddr + (uint32_t)(c_lo + 8 * i), tmp);
+          for (int i = 0; i < n_ld; ++i) tmem_ld8_issue(taddr + (uint32_t)(c_lo + 8 * i), raw + 8 * i);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int u = T - 1 - (c_lo + 8 * i + j);
-              if (u >= 0 && u < kLd) win[u] = tmp[j];
-            }
+          for (int i = 0; i < n_ld; ++i) tmem_ld8_finish(raw + 8 * i);
+#pragma unroll
+          for (int i = 0; i < 8 * n_ld; ++i) {
+            const int u = T - 1 - (c_lo + i);
+            if (u >= 0 && u < kLd) win[u] = __uint_as_float(raw[i]);
           }
 #pragma unroll
           for (int u = T - c_lo; u < kLd; ++u) win[u] = 0.f;    // (not reached by the loads; never used either)
