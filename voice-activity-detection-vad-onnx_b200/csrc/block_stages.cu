@@ -13,8 +13,11 @@
 //     reads ITS channel's whole time series with tcgen05.ld and runs the FIR along it in registers: no p tile at all,
 //     and since a chunk is zero-padded on both sides by definition there is no halo either;
 //   * T is a template parameter: every window index and every edge test is a compile-time constant.
+//   * MIRROR (default): the second half of the frames is processed in reversed time, so both halves run one shared
+//     unrolled body (half the code of a kernel that was instruction-fetch bound).
 // p never exists in HBM (the unfused pair writes and re-reads 0.5 KB per frame row), and the eight FIR warps overlap the
-// next stream's MMAs through two accumulators.
+// next stream's MMAs through two accumulators.  Callers: model.cu (FireRed, engine.fuse_stages); shapes it does not
+// cover (other chunk lengths or tap counts, streaming caches) take the two-kernel tail.
 #include <type_traits>
 
 #include "tc_ptx.cuh"

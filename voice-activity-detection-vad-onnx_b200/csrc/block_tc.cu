@@ -16,7 +16,8 @@
 // register file (loaders hold two stages of loads in registers, the FIR wants its 46-deep window) leave the FIR only
 // four warps, and measured on B200 the fused block is slower than the two streaming kernels it replaces
 // (0.75 ms vs 0.27 + 0.27 ms per block with a dedicated MMA warp; this 12-warp layout is slower still).  Kept as the
-// starting point for the version that moves the activation loads to bulk copies and frees the loaders' registers.
+// starting point for the version that moves the activation loads to bulk copies and frees the loaders' registers:
+// that version is block_stages.cu (default since the end of round 1).
 #include "tc_ptx.cuh"
 
 namespace vadx {
