@@ -194,16 +194,23 @@ int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* d_wl, int n
                          int64_t ldr, float* d_out, int64_t ldo, int64_t n_streams, int n_frames,
                          int n_channels, const float* d_cache_in, float* d_cache_out, void* stream);
 
-/* a8 + a6 fused -- the second dense layer of a DFSMN block and its memory block in one tensor-core kernel
- * (FireRedVAD/Export_FireRedVAD.py:253-263, :213-236):  p = act(x W^T + b),  out = p + FIR_back(p) + FIR_ahead(p)
- * (+ residual).  One row tile = one stream's chunk of n_frames <= 128 frames (zero-padded in time by
- * definition, so no halo), n_out = 128 channels, 20 (+20) unit-stride taps; d_x [S*T][ldx], d_residual /
- * d_out [S*T][128]; d_wimg from vadx_pack_weight_tc(W [128][n_in]).  act: NONE or RELU.  p never reaches HBM. */
-int vadx_fc2_memory_tc_supported(int n_in, int n_out, int n_frames, int n_back, int stride_back, int n_ahead,
-                                 int stride_ahead);
-int vadx_fc2_memory_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias, int act,
-                           const float* d_wl, int n_back, const float* d_wr, int n_ahead, const float* d_residual,
-                           float* d_out, int64_t n_streams, int n_frames, int n_in, void* stream);
+/* a8 + a6 fused -- one DFSMN block (FireRedVAD/Export_FireRedVAD.py:253-263 fc1/fc2, :213-236 memory block) as TWO
+ * tensor-core kernels that hand the hidden rows over in the MMA operand format:
+ *   vadx_linear_tc_stream_stages_f32:  h = act(x W1^T + b1), written as per-stream operand stages
+ *       d_himg [S][n_out/64][hi | lo][round_up(T,16) rows x 128 B] (two-term bf16 split, 128-byte swizzled);
+ *       d_x [S*T][n_in] fp32 rows, n_out % 64 == 0, rows_per_stream = T;
+ *   vadx_fc2_memory_stages_f32:  p = act(h W2^T + b2) issued transposed (accumulator = p^T in tensor memory),
+ *       out = p + FIR_back(p) + FIR_ahead(p) (+ residual); d_residual / d_out [S*T][128]; p never reaches HBM.
+ * Supported: n_out(fc2) = 128, n_in(fc2) in {64,128,192,256}, n_frames = 98, 20 + 20 unit-stride taps (a chunk is
+ * zero-padded in time by definition, so there is no halo); act NONE or RELU.  d_wimg from vadx_pack_weight_tc. */
+size_t vadx_fc2_memory_stages_stream_bytes(int n_in, int n_frames);
+int vadx_fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, int stride_back, int n_ahead,
+                                     int stride_ahead);
+int vadx_linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, void* d_himg,
+                                     int64_t n_rows, int rows_per_stream, int n_in, int n_out, int act, void* stream);
+int vadx_fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, const float* d_bias, int act,
+                               const float* d_wl, int n_back, const float* d_wr, int n_ahead, const float* d_residual,
+                               float* d_out, int64_t n_streams, int n_frames, void* stream);
 
 /* a4 -- FunASR low-frame-rate stacking + CMVN (FSMN/Export_FSMN_VAD.py:65-70,82-86):
  * out[s][t][j*n_mels + m] = (mel[s][clamp(t + j - (lfr_m-1)/2, 0, T-1)][m] + mean[..]) * var[..]; lfr_n = 1. */

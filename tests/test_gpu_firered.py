@@ -194,20 +194,6 @@ def test_resample_linear_kernel_matches_torch(cuda):
         assert out[:, :2].abs().max().item() == 0 and out[:, 2 + n_out:].abs().max().item() == 0
 
 
-def test_opt_in_fused_block_path_matches_default(cuda):
-    """engine.fuse_block = 1 routes fc2 + memory block through block_tc.cu: same probabilities as the default path."""
-    cfg = W.FireRedConfig()
-    w = W.firered_random_init(cfg, 0)
-    d = torch.from_numpy(synth.synth_chunks_fast(70, 16000, seed=4)).to(cuda)
-    a = vadx.FireRedSession(w, cfg)
-    b = vadx.FireRedSession(w, cfg)
-    b._e.set_scalar("engine.fuse_block", 1.0)
-    pa, pb = a.run_batch(d), b.run_batch(d)
-    # two valid fp32 evaluation orders of the same network (the default block tail sums half of the frames' taps in
-    # reversed order): the difference stays below the operand split's own error against the oracle (1e-4 .. 2e-4)
-    assert (pa - pb).abs().max().item() <= 1.5e-4
-
-
 @pytest.mark.parametrize("n", [70, 3, 333])
 def test_staged_hidden_handover_matches_fp32_rows(cuda, n):
     """engine.split_hidden (default on): fc1 writes relu(h) as the two-term bf16 operand stages fc2's MMA reads.  The split

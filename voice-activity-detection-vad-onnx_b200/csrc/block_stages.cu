@@ -4,7 +4,7 @@
 //   p   = act(h W^T + b)                                                    (FireRedVAD/Export_FireRedVAD.py:253-263, :290-296)
 //   out = p + sum_k wl[c][k] p[t-(N1-1)+k] + sum_k wr[c][k] p[t+1+k]  (+ res)      (FSMN.forward, :213-236)
 //
-// What block_tc.cu (first version, opt-in, slower than the unfused pair) ran out of was shared memory and registers: a
+// What the first version (block_tc.cu, removed in round 2; slower than the unfused pair) ran out of was shared memory and registers: a
 // 131 KB weight image, a 32 KB activation stage, a 50 KB p tile, and loader warps holding two stages of loads.  Here
 //   * h arrives as per-stream operand stages ([stream][K chunk][hi | lo] swizzled bf16 images written by fc1's epilogue,
 //     gemm_tc.cu y_split == 2): one thread streams them in with cp.async.bulk, there are no loader warps;
@@ -337,7 +337,7 @@ bool fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, 
 }
 
 static int parts_env() {
-  static const int parts = [] { const char* e = getenv("VADX_BS_PARTS"); return e && atoi(e) == 3 ? 3 : 2; }();
+  static const int parts = ab_env("VADX_BS_PARTS", 2) == 3 ? 3 : 2;
   return parts;
 }
 
@@ -350,12 +350,9 @@ int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, cons
   VADX_REQUIRE(act == VADX_ACT_NONE || act == VADX_ACT_RELU, "fc2_memory_stages_f32: activation %d", act);
   VADX_REQUIRE(aligned16(d_himg) && aligned16(d_wimg), "fc2_memory_stages_f32: operand images must be 16-byte aligned");
   if (n_streams == 0) return VADX_OK;
-  static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice per_device;
+  int n_sm = 148;
+  VADX_TRY(per_device.ensure(&n_sm, [] {
     cudaError_t e = cudaSuccess;
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
@@ -363,19 +360,18 @@ int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, cons
     opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, false>);  opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, false>);
     opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 2, 7, true>);   opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 2, 7, true>);
     opt_in(fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7, false>); opt_in(fc2_memory_stages_kernel<VADX_ACT_RELU, 98, 20, 20, 3, 7, false>);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fc2_memory_stages_kernel)");
-    configured = true;
-  }
+    return e;
+  }));
   BsArgs g{};
   g.Himg = static_cast<const uint8_t*>(d_himg); g.Wimg = static_cast<const uint8_t*>(d_wimg); g.bias = d_bias;
   g.wl = d_wl; g.wr = d_wr; g.res = d_res; g.out = d_out; g.n_streams = n_streams;
   g.kc = n_in / kTcBK; g.n_k16 = n_in / 16;
-  static const int pf = [] { const char* e = getenv("VADX_BS_PF"); return e ? atoi(e) : 0; }();   // measured slower on B200: off
+  static const int pf = ab_env("VADX_BS_PF", 0);   // measured slower on B200: off
   g.pf = pf;
-  static const int mirror = [] { const char* e = getenv("VADX_BS_MIRROR"); return e ? atoi(e) : 1; }();
+  static const int mirror = ab_env("VADX_BS_MIRROR", 1);
   g.mirror = (mirror && parts_env() == 2) ? 1 : 0;
   const size_t smem = bs_smem_bytes(g.kc, n_frames, n_back, n_ahead);
-  const int grid = (int)std::min<int64_t>(n_streams, n_sm > 0 ? n_sm : 148);
+  const int grid = (int)std::min<int64_t>(n_streams, n_sm);
   const int parts = parts_env();
   cudaStream_t cs = (cudaStream_t)stream;
   if (parts == 2) {
@@ -389,4 +385,17 @@ int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, cons
     else fc2_memory_stages_kernel<VADX_ACT_NONE, 98, 20, 20, 3, 7, false><<<grid, 14 * 32, smem, cs>>>(g);
   }
   return after_launch("fc2_memory_stages_f32");
+}
+
+extern "C" size_t vadx_fc2_memory_stages_stream_bytes(int n_in, int n_frames) { return fc2_memory_stages_stream_bytes(n_in, n_frames); }
+extern "C" int vadx_fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, int stride_back, int n_ahead,
+                                                int stride_ahead) {
+  return fc2_memory_stages_supported(n_in, n_out, n_frames, n_back, stride_back, n_ahead, stride_ahead) ? 1 : 0;
+}
+extern "C" int vadx_fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, const float* d_bias, int act,
+                                          const float* d_wl, int n_back, const float* d_wr, int n_ahead, const float* d_residual,
+                                          float* d_out, int64_t n_streams, int n_frames, void* stream) {
+  VADX_REQUIRE(n_streams >= 0, "vadx_fc2_memory_stages_f32: negative stream count");
+  return fc2_memory_stages_f32(d_himg, n_in, d_wimg, d_bias, act, d_wl, n_back, d_wr, n_ahead, d_residual, d_out, n_streams,
+                               n_frames, stream);
 }

@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "vadx.h"
 
@@ -26,6 +28,49 @@ inline int after_launch(const char* what) {
   if (e != cudaSuccess) return cuda_fail(e, what);
   return VADX_OK;
 }
+
+// One-time PER-DEVICE kernel setup: cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) and the SM count
+// belong to a device, not to the process, and ctypes callers release the GIL -- so the "already configured" state is
+// keyed by cudaGetDevice() and guarded by a mutex.
+//   static PerDevice pd;  int n_sm;  VADX_TRY(pd.ensure(&n_sm, [&] { return cudaFuncSetAttribute(...); }));
+struct PerDevice {
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  int sms[kMaxDevices] = {};
+  template <class F>
+  int ensure(int* n_sm, F&& configure) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= kMaxDevices) {
+      set_error("device ordinal %d is outside the supported range [0, %d)", dev, kMaxDevices);
+      return VADX_EINVAL;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[dev]) {
+      int n = 0;
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      e = configure();
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      sms[dev] = n > 0 ? n : 148;
+      done[dev] = true;
+    }
+    if (n_sm) *n_sm = sms[dev];
+    return VADX_OK;
+  }
+};
+
+// A/B switches of the measurements quoted in DESIGN.md: compiled in only with -DVADX_AB_SWITCHES (make AB=1); a
+// production build has no environment reads on any path.
+#ifdef VADX_AB_SWITCHES
+inline int ab_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+inline int ab_env(const char*, int dflt) { return dflt; }
+#endif
 
 // per-stage event timing (api.cu); a no-op unless vadx_profile_enable(1) was called
 struct StageTimer {

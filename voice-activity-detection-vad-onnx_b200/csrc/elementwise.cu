@@ -346,16 +346,11 @@ extern "C" int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t 
   if (n_rows == 0) return VADX_OK;
   size_t smem = ((size_t)kMelRows * ld_power + (size_t)n_mels * (max_len | 1) + 2 * (size_t)n_mels) * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_mel_log_f32: ld_power=%lld too large", (long long)ld_power);
-  static bool mel_cfg = false;
-  static int n_sm = 148;
-  if (!mel_cfg) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mel_log_kernel)");
-    mel_cfg = true;
-  }
+  static PerDevice per_device;
+  int n_sm = 148;
+  VADX_TRY(per_device.ensure(&n_sm, [] {
+    return cudaFuncSetAttribute(mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }));
   const int64_t tiles = ceil_div(n_rows, kMelRows);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));   // resident CTAs per SM
   const int64_t blocks = std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
@@ -385,20 +380,14 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
   const int halo_r = n_frames > 1 ? n_ahead * stride_ahead : 0;
   size_t smem = ((size_t)(kMemT + halo_l + halo_r) + n_back + n_ahead) * n_channels * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_fsmn_memory_f32: tile of %zu bytes exceeds shared memory", smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(fsmn_memory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_kernel)");
-    configured = 200 * 1024;
-  }
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(fsmn_memory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }));
   // whole-chunk shared-memory kernel (memory_bulk.cu) when the stream's tile fits: FireRed's [98][128]
   {
     size_t smem_b = 0;
-    static int no_bulk = -1;
-    if (no_bulk < 0) {
-      const char* e = getenv("VADX_MEM_NO_BULK");
-      no_bulk = e ? atoi(e) : 0;
-    }
+    static const int no_bulk = ab_env("VADX_MEM_NO_BULK", 0);
     if (!no_bulk && n_streams >= 32 &&
         memory_bulk_fits(n_back, stride_back, n_ahead, stride_ahead, n_frames, n_channels, ldp, ldr, ldo, d_p, d_residual,
                          d_out, d_cache_in, d_cache_out, &smem_b))
@@ -486,12 +475,10 @@ extern "C" int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const fl
   const int rows_in = (kDwT - 1) * stride + (kernel - 1) * dilation + 1;
   size_t smem = ((size_t)rows_in + kernel) * n_channels * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_depthwise_conv1d_f32: tile of %zu bytes exceeds shared memory", smem);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(depthwise_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(depthwise_conv1d_kernel)");
-    configured = true;
-  }
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(depthwise_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }));
   dim3 grid((unsigned)ceil_div(t_out, kDwT), (unsigned)n_streams);
   depthwise_conv1d_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, ldx, d_w, kernel, stride, dilation, pad, d_y,
                                                                      ldy, t_in, t_out, n_channels);

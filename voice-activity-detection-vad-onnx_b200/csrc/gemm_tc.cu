@@ -69,7 +69,7 @@ __device__ __forceinline__ float bias_act(float v, float b) {
 }
 
 static int lin_loader_warps() {
-  static const int lw = [] { const char* e = getenv("VADX_LIN_LOADERS"); const int v = e ? atoi(e) : 16; return v == 8 || v == 164 ? v : 16; }();
+  static const int lw = [] { const int v = ab_env("VADX_LIN_LOADERS", 16); return v == 8 || v == 164 ? v : 16; }();
   return lw;
 }
 static bool lw_is16() { return lin_loader_warps() != 8; }
@@ -584,10 +584,9 @@ extern "C" int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* 
 static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                             const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
                             int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
-                            int x_split = 0, int y_split = 0);
+                            int x_split = 0, int y_split = 0, int rows_per_stream = 0);
 
 // Internal (model.cu): the same layer with its input and/or output in the operand-stage format (TcArgs::x_split / y_split).
-static int g_ys_T = 0;   // rows per stream of the next y_split == 2 launch (set by linear_tc_stream_stages_f32)
 
 int linear_tc_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows, int n_in,
                          int n_out, int act, int x_split, int y_split, void* stream) {
@@ -617,7 +616,8 @@ extern "C" int vadx_linear_head_tc_f32(const float* d_x, int64_t ldx, const void
 static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                             const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
                             int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
-                            int x_split, int y_split) {
+                            int x_split, int y_split, int rows_per_stream) {
+  const int g_ys_T = y_split == 2 ? rows_per_stream : 0;
   StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
   VADX_REQUIRE(d_x && d_wimg, "vadx_linear_tc_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
@@ -625,12 +625,9 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   VADX_REQUIRE(s.ok, "vadx_linear_tc_f32: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
   VADX_REQUIRE(aligned16(d_wimg), "vadx_linear_tc_f32: weight image must be 16-byte aligned");
   if (n_rows == 0) return VADX_OK;
-  static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice per_device;
+  int n_sm = 148;
+  VADX_TRY(per_device.ensure(&n_sm, [] {
     cudaError_t e = cudaSuccess;
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
@@ -640,9 +637,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 8>);    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16>); opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_LOG, 8>);        opt_in(linear_tc_kernel<VADX_ACT_LOG, 16>); opt_in(linear_tc_kernel<VADX_ACT_LOG, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 8>);  opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 16>); opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 16, 4>);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(linear_tc_kernel)");
-    configured = true;
-  }
+    return e;
+  }));
   TcArgs g{};
   g.X = d_x; g.ldx = ldx; g.Wimg = static_cast<const uint8_t*>(d_wimg); g.bias = d_bias; g.res = d_residual;
   g.ldr = ldr; g.Y = d_y; g.ldy = ldy; g.M = n_rows; g.K = n_in; g.N = n_out; g.n_pad = s.n_pad; g.kc = s.kc;
@@ -652,24 +648,20 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_linear_tc_f32: too many rows");
   g.n_tiles = (int)tiles;
   {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("VADX_TC_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
+    static const int dbg = ab_env("VADX_TC_DEBUG", 0);
     g.debug = dbg;
   }
   g.vec_x = ((ldx & 3) == 0) && aligned16(d_x);
   {
-    static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
-    static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 64; }();
+    static const int bl = ab_env("VADX_TC_BACKOFF_LD", 64);
+    static const int be = ab_env("VADX_TC_BACKOFF_EPI", 64);
     g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
-    static const bool all_cols = getenv("VADX_TC_ALLCOLS") != nullptr;
+    static const bool all_cols = ab_env("VADX_TC_ALLCOLS", 0) != 0;
     g.k_live = all_cols ? s.kc * kTcBK : s.n_k16 * 16;
-    static const int pf = [] { const char* e = getenv("VADX_LIN_PF"); return e ? atoi(e) : 1; }();
+    static const int pf = ab_env("VADX_LIN_PF", 1);
     g.pf_tiles = (g.vec_x && (n_in & 3) == 0) ? pf : 0;   // bulk prefetch wants 16-byte aligned addresses and sizes
-    static const int spread = [] { const char* e = getenv("VADX_LIN_PF_SPREAD"); return e ? atoi(e) : 0; }();
-    static const int at = [] { const char* e = getenv("VADX_LIN_PF_AT"); return e ? atoi(e) : 0; }();
+    static const int spread = ab_env("VADX_LIN_PF_SPREAD", 0);
+    static const int at = ab_env("VADX_LIN_PF_AT", 0);
     g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
     g.x_split = x_split; g.y_split = y_split;
     g.ys_T = g_ys_T; g.ys_img = (int)round_up(g_ys_T, 16) * 128;
@@ -681,11 +673,11 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     g.pf_spread = (spread && s.kc <= 8 && ((kTcBM / 16) % s.kc) == 0 && lw_is16()) ? 1 : 0;
   }
   {
-    static const bool no256 = getenv("VADX_LIN_NO_LDG256") != nullptr;
+    static const bool no256 = ab_env("VADX_LIN_NO_LDG256", 0) != 0;
     if (g.vec_x && !no256 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 31u) == 0) g.vec_x = 2;
   }
   g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
-  int grid = (int)std::min<int64_t>(tiles, n_sm > 0 ? n_sm : 148);
+  int grid = (int)std::min<int64_t>(tiles, n_sm);
   const int lw = lin_loader_warps();
 #define VADX_LIN_LAUNCH(A)                                                                                \
   do {                                                                                                    \
@@ -711,8 +703,18 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
 
 int linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, float* d_y, int64_t n_rows,
                                 int rows_per_stream, int n_in, int n_out, int act, void* stream) {
-  g_ys_T = rows_per_stream;
-  const int rc = linear_tc_stages_f32(d_x, d_wimg, d_bias, d_y, n_rows, n_in, n_out, act, 0, 2, stream);
-  g_ys_T = 0;
-  return rc;
+  VADX_REQUIRE(d_y && rows_per_stream > 0, "linear_tc_stream_stages_f32: bad argument");
+  VADX_REQUIRE(n_out % kTcBK == 0, "linear_tc_stream_stages_f32: a staged output needs N %% 64 == 0 (got %d)", n_out);
+  return linear_tc_launch(d_x, n_in, d_wimg, d_bias, nullptr, 0, d_y, n_out, n_rows, n_in, n_out, act, nullptr, 0.f, nullptr,
+                          stream, 0, 2, rows_per_stream);
+}
+
+extern "C" int vadx_linear_tc_stream_stages_f32(const float* d_x, const void* d_wimg, const float* d_bias, void* d_himg,
+                                                int64_t n_rows, int rows_per_stream, int n_in, int n_out, int act, void* stream) {
+  VADX_REQUIRE(rows_per_stream > 0 && n_rows % rows_per_stream == 0,
+               "vadx_linear_tc_stream_stages_f32: %lld rows are not whole streams of %d", (long long)n_rows, rows_per_stream);
+  VADX_REQUIRE((n_rows / rows_per_stream) * (int64_t)((n_out / kTcBK) * 2 * ((rows_per_stream + 15) / 16 * 16) * 128) < (1LL << 32),
+               "vadx_linear_tc_stream_stages_f32: the stage images of one launch must stay below 4 GiB");
+  return linear_tc_stream_stages_f32(d_x, d_wimg, d_bias, static_cast<float*>(d_himg), n_rows, rows_per_stream, n_in, n_out, act,
+                                     stream);
 }

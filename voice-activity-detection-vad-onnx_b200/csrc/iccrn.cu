@@ -409,12 +409,10 @@ extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_in
   const size_t G = 4 * (size_t)hidden;
   const size_t smem = (G * n_in + G * hidden + G + (size_t)kLstmThreads * (n_in + 2 * hidden + G)) * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_lstm_seq_f32: in=%d hidden=%d needs %zu bytes of shared memory", n_in, hidden, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && configured == 0) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lstm_seq_kernel)");
-    configured = 1;
-  }
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }));
   LstmArgs a{d_x, x_outer, x_inner, x_step, d_y, y_outer, y_inner, y_step, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
              n_seq, n_inner, seq_len, n_in, hidden, reverse};
   lstm_seq_kernel<<<(unsigned)ceil_div(n_seq, kLstmThreads), kLstmThreads, smem, (cudaStream_t)stream>>>(a);

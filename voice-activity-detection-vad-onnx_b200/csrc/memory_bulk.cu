@@ -185,12 +185,9 @@ bool memory_bulk_fits(int n_back, int stride_back, int n_ahead, int stride_ahead
 
 int memory_bulk_launch(const float* p, const float* wl, const float* wr, int n_ahead, const float* res, float* out,
                        int64_t n_streams, int n_frames, size_t smem, cudaStream_t st) {
-  static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice per_device;
+  int n_sm = 148;
+  VADX_TRY(per_device.ensure(&n_sm, [] {
     cudaError_t e = cudaSuccess;
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
@@ -198,13 +195,12 @@ int memory_bulk_launch(const float* p, const float* wl, const float* wr, int n_a
     opt_in(fsmn_memory_bulk_kernel<20, 20, 7, 4>);  opt_in(fsmn_memory_bulk_kernel<20, 0, 7, 4>);
     opt_in(fsmn_memory_bulk_kernel<20, 20, 13, 2>); opt_in(fsmn_memory_bulk_kernel<20, 0, 13, 2>);
     opt_in(fsmn_memory_bulk_kernel<20, 20, 26, 1>); opt_in(fsmn_memory_bulk_kernel<20, 0, 26, 1>);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsmn_memory_bulk_kernel)");
-    configured = true;
-  }
-  static const int pf = [] { const char* e = getenv("VADX_MEM_PF"); return e ? atoi(e) : 0; }();   // measured slower on B200 (2.17 -> 2.5 ms per step): off
+    return e;
+  }));
+  static const int pf = ab_env("VADX_MEM_PF", 0);   // measured slower on B200 (2.17 -> 2.5 ms per step): off
   MemBulkArgs g{p, res, wl, wr, out, n_streams, n_frames, pf};
-  const int grid = (int)std::min<int64_t>(n_streams, n_sm > 0 ? n_sm : 148);
-  static const int rg = [] { const char* e = getenv("VADX_MEM_RG"); return e ? atoi(e) : 13; }();
+  const int grid = (int)std::min<int64_t>(n_streams, n_sm);
+  static const int rg = ab_env("VADX_MEM_RG", 13);
   if (rg == 7) {
     if (n_ahead == 20) fsmn_memory_bulk_kernel<20, 20, 7, 4><<<grid, kMbThreads, smem, st>>>(g);
     else fsmn_memory_bulk_kernel<20, 0, 7, 4><<<grid, kMbThreads, smem, st>>>(g);

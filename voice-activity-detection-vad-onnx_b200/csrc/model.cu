@@ -133,7 +133,6 @@ int firered_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
 // so slabs only add launches (8192 chunks: 11.9 ms whole, 13.8 ms at 1536, 18.1 ms at 384 per slab).
 static int64_t firered_slab(const vadx_model* m, int64_t S) {
   int64_t slab = (int64_t)m->scalar("engine.slab_streams", 0.0);
-  if (const char* e = getenv("VADX_SLAB")) slab = atoll(e);
   if (slab <= 0 || slab > S) slab = S;
   return slab;
 }
@@ -246,20 +245,13 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
                                   cin ? cin + layer * cache_layer : nullptr, cin ? cout + layer * cache_layer : nullptr,
                                   st);
     };
-    // second dense layer + memory block (+ residual) of every DFSMN block in one kernel when a chunk is one row tile
-    // (block_tc.cu): p never reaches HBM.  Opt-in ("engine.fuse_block" = 1): correct, but on B200 the FIR phase on
-    // the few warps the register file leaves next to the loaders is slower than the two streaming kernels
-    // (8192 chunks: 10.8 ms with a dedicated MMA warp / 18.7 ms in the 12-warp layout vs 8.97 ms unfused).
-    const bool fuse_block = use_tc && !cin && m->scalar("engine.fuse_block", 0.0) != 0.0 &&
-                            vadx_fc2_memory_tc_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1);
     // fc1 -> fc2 hand-over in the tensor-core operand format: fc1's epilogue writes relu(h) already split into the two bf16
     // terms and swizzled into the 16 KB stage images fc2's MMA reads, fc2 streams them in with bulk copies (same bytes in
     // HBM as fp32 rows; fc2 loses its load/convert/store loader, the stage the L1 data pipe was saturated by)
-    const bool split_hidden = use_tc && !fuse_block && (h.H % 64) == 0 && m->scalar("engine.split_hidden", 1.0) != 0.0 &&
-                              !getenv("VADX_NO_SPLIT_HIDDEN");
+    const bool split_hidden = use_tc && (h.H % 64) == 0 && m->scalar("engine.split_hidden", 1.0) != 0.0;
     // fc2 + memory block + residual in one kernel fed by per-stream stages (block_stages.cu): p never reaches HBM
     const bool fuse_stages = split_hidden && !cin && fc2_memory_stages_supported(h.H, h.P, T, h.N1, h.S1, h.N2, h.N2 > 0 ? h.S2 : 1) &&
-                             m->scalar("engine.fuse_stages", 1.0) != 0.0 && !getenv("VADX_NO_FUSE_STAGES") &&
+                             m->scalar("engine.fuse_stages", 1.0) != 0.0 &&
                              // fc1's epilogue addresses a stream's image set with 32-bit byte offsets
                              S * (int64_t)fc2_memory_stages_stream_bytes(h.H, T) < (1LL << 32);
     auto fc1 = [&](const float* x, int n_in, const std::string& w, const char* b) -> int {
@@ -272,12 +264,6 @@ int firered_run(vadx_model* m, bool dry, const void* const* in, void* const* out
     };
     auto block_tail = [&](const std::string& w, const char* b, int act, const std::string& mem_pre, int layer, const float* res,
                           float* o) -> int {
-      const uint8_t* img = fuse_block ? m->d<uint8_t>(w + "#TC") : nullptr;
-      if (img)
-        return vadx_fc2_memory_tc_f32(bufH, h.H, img, b ? m->d<float>(b) : nullptr, act,
-                                      m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,
-                                      h.N2 > 0 ? m->d<float>(mem_pre + "lookahead_filter.weight") : nullptr, h.N2, res, o, S, T,
-                                      h.H, st);
       if (fuse_stages)
         return fc2_memory_stages_f32(bufH, h.H, m->d<uint8_t>(w + "#TC"), b ? m->d<float>(b) : nullptr, act,
                                      m->d<float>(mem_pre + "lookback_filter.weight"), h.N1,

@@ -660,19 +660,15 @@ extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, c
                                                (std::max(n_frames, 1) + 31) / 32 + 1, 4);
   const size_t smem_w = (size_t)per_warp_floats * 4 * kPpWarps;
   if (smem_w <= 200 * 1024) {
-    static bool cfg_w = false;
-    if (smem_w > 48 * 1024 && !cfg_w) {
+    static PerDevice per_device_w;
+    VADX_TRY(per_device_w.ensure(nullptr, [] {
       cudaError_t e = cudaFuncSetAttribute(postprocess_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(postprocess_frames_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(postprocess_frames_warp_kernel)");
-      cfg_w = true;
-    }
-    static int legacy = -1;   // VADX_PP_LEGACY=1: the frame-by-frame kernel (kept as the cross-check of the run-based one)
-    if (legacy < 0) {
-      const char* e = getenv("VADX_PP_LEGACY");
-      legacy = e ? atoi(e) : 0;
-    }
+      return e;
+    }));
+    // VADX_PP_LEGACY=1 (AB build only): the frame-by-frame kernel, kept as the cross-check of the run-based one
+    static const int legacy = ab_env("VADX_PP_LEGACY", 0);
     if (legacy)
       postprocess_frames_warp_kernel<<<(unsigned)ceil_div(n_streams, kPpWarps), kPpWarps * 32, smem_w, (cudaStream_t)stream>>>(
           d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
@@ -686,12 +682,10 @@ extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, c
   const int64_t blocks = ceil_div(n_streams, 32);
   const size_t smem = (size_t)std::max(n_frames, 1) * 32;
   const int use_smem = smem <= 200 * 1024;
-  static bool configured = false;
-  if (use_smem && smem > 48 * 1024 && !configured) {
-    cudaError_t e = cudaFuncSetAttribute(postprocess_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(postprocess_frames_kernel)");
-    configured = true;
-  }
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(postprocess_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }));
   postprocess_frames_kernel<<<(unsigned)blocks, 32, use_smem ? smem : 0, (cudaStream_t)stream>>>(
       d_probs, ld_probs, d_n_frames, n_streams, n_frames, *cfg, d_decisions, d_seg_count, d_segments, max_segments,
       use_smem);

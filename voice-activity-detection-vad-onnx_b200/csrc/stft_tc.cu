@@ -612,12 +612,9 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   StftTcShape s = stft_tc_shape(n_taps, n_bins);
   VADX_REQUIRE(s.ok, "vadx_stft_power_tc_i16: shape not supported");
   if (n_streams == 0) return VADX_OK;
-  static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice per_device;
+  int n_sm = 148;
+  VADX_TRY(per_device.ensure(&n_sm, [] {
     cudaError_t e = cudaSuccess;
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
@@ -626,9 +623,8 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
     opt_in(stft_power_tc_kernel<true, false, 8>);   opt_in(stft_power_tc_kernel<true, false, 16>);
     opt_in(stft_power_tc_kernel<false, true, 8>);   opt_in(stft_power_tc_kernel<false, true, 16>);
     opt_in(stft_power_tc_kernel<true, true, 8>);    opt_in(stft_power_tc_kernel<true, true, 16>);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_power_tc_kernel)");
-    configured = true;
-  }
+    return e;
+  }));
   StftTcArgs g{};
   g.X = d_audio; g.in_stride = in_stride; g.L = n_samples; g.n_frames = n_frames; g.hop = hop;
   g.Wimg = static_cast<const uint8_t*>(d_img); g.P = d_power; g.ldp = ld_power; g.M = n_streams * n_frames;
@@ -636,19 +632,15 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   g.pad_left = pad_left; g.mean = d_mean; g.mean_int = d_mean_int; g.dc = d_dc_tables; g.power_scale = power_scale; g.n_edge_lo = n_edge_lo; g.t_edge_hi = t_edge_hi;
   g.vec_p = ((ld_power & 3) == 0) && aligned16(d_power);
   {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("VADX_TC_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
+    static const int dbg = ab_env("VADX_TC_DEBUG", 0);
     g.debug = dbg;
   }
-  static const int opt = [] { const char* e = getenv("VADX_ST_OPT"); return e ? atoi(e) : 3; }();   // bit 0 stack, bit 1 staged output
+  static const int opt = ab_env("VADX_ST_OPT", 3);   // bit 0 stack, bit 1 staged output
   {
-    static const int bl = [] { const char* e = getenv("VADX_TC_BACKOFF_LD"); return e ? atoi(e) : 64; }();
-    static const int be = [] { const char* e = getenv("VADX_TC_BACKOFF_EPI"); return e ? atoi(e) : 256; }();
+    static const int bl = ab_env("VADX_TC_BACKOFF_LD", 64);
+    static const int be = ab_env("VADX_TC_BACKOFF_EPI", 256);
     g.backoff_ld = (unsigned)bl; g.backoff_epi = (unsigned)be;
-    static const bool all_cols = getenv("VADX_TC_ALLCOLS") != nullptr;
+    static const bool all_cols = ab_env("VADX_TC_ALLCOLS", 0) != 0;
     g.k_live = all_cols ? s.kc * kTcBK : s.n_k16 * 16;
   }
   g.stack = (opt & 1) ? 1 : 0;
@@ -657,10 +649,10 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   int64_t tiles = ceil_div(g.M, kTcBM);
   VADX_REQUIRE(tiles <= 0x7fffffffLL, "vadx_stft_power_tc_i16: too many rows");
   g.n_tiles = (int)tiles;
-  int per = std::max(1, (n_sm > 0 ? n_sm : 148) / s.n_ntiles);
+  int per = std::max(1, n_sm / s.n_ntiles);
   dim3 grid((unsigned)std::min<int64_t>(tiles, per), (unsigned)s.n_ntiles);
   const bool ex = leaves_stream || d_mean, f16 = operand_format == VADX_TC_FMT_F16;
-  static const int lw = [] { const char* e = getenv("VADX_ST_LOADERS"); return e && atoi(e) == 8 ? 8 : 16; }();
+  static const int lw = ab_env("VADX_ST_LOADERS", 16) == 8 ? 8 : 16;
 #define VADX_ST_LAUNCH(EXV, F16V)                                                                                   \
   do {                                                                                                              \
     if (lw == 8) stft_power_tc_kernel<EXV, F16V, 8><<<grid, 13 * 32, smem, (cudaStream_t)stream>>>(g);              \

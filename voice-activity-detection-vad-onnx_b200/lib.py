@@ -57,8 +57,10 @@ SIGNATURES = {
     "vadx_tc_supported": (C.c_int, [_i32, _i32]),
     "vadx_pack_weight_tc": (C.c_int, [_vp, _i32, _i32, _vp, _sz, C.POINTER(_sz)]),
     "vadx_linear_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
-    "vadx_fc2_memory_tc_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
-    "vadx_fc2_memory_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "vadx_fc2_memory_stages_stream_bytes": (C.c_size_t, [_i32, _i32]),
+    "vadx_fc2_memory_stages_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "vadx_linear_tc_stream_stages_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "vadx_fc2_memory_stages_f32": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "vadx_depthwise_conv1d_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vadx_linear_head_tc_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _vp]),
     "vadx_fsmn_memory_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i64,
