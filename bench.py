@@ -317,16 +317,13 @@ def run_vadx(args):
     import torch
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
     import vadx
-    from vadx import firered_vad, lib, postprocess as PP, synth, weights as W
+    from vadx import distributed as D, firered_vad, lib, postprocess as PP, synth, weights as W
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # before any pinned allocation: keep this rank's host buffers on the NUMA node of its GPU (first touch)
+    numa = D.bind_to_local_numa_node(local_rank) if not os.environ.get("VADX_BENCH_NO_NUMA_BIND") else {"bound": False, "node_cpus": 0}
+    rank, world, dev = D.init("nccl")
 
     L = lib.load()
     cfg = W.FireRedConfig()
@@ -334,6 +331,10 @@ def run_vadx(args):
     B = (args.chunks // CHUNKS_PER_STREAM) * CHUNKS_PER_STREAM
     S = B // CHUNKS_PER_STREAM
     T = sess.frames(CHUNK)
+    # streams shard across ranks in contiguous blocks (vadx.distributed.shard_streams); the synthetic generator is seeded by
+    # the block so that every rank synthesises only its own streams
+    my_streams = D.shard_streams(world * S, rank, world)
+    assert len(my_streams) == S
     host = synth.synth_chunks_fast(B, CHUNK, seed=1234 + rank)
     pinned = torch.from_numpy(host).pin_memory()
     d_audio = pinned.to(dev)                                   # device-resident copy for `value`
@@ -348,7 +349,8 @@ def run_vadx(args):
         return firered_vad.run_vad_streams(sess, d_audio.view(S, CHUNKS_PER_STREAM, CHUNK), lengths, post,
                                            n_valid=n_valid)
 
-    pipe = firered_vad.HostBatchPipeline(sess, S, CHUNKS_PER_STREAM, post, dev)
+    # multi-GPU: the final gather of seg_count / segments (the path's only collective) is INSIDE the end-to-end region
+    pipe = firered_vad.HostBatchPipeline(sess, S, CHUNKS_PER_STREAM, post, dev, gather=world > 1)
     pinned2 = torch.from_numpy(np.roll(host, 1, axis=0).copy()).pin_memory()   # batches alternate between two host buffers
     host_batches = [pinned, pinned2]
     e2e_state = {"i": 0, "last": None}
@@ -400,8 +402,8 @@ def run_vadx(args):
     ms_e2e = timed(step_e2e, args.steps, W_)
     if rank == 0:
         sampler.stop()
-    segs_found = int(e2e_state["last"][0].sum().item())
-    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    segs_found = int(e2e_state["last"][0].sum().item()) if e2e_state["last"] is not None else 0
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes      # d2h: rank 0 reads the gathered global result back
     families = None
     if not args.no_families:
         del pipe, d_audio
@@ -484,8 +486,10 @@ def run_vadx(args):
                            "sharding": "streams split across ranks, no data-path collective"},
                 "rtfx": value * 3600.0,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
-                        "d2h_bytes_per_step": int(d2h_bytes) * world,
-                        "api": "vadx.firered_vad.HostBatchPipeline.run(pinned int16 batch): H2D of batch i+1 overlaps compute of batch i",
+                        "d2h_bytes_per_step": int(d2h_bytes),
+                        "api": "vadx.firered_vad.HostBatchPipeline.run(pinned int16 batch): H2D of batch i+1 overlaps compute of batch i"
+                               + ("; per-step all_gather of seg_count/segments over NCCL (vadx.distributed.gather_segments), rank 0 reads the global result back" if world > 1 else ""),
+                        "numa_bind": numa,
                         "ms_per_step": ms_e2e / args.steps, "segments_found_last_step": segs_found},
                 "gpu_launches": int(launches),
                 "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},

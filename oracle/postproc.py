@@ -184,6 +184,38 @@ def lookahead_hysteresis_flags(chunks, look_backward, speaking_score, silence_sc
     return saved
 
 
+def lookahead_hysteresis_probs(chunks, look_backward, speaking_score, silence_score):
+    """DFSMN flavour (DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:231-273): `chunks` is a list of float32
+    probability arrays.  Each frame is tested against SPEAKING_SCORE / SILENCE_SCORE (numpy float32 against a Python
+    float: float32 comparison under NEP 50), and so is the vote ratio (Python floats)."""
+    lb = look_backward if look_backward != 0 else 1
+    inv = float(1.0 / lb)
+    sp, si = np.float32(speaking_score), np.float32(silence_score)
+    saved, silence = [], True
+    pr = None
+    for pr in chunks:
+        pr = np.asarray(pr, np.float32)
+        for i in range(len(pr) - look_backward):
+            if silence:
+                if pr[i] >= sp:
+                    votes = 1 + sum(1 for j in range(1, lb) if pr[i + j] >= sp)
+                    silence = not (votes * inv >= speaking_score)
+                else:
+                    silence = True
+            else:
+                if pr[i] <= si:
+                    votes = 1 + sum(1 for j in range(1, lb) if pr[i + j] <= si)
+                    silence = not (votes * inv <= silence_score)
+                else:
+                    silence = False
+            saved.append(silence)
+    if pr is not None:
+        for i in range(len(pr) - look_backward, len(pr)):
+            silence = (not pr[i] >= sp) if silence else bool(pr[i] <= si)
+            saved.append(silence)
+    return saved
+
+
 def runs_to_timestamps(silence_flags, frame_duration):
     out, start = [], None
     for i, s in enumerate(silence_flags):

@@ -32,3 +32,39 @@ def cuda():
     vadx.lib.load()
     vadx.lib.require_device()
     return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------------------- measured parity errors
+# BASELINE.json's contract is 1e-3 on frame probabilities.  The tests assert each path's MEASURED bound instead (a 5x
+# numerical regression must not pass silently) and record what they measured: printed per test and written to
+# gpurun_out/parity_measured.json at the end of the session.
+CONTRACT_TOL = 1e-3
+_MEASURED = []
+
+
+class _Measured:
+    def __call__(self, what: str, err: float, bound: float):
+        err = float(err)
+        assert bound <= CONTRACT_TOL, f"{what}: asserted bound {bound} is looser than the 1e-3 contract"
+        _MEASURED.append({"what": what, "max_abs_err": err, "asserted_bound": bound})
+        print(f"[parity] {what}: max abs err {err:.3e} (asserted <= {bound:.1e}, contract 1e-3)")
+        assert err <= bound, f"{what}: max abs err {err:.3e} exceeds its measured bound {bound:.1e}"
+        return err
+
+
+@pytest.fixture(scope="session")
+def measured():
+    return _Measured()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _MEASURED:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.json"), "w") as f:
+            json.dump(_MEASURED, f, indent=1)
+    except OSError:
+        pass

@@ -14,6 +14,7 @@ from oracle.dfsmn_aec import DfsmnAecOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+BOUND = 5e-5  # what this path is ASSERTED to: measured 1.5e-5; TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -76,7 +77,7 @@ def test_echo_estimator_matches_reference_net(cuda, gold, wts):
     assert err <= 1e-4 * max(1.0, np.abs(ref).max())
 
 
-def test_whole_graph_against_reference_wrapper(cuda, gold, wts):
+def test_whole_graph_against_reference_wrapper(cuda, gold, wts, measured):
     cfg = W.DfsmnAecConfig()
     sess = vadx.DfsmnAecSession(wts, cfg, chunk_len=31841)
     near, far = torch.from_numpy(gold["near"]).to(cuda), torch.from_numpy(gold["far"]).to(cuda)
@@ -84,11 +85,10 @@ def test_whole_graph_against_reference_wrapper(cuda, gold, wts):
     assert p.shape == (2, 100)
     for s in range(2):
         err = np.abs(p[s] - gold[f"probs{s}"]).max()
-        print(f"stream {s}: max abs prob err {err:.2e}")
-        assert err <= TOL
+        measured("dfsmn_aec: stream", err, BOUND)
     # ORT-shaped single-stream call
     out = sess.run(["vad_results"], {"near_end_audio": gold["near"][:1, None, :], "far_end_audio": gold["far"][:1, None, :]})[0]
-    assert out.shape == (100,) and np.abs(out - gold["probs0"]).max() <= TOL
+    assert out.shape == (100,) and np.abs(out - gold["probs0"]).max() <= BOUND
     with pytest.raises(ValueError):
         sess.run(None, {"near_end_audio": gold["near"][:1, None, :1000], "far_end_audio": gold["far"][:1, None, :1000]})
 
@@ -114,7 +114,7 @@ def test_stream_loop_and_hysteresis(cuda, wts):
     chunks = []
     for wdx in range(2):
         ref = orc.forward(na[wdx * stride:wdx * stride + L], fa[wdx * stride:wdx * stride + L]).numpy()
-        assert np.abs(r.probs[wdx] - ref).max() <= TOL
+        assert np.abs(r.probs[wdx] - ref).max() <= BOUND
         chunks.append(r.probs[wdx])
     # hysteresis in probability mode: oracle machine on the SAME (device) probabilities
     flags = []
@@ -139,7 +139,7 @@ def test_stream_loop_and_hysteresis(cuda, wts):
     assert np.array_equal(r.saved, np.array(flags))
 
 
-def test_near_end_only_variant(cuda, golden_dir, wts):
+def test_near_end_only_variant(cuda, golden_dir, wts, measured):
     """DFSMN/only_near_end_audio: one input, the far end replaced by the graph's constant noise buffers."""
     g = np.load(os.path.join(golden_dir, "dfsmn_near.npz"))
     cfg = W.DfsmnAecConfig()
@@ -150,10 +150,9 @@ def test_near_end_only_variant(cuda, golden_dir, wts):
     assert p.shape == (2, 100)
     for s in range(2):
         err = np.abs(p[s] - g[f"probs{s}"]).max()
-        print(f"near-only stream {s}: max abs prob err {err:.2e}")
-        assert err <= TOL
+        measured("dfsmn_aec: near-only stream", err, BOUND)
     out = sess.run(["vad_results"], {"audio": g["near"][:1, None, :]})[0]
-    assert out.shape == (100,) and np.abs(out - g["probs0"]).max() <= TOL
+    assert out.shape == (100,) and np.abs(out - g["probs0"]).max() <= BOUND
     with pytest.raises(ValueError):
         sess.run(None, {"near_end_audio": g["near"][:1, None, :], "far_end_audio": g["near"][:1, None, :]})
     with pytest.raises(ValueError):

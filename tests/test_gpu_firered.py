@@ -13,6 +13,7 @@ from oracle.firered import FireRedOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3  # BASELINE.json north_star: frame-prob max abs err <= 1e-3 in fp32
+BOUND = 3e-4  # what this path is ASSERTED to: tcgen05 three-product bf16 split, measured 1.0e-4 .. 1.9e-4 (exact-fp32 FFMA path: 8.7e-6, asserted 2e-5 where it runs); TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +27,7 @@ def default_session(cuda):
     return vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=16000)
 
 
-def test_reference_recipe_through_run(gold, default_session):
+def test_reference_recipe_through_run(gold, default_session, measured):
     np.random.seed(1234)
     a = np.random.randint(-8000, 8000, size=(1, 1, 16000)).astype(np.int16)
     name_in = default_session.get_inputs()[0].name
@@ -34,16 +35,14 @@ def test_reference_recipe_through_run(gold, default_session):
     p = default_session.run([name_out], {name_in: a})[0]
     assert p.shape == (1, 1, 98) and p.dtype == np.float32
     err = np.abs(p - gold["recipe_probs"]).max()
-    print("recipe max abs err", err)
-    assert err <= TOL
+    measured("firered: recipe max abs err", err, BOUND)
 
 
-def test_synthetic_chunks_batched(gold, default_session):
+def test_synthetic_chunks_batched(gold, default_session, measured):
     chunks = synth.synth_streams(6, 16000, seed=1234)
     p = default_session.run(None, {"audio": chunks[:, None, :]})[0]
     err = np.abs(p - gold["synth_probs"]).max()
-    print("synth max abs err", err)
-    assert err <= TOL
+    measured("firered: synth max abs err", err, BOUND)
 
 
 def test_run_rejects_bad_inputs(default_session):
@@ -64,7 +63,7 @@ def test_dynamic_axis(cuda, gold, L):
     a = synth.synth_streams(1, L, seed=77)
     p = sess.run(None, {"audio": a[:, None, :]})[0]
     assert p.shape == gold[f"len{L}_probs"].shape
-    assert np.abs(p - gold[f"len{L}_probs"]).max() <= TOL
+    assert np.abs(p - gold[f"len{L}_probs"]).max() <= BOUND
 
 
 def test_aed_head_with_strides(cuda, gold):
@@ -73,21 +72,20 @@ def test_aed_head_with_strides(cuda, gold):
     chunks = synth.synth_streams(6, 16000, seed=1234)
     p = sess.run(None, {"audio": chunks[1:2, None, :]})[0]
     assert p.shape == (1, 3, 98)
-    assert np.abs(p - gold["aed_probs"]).max() <= TOL
+    assert np.abs(p - gold["aed_probs"]).max() <= BOUND
 
 
-def test_large_batch_against_oracle(cuda, default_session):
+def test_large_batch_against_oracle(cuda, default_session, measured):
     """300 chunks at once (ragged wrt. the 128-row tiles) vs the oracle."""
     cfg = W.FireRedConfig()
     chunks = synth.synth_chunks_fast(300, 16000, seed=5)
     got = default_session.run_batch(torch.from_numpy(chunks).to(cuda)).cpu().numpy()
     ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks).numpy()
     err = np.abs(got - ref).max()
-    print("batch-300 max abs err", err)
-    assert err <= TOL
+    measured("firered: batch-300 max abs err", err, BOUND)
 
 
-def test_full_step_is_batch_independent(cuda, default_session):
+def test_full_step_is_batch_independent(cuda, default_session, measured):
     """BASELINE.json's step size (8192 chunks = 802 816 frame rows, 6272 row tiles, 42-43 tiles per CTA: ring and
     accumulator wrap-arounds, the tile-ahead L2 prefetch past the last tile).  The oracle cannot run this size in
     seconds; the size-independent property is that a chunk's probabilities do not depend on what else is in the batch:
@@ -105,8 +103,7 @@ def test_full_step_is_batch_independent(cuda, default_session):
     idx = np.array([0, 1, 97, 4095, 4096, n - 2, n - 1])
     ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks[idx]).numpy()
     err = np.abs(big[idx] - ref).max()
-    print("full-step sample max abs err", err)
-    assert err <= TOL
+    measured("firered: full-step sample max abs err", err, BOUND)
 
 
 def _oracle_timestamps(probs, n_valid, wav_dur, post):
@@ -129,7 +126,7 @@ def test_vad_sample_timestamps_bit_exact(cuda, golden_dir, default_session, tmp_
     ref_p = FireRedOracle(W.firered_random_init(cfg, 0), cfg).forward(chunks).numpy().reshape(-1)
     n_valid = firered_vad.valid_frame_count(n)
     assert n_valid == 557 and r.probs.shape == (557,)
-    assert np.abs(r.probs - ref_p[:n_valid]).max() <= TOL
+    assert np.abs(r.probs - ref_p[:n_valid]).max() <= BOUND
     dec, ts = _oracle_timestamps(ref_p, n_valid, n / 16000, firered_vad.POST_DEFAULT)
     sm = OP.smooth_probs(ref_p[:n_valid].astype(np.float32), 5)
     if np.abs(sm - np.float32(0.4)).min() > TOL:
@@ -161,7 +158,7 @@ def test_many_streams_timestamps(cuda, default_session):
 
 
 @pytest.mark.parametrize("rate", [8000, 48000, 22050])
-def test_in_graph_resampler(cuda, golden_dir, rate):
+def test_in_graph_resampler(cuda, golden_dir, rate, measured):
     """IN_SAMPLE_RATE != 16000: the wrapper's linear resampler around the pre-emphasis
     (FireRedVAD/Export_FireRedVAD.py:389-393,431-449), golden from the reference wrapper built with that rate."""
     g = np.load(os.path.join(golden_dir, "firered_rates.npz"))
@@ -171,11 +168,10 @@ def test_in_graph_resampler(cuda, golden_dir, rate):
     p = sess.run([sess.get_outputs()[0].name], {"audio": a[:, None, :]})[0]
     assert p.shape == g[f"r{rate}_probs"].shape == (2, 1, 98)
     err = np.abs(p - g[f"r{rate}_probs"]).max()
-    print(f"in_sample_rate {rate}: max abs err {err:.2e}")
-    assert err <= TOL
+    measured("firered: in_sample_rate", err, BOUND)
     big = torch.from_numpy(synth.synth_streams(40, rate, seed=3)).to(cuda)     # tensor-core layers after the fp32 frontend
     ref = FireRedOracle(W.firered_random_init(cfg, 0), cfg, in_sample_rate=rate).forward(big.cpu().numpy()).numpy()
-    assert np.abs(sess.run_batch(big).cpu().numpy() - ref).max() <= TOL
+    assert np.abs(sess.run_batch(big).cpu().numpy() - ref).max() <= BOUND
 
 
 def test_resample_linear_kernel_matches_torch(cuda):
@@ -229,3 +225,28 @@ def test_fused_block_from_stages_matches_default(cuda, n):
     # same products; the fused tail's FIR runs the second half of the frames in reversed time (reversed tap order), so the
     # two paths differ by fp32 rounding amplified through eight blocks: 3e-5 .. 8e-5 measured, both 1e-4 .. 2e-4 from the oracle
     assert err <= 1.5e-4
+
+
+@pytest.mark.parametrize("depth,copy_chunks", [(2, 1), (2, 4), (3, 3)])
+def test_host_batch_pipeline_matches_direct_calls(cuda, default_session, depth, copy_chunks):
+    """The serving front door (pinned host batches in, pinned segment pairs out, H2D of batch i+1 overlapping the
+    compute of batch i): every batch's counts and pairs equal the direct device-resident call, whatever the queue
+    depth and however the copy is split."""
+    S, n_chunks = 24, 3
+    pipe = firered_vad.HostBatchPipeline(default_session, S, n_chunks, device=cuda, depth=depth, copy_chunks=copy_chunks)
+    batches = [torch.from_numpy(synth.synth_chunks_fast(S * n_chunks, 16000, seed=40 + i)).pin_memory() for i in range(4)]
+    got = []
+    for i, b in enumerate(batches):
+        cnt, seg = pipe.run(b, batches[i + 1] if i + 1 < len(batches) else None)
+        torch.cuda.synchronize()
+        got.append((cnt.clone(), seg.clone()))
+    assert pipe.h2d_bytes == S * n_chunks * 16000 * 2 and pipe.d2h_bytes == (S + S * pipe.max_seg * 2) * 4
+    for b, (cnt, seg) in zip(batches, got):
+        _, _, c2, s2, _ = firered_vad.run_vad_streams(default_session, b.to(cuda).view(S, n_chunks, 16000), [n_chunks * 16000] * S)
+        c2, s2 = PP.take_segments(c2, s2)
+        assert np.array_equal(cnt.numpy(), c2) and int(c2.sum()) > 0
+        for s in range(S):
+            assert np.array_equal(seg[s, :c2[s]].numpy(), s2[s, :c2[s]])
+    with pytest.raises(RuntimeError):
+        for _ in range(depth + 1):
+            pipe.prefetch(batches[0])

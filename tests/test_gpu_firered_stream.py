@@ -14,6 +14,7 @@ from oracle.firered import FireRedOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3  # BASELINE.json: max abs err of frame probabilities
+BOUND = 3e-4  # what this path is ASSERTED to: tcgen05 three-product bf16 split, measured <= 1.9e-4; TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -101,10 +102,10 @@ def test_stream_graph_cache_carry_ort_surface(gold, stream_session):
         a = chunks[2][i * 2560:(i + 1) * 2560].reshape(1, 1, -1)
         p, caches = sess.run(names_out, {"audio": a, "caches_in": caches})
         assert p.shape == (1, 1, 14)
-        assert np.abs(p[0, 0] - gold["stream_probs"][i]).max() <= TOL
+        assert np.abs(p[0, 0] - gold["stream_probs"][i]).max() <= BOUND
     # caches are un-normalised activations (|v| ~ 10): bound them relative to their scale
     ref_c = gold["stream_caches_last"]
-    assert np.abs(caches[:, 0, ::16, :] - ref_c).max() <= TOL * max(1.0, float(np.abs(ref_c).max()))
+    assert np.abs(caches[:, 0, ::16, :] - ref_c).max() <= BOUND * max(1.0, float(np.abs(ref_c).max()))
     with pytest.raises(ValueError):
         sess.run(names_out, {"audio": a})
     with pytest.raises(ValueError):
@@ -124,16 +125,15 @@ def test_stream_graph_fp32_path_matches_tighter(gold, cuda):
         assert np.abs(p.cpu().numpy()[0, 0] - gold["stream_probs"][i]).max() <= 5e-5
 
 
-def test_vad_sample_stream_section(gold_script, golden_dir, stream_session):
+def test_vad_sample_stream_section(gold_script, golden_dir, stream_session, measured):
     audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
     r = firered_vad.run_stream_vad(audio, stream_session)
     ref_p = gold_script["stream_probs"]
     assert r.probs.shape == ref_p.shape == (489,)
     err = np.abs(r.probs - ref_p).max()
-    print(f"stream-VAD vad_sample.wav: max abs err {err:.2e}")
-    assert err <= TOL
+    measured("firered_stream: stream-VAD vad_sample.wav: max abs err", err, BOUND)
     ref_c = gold_script["stream_caches_last"]
-    assert np.abs(r.caches.cpu().numpy()[:, 0, ::16, :] - ref_c).max() <= TOL * max(1.0, float(np.abs(ref_c).max()))
+    assert np.abs(r.caches.cpu().numpy()[:, 0, ::16, :] - ref_c).max() <= BOUND * max(1.0, float(np.abs(ref_c).max()))
     # the segmenter on the device probabilities equals the oracle on those same probabilities ...
     assert r.timestamps == OP.StreamPost(5, 0.4, 5, 8, 2000, 20).feed(r.probs)
     # ... and the script's record wherever no smoothed probability sits within TOL of the threshold
@@ -177,7 +177,7 @@ def test_stream_many_ragged_streams_against_oracle(cuda, stream_session):
         assert got_ts[s] == OP.StreamPost(5, 0.4, 5, 8, 2000, 20).feed(mine), s
         n_seg += len(got_ts[s])
     print(f"ragged lock-step streams: max abs err {worst:.2e}, segments {n_seg}")
-    assert worst <= TOL and n_seg > 0
+    assert worst <= BOUND and n_seg > 0
     assert got_ts[-1] == []
 
 
@@ -194,7 +194,7 @@ def test_vad_sample_vad_and_aed_sections(cuda, gold_script, golden_dir):
     g = gold_script
     err_v, err_a = np.abs(rv.probs - g["vad_probs"]).max(), np.abs(ra.probs - g["aed_probs"]).max()
     print(f"script sections: VAD max abs err {err_v:.2e}, AED {err_a:.2e}")
-    assert err_v <= TOL and err_a <= TOL
+    assert err_v <= BOUND and err_a <= BOUND
     if np.abs(OP.smooth_probs(g["vad_probs"], 5) - np.float32(0.4)).min() > TOL:
         assert np.array_equal(_pairs(rv.timestamps), g["vad_timestamps"])
     for e, (ev, thr) in enumerate((("speech", 0.4), ("singing", 0.5), ("music", 0.5))):
@@ -236,7 +236,7 @@ def test_aed_many_streams_against_oracle(cuda):
     probs, per_event, n_valid = firered_vad.run_aed_streams(sess, d, lengths)
     ref = FireRedOracle(wts, cfg).forward(audio.reshape(S * n_chunks, 16000)).numpy().reshape(S, n_chunks, 3, 98)
     ref = ref.transpose(0, 2, 1, 3).reshape(S, 3, n_chunks * 98)
-    assert np.abs(probs.cpu().numpy() - ref).max() <= TOL
+    assert np.abs(probs.cpu().numpy() - ref).max() <= BOUND
     nv = n_valid.cpu().numpy()
     p_host = probs.cpu().numpy()
     for e, (post, dec, cnt, seg) in enumerate(per_event):

@@ -12,6 +12,7 @@ from oracle import fsmn as OFS, postproc as OP
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+BOUND = 1e-4  # what this path is ASSERTED to: measured 3.5e-5; TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -88,6 +89,29 @@ def test_hysteresis_kernel_matches_oracle(cuda):
     assert np.array_equal(state0.saved[7, :len(ref0)].cpu().numpy().astype(bool), np.array(ref0))
 
 
+@pytest.mark.parametrize("speaking,silence_score", [(0.5, 0.5), (0.7, 0.3), (0.35, 0.6), (0.9, 0.1)])
+def test_probability_mode_hysteresis_uses_the_scores_per_frame(cuda, speaking, silence_score):
+    """DFSMN flavour: every frame votes with p >= SPEAKING_SCORE / p <= SILENCE_SCORE and the vote ratio is tested against
+    the same scores (DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:231-273); values ON the thresholds included."""
+    rs = np.random.RandomState(int(speaking * 100))
+    S, T, lb, n_chunks = 24, 83, 15, 4
+    base = rs.uniform(size=(n_chunks, S, (T + 5) // 6)).astype(np.float32)
+    probs = np.repeat(base, 6, axis=2)[:, :, :T] * 0.8 + rs.uniform(size=(n_chunks, S, T)).astype(np.float32) * 0.2
+    probs[:, :, ::11] = np.float32(speaking)         # exact ties with both scores
+    probs[:, :, 5::13] = np.float32(silence_score)
+    state = PP.HysteresisState(S, n_chunks * (T - lb) + lb, cuda)
+    for c in range(n_chunks):
+        PP.lookahead_hysteresis(torch.from_numpy(probs[c]).to(cuda), state, lb, speaking, silence_score, c == n_chunks - 1)
+    saved, n_saved = state.saved.cpu().numpy(), state.n_saved.cpu().numpy()
+    n_speech = 0
+    for s in range(S):
+        ref = OP.lookahead_hysteresis_probs([probs[c, s] for c in range(n_chunks)], lb, speaking, silence_score)
+        assert n_saved[s] == len(ref)
+        assert np.array_equal(saved[s, :len(ref)].astype(bool), np.array(ref)), s
+        n_speech += len(ref) - int(np.sum(ref))
+    assert n_speech > 0 or speaking >= 0.9      # the machine actually leaves silence
+
+
 @pytest.mark.parametrize("L", [16000, 512])
 def test_session_run_ort_contract(cuda, wts, L):
     cfg = W.FsmnConfig()
@@ -159,7 +183,7 @@ def test_vad_sample_against_reference_script(cuda, gold, golden_dir, wts, tmp_pa
     err_p = max(np.abs(r.p_silence[c] - o["trace"][c][0]).max() for c in range(len(o["trace"])))
     err_e = max(np.abs(r.power_dB[c] - o["trace"][c][1]).max() for c in range(len(o["trace"])))
     print(f"{tag}: max abs err P(silence) {err_p:.2e}, power_dB {err_e:.2e}")
-    assert err_p <= TOL and err_e <= TOL
+    assert err_p <= BOUND and err_e <= BOUND
     margin = min(min(np.abs(2 * t[0] - 1.0).min(), np.abs(t[1] - t[2]).min()) for t in o["trace"])
     if margin > TOL:
         assert np.array_equal(r.saved, gold[f"{tag}_saved"])

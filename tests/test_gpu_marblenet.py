@@ -14,6 +14,7 @@ from oracle.marblenet import MarbleNetOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+BOUND = 1e-4  # what this path is ASSERTED to: measured 3.0e-5; TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -45,26 +46,24 @@ def test_depthwise_conv(cuda, T, C, k, stride, dil):
 
 
 @pytest.mark.parametrize("L", [16000, 48000, 160000])
-def test_reference_recipe_through_run(gold, session, L):
+def test_reference_recipe_through_run(gold, session, L, measured):
     a = gold[f"recipe{L}_audio"].reshape(1, 1, -1)
     names = [o.name for o in session.get_outputs()]
     assert names == ["score_silence", "score_active", "signal_len"]
     sil, act, n = session.run(names, {session.get_inputs()[0].name: a})
     assert act.shape == (1, L // 320 + 1, 1) and n.dtype == np.int32 and int(n[0]) == int(gold[f"recipe{L}_signal_len"])
     err = max(np.abs(act[0, :, 0] - gold[f"recipe{L}_active"]).max(), np.abs(sil[0, :, 0] - gold[f"recipe{L}_silence"]).max())
-    print(f"recipe L={L}: max abs err {err:.2e}")
-    assert err <= TOL
+    measured("marblenet: recipe L=", err, BOUND)
 
 
-def test_synthetic_clips_batched_tc_and_simt(cuda, gold):
+def test_synthetic_clips_batched_tc_and_simt(cuda, gold, measured):
     cfg = W.MarbleNetConfig()
     w = W.marblenet_random_init(cfg, 0)
     clips = torch.from_numpy(synth.synth_streams(3, 160000, seed=1234)).to(cuda)
     for tc in (True, False):
         sc = vadx.MarbleNetSession(w, cfg, tensor_cores=tc).run_batch(clips).cpu().numpy()
         err = np.abs(sc[1] - gold["synth_active"]).max()
-        print(f"synthetic clips, tensor_cores={tc}: max abs err {err:.2e}")
-        assert err <= TOL
+        measured("marblenet: synthetic clips, tensor_cores=", err, BOUND)
         assert np.abs(sc[0] + sc[1] - 1.0).max() <= 1e-5
 
 
@@ -73,7 +72,7 @@ def test_vad_sample_timestamps(cuda, gold, golden_dir, session, tmp_path):
     f1, f2 = str(tmp_path / "s.txt"), str(tmp_path / "i.txt")
     r = marblenet_vad.run_vad(audio, session, save_timestamps_second=f1, save_timestamps_indices=f2)
     assert r.probs.shape == gold["sample_probs"].shape
-    assert np.abs(r.probs - gold["sample_probs"]).max() <= TOL
+    assert np.abs(r.probs - gold["sample_probs"]).max() <= BOUND
     sm = OP.smooth_probs(gold["sample_probs"], 3)
     if np.abs(sm - np.float32(0.5)).min() > TOL:
         assert np.array_equal(r.decisions, gold["sample_decisions"])
@@ -81,7 +80,7 @@ def test_vad_sample_timestamps(cuda, gold, golden_dir, session, tmp_path):
         assert open(f1).read() == str(gold["sample_file_second"]) and open(f2).read() == str(gold["sample_file_indices"])
 
 
-def test_long_clips_batch_against_oracle(cuda, session):
+def test_long_clips_batch_against_oracle(cuda, session, measured):
     """60 s clips (the BASELINE config-3 shape, small batch): 3000 valid frames each."""
     cfg = W.MarbleNetConfig()
     clips = synth.synth_streams(4, 960000, seed=8)
@@ -90,8 +89,7 @@ def test_long_clips_batch_against_oracle(cuda, session):
     _, act, n = MarbleNetOracle(W.marblenet_random_init(cfg, 0), cfg).forward(clips)
     assert n == 3000
     err = np.abs(probs.cpu().numpy() - act.numpy()[:, :3000, 0]).max()
-    print(f"60 s clips: max abs err {err:.2e}")
-    assert err <= TOL
+    measured("marblenet: 60 s clips: max abs err", err, BOUND)
     p = probs.cpu().numpy()
     for s in range(4):
         ref = OP.frame_decisions(p[s], 3, 0.5, 10, 1000, 10, 3, 0)
@@ -99,7 +97,7 @@ def test_long_clips_batch_against_oracle(cuda, session):
 
 
 @pytest.mark.parametrize("rate", [8000, 48000])
-def test_in_graph_resampler(cuda, golden_dir, rate):
+def test_in_graph_resampler(cuda, golden_dir, rate, measured):
     """IN_SAMPLE_RATE != 16000: golden from the reference's BN-folded wrapper built with that rate."""
     g = np.load(os.path.join(golden_dir, "marblenet_rates.npz"))
     cfg = W.MarbleNetConfig()
@@ -108,5 +106,4 @@ def test_in_graph_resampler(cuda, golden_dir, rate):
     sil, act, n = sess.run(None, {"audio": a[:, None, :]})
     assert int(n[0]) == int(g[f"r{rate}_signal_len"])
     err = np.abs(act[:, :, 0] - g[f"r{rate}_active"]).max()
-    print(f"marblenet in_sample_rate {rate}: max abs err {err:.2e}")
-    assert err <= TOL
+    measured("marblenet: marblenet in_sample_rate", err, BOUND)

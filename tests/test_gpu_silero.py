@@ -12,6 +12,7 @@ from oracle.silero import OnnxWrapperOracle, SileroNetOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+BOUND = 2e-4  # what this path is ASSERTED to: tcgen05 path; recurrent state carried over the windows; TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
@@ -55,7 +56,7 @@ def test_wrapper_call_and_state_carry(cuda, wts, session):
         o = session(a[:, t * 512:(t + 1) * 512], 16000)
         r = ref(a[:, t * 512:(t + 1) * 512], 16000)
         assert o.shape == (5, 1)
-        assert (o - r).abs().max().item() <= TOL
+        assert (o - r).abs().max().item() <= BOUND
     with pytest.raises(ValueError):
         session(a[:, :400], 16000)
     with pytest.raises(ValueError):
@@ -67,7 +68,7 @@ def test_vad_sample_against_reference_script(cuda, gold, golden_dir, session, tm
     probs = session.audio_forward(torch.from_numpy(audio.astype(np.float32) * 0.000030517578))
     err = np.abs(probs[0].numpy() - gold["sample_probs"]).max()
     print(f"vad_sample: max abs prob err {err:.2e}")
-    assert probs.shape == (1, 175) and err <= TOL
+    assert probs.shape == (1, 175) and err <= BOUND
     f1, f2 = str(tmp_path / "s.txt"), str(tmp_path / "i.txt")
     r = silero_vad.run_vad(audio, session, f1, f2)
     margin = min(np.abs(gold["sample_probs"] - 0.5).min(), np.abs(gold["sample_probs"] - 0.35).min())
@@ -93,7 +94,7 @@ def test_trigger_machine_matches_reference_function(cuda, gold):
         assert np.array_equal(np.array([(x["start"], x["end"]) for x in sec], np.float64).reshape(-1, 2), gold[f"ts{i}_sec"]), i
 
 
-def test_many_streams_batched(cuda, wts, session):
+def test_many_streams_batched(cuda, wts, session, measured):
     cfg = W.SileroConfig()
     S, n = 64, 512 * 60 + 123
     a = torch.from_numpy(synth.synth_streams(S, n, seed=3)).float() * 0.000030517578
@@ -101,8 +102,7 @@ def test_many_streams_batched(cuda, wts, session):
     ref = OnnxWrapperOracle(SileroNetOracle(wts, cfg)).audio_forward(a)
     assert probs.shape == ref.shape == (S, 61)
     err = (probs.cpu() - ref).abs().max().item()
-    print(f"{S} streams x 61 windows: max abs prob err {err:.2e}")
-    assert err <= TOL
+    measured("silero: prob err", err, BOUND)
     out = silero_vad.get_speech_timestamps(a, session, return_seconds=True)
     assert len(out) == S
 

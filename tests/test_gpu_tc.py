@@ -212,8 +212,9 @@ def test_firered_tc_vs_simt_and_oracle(cuda):
     ref = FireRedOracle(w, cfg).forward(chunks).numpy()
     e_tc, e_simt = np.abs(p_tc - ref).max(), np.abs(p_simt - ref).max()
     print(f"FireRed max abs prob err vs oracle: tensor-core {e_tc:.3e}, fp32 SIMT {e_simt:.3e}")
-    assert e_tc <= 1e-3 and e_simt <= 1e-3
-    assert np.abs(p_tc - p_simt).max() <= 1e-3
+    # asserted to each path's measured bound (contract: 1e-3): 1.0e-4 .. 1.9e-4 on the tcgen05 path, 8.7e-6 on the FFMA path
+    assert e_tc <= 3e-4 and e_simt <= 2e-5
+    assert np.abs(p_tc - p_simt).max() <= 3e-4
 
 
 @pytest.mark.parametrize("S", [1, 3, 300])

@@ -7,7 +7,7 @@ entry point raises if the CUDA library or a CUDA device is missing.
 """
 __version__ = "0.1.0"
 
-from . import constants, lib, tables, weights, synth  # noqa: F401
+from . import constants, lib, tables, weights, synth, distributed  # noqa: F401
 from .session import InferenceSession, FireRedSession, FireRedStreamSession, FsmnSession, MarbleNetSession, SileroSession  # noqa: F401
 from .postprocess import FramePostConfig, StreamVadPostprocessor, postprocess_frames  # noqa: F401
 from .dfsmn_aec import DfsmnAecSession  # noqa: F401,E402

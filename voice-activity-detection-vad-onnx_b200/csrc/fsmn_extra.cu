@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(128) fsmn_gate_kernel(const float* __restrict_
 // a13: look-ahead hysteresis, one stream per lane, state carried on the device between chunks.
 // mode 0 (FSMN): `in` is uint8 flags; a frame votes "speech" when flag != 0 and "silence" when
 //                flag != 1 (FSMN/Inference_FSMN_VAD_ONNX.py:188-215).
-// mode 1 (DFSMN): `in` is fp32 probabilities; votes are p >= 0.5 / p <= 0.5
-//                (DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:231-273).
+// mode 1 (DFSMN): `in` is fp32 probabilities; a frame votes with p >= SPEAKING_SCORE / p <= SILENCE_SCORE, the same two
+//                scores the vote RATIO is then tested against (DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:
+//                231-273).  The per-frame test compares a numpy float32 with a Python float: under NEP 50 (numpy >= 2) the
+//                Python float is the weak operand, so the comparison happens in float32; the ratio test is Python floats.
 __global__ void __launch_bounds__(128) lookahead_hysteresis_kernel(const void* __restrict__ in, int mode, int64_t ld_in,
                                                                    int64_t n_streams, int T, int look_backward,
                                                                    double speaking_score, double silence_score,
@@ -118,8 +120,9 @@ __global__ void __launch_bounds__(128) lookahead_hysteresis_kernel(const void* _
   if (s >= n_streams) return;
   const uint8_t* fl = static_cast<const uint8_t*>(in) + s * ld_in;
   const float* pr = static_cast<const float*>(in) + s * ld_in;
-  auto speech_vote = [&](int i) { return mode == 0 ? fl[i] != 0 : pr[i] >= 0.5f; };
-  auto silence_vote = [&](int i) { return mode == 0 ? fl[i] != 1 : pr[i] <= 0.5f; };
+  const float speak_f = (float)speaking_score, sil_f = (float)silence_score;
+  auto speech_vote = [&](int i) { return mode == 0 ? fl[i] != 0 : pr[i] >= speak_f; };
+  auto silence_vote = [&](int i) { return mode == 0 ? fl[i] != 1 : pr[i] <= sil_f; };
   const int lb = look_backward != 0 ? look_backward : 1;
   const double inv_d = 1.0 / (double)lb;
   bool silence = silence_state[s] != 0;

@@ -479,7 +479,7 @@ def run_vad(near, far, session: DfsmnAecSession, look_backward_s: float = LOOK_B
                                keep_trace=keep_trace)
     cnt, seg = state.segments()
     n_flags = int(state.n_saved[0].item())
-    pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
+    pairs = PP.take_segments(cnt, seg, 0)
     frame_d = OUTPUT_FRAME_LENGTH / SAMPLE_RATE
     ts = PP.process_timestamps(PP.runs_to_timestamps(pairs, n_flags, frame_d), FUSION_THRESHOLD, MIN_SPEECH_DURATION)
     sec, idx = PP.timestamp_lines(ts, SAMPLE_RATE)

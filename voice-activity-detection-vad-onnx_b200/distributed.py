@@ -1,0 +1,143 @@
+"""Multi-GPU plumbing of the VAD hot path: one process per GPU, streams split into contiguous
+blocks by rank, NO collective on the data path -- the reference has none either (every stream is an independent
+ORT call, e.g. FireRedVAD/Inference_FireRed_ONNX.py:567-572) -- and one final gather of the per-stream results:
+`seg_count [S]` and the `(start, end)` pairs `segments [S, max, 2]` the device post-processors emit.
+
+    init()                       -> (rank, world, device) from the torchrun environment (nccl on GPUs, gloo on CPU)
+    shard_streams(n, rank, world)-> this rank's contiguous block of stream indices
+    gather_segments(cnt, seg)    -> on every rank: counts [S_total] and pairs [S_total, max, 2] in global stream order
+    bind_to_local_numa_node(dev) -> pin this process (and therefore its pinned host buffers, first-touch) to the CPU
+                                    cores next to its GPU, so that 8 ranks do not push their H2D traffic through one
+                                    socket's memory controller
+
+The gather is two all_gathers: the per-rank block sizes are a pure function of (n_streams, world), so only the padded
+[block, max, 2] pair arrays and the counts travel; ranks whose block is shorter pad with zero-count rows that are cut off
+again.  Works on CUDA tensors over NCCL (NVLink / NVSwitch) and on CPU tensors over gloo (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+import os
+
+
+def shard_streams(n_streams: int, rank: int, world: int) -> range:
+    """Contiguous block of streams owned by `rank`: ceil(n/world) per rank, the last ranks may be short or empty."""
+    if world < 1 or not (0 <= rank < world) or n_streams < 0:
+        raise ValueError(f"shard_streams: bad arguments n_streams={n_streams} rank={rank} world={world}")
+    per = (n_streams + world - 1) // world
+    return range(min(n_streams, rank * per), min(n_streams, (rank + 1) * per))
+
+
+def block_size(n_streams: int, world: int) -> int:
+    return (n_streams + world - 1) // world
+
+
+def init(backend: str | None = None):
+    """Process-group setup from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
+    Returns (rank, world, device).  With WORLD_SIZE == 1 no process group is created."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+    else:
+        dev = torch.device("cpu")
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if dev.type == "cuda" else "gloo")
+        if backend == "nccl":
+            dist.init_process_group(backend, device_id=dev)
+        else:
+            dist.init_process_group(backend)
+    return rank, world, dev
+
+
+def gather_segments(seg_count, segments, n_streams_total: int | None = None, group=None):
+    """All ranks receive every rank's post-processor output in global stream order.
+
+    seg_count: int32 [S_local]; segments: int [S_local, max_segments, 2] (same max_segments and dtype on every rank; CUDA
+    for nccl, CPU for gloo).  n_streams_total: the global stream count the blocks came from (shard_streams); default =
+    world * S_local (equal blocks).  Returns (counts [S_total], pairs [S_total, max_segments, 2])."""
+    import torch
+    import torch.distributed as dist
+    if seg_count.dim() != 1 or segments.dim() != 3 or segments.shape[0] != seg_count.shape[0] or segments.shape[2] != 2:
+        raise ValueError("gather_segments: expected seg_count [S] and segments [S, max_segments, 2]")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if n_streams_total is not None and n_streams_total != seg_count.shape[0]:
+            raise ValueError("gather_segments: single rank but n_streams_total != local stream count")
+        return seg_count, segments
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    S_local, max_seg = seg_count.shape[0], segments.shape[1]
+    if n_streams_total is None:
+        n_streams_total = world * S_local
+    per = block_size(n_streams_total, world)
+    if S_local != len(shard_streams(n_streams_total, rank, world)):
+        raise ValueError(f"gather_segments: rank {rank} holds {S_local} streams, its block of {n_streams_total} has "
+                         f"{len(shard_streams(n_streams_total, rank, world))}")
+    cnt = seg_count.contiguous()
+    seg = segments.contiguous()
+    if S_local < per:       # short (or empty) last blocks: pad to the common block size, cut off after the gather
+        cnt = torch.cat([cnt, cnt.new_zeros((per - S_local,))])
+        seg = torch.cat([seg, seg.new_zeros((per - S_local, max_seg, 2))])
+    all_cnt = cnt.new_empty((world * per,))
+    all_seg = seg.new_empty((world * per, max_seg, 2))
+    dist.all_gather_into_tensor(all_cnt, cnt, group=group)
+    dist.all_gather_into_tensor(all_seg, seg, group=group)
+    return all_cnt[:n_streams_total], all_seg[:n_streams_total]
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """The timing rule of every multi-GPU number: device time as the maximum over ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def _cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def local_numa_cpus(device_index: int):
+    """CPU cores of the NUMA node the GPU hangs off (sysfs through the PCI bus id NVML / torch report); None when the
+    platform does not say (single-socket boxes report node -1)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(os.path.join(path, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        return _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) or None
+    except Exception:
+        return None
+
+
+def bind_to_local_numa_node(device_index: int) -> dict:
+    """Restrict this process to the cores next to its GPU BEFORE allocating pinned host buffers: pages are placed on the
+    node of the first-touching thread, so the H2D copies of a rank then read local memory.  Returns what was done
+    ({"node_cpus": n, "bound": bool}); a no-op where the topology is unknown or the affinity call is refused."""
+    cpus = local_numa_cpus(device_index)
+    if not cpus:
+        return {"node_cpus": 0, "bound": False}
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = set(cpus) & allowed
+        if not want:
+            return {"node_cpus": len(cpus), "bound": False}
+        os.sched_setaffinity(0, want)
+        return {"node_cpus": len(want), "bound": True}
+    except OSError:
+        return {"node_cpus": len(cpus), "bound": False}

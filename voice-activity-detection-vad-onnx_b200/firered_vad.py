@@ -72,7 +72,8 @@ def run_vad_streams(session: FireRedSession, chunks, lengths, post: PP.FramePost
         raise ValueError("run_vad_streams expects the VAD head (odim == 1)")
     probs = probs.reshape(S, n_chunks * T)
     if n_valid is None:   # pass a cached CUDA int32 tensor to keep the call free of host->device copies
-        n_valid = torch.tensor([min(valid_frame_count(int(n)), n_chunks * T) for n in lengths], dtype=torch.int32,
+        in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
+        n_valid = torch.tensor([min(valid_frame_count(int(n), in_sr), n_chunks * T) for n in lengths], dtype=torch.int32,
                                device=chunks.device)
     dec, cnt, seg = PP.postprocess_frames(probs, post, n_valid, stream=stream)
     return probs, dec, cnt, seg, n_valid
@@ -80,28 +81,43 @@ def run_vad_streams(session: FireRedSession, chunks, lengths, post: PP.FramePost
 
 class HostBatchPipeline:
     """Host-buffer front door for serving: pinned int16 batches in, segment frame pairs back in pinned
-    host memory.  The H2D copy of batch i+1 runs on a copy stream while batch i computes (two device
+    host memory.  The H2D copy of batch i+1 runs on a copy stream while batch i computes (`depth` device
     input buffers, event hand-over), so a steady stream of batches costs max(copy, compute) per batch
-    instead of their sum; results (seg_count, segments) are copied back asynchronously."""
+    instead of their sum; results (seg_count, segments) are copied back asynchronously.  The copy is
+    issued in `copy_chunks` pieces so that the copy engine always has the next piece queued behind the
+    running one and a late `consumed` event delays only the first piece.
+
+    gather=True (multi-GPU): after the post-processor the per-rank results are all-gathered on the
+    device over NCCL (vadx.distributed.gather_segments, the path's only collective) and rank 0's pinned
+    buffers receive the GLOBAL result: seg_count [world*S], segments [world*S, max, 2]; the other ranks read
+    nothing back (run returns None there)."""
 
     def __init__(self, session: FireRedSession, n_streams: int, n_chunks: int, post: PP.FramePostConfig = POST_DEFAULT,
-                 device=None):
+                 device=None, depth: int = 2, copy_chunks: int = 4, gather: bool = False):
         import torch
+        import torch.distributed as dist
         self.session, self.post = session, post
         self.S, self.n_chunks, self.L = n_streams, n_chunks, session.chunk_len
         dev = device or torch.device("cuda", torch.cuda.current_device())
         self.T = session.frames(self.L)
         self.max_seg = (n_chunks * self.T) // 2 + 1
-        self.d_in = [torch.empty((n_streams, n_chunks, self.L), dtype=torch.int16, device=dev) for _ in range(2)]
+        self.depth = max(2, int(depth))
+        self.copy_chunks = max(1, min(int(copy_chunks), n_streams))
+        self.gather = bool(gather) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.gather else 1
+        self.reads_back = (not self.gather) or dist.get_rank() == 0
+        self.d_in = [torch.empty((n_streams, n_chunks, self.L), dtype=torch.int16, device=dev) for _ in range(self.depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
-        self.h_cnt = [torch.empty((n_streams,), dtype=torch.int32).pin_memory() for _ in range(2)]
-        self.h_seg = [torch.empty((n_streams, self.max_seg, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
-        self.n_valid = torch.full((n_streams,), min(valid_frame_count(n_chunks * self.L), n_chunks * self.T),
+        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
+        S_out = n_streams * self.world
+        self.h_cnt = [torch.empty((S_out,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.h_seg = [torch.empty((S_out, self.max_seg, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+        in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
+        self.n_valid = torch.full((n_streams,), min(valid_frame_count(n_chunks * self.L, in_sr), n_chunks * self.T),
                                   dtype=torch.int32, device=dev)
-        self._i = 0
-        self._prefetched = False
+        self._i = 0            # batches run
+        self._queued = 0       # batches whose H2D copy has been enqueued
 
     @property
     def h2d_bytes(self) -> int:
@@ -109,56 +125,70 @@ class HostBatchPipeline:
 
     @property
     def d2h_bytes(self) -> int:
-        return self.h_cnt[0].numel() * 4 + self.h_seg[0].numel() * 4
+        return (self.h_cnt[0].numel() * 4 + self.h_seg[0].numel() * 4) if self.reads_back else 0
 
     def prefetch(self, pinned):
-        """enqueue the H2D copy of the NEXT batch (returns immediately)"""
+        """enqueue the H2D copy of the NEXT not-yet-queued batch (returns immediately); up to depth - 1 batches
+        may be queued ahead of the one being computed"""
         import torch
-        b = self._i % 2
+        if self._queued - self._i >= self.depth:
+            raise RuntimeError("HostBatchPipeline.prefetch: every device input buffer already holds a queued batch")
+        b = self._queued % self.depth
+        src = pinned.view(self.S, self.n_chunks, self.L)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[b])
-            self.d_in[b].copy_(pinned.view(self.S, self.n_chunks, self.L), non_blocking=True)
+            step = (self.S + self.copy_chunks - 1) // self.copy_chunks
+            for lo in range(0, self.S, step):
+                self.d_in[b][lo:lo + step].copy_(src[lo:lo + step], non_blocking=True)
             self.copied[b].record(self.copy_stream)
-        self._prefetched = True
+        self._queued += 1
 
     def run(self, pinned, next_pinned=None):
         """process one batch; if `next_pinned` is given its copy overlaps this batch's compute.
         Returns the pinned (seg_count, segments) buffers this batch's results are being copied into
         (valid after the current stream is synchronised)."""
         import torch
-        if not self._prefetched:
+        if self._queued == self._i:
             self.prefetch(pinned)
-        b = self._i % 2
+        b = self._i % self.depth
         main = torch.cuda.current_stream()
         main.wait_event(self.copied[b])
         self._i += 1
-        self._prefetched = False
-        if next_pinned is not None:
+        if next_pinned is not None and self._queued - self._i < self.depth - 1:
             self.prefetch(next_pinned)
         _, _, cnt, seg, _ = run_vad_streams(self.session, self.d_in[b], None, self.post, n_valid=self.n_valid)
         self.consumed[b].record(main)
-        self.h_cnt[b].copy_(cnt, non_blocking=True)
-        self.h_seg[b].copy_(seg, non_blocking=True)
-        return self.h_cnt[b], self.h_seg[b]
+        if self.gather:
+            from . import distributed as D
+            cnt, seg = D.gather_segments(cnt, seg)
+            if not self.reads_back:
+                return None
+        r = (self._i - 1) % 2
+        self.h_cnt[r].copy_(cnt, non_blocking=True)
+        self.h_seg[r].copy_(seg, non_blocking=True)
+        return self.h_cnt[r], self.h_seg[r]
 
 
 def run_vad(audio, session: FireRedSession, post: PP.FramePostConfig = POST_DEFAULT, rng=None,
             save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None) -> VadResult:
-    """One stream, the reference's behaviour: `audio` is a path to a wav file or an int16 array."""
+    """One stream, the reference's behaviour: `audio` is a path to a wav file or an int16 array at the session's
+    IN_SAMPLE_RATE (FireRedSession(in_sample_rate=...), default 16000): loading, valid_frame_count, the open-tail clamp
+    and the sample indices all use that rate, as the reference's module constant does (:84-89, :538, :590, :606)."""
     import torch
+    in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
     if isinstance(audio, str):
-        audio = audio_io.load_wav_int16(audio, IN_SAMPLE_RATE)
-    chunk_len = session.chunk_len or min(IN_SAMPLE_RATE * 3600, len(audio))
+        audio = audio_io.load_wav_int16(audio, in_sr)
+    chunk_len = session.chunk_len or min(in_sr * 3600, len(audio))
     chunks, audio_len = audio_io.align_non_overlapping(audio, chunk_len, rng)
     d = torch.from_numpy(chunks).cuda().unsqueeze(0)
     probs, dec, cnt, seg, n_valid = run_vad_streams(session, d, [audio_len], post)
     n = int(n_valid[0].item())
-    k = int(cnt[0].item())
+    k = len(PP.take_segments(cnt, seg, 0))
     pairs = seg[0, :k].cpu().numpy()
-    ts = PP.segments_to_seconds(pairs, n, post, audio_len / IN_SAMPLE_RATE)
-    sec, idx = PP.timestamp_lines(ts, IN_SAMPLE_RATE)
+    ts = PP.segments_to_seconds(pairs, n, post, audio_len / in_sr)
+    sec, idx = PP.timestamp_lines(ts, in_sr)
     if save_timestamps_second and save_timestamps_indices:
-        PP.write_timestamp_files(ts, save_timestamps_second, save_timestamps_indices, IN_SAMPLE_RATE)
+        PP.write_timestamp_files(ts, save_timestamps_second, save_timestamps_indices, in_sr)
     return VadResult(ts, probs[0, :n].cpu().numpy(), dec[0, :n].cpu().numpy(), sec, idx)
 
 
@@ -179,7 +209,8 @@ def run_aed_streams(session: FireRedSession, chunks, lengths, thresholds=None, s
     thresholds = thresholds or [SPEAKING_SCORE, SINGING_THRESHOLD, MUSIC_THRESHOLD][:odim]
     p = session.run_batch(chunks.reshape(S * n_chunks, L), stream=stream)               # [S*n_chunks, odim, T]
     probs = p.view(S, n_chunks, odim, T).permute(0, 2, 1, 3).reshape(S, odim, n_chunks * T)
-    n_valid = torch.tensor([min(valid_frame_count(int(n)), n_chunks * T) for n in lengths], dtype=torch.int32,
+    in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
+    n_valid = torch.tensor([min(valid_frame_count(int(n), in_sr), n_chunks * T) for n in lengths], dtype=torch.int32,
                            device=chunks.device)
     per_event = []
     for e in range(odim):
@@ -192,9 +223,10 @@ def run_aed_streams(session: FireRedSession, chunks, lengths, thresholds=None, s
 def run_aed(audio, session: FireRedSession, rng=None) -> AedResult:
     """One stream, the reference's RUN_AED section (:620-738)."""
     import torch
+    in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
     if isinstance(audio, str):
-        audio = audio_io.load_wav_int16(audio, IN_SAMPLE_RATE)
-    chunk_len = session.chunk_len or min(IN_SAMPLE_RATE * 3600, len(audio))
+        audio = audio_io.load_wav_int16(audio, in_sr)
+    chunk_len = session.chunk_len or min(in_sr * 3600, len(audio))
     chunks, audio_len = audio_io.align_non_overlapping(audio, chunk_len, rng)
     d = torch.from_numpy(chunks).cuda().unsqueeze(0)
     probs, per_event, n_valid = run_aed_streams(session, d, [audio_len])
@@ -203,8 +235,8 @@ def run_aed(audio, session: FireRedSession, rng=None) -> AedResult:
     ts, ratio = {}, {}
     for e, (post, _dec, cnt, seg) in enumerate(per_event):
         name = IDX2EVENT.get(e, str(e))
-        pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
-        ts[name] = PP.segments_to_seconds(pairs, n, post, audio_len / IN_SAMPLE_RATE)
+        pairs = PP.take_segments(cnt, seg, 0)
+        ts[name] = PP.segments_to_seconds(pairs, n, post, audio_len / in_sr)
         ratio[name] = round(float(np.mean(host[e] >= post.prob_threshold)) if n > 0 else 0.0, 3)
     return AedResult(ts, ratio, host)
 

@@ -161,7 +161,7 @@ def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD,
     state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace, graph=graph)
     cnt, seg = state.segments()
     n_flags = int(state.n_saved[0].item())
-    pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
+    pairs = PP.take_segments(cnt, seg, 0)
     frame_d = OUTPUT_FRAME_LENGTH / SAMPLE_RATE
     ts = PP.process_timestamps(PP.runs_to_timestamps(pairs, n_flags, frame_d), fusion_threshold, min_speech_duration)
     sec, idx = PP.timestamp_lines(ts, SAMPLE_RATE)

@@ -60,7 +60,7 @@ def run_vad(audio, session: MarbleNetSession, post: PP.FramePostConfig = POST_DE
     d = torch.from_numpy(audio).cuda().unsqueeze(0)
     probs, dec, cnt, seg = run_vad_clips(session, d, post)
     n = probs.shape[1]
-    pairs = seg[0, :int(cnt[0].item())].cpu().numpy()
+    pairs = PP.take_segments(cnt, seg, 0)
     ts = PP.segments_to_seconds(pairs, n, post, audio_len / IN_SAMPLE_RATE)
     sec, idx = PP.timestamp_lines(ts, IN_SAMPLE_RATE)
     if save_timestamps_second and save_timestamps_indices:

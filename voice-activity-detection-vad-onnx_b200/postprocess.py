@@ -80,6 +80,23 @@ def segments_to_seconds(pairs: np.ndarray, n_frames: int, cfg: FramePostConfig, 
     return [(round(a, 3), round(b, 3)) for a, b in seg.tolist()]
 
 
+def take_segments(seg_count, segments, stream_index: int | None = None):
+    """Host view of the device post-processors' output with the overflow check every consumer needs: the kernels COUNT
+    every segment but only STORE the first max_segments (= segments.shape[1]), so a count above that bound means
+    trailing segments were dropped.  seg_count [S], segments [S, max, 2] (CUDA or CPU tensors / numpy arrays).
+    Returns (counts ndarray [S], pairs ndarray [S, max, 2]), or the [k, 2] pairs of one stream when stream_index is given."""
+    cnt = seg_count.cpu().numpy() if hasattr(seg_count, "cpu") else np.asarray(seg_count)
+    seg = segments.cpu().numpy() if hasattr(segments, "cpu") else np.asarray(segments)
+    max_segments = seg.shape[1]
+    if cnt.size and int(cnt.max()) > max_segments:
+        worst = int(cnt.argmax())
+        raise RuntimeError(f"stream {worst} produced {int(cnt.max())} segments but only max_segments={max_segments} were stored; "
+                           f"pass a larger max_segments")
+    if stream_index is None:
+        return cnt, seg
+    return seg[stream_index, :int(cnt[stream_index])]
+
+
 def lookahead_hysteresis(values, state, look_backward: int, speaking_score: float, silence_score: float,
                          is_final: bool, noisy_dB=None, snr_threshold: float = 1.0, stream=None):
     """One chunk of the FSMN / DFSMN look-ahead state machine for S streams, on the device.

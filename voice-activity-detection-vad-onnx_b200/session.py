@@ -39,7 +39,7 @@ class _Engine:
         h = C.c_void_p()
         lib.check(self._lib.vadx_create(kind.encode(), hp, len(hparams), C.byref(h)))
         self._h = h
-        self._ws = None
+        self._ws = {}            # (device, stream handle) -> workspace: calls in flight on different streams never share scratch
         self._captured_ws = []
 
     def close(self):
@@ -68,17 +68,26 @@ class _Engine:
         lib.check(self._lib.vadx_workspace_bytes(self._h, n_streams, n_samples, C.byref(out)))
         return out.value
 
-    def workspace(self, n_bytes: int, device):
+    def workspace(self, n_bytes: int, device, stream=None):
+        """One growable scratch buffer per (device, stream): two calls enqueued on different streams may overlap on the
+        GPU, so they must not share it.  A buffer that is outgrown may still be in use by work queued on ITS stream;
+        record_stream keeps the caching allocator from handing the block out before that work has finished."""
         torch = self._torch
-        if self._ws is None or self._ws.numel() < n_bytes or self._ws.device != device:
-            self._ws = None
-            self._ws = torch.empty(n_bytes, dtype=torch.uint8, device=device)
-        return self._ws
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), int(st.cuda_stream))
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < n_bytes:
+            if ws is not None:
+                ws.record_stream(st)
+            with torch.cuda.device(device):
+                ws = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
 
     def forward(self, inputs, outputs, states, n_streams, n_samples, stream=None):
         dev = inputs[0].device
         need = self.workspace_bytes(n_streams, n_samples)
-        ws = self.workspace(need, dev)
+        ws = self.workspace(need, dev, stream)
         if self._torch.cuda.is_current_stream_capturing() and not any(ws is k for k in self._captured_ws):
             self._captured_ws.append(ws)   # a CUDA graph now holds this address: never free it (growth allocates anew)
         ins = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])

@@ -53,7 +53,7 @@ def raw_segments(probs, n_samples, threshold: float = 0.5, sampling_rate: int = 
         raise ValueError("raw_segments: fewer probabilities than windows")
     d_ns = torch.from_numpy(n_samples).to(probs.device)
     d_nw = torch.from_numpy(n_windows).to(probs.device)
-    max_segments = max_segments or n_win // 2 + 2
+    max_segments = max_segments or n_win + 1      # a max-speech cut can close a segment in every window
     cnt = torch.empty((S,), dtype=torch.int32, device=probs.device)
     seg = torch.empty((S, max_segments, 2), dtype=torch.int64, device=probs.device)
     lib.check(lib.load().vadx_silero_timestamps(
@@ -117,7 +117,7 @@ def get_speech_timestamps(audio, model: SileroSession, threshold: float = 0.5, s
     cnt, seg = raw_segments(probs, [n] * d.shape[0], threshold, sampling_rate, min_speech_duration_ms,
                             max_speech_duration_s, min_silence_duration_ms, speech_pad_ms, neg_threshold,
                             min_silence_at_max_speech, use_max_poss_sil_at_max_speech)
-    cnt, seg = cnt.cpu().numpy(), seg.cpu().numpy()
+    cnt, seg = PP.take_segments(cnt, seg)
     out = []
     for s in range(d.shape[0]):
         sp = pad_and_convert(seg[s, :cnt[s]], n, sampling_rate, speech_pad_ms, return_seconds, time_resolution)
