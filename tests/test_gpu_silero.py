@@ -12,7 +12,7 @@ from oracle.silero import OnnxWrapperOracle, SileroNetOracle
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
-BOUND = 2e-4  # what this path is ASSERTED to: tcgen05 path; recurrent state carried over the windows; TOL stays the contract and the decision-margin test
+BOUND = 5e-5  # what this path is ASSERTED to: measured 7e-6 (tcgen05 path, recurrent state carried over the windows); TOL stays the contract and the decision-margin test
 
 
 @pytest.fixture(scope="module")
