@@ -721,7 +721,16 @@ def gen_dfsmn_near():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_near.npz"), **out)
 
 
-GENERATORS = {"dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "marblenet_rates": gen_marblenet_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+def gen_dropin():
+    """The session-call transcript of the three unmodified inference scripts (oracle/dropin.py, stage "record")."""
+    from oracle import dropin
+    out = dropin.record_transcripts()
+    for fam in dropin.FAMILIES:
+        print(fam, {k: getattr(v, "shape", None) for k, v in out.items() if k.startswith(fam + "_") and "file" not in k})
+    np.savez_compressed(os.path.join(GOLD, "dropin_transcript.npz"), **out)
+
+
+GENERATORS = {"dropin": gen_dropin, "dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "marblenet_rates": gen_marblenet_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 

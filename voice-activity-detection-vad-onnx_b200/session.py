@@ -531,7 +531,21 @@ class SileroSession:
         self._e.set_scalar("engine.use_tc", 1.0 if tensor_cores else 0.0)
         self._row_stride = None
         self._dev = torch.device("cuda", torch.cuda.current_device())
+        n_in = cfg.window + cfg.context
+        self._inputs_meta = [NodeArg("input", [None, n_in], "tensor(float)"), NodeArg("state", [2, None, cfg.hidden], "tensor(float)"),
+                             NodeArg("sr", [], "tensor(int64)")]
+        self._outputs_meta = [NodeArg("output", [None, 1], "tensor(float)"), NodeArg("stateN", [2, None, cfg.hidden], "tensor(float)")]
         self.reset_states()
+
+    # ---- ORT surface of the opaque silero_vad.onnx session the reference's OnnxWrapper holds (utils_vad.py:33-61,119-123)
+    def get_inputs(self):
+        return list(self._inputs_meta)
+
+    def get_outputs(self):
+        return list(self._outputs_meta)
+
+    def get_providers(self):
+        return ["B200ExecutionProvider"]
 
     # ---- raw graph ---------------------------------------------------------------------------
     def step(self, x, state, row_stride: int | None = None, stream=None):
