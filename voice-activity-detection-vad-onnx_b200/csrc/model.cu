@@ -321,6 +321,7 @@ const KindOps kKinds[] = {
     {"fsmn", fsmn_check, fsmn_finalize, fsmn_frames, fsmn_run},
     {"silero", silero_check, silero_finalize, silero_frames, silero_run},
     {"marblenet", marblenet_check, marblenet_finalize, marblenet_frames, marblenet_run},
+    {"dfsmn_aec", dfsmn_check, dfsmn_finalize, dfsmn_frames, dfsmn_run},
 };
 const KindOps* ops_of(const std::string& kind) {
   for (const auto& k : kKinds)

@@ -205,3 +205,8 @@ int fsmn_finalize(vadx_model* m);
 int fsmn_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
 int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S,
              int64_t L, void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);
+int dfsmn_check(const vadx_model* m);
+int dfsmn_finalize(vadx_model* m);
+int dfsmn_frames(const vadx_model* m, int64_t n_samples, int32_t* out);
+int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* state, int64_t S, int64_t L,
+              void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st);

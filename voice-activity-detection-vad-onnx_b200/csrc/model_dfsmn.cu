@@ -1,0 +1,405 @@
+// model_dfsmn.cu -- the DFSMN AEC-VAD graph (DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py:317-354, and the
+// near-end-only twin DFSMN/only_near_end_audio/Export_DFSMN_VAD.py:291-352) as one kernel sequence on the caller's
+// stream: both inputs scaled + DC-removed -> STFT-B (319/160) -> AlphaPredictor scaling of the far end -> ICCRN echo
+// estimator (:65-284: frequency bi-LSTM, 10 gated conv blocks with cepstral bi-LSTMs, 2-layer time LSTM bottleneck,
+// time LSTM, ISTFT) -> pre-emphasis, echo = near - 1.15 aec -> 3 x STFT-A (1024/640/320) power -> HTK mel -> log ->
+// mask-net (linear1, relu, N x UniDeepFsmn, linear3, sigmoid) -> one probability per 20 ms frame.
+//
+// vadx_forward contract for kind "dfsmn_aec":
+//   hparams  {channels, n_fft_b, hop_b, alpha_k, n_fft_a, win_a, hop_a, n_mels, mask_hidden, mask_layers, mask_inner,
+//             mask_lorder, max_frames, near_only, first_a}
+//   inputs   [0] near-end int16 [S][L]   [1] far-end int16 [S][L] (null for near_only)
+//            [2] optional: the 4-channel ICCRN input [S*T_b*F][4] injected instead of the computed one (stage parity tests)
+//   outputs  [0] probabilities fp32 [S][T], T = L / hop_a + 1        [1] optional: echo estimate fp32 [S][L]
+//   tensors  the reference state dict re-laid by the host (vadx/dfsmn_aec.py): "<layer>.weight" [out][in], "<layer>.bias",
+//            LSTM parts under their PyTorch names, layer-norm tables as [bin][channel], the DFT / cepstral / ISTFT tables
+//   scalars  pre_emphasis, echo_factor, log_floor, alpha.w1_far, alpha.w1_mix, alpha.b1, alpha.b2, engine.use_tc
+// Activations are [stream][frame][bin][channel]; the ~60-layer echo estimator runs on the exact-fp32 kernels of
+// iccrn.cu / gemm_simt.cu, the 128/256-wide mask-net on tcgen05 (gemm_tc.cu).  The workspace is a stack: every gated
+// conv block releases its scratch when it returns, so the peak is one block's scratch plus the six skip tensors.
+#include "model.hpp"
+
+namespace {
+struct DfsmnHP {
+  int c, n_fft_b, hop_b, alpha_k, n_fft_a, win_a, hop_a, n_mels, mask_h, mask_layers, mask_inner, mask_lorder, max_frames,
+      near_only, first_a;
+  int F() const { return n_fft_b / 2 + 1; }
+  int cb() const { return F() / 2 + 1; }
+  int Tb(int64_t L) const { return (int)((L - 1) / hop_b + 1); }
+  int T(int64_t L) const { return (int)(L / hop_a + 1); }
+};
+
+int dfsmn_hp(const vadx_model* m, DfsmnHP* h) {
+  VADX_REQUIRE(m->hp.size() == 15, "dfsmn_aec: expected 15 hyper-parameters, got %zu", m->hp.size());
+  const int32_t* v = m->hp.data();
+  *h = DfsmnHP{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14]};
+  VADX_REQUIRE(h->c >= 1 && h->n_fft_b >= 3 && h->hop_b >= 1 && h->alpha_k >= 1 && h->n_fft_a >= 2 && h->win_a >= 1 &&
+                   h->hop_a >= 1 && h->n_mels >= 1 && h->mask_h >= 1 && h->mask_layers >= 0 && h->mask_inner >= 1 &&
+                   h->mask_lorder >= 1 && h->max_frames >= 1,
+               "dfsmn_aec: hyper-parameter out of range");
+  return VADX_OK;
+}
+
+// names of the ten gated conv blocks in execution order: encoder 1..5, decoder 5..1
+std::string cfb_name(int i) { return i < 5 ? "cfb_e" + std::to_string(i + 1) : "cfb_d" + std::to_string(10 - i); }
+}  // namespace
+
+int dfsmn_check(const vadx_model* m) {
+  DfsmnHP h;
+  return dfsmn_hp(m, &h);
+}
+
+int dfsmn_frames(const vadx_model* m, int64_t n_samples, int32_t* out) {
+  DfsmnHP h;
+  VADX_TRY(dfsmn_hp(m, &h));
+  *out = h.T(n_samples);
+  return VADX_OK;
+}
+
+int dfsmn_finalize(vadx_model* m) {
+  DfsmnHP h;
+  VADX_TRY(dfsmn_hp(m, &h));
+  const int c = h.c, F = h.F(), cb = h.cb();
+  auto linear = [&](const std::string& n, int n_out, int n_in, bool bias) -> int {
+    VADX_TRY(m->upload_linear(n + ".weight", n_out, n_in));
+    if (bias) VADX_TRY(m->upload_raw(n + ".bias", n_out, VADX_DT_F32));
+    return VADX_OK;
+  };
+  auto lstm = [&](const std::string& n, int n_in, int H, int layers, bool bi) -> int {
+    for (int l = 0; l < layers; ++l)
+      for (int d = 0; d < (bi ? 2 : 1); ++d) {
+        const std::string suf = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+        const int in_l = l == 0 ? n_in : H * (bi ? 2 : 1);
+        VADX_TRY(m->upload_raw(n + ".weight_ih" + suf, (int64_t)4 * H * in_l, VADX_DT_F32));
+        VADX_TRY(m->upload_raw(n + ".weight_hh" + suf, (int64_t)4 * H * H, VADX_DT_F32));
+        VADX_TRY(m->upload_raw(n + ".bias_ih" + suf, 4 * H, VADX_DT_F32));
+        VADX_TRY(m->upload_raw(n + ".bias_hh" + suf, 4 * H, VADX_DT_F32));
+      }
+    return VADX_OK;
+  };
+  VADX_TRY(m->upload_raw("basis_b", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_raw("basis_a", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_raw("mel_start", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("mel_len", h.n_mels, VADX_DT_I32));
+  VADX_TRY(m->upload_raw("mel_w", -1, VADX_DT_F32));
+  VADX_TRY(linear("ceps.dft", 2 * cb, F, false));
+  VADX_TRY(linear("ceps.idft", F, 2 * cb, false));
+  VADX_TRY(linear("istft", h.n_fft_b, 2 * F, false));
+  VADX_TRY(m->upload_raw("wsum_inv", -1, VADX_DT_F32));
+  VADX_TRY(m->upload_raw("alpha.w2", h.alpha_k, VADX_DT_F32));
+  if (h.near_only) {
+    VADX_TRY(m->upload_raw("far.pow", (int64_t)F * h.max_frames * h.alpha_k, VADX_DT_F32));
+    VADX_TRY(m->upload_raw("far.comp", (int64_t)2 * F * h.max_frames, VADX_DT_F32));
+  }
+  VADX_TRY(lstm("in_lstm", 4, c, 1, true));
+  VADX_TRY(linear("in_lstm.linear", c, 2 * c, true));
+  VADX_TRY(linear("in_conv", c, c + 4, true));
+  for (int i = 0; i < 10; ++i) {
+    const std::string n = cfb_name(i);
+    const int cin = (i >= 6) ? 2 * c : c;       // decoder blocks 4..1 take cat(skip, previous)
+    VADX_TRY(linear(n + ".gate", c, cin, true));
+    VADX_TRY(linear(n + ".input", c, cin, true));
+    VADX_TRY(linear(n + ".conv", c, 3 * c, true));
+    VADX_TRY(m->upload_raw(n + ".LN0.w", (int64_t)F * cin, VADX_DT_F32));
+    VADX_TRY(m->upload_raw(n + ".LN0.b", (int64_t)F * cin, VADX_DT_F32));
+    for (const char* ln : {".LN1", ".LN2"}) {
+      VADX_TRY(m->upload_raw(n + ln + ".w", (int64_t)F * c, VADX_DT_F32));
+      VADX_TRY(m->upload_raw(n + ln + ".b", (int64_t)F * c, VADX_DT_F32));
+    }
+    VADX_TRY(m->upload_raw(n + ".cLN.w", (int64_t)cb * 2 * c, VADX_DT_F32));
+    VADX_TRY(m->upload_raw(n + ".cLN.b", (int64_t)cb * 2 * c, VADX_DT_F32));
+    VADX_TRY(lstm(n + ".clstm", 2 * c, c, 1, true));
+    VADX_TRY(linear(n + ".clstm.linear", 2 * c, 2 * c, true));
+  }
+  VADX_TRY(m->upload_raw("ln.w", (int64_t)F * c, VADX_DT_F32));
+  VADX_TRY(m->upload_raw("ln.b", (int64_t)F * c, VADX_DT_F32));
+  VADX_TRY(lstm("mid_lstm", c, 2 * c, 2, false));
+  VADX_TRY(linear("mid_lstm.linear", c, 2 * c, true));
+  VADX_TRY(lstm("out_lstm", 2 * c, c, 1, false));
+  VADX_TRY(linear("out_lstm.linear", 2 * c, c, true));
+  VADX_TRY(linear("out_conv", 2, 3 * c, true));
+  VADX_TRY(linear("mask.linear1", h.mask_h, 3 * h.n_mels, true));
+  for (int i = 0; i < h.mask_layers; ++i) {
+    const std::string p = "mask." + std::to_string(i);
+    VADX_TRY(linear(p + ".linear", h.mask_inner, h.mask_h, true));
+    VADX_TRY(linear(p + ".project", h.mask_h, h.mask_inner, false));
+    VADX_TRY(m->upload_raw(p + ".conv", (int64_t)h.mask_h * h.mask_lorder, VADX_DT_F32));
+  }
+  VADX_TRY(linear("mask.linear3", 1, h.mask_h, true));
+  return VADX_OK;
+}
+
+int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, void* const* /*state*/, int64_t S, int64_t L,
+              void* ws_ptr, size_t ws_bytes, size_t* need, cudaStream_t st) {
+  DfsmnHP h;
+  VADX_TRY(dfsmn_hp(m, &h));
+  VADX_REQUIRE((L - 1) % h.hop_b == 0, "dfsmn_aec: chunk length %lld must be 1 + a multiple of %d", (long long)L, h.hop_b);
+  const int c = h.c, F = h.F(), cb = h.cb(), Tb = h.Tb(L), T = h.T(L);
+  VADX_REQUIRE(Tb <= h.max_frames, "dfsmn_aec: %d STFT frames exceed max_frames = %d", Tb, h.max_frames);
+  const int64_t B = S * Tb, R = B * F;
+  const int half = h.n_fft_b / 2;
+  const int64_t Lpb = round_up((int64_t)half + L + half + h.n_fft_b, 4);
+  const int pad_a = h.n_fft_a / 2 - h.first_a;
+  const int taps_a = std::min(h.win_a, h.n_fft_a);
+  const int64_t Lpa = round_up((int64_t)pad_a + L + taps_a + h.hop_a, 4);
+  const int nb_a = h.n_fft_a / 2 + 1;
+  const int ldp_a = (nb_a + 1) / 2 * 2;
+  const int64_t rows = S * T;
+  const int Hm = h.mask_h;
+
+  Workspace ws(ws_ptr, ws_bytes, dry);
+  size_t peak = 0;
+  auto take = [&](int64_t n) {
+    float* p = ws.take<float>(n);
+    peak = std::max(peak, ws.off);
+    return p;
+  };
+  // ---- buffers that live across the echo estimator
+  float* aec = take(S * L);
+  float* ri_near = take(B * 2 * F);
+  float* ri_far = h.near_only ? nullptr : take(B * 2 * F);
+  float* x4_own = take(R * 4);
+  float* e[6];
+  for (auto& p : e) p = take(R * c);
+  float* dcur = take(R * c);
+  float* dnext = take(R * c);
+  const size_t mark_top = ws.off;
+
+  const bool real = !dry;
+  if (real && ws.off > ws_bytes) {   // cheap early test; the full requirement is checked by the dry pass below
+    set_error("dfsmn_aec: workspace of %zu bytes is too small", ws_bytes);
+    return VADX_ENOMEM;
+  }
+  if (real) {
+    size_t want = 0;
+    VADX_TRY(dfsmn_run(m, true, nullptr, nullptr, nullptr, S, L, nullptr, 0, &want, nullptr));
+    if (want > ws_bytes) {
+      set_error("dfsmn_aec: workspace of %zu bytes is smaller than the %zu needed", ws_bytes, want);
+      return VADX_ENOMEM;
+    }
+    VADX_REQUIRE(in[0] && (h.near_only || in[1]) && out[0], "dfsmn_aec: near (and far) input and the probability output are required");
+  }
+  const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
+  void* s_ = (void*)st;
+
+  // ---- kernel wrappers (no-ops in the dry pass, which only measures)
+  auto lin = [&](const std::string& n, const float* x, int64_t ldx, int64_t n_rows, float* y, int64_t ldy, int act,
+                 const float* res = nullptr, int64_t ldr = 0) -> int {
+    if (!real) return VADX_OK;
+    const HostTensor* w = m->find(n + ".weight");
+    VADX_REQUIRE(w && w->dims.size() == 2, "dfsmn_aec: weight '%s.weight' missing", n.c_str());
+    const int n_out = (int)w->dims[0], n_in = (int)w->dims[1];
+    const float* bias = m->d<float>(n + ".bias");
+    const uint8_t* img = (use_tc && n_out > 8 && n.compare(0, 5, "mask.") == 0) ? m->d<uint8_t>(n + ".weight#TC") : nullptr;
+    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, s_);
+    return vadx_linear_f32(x, ldx, m->d<float>(n + ".weight#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, n_rows, n_in,
+                           n_out, act, s_);
+  };
+  auto layernorm = [&](const float* x, int64_t n_rows, int D, const std::string& n, float* y) -> int {
+    if (!real) return VADX_OK;
+    return vadx_layernorm_f32(x, n_rows, D, m->d<float>(n + ".w"), m->d<float>(n + ".b"), 1e-6f, y, s_);
+  };
+  auto perm = [&](const float* x, float* y, int64_t n0, int64_t n1, int64_t n2, int64_t n3, int p0, int p1, int p2, int p3) -> int {
+    if (!real) return VADX_OK;
+    return vadx_permute4_f32(x, y, n0, n1, n2, n3, p0, p1, p2, p3, s_);
+  };
+  auto ew = [&](int op, const float* a, int64_t lda, const float* b, int64_t ldb, float* o, int64_t ldo, float* o2, int64_t ldo2,
+                int64_t n_rows, int n_cols, float scalar = 0.f) -> int {
+    if (!real) return VADX_OK;
+    return vadx_ew2_f32(op, a, lda, b, ldb, o, ldo, o2, ldo2, n_rows, n_cols, scalar, s_);
+  };
+  auto lstm = [&](const std::string& n, int layer, bool rev_w, const float* x, int64_t xo, int64_t xi, int64_t xs, float* y,
+                  int64_t yo, int64_t yi, int64_t ys, int64_t n_seq, int n_inner, int len, int n_in, int H, int reverse) -> int {
+    if (!real) return VADX_OK;
+    const std::string suf = "_l" + std::to_string(layer) + (rev_w ? "_reverse" : "");
+    return vadx_lstm_seq_f32(x, xo, xi, xs, y, yo, yi, ys, m->d<float>(n + ".weight_ih" + suf), m->d<float>(n + ".weight_hh" + suf),
+                             m->d<float>(n + ".bias_ih" + suf), m->d<float>(n + ".bias_hh" + suf), n_seq, n_inner, len, n_in, H,
+                             reverse, s_);
+  };
+  // bi-LSTM over `len` consecutive rows of n_in features per sequence -> [n_seq*len][2H]
+  auto bilstm_rows = [&](const std::string& n, const float* x, int64_t n_seq, int len, int n_in, int H, float* y) -> int {
+    VADX_TRY(lstm(n, 0, false, x, (int64_t)len * n_in, 0, n_in, y, (int64_t)len * 2 * H, 0, 2 * H, n_seq, 1, len, n_in, H, 0));
+    return lstm(n, 0, true, x, (int64_t)len * n_in, 0, n_in, y + H, (int64_t)len * 2 * H, 0, 2 * H, n_seq, 1, len, n_in, H, 1);
+  };
+  auto cat = [&](const float* a, int ca, const float* b, int cb_, float* o) -> int {
+    VADX_TRY(ew(3, a, ca, nullptr, 0, o, ca + cb_, nullptr, 0, R, ca));
+    return ew(3, b, cb_, nullptr, 0, o + ca, ca + cb_, nullptr, 0, R, cb_);
+  };
+  // one gated conv block with its cepstral unit (Export_DFSMN_VAD.py:133-207): x [R][cin] -> y [R][c]
+  auto cfb = [&](const float* x, int cin, const std::string& n, float* y) -> int {
+    const size_t mk = ws.off;
+    float* ln0 = take(R * cin);
+    float* g = take(R * c);
+    float* xi = take(R * c);
+    float* d = take(R * c);
+    float* gx = take(R * c);
+    float* col = take(R * 3 * c);
+    float* y1 = take(R * c);
+    float* spec = take(B * c * 2 * cb);
+    float* P = take(B * cb * 2 * c);
+    float* Pn = take(B * cb * 2 * c);
+    float* hseq = take(B * cb * 2 * c);
+    VADX_TRY(layernorm(x, B, F * cin, n + ".LN0", ln0));
+    VADX_TRY(lin(n + ".gate", ln0, cin, R, g, c, VADX_ACT_SIGMOID));
+    VADX_TRY(lin(n + ".input", x, cin, R, xi, c, VADX_ACT_NONE));
+    VADX_TRY(ew(4, g, c, xi, c, gx, c, d, c, R, c));                         // gx = g * xi, d = xi - gx
+    float* ln1 = ln0;                                                        // LN0's output is dead: reuse ([R][cin] >= [R][c])
+    VADX_TRY(layernorm(gx, B, F * c, n + ".LN1", ln1));
+    if (real) VADX_TRY(vadx_im2col_f3_f32(ln1, col, B, F, c, s_));
+    VADX_TRY(lin(n + ".conv", col, 3 * c, R, y1, c, VADX_ACT_NONE));
+    // cepstral unit on LN2(xi - gx): DFT over the bins per channel, bi-LSTM along the cepstral bins, complex gain, IDFT
+    float* ln2 = g;                                                          // g and xi are dead from here on
+    float* z = xi;
+    VADX_TRY(layernorm(d, B, F * c, n + ".LN2", ln2));
+    VADX_TRY(perm(ln2, z, B, F, c, 1, 0, 2, 1, 3));                          // [B][c][F]
+    VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));     // [B*c][re(cb) | im(cb)]
+    VADX_TRY(perm(spec, P, B, c, 2, cb, 0, 3, 2, 1));                        // [B][cb][2][c]
+    VADX_TRY(layernorm(P, B, cb * 2 * c, n + ".cLN", Pn));
+    VADX_TRY(bilstm_rows(n + ".clstm", Pn, B, cb, 2 * c, c, hseq));          // [B*cb][2c]
+    float* Q = Pn;                                                           // in place is not allowed by the kernels: Pn -> spec
+    Q = spec;
+    VADX_TRY(lin(n + ".clstm.linear", hseq, 2 * c, B * cb, Q, 2 * c, VADX_ACT_NONE));
+    float* O = Pn;
+    if (real) VADX_TRY(vadx_ceps_cmul_f32(Q, P, O, B * cb, c, s_));
+    float* Ot = hseq;
+    VADX_TRY(perm(O, Ot, B, cb, 2, c, 0, 3, 2, 1));                          // [B][c][2][cb]
+    float* inv = gx;                                                         // [B*c][F] = R*c floats
+    VADX_TRY(lin("ceps.idft", Ot, 2 * cb, B * c, inv, F, VADX_ACT_NONE));
+    float* ceps = d;
+    VADX_TRY(perm(inv, ceps, B, c, F, 1, 0, 2, 1, 3));                       // [B][F][c]
+    VADX_TRY(ew(0, y1, c, ceps, c, y, c, nullptr, 0, R, c));
+    ws.off = mk;
+    return VADX_OK;
+  };
+
+  // ------------------------------------------------------------------ echo estimator
+  {
+    float* sig = take(S * Lpb);
+    for (int a = 0; a < (h.near_only ? 1 : 2); ++a) {
+      float* ri = a == 0 ? ri_near : ri_far;
+      if (real) {
+        VADX_TRY(vadx_prep_audio(in[a], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 1, 0, 0.f, half, sig, Lpb, s_));
+        const HostTensor* bb = m->find("basis_b");
+        VADX_TRY(vadx_stft_complex_f32(sig, Lpb, S, Tb, h.hop_b, h.n_fft_b, m->d<float>("basis_b"), (int)bb->dims[1], F, ri,
+                                       2 * F, s_));
+      }
+    }
+    ws.off = mark_top;
+  }
+  const float* x4 = x4_own;
+  if (real) {
+    const float w1f = (float)m->scalar("alpha.w1_far", 0.0), w1m = (float)m->scalar("alpha.w1_mix", 0.0);
+    const float b1 = (float)m->scalar("alpha.b1", 0.0), b2 = (float)m->scalar("alpha.b2", 0.0);
+    if (h.near_only)
+      VADX_TRY(vadx_alpha_x4_const_f32(ri_near, m->d<float>("far.pow"), m->d<float>("far.comp"), h.max_frames, S, Tb, F, h.alpha_k,
+                                       w1f, w1m, b1, m->d<float>("alpha.w2"), b2, x4_own, nullptr, s_));
+    else
+      VADX_TRY(vadx_alpha_x4_f32(ri_near, ri_far, S, Tb, F, h.alpha_k, w1f, w1m, b1, m->d<float>("alpha.w2"), b2, x4_own, nullptr,
+                                 s_));
+    if (in[2]) x4 = static_cast<const float*>(in[2]);
+  }
+  {
+    float* hh = take(R * 2 * c);
+    float* catb = take(R * (c + 4));
+    VADX_TRY(bilstm_rows("in_lstm", x4, B, F, 4, c, hh));                    // [R][2c]
+    VADX_TRY(lin("in_lstm.linear", hh, 2 * c, R, catb, c + 4, VADX_ACT_NONE));
+    VADX_TRY(ew(3, x4, 4, nullptr, 0, catb + c, c + 4, nullptr, 0, R, 4));
+    VADX_TRY(lin("in_conv", catb, c + 4, R, e[0], c, VADX_ACT_NONE));
+    ws.off = mark_top;
+  }
+  for (int i = 1; i <= 5; ++i) VADX_TRY(cfb(e[i - 1], c, "cfb_e" + std::to_string(i), e[i]));
+  {
+    // 2-layer time LSTM over the frames of every (stream, bin), then the bottleneck product
+    const int H = 2 * c;
+    float* lnb = take(R * c);
+    float* y1 = take(R * H);
+    float* y2 = take(R * H);
+    float* lo = take(R * c);
+    float* prod = take(R * c);
+    VADX_TRY(layernorm(e[5], B, F * c, "ln", lnb));
+    VADX_TRY(lstm("mid_lstm", 0, false, lnb, (int64_t)Tb * F * c, c, (int64_t)F * c, y1, (int64_t)Tb * F * H, H, (int64_t)F * H,
+                  S * F, F, Tb, c, H, 0));
+    VADX_TRY(lstm("mid_lstm", 1, false, y1, (int64_t)Tb * F * H, H, (int64_t)F * H, y2, (int64_t)Tb * F * H, H, (int64_t)F * H,
+                  S * F, F, Tb, H, H, 0));
+    VADX_TRY(lin("mid_lstm.linear", y2, H, R, lo, c, VADX_ACT_NONE));
+    VADX_TRY(ew(1, e[5], c, lo, c, prod, c, nullptr, 0, R, c));
+    VADX_TRY(cfb(prod, c, "cfb_d5", dcur));
+    ws.off = mark_top;
+  }
+  for (int i = 4; i >= 1; --i) {
+    float* cc = take(R * 2 * c);
+    VADX_TRY(cat(e[i], c, dcur, c, cc));
+    VADX_TRY(cfb(cc, 2 * c, "cfb_d" + std::to_string(i), dnext));
+    std::swap(dcur, dnext);
+    ws.off = mark_top;
+  }
+  {
+    float* cat2 = take(R * 2 * c);
+    float* y3 = take(R * c);
+    float* d0 = take(R * 2 * c);
+    float* cat3 = take(R * 3 * c);
+    float* o2 = take(R * 2);
+    float* Y = take(B * 2 * F);
+    float* frames = take(B * h.n_fft_b);
+    VADX_TRY(cat(e[0], c, dcur, c, cat2));
+    VADX_TRY(lstm("out_lstm", 0, false, cat2, (int64_t)Tb * F * 2 * c, 2 * c, (int64_t)F * 2 * c, y3, (int64_t)Tb * F * c, c,
+                  (int64_t)F * c, S * F, F, Tb, 2 * c, c, 0));
+    VADX_TRY(lin("out_lstm.linear", y3, c, R, d0, 2 * c, VADX_ACT_NONE));
+    VADX_TRY(ew(3, d0, 2 * c, nullptr, 0, cat3, 3 * c, nullptr, 0, R, 2 * c));
+    VADX_TRY(ew(3, dcur, c, nullptr, 0, cat3 + 2 * c, 3 * c, nullptr, 0, R, c));
+    VADX_TRY(lin("out_conv", cat3, 3 * c, R, o2, 2, VADX_ACT_NONE));         // [R][re, im]
+    VADX_TRY(perm(o2, Y, B, F, 2, 1, 0, 2, 1, 3));                           // [B][2][F]
+    VADX_TRY(lin("istft", Y, 2 * F, B, frames, h.n_fft_b, VADX_ACT_NONE));   // [B][n_fft_b]
+    if (real)
+      VADX_TRY(vadx_istft_ola_f32(frames, h.n_fft_b, S, Tb, h.n_fft_b, h.hop_b, m->d<float>("wsum_inv"), (int)L, aec, L, s_));
+    if (real && out[1])
+      VADX_TRY(vadx_ew2_f32(3, aec, L, nullptr, 0, static_cast<float*>(out[1]), L, nullptr, 0, S, (int)L, 0.f, s_));
+    ws.off = mark_top;
+  }
+  // ------------------------------------------------------------------ features + mask-net
+  {
+    float* near_sig = take(S * Lpa);
+    float* aec_sig = take(S * Lpa);
+    float* echo_sig = take(S * Lpa);
+    float* feat = take(rows * 3 * h.n_mels);
+    float* power = take(rows * ldp_a);
+    float* hA = take(rows * Hm);
+    float* hB = take(rows * Hm);
+    float* zb = take(rows * h.mask_inner);
+    float* pb = take(rows * Hm);
+    if (real) {
+      const float pre = (float)m->scalar("pre_emphasis", 0.97);
+      VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f / 32768.0f, 1, VADX_PREEMPH_KEEP_FIRST, pre, pad_a, near_sig, Lpa,
+                               s_));
+      VADX_TRY(vadx_prep_audio(aec, VADX_DT_F32, S, L, L, 1.0f, 0, VADX_PREEMPH_KEEP_FIRST, pre, pad_a, aec_sig, Lpa, s_));
+      VADX_TRY(vadx_ew2_f32(2, near_sig, Lpa, aec_sig, Lpa, echo_sig, Lpa, nullptr, 0, S, (int)Lpa,
+                            (float)m->scalar("echo_factor", 1.15), s_));
+      const HostTensor* ba = m->find("basis_a");
+      const int mel_max = (int)(m->find("mel_w")->numel() / h.n_mels);
+      const float* sigs[3] = {near_sig, aec_sig, echo_sig};
+      for (int j = 0; j < 3; ++j) {
+        VADX_TRY(vadx_stft_power_f32(sigs[j], Lpa, S, T, h.hop_a, taps_a, m->d<float>("basis_a"), (int)ba->dims[1], nb_a, power,
+                                     ldp_a, s_));
+        VADX_TRY(vadx_mel_log_f32(power, ldp_a, rows, nb_a, h.n_mels, m->d<int32_t>("mel_start"), m->d<int32_t>("mel_len"),
+                                  m->d<float>("mel_w"), mel_max, VADX_FLOOR_CLAMP, (float)m->scalar("log_floor", 1e-6),
+                                  feat + j * h.n_mels, 3 * h.n_mels, s_));
+      }
+    }
+    VADX_TRY(lin("mask.linear1", feat, 3 * h.n_mels, rows, hA, Hm, VADX_ACT_RELU));
+    float* hcur = hA;
+    float* hnext = hB;
+    for (int i = 0; i < h.mask_layers; ++i) {
+      const std::string p = "mask." + std::to_string(i);
+      VADX_TRY(lin(p + ".linear", hcur, Hm, rows, zb, h.mask_inner, VADX_ACT_RELU));
+      VADX_TRY(lin(p + ".project", zb, h.mask_inner, rows, pb, Hm, VADX_ACT_NONE));
+      if (real)
+        VADX_TRY(vadx_fsmn_memory_f32(pb, Hm, m->d<float>(p + ".conv"), h.mask_lorder, 1, nullptr, 0, 1, hcur, Hm, hnext, Hm, S, T,
+                                      Hm, nullptr, nullptr, s_));
+      std::swap(hcur, hnext);
+    }
+    VADX_TRY(lin("mask.linear3", hcur, Hm, rows, real ? static_cast<float*>(out[0]) : nullptr, 1, VADX_ACT_SIGMOID));
+    ws.off = mark_top;
+  }
+  if (need) *need = peak;
+  return VADX_OK;
+}

@@ -90,8 +90,8 @@ class _Engine:
         ws = self.workspace(need, dev, stream)
         if self._torch.cuda.is_current_stream_capturing() and not any(ws is k for k in self._captured_ws):
             self._captured_ws.append(ws)   # a CUDA graph now holds this address: never free it (growth allocates anew)
-        ins = (C.c_void_p * len(inputs))(*[t.data_ptr() for t in inputs])
-        outs = (C.c_void_p * len(outputs))(*[t.data_ptr() for t in outputs])
+        ins = (C.c_void_p * len(inputs))(*[None if t is None else t.data_ptr() for t in inputs])      # None = optional input absent
+        outs = (C.c_void_p * len(outputs))(*[None if t is None else t.data_ptr() for t in outputs])
         sts = (C.c_void_p * max(len(states), 1))(*([t.data_ptr() for t in states] or [None]))
         lib.check(self._lib.vadx_forward(self._h, ins, outs, sts, n_streams, n_samples, ws.data_ptr(), need,
                                          lib.stream_ptr(stream)))
