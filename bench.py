@@ -196,13 +196,159 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------- other families
-def family_rtfx(dev, world, dist):
-    """Short device-resident RTFx runs of the other model families (BASELINE configs 0-2), same timing
-    rules (3 warm-ups, CUDA events, max over ranks).  Reported next to the headline, not as it."""
+def ncu_family_traffic(family, kernel):
+    """DRAM bytes per launch of `kernel` from the committed per-family ncu capture (profiles/r02_top_kernels_<family>.txt)."""
+    import re
+    p = os.path.join(ROOT, "profiles", f"r02_top_kernels_{family}.txt")
+    if not os.path.exists(p):
+        return None
+    vals = []
+    base = kernel.split("(")[0].split("+")[0]
+    for line in open(p):
+        if base in line.split(";")[0]:
+            rd = re.search(r"dram__bytes_read\.sum=([0-9.]+) (\w+)", line)
+            wr = re.search(r"dram__bytes_write\.sum=([0-9.]+) (\w+)", line)
+            if rd and wr:
+                mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                vals.append(float(rd.group(1)) * mul[rd.group(2)] + float(wr.group(1)) * mul[wr.group(2)])
+    return sum(vals) / len(vals) if vals else None
+
+
+def kernel_roofline(family, kernels, pk):
+    """roofline block of one family from the library's per-kernel records (lib.profile_collect_kernels): every entry point
+    reports its kernel's name and the ALGORITHMIC bytes / flops of each call (include/vadx.h, vadx_kernel_stat), timed by
+    CUDA-event pairs on the launching stream.  The dominant kernel (largest share of the step) is the headline; the rest
+    is listed by share."""
+    kernels = {k: v for k, v in kernels.items() if v["calls"] and v["ms"] > 0}
+    if not kernels:
+        return None
+    total = sum(v["ms"] for v in kernels.values())
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    d = kernels[dom]
+    gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    # tcgen05 kernels run the fp32 contraction as 3 (dense layers) or 4 (DFT) bf16/fp16 products
+    products = 4 if "stft_power_tc" in dom else (3 if "_tc_" in dom or "fc2_memory" in dom else 0)
+    frac_hbm = gbs / pk["hbm_gbs"]
+    frac_tensor = tf * products / pk["bf16_tflops_sustained"] if products else 0.0
+    tensor_bound = frac_tensor > frac_hbm
+    roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": dom,
+            "achieved": tf * products if tensor_bound else gbs,
+            "peak": pk["bf16_tflops_sustained"] if tensor_bound else pk["hbm_gbs"],
+            "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": frac_tensor if tensor_bound else frac_hbm,
+            "traffic": ncu_family_traffic(family, dom), "launches_timed": d["calls"], "avg_launch_ms": d["ms"] / d["calls"],
+            "algorithmic_bytes_per_launch": d["bytes"] / d["calls"], "algorithmic_flops_per_launch": d["flops"] / d["calls"],
+            "share_of_step": d["ms"] / total, "hbm_gbs": gbs, "fp32_equiv_tflops": tf,
+            "peak_source": pk["source"] + " (MEASURED_PEAKS.json: hbm_gbs copy; bf16_tflops_sustained for tensor-bound kernels)"}
+    if roof["traffic"] is not None:
+        roof["traffic_source"] = f"profiles/r02_top_kernels_{family}.txt (ncu --set full, dram bytes read + written per launch)"
+    roof["kernels_by_share"] = [
+        {"kernel": k, "share": round(v["ms"] / total, 4), "launches": v["calls"], "avg_launch_ms": round(v["ms"] / v["calls"], 5),
+         "hbm_gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1), "frac_hbm": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+         "fp32_equiv_tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)}
+        for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])[:8]]
+    return roof
+
+
+def family_workloads(dev, only=None):
+    """The bench workloads of the other model families (BASELINE configs 0, 1, 2, 4 and the streaming FireRed twin) at the
+    SURVEY section 8(d) shapes: name -> dict(step=callable timed as one step, eager=callable with the same kernels launched
+    eagerly (for the per-kernel records; None = same as step), audio_s=audio seconds per step per GPU, config=str,
+    steps/warm).  Generator: each workload is built when reached and dropped before the next."""
     import numpy as np
     import torch
     import vadx
     from vadx import fsmn_vad, marblenet_vad, postprocess as PP, silero_vad, synth, weights as W
+
+    def want(n):
+        return only is None or n in only
+
+    if want("fsmn"):
+        # FSMN (config 0 shape, batched): S streams x 4 overlapping 16000-sample windows, state carried on device
+        cfg = W.FsmnConfig()
+        sess = vadx.FsmnSession(W.fsmn_random_init(cfg, 0), cfg, chunk_len=16000)
+        S, stride = 1024, 16000 - 31 * 160
+        n = 16000 + 3 * stride
+        a = torch.from_numpy(synth.synth_chunks_fast(S, n, seed=11)).to(dev)
+        yield "fsmn", dict(step=lambda: fsmn_vad.run_streams(sess, a, stride), eager=None, audio_s=S * n / 16000, steps=3, warm=3,
+                           config=f"{S} streams/GPU x 4 windows of 16000 samples (stride {stride}), caches + hysteresis on device")
+        del sess, a
+    if want("marblenet"):
+        # MarbleNet (config 2): 60 s clips, the survey's 256 clips per GPU
+        cfg = W.MarbleNetConfig()
+        sess = vadx.MarbleNetSession(W.marblenet_random_init(cfg, 0), cfg)
+        B = 256
+        clips = torch.from_numpy(synth.synth_chunks_fast(B, 960000, seed=12)).to(dev)
+        yield "marblenet", dict(step=lambda: marblenet_vad.run_vad_clips(sess, clips), eager=None, audio_s=B * 60.0, steps=3, warm=3,
+                                config=f"{B} clips/GPU x 60 s, post-processing on device")
+        del sess, clips
+    if want("silero"):
+        # Silero (config 1): 4096 streams, 32 ms windows with LSTM state carry
+        cfg = W.SileroConfig()
+        sess = vadx.SileroSession(W.silero_random_init(cfg, 0), cfg)
+        S, n_win = 4096, 32
+        audio = (torch.from_numpy(synth.synth_chunks_fast(S, n_win * 512, seed=13)).to(dev).float() * 0.000030517578)
+        lens = [n_win * 512] * S
+
+        def silero_step():
+            probs = sess.speech_probs(audio)
+            return silero_vad.raw_segments(probs, lens, 0.5, 16000, 250, 20, 250)
+
+        yield "silero", dict(step=silero_step, eager=None, audio_s=S * n_win * 0.032, steps=3, warm=3,
+                             config=f"{S} streams/GPU x {n_win} windows of 512 samples, LSTM state + trigger machine on device")
+        del sess, audio
+    if want("dfsmn_aec"):
+        # DFSMN AEC-VAD (config 4): near + far end, 31841-sample chunks; the survey's 1024 pairs per GPU when the workspace
+        # (about 80 MB per pair) leaves room, else the largest power of two that does
+        from vadx import dfsmn_aec  # noqa: F401
+        cfg = W.DfsmnAecConfig()
+        sess = vadx.DfsmnAecSession(W.dfsmn_aec_random_init(cfg, 0), cfg, chunk_len=31841)
+        free_b, _total = torch.cuda.mem_get_info(dev)
+        S = 1024
+        while S > 32 and sess._e.workspace_bytes(S, 31841) > 0.7 * free_b:
+            S //= 2
+        ws_gb = sess._e.workspace_bytes(S, 31841) / 1e9
+        far = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=14)).to(dev)
+        near = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=15)).to(dev)
+        state = PP.HysteresisState(S, 100, dev)
+        probs = torch.empty((S, sess.T), dtype=torch.float32, device=dev)
+
+        def aec_step():
+            sess.run_batch(near, far, out=probs)
+            state.n_saved.zero_()
+            PP.lookahead_hysteresis(probs, state, 15, 0.5, 0.5, is_final=True)
+
+        yield "dfsmn_aec", dict(step=aec_step, eager=None, audio_s=S * 31841 / 16000, steps=2, warm=2,
+                                config=f"{S} near+far stream pairs/GPU x one 31841-sample chunk ({ws_gb:.1f} GB workspace), one "
+                                       "vadx_forward of the native dfsmn_aec model (echo estimator on fp32 FFMA kernels, mask-net "
+                                       "on tcgen05), hysteresis on device")
+        del sess, near, far
+    if want("firered_stream"):
+        # FireRed Stream-VAD: 4096 streams in lock-step, 160 ms chunks (14 frames) with cache carry + streaming segmenter
+        from vadx import firered_vad
+        cfg = W.FireRedConfig(N2=0, S2=0, streaming=True)
+        sess = vadx.FireRedStreamSession(W.firered_random_init(cfg, 5), cfg)
+        S, n_calls = 4096, 25
+        a = torch.from_numpy(synth.synth_chunks_fast(S, n_calls * 2560, seed=16)).to(dev)
+        lens = [n_calls * 2560] * S
+        yield "firered_stream", dict(step=lambda: firered_vad.run_stream_vad_streams(sess, a, lens, graph=True),
+                                     eager=lambda: firered_vad.run_stream_vad_streams(sess, a, lens, graph=False),
+                                     audio_s=S * n_calls * 0.16, steps=2, warm=2, per_chunk=n_calls,
+                                     config=f"{S} streams/GPU x {n_calls} chunks of 2560 samples, caches + streaming segmenter on device, "
+                                            "one CUDA-graph replay per chunk")
+        del sess, a
+
+
+def family_rtfx(dev, world, dist):
+    """Short device-resident RTFx runs of the other model families (BASELINE configs 0-2, 4), same timing rules (warm-ups,
+    CUDA events, max over ranks), each with its own roofline block from the library's per-kernel records.  Reported next
+    to the headline, not as it."""
+    import numpy as np
+    import torch
+    import vadx
+    from vadx import fsmn_vad, lib, weights as W
+
+    pk = peaks()
 
     def timed(fn, steps=3, warm=3):
         for _ in range(warm):
@@ -220,71 +366,22 @@ def family_rtfx(dev, world, dist):
         return float(ms.item())
 
     out = {}
-    # FSMN (config 0 shape, batched): S streams x 4 overlapping 16000-sample windows, state carried on device
-    cfg = W.FsmnConfig()
-    sess = vadx.FsmnSession(W.fsmn_random_init(cfg, 0), cfg, chunk_len=16000)
-    S, stride = 1024, 16000 - 31 * 160
-    n = 16000 + 3 * stride
-    a = torch.from_numpy(synth.synth_chunks_fast(S, n, seed=11)).to(dev)
-    ms = timed(lambda: fsmn_vad.run_streams(sess, a, stride))
-    out["fsmn"] = {"audio_hours_per_sec": world * S * n / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
-                   "config": f"{S} streams/GPU x 4 windows of 16000 samples (stride {stride}), caches + hysteresis on device"}
-    del sess, a
-    # MarbleNet (config 2): 60 s clips
-    cfg = W.MarbleNetConfig()
-    sess = vadx.MarbleNetSession(W.marblenet_random_init(cfg, 0), cfg)
-    B = 64
-    clips = torch.from_numpy(synth.synth_chunks_fast(B, 960000, seed=12)).to(dev)
-    ms = timed(lambda: marblenet_vad.run_vad_clips(sess, clips))
-    out["marblenet"] = {"audio_hours_per_sec": world * B * 60.0 / (ms / 1e3) / 3600, "ms_per_step": ms,
-                        "config": f"{B} clips/GPU x 60 s, post-processing on device"}
-    del sess, clips
-    # Silero (config 1): 4096 streams, 32 ms windows with LSTM state carry
-    cfg = W.SileroConfig()
-    sess = vadx.SileroSession(W.silero_random_init(cfg, 0), cfg)
-    S, n_win = 4096, 32
-    audio = (torch.from_numpy(synth.synth_chunks_fast(S, n_win * 512, seed=13)).to(dev).float() * 0.000030517578)
-    lens = [n_win * 512] * S
-
-    def silero_step():
-        probs = sess.speech_probs(audio)
-        return silero_vad.raw_segments(probs, lens, 0.5, 16000, 250, 20, 250)
-
-    ms = timed(silero_step)
-    out["silero"] = {"audio_hours_per_sec": world * S * n_win * 0.032 / (ms / 1e3) / 3600, "ms_per_step": ms,
-                     "config": f"{S} streams/GPU x {n_win} windows of 512 samples, LSTM state + trigger machine on device"}
-    del sess, audio
-    # DFSMN AEC-VAD (config 4): near + far end, 31841-sample chunks
-    from vadx import dfsmn_aec
-    cfg = W.DfsmnAecConfig()
-    sess = vadx.DfsmnAecSession(W.dfsmn_aec_random_init(cfg, 0), cfg, chunk_len=31841)
-    S = 32
-    far = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=14)).to(dev)
-    near = torch.from_numpy(synth.synth_chunks_fast(S, 31841, seed=15)).to(dev)
-    state = PP.HysteresisState(S, 100, dev)
-
-    def aec_step():
-        probs = sess.run_batch_graph(near, far)
-        state.n_saved.zero_()
-        PP.lookahead_hysteresis(probs, state, 15, 0.5, 0.5, is_final=True)
-
-    ms = timed(aec_step, steps=2, warm=2)
-    out["dfsmn_aec"] = {"audio_hours_per_sec": world * S * 31841 / 16000 / (ms / 1e3) / 3600, "ms_per_step": ms,
-                        "config": f"{S} near+far stream pairs/GPU x one 31841-sample chunk, echo estimator on fp32 FFMA "
-                                  "kernels, mask-net on tcgen05, whole call replayed as one CUDA graph, hysteresis on device"}
-    del sess, near, far
-    # FireRed Stream-VAD: 4096 streams in lock-step, 160 ms chunks (14 frames) with cache carry + streaming segmenter
-    from vadx import firered_vad
-    cfg = W.FireRedConfig(N2=0, S2=0, streaming=True)
-    sess = vadx.FireRedStreamSession(W.firered_random_init(cfg, 5), cfg)
-    S, n_calls = 4096, 25
-    a = torch.from_numpy(synth.synth_chunks_fast(S, n_calls * 2560, seed=16)).to(dev)
-    lens = [n_calls * 2560] * S
-    ms = timed(lambda: firered_vad.run_stream_vad_streams(sess, a, lens, graph=True), steps=2, warm=2)
-    out["firered_stream"] = {"audio_hours_per_sec": world * S * n_calls * 0.16 / (ms / 1e3) / 3600, "ms_per_step": ms,
-                             "ms_per_160ms_chunk": ms / n_calls,
-                             "config": f"{S} streams/GPU x {n_calls} chunks of 2560 samples, caches + streaming segmenter on device, one CUDA-graph replay per chunk"}
-    del sess, a
+    for name, w in family_workloads(dev):
+        ms = timed(w["step"], w["steps"], w["warm"])
+        r = {"audio_hours_per_sec": world * w["audio_s"] / (ms / 1e3) / 3600, "ms_per_step": ms, "config": w["config"]}
+        if "per_chunk" in w:
+            r["ms_per_160ms_chunk"] = ms / w["per_chunk"]
+        # per-kernel records: a separate, untimed pass with the library's event pairs around every entry point
+        lib.profile_enable(True)
+        lib.profile_collect_kernels()
+        (w["eager"] or w["step"])()
+        torch.cuda.synchronize()
+        kernels = lib.profile_collect_kernels()
+        lib.profile_enable(False)
+        lib.profile_collect()
+        r["roofline"] = kernel_roofline(name, kernels, pk)
+        out[name] = r
+        torch.cuda.empty_cache()
     for v in out.values():
         v["rtfx"] = v["audio_hours_per_sec"] * 3600
     # BASELINE configs[0] as the reference runs it: ONE stream, 512-sample chunks, batch 1 (latency-bound; the
@@ -393,10 +490,12 @@ def run_vadx(args):
         step_device()
     torch.cuda.synchronize()
     lib.profile_collect()                                     # drop warm-up records
+    lib.profile_collect_kernels()
     launches0 = L.vadx_launch_count()
     ms_total = timed(step_device, args.steps, 0)
     launches = L.vadx_launch_count() - launches0
     stages = lib.profile_collect()
+    kernel_records = lib.profile_collect_kernels()
     lib.profile_enable(False)
     # ---- end to end through the public API with host buffers
     ms_e2e = timed(step_e2e, args.steps, W_)
@@ -471,6 +570,9 @@ def run_vadx(args):
                                   "hbm_gbs": (stage_bytes[k] * args.steps / (stages[k][0] * 1e-3) / 1e9) if stages[k][0] > 0 else None,
                                   "frac": (stage_bytes[k] * args.steps / (stages[k][0] * 1e-3) / 1e9 / pk["hbm_gbs"]) if stages[k][0] > 0 else None}
                               for k in stages}
+        kr = kernel_roofline("firered", kernel_records, pk)
+        if kr:
+            roof["kernels_by_share"] = kr["kernels_by_share"]      # the same step through the library's per-kernel records
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = cpu_reference_leg(args.cpu_seconds)

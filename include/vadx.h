@@ -80,6 +80,18 @@ enum {
 };
 int vadx_profile_enable(int on);
 int vadx_profile_collect(double* ms, uint64_t* calls, int n_stages);
+/* The same records per KERNEL: every entry point also reports the name of the kernel it launches and the algorithmic
+ * bytes (tensors read + written once) and flops (2 x MACs) of the call, so a caller gets achieved GB/s and FLOP/s per
+ * kernel without re-deriving shapes.  Fills out[0 .. *n_out) and clears the totals; when capacity is too small only
+ * *n_out is set (nothing is cleared).  Names are static strings owned by the library. */
+typedef struct vadx_kernel_stat {
+  const char* name;
+  double ms;
+  uint64_t calls;
+  double bytes;
+  double flops;
+} vadx_kernel_stat;
+int vadx_profile_collect_kernels(vadx_kernel_stat* out, int capacity, int* n_out);
 
 /* ------------------------------------------------------------------------------------------
  * Per-kernel entry points (also what the unit parity tests and ncu captures call).

@@ -344,7 +344,10 @@ static int parts_env() {
 int fc2_memory_stages_f32(const void* d_himg, int n_in, const void* d_wimg, const float* d_bias, int act, const float* d_wl,
                           int n_back, const float* d_wr, int n_ahead, const float* d_res, float* d_out, int64_t n_streams,
                           int n_frames, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  // h stages (two bf16 terms = 4 B per value) + residual rows in, out rows
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "fc2_memory_stages_kernel",
+                    4.0 * n_streams * n_frames * (n_in + kBsC * (d_res ? 2 : 1)),
+                    2.0 * n_streams * n_frames * kBsC * (double)(n_in + n_back + n_ahead));
   VADX_REQUIRE(d_himg && d_wimg && d_wl && d_out, "fc2_memory_stages_f32: null pointer");
   VADX_REQUIRE(fc2_memory_stages_supported(n_in, kBsC, n_frames, n_back, 1, n_ahead, 1), "fc2_memory_stages_f32: shape not supported");
   VADX_REQUIRE(act == VADX_ACT_NONE || act == VADX_ACT_RELU, "fc2_memory_stages_f32: activation %d", act);

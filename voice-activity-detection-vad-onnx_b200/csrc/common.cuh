@@ -72,12 +72,14 @@ inline int ab_env(const char* name, int dflt) {
 inline int ab_env(const char*, int dflt) { return dflt; }
 #endif
 
-// per-stage event timing (api.cu); a no-op unless vadx_profile_enable(1) was called
+// per-stage / per-kernel event timing (api.cu); a no-op unless vadx_profile_enable(1) was called.  `kernel` names the
+// entry point's kernel, `bytes` / `flops` are the ALGORITHMIC work of this call (the tensors it must read and write once,
+// 2 x MACs of the contraction it computes) -- what bench.py divides by the measured time for the roofline lines.
 struct StageTimer {
   int stage;
   cudaStream_t st;
   int slot;
-  StageTimer(int stage_, cudaStream_t st_);
+  StageTimer(int stage_, cudaStream_t st_, const char* kernel = nullptr, double bytes = 0.0, double flops = 0.0);
   ~StageTimer();
 };
 

@@ -312,7 +312,7 @@ using namespace vadx;
 extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_streams, int64_t n_samples,
                                int64_t in_stride, float scale, int remove_dc, int preemph_mode, float preemph,
                                int64_t pad_left, float* d_out, int64_t out_stride, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "prep_audio_kernel", n_streams * (double)n_samples * (in_dtype == VADX_DT_I16 ? 2.0 : 4.0) + 4.0 * n_streams * out_stride);
   VADX_REQUIRE(d_audio && d_out, "vadx_prep_audio: null pointer");
   VADX_REQUIRE(in_dtype == VADX_DT_I16 || in_dtype == VADX_DT_F32, "vadx_prep_audio: dtype %d", in_dtype);
   VADX_REQUIRE(n_streams >= 0 && n_samples > 0 && in_stride >= n_samples && pad_left >= 0 &&
@@ -338,7 +338,7 @@ extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_stre
 extern "C" int vadx_mel_log_f32(const float* d_power, int64_t ld_power, int64_t n_rows, int n_bins, int n_mels,
                                 const int32_t* d_start, const int32_t* d_len, const float* d_w, int max_len,
                                 int floor_mode, float floor_value, float* d_out, int64_t ld_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "mel_log_kernel", 4.0 * n_rows * (n_bins + n_mels), 2.0 * n_rows * n_mels * (double)max_len);
   VADX_REQUIRE(d_power && d_start && d_len && d_w && d_out, "vadx_mel_log_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_bins > 0 && n_mels > 0 && max_len > 0 && ld_power >= n_bins && ld_out >= n_mels,
                "vadx_mel_log_f32: bad shape");
@@ -365,7 +365,9 @@ extern "C" int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* 
                                     const float* d_wr, int n_ahead, int stride_ahead, const float* d_residual,
                                     int64_t ldr, float* d_out, int64_t ldo, int64_t n_streams, int n_frames,
                                     int n_channels, const float* d_cache_in, float* d_cache_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "fsmn_memory_kernel",
+                    4.0 * n_streams * n_frames * n_channels * (2 + (d_residual ? 1 : 0)),      // p (+ residual) in, out
+                    2.0 * n_streams * n_frames * n_channels * (double)(n_back + n_ahead));
   VADX_REQUIRE(d_p && d_wl && d_out, "vadx_fsmn_memory_f32: null pointer");
   VADX_REQUIRE(n_back >= 1 && stride_back >= 1 && n_ahead >= 0 && (n_ahead == 0 || (d_wr && stride_ahead >= 1)),
                "vadx_fsmn_memory_f32: bad taps back=%d/%d ahead=%d/%d", n_back, stride_back, n_ahead, stride_ahead);
@@ -463,7 +465,8 @@ __global__ void __launch_bounds__(256) depthwise_conv1d_kernel(const float* __re
 extern "C" int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const float* d_w, int kernel, int stride,
                                          int dilation, int pad, float* d_y, int64_t ldy, int64_t n_streams, int t_in,
                                          int t_out, int n_channels, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "depthwise_conv1d_kernel",
+                    4.0 * n_streams * n_channels * ((double)t_in + t_out), 2.0 * n_streams * t_out * n_channels * (double)kernel);
   VADX_REQUIRE(d_x && d_w && d_y && d_x != d_y, "vadx_depthwise_conv1d_f32: null or aliased pointer");
   VADX_REQUIRE(kernel >= 1 && stride >= 1 && dilation >= 1 && pad >= 0 && n_streams >= 0 && t_in >= 1 && t_out >= 1 &&
                    n_channels >= 1 && ldx >= n_channels && ldy >= n_channels,

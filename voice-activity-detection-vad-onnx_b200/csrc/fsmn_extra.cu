@@ -202,7 +202,7 @@ static inline unsigned grid_for(int64_t items, int per_block, int cap = 148 * 16
 extern "C" int vadx_lfr_cmvn_f32(const float* d_mel, int64_t ld_mel, const float* d_mean, const float* d_var,
                                  float* d_out, int64_t ld_out, int64_t n_streams, int n_frames, int n_mels, int lfr_m,
                                  int lfr_n, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "lfr_cmvn_kernel", 4.0 * n_streams * n_frames * n_mels * (1.0 + lfr_m));
   VADX_REQUIRE(d_mel && d_mean && d_var && d_out, "vadx_lfr_cmvn_f32: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames >= 1 && n_mels >= 1 && lfr_m >= 1 && lfr_n == 1 && ld_mel >= n_mels &&
                    ld_out >= n_mels * lfr_m,
@@ -215,7 +215,7 @@ extern "C" int vadx_lfr_cmvn_f32(const float* d_mel, int64_t ld_mel, const float
 
 extern "C" int vadx_softmax_class0_f32(const float* d_logits, int64_t ld, int64_t n_rows, int n_classes, float* d_p0,
                                        void* stream) {
-  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream, "softmax_class0_kernel", 4.0 * n_rows * (n_classes + 1.0));
   VADX_REQUIRE(d_logits && d_p0 && n_rows >= 0 && n_classes >= 1 && ld >= n_classes, "vadx_softmax_class0_f32: bad argument");
   if (n_rows == 0) return VADX_OK;
   softmax_class0_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(d_logits, ld, n_rows, n_classes, d_p0);
@@ -225,7 +225,7 @@ extern "C" int vadx_softmax_class0_f32(const float* d_logits, int64_t ld, int64_
 extern "C" int vadx_frame_energy_log10_f32(const float* d_sig, int64_t sig_stride, int64_t offset, int64_t n_streams,
                                            int win, int hop, int n_energy, int n_frames, float scale, float eps,
                                            float* d_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream, "frame_energy_log10_kernel");
   VADX_REQUIRE(d_sig && d_out, "vadx_frame_energy_log10_f32: null pointer");
   VADX_REQUIRE(n_streams >= 0 && win >= 1 && hop >= 1 && n_energy >= 1 && n_frames >= n_energy && offset >= 0 &&
                    sig_stride >= offset + (int64_t)(n_energy - 1) * hop + win,
@@ -239,7 +239,7 @@ extern "C" int vadx_frame_energy_log10_f32(const float* d_sig, int64_t sig_strid
 extern "C" int vadx_fsmn_gate(const float* d_p_sil, const float* d_power_dB, const float* d_noise_avg,
                               float one_minus_speech_threshold, float speech_2_noise_ratio, int64_t n_streams,
                               int n_frames, uint8_t* d_score, float* d_noisy_dB, void* stream) {
-  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream, "fsmn_gate_kernel", 9.0 * n_streams * n_frames);
   VADX_REQUIRE(d_p_sil && d_power_dB && d_noise_avg && d_score && d_noisy_dB, "vadx_fsmn_gate: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames >= 1, "vadx_fsmn_gate: bad shape");
   if (n_streams == 0) return VADX_OK;
@@ -255,7 +255,7 @@ extern "C" int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_
                                          uint8_t* d_silence_state, int32_t* d_n_saved, uint8_t* d_saved,
                                          int64_t ld_saved, float* d_noise_avg, const float* d_noisy_dB,
                                          float snr_threshold, void* stream) {
-  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "lookahead_hysteresis_kernel");
   VADX_REQUIRE(d_in && d_silence_state && d_n_saved && d_saved, "vadx_lookahead_hysteresis: null pointer");
   VADX_REQUIRE((mode == 0 || mode == 1) && n_streams >= 0 && n_frames >= 1 && look_backward >= 0 &&
                    look_backward <= n_frames && ld_in >= n_frames && ld_saved >= 0,
@@ -270,7 +270,7 @@ extern "C" int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_
 extern "C" int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags,
                                      int64_t n_streams, int32_t* d_seg_count, int32_t* d_segments, int max_segments,
                                      void* stream) {
-  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "runs_to_segments_kernel");
   VADX_REQUIRE(d_silence_flags && d_n_flags && d_seg_count && d_segments && max_segments >= 1 && ld >= 0,
                "vadx_runs_to_segments: bad argument");
   if (n_streams == 0) return VADX_OK;

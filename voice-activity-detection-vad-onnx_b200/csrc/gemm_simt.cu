@@ -393,7 +393,7 @@ static int launch_gemm(const GemmArgs& g, int n_cols, cudaStream_t st, const cha
 int linear_narrow(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias, float* d_y,
                   int64_t n_rows, int n_in, int n_out, int act, int rows_per_group, int64_t group_stride,
                   int64_t out_stride, cudaStream_t st) {
-  StageTimer _timer(VADX_STAGE_HEAD, st);
+  StageTimer _timer(VADX_STAGE_HEAD, st, "linear_narrow_kernel", 4.0 * n_rows * (n_in + n_out), 2.0 * n_rows * n_in * n_out);
   VADX_REQUIRE(n_out >= 1 && n_out <= 8, "linear_narrow: n_out=%d not in [1,8]", n_out);
   if (n_rows == 0) return VADX_OK;
   int64_t blocks = ceil_div(n_rows, 8);
@@ -410,7 +410,8 @@ using namespace vadx;
 extern "C" int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt, int ldw, const float* d_bias,
                                const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows,
                                int n_in, int n_out, int act, void* stream) {
-  StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream, n_rows <= kSkinnyMaxRows ? "gemm_skinny_kernel" : "gemm_f32_kernel(linear)",
+                    4.0 * n_rows * (n_in + n_out + (d_residual ? n_out : 0)), 2.0 * n_rows * n_in * n_out);
   VADX_REQUIRE(d_x && d_wt && d_y, "vadx_linear_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0, "vadx_linear_f32: bad shape rows=%lld in=%d out=%d",
                (long long)n_rows, n_in, n_out);
@@ -432,7 +433,9 @@ extern "C" int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt,
 extern "C" int vadx_stft_power_f32(const float* d_sig, int64_t sig_stride, int64_t n_streams, int n_frames, int hop,
                                    int n_taps, const float* d_basis, int ld_basis, int n_bins, float* d_power,
                                    int64_t ld_power, void* stream) {
-  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream, "gemm_f32_kernel(stft_power)",
+                    4.0 * n_streams * ((n_frames - 1) * (double)hop + n_taps) + 4.0 * n_streams * n_frames * n_bins,
+                    2.0 * n_streams * n_frames * n_taps * 2.0 * n_bins);
   VADX_REQUIRE(d_sig && d_basis && d_power, "vadx_stft_power_f32: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0,
                "vadx_stft_power_f32: bad shape");
@@ -453,7 +456,9 @@ extern "C" int vadx_stft_power_f32(const float* d_sig, int64_t sig_stride, int64
 extern "C" int vadx_stft_complex_f32(const float* d_sig, int64_t sig_stride, int64_t n_streams, int n_frames, int hop,
                                      int n_taps, const float* d_basis, int ld_basis, int n_bins, float* d_out,
                                      int64_t ld_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream, "gemm_f32_kernel(stft_complex)",
+                    4.0 * n_streams * ((n_frames - 1) * (double)hop + n_taps) + 8.0 * n_streams * n_frames * n_bins,
+                    2.0 * n_streams * n_frames * n_taps * 2.0 * n_bins);
   VADX_REQUIRE(d_sig && d_basis && d_out, "vadx_stft_complex_f32: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0, "vadx_stft_complex_f32: bad shape");
   VADX_REQUIRE(ld_basis >= 2 * n_bins && (ld_basis & 3) == 0 && aligned16(d_basis) && ld_out >= 2 * n_bins,

@@ -618,7 +618,9 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
                             int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
                             int x_split, int y_split, int rows_per_stream) {
   const int g_ys_T = y_split == 2 ? rows_per_stream : 0;
-  StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream);
+  // rows in + rows out at 4 B per value (the operand-stage hand-overs carry two bf16 terms = the same 4 B), + residual rows
+  StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream, d_head_out ? "linear_tc_kernel+head" : "linear_tc_kernel",
+                    4.0 * n_rows * (n_in + (d_head_out ? 1 : n_out) + (d_residual ? n_out : 0)), 2.0 * n_rows * n_in * n_out);
   VADX_REQUIRE(d_x && d_wimg, "vadx_linear_tc_f32: null pointer");
   VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
   TcShape s = tc_shape(n_in, n_out);

@@ -366,7 +366,7 @@ static inline unsigned g1(int64_t items) {
 
 extern "C" int vadx_permute4_f32(const float* d_in, float* d_out, int64_t n0, int64_t n1, int64_t n2, int64_t n3, int p0,
                                  int p1, int p2, int p3, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "permute4_kernel", 8.0 * n0 * n1 * n2 * n3);
   VADX_REQUIRE(d_in && d_out && d_in != d_out && n0 >= 0 && n1 >= 1 && n2 >= 1 && n3 >= 1, "vadx_permute4_f32: bad argument");
   int seen = 0;
   for (int p : {p0, p1, p2, p3}) {
@@ -381,7 +381,7 @@ extern "C" int vadx_permute4_f32(const float* d_in, float* d_out, int64_t n0, in
 
 extern "C" int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len, const float* d_w, const float* d_b,
                                   float eps, float* d_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "layernorm_kernel", 8.0 * n_rows * row_len);
   VADX_REQUIRE(d_x && d_w && d_b && d_out && n_rows >= 0 && row_len >= 2, "vadx_layernorm_f32: bad argument");
   VADX_REQUIRE(n_rows <= 0x7fffffffLL, "vadx_layernorm_f32: too many rows");
   if (n_rows == 0) return VADX_OK;
@@ -393,7 +393,8 @@ extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_in
                                  int64_t y_outer, int64_t y_inner, int64_t y_step, const float* d_w_ih,
                                  const float* d_w_hh, const float* d_b_ih, const float* d_b_hh, int64_t n_seq,
                                  int n_inner, int seq_len, int n_in, int hidden, int reverse, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "lstm_seq_kernel",
+                    4.0 * n_seq * seq_len * ((double)n_in + hidden), 2.0 * n_seq * seq_len * 4.0 * hidden * ((double)n_in + hidden));
   VADX_REQUIRE(d_x && d_y && d_w_ih && d_w_hh && d_b_ih && d_b_hh, "vadx_lstm_seq_f32: null pointer");
   VADX_REQUIRE(n_seq >= 0 && n_inner >= 1 && seq_len >= 1 && n_in >= 1 && hidden >= 1, "vadx_lstm_seq_f32: bad shape");
   if (n_seq == 0) return VADX_OK;
@@ -422,7 +423,7 @@ extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_in
 extern "C" int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_out,
                             int64_t ldo, float* d_out2, int64_t ldo2, int64_t n_rows, int n_cols, float scalar,
                             void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "ew2_kernel", 4.0 * n_rows * n_cols * (1 + (d_b ? 1 : 0) + 1 + (d_out2 ? 1 : 0)));
   VADX_REQUIRE(d_a && d_out && op >= 0 && op <= 4 && (op == 3 || d_b) && (op != 4 || d_out2) && n_rows >= 0 && n_cols >= 1,
                "vadx_ew2_f32: bad argument");
   if (n_rows == 0) return VADX_OK;
@@ -433,7 +434,7 @@ extern "C" int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* 
 
 extern "C" int vadx_ceps_cmul_f32(const float* d_q, const float* d_p, float* d_out, int64_t n_rows, int n_channels,
                                   void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "cmul_kernel", 4.0 * n_rows * n_channels * 6.0);
   VADX_REQUIRE(d_q && d_p && d_out && n_rows >= 0 && n_channels >= 1, "vadx_ceps_cmul_f32: bad argument");
   if (n_rows == 0) return VADX_OK;
   cmul_kernel<<<g1(n_rows * n_channels), 256, 0, (cudaStream_t)stream>>>(d_q, d_p, d_out, n_rows, n_channels);
@@ -442,7 +443,7 @@ extern "C" int vadx_ceps_cmul_f32(const float* d_q, const float* d_p, float* d_o
 
 extern "C" int vadx_im2col_f3_f32(const float* d_x, float* d_out, int64_t n_blocks, int n_bins, int n_channels,
                                   void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "im2col_f3_kernel", 4.0 * n_blocks * n_bins * n_channels * 4.0);
   VADX_REQUIRE(d_x && d_out && n_blocks >= 0 && n_bins >= 1 && n_channels >= 1, "vadx_im2col_f3_f32: bad argument");
   if (n_blocks == 0) return VADX_OK;
   im2col_f3_kernel<<<g1(n_blocks * n_bins * 3 * n_channels), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n_blocks, n_bins,
@@ -453,7 +454,7 @@ extern "C" int vadx_im2col_f3_f32(const float* d_x, float* d_out, int64_t n_bloc
 extern "C" int vadx_alpha_x4_f32(const float* d_near_ri, const float* d_far_ri, int64_t n_streams, int n_frames,
                                  int n_bins, int k, float w1_far, float w1_mix, float b1, const float* d_w2, float b2,
                                  float* d_x4, float* d_alpha, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "alpha_x4_kernel", 4.0 * n_streams * n_frames * n_bins * 8.0);
   VADX_REQUIRE(d_near_ri && d_far_ri && d_w2 && d_x4 && n_streams >= 0 && n_frames >= 1 && n_bins >= 1 && k >= 1,
                "vadx_alpha_x4_f32: bad argument");
   if (n_streams == 0) return VADX_OK;
@@ -466,7 +467,7 @@ extern "C" int vadx_alpha_x4_const_f32(const float* d_near_ri, const float* d_po
                                        int t_max, int64_t n_streams, int n_frames, int n_bins, int k, float w1_far,
                                        float w1_mix, float b1, const float* d_w2, float b2, float* d_x4, float* d_alpha,
                                        void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "alpha_x4_const_kernel", 4.0 * n_streams * n_frames * n_bins * 6.0);
   VADX_REQUIRE(d_near_ri && d_pow_far && d_far_comp && d_w2 && d_x4 && n_streams >= 0 && n_frames >= 1 && n_bins >= 1 &&
                    k >= 1 && t_max >= n_frames,
                "vadx_alpha_x4_const_f32: bad argument (t_max %d must cover n_frames %d)", t_max, n_frames);
@@ -478,7 +479,7 @@ extern "C" int vadx_alpha_x4_const_f32(const float* d_near_ri, const float* d_po
 
 extern "C" int vadx_istft_ola_f32(const float* d_frames, int64_t ld, int64_t n_streams, int n_frames, int n_fft, int hop,
                                   const float* d_wsum_inv, int n_out, float* d_y, int64_t ldy, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "istft_ola_kernel", 4.0 * n_streams * ((double)n_frames * n_fft + n_out));
   VADX_REQUIRE(d_frames && d_wsum_inv && d_y && n_streams >= 0 && n_frames >= 1 && n_fft >= 2 && hop >= 1 && ld >= n_fft &&
                    n_out >= 1 && n_out <= (n_frames - 1) * hop + n_fft - 2 * (n_fft / 2) && ldy >= n_out,
                "vadx_istft_ola_f32: bad argument");

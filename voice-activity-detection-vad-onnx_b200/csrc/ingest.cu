@@ -80,7 +80,7 @@ extern "C" int64_t vadx_resample_out_len(int64_t n_in, double scale) {
 
 extern "C" int vadx_resample_linear_f32(const float* d_in, int64_t in_stride, int64_t n_in, int64_t n_streams, double scale,
                                         float* d_out, int64_t out_stride, int64_t out_offset, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "resample_linear_kernel", 4.0 * n_streams * n_in * (1.0 + scale));
   VADX_REQUIRE(d_in && d_out && scale > 0.0, "vadx_resample_linear_f32: bad argument");
   const int64_t n_out = vadx_resample_out_len(n_in, scale);
   VADX_REQUIRE(n_streams >= 0 && n_streams <= 65535 && n_in >= 1 && in_stride >= n_in && out_offset >= 0 &&
@@ -103,7 +103,7 @@ extern "C" int64_t vadx_ingest_out_frames(int64_t n_frames_in, int in_rate, int 
 extern "C" int vadx_ingest_pcm16(const int16_t* d_pcm, int64_t in_stride, const int64_t* d_n_in, int64_t n_streams,
                                  int64_t n_frames_in, int n_channels, int in_rate, int out_rate, int16_t* d_out,
                                  int64_t out_stride, int64_t* d_n_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "ingest_pcm16_kernel", 2.0 * n_streams * n_frames_in * n_channels * (1.0 + (double)out_rate / (in_rate * n_channels)));
   VADX_REQUIRE(d_pcm && d_out, "vadx_ingest_pcm16: null pointer");
   VADX_REQUIRE(n_channels == 1 || n_channels == 2, "vadx_ingest_pcm16: %d channels are not supported", n_channels);
   VADX_REQUIRE(in_rate > 0 && out_rate > 0 && out_rate <= 65536 * (int)gcd_i64(in_rate, out_rate),

@@ -138,8 +138,53 @@ struct vadx_model {
         VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, img.data(), img.size(), &bytes));
         VADX_TRY(upload(name + (part ? "#TC1" : "#TC0"), img.data(), img.size()));
       }
+    } else if (n_out > 16) {
+      // N too wide for one stationary image (more than 256 columns, or the image leaves no room for the activation
+      // stages: Silero 128 -> 512, FSMN 140 -> 250): column blocks "#TCN<j>" of equal 16-aligned width, one launch per
+      // block writing its slice of the output rows (the input rows are read once per block)
+      for (int wmax : {256, 128, 64}) {
+        const int n_blocks = (n_out + wmax - 1) / wmax;
+        const int bw = (int)round_up((n_out + n_blocks - 1) / n_blocks, 16);
+        if (n_blocks < 2 || !vadx_tc_supported(n_in, bw) || n_out - (n_blocks - 1) * bw <= 8) continue;
+        for (int j = 0; j < n_blocks; ++j) {
+          const int c0 = j * bw, cn = std::min(bw, n_out - c0);
+          size_t bytes = 0;
+          VADX_TRY(vadx_pack_weight_tc(w + (size_t)c0 * n_in, cn, n_in, nullptr, 0, &bytes));
+          std::vector<uint8_t> img(bytes);
+          VADX_TRY(vadx_pack_weight_tc(w + (size_t)c0 * n_in, cn, n_in, img.data(), img.size(), &bytes));
+          VADX_TRY(upload(name + "#TCN" + std::to_string(j), img.data(), img.size()));
+        }
+        scalars["derived.nsplit." + name] = bw;
+        break;
+      }
     }
     return VADX_OK;
+  }
+  // Y = act(X W^T + b) (+ res) for the layer uploaded by upload_linear(name, ...): one stationary tensor-core image when it
+  // fits, two K halves (activation-free layers only), N column blocks, or the exact-fp32 FFMA kernel (use_tc = false, rows
+  // <= kSkinnyMaxRows, shapes none of the above covers)
+  int linear(const std::string& name, const float* x, int64_t ldx, const float* bias, const float* res, int64_t ldr, float* y,
+             int64_t ldy, int64_t n_rows, int n_in, int n_out, int act, bool use_tc, void* st) const {
+    if (use_tc && n_rows > kSkinnyMaxRows) {
+      if (const uint8_t* img = d<uint8_t>(name + "#TC"))
+        return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, st);
+      const uint8_t* img0 = d<uint8_t>(name + "#TC0");
+      if (img0 && (act & 15) == VADX_ACT_NONE && !res) {
+        // long K split over two stationary images: y = x[:, :256] W0^T + b, then y += x[:, 256:] W1^T
+        VADX_TRY(vadx_linear_tc_f32(x, ldx, img0, bias, nullptr, 0, y, ldy, n_rows, 256, n_out, VADX_ACT_NONE, st));
+        return vadx_linear_tc_f32(x + 256, ldx, d<uint8_t>(name + "#TC1"), nullptr, y, ldy, y, ldy, n_rows, n_in - 256, n_out,
+                                  VADX_ACT_NONE, st);
+      }
+      const int bw = (int)scalar(("derived.nsplit." + name).c_str(), 0.0);
+      if (bw > 0 && ((ldy & 3) == 0 || (bw & 3) == 0)) {
+        for (int j = 0, c0 = 0; c0 < n_out; ++j, c0 += bw)
+          VADX_TRY(vadx_linear_tc_f32(x, ldx, d<uint8_t>(name + "#TCN" + std::to_string(j)), bias ? bias + c0 : nullptr,
+                                      res ? res + c0 : nullptr, ldr, y + c0, ldy, n_rows, n_in, std::min(bw, n_out - c0), act, st));
+        return VADX_OK;
+      }
+    }
+    return vadx_linear_f32(x, ldx, d<float>(name + "#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, n_rows, n_in, n_out,
+                           act, st);
   }
   // the sparse filterbank (frontend.mel_start / mel_len / mel_w) as a dense [n_mels][n_bins] tensor-core layer image
   // ("frontend.mel#TC") plus its per-column floor / epsilon vector ("frontend.mel_floor"); no-op when it does not fit

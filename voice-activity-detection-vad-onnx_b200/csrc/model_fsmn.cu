@@ -183,20 +183,10 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   }
   VADX_TRY(vadx_lfr_cmvn_f32(mel, h.n_mels, m->d<float>("cmvn_means"), m->d<float>("cmvn_vars"), feat, h.input_dim, S,
                              T, h.n_mels, h.lfr_m, h.lfr_n, st));
+  const bool tc_rows = m->scalar("engine.use_tc", 1.0) != 0.0;
   auto lin = [&](const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, float* y, int64_t ldy,
                  int n_out, int act) -> int {
-    const uint8_t* img = use_tc ? m->d<uint8_t>(w + "#TC") : nullptr;
-    const float* bias = b ? m->d<float>(b) : nullptr;
-    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, nullptr, 0, y, ldy, rows, n_in, n_out, act, st);
-    const uint8_t* img0 = use_tc ? m->d<uint8_t>(w + "#TC0") : nullptr;
-    if (img0 && (act & 15) == VADX_ACT_NONE) {
-      // long K split over two stationary images: y = x[:, :256] W0^T + b, then y += x[:, 256:] W1^T
-      VADX_TRY(vadx_linear_tc_f32(x, ldx, img0, bias, nullptr, 0, y, ldy, rows, 256, n_out, VADX_ACT_NONE, st));
-      return vadx_linear_tc_f32(x + 256, ldx, m->d<uint8_t>(w + "#TC1"), nullptr, y, ldy, y, ldy, rows, n_in - 256, n_out,
-                                VADX_ACT_NONE, st);
-    }
-    return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, nullptr, 0, y, ldy, rows, n_in,
-                           n_out, act, st);
+    return m->linear(w, x, ldx, b ? m->d<float>(b) : nullptr, nullptr, 0, y, ldy, rows, n_in, n_out, act, tc_rows, st);
   };
   VADX_TRY(lin(feat, h.input_dim, h.input_dim, "in_linear1.linear.weight", "in_linear1.linear.bias", bufA, ldw,
                h.affine, VADX_ACT_NONE));

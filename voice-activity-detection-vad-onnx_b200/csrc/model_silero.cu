@@ -106,11 +106,7 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
   const bool tc_ok = m->scalar("engine.use_tc", 1.0) != 0.0;
   auto lin = [&](int64_t n_rows, const float* x, int64_t ldx, int n_in, const std::string& w, const char* b, const float* res,
                  int64_t ldr, float* y, int64_t ldy, int n_out, int act) -> int {
-    const uint8_t* img = tc_ok && n_rows > kSkinnyMaxRows ? m->d<uint8_t>(w + "#TC") : nullptr;
-    const float* bias = b ? m->d<float>(b) : nullptr;
-    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, st);
-    return vadx_linear_f32(x, ldx, m->d<float>(w + "#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, n_rows, n_in,
-                           n_out, act, st);
+    return m->linear(w, x, ldx, b ? m->d<float>(b) : nullptr, res, ldr, y, ldy, n_rows, n_in, n_out, act, tc_ok, st);
   };
   // rows are ordered [window][stream] so that one window's gates are contiguous for the recurrence
   for (int w = 0; w < W; ++w)

@@ -631,7 +631,7 @@ extern "C" int vadx_stream_postprocess(const float* d_probs, int64_t ld_probs, c
                                        int64_t n_streams, int n_frames, const vadx_stream_post_cfg* cfg,
                                        int32_t* d_state, int32_t* d_seg_count, int32_t* d_segments, int max_segments,
                                        int32_t* d_open, void* stream) {
-  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "stream_postprocess_kernel", 4.0 * n_streams * n_frames);
   VADX_REQUIRE(d_probs && cfg && d_state, "vadx_stream_postprocess: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames >= 0 && ld_probs >= n_frames, "vadx_stream_postprocess: bad shape");
   VADX_REQUIRE(cfg->smooth_window <= kMaxSmooth, "vadx_stream_postprocess: smooth_window %d > %d", cfg->smooth_window,
@@ -648,7 +648,7 @@ extern "C" int vadx_postprocess_frames(const float* d_probs, int64_t ld_probs, c
                                        int64_t n_streams, int n_frames, const vadx_post_cfg* cfg,
                                        int8_t* d_decisions, int32_t* d_seg_count, int32_t* d_segments,
                                        int max_segments, void* stream) {
-  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "postprocess_frames_runs_kernel", 5.0 * n_streams * n_frames);
   VADX_REQUIRE(d_probs && cfg && d_decisions, "vadx_postprocess_frames: null pointer (d_decisions is required)");
   VADX_REQUIRE(n_streams >= 0 && n_frames >= 0 && ld_probs >= n_frames, "vadx_postprocess_frames: bad shape");
   VADX_REQUIRE(cfg->smooth_window <= kMaxSmooth, "vadx_postprocess_frames: smooth_window %d > %d", cfg->smooth_window,

@@ -144,7 +144,7 @@ static inline unsigned grid1d(int64_t items) {
 
 extern "C" int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_in, int pad,
                                        float* d_out, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "reflect_window_kernel", 4.0 * n_streams * (2.0 * n_in + pad));
   VADX_REQUIRE(d_x && d_out && n_streams >= 0 && n_in >= 2 && pad >= 0 && pad <= n_in - 1 && in_stride >= 1,
                "vadx_reflect_window_f32: bad argument");
   if (n_streams == 0) return VADX_OK;
@@ -154,7 +154,7 @@ extern "C" int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int6
 }
 
 extern "C" int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "sqrt_inplace_kernel", 8.0 * n);
   VADX_REQUIRE(d_p && n >= 0, "vadx_sqrt_inplace_f32: bad argument");
   if (n == 0) return VADX_OK;
   sqrt_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(d_p, n);
@@ -163,7 +163,7 @@ extern "C" int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream) {
 
 extern "C" int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, float* d_h_out, float* d_c_out,
                                   float* d_h_relu, int64_t n_streams, int hidden, void* stream) {
-  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "lstm_cell_kernel", 4.0 * n_streams * hidden * (4 + 1 + 2 + (d_h_relu ? 1 : 0)));
   VADX_REQUIRE(d_gates && d_c_in && d_h_out && d_c_out && n_streams >= 0 && hidden >= 1, "vadx_lstm_cell_f32: bad argument");
   if (n_streams == 0) return VADX_OK;
   lstm_cell_kernel<<<grid1d(n_streams * hidden), 256, 0, (cudaStream_t)stream>>>(d_gates, d_c_in, d_h_out, d_c_out,
@@ -177,7 +177,7 @@ extern "C" int vadx_silero_timestamps(const float* d_probs, int64_t ld, const in
                                       double min_silence_samples, double min_silence_samples_at_max_speech,
                                       int window, int use_max_poss_sil, int32_t* d_seg_count, int64_t* d_segments,
                                       int max_segments, void* stream) {
-  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "silero_timestamps_kernel");
   VADX_REQUIRE(d_probs && d_n_windows && d_n_samples && d_seg_count && d_segments && max_segments >= 1 && window >= 1,
                "vadx_silero_timestamps: bad argument");
   if (n_streams == 0) return VADX_OK;

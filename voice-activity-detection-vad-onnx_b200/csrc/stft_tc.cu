@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) stream_mean_i16_kernel(const int16_t* __r
 
 extern "C" int vadx_stream_mean_i16(const int16_t* d_audio, int64_t in_stride, int64_t n_samples, int64_t n_streams,
                                     float* d_mean_frac, int32_t* d_mean_int, void* stream) {
-  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "stream_mean_i16_kernel", 2.0 * n_streams * n_samples);
   VADX_REQUIRE(d_audio && d_mean_frac && d_mean_int && n_samples > 0 && in_stride >= n_samples && n_streams >= 0,
                "vadx_stream_mean_i16: bad argument");
   if (n_streams == 0) return VADX_OK;
@@ -598,7 +598,9 @@ extern "C" int vadx_stft_power_tc_i16_ex(const int16_t* d_audio, int64_t in_stri
   VADX_REQUIRE(operand_format == VADX_TC_FMT_BF16 || (operand_format == VADX_TC_FMT_F16 && !d_mean_frac),
                "vadx_stft_power_tc_i16: fp16 operands cannot carry the mean-removed (17-bit) samples");
   VADX_REQUIRE((d_mean_frac == nullptr) == (d_mean_int == nullptr), "vadx_stft_power_tc_i16: mean needs both its parts");
-  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream);
+  StageTimer _timer(VADX_STAGE_STFT, (cudaStream_t)stream, "stft_power_tc_kernel",
+                    2.0 * n_streams * n_samples + 4.0 * n_streams * n_frames * n_bins,      // int16 audio in, power out
+                    2.0 * n_streams * n_frames * n_taps * 2.0 * n_bins);
   VADX_REQUIRE(d_audio && d_img && d_power, "vadx_stft_power_tc_i16: null pointer");
   VADX_REQUIRE(n_streams >= 0 && n_frames > 0 && hop > 0 && n_taps > 0 && n_bins > 0 && ld_power >= n_bins,
                "vadx_stft_power_tc_i16: bad shape");

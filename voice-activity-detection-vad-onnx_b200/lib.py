@@ -41,6 +41,7 @@ SIGNATURES = {
     "vadx_launch_count": (C.c_uint64, []),
     "vadx_profile_enable": (C.c_int, [_i32]),
     "vadx_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), _i32]),
+    "vadx_profile_collect_kernels": (C.c_int, [_vp, _i32, C.POINTER(C.c_int)]),
     "vadx_prep_audio": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _f32, _i32, _i32, _f32, _i64, _vp, _i64, _vp]),
     "vadx_stft_power_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "vadx_stft_tc_supported": (C.c_int, [_i32, _i32]),
@@ -142,6 +143,23 @@ def profile_collect() -> dict:
     calls = (C.c_uint64 * len(STAGES))()
     check(load().vadx_profile_collect(ms, calls, len(STAGES)))
     return {n: (ms[i], int(calls[i])) for i, n in enumerate(STAGES)}
+
+
+class _KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_double), ("calls", C.c_uint64), ("bytes", C.c_double), ("flops", C.c_double)]
+
+
+def profile_collect_kernels() -> dict:
+    """-> {kernel name: {"ms", "calls", "bytes", "flops"}} accumulated since the last collect (synchronises): the
+    algorithmic bytes / flops every entry point reports for its calls, next to their measured device time."""
+    n = C.c_int(0)
+    check(load().vadx_profile_collect_kernels(None, 0, C.byref(n)))
+    if n.value == 0:
+        return {}
+    buf = (_KernelStat * n.value)()
+    check(load().vadx_profile_collect_kernels(C.cast(buf, C.c_void_p), n.value, C.byref(n)))
+    return {buf[i].name.decode(): {"ms": buf[i].ms, "calls": int(buf[i].calls), "bytes": buf[i].bytes, "flops": buf[i].flops}
+            for i in range(n.value)}
 
 
 def check(rc: int) -> None:
