@@ -29,7 +29,11 @@ def session(cuda):
 
 
 @pytest.mark.parametrize("T,C,k,stride,dil", [(601, 80, 11, 2, 1), (300, 64, 13, 1, 1), (300, 64, 29, 1, 2),
-                                              (50, 128, 1, 1, 1), (33, 128, 17, 1, 1)])
+                                              (50, 128, 1, 1, 1), (33, 128, 17, 1, 1),
+                                              # several 4-tile CTAs per stream with a ragged last tile (register-window kernel)
+                                              (3001, 64, 15, 1, 1), (1500, 128, 13, 1, 1), (6001, 80, 11, 2, 1), (1111, 64, 29, 1, 2),
+                                              # shapes only the generic shared-memory kernel covers
+                                              (200, 30, 7, 1, 1), (200, 64, 5, 3, 2)])
 def test_depthwise_conv(cuda, T, C, k, stride, dil):
     S = 3
     g = torch.Generator().manual_seed(T + k)

@@ -462,6 +462,88 @@ __global__ void __launch_bounds__(256) depthwise_conv1d_kernel(const float* __re
 }
 }  // namespace vadx
 
+namespace vadx {
+// Register-window depthwise conv for the shapes the Jasper blocks use (compile-time taps / stride / dilation, channels a
+// multiple of 4): a CTA stages TS = groups * 8 output frames (+ halo) of one stream as float4 rows, thread = (channel quad,
+// 8 consecutive outputs) walks its input rows ONCE -- every float4 it reads feeds all the outputs and taps it belongs to,
+// the taps live in registers -- and a CTA runs kDwTiles consecutive tiles so the tap loads are amortised.  The generic
+// kernel above reads one shared-memory scalar per FMA and re-loads a 32-frame tile's halo (up to 175 % at 29 taps, dilation 2).
+constexpr int kDwR = 8;       // outputs per thread
+constexpr int kDwTiles = 4;   // consecutive tiles per CTA
+template <int K, int STRIDE, int DIL, int MINB>
+__global__ void __launch_bounds__(256, MINB) depthwise_conv1d_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                        int pad, float* __restrict__ y, int t_in, int t_out, int C) {
+  constexpr int NI = (kDwR - 1) * STRIDE + (K - 1) * DIL + 1;      // input rows one thread reads per tile
+  extern __shared__ float4 dw_tile[];                               // [rows_in][C / 4]
+  const int C4 = C >> 2;
+  const int groups = 256 / C4;
+  const int ts = groups * kDwR;                                     // outputs per tile
+  const int rows_in = (ts - 1) * STRIDE + (K - 1) * DIL + 1;
+  const int q = threadIdx.x % C4, g = threadIdx.x / C4;
+  const int64_t s = blockIdx.y;
+  const float4* xs = reinterpret_cast<const float4*>(x + s * (int64_t)t_in * C);
+  float4* ys = reinterpret_cast<float4*>(y + s * (int64_t)t_out * C);
+  float4 wq[K];
+  if (g < groups) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      wq[k] = make_float4(__ldg(w + (4 * q + 0) * K + k), __ldg(w + (4 * q + 1) * K + k), __ldg(w + (4 * q + 2) * K + k),
+                          __ldg(w + (4 * q + 3) * K + k));
+  }
+  for (int tile = 0; tile < kDwTiles; ++tile) {
+    const int o0 = (blockIdx.x * kDwTiles + tile) * ts;
+    if (o0 >= t_out) break;
+    const int i0 = o0 * STRIDE - pad;
+    __syncthreads();                                                // the previous tile's readers are done
+    for (int i = threadIdx.x; i < rows_in * C4; i += 256) {
+      const int r = i / C4, t = i0 + r;
+      dw_tile[i] = (t >= 0 && t < t_in) ? __ldg(xs + (int64_t)t * C4 + (i - r * C4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (g < groups) {
+      float4 acc[kDwR];
+#pragma unroll
+      for (int j = 0; j < kDwR; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = dw_tile + (size_t)(g * kDwR * STRIDE) * C4 + q;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float4 v = src[(size_t)i * C4];
+#pragma unroll
+        for (int j = 0; j < kDwR; ++j) {
+          const int d = i - j * STRIDE;                             // compile-time after unrolling
+          if (d >= 0 && d % DIL == 0 && d / DIL < K) {
+            const float4 t = wq[d / DIL];
+            acc[j].x = fmaf(t.x, v.x, acc[j].x); acc[j].y = fmaf(t.y, v.y, acc[j].y);
+            acc[j].z = fmaf(t.z, v.z, acc[j].z); acc[j].w = fmaf(t.w, v.w, acc[j].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kDwR; ++j) {
+        const int o = o0 + g * kDwR + j;
+        if (o < t_out) ys[(int64_t)o * C4 + q] = acc[j];
+      }
+    }
+  }
+}
+
+template <int K, int STRIDE, int DIL, int MINB>
+static int launch_depthwise_reg(const float* x, const float* w, int pad, float* y, int64_t S, int t_in, int t_out, int C,
+                                cudaStream_t st) {
+  const int C4 = C / 4, groups = 256 / C4, ts = groups * kDwR;
+  const int rows_in = (ts - 1) * STRIDE + (K - 1) * DIL + 1;
+  const size_t smem = (size_t)rows_in * C * sizeof(float);
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(depthwise_conv1d_reg_kernel<K, STRIDE, DIL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                100 * 1024);
+  }));
+  dim3 grid((unsigned)ceil_div(t_out, (int64_t)ts * kDwTiles), (unsigned)S);
+  depthwise_conv1d_reg_kernel<K, STRIDE, DIL, MINB><<<grid, 256, smem, st>>>(x, w, pad, y, t_in, t_out, C);
+  return after_launch("vadx_depthwise_conv1d_f32");
+}
+}  // namespace vadx
+
 extern "C" int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const float* d_w, int kernel, int stride,
                                          int dilation, int pad, float* d_y, int64_t ldy, int64_t n_streams, int t_in,
                                          int t_out, int n_channels, void* stream) {
@@ -475,6 +557,17 @@ extern "C" int vadx_depthwise_conv1d_f32(const float* d_x, int64_t ldx, const fl
                "vadx_depthwise_conv1d_f32: t_out inconsistent with t_in");
   VADX_REQUIRE(n_streams <= 65535, "vadx_depthwise_conv1d_f32: at most 65535 streams per call");
   if (n_streams == 0) return VADX_OK;
+  // the Jasper shapes on the register-window kernel: dense rows of 16 .. 256 channels (a multiple of 4), 16-byte aligned
+  if (ldx == n_channels && ldy == n_channels && (n_channels & 3) == 0 && n_channels >= 16 && n_channels <= 256 &&
+      aligned16(d_x) && aligned16(d_y) && (int64_t)t_in * n_channels < (1LL << 40)) {
+    cudaStream_t cs = (cudaStream_t)stream;
+#define VADX_DW_CASE(KK, SS, DD, MB)                                                                                   \
+    if (kernel == KK && stride == SS && dilation == DD)                                                              \
+      return launch_depthwise_reg<KK, SS, DD, MB>(d_x, d_w, pad, d_y, n_streams, t_in, t_out, n_channels, cs);
+    VADX_DW_CASE(11, 2, 1, 2) VADX_DW_CASE(13, 1, 1, 2) VADX_DW_CASE(15, 1, 1, 2) VADX_DW_CASE(17, 1, 1, 2)
+    VADX_DW_CASE(29, 1, 2, 1) VADX_DW_CASE(1, 1, 1, 2)
+#undef VADX_DW_CASE
+  }
   const int rows_in = (kDwT - 1) * stride + (kernel - 1) * dilation + 1;
   size_t smem = ((size_t)rows_in + kernel) * n_channels * sizeof(float);
   VADX_REQUIRE(smem <= 200 * 1024, "vadx_depthwise_conv1d_f32: tile of %zu bytes exceeds shared memory", smem);
