@@ -263,6 +263,21 @@ def family_workloads(dev, only=None):
     def want(n):
         return only is None or n in only
 
+    if only is not None and "firered" in only:
+        # the headline workload (BASELINE configs[3]) as a family step, for tools/family_step.py (ncu captures)
+        from vadx import firered_vad
+        cfg = W.FireRedConfig()
+        sess = vadx.FireRedSession(W.firered_random_init(cfg, 0), cfg, chunk_len=CHUNK)
+        B = 8192
+        S = B // CHUNKS_PER_STREAM
+        d_audio = torch.from_numpy(synth.synth_chunks_fast(B, CHUNK, seed=1234)).to(dev)
+        lengths = [CHUNKS_PER_STREAM * CHUNK] * S
+        n_valid = torch.full((S,), min(firered_vad.valid_frame_count(lengths[0]), CHUNKS_PER_STREAM * sess.frames(CHUNK)),
+                             dtype=torch.int32, device=dev)
+        yield "firered", dict(step=lambda: firered_vad.run_vad_streams(sess, d_audio.view(S, CHUNKS_PER_STREAM, CHUNK), lengths,
+                                                                       firered_vad.POST_DEFAULT, n_valid=n_valid),
+                              eager=None, audio_s=B * 1.0, steps=10, warm=3, config=f"{B} chunks of {CHUNK} samples")
+        del sess, d_audio
     if want("fsmn"):
         # FSMN (config 0 shape, batched): S streams x 4 overlapping 16000-sample windows, state carried on device
         cfg = W.FsmnConfig()
@@ -304,7 +319,7 @@ def family_workloads(dev, only=None):
         cfg = W.DfsmnAecConfig()
         sess = vadx.DfsmnAecSession(W.dfsmn_aec_random_init(cfg, 0), cfg, chunk_len=31841)
         free_b, _total = torch.cuda.mem_get_info(dev)
-        S = 1024
+        S = int(os.environ.get("VADX_BENCH_DFSMN_PAIRS", "1024"))     # (the ncu captures run a smaller batch)
         while S > 32 and sess._e.workspace_bytes(S, 31841) > 0.7 * free_b:
             S //= 2
         ws_gb = sess._e.workspace_bytes(S, 31841) / 1e9
@@ -392,19 +407,22 @@ def family_rtfx(dev, world, dist):
         audio = np.load(gold)["audio"].astype(np.int16)
         cfg = W.FsmnConfig()
         sess = vadx.FsmnSession(W.fsmn_random_init(cfg, 0), cfg, chunk_len=512)
-        for graph in (False, True):
-            for _ in range(2):
-                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), graph=graph)
+        for mode in ("", "_graph", "_whole"):
+            kw = {"graph": mode == "_graph", "whole": mode == "_whole"}
+            for _ in range(3):
+                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), **kw)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for _ in range(3):
-                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), graph=graph)
+            for _ in range(5):
+                fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1), **kw)
             torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / 3
-            out["fsmn_c1_single_stream" + ("_graph" if graph else "")] = {
+            dt = (time.perf_counter() - t0) / 5
+            out["fsmn_c1_single_stream" + mode] = {
                 "rtf": dt / (len(audio) / 16000.0), "rtfx": (len(audio) / 16000.0) / dt, "seconds": dt,
-                "config": "vad_sample.wav (5.59 s), one stream, 512-sample chunks, 254 windows, wall clock of run_vad"
-                          + (", one CUDA-graph replay per window" if graph else ", eager launches")}
+                "config": "vad_sample.wav (5.59 s), one stream, 512-sample chunks, 254 windows, wall clock of run_vad (host "
+                          "normalisation, alignment and H2D included)"
+                          + {"": ", eager launches per window", "_graph": ", one CUDA-graph replay per window",
+                             "_whole": ", ALL windows in one forward + one sequential gate kernel (fsmn_vad.run_vad(whole=True))"}[mode]}
     return out
 
 

@@ -257,6 +257,18 @@ int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_in, int64_t
                               uint8_t* d_silence_state, int32_t* d_n_saved, uint8_t* d_saved, int64_t ld_saved,
                               float* d_noise_avg, const float* d_noisy_dB, float snr_threshold, void* stream);
 
+/* a9 + a13 for ALL windows of a recording in one launch (whole-file mode, see vadx_forward kind "fsmn" with the scalar
+ * input.n_windows): d_p_sil / d_power_dB [S][W][T] from one forward over every window; per stream the windows are walked in
+ * order -- gate of window w against the running background level, non-speech mean, look-ahead machine on the window's
+ * flags (the last window flushes the tail), level update (FSMN/Inference_FSMN_VAD_ONNX.py:177-234).  Optional traces:
+ * d_score u8 [S][W][T], d_noisy_dB / d_noise_in fp32 [S][W].  State arguments as vadx_lookahead_hysteresis. */
+int vadx_fsmn_gate_hysteresis_windows(const float* d_p_sil, const float* d_power_dB, int64_t n_streams, int n_windows,
+                                      int n_frames, float one_minus_speech_threshold, float speech_2_noise_ratio,
+                                      int look_backward, double speaking_score, double silence_score, uint8_t* d_score,
+                                      float* d_noisy_dB, float* d_noise_in, uint8_t* d_silence_state, int32_t* d_n_saved,
+                                      uint8_t* d_saved, int64_t ld_saved, float* d_noise_avg, float snr_threshold,
+                                      void* stream);
+
 /* a14 -- runs of non-silence flags -> (start, end-exclusive) frame pairs per stream
  * (vad_to_timestamps, FSMN/Inference_FSMN_VAD_ONNX.py:124-141). */
 int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags, int64_t n_streams,

@@ -721,6 +721,35 @@ def gen_dfsmn_near():
     np.savez_compressed(os.path.join(GOLD, "dfsmn_near.npz"), **out)
 
 
+def gen_marblenet_windows():
+    """The unmodified MarbleNet inference script in its STATIC-axis mode (a 32000-sample export: vad_sample.wav becomes three
+    non-overlapping windows, the last padded with RMS-matched noise, :130-147) -- the same code path that splits recordings
+    longer than one hour in the dynamic mode."""
+    import vadx  # noqa: F401
+    from vadx import audio_io, weights as W
+    from oracle import ref_runner as RR
+    cfg = W.MarbleNetConfig()
+    w = W.marblenet_random_init(cfg, 0)
+    wav = os.path.join(RL.REF_ROOT, "NVIDIA_Frame_VAD_Multilingual_MarbleNet", "vad_sample.wav")
+    box = {}
+
+    def factory(_p):
+        s = marblenet_fake_session(cfg, w)
+        s._inputs_meta[0].shape = [1, 1, 32000]
+        box["s"] = s
+        return s
+
+    ns, files = RR.run_script("NVIDIA_Frame_VAD_Multilingual_MarbleNet/Inference_NVIDIA_MarbleNet_VAD_ONNX.py", factory,
+                              lambda p, sr: audio_io.load_wav_int16(os.path.realpath(p), sr), seed=1234,
+                              files_to_link={"vad_sample.wav": wav})
+    out = {"probs": np.asarray(ns["all_vad_probs"], np.float32), "decisions": np.asarray(ns["vad_decisions"], np.int8),
+           "timestamps": np.array(ns["timestamps"], np.float64).reshape(-1, 2),
+           "file_second": np.array(files["timestamps_second.txt"]), "file_indices": np.array(files["timestamps_indices.txt"]),
+           "n_calls": np.array(len(box["s"].calls)), "window": np.array(32000)}
+    print("marblenet static 32000:", len(box["s"].calls), "windows,", out["probs"].shape, out["timestamps"].tolist())
+    np.savez_compressed(os.path.join(GOLD, "marblenet_windows.npz"), **out)
+
+
 def gen_dropin():
     """The session-call transcript of the three unmodified inference scripts (oracle/dropin.py, stage "record")."""
     from oracle import dropin
@@ -730,7 +759,7 @@ def gen_dropin():
     np.savez_compressed(os.path.join(GOLD, "dropin_transcript.npz"), **out)
 
 
-GENERATORS = {"dropin": gen_dropin, "dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "marblenet_rates": gen_marblenet_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
+GENERATORS = {"dropin": gen_dropin, "marblenet_windows": gen_marblenet_windows, "dfsmn_near": gen_dfsmn_near, "firered_rates": gen_firered_rates, "marblenet_rates": gen_marblenet_rates, "firered": gen_firered, "firered_script": gen_firered_script, "postproc": gen_postproc, "audio": gen_audio, "fsmn": gen_fsmn,
               "marblenet": gen_marblenet, "silero": gen_silero, "silero_iterator": gen_silero_iterator, "dfsmn_aec": gen_dfsmn_aec}
 
 

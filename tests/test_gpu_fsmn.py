@@ -165,17 +165,19 @@ def test_run_rejects_bad_inputs(cuda, wts):
         vadx.FsmnSession(wts, W.FsmnConfig(), chunk_len=256)
 
 
+@pytest.mark.parametrize("whole", [False, True])
 @pytest.mark.parametrize("tag,L,lookback", [("c16000", 16000, 0.3), ("c512", 512, 0.0)])
-def test_vad_sample_against_reference_script(cuda, gold, golden_dir, wts, tmp_path, tag, L, lookback):
+def test_vad_sample_against_reference_script(cuda, gold, golden_dir, wts, tmp_path, tag, L, lookback, whole):
     """vad_sample.wav end to end vs the record of the reference's unmodified script (same weights,
     same tail noise).  Frame probabilities within TOL of the oracle; every flag, timestamp and
-    output file byte identical unless a decision variable sits within TOL of its threshold."""
+    output file byte identical unless a decision variable sits within TOL of its threshold.
+    whole=True: all windows of the recording in one pass (FsmnSession.run_windows + the sequential gate kernel)."""
     cfg = W.FsmnConfig()
     sess = vadx.FsmnSession(wts, cfg, chunk_len=L)
     audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
     f1, f2 = str(tmp_path / "timestamps_second.txt"), str(tmp_path / "timestamps_indices.txt")
     r = fsmn_vad.run_vad(audio, sess, lookback, rng=np.random.RandomState(1234), save_timestamps_second=f1,
-                         save_timestamps_indices=f2, keep_trace=True)
+                         save_timestamps_indices=f2, keep_trace=True, whole=whole)
     orc = OFS.FsmnOracle(wts, cfg, L)
     a16 = audio_io.normalize_to_int16(audio.astype(np.float32))
     o = OFS.run_stream(orc, a16, look_backward_s=lookback, noise=np.random.RandomState(1234).normal(size=(20000,)))
@@ -194,6 +196,29 @@ def test_vad_sample_against_reference_script(cuda, gold, golden_dir, wts, tmp_pa
         # decisions away from the thresholds must still agree
         print(f"{tag}: a decision variable lies within {margin:.1e} of its threshold; comparing the rest")
         assert (r.saved != gold[f"{tag}_saved"]).mean() < 0.02
+
+
+def test_whole_file_mode_equals_window_by_window(cuda, wts):
+    """Several ragged-content streams, 16000-sample windows: the one-pass path (all windows batched, memory blocks as a
+    causal FIR over the concatenated frames, one sequential gate kernel) against the window-by-window loop: same decisions
+    wherever no decision variable sits on its threshold, P(silence) within the tensor-core tile-order noise, caches equal."""
+    cfg = W.FsmnConfig()
+    sess = vadx.FsmnSession(wts, cfg, chunk_len=16000)
+    S, stride = 5, 16000 - 31 * 160
+    a = torch.from_numpy(synth.synth_streams(S, 16000 + 4 * stride, seed=21)).to(cuda)
+    st_a, tr_a = fsmn_vad.run_streams(sess, a, stride, keep_trace=True)
+    st_b, tr_b = fsmn_vad.run_streams(sess, a, stride, keep_trace=True, whole=True)
+    assert len(tr_a) == len(tr_b) == 5
+    worst = max((x[1] - y[1]).abs().max().item() for x, y in zip(tr_a, tr_b))
+    worst_e = max((x[2] - y[2]).abs().max().item() for x, y in zip(tr_a, tr_b))
+    print(f"whole-file vs window loop: max |dP(silence)| {worst:.2e}, |d power_dB| {worst_e:.2e}")
+    assert worst <= 1e-4 and worst_e <= 1e-5
+    assert torch.equal(st_a.n_saved, st_b.n_saved)
+    margin = min(min((2 * t[1] - 1.0).abs().min().item(), (t[2] - t[3][:, None]).abs().min().item()) for t in tr_a)
+    if margin > 1e-3:
+        n = int(st_a.n_saved[0])
+        assert torch.equal(st_a.saved[:, :n], st_b.saved[:, :n])
+        assert (st_a.noise_avg - st_b.noise_avg).abs().max().item() <= 1e-5
 
 
 def test_many_streams_lockstep(cuda, wts):

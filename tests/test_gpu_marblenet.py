@@ -84,6 +84,32 @@ def test_vad_sample_timestamps(cuda, gold, golden_dir, session, tmp_path):
         assert open(f1).read() == str(gold["sample_file_second"]) and open(f2).read() == str(gold["sample_file_indices"])
 
 
+def test_static_axis_windows_against_reference_script(cuda, golden_dir, session, tmp_path, measured):
+    """The reference script's static-axis mode (a 32000-sample export; the same code path that splits recordings longer than
+    one hour in the dynamic mode, :130-147): vad_sample.wav becomes three non-overlapping windows, the last padded with
+    RMS-matched noise, all run as ONE batch here; valid frames concatenated, post-processed, written."""
+    g = np.load(os.path.join(golden_dir, "marblenet_windows.npz"))
+    audio = np.load(os.path.join(golden_dir, "vad_sample_16k.npz"))["audio"]
+    f1, f2 = str(tmp_path / "s.txt"), str(tmp_path / "i.txt")
+    r = marblenet_vad.run_vad(audio, session, save_timestamps_second=f1, save_timestamps_indices=f2,
+                              input_audio_length=int(g["window"]), rng=np.random.RandomState(1234))
+    assert int(g["n_calls"]) == 3 and r.probs.shape == g["probs"].shape == (300,)
+    measured("marblenet: static-axis windows vs the reference script", np.abs(r.probs - g["probs"]).max(), BOUND)
+    if np.abs(OP.smooth_probs(g["probs"], 3) - np.float32(0.5)).min() > TOL:
+        assert np.array_equal(r.decisions, g["decisions"])
+        assert np.array_equal(np.array(r.timestamps, np.float64).reshape(-1, 2), g["timestamps"])
+        assert open(f1).read() == str(g["file_second"]) and open(f2).read() == str(g["file_indices"])
+    # recordings longer than one hour take the same path instead of raising: shrink "one hour" to keep the test small
+    old = marblenet_vad.IN_SAMPLE_RATE
+    try:
+        marblenet_vad.IN_SAMPLE_RATE = 16000
+        long = np.tile(audio, 3)[:200000]
+        r2 = marblenet_vad.run_vad(long, session, input_audio_length=64000, rng=np.random.RandomState(5))
+        assert r2.probs.shape == (4 * 200,)
+    finally:
+        marblenet_vad.IN_SAMPLE_RATE = old
+
+
 def test_long_clips_batch_against_oracle(cuda, session, measured):
     """60 s clips (the BASELINE config-3 shape, small batch): 3000 valid frames each."""
     cfg = W.MarbleNetConfig()

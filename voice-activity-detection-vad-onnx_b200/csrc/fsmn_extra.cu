@@ -108,26 +108,15 @@ __global__ void __launch_bounds__(128) fsmn_gate_kernel(const float* __restrict_
 //                scores the vote RATIO is then tested against (DFSMN/near_and_far_end_audio/Inference_DFSMN_VAD_ONNX.py:
 //                231-273).  The per-frame test compares a numpy float32 with a Python float: under NEP 50 (numpy >= 2) the
 //                Python float is the weak operand, so the comparison happens in float32; the ratio test is Python floats.
-__global__ void __launch_bounds__(128) lookahead_hysteresis_kernel(const void* __restrict__ in, int mode, int64_t ld_in,
-                                                                   int64_t n_streams, int T, int look_backward,
-                                                                   double speaking_score, double silence_score,
-                                                                   int is_final, uint8_t* __restrict__ silence_state,
-                                                                   int32_t* __restrict__ n_saved,
-                                                                   uint8_t* __restrict__ saved, int64_t ld_saved,
-                                                                   float* __restrict__ noise_avg,
-                                                                   const float* __restrict__ noisy_dB, float snr) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_streams) return;
-  const uint8_t* fl = static_cast<const uint8_t*>(in) + s * ld_in;
-  const float* pr = static_cast<const float*>(in) + s * ld_in;
+// one chunk of the machine for one stream: appends T - look_backward decisions (all T when is_final) to out[n...]
+__device__ __forceinline__ void hysteresis_chunk(const uint8_t* fl, const float* pr, int mode, int T, int look_backward,
+                                                 double speaking_score, double silence_score, int is_final, bool& silence, int& n,
+                                                 uint8_t* out, int64_t ld_saved) {
   const float speak_f = (float)speaking_score, sil_f = (float)silence_score;
   auto speech_vote = [&](int i) { return mode == 0 ? fl[i] != 0 : pr[i] >= speak_f; };
   auto silence_vote = [&](int i) { return mode == 0 ? fl[i] != 1 : pr[i] <= sil_f; };
   const int lb = look_backward != 0 ? look_backward : 1;
   const double inv_d = 1.0 / (double)lb;
-  bool silence = silence_state[s] != 0;
-  int n = n_saved[s];
-  uint8_t* out = saved + s * ld_saved;
   const int range = T - look_backward;
   for (int i = 0; i < range; ++i) {
     if (silence) {
@@ -155,11 +144,87 @@ __global__ void __launch_bounds__(128) lookahead_hysteresis_kernel(const void* _
       ++n;
     }
   }
+}
+
+__global__ void __launch_bounds__(128) lookahead_hysteresis_kernel(const void* __restrict__ in, int mode, int64_t ld_in,
+                                                                   int64_t n_streams, int T, int look_backward,
+                                                                   double speaking_score, double silence_score,
+                                                                   int is_final, uint8_t* __restrict__ silence_state,
+                                                                   int32_t* __restrict__ n_saved,
+                                                                   uint8_t* __restrict__ saved, int64_t ld_saved,
+                                                                   float* __restrict__ noise_avg,
+                                                                   const float* __restrict__ noisy_dB, float snr) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  bool silence = silence_state[s] != 0;
+  int n = n_saved[s];
+  hysteresis_chunk(static_cast<const uint8_t*>(in) + s * ld_in, static_cast<const float*>(in) + s * ld_in, mode, T, look_backward,
+                   speaking_score, silence_score, is_final, silence, n, saved + s * ld_saved, ld_saved);
   silence_state[s] = silence ? 1 : 0;
   n_saved[s] = n;
   if (noise_avg && noisy_dB) {
     float nd = noisy_dB[s];
     if (nd > 0.0f) noise_avg[s] = 0.5f * ((noise_avg[s] + nd) + snr);
+  }
+}
+
+// a9 + a13 over ALL windows of a recording in one launch (whole-file mode of the FSMN path): the only sequential
+// dependence between windows is the running background level -- window w's gate compares against the level windows
+// 0..w-1 produced (FSMN/Inference_FSMN_VAD_ONNX.py:177-187,224-225) -- so one block per stream walks the windows: the 128
+// threads evaluate the gate of window w and reduce its non-speech mean exactly like fsmn_gate_kernel (same striding, same
+// tree: bit-identical noisy_dB), thread 0 then runs the look-ahead machine on that window's flags and updates the level.
+__global__ void __launch_bounds__(128) fsmn_gate_hysteresis_windows_kernel(
+    const float* __restrict__ p_sil, const float* __restrict__ power, int W, int T, float one_minus_thr, float ratio,
+    int look_backward, double speaking_score, double silence_score, uint8_t* __restrict__ score_out, float* __restrict__ noisy_out,
+    float* __restrict__ noise_in_out, uint8_t* __restrict__ silence_state, int32_t* __restrict__ n_saved,
+    uint8_t* __restrict__ saved, int64_t ld_saved, float* __restrict__ noise_avg, float snr) {
+  extern __shared__ uint8_t s_flags[];       // [T]
+  __shared__ float s_sum[128];
+  __shared__ int s_cnt[128];
+  __shared__ float s_noise;
+  const int64_t s = blockIdx.x;
+  bool silence = silence_state[s] != 0;
+  int n = n_saved[s];
+  if (threadIdx.x == 0) s_noise = noise_avg[s];
+  __syncthreads();
+  for (int w = 0; w < W; ++w) {
+    const float noise = s_noise;
+    const int64_t base = (s * W + w) * (int64_t)T;
+    float sum = 0.f;
+    int cnt = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const float p = p_sil[base + t];
+      const float sc = p + (ratio > 1.0f ? powf(p, ratio) : (ratio < 1.0f ? 1.0f : p));
+      const float pw = power[base + t];
+      const bool cond = (sc <= one_minus_thr) && (pw >= noise);
+      s_flags[t] = cond ? 1 : 0;
+      if (score_out) score_out[base + t] = cond ? 1 : 0;
+      if (!cond) { sum += pw; ++cnt; }
+    }
+    s_sum[threadIdx.x] = sum;
+    s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) {
+        s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+        s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float nd = s_sum[0] / (float)s_cnt[0];      // 0/0 = NaN like torch.mean of nothing
+      if (noisy_out) noisy_out[s * W + w] = nd;
+      if (noise_in_out) noise_in_out[s * W + w] = noise;
+      hysteresis_chunk(s_flags, nullptr, 0, T, look_backward, speaking_score, silence_score, w == W - 1, silence, n,
+                       saved + s * ld_saved, ld_saved);
+      if (nd > 0.0f) s_noise = 0.5f * ((noise + nd) + snr);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    silence_state[s] = silence ? 1 : 0;
+    n_saved[s] = n;
+    noise_avg[s] = s_noise;
   }
 }
 
@@ -265,6 +330,26 @@ extern "C" int vadx_lookahead_hysteresis(const void* d_in, int mode, int64_t ld_
       d_in, mode, ld_in, n_streams, n_frames, look_backward, speaking_score, silence_score, is_final, d_silence_state,
       d_n_saved, d_saved, ld_saved, d_noise_avg, d_noisy_dB, snr_threshold);
   return after_launch("vadx_lookahead_hysteresis");
+}
+
+extern "C" int vadx_fsmn_gate_hysteresis_windows(const float* d_p_sil, const float* d_power_dB, int64_t n_streams, int n_windows,
+                                                 int n_frames, float one_minus_speech_threshold, float speech_2_noise_ratio,
+                                                 int look_backward, double speaking_score, double silence_score,
+                                                 uint8_t* d_score, float* d_noisy_dB, float* d_noise_in,
+                                                 uint8_t* d_silence_state, int32_t* d_n_saved, uint8_t* d_saved,
+                                                 int64_t ld_saved, float* d_noise_avg, float snr_threshold, void* stream) {
+  StageTimer _timer(VADX_STAGE_POSTPROC, (cudaStream_t)stream, "fsmn_gate_hysteresis_windows_kernel",
+                    9.0 * n_streams * n_windows * n_frames);
+  VADX_REQUIRE(d_p_sil && d_power_dB && d_silence_state && d_n_saved && d_saved && d_noise_avg,
+               "vadx_fsmn_gate_hysteresis_windows: null pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_windows >= 1 && n_frames >= 1 && look_backward >= 0 && look_backward <= n_frames &&
+                   ld_saved >= 0 && n_frames <= 48 * 1024,
+               "vadx_fsmn_gate_hysteresis_windows: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  fsmn_gate_hysteresis_windows_kernel<<<(unsigned)n_streams, 128, (size_t)n_frames, (cudaStream_t)stream>>>(
+      d_p_sil, d_power_dB, n_windows, n_frames, one_minus_speech_threshold, speech_2_noise_ratio, look_backward, speaking_score,
+      silence_score, d_score, d_noisy_dB, d_noise_in, d_silence_state, d_n_saved, d_saved, ld_saved, d_noise_avg, snr_threshold);
+  return after_launch("vadx_fsmn_gate_hysteresis_windows");
 }
 
 extern "C" int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags,

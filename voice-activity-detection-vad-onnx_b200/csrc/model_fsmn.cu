@@ -104,6 +104,18 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   FsmnHP h;
   VADX_TRY(fsmn_hp(m, &h));
   const int T = h.frames(L);
+  // Whole-file mode ("input.n_windows" = W > 1): in[0] is the chunk-aligned recording [S][input.stream_stride], the call
+  // covers its W overlapping windows of L samples, "input.window_stride" apart.  Everything window-local (DC removal,
+  // framing, mel, LFR, the dense layers, frame energy) runs ONCE over S*W window rows; the FSMN caches across windows are
+  // nothing but a causal FIR over the concatenation of all windows' frames (encoder.py:78-83: cache_out = the last 19 frames
+  // of cat(cache_in, p)), so every memory block runs as S streams of W*T frames.  Only the running background level is
+  // sequential: the gate + look-ahead machine run afterwards (vadx_fsmn_gate_hysteresis_windows); this call returns
+  // P(silence) and power_dB [S][W][T] (outputs 2, 3) and leaves outputs 0, 1 untouched.
+  const int W = std::max(1, (int)m->scalar("input.n_windows", 1.0));
+  const int64_t wstride = (int64_t)m->scalar("input.window_stride", (double)L);
+  const int64_t sstride = (int64_t)m->scalar("input.stream_stride", (double)(L + (W - 1) * wstride));
+  const int64_t S_streams = S;
+  S = S * W;                                                     // window rows from here on
   const int64_t rows = S * T;
   const int64_t Lp = round_up(h.pad_left() + L + h.n_taps(), 4);
   const int wide = std::max(std::max(h.affine, h.linear), std::max(h.out_affine, h.out_dim));
@@ -129,7 +141,12 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   }
   VADX_REQUIRE(L >= h.n_fft, "fsmn: chunk of %lld samples is shorter than the %d-sample energy frame", (long long)L,
                h.n_fft);
-  VADX_REQUIRE(in[1] && out[1] && state, "fsmn: noise_average_dB input, noisy_dB output and cache state are required");
+  VADX_REQUIRE(state && (W > 1 ? (out[2] && out[3]) : (in[1] && out[1])),
+               W > 1 ? "fsmn: whole-file mode needs the P(silence) and power_dB outputs and the cache state"
+                     : "fsmn: noise_average_dB input, noisy_dB output and cache state are required");
+  VADX_REQUIRE(W == 1 || (wstride >= 1 && sstride >= L + (int64_t)(W - 1) * wstride),
+               "fsmn: input.stream_stride %lld does not hold %d windows of %lld samples, %lld apart", (long long)sstride, W,
+               (long long)L, (long long)wstride);
   for (int i = 0; i < 2 * h.layers; ++i) VADX_REQUIRE(state[i], "fsmn: cache state %d is null", i);
   const float* noise_avg = static_cast<const float*>(in[1]);
   uint8_t* score = static_cast<uint8_t*>(out[0]);
@@ -143,9 +160,15 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
   const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
 
-  VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,
-                           h.pad_left(), sig, Lp, st));
-  const uint8_t* stft_img = use_tc ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
+  if (W == 1) {
+    VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,
+                             h.pad_left(), sig, Lp, st));
+  } else {
+    for (int64_t s = 0; s < S_streams; ++s)      // the W windows of one stream are rows `wstride` samples apart
+      VADX_TRY(vadx_prep_audio(static_cast<const int16_t*>(in[0]) + s * sstride, VADX_DT_I16, W, L, wstride, 1.0f, 1,
+                               preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph, h.pad_left(), sig + s * W * Lp, Lp, st));
+  }
+  const uint8_t* stft_img = (use_tc && W == 1) ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
   if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
     // framed DFT on the tensor cores straight from the int16 samples; the mean is removed in the epilogue
     const std::string key = "frontend.dc#" + std::to_string((long long)L);
@@ -200,7 +223,7 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
     std::string ab = p + "affine.linear.bias";
     VADX_TRY(lin(hcur, ldw, h.linear, p + "linear.linear.weight", nullptr, bufP, h.proj, h.proj, VADX_ACT_NONE));
     VADX_TRY(vadx_fsmn_memory_f32(bufP, h.proj, m->d<float>(p + "fsmn_block.conv_left.weight"), h.lorder, h.lstride,
-                                  nullptr, 0, 1, nullptr, 0, bufM, h.proj, S, T, h.proj,
+                                  nullptr, 0, 1, nullptr, 0, bufM, h.proj, S_streams, W * T, h.proj,
                                   halo > 0 ? static_cast<const float*>(state[i]) : nullptr,
                                   halo > 0 ? static_cast<float*>(state[h.layers + i]) : nullptr, st));
     VADX_TRY(lin(bufM, h.proj, h.proj, p + "affine.linear.weight", ab.c_str(), hnext, ldw, h.linear, VADX_ACT_RELU));
@@ -215,6 +238,7 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   const float inv_ref = (float)(1.0 / (std::sqrt((double)L) * 2e-5));
   VADX_TRY(vadx_frame_energy_log10_f32(sig, Lp, h.pad_left(), S, h.n_fft, h.hop, n_energy, T, inv_ref, 0.00002f,
                                        power_db, st));
+  if (W > 1) return VADX_OK;      // the gate needs the running background level: vadx_fsmn_gate_hysteresis_windows
   VADX_TRY(vadx_fsmn_gate(p_sil, power_db, noise_avg, thr, ratio, S, T, score, noisy, st));
   return VADX_OK;
 }

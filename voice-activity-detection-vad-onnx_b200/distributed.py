@@ -109,20 +109,36 @@ def _cpulist(text: str):
 
 
 def local_numa_cpus(device_index: int):
-    """CPU cores of the NUMA node the GPU hangs off (sysfs through the PCI bus id NVML / torch report); None when the
-    platform does not say (single-socket boxes report node -1)."""
+    """CPU cores next to the GPU: NVML's ideal-affinity mask for the device (the driver's own topology answer), else the
+    sysfs NUMA node of its PCI function; None when the platform does not say (single-socket boxes report node -1)."""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
-        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
-        dev = torch.cuda.get_device_properties(device_index).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        if cpus and len(cpus) < n_cpu:
+            return cpus
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/" + bus.lower()[-12:]
         node = int(open(os.path.join(path, "numa_node")).read().strip())
-        if node < 0:
-            return None
-        return _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) or None
+        if node >= 0:
+            return _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) or None
     except Exception:
-        return None
+        pass
+    return None
+
+
+def _physical_index(device_index: int) -> int:
+    """NVML enumerates every GPU of the box; CUDA_VISIBLE_DEVICES may renumber them for this process."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if device_index < len(ids) and ids[device_index].isdigit():
+            return int(ids[device_index])
+    return device_index
 
 
 def bind_to_local_numa_node(device_index: int) -> dict:

@@ -46,13 +46,19 @@ def look_backward_frames(look_backward_s: float) -> int:
 def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: float = LOOK_BACKWARD,
                 one_minus_speech_threshold: float = ONE_MINUS_SPEECH_THRESHOLD, snr_threshold_db: float = SNR_THRESHOLD,
                 noise_init_db: float = BACKGROUND_NOISE_dB_INIT, speaking_score: float = SPEAKING_SCORE,
-                silence_score: float = SILENCE_SCORE, keep_trace: bool = False, stream=None, graph: bool = False):
+                silence_score: float = SILENCE_SCORE, keep_trace: bool = False, stream=None, graph: bool = False,
+                whole: bool = False):
     """aligned: CUDA int16 [S, n] (already chunk-aligned, see audio_io.align_overlapping).
     -> (HysteresisState, trace) with every decision of every stream on the device.
+    whole=True computes ALL windows of the recordings in one pass (FsmnSession.run_windows: two launches-worth of work
+    instead of one graph per window; the only sequential part, the running background level, is one small kernel).
     graph=True captures one window (forward + hysteresis + cache hand-over, ~30 kernels) into a CUDA
     graph and replays it per window: the per-window cost drops from ~30 launches to one, which is
     what matters for few streams and short chunks (the reference's 512-sample configuration)."""
     import torch
+    if whole:
+        return _run_streams_whole(session, aligned, stride, look_backward_s, one_minus_speech_threshold, snr_threshold_db,
+                                  noise_init_db, speaking_score, silence_score, keep_trace, stream)
     if graph and not keep_trace:
         return _run_streams_graph(session, aligned, stride, look_backward_s, one_minus_speech_threshold,
                                   snr_threshold_db, noise_init_db, speaking_score, silence_score), []
@@ -75,6 +81,24 @@ def run_streams(session: FsmnSession, aligned, stride: int, look_backward_s: flo
                                 noisy_dB=noisy, snr_threshold=snr, stream=stream)
         if keep_trace:
             trace.append((score, p_sil, power, noise_in, noisy))
+    return state, trace
+
+
+def _run_streams_whole(session, aligned, stride, look_backward_s, thr, snr_threshold_db, noise_init_db, speaking_score,
+                       silence_score, keep_trace, stream):
+    S, n = aligned.shape
+    L, T = session.chunk_len, session.T
+    lb = look_backward_frames(look_backward_s)
+    n_windows = (n - L) // stride + 1
+    state = PP.HysteresisState(S, n_windows * (T - lb) + lb, aligned.device,
+                               noise_init=float(np.float32(noise_init_db + snr_threshold_db) * np.float32(0.1)))
+    p_sil, power, _caches = session.run_windows(aligned, stride, session.new_caches(S, aligned.device), stream)
+    score, noisy, noise_in = PP.fsmn_gate_hysteresis_windows(p_sil, power, state, lb, speaking_score, silence_score, thr,
+                                                             session.cfg.speech_2_noise_ratio, snr_threshold_db * 0.1,
+                                                             keep_trace=keep_trace, stream=stream)
+    trace = []
+    if keep_trace:
+        trace = [(score[:, w], p_sil[:, w], power[:, w], noise_in[:, w], noisy[:, w]) for w in range(n_windows)]
     return state, trace
 
 
@@ -149,8 +173,9 @@ def _run_streams_graph(session, aligned, stride, look_backward_s, thr, snr_thres
 def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD, rng=None,
             save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None,
             fusion_threshold: float = FUSION_THRESHOLD, min_speech_duration: float = MIN_SPEECH_DURATION,
-            normalize: bool = True, keep_trace: bool = False, graph: bool = False) -> FsmnResult:
-    """One stream, the reference's behaviour: `audio` is a wav path or an int16/float array."""
+            normalize: bool = True, keep_trace: bool = False, graph: bool = False, whole: bool = False) -> FsmnResult:
+    """One stream, the reference's behaviour: `audio` is a wav path or an int16/float array.
+    whole=True: all windows in one pass (see run_streams); graph=True: one CUDA-graph replay per window."""
     import torch
     if isinstance(audio, str):
         audio = audio_io.load_wav_int16(audio, SAMPLE_RATE)
@@ -158,7 +183,7 @@ def run_vad(audio, session: FsmnSession, look_backward_s: float = LOOK_BACKWARD,
     lb = look_backward_frames(look_backward_s)
     aligned, stride, _n = audio_io.align_overlapping(a16, session.chunk_len, lb, OUTPUT_FRAME_LENGTH, rng)
     d = torch.from_numpy(aligned).cuda().unsqueeze(0)
-    state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace, graph=graph)
+    state, trace = run_streams(session, d, stride, look_backward_s, keep_trace=keep_trace, graph=graph, whole=whole)
     cnt, seg = state.segments()
     n_flags = int(state.n_saved[0].item())
     pairs = PP.take_segments(cnt, seg, 0)

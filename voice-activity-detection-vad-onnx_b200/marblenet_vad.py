@@ -46,8 +46,27 @@ def run_vad_clips(session: MarbleNetSession, clips, post: PP.FramePostConfig = P
     return probs, dec, cnt, seg
 
 
+def run_vad_windows(session: MarbleNetSession, windows, post: PP.FramePostConfig = POST_DEFAULT, stream=None):
+    """windows: CUDA int16 [S, n_windows, L] -- every stream's recording cut into non-overlapping windows of L samples
+    (audio_io.align_non_overlapping; the reference's static-axis mode and its split of recordings longer than one hour,
+    :130-147).  All S * n_windows windows go through the network as ONE batch; each window contributes its signal_len
+    valid frames, the per-stream concatenation (:358-378) is post-processed on the device.
+    -> (probs [S, n_windows * (T'-1)], decisions, seg_count, segments)."""
+    S, n_win, L = windows.shape
+    scores = session.run_batch(windows.reshape(S * n_win, L), stream=stream)        # [2, S*n_win, T']
+    n = scores.shape[2] - 1                                                         # signal_len = T' - 1 (:366-373)
+    probs = scores[1, :, :n].reshape(S, n_win * n)
+    dec, cnt, seg = PP.postprocess_frames(probs, post, None, stream=stream)
+    return probs, dec, cnt, seg
+
+
 def run_vad(audio, session: MarbleNetSession, post: PP.FramePostConfig = POST_DEFAULT, normalize: bool = False,
-            save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None) -> VadResult:
+            save_timestamps_second: str | None = None, save_timestamps_indices: str | None = None,
+            input_audio_length: int | None = None, rng=None) -> VadResult:
+    """One recording, the reference's behaviour (:121-147, :355-403).  input_audio_length = the export's static audio axis
+    (the reference reads it from _inputs_meta[0].shape[-1]); None = the dynamic axis: one window of min(one hour, the
+    recording).  Longer recordings are cut into non-overlapping windows, the last one padded with RMS-matched noise (`rng`
+    makes the padding reproducible), all windows run as one batch and their valid frames are concatenated."""
     import torch
     if isinstance(audio, str):
         audio = audio_io.load_wav_int16(audio, IN_SAMPLE_RATE)
@@ -55,10 +74,13 @@ def run_vad(audio, session: MarbleNetSession, post: PP.FramePostConfig = POST_DE
     if normalize:
         audio = normalise_audio(audio)
     audio_len = len(audio)
-    if audio_len > IN_SAMPLE_RATE * 3600:
-        raise ValueError("clips longer than one hour must be windowed by the caller (the reference pads with noise)")
-    d = torch.from_numpy(audio).cuda().unsqueeze(0)
-    probs, dec, cnt, seg = run_vad_clips(session, d, post)
+    L = int(input_audio_length) if input_audio_length else min(IN_SAMPLE_RATE * 3600, audio_len)
+    if audio_len == L:
+        d = torch.from_numpy(audio).cuda().unsqueeze(0)
+        probs, dec, cnt, seg = run_vad_clips(session, d, post)
+    else:
+        windows, _ = audio_io.align_non_overlapping(audio, L, rng)
+        probs, dec, cnt, seg = run_vad_windows(session, torch.from_numpy(windows).cuda().unsqueeze(0), post)
     n = probs.shape[1]
     pairs = PP.take_segments(cnt, seg, 0)
     ts = PP.segments_to_seconds(pairs, n, post, audio_len / IN_SAMPLE_RATE)

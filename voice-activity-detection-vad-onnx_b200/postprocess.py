@@ -114,6 +114,31 @@ def lookahead_hysteresis(values, state, look_backward: int, speaking_score: floa
         lib.ptr(noisy_dB), float(snr_threshold), lib.stream_ptr(stream)))
 
 
+def fsmn_gate_hysteresis_windows(p_silence, power_dB, state, look_backward: int, speaking_score: float, silence_score: float,
+                                 one_minus_speech_threshold: float, speech_2_noise_ratio: float, snr_threshold: float,
+                                 keep_trace: bool = False, stream=None):
+    """Whole-file twin of (vadx_fsmn_gate + lookahead_hysteresis) x W windows in ONE launch: p_silence / power_dB CUDA fp32
+    [S, W, T]; per stream the windows are walked in order because the gate compares against the running background level
+    (FSMN/Inference_FSMN_VAD_ONNX.py:177-234).  state: HysteresisState (updated in place).  keep_trace -> (score u8 [S,W,T],
+    noisy_dB [S,W], noise_in [S,W])."""
+    import torch
+    if not (p_silence.is_cuda and p_silence.dtype == torch.float32 and p_silence.dim() == 3 and p_silence.is_contiguous()
+            and power_dB.shape == p_silence.shape and power_dB.dtype == torch.float32 and power_dB.is_contiguous()):
+        raise ValueError("fsmn_gate_hysteresis_windows: p_silence / power_dB must be contiguous CUDA fp32 [S, W, T]")
+    S, Wn, T = p_silence.shape
+    score = noisy = noise_in = None
+    if keep_trace:
+        score = torch.empty((S, Wn, T), dtype=torch.uint8, device=p_silence.device)
+        noisy = torch.empty((S, Wn), dtype=torch.float32, device=p_silence.device)
+        noise_in = torch.empty((S, Wn), dtype=torch.float32, device=p_silence.device)
+    lib.check(lib.load().vadx_fsmn_gate_hysteresis_windows(
+        p_silence.data_ptr(), power_dB.data_ptr(), S, Wn, T, float(one_minus_speech_threshold), float(speech_2_noise_ratio),
+        int(look_backward), float(speaking_score), float(silence_score), lib.ptr(score), lib.ptr(noisy), lib.ptr(noise_in),
+        state.silence.data_ptr(), state.n_saved.data_ptr(), state.saved.data_ptr(), state.saved.shape[1],
+        state.noise_avg.data_ptr(), float(snr_threshold), lib.stream_ptr(stream)))
+    return score, noisy, noise_in
+
+
 class HysteresisState:
     """Device-resident per-stream state of the look-ahead machine: current silence flag, number of
     decisions emitted, the decisions themselves (1 = silence) and the running background level."""

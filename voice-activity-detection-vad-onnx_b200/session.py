@@ -244,6 +244,42 @@ class FireRedStreamSession(FireRedSession):
         self._e.forward([audio], [out], [caches_in, caches_out], S, L, stream)
         return out, caches_out
 
+    def run_windows(self, aligned, stride: int, caches, stream=None):
+        """Whole-file mode: aligned cuda int16 [S, n] (chunk-aligned recordings, audio_io.align_overlapping), windows of
+        chunk_len samples `stride` apart.  ONE forward covers all W = (n - chunk_len) // stride + 1 windows of every stream
+        (the caches across windows are a causal FIR over the concatenated frames, see csrc/model_fsmn.cu).
+        -> (p_silence [S, W, T], power_dB [S, W, T], new_caches); the gate and the look-ahead machine, which depend on the
+        running background level, follow in postprocess.fsmn_gate_hysteresis_windows."""
+        import torch
+        if not (torch.is_tensor(aligned) and aligned.is_cuda and aligned.dtype == torch.int16 and aligned.dim() == 2
+                and aligned.is_contiguous()):
+            raise ValueError("run_windows: aligned must be a contiguous CUDA int16 tensor [S, n]")
+        S, n = aligned.shape
+        L = self.chunk_len
+        if n < L or stride < 1:
+            raise ValueError(f"run_windows: recordings of {n} samples are shorter than one {L}-sample window")
+        Wn = (n - L) // stride + 1
+        key = (Wn, int(stride), int(n))
+        if getattr(self, "_win_key", None) != key:
+            self._e.set_scalar("input.n_windows", float(Wn))
+            self._e.set_scalar("input.window_stride", float(stride))
+            self._e.set_scalar("input.stream_stride", float(n))
+            self._win_key = key
+        dev = aligned.device
+        p_sil = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        power = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        new = [torch.empty_like(c) for c in caches]
+        try:
+            self._e.forward([aligned, None], [p_sil, None, p_sil, power], list(caches) + new, S, L, stream)
+        finally:
+            pass
+        return p_sil, power, new
+
+    def _leave_window_mode(self):
+        if getattr(self, "_win_key", None) is not None:
+            self._e.set_scalar("input.n_windows", 1.0)
+            self._win_key = None
+
     def run(self, output_names, input_feed: dict):
         import torch
         names = [o.name for o in self._outputs_meta]
@@ -354,6 +390,7 @@ class FsmnSession:
         if float(one_minus_speech_threshold) != self._thr:
             self._thr = float(one_minus_speech_threshold)
             self._e.set_scalar("one_minus_speech_threshold", self._thr)
+        self._leave_window_mode()
         dev = audio.device
         score = torch.empty((S, self.T), dtype=torch.uint8, device=dev)
         noisy = torch.empty((S,), dtype=torch.float32, device=dev)
@@ -362,6 +399,42 @@ class FsmnSession:
         new = [torch.empty_like(c) for c in caches]
         self._e.forward([audio, noise_average_dB], [score, noisy, p_sil, power], list(caches) + new, S, L, stream)
         return score, new, noisy, p_sil, power
+
+    def run_windows(self, aligned, stride: int, caches, stream=None):
+        """Whole-file mode: aligned cuda int16 [S, n] (chunk-aligned recordings, audio_io.align_overlapping), windows of
+        chunk_len samples `stride` apart.  ONE forward covers all W = (n - chunk_len) // stride + 1 windows of every stream
+        (the caches across windows are a causal FIR over the concatenated frames, see csrc/model_fsmn.cu).
+        -> (p_silence [S, W, T], power_dB [S, W, T], new_caches); the gate and the look-ahead machine, which depend on the
+        running background level, follow in postprocess.fsmn_gate_hysteresis_windows."""
+        import torch
+        if not (torch.is_tensor(aligned) and aligned.is_cuda and aligned.dtype == torch.int16 and aligned.dim() == 2
+                and aligned.is_contiguous()):
+            raise ValueError("run_windows: aligned must be a contiguous CUDA int16 tensor [S, n]")
+        S, n = aligned.shape
+        L = self.chunk_len
+        if n < L or stride < 1:
+            raise ValueError(f"run_windows: recordings of {n} samples are shorter than one {L}-sample window")
+        Wn = (n - L) // stride + 1
+        key = (Wn, int(stride), int(n))
+        if getattr(self, "_win_key", None) != key:
+            self._e.set_scalar("input.n_windows", float(Wn))
+            self._e.set_scalar("input.window_stride", float(stride))
+            self._e.set_scalar("input.stream_stride", float(n))
+            self._win_key = key
+        dev = aligned.device
+        p_sil = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        power = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        new = [torch.empty_like(c) for c in caches]
+        try:
+            self._e.forward([aligned, None], [p_sil, None, p_sil, power], list(caches) + new, S, L, stream)
+        finally:
+            pass
+        return p_sil, power, new
+
+    def _leave_window_mode(self):
+        if getattr(self, "_win_key", None) is not None:
+            self._e.set_scalar("input.n_windows", 1.0)
+            self._win_key = None
 
     def run(self, output_names, input_feed: dict):
         import torch
@@ -470,6 +543,42 @@ class MarbleNetSession:
             self._e.forward([audio[s0:s1]], [part[0], part[1]], [], s1 - s0, L, stream)
             out[:, s0:s1] = part
         return out
+
+    def run_windows(self, aligned, stride: int, caches, stream=None):
+        """Whole-file mode: aligned cuda int16 [S, n] (chunk-aligned recordings, audio_io.align_overlapping), windows of
+        chunk_len samples `stride` apart.  ONE forward covers all W = (n - chunk_len) // stride + 1 windows of every stream
+        (the caches across windows are a causal FIR over the concatenated frames, see csrc/model_fsmn.cu).
+        -> (p_silence [S, W, T], power_dB [S, W, T], new_caches); the gate and the look-ahead machine, which depend on the
+        running background level, follow in postprocess.fsmn_gate_hysteresis_windows."""
+        import torch
+        if not (torch.is_tensor(aligned) and aligned.is_cuda and aligned.dtype == torch.int16 and aligned.dim() == 2
+                and aligned.is_contiguous()):
+            raise ValueError("run_windows: aligned must be a contiguous CUDA int16 tensor [S, n]")
+        S, n = aligned.shape
+        L = self.chunk_len
+        if n < L or stride < 1:
+            raise ValueError(f"run_windows: recordings of {n} samples are shorter than one {L}-sample window")
+        Wn = (n - L) // stride + 1
+        key = (Wn, int(stride), int(n))
+        if getattr(self, "_win_key", None) != key:
+            self._e.set_scalar("input.n_windows", float(Wn))
+            self._e.set_scalar("input.window_stride", float(stride))
+            self._e.set_scalar("input.stream_stride", float(n))
+            self._win_key = key
+        dev = aligned.device
+        p_sil = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        power = torch.empty((S, Wn, self.T), dtype=torch.float32, device=dev)
+        new = [torch.empty_like(c) for c in caches]
+        try:
+            self._e.forward([aligned, None], [p_sil, None, p_sil, power], list(caches) + new, S, L, stream)
+        finally:
+            pass
+        return p_sil, power, new
+
+    def _leave_window_mode(self):
+        if getattr(self, "_win_key", None) is not None:
+            self._e.set_scalar("input.n_windows", 1.0)
+            self._win_key = None
 
     def run(self, output_names, input_feed: dict):
         import torch
