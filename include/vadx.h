@@ -98,7 +98,8 @@ int vadx_profile_collect_kernels(vadx_kernel_stat* out, int capacity, int* n_out
  * ------------------------------------------------------------------------------------------ */
 
 /* a2 -- cast / scale / DC removal / pre-emphasis / zero centre-pad, one pass.
- * d_audio [S][in_stride] (int16 or fp32) -> d_out [S][out_stride] fp32 with
+ * d_audio [S][in_stride] (int16 or fp32; in_stride < n_samples = overlapping windows of one recording) -> d_out
+ * [S][out_stride] fp32 with
  * out[s][pad_left + n] = y[n], zeros in [0,pad_left) and [pad_left+L, out_stride).
  * remove_dc: subtract the mean over the L samples of the stream's chunk first
  * (FSMN/Export_FSMN_VAD.py:77). */

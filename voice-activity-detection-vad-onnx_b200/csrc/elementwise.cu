@@ -315,7 +315,8 @@ extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_stre
   StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "prep_audio_kernel", n_streams * (double)n_samples * (in_dtype == VADX_DT_I16 ? 2.0 : 4.0) + 4.0 * n_streams * out_stride);
   VADX_REQUIRE(d_audio && d_out, "vadx_prep_audio: null pointer");
   VADX_REQUIRE(in_dtype == VADX_DT_I16 || in_dtype == VADX_DT_F32, "vadx_prep_audio: dtype %d", in_dtype);
-  VADX_REQUIRE(n_streams >= 0 && n_samples > 0 && in_stride >= n_samples && pad_left >= 0 &&
+  // in_stride < n_samples is allowed: the rows are then OVERLAPPING windows of one recording (the input is only read)
+  VADX_REQUIRE(n_streams >= 0 && n_samples > 0 && in_stride >= 1 && pad_left >= 0 &&
                    out_stride >= pad_left + n_samples,
                "vadx_prep_audio: bad shape S=%lld L=%lld in_stride=%lld pad_left=%lld out_stride=%lld",
                (long long)n_streams, (long long)n_samples, (long long)in_stride, (long long)pad_left,
