@@ -519,6 +519,20 @@ def run_vadx(args):
     ms_e2e = timed(step_e2e, args.steps, W_)
     if rank == 0:
         sampler.stop()
+    # concurrent pinned-H2D ceiling of this box at this rank count (tools/h2d_microbench.py inlined): the end-to-end arm moves
+    # h2d_bytes per rank per step through it, so max(compute, copy at the ceiling) is its floor
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(pipe.copy_stream):
+        c0.record(pipe.copy_stream)
+        for i in range(8):
+            pipe.d_in[i % 2].copy_(host_batches[i % 2].view(S, CHUNKS_PER_STREAM, CHUNK), non_blocking=True)
+        c1.record(pipe.copy_stream)
+    barrier()
+    h2d_gbs = torch.tensor([8.0 * pipe.h2d_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
+    h2d_gbs = float(h2d_gbs.item())
     segs_found = int(e2e_state["last"][0].sum().item()) if e2e_state["last"] is not None else 0
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes      # d2h: rank 0 reads the gathered global result back
     families = None
@@ -610,6 +624,10 @@ def run_vadx(args):
                         "api": "vadx.firered_vad.HostBatchPipeline.run(pinned int16 batch): H2D of batch i+1 overlaps compute of batch i"
                                + ("; per-step all_gather of seg_count/segments over NCCL (vadx.distributed.gather_segments), rank 0 reads the global result back" if world > 1 else ""),
                         "numa_bind": numa,
+                        "h2d_ceiling": {"pinned_gbs_per_rank_min": h2d_gbs, "ranks_copying_concurrently": world,
+                                        "copy_floor_ms_per_step": 1e3 * h2d_bytes / (h2d_gbs * 1e9),
+                                        "e2e_floor_ms_per_step": max(1e3 * h2d_bytes / (h2d_gbs * 1e9), ms_total / args.steps),
+                                        "e2e_frac_of_floor": max(1e3 * h2d_bytes / (h2d_gbs * 1e9), ms_total / args.steps) / (ms_e2e / args.steps)},
                         "ms_per_step": ms_e2e / args.steps, "segments_found_last_step": segs_found},
                 "gpu_launches": int(launches),
                 "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
