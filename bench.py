@@ -464,17 +464,6 @@ def run_vadx(args):
         return firered_vad.run_vad_streams(sess, d_audio.view(S, CHUNKS_PER_STREAM, CHUNK), lengths, post,
                                            n_valid=n_valid)
 
-    # multi-GPU: the final gather of seg_count / segments (the path's only collective) is INSIDE the end-to-end region
-    pipe = firered_vad.HostBatchPipeline(sess, S, CHUNKS_PER_STREAM, post, dev, gather=world > 1)
-    pinned2 = torch.from_numpy(np.roll(host, 1, axis=0).copy()).pin_memory()   # batches alternate between two host buffers
-    host_batches = [pinned, pinned2]
-    e2e_state = {"i": 0, "last": None}
-
-    def step_e2e():
-        i = e2e_state["i"]
-        e2e_state["i"] = i + 1
-        e2e_state["last"] = pipe.run(host_batches[i % 2], host_batches[(i + 1) % 2])
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -516,6 +505,34 @@ def run_vadx(args):
     kernel_records = lib.profile_collect_kernels()
     lib.profile_enable(False)
     # ---- end to end through the public API with host buffers
+    # multi-GPU: the final gather of seg_count / segments (the path's only collective) is INSIDE the end-to-end region.
+    # The host-fed arm is bound by each GPU's pinned host->device rate, which is NOT the same for all GPUs of the box (PCIe
+    # switch sharing: 23 vs 35 GB/s with eight ranks copying, profiles/r02_h2d_ceiling.json), so the SAME total number of
+    # streams is split in proportion to the rate each rank measures at start-up, capped by the rate its compute consumes
+    # (vadx.distributed.weighted_blocks); the device-resident `value` keeps equal blocks.
+    e2e_sizes, h2d_rates = None, None
+    S_e2e = S
+    if world > 1 and not os.environ.get("VADX_BENCH_EQUAL_E2E_BLOCKS"):
+        h2d_rates = D.measure_h2d_rates(dev)
+        # what this GPU's compute consumes, from the device-resident timing just taken (3 % headroom for the copy traffic)
+        compute_gbs = 0.97 * (B * CHUNK * 2) / (ms_total / args.steps * 1e-3) / 1e9
+        e2e_sizes = D.weighted_blocks(world * S, [min(r, compute_gbs) for r in h2d_rates])
+        S_e2e = e2e_sizes[rank]
+    pipe = firered_vad.HostBatchPipeline(sess, S_e2e, CHUNKS_PER_STREAM, post, dev, gather=world > 1, gather_sizes=e2e_sizes)
+    if S_e2e == S:
+        host_e2e = host
+    else:
+        host_e2e = synth.synth_chunks_fast(S_e2e * CHUNKS_PER_STREAM, CHUNK, seed=4321 + rank)
+        pinned = torch.from_numpy(host_e2e).pin_memory()
+    pinned2 = torch.from_numpy(np.roll(host_e2e, 1, axis=0).copy()).pin_memory()   # batches alternate between two host buffers
+    host_batches = [pinned, pinned2]
+    e2e_state = {"i": 0, "last": None}
+
+    def step_e2e():
+        i = e2e_state["i"]
+        e2e_state["i"] = i + 1
+        e2e_state["last"] = pipe.run(host_batches[i % 2], host_batches[(i + 1) % 2])
+
     ms_e2e = timed(step_e2e, args.steps, W_)
     if rank == 0:
         sampler.stop()
@@ -526,15 +543,24 @@ def run_vadx(args):
     with torch.cuda.stream(pipe.copy_stream):
         c0.record(pipe.copy_stream)
         for i in range(8):
-            pipe.d_in[i % 2].copy_(host_batches[i % 2].view(S, CHUNKS_PER_STREAM, CHUNK), non_blocking=True)
+            pipe.d_in[i % 2].copy_(host_batches[i % 2].view(S_e2e, CHUNKS_PER_STREAM, CHUNK), non_blocking=True)
         c1.record(pipe.copy_stream)
     barrier()
-    h2d_gbs = torch.tensor([8.0 * pipe.h2d_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9], device=dev, dtype=torch.float64)
+    my_gbs = 8.0 * pipe.h2d_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    h2d_gbs = torch.tensor([my_gbs], device=dev, dtype=torch.float64)
+    copy_floor = torch.tensor([1e3 * pipe.h2d_bytes / (my_gbs * 1e9)], device=dev, dtype=torch.float64)   # ms for this rank's block
+    h2d_sum = h2d_gbs.clone()
     if world > 1:
         dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
-    h2d_gbs = float(h2d_gbs.item())
+        dist.all_reduce(h2d_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(copy_floor, op=dist.ReduceOp.MAX)
+    h2d_gbs, h2d_sum, copy_floor = float(h2d_gbs.item()), float(h2d_sum.item()), float(copy_floor.item())
     segs_found = int(e2e_state["last"][0].sum().item()) if e2e_state["last"] is not None else 0
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes      # d2h: rank 0 reads the gathered global result back
+    h2d_total = torch.tensor([float(h2d_bytes)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(h2d_total, op=dist.ReduceOp.SUM)
+    h2d_total = int(h2d_total.item())
     families = None
     if not args.no_families:
         del pipe, d_audio
@@ -619,15 +645,17 @@ def run_vadx(args):
                            "l2": "inputs (%.0f MB/step/GPU) and activations exceed the 126 MB L2" % (B * CHUNK * 2 / 1e6),
                            "sharding": "streams split across ranks, no data-path collective"},
                 "rtfx": value * 3600.0,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
                         "d2h_bytes_per_step": int(d2h_bytes),
                         "api": "vadx.firered_vad.HostBatchPipeline.run(pinned int16 batch): H2D of batch i+1 overlaps compute of batch i"
                                + ("; per-step all_gather of seg_count/segments over NCCL (vadx.distributed.gather_segments), rank 0 reads the global result back" if world > 1 else ""),
                         "numa_bind": numa,
-                        "h2d_ceiling": {"pinned_gbs_per_rank_min": h2d_gbs, "ranks_copying_concurrently": world,
-                                        "copy_floor_ms_per_step": 1e3 * h2d_bytes / (h2d_gbs * 1e9),
-                                        "e2e_floor_ms_per_step": max(1e3 * h2d_bytes / (h2d_gbs * 1e9), ms_total / args.steps),
-                                        "e2e_frac_of_floor": max(1e3 * h2d_bytes / (h2d_gbs * 1e9), ms_total / args.steps) / (ms_e2e / args.steps)},
+                        "streams_per_rank": e2e_sizes or [S] * world, "h2d_gbs_per_rank_at_startup": h2d_rates,
+                        "h2d_ceiling": {"pinned_gbs_per_rank_min": h2d_gbs, "pinned_gbs_aggregate": h2d_sum,
+                                        "ranks_copying_concurrently": world,
+                                        "copy_floor_ms_per_step": copy_floor,      # slowest rank: its block / its measured rate
+                                        "e2e_floor_ms_per_step": max(copy_floor, ms_total / args.steps),
+                                        "e2e_frac_of_floor": max(copy_floor, ms_total / args.steps) / (ms_e2e / args.steps)},
                         "ms_per_step": ms_e2e / args.steps, "segments_found_last_step": segs_found},
                 "gpu_launches": int(launches),
                 "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},

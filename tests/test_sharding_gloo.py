@@ -26,6 +26,42 @@ def _fake_results(streams):
     return cnt, seg
 
 
+def _worker_weighted(rank, world, port, sizes, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    D.init("gloo")
+    mine = list(D.block_of(sizes, rank))
+    cnt, seg = _fake_results(mine)
+    all_cnt, all_seg = D.gather_segments(cnt, seg, sizes=sizes)
+    ret[rank] = (all_cnt.tolist(), all_seg.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weighted_blocks_and_unequal_gather():
+    """Bandwidth-aware sharding: blocks proportional to per-rank rates, gathered back in global stream order."""
+    assert D.weighted_blocks(10, [1, 1]) == [5, 5]
+    assert D.weighted_blocks(4096, [23.3, 23.3, 23.3, 23.3, 35.5, 35.5, 35.5, 35.5]) == [406, 406, 406, 406, 618, 618, 618, 618]
+    assert sum(D.weighted_blocks(11, [3, 1, 0.5])) == 11 and D.weighted_blocks(11, [3, 1, 0.5])[0] == 7
+    with pytest.raises(ValueError):
+        D.weighted_blocks(5, [0, 0])
+    sizes = D.weighted_blocks(11, [3, 1, 2])
+    assert sizes == [5, 2, 4] and [list(D.block_of(sizes, r)) for r in range(3)] == [[0, 1, 2, 3, 4], [5, 6], [7, 8, 9, 10]]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_weighted, args=(3, port, sizes, ret), nprocs=3, join=True)
+    want_cnt, want_seg = _fake_results(list(range(11)))
+    for rank in range(3):
+        cnt, seg = ret[rank]
+        assert cnt == want_cnt.tolist()
+        got = np.asarray(seg, np.int32).reshape(11, MAX_SEG, 2)
+        for s_ in range(11):
+            assert np.array_equal(got[s_, :cnt[s_]], want_seg[s_, :cnt[s_]].numpy())
+
+
 def _worker(rank, world, port, n_streams, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))

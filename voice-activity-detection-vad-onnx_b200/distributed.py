@@ -31,6 +31,56 @@ def block_size(n_streams: int, world: int) -> int:
     return (n_streams + world - 1) // world
 
 
+def weighted_blocks(n_streams: int, weights) -> list:
+    """Block sizes proportional to per-rank `weights` (largest-remainder rounding; they sum to n_streams).  Used when the
+    ranks are NOT equally fast at the step that bounds them -- on an 8-GPU box the pinned host->device rate differs per GPU
+    (PCIe switch sharing: 23 vs 35 GB/s measured, profiles/r02_h2d_ceiling.json), so equal blocks leave the well-fed GPUs
+    idle while the others copy."""
+    w = [max(float(x), 0.0) for x in weights]
+    if not w or sum(w) <= 0 or n_streams < 0:
+        raise ValueError("weighted_blocks: need positive weights")
+    exact = [n_streams * x / sum(w) for x in w]
+    sizes = [int(e) for e in exact]
+    order = sorted(range(len(w)), key=lambda i: exact[i] - sizes[i], reverse=True)
+    for i in order[:n_streams - sum(sizes)]:
+        sizes[i] += 1
+    return sizes
+
+
+def block_of(sizes, rank: int) -> range:
+    """This rank's contiguous block under explicit block sizes (weighted_blocks)."""
+    lo = sum(sizes[:rank])
+    return range(lo, lo + sizes[rank])
+
+
+def measure_h2d_rates(device, mb: float = 64.0, reps: int = 6, group=None) -> list:
+    """Pinned host -> device GB/s of EVERY rank while all ranks copy at the same time (the rate that matters for a
+    host-fed pipeline).  Collective: every rank must call it.  Returns the per-rank list on every rank."""
+    import torch
+    import torch.distributed as dist
+    n = int(mb * 1e6) // 2
+    h = torch.empty((n,), dtype=torch.int16).pin_memory()
+    h.zero_()
+    d = torch.empty((n,), dtype=torch.int16, device=device)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(device)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
+        dist.barrier(group=group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    gbs = torch.tensor([2.0 * n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+    if not multi:
+        return [float(gbs.item())]
+    allv = [torch.zeros_like(gbs) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(allv, gbs, group=group)
+    return [float(v.item()) for v in allv]
+
+
 def init(backend: str | None = None):
     """Process-group setup from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
     Returns (rank, world, device).  With WORLD_SIZE == 1 no process group is created."""
@@ -53,8 +103,9 @@ def init(backend: str | None = None):
     return rank, world, dev
 
 
-def gather_segments(seg_count, segments, n_streams_total: int | None = None, group=None):
+def gather_segments(seg_count, segments, n_streams_total: int | None = None, group=None, sizes=None):
     """All ranks receive every rank's post-processor output in global stream order.
+    sizes: explicit per-rank block sizes (weighted_blocks) instead of the equal blocks of shard_streams.
 
     seg_count: int32 [S_local]; segments: int [S_local, max_segments, 2] (same max_segments and dtype on every rank; CUDA
     for nccl, CPU for gloo).  n_streams_total: the global stream count the blocks came from (shard_streams); default =
@@ -69,6 +120,22 @@ def gather_segments(seg_count, segments, n_streams_total: int | None = None, gro
         return seg_count, segments
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     S_local, max_seg = seg_count.shape[0], segments.shape[1]
+    if sizes is not None:
+        if len(sizes) != world or sizes[rank] != S_local:
+            raise ValueError(f"gather_segments: rank {rank} holds {S_local} streams, sizes say {list(sizes)}")
+        per = max(sizes)
+        cnt, seg = seg_count.contiguous(), segments.contiguous()
+        if S_local < per:
+            cnt = torch.cat([cnt, cnt.new_zeros((per - S_local,))])
+            seg = torch.cat([seg, seg.new_zeros((per - S_local, max_seg, 2))])
+        all_cnt = cnt.new_empty((world * per,))
+        all_seg = seg.new_empty((world * per, max_seg, 2))
+        dist.all_gather_into_tensor(all_cnt, cnt, group=group)
+        dist.all_gather_into_tensor(all_seg, seg, group=group)
+        if all(sz == per for sz in sizes):
+            return all_cnt, all_seg
+        keep = torch.cat([torch.arange(r * per, r * per + sizes[r], device=cnt.device) for r in range(world)])
+        return all_cnt.index_select(0, keep), all_seg.index_select(0, keep)
     if n_streams_total is None:
         n_streams_total = world * S_local
     per = block_size(n_streams_total, world)

@@ -93,7 +93,7 @@ class HostBatchPipeline:
     nothing back (run returns None there)."""
 
     def __init__(self, session: FireRedSession, n_streams: int, n_chunks: int, post: PP.FramePostConfig = POST_DEFAULT,
-                 device=None, depth: int = 2, copy_chunks: int = 4, gather: bool = False):
+                 device=None, depth: int = 2, copy_chunks: int = 4, gather: bool = False, gather_sizes=None):
         import torch
         import torch.distributed as dist
         self.session, self.post = session, post
@@ -105,12 +105,13 @@ class HostBatchPipeline:
         self.copy_chunks = max(1, min(int(copy_chunks), n_streams))
         self.gather = bool(gather) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.gather else 1
+        self.gather_sizes = list(gather_sizes) if (self.gather and gather_sizes is not None) else None   # unequal blocks per rank
         self.reads_back = (not self.gather) or dist.get_rank() == 0
         self.d_in = [torch.empty((n_streams, n_chunks, self.L), dtype=torch.int16, device=dev) for _ in range(self.depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.copied = [torch.cuda.Event() for _ in range(self.depth)]
         self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
-        S_out = n_streams * self.world
+        S_out = sum(self.gather_sizes) if self.gather_sizes else n_streams * self.world
         self.h_cnt = [torch.empty((S_out,), dtype=torch.int32).pin_memory() for _ in range(2)]
         self.h_seg = [torch.empty((S_out, self.max_seg, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
         in_sr = getattr(session, "in_sample_rate", IN_SAMPLE_RATE)
@@ -160,7 +161,7 @@ class HostBatchPipeline:
         self.consumed[b].record(main)
         if self.gather:
             from . import distributed as D
-            cnt, seg = D.gather_segments(cnt, seg)
+            cnt, seg = D.gather_segments(cnt, seg, sizes=self.gather_sizes)
             if not self.reads_back:
                 return None
         r = (self._i - 1) % 2
