@@ -278,6 +278,10 @@ int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int3
 /* a11 helpers (Silero): right reflect padding of each row (out[s][n_in + j] = x[s][n_in - 2 - j]), in-place
  * square root (power -> magnitude) and the LSTM cell update (PyTorch gate order i,f,g,o;
  * c' = sig(f)*c + sig(i)*tanh(g), h' = sig(o)*tanh(c'); d_h_relu optional = relu(h')). */
+/* (re, im)-interleaved DFT rows -> magnitudes [n_windows][n_frames][n_bins]; the input has rows_per_window rows per window
+ * of which the first n_frames are frames (the framed DFT as a dense layer over hop-strided rows, csrc/model_silero.cu). */
+int vadx_stft_mag_compact_f32(const float* d_y, int64_t ldy, int64_t n_windows, int rows_per_window, int n_frames,
+                              int n_bins, float* d_mag, void* stream);
 int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_in, int pad, float* d_out,
                             void* stream);
 int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream);

@@ -622,7 +622,9 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   StageTimer _timer(VADX_STAGE_LINEAR, (cudaStream_t)stream, d_head_out ? "linear_tc_kernel+head" : "linear_tc_kernel",
                     4.0 * n_rows * (n_in + (d_head_out ? 1 : n_out) + (d_residual ? n_out : 0)), 2.0 * n_rows * n_in * n_out);
   VADX_REQUIRE(d_x && d_wimg, "vadx_linear_tc_f32: null pointer");
-  VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
+  // ldx < n_in is allowed: the input rows then OVERLAP (hop-strided frames of a signal: the framed DFT as a dense layer);
+  // the input is only read, and the caller guarantees that the last row's n_in values are in bounds
+  VADX_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && ldx >= 1 && ldy >= n_out, "vadx_linear_tc_f32: bad shape");
   TcShape s = tc_shape(n_in, n_out);
   VADX_REQUIRE(s.ok, "vadx_linear_tc_f32: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
   VADX_REQUIRE(aligned16(d_wimg), "vadx_linear_tc_f32: weight image must be 16-byte aligned");

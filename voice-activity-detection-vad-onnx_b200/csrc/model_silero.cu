@@ -13,6 +13,7 @@ extern "C" {
 int vadx_reflect_window_f32(const float*, int64_t, int64_t, int, int, float*, void*);
 int vadx_sqrt_inplace_f32(float*, int64_t, void*);
 int vadx_lstm_cell_f32(const float*, const float*, float*, float*, float*, int64_t, int, void*);
+int vadx_stft_mag_compact_f32(const float*, int64_t, int64_t, int, int, int, float*, void*);
 }
 
 namespace {
@@ -51,6 +52,20 @@ int silero_finalize(vadx_model* m) {
   SileroHP h;
   VADX_TRY(silero_hp(m, &h));
   VADX_TRY(m->upload_raw("frontend.basis", (int64_t)h.n_fft * h.ld_basis(), VADX_DT_F32));
+  {
+    // the framed DFT as a dense tensor-core layer over the hop-strided frames of the padded window: W[2f | 2f+1][k] =
+    // basis[k][re f | im f] (column blocks, 2F = 258 > 256)
+    const float* hb = m->find("frontend.basis")->f32();
+    HostTensor t;
+    t.dtype = VADX_DT_F32;
+    t.dims = {2 * h.n_bins(), h.n_fft};
+    t.bytes.resize((size_t)2 * h.n_bins() * h.n_fft * sizeof(float));
+    float* w = reinterpret_cast<float*>(t.bytes.data());
+    for (int j = 0; j < 2 * h.n_bins(); ++j)
+      for (int k = 0; k < h.n_fft; ++k) w[(size_t)j * h.n_fft + k] = hb[(size_t)k * h.ld_basis() + j];
+    m->host["frontend.stft.weight"] = std::move(t);
+    VADX_TRY(m->upload_linear("frontend.stft.weight", 2 * h.n_bins(), h.n_fft));
+  }
   for (int i = 0; i < h.n_layers; ++i) {
     std::string p = "enc." + std::to_string(i) + ".";
     VADX_TRY(m->upload_linear(p + "weight", h.dims[i].first, h.dims[i].second));
@@ -84,6 +99,11 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
   Workspace ws(ws_ptr, ws_bytes, dry);
   float* win = ws.take<float>(rows * nwin);
   float* mag = ws.take<float>(rows * T * F + 4);
+  // tensor-core DFT: `per` hop-strided rows per window (the first T are its frames), (re, im) interleaved
+  const int per = (nwin % h.hop) == 0 ? nwin / h.hop : 0;
+  const int ld_ri = (int)round_up(2 * F, 4);
+  const bool stft_tc = per >= T && (h.hop % 8) == 0 && rows * (int64_t)T > kSkinnyMaxRows;
+  float* ri = stft_tc ? ws.take<float>(((rows - 1) * per + T) * (int64_t)ld_ri) : nullptr;
   float* bufA = ws.take<float>(rows * ldw);
   float* bufB = ws.take<float>(rows * ldw);
   float* gates = ws.take<float>(S * ldw);
@@ -112,9 +132,16 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
   for (int w = 0; w < W; ++w)
     VADX_TRY(vadx_reflect_window_f32(static_cast<const float*>(in[0]) + (int64_t)w * h.window, in_stride, S, h.n_in(),
                                      h.reflect, win + (int64_t)w * S * nwin, st));
-  VADX_TRY(vadx_stft_power_f32(win, nwin, rows, T, h.hop, h.n_fft, m->d<float>("frontend.basis"), h.ld_basis(), F, mag, F,
-                               st));
-  VADX_TRY(vadx_sqrt_inplace_f32(mag, rows * (int64_t)T * F, st));
+  if (stft_tc && tc_ok && m->scalar("derived.nsplit.frontend.stft.weight", 0.0) > 0) {
+    // frame (r, t) = row r*per + t of the [.][n_fft] matrix with row stride hop over `win`; the rows in between are junk
+    VADX_TRY(m->linear("frontend.stft.weight", win, h.hop, nullptr, nullptr, 0, ri, ld_ri, (rows - 1) * per + T, h.n_fft, 2 * F,
+                       VADX_ACT_NONE, true, st));
+    VADX_TRY(vadx_stft_mag_compact_f32(ri, ld_ri, rows, per, T, F, mag, st));
+  } else {
+    VADX_TRY(vadx_stft_power_f32(win, nwin, rows, T, h.hop, h.n_fft, m->d<float>("frontend.basis"), h.ld_basis(), F, mag, F,
+                                 st));
+    VADX_TRY(vadx_sqrt_inplace_f32(mag, rows * (int64_t)T * F, st));
+  }
   const float* cur = mag;
   int64_t ldc = (int64_t)T * F;
   float* pp[2] = {bufA, bufB};

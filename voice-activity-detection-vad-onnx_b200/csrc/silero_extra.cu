@@ -161,6 +161,34 @@ extern "C" int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream) {
   return after_launch("vadx_sqrt_inplace_f32");
 }
 
+// interleaved (re, im) rows of the framed DFT -> magnitudes, dropping the junk rows between windows: the DFT ran as a
+// dense layer over hop-strided rows, `per` rows per window of which the first T are frames (model_silero.cu)
+namespace vadx {
+__global__ void __launch_bounds__(256) stft_mag_compact_kernel(const float* __restrict__ y, int64_t ldy, int64_t n_windows,
+                                                               int per, int T, int F, float* __restrict__ mag) {
+  const int64_t total = n_windows * T * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ((int64_t)T * F);
+    const int rem = (int)(i - r * (int64_t)T * F);
+    const int t = rem / F, f = rem - t * F;
+    const float2 v = *reinterpret_cast<const float2*>(y + (r * per + t) * ldy + 2 * f);
+    mag[i] = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+  }
+}
+}  // namespace vadx
+
+extern "C" int vadx_stft_mag_compact_f32(const float* d_y, int64_t ldy, int64_t n_windows, int rows_per_window, int n_frames,
+                                         int n_bins, float* d_mag, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "stft_mag_compact_kernel", 12.0 * n_windows * n_frames * n_bins);
+  VADX_REQUIRE(d_y && d_mag && n_windows >= 0 && rows_per_window >= n_frames && n_frames >= 1 && n_bins >= 1 &&
+                   ldy >= 2 * n_bins && (ldy & 1) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 7u) == 0,
+               "vadx_stft_mag_compact_f32: bad argument");
+  if (n_windows == 0) return VADX_OK;
+  stft_mag_compact_kernel<<<grid1d(n_windows * n_frames * n_bins), 256, 0, (cudaStream_t)stream>>>(d_y, ldy, n_windows,
+                                                                                                 rows_per_window, n_frames, n_bins, d_mag);
+  return after_launch("vadx_stft_mag_compact_f32");
+}
+
 extern "C" int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, float* d_h_out, float* d_c_out,
                                   float* d_h_relu, int64_t n_streams, int hidden, void* stream) {
   StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "lstm_cell_kernel", 4.0 * n_streams * hidden * (4 + 1 + 2 + (d_h_relu ? 1 : 0)));
