@@ -284,9 +284,21 @@ int vadx_stft_mag_compact_f32(const float* d_y, int64_t ldy, int64_t n_windows, 
                               int n_bins, float* d_mag, void* stream);
 int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_in, int pad, float* d_out,
                             void* stream);
+/* all W windows of a multi-window call at once: d_out [W][S][n_in + pad], window w of stream s starts at
+ * d_x + s*in_stride + w*window_step */
+int vadx_reflect_windows_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_windows, int64_t window_step,
+                             int n_in, int pad, float* d_out, void* stream);
 int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream);
 int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, float* d_h_out, float* d_c_out, float* d_h_relu,
                        int64_t n_streams, int hidden, void* stream);
+
+/* a11 -- the LSTM recurrence of a multi-window call in ONE launch (persistent CTAs own 28 streams each and walk the
+ * windows with h, c in shared memory): d_gates_in [W][S][4H] = the input half of the gates incl. both biases, d_wt_hh the
+ * TRANSPOSED recurrent weight [H][ldw], state [2][S][H] (h ; c) in -> out (distinct), d_head_w [H] + head_bias the 1-output
+ * head on relu(h) -> d_probs [W][S].  PyTorch gate order (i, f, g, o); hidden = 128; exact fp32. */
+int vadx_silero_lstm_windows_f32(const float* d_gates_in, const float* d_wt_hh, int ldw, const float* d_state_in,
+                                 float* d_state_out, const float* d_head_w, float head_bias, float* d_probs,
+                                 int64_t n_streams, int n_windows, int hidden, void* stream);
 
 /* a16 -- the trigger / release / max-speech machine of Silero's get_speech_timestamps
  * (Silero/modeling_modified/utils_vad.py:374-462), one stream per lane: d_probs [S][ld] (one value per

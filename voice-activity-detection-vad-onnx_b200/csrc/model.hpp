@@ -118,27 +118,37 @@ struct vadx_model {
     for (int o = 0; o < n_out; ++o)
       for (int i = 0; i < n_in; ++i) wt[(size_t)i * ldw + o] = w[(size_t)o * n_in + i];
     VADX_TRY(upload(name + "#T", wt.data(), wt.size() * sizeof(float)));
+    bool placed = false;
     if (vadx_tc_supported(n_in, n_out)) {
       size_t bytes = 0;
       VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, nullptr, 0, &bytes));
       std::vector<uint8_t> img(bytes);
       VADX_TRY(vadx_pack_weight_tc(w, n_out, n_in, img.data(), img.size(), &bytes));
       VADX_TRY(upload(name + "#TC", img.data(), img.size()));
-    } else if (n_in > 256 && n_out > 8 && vadx_tc_supported(256, n_out) && vadx_tc_supported(n_in - 256, n_out)) {
-      // K too long for one stationary operand image (e.g. FSMN 400 -> 140): two images over K = [0, 256) and
-      // [256, n_in); the second launch accumulates onto the first through the residual input
-      for (int part = 0; part < 2; ++part) {
-        const int k0 = part ? 256 : 0, kn = part ? n_in - 256 : 256;
-        std::vector<float> sub((size_t)n_out * kn);
-        for (int o = 0; o < n_out; ++o)
-          for (int i = 0; i < kn; ++i) sub[(size_t)o * kn + i] = w[(size_t)o * n_in + k0 + i];
-        size_t bytes = 0;
-        VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, nullptr, 0, &bytes));
-        std::vector<uint8_t> img(bytes);
-        VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, img.data(), img.size(), &bytes));
-        VADX_TRY(upload(name + (part ? "#TC1" : "#TC0"), img.data(), img.size()));
+      placed = true;
+    } else if (n_in > 256 && n_out > 8 && n_out <= 256) {
+      // K too long for one stationary operand image (FSMN 400 -> 140, Silero 516 -> 128): equal 64-aligned K parts
+      // "#TCK<j>", each launch accumulating onto the previous one through the residual input (bias in the first part,
+      // activation in the last)
+      const int n_parts = (n_in + 255) / 256;
+      const int pk = (int)round_up((n_in + n_parts - 1) / n_parts, 64);
+      if (vadx_tc_supported(pk, n_out) && n_in - (n_parts - 1) * pk > 0) {
+        for (int part = 0; part < n_parts; ++part) {
+          const int k0 = part * pk, kn = std::min(pk, n_in - k0);
+          std::vector<float> sub((size_t)n_out * kn);
+          for (int o = 0; o < n_out; ++o)
+            for (int i = 0; i < kn; ++i) sub[(size_t)o * kn + i] = w[(size_t)o * n_in + k0 + i];
+          size_t bytes = 0;
+          VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, nullptr, 0, &bytes));
+          std::vector<uint8_t> img(bytes);
+          VADX_TRY(vadx_pack_weight_tc(sub.data(), n_out, kn, img.data(), img.size(), &bytes));
+          VADX_TRY(upload(name + "#TCK" + std::to_string(part), img.data(), img.size()));
+        }
+        scalars["derived.ksplit." + name] = pk;
+        placed = true;
       }
-    } else if (n_out > 16) {
+    }
+    if (!placed && n_out > 16) {
       // N too wide for one stationary image (more than 256 columns, or the image leaves no room for the activation
       // stages: Silero 128 -> 512, FSMN 140 -> 250): column blocks "#TCN<j>" of equal 16-aligned width, one launch per
       // block writing its slice of the output rows (the input rows are read once per block)
@@ -168,12 +178,17 @@ struct vadx_model {
     if (use_tc && n_rows > kSkinnyMaxRows) {
       if (const uint8_t* img = d<uint8_t>(name + "#TC"))
         return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, st);
-      const uint8_t* img0 = d<uint8_t>(name + "#TC0");
-      if (img0 && (act & 15) == VADX_ACT_NONE && !res) {
-        // long K split over two stationary images: y = x[:, :256] W0^T + b, then y += x[:, 256:] W1^T
-        VADX_TRY(vadx_linear_tc_f32(x, ldx, img0, bias, nullptr, 0, y, ldy, n_rows, 256, n_out, VADX_ACT_NONE, st));
-        return vadx_linear_tc_f32(x + 256, ldx, d<uint8_t>(name + "#TC1"), nullptr, y, ldy, y, ldy, n_rows, n_in - 256, n_out,
-                                  VADX_ACT_NONE, st);
+      const int pk = (int)scalar(("derived.ksplit." + name).c_str(), 0.0);
+      if (pk > 0 && !res && (act & VADX_ACT_RES_FIRST) == 0) {
+        // long K in parts: y = x[:, :pk] W0^T + b, then y += x[:, pk:2pk] W1^T ..., the activation applied by the last part
+        // on (partial sum + its own product)
+        for (int part = 0, k0 = 0; k0 < n_in; ++part, k0 += pk) {
+          const bool first = part == 0, last = k0 + pk >= n_in;
+          VADX_TRY(vadx_linear_tc_f32(x + k0, ldx, d<uint8_t>(name + "#TCK" + std::to_string(part)), first ? bias : nullptr,
+                                      first ? nullptr : y, ldy, y, ldy, n_rows, std::min(pk, n_in - k0), n_out,
+                                      last ? (act | (first ? 0 : VADX_ACT_RES_FIRST)) : VADX_ACT_NONE, st));
+        }
+        return VADX_OK;
       }
       const int bw = (int)scalar(("derived.nsplit." + name).c_str(), 0.0);
       if (bw > 0 && ((ldy & 3) == 0 || (bw & 3) == 0)) {

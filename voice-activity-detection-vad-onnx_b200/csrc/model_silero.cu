@@ -11,9 +11,12 @@
 
 extern "C" {
 int vadx_reflect_window_f32(const float*, int64_t, int64_t, int, int, float*, void*);
+int vadx_reflect_windows_f32(const float*, int64_t, int64_t, int, int64_t, int, int, float*, void*);
 int vadx_sqrt_inplace_f32(float*, int64_t, void*);
 int vadx_lstm_cell_f32(const float*, const float*, float*, float*, float*, int64_t, int, void*);
 int vadx_stft_mag_compact_f32(const float*, int64_t, int64_t, int, int, int, float*, void*);
+int vadx_silero_lstm_windows_f32(const float*, const float*, int, const float*, float*, const float*, float, float*, int64_t, int,
+                                 int, void*);
 }
 
 namespace {
@@ -76,6 +79,7 @@ int silero_finalize(vadx_model* m) {
   VADX_TRY(m->upload_linear("rnn.weight_hh", 4 * h.hidden, h.hidden));
   VADX_TRY(m->upload_raw("rnn.bias", 4 * h.hidden, VADX_DT_F32));
   VADX_TRY(m->upload_linear("head.weight", 1, h.hidden));
+  VADX_TRY(m->upload_raw("head.weight", h.hidden, VADX_DT_F32));
   VADX_TRY(m->upload_raw("head.bias", 1, VADX_DT_F32));
   return VADX_OK;
 }
@@ -129,9 +133,7 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
     return m->linear(w, x, ldx, b ? m->d<float>(b) : nullptr, res, ldr, y, ldy, n_rows, n_in, n_out, act, tc_ok, st);
   };
   // rows are ordered [window][stream] so that one window's gates are contiguous for the recurrence
-  for (int w = 0; w < W; ++w)
-    VADX_TRY(vadx_reflect_window_f32(static_cast<const float*>(in[0]) + (int64_t)w * h.window, in_stride, S, h.n_in(),
-                                     h.reflect, win + (int64_t)w * S * nwin, st));
+  VADX_TRY(vadx_reflect_windows_f32(static_cast<const float*>(in[0]), in_stride, S, W, h.window, h.n_in(), h.reflect, win, st));
   if (stft_tc && tc_ok && m->scalar("derived.nsplit.frontend.stft.weight", 0.0) > 0) {
     // frame (r, t) = row r*per + t of the [.][n_fft] matrix with row stride hop over `win`; the rows in between are junk
     VADX_TRY(m->linear("frontend.stft.weight", win, h.hop, nullptr, nullptr, 0, ri, ld_ri, (rows - 1) * per + T, h.n_fft, 2 * F,
@@ -160,6 +162,12 @@ int silero_run(vadx_model* m, bool dry, const void* const* in, void* const* out,
   // gates rows have stride ldw; the cell kernel wants them dense [S][4H]: ldw == 4H whenever 4H is the widest layer
   VADX_REQUIRE(ldw == 4 * h.hidden, "silero: 4*hidden must be the widest layer (got ld %d)", ldw);
   float* probs = static_cast<float*>(out[0]);
+  if (W > 1 && h.hidden == 128 && S > kSkinnyMaxRows && m->scalar("engine.fuse_recurrence", 1.0) != 0.0) {
+    // the whole recurrence in one launch (silero_extra.cu): state in -> W windows -> state out
+    const HostTensor* hb = m->find("head.bias");
+    return vadx_silero_lstm_windows_f32(g1, m->d<float>("rnn.weight_hh#T"), ldw, st_in, st_out, m->d<float>("head.weight"),
+                                        hb->f32()[0], probs, S, W, h.hidden, st);
+  }
   for (int w = 0; w < W; ++w) {
     const float* src = w == 0 ? st_in : tmp_state[(w - 1) & 1];
     float* dst = w == W - 1 ? st_out : tmp_state[w & 1];

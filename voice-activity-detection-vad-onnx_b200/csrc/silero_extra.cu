@@ -4,17 +4,19 @@
 
 namespace vadx {
 
-// out[s][j] = x[s][j] (j < n_in), out[s][n_in + j] = x[s][n_in - 2 - j] (j < pad): right reflect pad
+// out[w][s][j] = x[s][w*step + j] (j < n_in), out[w][s][n_in + j] = x[s][w*step + n_in - 2 - j] (j < pad): the right
+// reflect pad of window w of stream s; all W windows of a multi-window call in one launch
 __global__ void __launch_bounds__(256) reflect_window_kernel(const float* __restrict__ x, int64_t in_stride,
-                                                             int64_t n_streams, int n_in, int pad,
-                                                             float* __restrict__ out) {
+                                                             int64_t n_streams, int n_windows, int64_t window_step, int n_in,
+                                                             int pad, float* __restrict__ out) {
   const int n_out = n_in + pad;
-  const int64_t total = n_streams * n_out;
+  const int64_t total = n_streams * n_windows * n_out;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t s = i / n_out;
-    int j = (int)(i - s * n_out);
-    int src = j < n_in ? j : n_in - 2 - (j - n_in);
-    out[i] = x[s * in_stride + src];
+    const int64_t row = i / n_out;                 // row = w * n_streams + s
+    const int j = (int)(i - row * n_out);
+    const int64_t w = row / n_streams, s = row - w * n_streams;
+    const int src = j < n_in ? j : n_in - 2 - (j - n_in);
+    out[i] = x[s * in_stride + w * window_step + src];
   }
 }
 
@@ -40,6 +42,78 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict_
     c_out[i] = c;
     h_out[i] = h;
     if (h_relu) h_relu[i] = fmaxf(h, 0.f);
+  }
+}
+
+// The whole recurrence of a multi-window call in ONE launch: per window only gates = g_in[w] + h W_hh^T, the cell and the
+// 1-output head depend on the previous window, and streams are independent -- so a persistent CTA owns SB streams and
+// walks the W windows with h and c resident in shared memory (state in -> W windows -> state out), instead of three
+// launches per 32 ms window over a grid that 4096 streams cannot fill.  thread = gate column n (4H = 512 threads): the
+// recurrent product runs in exact fp32 with W_hh^T read k-row by k-row (coalesced, L2-resident: 256 KB) and h broadcast
+// from shared memory as float4; then (stream, unit) items update the cell, and each warp reduces the heads of its streams.
+template <int H, int SB>
+__global__ void __launch_bounds__(4 * H, 1) silero_lstm_windows_kernel(
+    const float* __restrict__ g_in, const float* __restrict__ wt_hh, int ldw, const float* __restrict__ state_in,
+    float* __restrict__ state_out, const float* __restrict__ head_w, float head_b, float* __restrict__ probs, int64_t S, int W) {
+  extern __shared__ float lw_sm[];
+  float* h_s = lw_sm;                 // [SB][H]
+  float* c_s = h_s + SB * H;          // [SB][H]
+  float* gt = c_s + SB * H;           // [SB][4H]
+  const int n = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * SB;
+  const int nb = (int)min((int64_t)SB, S - s0);
+  for (int i = n; i < SB * H; i += 4 * H) {
+    const int s = i / H, j = i - s * H;
+    h_s[i] = s < nb ? state_in[(s0 + s) * H + j] : 0.f;
+    c_s[i] = s < nb ? state_in[(S + s0 + s) * H + j] : 0.f;
+  }
+  float hw[H / 32];
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) hw[i] = __ldg(head_w + lane + 32 * i);
+  const float4* h4 = reinterpret_cast<const float4*>(h_s);
+  for (int w = 0; w < W; ++w) {
+    __syncthreads();
+    float acc[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) acc[s] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < H / 4; ++k4) {
+      const float w0 = __ldg(wt_hh + (size_t)(4 * k4 + 0) * ldw + n), w1 = __ldg(wt_hh + (size_t)(4 * k4 + 1) * ldw + n);
+      const float w2 = __ldg(wt_hh + (size_t)(4 * k4 + 2) * ldw + n), w3 = __ldg(wt_hh + (size_t)(4 * k4 + 3) * ldw + n);
+#pragma unroll
+      for (int s = 0; s < SB; ++s) {
+        const float4 hv = h4[s * (H / 4) + k4];
+        acc[s] = fmaf(hv.w, w3, fmaf(hv.z, w2, fmaf(hv.y, w1, fmaf(hv.x, w0, acc[s]))));
+      }
+    }
+    const float* gi = g_in + ((int64_t)w * S + s0) * (4 * H) + n;
+#pragma unroll
+    for (int s = 0; s < SB; ++s)
+      if (s < nb) gt[s * 4 * H + n] = acc[s] + gi[(int64_t)s * 4 * H];
+    __syncthreads();
+    for (int i = n; i < nb * H; i += 4 * H) {
+      const int s = i / H, j = i - s * H;
+      const float* g = gt + s * 4 * H;
+      const float ig = sigmoidf_(g[j]), fg = sigmoidf_(g[H + j]), gg = tanhf(g[2 * H + j]), og = sigmoidf_(g[3 * H + j]);
+      const float c = fg * c_s[i] + ig * gg;
+      c_s[i] = c;
+      h_s[i] = og * tanhf(c);
+    }
+    __syncthreads();
+    for (int s = warp; s < nb; s += 4 * H / 32) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < H / 32; ++i) part = fmaf(fmaxf(h_s[s * H + lane + 32 * i], 0.f), hw[i], part);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (lane == 0) probs[(int64_t)w * S + s0 + s] = sigmoidf_(part + head_b);
+    }
+  }
+  __syncthreads();
+  for (int i = n; i < nb * H; i += 4 * H) {
+    const int s = i / H, j = i - s * H;
+    state_out[(s0 + s) * H + j] = h_s[i];
+    state_out[(S + s0 + s) * H + j] = c_s[i];
   }
 }
 
@@ -148,9 +222,22 @@ extern "C" int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int6
   VADX_REQUIRE(d_x && d_out && n_streams >= 0 && n_in >= 2 && pad >= 0 && pad <= n_in - 1 && in_stride >= 1,
                "vadx_reflect_window_f32: bad argument");
   if (n_streams == 0) return VADX_OK;
-  reflect_window_kernel<<<grid1d(n_streams * (n_in + pad)), 256, 0, (cudaStream_t)stream>>>(d_x, in_stride, n_streams,
+  reflect_window_kernel<<<grid1d(n_streams * (n_in + pad)), 256, 0, (cudaStream_t)stream>>>(d_x, in_stride, n_streams, 1, 0,
                                                                                           n_in, pad, d_out);
   return after_launch("vadx_reflect_window_f32");
+}
+
+extern "C" int vadx_reflect_windows_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_windows,
+                                        int64_t window_step, int n_in, int pad, float* d_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "reflect_window_kernel",
+                    4.0 * n_streams * n_windows * (2.0 * n_in + pad));
+  VADX_REQUIRE(d_x && d_out && n_streams >= 0 && n_windows >= 1 && window_step >= 0 && n_in >= 2 && pad >= 0 &&
+                   pad <= n_in - 1 && in_stride >= 1,
+               "vadx_reflect_windows_f32: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  reflect_window_kernel<<<grid1d(n_streams * n_windows * (n_in + pad)), 256, 0, (cudaStream_t)stream>>>(
+      d_x, in_stride, n_streams, n_windows, window_step, n_in, pad, d_out);
+  return after_launch("vadx_reflect_windows_f32");
 }
 
 extern "C" int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream) {
@@ -197,6 +284,28 @@ extern "C" int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, flo
   lstm_cell_kernel<<<grid1d(n_streams * hidden), 256, 0, (cudaStream_t)stream>>>(d_gates, d_c_in, d_h_out, d_c_out,
                                                                                 d_h_relu, n_streams, hidden);
   return after_launch("vadx_lstm_cell_f32");
+}
+
+extern "C" int vadx_silero_lstm_windows_f32(const float* d_gates_in, const float* d_wt_hh, int ldw, const float* d_state_in,
+                                            float* d_state_out, const float* d_head_w, float head_bias, float* d_probs,
+                                            int64_t n_streams, int n_windows, int hidden, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "silero_lstm_windows_kernel",
+                    4.0 * n_streams * n_windows * (4.0 * hidden + 1.0) + 16.0 * n_streams * hidden,
+                    2.0 * n_streams * n_windows * 4.0 * hidden * hidden);
+  VADX_REQUIRE(d_gates_in && d_wt_hh && d_state_in && d_state_out && d_head_w && d_probs && d_state_in != d_state_out,
+               "vadx_silero_lstm_windows_f32: null or aliased pointer");
+  VADX_REQUIRE(n_streams >= 0 && n_windows >= 1 && hidden == 128 && ldw >= 4 * hidden,
+               "vadx_silero_lstm_windows_f32: hidden must be 128 (got %d) and ldw >= 4*hidden", hidden);
+  if (n_streams == 0) return VADX_OK;
+  constexpr int H = 128, SB = 28;            // 4096 streams -> 147 CTAs of 28 streams: one wave on 148 SMs
+  const size_t smem = (size_t)SB * H * 6 * sizeof(float);
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(silero_lstm_windows_kernel<H, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }));
+  silero_lstm_windows_kernel<H, SB><<<(unsigned)ceil_div(n_streams, SB), 4 * H, smem, (cudaStream_t)stream>>>(
+      d_gates_in, d_wt_hh, ldw, d_state_in, d_state_out, d_head_w, head_bias, d_probs, n_streams, n_windows);
+  return after_launch("vadx_silero_lstm_windows_f32");
 }
 
 extern "C" int vadx_silero_timestamps(const float* d_probs, int64_t ld, const int32_t* d_n_windows,
