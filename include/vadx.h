@@ -335,6 +335,14 @@ int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_
                       int64_t y_inner, int64_t y_step, const float* d_w_ih, const float* d_w_hh, const float* d_b_ih,
                       const float* d_b_hh, int64_t n_seq, int n_inner, int seq_len, int n_in, int hidden, int reverse,
                       void* stream);
+/* LSTM with the input projection hoisted out of the recurrence: d_gates_in holds x W_ih^T + b_ih + b_hh for every step of
+ * every sequence, computed beforehand as one dense layer, with the gate rows PERMUTED to row' = 4*unit + gate (i, f, g, o);
+ * d_w_hh_perm is W_hh in the same order, [hidden][4][hidden].  Sequence / step addressing as vadx_lstm_seq_f32 (strides in
+ * floats, multiples of 4); d_y receives h of every step.  One thread per sequence, no barrier inside the time loop. */
+int vadx_lstm_recurrence_supported(int hidden);
+int vadx_lstm_recurrence_f32(const float* d_gates_in, int64_t g_outer, int64_t g_inner, int64_t g_step, float* d_y,
+                             int64_t y_outer, int64_t y_inner, int64_t y_step, const float* d_w_hh_perm, int64_t n_seq,
+                             int n_inner, int seq_len, int hidden, int reverse, void* stream);
 int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_out, int64_t ldo,
                  float* d_out2, int64_t ldo2, int64_t n_rows, int n_cols, float scalar, void* stream);
 int vadx_ceps_cmul_f32(const float* d_q, const float* d_p, float* d_out, int64_t n_rows, int n_channels, void* stream);

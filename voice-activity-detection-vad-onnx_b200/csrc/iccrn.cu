@@ -215,6 +215,87 @@ static int launch_lstm_gates(const LstmArgs& a, cudaStream_t st) {
   return after_launch("vadx_lstm_seq_f32");
 }
 
+// Recurrence-only LSTM (the input half of the gates, x W_ih^T + b_ih + b_hh, is computed beforehand as ONE dense layer over
+// all steps of all sequences -- no recurrence in it, so it runs on the tensor cores): one THREAD per sequence, h in
+// registers, c and the next h in conflict-free shared-memory columns, W_hh broadcast from shared memory as float4.  The gate
+// rows are PERMUTED so that the four gates of hidden unit j are adjacent (row' = 4j + gate): one float4 of pre-activations
+// per unit and step.  No barrier inside the time loop (the gate-parallel kernel above needs two per step and one
+// shared-memory read per FMA).
+struct LstmRecArgs {
+  const float* g;      // permuted gate pre-activations; sequence q = (qo, qi) at g + qo*g_outer + qi*g_inner, step t at + t*g_step
+  int64_t g_outer, g_inner, g_step;
+  float* y;
+  int64_t y_outer, y_inner, y_step;
+  const float* w_hh_p;  // [H][4][H]: unit j, gate (i, f, g, o), k
+  int64_t n_seq;
+  int n_inner, L, reverse;
+};
+constexpr int kRecThreads = 128;
+template <int H>
+__global__ void __launch_bounds__(kRecThreads) lstm_rec_kernel(const LstmRecArgs a) {
+  extern __shared__ float rec_sm[];
+  float* w = rec_sm;                        // [H][4][H]
+  float* cs = w + 4 * H * H;                // [H][kRecThreads]
+  float* hn = cs + H * kRecThreads;         // [H][kRecThreads]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 4 * H * H; i += kRecThreads) w[i] = a.w_hh_p[i];
+#pragma unroll
+  for (int j = 0; j < H; ++j) cs[j * kRecThreads + tid] = 0.f;
+  __syncthreads();
+  const int64_t q = (int64_t)blockIdx.x * kRecThreads + tid;
+  if (q >= a.n_seq) return;
+  const int64_t qo = q / a.n_inner, qi = q - qo * a.n_inner;
+  const float* gq = a.g + qo * a.g_outer + qi * a.g_inner;
+  float* yq = a.y + qo * a.y_outer + qi * a.y_inner;
+  float h[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) h[k] = 0.f;
+  for (int step = 0; step < a.L; ++step) {
+    const int t = a.reverse ? a.L - 1 - step : step;
+    const float4* gt = reinterpret_cast<const float4*>(gq + (int64_t)t * a.g_step);
+#pragma unroll 2
+    for (int j = 0; j < H; ++j) {
+      float4 acc = __ldg(gt + j);
+      const float4* wj = reinterpret_cast<const float4*>(w + j * 4 * H);
+#pragma unroll
+      for (int k4 = 0; k4 < H / 4; ++k4) {
+        const float4 wi = wj[k4], wf = wj[H / 4 + k4], wg = wj[2 * (H / 4) + k4], wo = wj[3 * (H / 4) + k4];
+        acc.x = fmaf(wi.w, h[4 * k4 + 3], fmaf(wi.z, h[4 * k4 + 2], fmaf(wi.y, h[4 * k4 + 1], fmaf(wi.x, h[4 * k4], acc.x))));
+        acc.y = fmaf(wf.w, h[4 * k4 + 3], fmaf(wf.z, h[4 * k4 + 2], fmaf(wf.y, h[4 * k4 + 1], fmaf(wf.x, h[4 * k4], acc.y))));
+        acc.z = fmaf(wg.w, h[4 * k4 + 3], fmaf(wg.z, h[4 * k4 + 2], fmaf(wg.y, h[4 * k4 + 1], fmaf(wg.x, h[4 * k4], acc.z))));
+        acc.w = fmaf(wo.w, h[4 * k4 + 3], fmaf(wo.z, h[4 * k4 + 2], fmaf(wo.y, h[4 * k4 + 1], fmaf(wo.x, h[4 * k4], acc.w))));
+      }
+      const float ig = 1.0f / (1.0f + expf(-acc.x));
+      const float fg = 1.0f / (1.0f + expf(-acc.y));
+      const float gg = tanhf(acc.z);
+      const float og = 1.0f / (1.0f + expf(-acc.w));
+      const float c = fg * cs[j * kRecThreads + tid] + ig * gg;
+      cs[j * kRecThreads + tid] = c;
+      hn[j * kRecThreads + tid] = og * tanhf(c);
+    }
+    float4* yt = reinterpret_cast<float4*>(yq + (int64_t)t * a.y_step);
+#pragma unroll
+    for (int k4 = 0; k4 < H / 4; ++k4) {
+      h[4 * k4] = hn[(4 * k4) * kRecThreads + tid];
+      h[4 * k4 + 1] = hn[(4 * k4 + 1) * kRecThreads + tid];
+      h[4 * k4 + 2] = hn[(4 * k4 + 2) * kRecThreads + tid];
+      h[4 * k4 + 3] = hn[(4 * k4 + 3) * kRecThreads + tid];
+      yt[k4] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
+    }
+  }
+}
+
+template <int H>
+static int launch_lstm_rec(const LstmRecArgs& a, cudaStream_t st) {
+  const size_t smem = ((size_t)4 * H * H + 2 * (size_t)H * kRecThreads) * sizeof(float);
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(lstm_rec_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }));
+  lstm_rec_kernel<H><<<(unsigned)ceil_div(a.n_seq, kRecThreads), kRecThreads, smem, st>>>(a);
+  return after_launch("vadx_lstm_recurrence_f32");
+}
+
 // ---------------------------------------------------------------------------------- element-wise
 // op 0: out = a + b; 1: out = a * b; 2: out = a - s*b; 3: out = a (copy); 4: gate: out = a*b, out2 = b - a*b
 __global__ void __launch_bounds__(256) ew2_kernel(int op, const float* __restrict__ a, int64_t lda,
@@ -418,6 +499,24 @@ extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_in
              n_seq, n_inner, seq_len, n_in, hidden, reverse};
   lstm_seq_kernel<<<(unsigned)ceil_div(n_seq, kLstmThreads), kLstmThreads, smem, (cudaStream_t)stream>>>(a);
   return after_launch("vadx_lstm_seq_f32");
+}
+
+extern "C" int vadx_lstm_recurrence_supported(int hidden) { return (hidden == 20 || hidden == 40) ? 1 : 0; }
+
+extern "C" int vadx_lstm_recurrence_f32(const float* d_gates_in, int64_t g_outer, int64_t g_inner, int64_t g_step, float* d_y,
+                                        int64_t y_outer, int64_t y_inner, int64_t y_step, const float* d_w_hh_perm,
+                                        int64_t n_seq, int n_inner, int seq_len, int hidden, int reverse, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEMORY, (cudaStream_t)stream, "lstm_rec_kernel", 4.0 * n_seq * seq_len * 5.0 * hidden,
+                    2.0 * n_seq * seq_len * 4.0 * hidden * hidden);
+  VADX_REQUIRE(d_gates_in && d_y && d_w_hh_perm, "vadx_lstm_recurrence_f32: null pointer");
+  VADX_REQUIRE(n_seq >= 0 && n_inner >= 1 && seq_len >= 1, "vadx_lstm_recurrence_f32: bad shape");
+  VADX_REQUIRE(vadx_lstm_recurrence_supported(hidden), "vadx_lstm_recurrence_f32: hidden %d is not instantiated (20, 40)", hidden);
+  VADX_REQUIRE(((g_outer | g_inner | g_step | y_outer | y_inner | y_step) & 3) == 0 && aligned16(d_gates_in) && aligned16(d_y),
+               "vadx_lstm_recurrence_f32: strides must be multiples of 4 floats and the bases 16-byte aligned");
+  if (n_seq == 0) return VADX_OK;
+  LstmRecArgs a{d_gates_in, g_outer, g_inner, g_step, d_y, y_outer, y_inner, y_step, d_w_hh_perm, n_seq, n_inner, seq_len, reverse};
+  if (hidden == 20) return launch_lstm_rec<20>(a, (cudaStream_t)stream);
+  return launch_lstm_rec<40>(a, (cudaStream_t)stream);
 }
 
 extern "C" int vadx_ew2_f32(int op, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_out,

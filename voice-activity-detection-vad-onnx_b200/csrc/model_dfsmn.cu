@@ -75,6 +75,42 @@ int dfsmn_finalize(vadx_model* m) {
         VADX_TRY(m->upload_raw(n + ".bias_ih" + suf, 4 * H, VADX_DT_F32));
         VADX_TRY(m->upload_raw(n + ".bias_hh" + suf, 4 * H, VADX_DT_F32));
       }
+    if (!vadx_lstm_recurrence_supported(H)) return VADX_OK;
+    // the split form (iccrn.cu, lstm_rec_kernel): per layer ONE dense layer "<n>.ihp_l<l>" = the input projections of all
+    // directions stacked, gate rows permuted to 4*unit + gate, bias = b_ih + b_hh; and W_hh in the same order per direction
+    const int nd = bi ? 2 : 1;
+    for (int l = 0; l < layers; ++l) {
+      const int in_l = l == 0 ? n_in : H * nd;
+      HostTensor wp, bp;
+      wp.dtype = bp.dtype = VADX_DT_F32;
+      wp.dims = {(int64_t)nd * 4 * H, in_l};
+      bp.dims = {(int64_t)nd * 4 * H};
+      wp.bytes.resize((size_t)nd * 4 * H * in_l * sizeof(float));
+      bp.bytes.resize((size_t)nd * 4 * H * sizeof(float));
+      float* w = reinterpret_cast<float*>(wp.bytes.data());
+      float* b = reinterpret_cast<float*>(bp.bytes.data());
+      for (int d = 0; d < nd; ++d) {
+        const std::string suf = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+        const float* wih = m->find(n + ".weight_ih" + suf)->f32();
+        const float* whh = m->find(n + ".weight_hh" + suf)->f32();
+        const float* bih = m->find(n + ".bias_ih" + suf)->f32();
+        const float* bhh = m->find(n + ".bias_hh" + suf)->f32();
+        std::vector<float> hp((size_t)4 * H * H);
+        for (int j = 0; j < H; ++j)
+          for (int g = 0; g < 4; ++g) {
+            const int src = g * H + j, dst = d * 4 * H + j * 4 + g;
+            memcpy(w + (size_t)dst * in_l, wih + (size_t)src * in_l, (size_t)in_l * sizeof(float));
+            b[dst] = bih[src] + bhh[src];
+            memcpy(hp.data() + ((size_t)j * 4 + g) * H, whh + (size_t)src * H, (size_t)H * sizeof(float));
+          }
+        VADX_TRY(m->upload(n + ".hhp" + suf, hp.data(), hp.size() * sizeof(float)));
+      }
+      const std::string key = n + ".ihp_l" + std::to_string(l);
+      m->host[key + ".weight"] = std::move(wp);
+      m->host[key + ".bias"] = std::move(bp);
+      VADX_TRY(m->upload_linear(key + ".weight", nd * 4 * H, in_l));
+      VADX_TRY(m->upload_raw(key + ".bias", (int64_t)nd * 4 * H, VADX_DT_F32));
+    }
     return VADX_OK;
   };
   VADX_TRY(m->upload_raw("basis_b", -1, VADX_DT_F32));
@@ -180,6 +216,7 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     VADX_REQUIRE(in[0] && (h.near_only || in[1]) && out[0], "dfsmn_aec: near (and far) input and the probability output are required");
   }
   const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
+  const bool tc_iccrn = m->scalar("engine.tc_iccrn", 1.0) != 0.0;
   void* s_ = (void*)st;
 
   // ---- kernel wrappers (no-ops in the dry pass, which only measures)
@@ -190,10 +227,10 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     VADX_REQUIRE(w && w->dims.size() == 2, "dfsmn_aec: weight '%s.weight' missing", n.c_str());
     const int n_out = (int)w->dims[0], n_in = (int)w->dims[1];
     const float* bias = m->d<float>(n + ".bias");
-    const uint8_t* img = (use_tc && n_out > 8 && n.compare(0, 5, "mask.") == 0) ? m->d<uint8_t>(n + ".weight#TC") : nullptr;
-    if (img) return vadx_linear_tc_f32(x, ldx, img, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, s_);
-    return vadx_linear_f32(x, ldx, m->d<float>(n + ".weight#T"), (int)round_up(n_out, 4), bias, res, ldr, y, ldy, n_rows, n_in,
-                           n_out, act, s_);
+    // mask-net (128/256 wide) always on tcgen05; the echo estimator's small contractions (20..162 wide) too when
+    // "engine.tc_iccrn" is set: they are HBM-bound either way, the three-product split keeps fp32-grade results
+    const bool tc = use_tc && n_out > 8 && (n.compare(0, 5, "mask.") == 0 || tc_iccrn);
+    return m->linear(n + ".weight", x, ldx, bias, res, ldr, y, ldy, n_rows, n_in, n_out, act, tc, s_);
   };
   auto layernorm = [&](const float* x, int64_t n_rows, int D, const std::string& n, float* y) -> int {
     if (!real) return VADX_OK;
@@ -216,10 +253,46 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
                              m->d<float>(n + ".bias_ih" + suf), m->d<float>(n + ".bias_hh" + suf), n_seq, n_inner, len, n_in, H,
                              reverse, s_);
   };
+  // Split LSTM: gates_in = x W_ih^T + b for ALL rows as one dense layer (x is a dense [n_rows][n_in] matrix in every use:
+  // the sequence structure only re-indexes its rows), then the recurrence per direction.  `g` is scratch for
+  // [n_rows][nd*4H].  Sequence q = (qo, qi) of the x rows starts at row qo*r_outer + qi*r_inner, steps are r_step rows apart.
+  const bool split_lstm = m->scalar("engine.split_lstm", 1.0) != 0.0;
+  auto lstm_split = [&](const std::string& n, int layer, int nd, const float* x, int64_t n_rows, int n_in, int H, float* g,
+                        int64_t r_outer, int64_t r_inner, int64_t r_step, float* y, int64_t ldy, int64_t n_seq, int n_inner,
+                        int len) -> int {
+    if (!real) return VADX_OK;
+    const int G = nd * 4 * H;
+    VADX_TRY(lin(n + ".ihp_l" + std::to_string(layer), x, n_in, n_rows, g, G, VADX_ACT_NONE));
+    for (int d = 0; d < nd; ++d) {
+      const std::string suf = "_l" + std::to_string(layer) + (d ? "_reverse" : "");
+      VADX_TRY(vadx_lstm_recurrence_f32(g + d * 4 * H, r_outer * G, r_inner * G, r_step * G, y + d * H, r_outer * ldy, r_inner * ldy,
+                                        r_step * ldy, m->d<float>(n + ".hhp" + suf), n_seq, n_inner, len, H, d, s_));
+    }
+    return VADX_OK;
+  };
   // bi-LSTM over `len` consecutive rows of n_in features per sequence -> [n_seq*len][2H]
   auto bilstm_rows = [&](const std::string& n, const float* x, int64_t n_seq, int len, int n_in, int H, float* y) -> int {
+    if (split_lstm && vadx_lstm_recurrence_supported(H)) {
+      const size_t mk = ws.off;
+      float* g = take(n_seq * len * 8 * H);
+      const int rc = lstm_split(n, 0, 2, x, n_seq * len, n_in, H, g, len, 0, 1, y, 2 * H, n_seq, 1, len);
+      ws.off = mk;
+      return rc;
+    }
     VADX_TRY(lstm(n, 0, false, x, (int64_t)len * n_in, 0, n_in, y, (int64_t)len * 2 * H, 0, 2 * H, n_seq, 1, len, n_in, H, 0));
     return lstm(n, 0, true, x, (int64_t)len * n_in, 0, n_in, y + H, (int64_t)len * 2 * H, 0, 2 * H, n_seq, 1, len, n_in, H, 1);
+  };
+  // uni-directional LSTM over the FRAMES of every (stream, bin): x [S][Tb][F][n_in] -> y [S][Tb][F][H]
+  auto lstm_time = [&](const std::string& n, int layer, const float* x, int n_in, int H, float* y) -> int {
+    if (split_lstm && vadx_lstm_recurrence_supported(H)) {
+      const size_t mk = ws.off;
+      float* g = take(R * 4 * H);
+      const int rc = lstm_split(n, layer, 1, x, R, n_in, H, g, (int64_t)Tb * F, 1, F, y, H, S * F, F, Tb);
+      ws.off = mk;
+      return rc;
+    }
+    return lstm(n, layer, false, x, (int64_t)Tb * F * n_in, n_in, (int64_t)F * n_in, y, (int64_t)Tb * F * H, H, (int64_t)F * H,
+                S * F, F, Tb, n_in, H, 0);
   };
   auto cat = [&](const float* a, int ca, const float* b, int cb_, float* o) -> int {
     VADX_TRY(ew(3, a, ca, nullptr, 0, o, ca + cb_, nullptr, 0, R, ca));
@@ -317,10 +390,8 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     float* lo = take(R * c);
     float* prod = take(R * c);
     VADX_TRY(layernorm(e[5], B, F * c, "ln", lnb));
-    VADX_TRY(lstm("mid_lstm", 0, false, lnb, (int64_t)Tb * F * c, c, (int64_t)F * c, y1, (int64_t)Tb * F * H, H, (int64_t)F * H,
-                  S * F, F, Tb, c, H, 0));
-    VADX_TRY(lstm("mid_lstm", 1, false, y1, (int64_t)Tb * F * H, H, (int64_t)F * H, y2, (int64_t)Tb * F * H, H, (int64_t)F * H,
-                  S * F, F, Tb, H, H, 0));
+    VADX_TRY(lstm_time("mid_lstm", 0, lnb, c, H, y1));
+    VADX_TRY(lstm_time("mid_lstm", 1, y1, H, H, y2));
     VADX_TRY(lin("mid_lstm.linear", y2, H, R, lo, c, VADX_ACT_NONE));
     VADX_TRY(ew(1, e[5], c, lo, c, prod, c, nullptr, 0, R, c));
     VADX_TRY(cfb(prod, c, "cfb_d5", dcur));
@@ -342,8 +413,7 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     float* Y = take(B * 2 * F);
     float* frames = take(B * h.n_fft_b);
     VADX_TRY(cat(e[0], c, dcur, c, cat2));
-    VADX_TRY(lstm("out_lstm", 0, false, cat2, (int64_t)Tb * F * 2 * c, 2 * c, (int64_t)F * 2 * c, y3, (int64_t)Tb * F * c, c,
-                  (int64_t)F * c, S * F, F, Tb, 2 * c, c, 0));
+    VADX_TRY(lstm_time("out_lstm", 0, cat2, 2 * c, c, y3));
     VADX_TRY(lin("out_lstm.linear", y3, c, R, d0, 2 * c, VADX_ACT_NONE));
     VADX_TRY(ew(3, d0, 2 * c, nullptr, 0, cat3, 3 * c, nullptr, 0, R, 2 * c));
     VADX_TRY(ew(3, dcur, c, nullptr, 0, cat3 + 2 * c, 3 * c, nullptr, 0, R, c));
