@@ -65,6 +65,63 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < D; i += blockDim.x) o[i] = (xr[i] - mean) * inv * w[i] + b[i];
 }
 
+// LayerNorm with an in-row permutation folded in: the row is a [n1][n2][n3] block, the output is written in the order
+// (q0, q1, q2) of those axes (identity = plain LayerNorm); the affine tables are indexed in input order or, with
+// w_out_order, in output order.  The row is staged in shared memory once (the plain kernel reads it three times), so a
+// transposing permute4 launch before or after a LayerNorm costs nothing.  D = n1*n2*n3 <= 12288.
+__global__ void __launch_bounds__(256) layernorm_perm_kernel(const float* __restrict__ x, int n1, int n2, int n3, int q0, int q1,
+                                                             int q2, const float* __restrict__ w, const float* __restrict__ b,
+                                                             int w_out_order, float eps, float* __restrict__ out) {
+  extern __shared__ float ln_row[];
+  __shared__ float red[256];
+  __shared__ float s_mean, s_inv;
+  const int D = n1 * n2 * n3;
+  const int64_t row = blockIdx.x;
+  const float* xr = x + row * D;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float v = xr[i];
+    ln_row[i] = v;
+    acc += v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_mean = red[0] / (float)D;
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float d = ln_row[i] - mean;
+    acc = fmaf(d, d, acc);
+  }
+  __syncthreads();
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_inv = 1.0f / (sqrtf(red[0] / (float)(D - 1)) + eps);
+  __syncthreads();
+  const float inv = s_inv;
+  const int n[3] = {n1, n2, n3};
+  const int st[3] = {n2 * n3, n3, 1};
+  const int o1 = n[q1], o2 = n[q2];
+  const int s0 = st[q0], s1 = st[q1], s2 = st[q2];
+  float* o = out + row * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const int i2 = i % o2, r = i / o2;
+    const int i1 = r % o1, i0 = r / o1;
+    const int src = i0 * s0 + i1 * s1 + i2 * s2;
+    const int wi = w_out_order ? i : src;
+    o[i] = (ln_row[src] - mean) * inv * w[wi] + b[wi];
+  }
+}
+
 // ---------------------------------------------------------------------------------- LSTM sequences
 // Thread = one sequence; weights, the thread's x / h / c / gate columns live in shared memory
 // ([k][thread]: conflict-free), gate order i,f,g,o (PyTorch).  Sequence q = o*n_inner + i starts at
@@ -335,6 +392,40 @@ __global__ void __launch_bounds__(256) cmul_kernel(const float* __restrict__ q, 
   }
 }
 
+// CepsUnit complex gain with the layout change folded in (Export_DFSMN_VAD.py:145-146): q = the bi-LSTM head's output in
+// cepstral-major order [B][cb][re(C) | im(C)], spec = the cepstral DFT's native output [B][C][re(cb) | im(cb)]; the product is
+// written in spec's layout, which is what the inverse DFT layer reads -- neither permute4 launch of the unfused sequence
+// (spec -> cepstral-major copy, product -> back) is needed.
+__global__ void __launch_bounds__(256) cmul_t_kernel(const float* __restrict__ q, const float* __restrict__ spec,
+                                                     float* __restrict__ out, int64_t B, int C, int cb) {
+  const int64_t total = B * C * cb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % cb);
+    const int64_t r = i / cb;
+    const int c = (int)(r % C);
+    const int64_t b = r / C;
+    const float* qp = q + (b * cb + k) * 2 * C;
+    const float qr = qp[c], qi = qp[C + c];
+    const int64_t sp = (b * C + c) * 2 * cb + k;
+    const float pr = spec[sp], pi = spec[sp + cb];
+    out[sp] = qr * pr - qi * pi;
+    out[sp + cb] = qr * pi + qi * pr;
+  }
+}
+
+// out[b][f][c] = a[b][f][c] + t[b][c][f]: the block's last add with the [C][F] -> [F][C] transpose of the inverse DFT folded in
+__global__ void __launch_bounds__(256) add_transposed_kernel(const float* __restrict__ a, const float* __restrict__ t,
+                                                             float* __restrict__ out, int64_t B, int F, int C) {
+  const int64_t total = B * F * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int f = (int)(r % F);
+    const int64_t b = r / F;
+    out[i] = a[i] + t[(b * C + c) * F + f];
+  }
+}
+
 // 3-tap frequency im2col: out[(blk, f)][j*C + c] = x[(blk, f + j - 1)][c], zero outside [0, F)
 __global__ void __launch_bounds__(256) im2col_f3_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                         int64_t n_blk, int F, int C) {
@@ -468,6 +559,44 @@ extern "C" int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len,
   if (n_rows == 0) return VADX_OK;
   layernorm_kernel<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(d_x, n_rows, row_len, d_w, d_b, eps, d_out);
   return after_launch("vadx_layernorm_f32");
+}
+
+extern "C" int vadx_layernorm_perm_f32(const float* d_x, int64_t n_rows, int n1, int n2, int n3, int q0, int q1, int q2,
+                                       const float* d_w, const float* d_b, int w_out_order, float eps, float* d_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "layernorm_perm_kernel", 8.0 * n_rows * n1 * n2 * n3);
+  VADX_REQUIRE(d_x && d_w && d_b && d_out && d_x != d_out && n_rows >= 0 && n1 >= 1 && n2 >= 1 && n3 >= 1,
+               "vadx_layernorm_perm_f32: bad argument");
+  VADX_REQUIRE((int64_t)n1 * n2 * n3 >= 2 && (int64_t)n1 * n2 * n3 <= 12288, "vadx_layernorm_perm_f32: row of %lld elements",
+               (long long)n1 * n2 * n3);
+  VADX_REQUIRE(((1 << q0) | (1 << q1) | (1 << q2)) == 7 && q0 >= 0 && q1 >= 0 && q2 >= 0, "vadx_layernorm_perm_f32: not a permutation");
+  VADX_REQUIRE(n_rows <= 0x7fffffffLL, "vadx_layernorm_perm_f32: too many rows");
+  if (n_rows == 0) return VADX_OK;
+  static PerDevice per_device;
+  VADX_TRY(per_device.ensure(nullptr, [] {
+    return cudaFuncSetAttribute(layernorm_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4);
+  }));
+  layernorm_perm_kernel<<<(unsigned)n_rows, 256, (size_t)n1 * n2 * n3 * sizeof(float), (cudaStream_t)stream>>>(
+      d_x, n1, n2, n3, q0, q1, q2, d_w, d_b, w_out_order, eps, d_out);
+  return after_launch("vadx_layernorm_perm_f32");
+}
+
+extern "C" int vadx_ceps_cmul_t_f32(const float* d_q, const float* d_spec, float* d_out, int64_t n_blocks, int n_channels,
+                                    int n_ceps, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "cmul_t_kernel", 4.0 * n_blocks * n_channels * n_ceps * 6.0);
+  VADX_REQUIRE(d_q && d_spec && d_out && n_blocks >= 0 && n_channels >= 1 && n_ceps >= 1, "vadx_ceps_cmul_t_f32: bad argument");
+  if (n_blocks == 0) return VADX_OK;
+  cmul_t_kernel<<<g1(n_blocks * n_channels * n_ceps), 256, 0, (cudaStream_t)stream>>>(d_q, d_spec, d_out, n_blocks, n_channels, n_ceps);
+  return after_launch("vadx_ceps_cmul_t_f32");
+}
+
+extern "C" int vadx_add_transposed_f32(const float* d_a, const float* d_t, float* d_out, int64_t n_blocks, int n_bins,
+                                       int n_channels, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "add_transposed_kernel", 12.0 * n_blocks * n_bins * n_channels);
+  VADX_REQUIRE(d_a && d_t && d_out && n_blocks >= 0 && n_bins >= 1 && n_channels >= 1, "vadx_add_transposed_f32: bad argument");
+  if (n_blocks == 0) return VADX_OK;
+  add_transposed_kernel<<<g1(n_blocks * n_bins * n_channels), 256, 0, (cudaStream_t)stream>>>(d_a, d_t, d_out, n_blocks, n_bins,
+                                                                                          n_channels);
+  return after_launch("vadx_add_transposed_f32");
 }
 
 extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y,

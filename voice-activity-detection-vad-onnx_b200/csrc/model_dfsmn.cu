@@ -257,6 +257,7 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
   // the sequence structure only re-indexes its rows), then the recurrence per direction.  `g` is scratch for
   // [n_rows][nd*4H].  Sequence q = (qo, qi) of the x rows starts at row qo*r_outer + qi*r_inner, steps are r_step rows apart.
   const bool split_lstm = m->scalar("engine.split_lstm", 1.0) != 0.0;
+  const bool fold = m->scalar("engine.fold_permutes", 1.0) != 0.0;
   auto lstm_split = [&](const std::string& n, int layer, int nd, const float* x, int64_t n_rows, int n_in, int H, float* g,
                         int64_t r_outer, int64_t r_inner, int64_t r_step, float* y, int64_t ldy, int64_t n_seq, int n_inner,
                         int len) -> int {
@@ -320,27 +321,45 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     VADX_TRY(layernorm(gx, B, F * c, n + ".LN1", ln1));
     if (real) VADX_TRY(vadx_im2col_f3_f32(ln1, col, B, F, c, s_));
     VADX_TRY(lin(n + ".conv", col, 3 * c, R, y1, c, VADX_ACT_NONE));
-    // cepstral unit on LN2(xi - gx): DFT over the bins per channel, bi-LSTM along the cepstral bins, complex gain, IDFT
+    // cepstral unit on LN2(xi - gx): DFT over the bins per channel, bi-LSTM along the cepstral bins, complex gain, IDFT.
+    // Every layout change is folded into a neighbour (iccrn.cu): LN2 writes [c][F], the cepstral LayerNorm reads the DFT's
+    // native [c][re | im][cb] output and writes cepstral-major rows, the complex gain writes the DFT layout back, the last add
+    // reads the inverse DFT transposed.  ("engine.fold_permutes" = 0: the literal sequence with four permute4 launches.)
     float* ln2 = g;                                                          // g and xi are dead from here on
     float* z = xi;
-    VADX_TRY(layernorm(d, B, F * c, n + ".LN2", ln2));
-    VADX_TRY(perm(ln2, z, B, F, c, 1, 0, 2, 1, 3));                          // [B][c][F]
-    VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));     // [B*c][re(cb) | im(cb)]
-    VADX_TRY(perm(spec, P, B, c, 2, cb, 0, 3, 2, 1));                        // [B][cb][2][c]
-    VADX_TRY(layernorm(P, B, cb * 2 * c, n + ".cLN", Pn));
-    VADX_TRY(bilstm_rows(n + ".clstm", Pn, B, cb, 2 * c, c, hseq));          // [B*cb][2c]
-    float* Q = Pn;                                                           // in place is not allowed by the kernels: Pn -> spec
-    Q = spec;
-    VADX_TRY(lin(n + ".clstm.linear", hseq, 2 * c, B * cb, Q, 2 * c, VADX_ACT_NONE));
-    float* O = Pn;
-    if (real) VADX_TRY(vadx_ceps_cmul_f32(Q, P, O, B * cb, c, s_));
-    float* Ot = hseq;
-    VADX_TRY(perm(O, Ot, B, cb, 2, c, 0, 3, 2, 1));                          // [B][c][2][cb]
-    float* inv = gx;                                                         // [B*c][F] = R*c floats
-    VADX_TRY(lin("ceps.idft", Ot, 2 * cb, B * c, inv, F, VADX_ACT_NONE));
-    float* ceps = d;
-    VADX_TRY(perm(inv, ceps, B, c, F, 1, 0, 2, 1, 3));                       // [B][F][c]
-    VADX_TRY(ew(0, y1, c, ceps, c, y, c, nullptr, 0, R, c));
+    if (fold) {
+      if (real) VADX_TRY(vadx_layernorm_perm_f32(d, B, F, c, 1, 1, 0, 2, m->d<float>(n + ".LN2.w"), m->d<float>(n + ".LN2.b"), 0, 1e-6f,
+                                                 z, s_));                    // [B][c][F]
+      VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));   // [B][c][re(cb) | im(cb)]
+      if (real) VADX_TRY(vadx_layernorm_perm_f32(spec, B, c, 2, cb, 2, 1, 0, m->d<float>(n + ".cLN.w"), m->d<float>(n + ".cLN.b"), 1,
+                                                 1e-6f, Pn, s_));            // [B][cb][2][c]
+      VADX_TRY(bilstm_rows(n + ".clstm", Pn, B, cb, 2 * c, c, hseq));        // [B*cb][2c]
+      float* Q = P;
+      VADX_TRY(lin(n + ".clstm.linear", hseq, 2 * c, B * cb, Q, 2 * c, VADX_ACT_NONE));
+      float* Ot = Pn;
+      if (real) VADX_TRY(vadx_ceps_cmul_t_f32(Q, spec, Ot, B, c, cb, s_));   // [B][c][2][cb]
+      float* inv = gx;                                                       // [B*c][F] = R*c floats
+      VADX_TRY(lin("ceps.idft", Ot, 2 * cb, B * c, inv, F, VADX_ACT_NONE));
+      if (real) VADX_TRY(vadx_add_transposed_f32(y1, inv, y, B, F, c, s_));
+    } else {
+      VADX_TRY(layernorm(d, B, F * c, n + ".LN2", ln2));
+      VADX_TRY(perm(ln2, z, B, F, c, 1, 0, 2, 1, 3));                          // [B][c][F]
+      VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));     // [B*c][re(cb) | im(cb)]
+      VADX_TRY(perm(spec, P, B, c, 2, cb, 0, 3, 2, 1));                        // [B][cb][2][c]
+      VADX_TRY(layernorm(P, B, cb * 2 * c, n + ".cLN", Pn));
+      VADX_TRY(bilstm_rows(n + ".clstm", Pn, B, cb, 2 * c, c, hseq));          // [B*cb][2c]
+      float* Q = spec;
+      VADX_TRY(lin(n + ".clstm.linear", hseq, 2 * c, B * cb, Q, 2 * c, VADX_ACT_NONE));
+      float* O = Pn;
+      if (real) VADX_TRY(vadx_ceps_cmul_f32(Q, P, O, B * cb, c, s_));
+      float* Ot = hseq;
+      VADX_TRY(perm(O, Ot, B, cb, 2, c, 0, 3, 2, 1));                          // [B][c][2][cb]
+      float* inv = gx;                                                         // [B*c][F] = R*c floats
+      VADX_TRY(lin("ceps.idft", Ot, 2 * cb, B * c, inv, F, VADX_ACT_NONE));
+      float* ceps = d;
+      VADX_TRY(perm(inv, ceps, B, c, F, 1, 0, 2, 1, 3));                       // [B][F][c]
+      VADX_TRY(ew(0, y1, c, ceps, c, y, c, nullptr, 0, R, c));
+    }
     ws.off = mk;
     return VADX_OK;
   };
