@@ -333,15 +333,17 @@ int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len, const floa
                        float* d_out, void* stream);
 /* The same building blocks with the layout changes of the cepstral unit folded in (no permute4 launches):
  *  vadx_layernorm_perm_f32: LayerNorm of rows that are [n1][n2][n3] blocks, written in the axis order (q0, q1, q2); the affine
- *      tables are indexed in input order, or in output order with w_out_order = 1.
+ *      tables are indexed in input order, or in output order with w_out_order = 1.  Output rows are out_stride floats apart
+ *      (0 = dense) with `pad` zeros written before and after each row: the zero padding of a following 3-tap frequency conv
+ *      that runs as a dense layer over OVERLAPPING rows (vadx_linear_tc_f32 with ldx < n_in) instead of an im2col copy.
  *  vadx_ceps_cmul_t_f32: q [B][cb][re(C) | im(C)] x spec [B][C][re(cb) | im(cb)] -> product in spec's layout.
- *  vadx_add_transposed_f32: out[b][f][c] = a[b][f][c] + t[b][c][f]. */
+ *  vadx_add_transposed_f32: out[b][f][c] = a[b][f][c] + t[b][c][f]; a's blocks are a_block_stride floats apart (0 = dense). */
 int vadx_layernorm_perm_f32(const float* d_x, int64_t n_rows, int n1, int n2, int n3, int q0, int q1, int q2, const float* d_w,
-                            const float* d_b, int w_out_order, float eps, float* d_out, void* stream);
+                            const float* d_b, int w_out_order, float eps, float* d_out, int64_t out_stride, int pad, void* stream);
 int vadx_ceps_cmul_t_f32(const float* d_q, const float* d_spec, float* d_out, int64_t n_blocks, int n_channels, int n_ceps,
                          void* stream);
-int vadx_add_transposed_f32(const float* d_a, const float* d_t, float* d_out, int64_t n_blocks, int n_bins, int n_channels,
-                            void* stream);
+int vadx_add_transposed_f32(const float* d_a, int64_t a_block_stride, const float* d_t, float* d_out, int64_t n_blocks, int n_bins,
+                            int n_channels, void* stream);
 int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y, int64_t y_outer,
                       int64_t y_inner, int64_t y_step, const float* d_w_ih, const float* d_w_hh, const float* d_b_ih,
                       const float* d_b_hh, int64_t n_seq, int n_inner, int seq_len, int n_in, int hidden, int reverse,

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // transposing permute4 launch before or after a LayerNorm costs nothing.  D = n1*n2*n3 <= 12288.
 __global__ void __launch_bounds__(256) layernorm_perm_kernel(const float* __restrict__ x, int n1, int n2, int n3, int q0, int q1,
                                                              int q2, const float* __restrict__ w, const float* __restrict__ b,
-                                                             int w_out_order, float eps, float* __restrict__ out) {
+                                                             int w_out_order, float eps, float* __restrict__ out, int64_t out_stride,
+                                                             int pad) {
   extern __shared__ float ln_row[];
   __shared__ float red[256];
   __shared__ float s_mean, s_inv;
@@ -112,7 +113,13 @@ __global__ void __launch_bounds__(256) layernorm_perm_kernel(const float* __rest
   const int st[3] = {n2 * n3, n3, 1};
   const int o1 = n[q1], o2 = n[q2];
   const int s0 = st[q0], s1 = st[q1], s2 = st[q2];
-  float* o = out + row * D;
+  // out_stride >= D + 2*pad floats per row: `pad` zeros are written before and after the row (the zero padding a following
+  // 3-tap frequency conv reads when it runs as a dense layer over overlapping rows)
+  float* o = out + row * out_stride + pad;
+  for (int i = threadIdx.x; i < pad; i += blockDim.x) {
+    o[i - pad] = 0.f;
+    o[D + i] = 0.f;
+  }
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     const int i2 = i % o2, r = i / o2;
     const int i1 = r % o1, i0 = r / o1;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(256) cmul_t_kernel(const float* __restrict__ q
 }
 
 // out[b][f][c] = a[b][f][c] + t[b][c][f]: the block's last add with the [C][F] -> [F][C] transpose of the inverse DFT folded in
-__global__ void __launch_bounds__(256) add_transposed_kernel(const float* __restrict__ a, const float* __restrict__ t,
+__global__ void __launch_bounds__(256) add_transposed_kernel(const float* __restrict__ a, int64_t a_block, const float* __restrict__ t,
                                                              float* __restrict__ out, int64_t B, int F, int C) {
   const int64_t total = B * F * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(256) add_transposed_kernel(const float* __rest
     const int64_t r = i / C;
     const int f = (int)(r % F);
     const int64_t b = r / F;
-    out[i] = a[i] + t[(b * C + c) * F + f];
+    out[i] = a[b * a_block + (int64_t)f * C + c] + t[(b * C + c) * F + f];
   }
 }
 
@@ -562,7 +569,8 @@ extern "C" int vadx_layernorm_f32(const float* d_x, int64_t n_rows, int row_len,
 }
 
 extern "C" int vadx_layernorm_perm_f32(const float* d_x, int64_t n_rows, int n1, int n2, int n3, int q0, int q1, int q2,
-                                       const float* d_w, const float* d_b, int w_out_order, float eps, float* d_out, void* stream) {
+                                       const float* d_w, const float* d_b, int w_out_order, float eps, float* d_out,
+                                       int64_t out_stride, int pad, void* stream) {
   StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "layernorm_perm_kernel", 8.0 * n_rows * n1 * n2 * n3);
   VADX_REQUIRE(d_x && d_w && d_b && d_out && d_x != d_out && n_rows >= 0 && n1 >= 1 && n2 >= 1 && n3 >= 1,
                "vadx_layernorm_perm_f32: bad argument");
@@ -570,13 +578,16 @@ extern "C" int vadx_layernorm_perm_f32(const float* d_x, int64_t n_rows, int n1,
                (long long)n1 * n2 * n3);
   VADX_REQUIRE(((1 << q0) | (1 << q1) | (1 << q2)) == 7 && q0 >= 0 && q1 >= 0 && q2 >= 0, "vadx_layernorm_perm_f32: not a permutation");
   VADX_REQUIRE(n_rows <= 0x7fffffffLL, "vadx_layernorm_perm_f32: too many rows");
+  if (out_stride == 0) out_stride = (int64_t)n1 * n2 * n3 + 2 * pad;
+  VADX_REQUIRE(pad >= 0 && out_stride >= (int64_t)n1 * n2 * n3 + 2 * pad, "vadx_layernorm_perm_f32: out_stride %lld too small",
+               (long long)out_stride);
   if (n_rows == 0) return VADX_OK;
   static PerDevice per_device;
   VADX_TRY(per_device.ensure(nullptr, [] {
     return cudaFuncSetAttribute(layernorm_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4);
   }));
   layernorm_perm_kernel<<<(unsigned)n_rows, 256, (size_t)n1 * n2 * n3 * sizeof(float), (cudaStream_t)stream>>>(
-      d_x, n1, n2, n3, q0, q1, q2, d_w, d_b, w_out_order, eps, d_out);
+      d_x, n1, n2, n3, q0, q1, q2, d_w, d_b, w_out_order, eps, d_out, out_stride, pad);
   return after_launch("vadx_layernorm_perm_f32");
 }
 
@@ -589,13 +600,15 @@ extern "C" int vadx_ceps_cmul_t_f32(const float* d_q, const float* d_spec, float
   return after_launch("vadx_ceps_cmul_t_f32");
 }
 
-extern "C" int vadx_add_transposed_f32(const float* d_a, const float* d_t, float* d_out, int64_t n_blocks, int n_bins,
-                                       int n_channels, void* stream) {
+extern "C" int vadx_add_transposed_f32(const float* d_a, int64_t a_block_stride, const float* d_t, float* d_out, int64_t n_blocks,
+                                       int n_bins, int n_channels, void* stream) {
   StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "add_transposed_kernel", 12.0 * n_blocks * n_bins * n_channels);
   VADX_REQUIRE(d_a && d_t && d_out && n_blocks >= 0 && n_bins >= 1 && n_channels >= 1, "vadx_add_transposed_f32: bad argument");
   if (n_blocks == 0) return VADX_OK;
-  add_transposed_kernel<<<g1(n_blocks * n_bins * n_channels), 256, 0, (cudaStream_t)stream>>>(d_a, d_t, d_out, n_blocks, n_bins,
-                                                                                          n_channels);
+  if (a_block_stride == 0) a_block_stride = (int64_t)n_bins * n_channels;
+  VADX_REQUIRE(a_block_stride >= (int64_t)n_bins * n_channels, "vadx_add_transposed_f32: a_block_stride too small");
+  add_transposed_kernel<<<g1(n_blocks * n_bins * n_channels), 256, 0, (cudaStream_t)stream>>>(d_a, a_block_stride, d_t, d_out,
+                                                                                          n_blocks, n_bins, n_channels);
   return after_launch("vadx_add_transposed_f32");
 }
 

@@ -307,8 +307,12 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     float* xi = take(R * c);
     float* d = take(R * c);
     float* gx = take(R * c);
-    float* col = take(R * 3 * c);
-    float* y1 = take(R * c);
+    // the (3,1) frequency conv: an im2col copy + dense layer, or (fold) a dense layer over OVERLAPPING rows of the padded
+    // LayerNorm output [B][F + 2][c] (row (b, f) = the 3c contiguous values from bin f-1), output rows in the same padded
+    // indexing
+    const bool fold_conv = fold && use_tc && tc_iccrn && m->d<uint8_t>(n + ".conv.weight#TC") != nullptr;
+    float* col = fold_conv ? take(B * (F + 2) * c) : take(R * 3 * c);
+    float* y1 = fold_conv ? take(B * (F + 2) * c) : take(R * c);
     float* spec = take(B * c * 2 * cb);
     float* P = take(B * cb * 2 * c);
     float* Pn = take(B * cb * 2 * c);
@@ -317,10 +321,16 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     VADX_TRY(lin(n + ".gate", ln0, cin, R, g, c, VADX_ACT_SIGMOID));
     VADX_TRY(lin(n + ".input", x, cin, R, xi, c, VADX_ACT_NONE));
     VADX_TRY(ew(4, g, c, xi, c, gx, c, d, c, R, c));                         // gx = g * xi, d = xi - gx
-    float* ln1 = ln0;                                                        // LN0's output is dead: reuse ([R][cin] >= [R][c])
-    VADX_TRY(layernorm(gx, B, F * c, n + ".LN1", ln1));
-    if (real) VADX_TRY(vadx_im2col_f3_f32(ln1, col, B, F, c, s_));
-    VADX_TRY(lin(n + ".conv", col, 3 * c, R, y1, c, VADX_ACT_NONE));
+    if (fold_conv) {
+      if (real) VADX_TRY(vadx_layernorm_perm_f32(gx, B, F, c, 1, 0, 1, 2, m->d<float>(n + ".LN1.w"), m->d<float>(n + ".LN1.b"), 0, 1e-6f,
+                                                 col, (int64_t)(F + 2) * c, c, s_));
+      VADX_TRY(lin(n + ".conv", col, c, B * (F + 2) - 2, y1, c, VADX_ACT_NONE));
+    } else {
+      float* ln1 = ln0;                                                      // LN0's output is dead: reuse ([R][cin] >= [R][c])
+      VADX_TRY(layernorm(gx, B, F * c, n + ".LN1", ln1));
+      if (real) VADX_TRY(vadx_im2col_f3_f32(ln1, col, B, F, c, s_));
+      VADX_TRY(lin(n + ".conv", col, 3 * c, R, y1, c, VADX_ACT_NONE));
+    }
     // cepstral unit on LN2(xi - gx): DFT over the bins per channel, bi-LSTM along the cepstral bins, complex gain, IDFT.
     // Every layout change is folded into a neighbour (iccrn.cu): LN2 writes [c][F], the cepstral LayerNorm reads the DFT's
     // native [c][re | im][cb] output and writes cepstral-major rows, the complex gain writes the DFT layout back, the last add
@@ -329,10 +339,10 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     float* z = xi;
     if (fold) {
       if (real) VADX_TRY(vadx_layernorm_perm_f32(d, B, F, c, 1, 1, 0, 2, m->d<float>(n + ".LN2.w"), m->d<float>(n + ".LN2.b"), 0, 1e-6f,
-                                                 z, s_));                    // [B][c][F]
+                                                 z, 0, 0, s_));              // [B][c][F]
       VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));   // [B][c][re(cb) | im(cb)]
       if (real) VADX_TRY(vadx_layernorm_perm_f32(spec, B, c, 2, cb, 2, 1, 0, m->d<float>(n + ".cLN.w"), m->d<float>(n + ".cLN.b"), 1,
-                                                 1e-6f, Pn, s_));            // [B][cb][2][c]
+                                                 1e-6f, Pn, 0, 0, s_));      // [B][cb][2][c]
       VADX_TRY(bilstm_rows(n + ".clstm", Pn, B, cb, 2 * c, c, hseq));        // [B*cb][2c]
       float* Q = P;
       VADX_TRY(lin(n + ".clstm.linear", hseq, 2 * c, B * cb, Q, 2 * c, VADX_ACT_NONE));
@@ -340,7 +350,7 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
       if (real) VADX_TRY(vadx_ceps_cmul_t_f32(Q, spec, Ot, B, c, cb, s_));   // [B][c][2][cb]
       float* inv = gx;                                                       // [B*c][F] = R*c floats
       VADX_TRY(lin("ceps.idft", Ot, 2 * cb, B * c, inv, F, VADX_ACT_NONE));
-      if (real) VADX_TRY(vadx_add_transposed_f32(y1, inv, y, B, F, c, s_));
+      if (real) VADX_TRY(vadx_add_transposed_f32(y1, fold_conv ? (int64_t)(F + 2) * c : 0, inv, y, B, F, c, s_));
     } else {
       VADX_TRY(layernorm(d, B, F * c, n + ".LN2", ln2));
       VADX_TRY(perm(ln2, z, B, F, c, 1, 0, 2, 1, 3));                          // [B][c][F]
