@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-families", action="store_true", help="skip the short RTFx runs of the other model families")
+    ap.add_argument("--sustain-seconds", type=float, default=4.0,
+                    help="extra device-resident leg of about this many seconds (steady-state clocks / power); 0 = skip")
     return ap.parse_args()
 
 
@@ -504,6 +506,23 @@ def run_vadx(args):
     stages = lib.profile_collect()
     kernel_records = lib.profile_collect_kernels()
     lib.profile_enable(False)
+    # ---- the same step back to back for a few seconds: the timed region above is ~0.1 s, this leg shows the step time and
+    # the clocks once the part sits at its power / thermal steady state (reported next to `value`, not as it)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms_total / args.steps, 1e-3)))
+        sus_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sus_sampler.start()
+        keep = sampler
+        sampler = sus_sampler
+        ms_sus = timed(step_device, n_sus, 0)
+        sampler = keep
+        if rank == 0:
+            sus_sampler.stop()
+        sustained = {"steps": n_sus, "seconds": ms_sus / 1e3, "ms_per_step": ms_sus / n_sus,
+                     "value": world * B * (CHUNK / 16000.0) * n_sus / (ms_sus / 1e3) / 3600.0, "unit": UNIT,
+                     "clocks": sus_sampler.summary() if rank == 0 else None}
     # ---- end to end through the public API with host buffers
     # multi-GPU: the final gather of seg_count / segments (the path's only collective) is INSIDE the end-to-end region.
     # The host-fed arm is bound by each GPU's pinned host->device rate, which is NOT the same for all GPUs of the box (PCIe
@@ -660,6 +679,7 @@ def run_vadx(args):
                 "gpu_launches": int(launches),
                 "roofline": roof, "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                 "stage_share": stage_share,
+                "sustained": sustained,
                 "cpu_baseline": cpu, "clocks": sampler.summary(), "families": families}
         print(json.dumps(line), flush=True)
     if world > 1:

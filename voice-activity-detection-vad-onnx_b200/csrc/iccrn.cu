@@ -2,7 +2,7 @@
 // activations: 4-D permute, (C,F)-LayerNorm with unbiased std, batched LSTM sequences, gated
 // element-wise ops, 3-tap frequency im2col, the AlphaPredictor scaling and the ISTFT overlap-add.
 // Reference: DFSMN/near_and_far_end_audio/Export_DFSMN_VAD.py:65-354.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace vadx {
 
@@ -317,25 +317,31 @@ __global__ void __launch_bounds__(kRecThreads) lstm_rec_kernel(const LstmRecArgs
   for (int step = 0; step < a.L; ++step) {
     const int t = a.reverse ? a.L - 1 - step : step;
     const float4* gt = reinterpret_cast<const float4*>(gq + (int64_t)t * a.g_step);
-#pragma unroll 2
-    for (int j = 0; j < H; ++j) {
-      float4 acc = __ldg(gt + j);
-      const float4* wj = reinterpret_cast<const float4*>(w + j * 4 * H);
+    // two units per 256-bit load: a lane's row is 52 KB away from its neighbour's, so every load touches 32 different
+    // sectors; with 128-bit loads each 32-byte sector was requested twice and L1 (10 % hit rate under ncu) did not keep it
+    for (int j = 0; j < H; j += 2) {
+      float4 acc2[2];
+      ldg256_nc(reinterpret_cast<const float*>(gt + j), acc2[0], acc2[1]);
 #pragma unroll
-      for (int k4 = 0; k4 < H / 4; ++k4) {
-        const float4 wi = wj[k4], wf = wj[H / 4 + k4], wg = wj[2 * (H / 4) + k4], wo = wj[3 * (H / 4) + k4];
-        acc.x = fmaf(wi.w, h[4 * k4 + 3], fmaf(wi.z, h[4 * k4 + 2], fmaf(wi.y, h[4 * k4 + 1], fmaf(wi.x, h[4 * k4], acc.x))));
-        acc.y = fmaf(wf.w, h[4 * k4 + 3], fmaf(wf.z, h[4 * k4 + 2], fmaf(wf.y, h[4 * k4 + 1], fmaf(wf.x, h[4 * k4], acc.y))));
-        acc.z = fmaf(wg.w, h[4 * k4 + 3], fmaf(wg.z, h[4 * k4 + 2], fmaf(wg.y, h[4 * k4 + 1], fmaf(wg.x, h[4 * k4], acc.z))));
-        acc.w = fmaf(wo.w, h[4 * k4 + 3], fmaf(wo.z, h[4 * k4 + 2], fmaf(wo.y, h[4 * k4 + 1], fmaf(wo.x, h[4 * k4], acc.w))));
+      for (int u = 0; u < 2; ++u) {
+        float4 acc = acc2[u];
+        const float4* wj = reinterpret_cast<const float4*>(w + (j + u) * 4 * H);
+#pragma unroll
+        for (int k4 = 0; k4 < H / 4; ++k4) {
+          const float4 wi = wj[k4], wf = wj[H / 4 + k4], wg = wj[2 * (H / 4) + k4], wo = wj[3 * (H / 4) + k4];
+          acc.x = fmaf(wi.w, h[4 * k4 + 3], fmaf(wi.z, h[4 * k4 + 2], fmaf(wi.y, h[4 * k4 + 1], fmaf(wi.x, h[4 * k4], acc.x))));
+          acc.y = fmaf(wf.w, h[4 * k4 + 3], fmaf(wf.z, h[4 * k4 + 2], fmaf(wf.y, h[4 * k4 + 1], fmaf(wf.x, h[4 * k4], acc.y))));
+          acc.z = fmaf(wg.w, h[4 * k4 + 3], fmaf(wg.z, h[4 * k4 + 2], fmaf(wg.y, h[4 * k4 + 1], fmaf(wg.x, h[4 * k4], acc.z))));
+          acc.w = fmaf(wo.w, h[4 * k4 + 3], fmaf(wo.z, h[4 * k4 + 2], fmaf(wo.y, h[4 * k4 + 1], fmaf(wo.x, h[4 * k4], acc.w))));
+        }
+        const float ig = 1.0f / (1.0f + expf(-acc.x));
+        const float fg = 1.0f / (1.0f + expf(-acc.y));
+        const float gg = tanhf(acc.z);
+        const float og = 1.0f / (1.0f + expf(-acc.w));
+        const float c = fg * cs[(j + u) * kRecThreads + tid] + ig * gg;
+        cs[(j + u) * kRecThreads + tid] = c;
+        hn[(j + u) * kRecThreads + tid] = og * tanhf(c);
       }
-      const float ig = 1.0f / (1.0f + expf(-acc.x));
-      const float fg = 1.0f / (1.0f + expf(-acc.y));
-      const float gg = tanhf(acc.z);
-      const float og = 1.0f / (1.0f + expf(-acc.w));
-      const float c = fg * cs[j * kRecThreads + tid] + ig * gg;
-      cs[j * kRecThreads + tid] = c;
-      hn[j * kRecThreads + tid] = og * tanhf(c);
     }
     float4* yt = reinterpret_cast<float4*>(yq + (int64_t)t * a.y_step);
 #pragma unroll
@@ -653,8 +659,10 @@ extern "C" int vadx_lstm_recurrence_f32(const float* d_gates_in, int64_t g_outer
   VADX_REQUIRE(d_gates_in && d_y && d_w_hh_perm, "vadx_lstm_recurrence_f32: null pointer");
   VADX_REQUIRE(n_seq >= 0 && n_inner >= 1 && seq_len >= 1, "vadx_lstm_recurrence_f32: bad shape");
   VADX_REQUIRE(vadx_lstm_recurrence_supported(hidden), "vadx_lstm_recurrence_f32: hidden %d is not instantiated (20, 40)", hidden);
-  VADX_REQUIRE(((g_outer | g_inner | g_step | y_outer | y_inner | y_step) & 3) == 0 && aligned16(d_gates_in) && aligned16(d_y),
-               "vadx_lstm_recurrence_f32: strides must be multiples of 4 floats and the bases 16-byte aligned");
+  VADX_REQUIRE(((y_outer | y_inner | y_step) & 3) == 0 && aligned16(d_y) && ((g_outer | g_inner | g_step) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_gates_in) & 31u) == 0,
+               "vadx_lstm_recurrence_f32: output strides must be multiples of 4 floats (16-byte aligned base), gate strides multiples "
+               "of 8 floats (32-byte aligned base)");
   if (n_seq == 0) return VADX_OK;
   LstmRecArgs a{d_gates_in, g_outer, g_inner, g_step, d_y, y_outer, y_inner, y_step, d_w_hh_perm, n_seq, n_inner, seq_len, reverse};
   if (hidden == 20) return launch_lstm_rec<20>(a, (cudaStream_t)stream);
