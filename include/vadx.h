@@ -344,6 +344,16 @@ int vadx_ceps_cmul_t_f32(const float* d_q, const float* d_spec, float* d_out, in
                          void* stream);
 int vadx_add_transposed_f32(const float* d_a, int64_t a_block_stride, const float* d_t, float* d_out, int64_t n_blocks, int n_bins,
                             int n_channels, void* stream);
+/* The front of a gated conv block in one kernel (CFB, Export_DFSMN_VAD.py:87-93,133-154), one CTA per (stream, frame)
+ * block of n_bins bins:  g = sigmoid(W_g LN0(x) + b_g), xi = W_i x + b_i, gx = g*xi, d = xi - gx;
+ *   d_col = LN1(gx) as zero-padded rows [n_blocks][n_bins + 2][C]   (input of the frequency conv as a dense layer over
+ *           overlapping rows),   d_z = LN2(d) transposed [n_blocks][C][n_bins]   (input of the cepstral DFT layer).
+ * d_x [n_blocks][n_bins][n_in]; W_g, W_i [C][n_in] in the reference layout; LayerNorm tables [n_bins][.]; C = 20, n_in 20 | 40. */
+int vadx_cfb_front_supported(int n_in, int n_channels, int n_bins);
+int vadx_cfb_front_f32(const float* d_x, int64_t n_blocks, int n_bins, int n_in, int n_channels, const float* d_ln0_w,
+                       const float* d_ln0_b, const float* d_wg, const float* d_bg, const float* d_wi, const float* d_bi,
+                       const float* d_ln1_w, const float* d_ln1_b, const float* d_ln2_w, const float* d_ln2_b, float eps,
+                       float* d_col, float* d_z, void* stream);
 int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y, int64_t y_outer,
                       int64_t y_inner, int64_t y_step, const float* d_w_ih, const float* d_w_hh, const float* d_b_ih,
                       const float* d_b_hh, int64_t n_seq, int n_inner, int seq_len, int n_in, int hidden, int reverse,

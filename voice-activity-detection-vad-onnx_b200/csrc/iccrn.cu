@@ -129,6 +129,143 @@ __global__ void __launch_bounds__(256) layernorm_perm_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------- gated-block front, fused
+// The front of a gated conv block (CFB, Export_DFSMN_VAD.py:87-93,133-154) in ONE kernel, one CTA per (stream, frame) block
+// b of F bins:   g = sigmoid(W_g LN0(x) + b_g),  xi = W_i x + b_i,  gx = g * xi,  d = xi - gx,
+//                col = LN1(gx) as padded rows [F + 2][C] (the overlapping-row input of the (3,1) frequency conv),
+//                z   = LN2(d) transposed to [C][F] (the input of the cepstral DFT layer).
+// The unfused sequence is six launches (LN0, two dense layers, the gating, LN1, LN2) that move ~1300 bytes per (bin) row; here
+// the block is read once (CIN floats per row) and two C-wide rows are written.  thread = bin f: its x row and LN0 row live in
+// registers, the two C x CIN weights are broadcast from shared memory, gx / d go to odd-stride shared-memory rows for the two
+// block statistics.  LayerNorm = (v - mean) / (unbiased std + eps) * w + b over the whole [F][.] block, as layernorm_kernel.
+template <int CIN, int C>
+__global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restrict__ x, int F, const float* __restrict__ ln0_w,
+                                                          const float* __restrict__ ln0_b, const float* __restrict__ wg,
+                                                          const float* __restrict__ bg, const float* __restrict__ wi,
+                                                          const float* __restrict__ bi, const float* __restrict__ ln1_w,
+                                                          const float* __restrict__ ln1_b, const float* __restrict__ ln2_w,
+                                                          const float* __restrict__ ln2_b, float eps, float* __restrict__ col,
+                                                          float* __restrict__ z) {
+  constexpr int kT = 160;                 // threads = max bins per block
+  constexpr int LD = C + 1;               // odd row stride: a thread's private row is conflict-free
+  extern __shared__ __align__(16) float cf_sm[];
+  float* wgs = cf_sm;                     // [C][CIN]
+  float* wis = wgs + C * CIN;             // [C][CIN]
+  float* gxs = wis + C * CIN;             // [F][LD]
+  float* ds = gxs + kT * LD;              // [F][LD]
+  __shared__ float red[kT];
+  __shared__ float s_stat[2];
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  for (int i = tid; i < C * CIN; i += kT) {
+    wgs[i] = wg[i];
+    wis[i] = wi[i];
+  }
+  // block reduction with the tree of layernorm_kernel (its 256-thread tree over 160 partial sums: the upper slots are zero)
+  auto block_sum = [&](float v) -> float {
+    __syncthreads();
+    red[tid] = v;
+    __syncthreads();
+    if (tid < 32) red[tid] += (tid + 128 < kT) ? red[tid + 128] : 0.f;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    return red[0];
+  };
+  // ---- LN0 statistics over the [F][CIN] block; the thread keeps ITS row
+  const bool live = tid < F;
+  float xr[CIN];
+  const float4* xp = reinterpret_cast<const float4*>(x + (b * F + (live ? tid : 0)) * CIN);
+  float part = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < CIN / 4; ++k4) {
+    const float4 v = live ? __ldg(xp + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xr[4 * k4] = v.x; xr[4 * k4 + 1] = v.y; xr[4 * k4 + 2] = v.z; xr[4 * k4 + 3] = v.w;
+    part += (v.x + v.y) + (v.z + v.w);
+  }
+  const float D0 = (float)(F * CIN);
+  const float mean0 = block_sum(part) / D0;
+  part = 0.f;
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      const float dlt = xr[k] - mean0;
+      part = fmaf(dlt, dlt, part);
+    }
+  }
+  const float inv0 = 1.0f / (sqrtf(block_sum(part) / (D0 - 1.0f)) + eps);
+  // ---- the two C x CIN products of this bin, gating
+  float sum_gx = 0.f, sum_d = 0.f;
+  if (live) {
+    float lr[CIN];
+    const float4* w0 = reinterpret_cast<const float4*>(ln0_w + (size_t)tid * CIN);
+    const float4* b0 = reinterpret_cast<const float4*>(ln0_b + (size_t)tid * CIN);
+#pragma unroll
+    for (int k4 = 0; k4 < CIN / 4; ++k4) {
+      const float4 wv = __ldg(w0 + k4), bv = __ldg(b0 + k4);
+      lr[4 * k4] = (xr[4 * k4] - mean0) * inv0 * wv.x + bv.x;
+      lr[4 * k4 + 1] = (xr[4 * k4 + 1] - mean0) * inv0 * wv.y + bv.y;
+      lr[4 * k4 + 2] = (xr[4 * k4 + 2] - mean0) * inv0 * wv.z + bv.z;
+      lr[4 * k4 + 3] = (xr[4 * k4 + 3] - mean0) * inv0 * wv.w + bv.w;
+    }
+#pragma unroll 2
+    for (int o = 0; o < C; ++o) {
+      const float4* g4 = reinterpret_cast<const float4*>(wgs + o * CIN);
+      const float4* i4 = reinterpret_cast<const float4*>(wis + o * CIN);
+      float ag0 = __ldg(bg + o), ag1 = 0.f, ai0 = __ldg(bi + o), ai1 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < CIN / 4; ++k4) {
+        const float4 a = g4[k4], c4 = i4[k4];
+        ag0 = fmaf(a.y, lr[4 * k4 + 1], fmaf(a.x, lr[4 * k4], ag0));
+        ag1 = fmaf(a.w, lr[4 * k4 + 3], fmaf(a.z, lr[4 * k4 + 2], ag1));
+        ai0 = fmaf(c4.y, xr[4 * k4 + 1], fmaf(c4.x, xr[4 * k4], ai0));
+        ai1 = fmaf(c4.w, xr[4 * k4 + 3], fmaf(c4.z, xr[4 * k4 + 2], ai1));
+      }
+      const float g = 1.0f / (1.0f + expf(-(ag0 + ag1)));
+      const float xi = ai0 + ai1;
+      const float gx = g * xi, dd = xi - gx;
+      gxs[tid * LD + o] = gx;
+      ds[tid * LD + o] = dd;
+      sum_gx += gx;
+      sum_d += dd;
+    }
+  }
+  // ---- LN1 / LN2 statistics over the [F][C] blocks
+  const float D1 = (float)(F * C);
+  const float mean1 = block_sum(sum_gx) / D1;
+  const float mean2 = block_sum(sum_d) / D1;
+  float v1 = 0.f, v2 = 0.f;
+  if (live) {
+#pragma unroll
+    for (int o = 0; o < C; ++o) {
+      const float a = gxs[tid * LD + o] - mean1, c2 = ds[tid * LD + o] - mean2;
+      v1 = fmaf(a, a, v1);
+      v2 = fmaf(c2, c2, v2);
+    }
+  }
+  const float inv1 = 1.0f / (sqrtf(block_sum(v1) / (D1 - 1.0f)) + eps);
+  const float inv2 = 1.0f / (sqrtf(block_sum(v2) / (D1 - 1.0f)) + eps);
+  (void)s_stat;
+  // ---- col: padded rows [F + 2][C]; z: [C][F]
+  float* cb_ = col + b * (int64_t)(F + 2) * C;
+  for (int i = tid; i < C; i += kT) {
+    cb_[i] = 0.f;
+    cb_[(int64_t)(F + 1) * C + i] = 0.f;
+  }
+  for (int i = tid; i < F * C; i += kT) {
+    const int f = i / C, o = i - f * C;
+    cb_[C + i] = (gxs[f * LD + o] - mean1) * inv1 * __ldg(ln1_w + i) + __ldg(ln1_b + i);
+  }
+  float* zb = z + b * (int64_t)F * C;
+  for (int i = tid; i < F * C; i += kT) {
+    const int o = i / F, f = i - o * F;
+    const int src = f * C + o;
+    zb[i] = (ds[f * LD + o] - mean2) * inv2 * __ldg(ln2_w + src) + __ldg(ln2_b + src);
+  }
+}
+
 // ---------------------------------------------------------------------------------- LSTM sequences
 // Thread = one sequence; weights, the thread's x / h / c / gate columns live in shared memory
 // ([k][thread]: conflict-free), gate order i,f,g,o (PyTorch).  Sequence q = o*n_inner + i starts at
@@ -616,6 +753,37 @@ extern "C" int vadx_add_transposed_f32(const float* d_a, int64_t a_block_stride,
   add_transposed_kernel<<<g1(n_blocks * n_bins * n_channels), 256, 0, (cudaStream_t)stream>>>(d_a, a_block_stride, d_t, d_out,
                                                                                           n_blocks, n_bins, n_channels);
   return after_launch("vadx_add_transposed_f32");
+}
+
+extern "C" int vadx_cfb_front_supported(int n_in, int n_channels, int n_bins) {
+  return (n_channels == 20 && (n_in == 20 || n_in == 40) && n_bins >= 2 && n_bins <= 160) ? 1 : 0;
+}
+
+extern "C" int vadx_cfb_front_f32(const float* d_x, int64_t n_blocks, int n_bins, int n_in, int n_channels, const float* d_ln0_w,
+                                  const float* d_ln0_b, const float* d_wg, const float* d_bg, const float* d_wi, const float* d_bi,
+                                  const float* d_ln1_w, const float* d_ln1_b, const float* d_ln2_w, const float* d_ln2_b, float eps,
+                                  float* d_col, float* d_z, void* stream) {
+  StageTimer _timer(VADX_STAGE_MEL, (cudaStream_t)stream, "cfb_front_kernel",
+                    4.0 * n_blocks * n_bins * ((double)n_in + 2.0 * n_channels), 4.0 * n_blocks * n_bins * n_channels * (double)n_in);
+  VADX_REQUIRE(d_x && d_ln0_w && d_ln0_b && d_wg && d_bg && d_wi && d_bi && d_ln1_w && d_ln1_b && d_ln2_w && d_ln2_b && d_col && d_z,
+               "vadx_cfb_front_f32: null pointer");
+  VADX_REQUIRE(vadx_cfb_front_supported(n_in, n_channels, n_bins), "vadx_cfb_front_f32: shape (%d -> %d channels, %d bins) not instantiated",
+               n_in, n_channels, n_bins);
+  VADX_REQUIRE(n_blocks >= 0 && n_blocks <= 0x7fffffffLL && aligned16(d_x) && aligned16(d_ln0_w) && aligned16(d_ln0_b),
+               "vadx_cfb_front_f32: bad argument");
+  if (n_blocks == 0) return VADX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int C = 20;
+  if (n_in == 20) {
+    const size_t smem = (size_t)(2 * C * 20 + 2 * 160 * (C + 1)) * sizeof(float);
+    cfb_front_kernel<20, C><<<(unsigned)n_blocks, 160, smem, st>>>(d_x, n_bins, d_ln0_w, d_ln0_b, d_wg, d_bg, d_wi, d_bi, d_ln1_w, d_ln1_b,
+                                                                d_ln2_w, d_ln2_b, eps, d_col, d_z);
+  } else {
+    const size_t smem = (size_t)(2 * C * 40 + 2 * 160 * (C + 1)) * sizeof(float);
+    cfb_front_kernel<40, C><<<(unsigned)n_blocks, 160, smem, st>>>(d_x, n_bins, d_ln0_w, d_ln0_b, d_wg, d_bg, d_wi, d_bi, d_ln1_w, d_ln1_b,
+                                                                d_ln2_w, d_ln2_b, eps, d_col, d_z);
+  }
+  return after_launch("vadx_cfb_front_f32");
 }
 
 extern "C" int vadx_lstm_seq_f32(const float* d_x, int64_t x_outer, int64_t x_inner, int64_t x_step, float* d_y,

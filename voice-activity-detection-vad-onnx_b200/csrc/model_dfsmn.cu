@@ -135,6 +135,8 @@ int dfsmn_finalize(vadx_model* m) {
     const int cin = (i >= 6) ? 2 * c : c;       // decoder blocks 4..1 take cat(skip, previous)
     VADX_TRY(linear(n + ".gate", c, cin, true));
     VADX_TRY(linear(n + ".input", c, cin, true));
+    VADX_TRY(m->upload_raw(n + ".gate.weight", (int64_t)c * cin, VADX_DT_F32));      // reference layout for the fused front kernel
+    VADX_TRY(m->upload_raw(n + ".input.weight", (int64_t)c * cin, VADX_DT_F32));
     VADX_TRY(linear(n + ".conv", c, 3 * c, true));
     VADX_TRY(m->upload_raw(n + ".LN0.w", (int64_t)F * cin, VADX_DT_F32));
     VADX_TRY(m->upload_raw(n + ".LN0.b", (int64_t)F * cin, VADX_DT_F32));
@@ -317,6 +319,17 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
     float* P = take(B * cb * 2 * c);
     float* Pn = take(B * cb * 2 * c);
     float* hseq = take(B * cb * 2 * c);
+    // LN0 + gate + input + gating + LN1 + LN2 in one kernel (iccrn.cu, cfb_front_kernel) when the block takes the folded forms
+    const bool fuse_front = fold_conv && m->scalar("engine.fuse_front", 1.0) != 0.0 && vadx_cfb_front_supported(cin, c, F);
+    float* z = xi;
+    if (fuse_front) {
+      if (real)
+        VADX_TRY(vadx_cfb_front_f32(x, B, F, cin, c, m->d<float>(n + ".LN0.w"), m->d<float>(n + ".LN0.b"), m->d<float>(n + ".gate.weight"),
+                                    m->d<float>(n + ".gate.bias"), m->d<float>(n + ".input.weight"), m->d<float>(n + ".input.bias"),
+                                    m->d<float>(n + ".LN1.w"), m->d<float>(n + ".LN1.b"), m->d<float>(n + ".LN2.w"),
+                                    m->d<float>(n + ".LN2.b"), 1e-6f, col, z, s_));
+      VADX_TRY(lin(n + ".conv", col, c, B * (F + 2) - 2, y1, c, VADX_ACT_NONE));
+    } else {
     VADX_TRY(layernorm(x, B, F * cin, n + ".LN0", ln0));
     VADX_TRY(lin(n + ".gate", ln0, cin, R, g, c, VADX_ACT_SIGMOID));
     VADX_TRY(lin(n + ".input", x, cin, R, xi, c, VADX_ACT_NONE));
@@ -331,15 +344,16 @@ int dfsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, 
       if (real) VADX_TRY(vadx_im2col_f3_f32(ln1, col, B, F, c, s_));
       VADX_TRY(lin(n + ".conv", col, 3 * c, R, y1, c, VADX_ACT_NONE));
     }
+    }
     // cepstral unit on LN2(xi - gx): DFT over the bins per channel, bi-LSTM along the cepstral bins, complex gain, IDFT.
     // Every layout change is folded into a neighbour (iccrn.cu): LN2 writes [c][F], the cepstral LayerNorm reads the DFT's
     // native [c][re | im][cb] output and writes cepstral-major rows, the complex gain writes the DFT layout back, the last add
     // reads the inverse DFT transposed.  ("engine.fold_permutes" = 0: the literal sequence with four permute4 launches.)
     float* ln2 = g;                                                          // g and xi are dead from here on
-    float* z = xi;
     if (fold) {
-      if (real) VADX_TRY(vadx_layernorm_perm_f32(d, B, F, c, 1, 1, 0, 2, m->d<float>(n + ".LN2.w"), m->d<float>(n + ".LN2.b"), 0, 1e-6f,
-                                                 z, 0, 0, s_));              // [B][c][F]
+      if (real && !fuse_front)
+        VADX_TRY(vadx_layernorm_perm_f32(d, B, F, c, 1, 1, 0, 2, m->d<float>(n + ".LN2.w"), m->d<float>(n + ".LN2.b"), 0, 1e-6f,
+                                         z, 0, 0, s_));                      // [B][c][F]
       VADX_TRY(lin("ceps.dft", z, F, B * c, spec, 2 * cb, VADX_ACT_NONE));   // [B][c][re(cb) | im(cb)]
       if (real) VADX_TRY(vadx_layernorm_perm_f32(spec, B, c, 2, cb, 2, 1, 0, m->d<float>(n + ".cLN.w"), m->d<float>(n + ".cLN.b"), 1,
                                                  1e-6f, Pn, 0, 0, s_));      // [B][cb][2][c]

@@ -70,6 +70,8 @@ SIGNATURES = {
     "vadx_softmax_class0_f32": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "vadx_frame_energy_log10_f32": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
     "vadx_fsmn_gate": (C.c_int, [_vp, _vp, _vp, _f32, _f32, _i64, _i32, _vp, _vp, _vp]),
+    "vadx_cfb_front_supported": (C.c_int, [_i32, _i32, _i32]),
+    "vadx_cfb_front_f32": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "vadx_layernorm_perm_f32": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, C.c_float, _vp, _i64, _i32, _vp]),
     "vadx_ceps_cmul_t_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "vadx_add_transposed_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
