@@ -153,26 +153,33 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
   float* wis = wgs + C * CIN;             // [C][CIN]
   float* gxs = wis + C * CIN;             // [F][LD]
   float* ds = gxs + kT * LD;              // [F][LD]
-  __shared__ float red[kT];
-  __shared__ float s_stat[2];
+  __shared__ float red[4 * 16];
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
   for (int i = tid; i < C * CIN; i += kT) {
     wgs[i] = wg[i];
     wis[i] = wi[i];
   }
-  // block reduction with the tree of layernorm_kernel (its 256-thread tree over 160 partial sums: the upper slots are zero)
-  auto block_sum = [&](float v) -> float {
-    __syncthreads();
-    red[tid] = v;
-    __syncthreads();
-    if (tid < 32) red[tid] += (tid + 128 < kT) ? red[tid + 128] : 0.f;
-    __syncthreads();
-    for (int off = 64; off > 0; off >>= 1) {
-      if (tid < off) red[tid] += red[tid + off];
-      __syncthreads();
+  // block sums of up to two values at once: warp shuffles, one partial per warp in a slot of its own (no slot is reused, so
+  // one barrier per reduction)
+  const int lane = tid & 31, warp = tid >> 5;
+  auto block_sum2 = [&](float va, float vb, int slot, float& ra, float& rb) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      va += __shfl_xor_sync(0xffffffffu, va, off);
+      vb += __shfl_xor_sync(0xffffffffu, vb, off);
     }
-    return red[0];
+    if (lane == 0) {
+      red[slot * 16 + warp] = va;
+      red[slot * 16 + 8 + warp] = vb;
+    }
+    __syncthreads();
+    ra = rb = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kT / 32; ++wq) {
+      ra += red[slot * 16 + wq];
+      rb += red[slot * 16 + 8 + wq];
+    }
   };
   // ---- LN0 statistics over the [F][CIN] block; the thread keeps ITS row
   const bool live = tid < F;
@@ -186,7 +193,9 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
     part += (v.x + v.y) + (v.z + v.w);
   }
   const float D0 = (float)(F * CIN);
-  const float mean0 = block_sum(part) / D0;
+  float r0, r1;
+  block_sum2(part, 0.f, 0, r0, r1);
+  const float mean0 = r0 / D0;
   part = 0.f;
   if (live) {
 #pragma unroll
@@ -195,7 +204,8 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
       part = fmaf(dlt, dlt, part);
     }
   }
-  const float inv0 = 1.0f / (sqrtf(block_sum(part) / (D0 - 1.0f)) + eps);
+  block_sum2(part, 0.f, 1, r0, r1);
+  const float inv0 = 1.0f / (sqrtf(r0 / (D0 - 1.0f)) + eps);
   // ---- the two C x CIN products of this bin, gating
   float sum_gx = 0.f, sum_d = 0.f;
   if (live) {
@@ -234,8 +244,8 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
   }
   // ---- LN1 / LN2 statistics over the [F][C] blocks
   const float D1 = (float)(F * C);
-  const float mean1 = block_sum(sum_gx) / D1;
-  const float mean2 = block_sum(sum_d) / D1;
+  block_sum2(sum_gx, sum_d, 2, r0, r1);
+  const float mean1 = r0 / D1, mean2 = r1 / D1;
   float v1 = 0.f, v2 = 0.f;
   if (live) {
 #pragma unroll
@@ -245,9 +255,9 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
       v2 = fmaf(c2, c2, v2);
     }
   }
-  const float inv1 = 1.0f / (sqrtf(block_sum(v1) / (D1 - 1.0f)) + eps);
-  const float inv2 = 1.0f / (sqrtf(block_sum(v2) / (D1 - 1.0f)) + eps);
-  (void)s_stat;
+  block_sum2(v1, v2, 3, r0, r1);
+  const float inv1 = 1.0f / (sqrtf(r0 / (D1 - 1.0f)) + eps);
+  const float inv2 = 1.0f / (sqrtf(r1 / (D1 - 1.0f)) + eps);
   // ---- col: padded rows [F + 2][C]; z: [C][F]
   float* cb_ = col + b * (int64_t)(F + 2) * C;
   for (int i = tid; i < C; i += kT) {
