@@ -255,3 +255,28 @@ def test_cuda_graph_replay_is_bit_identical(cuda, wts, golden_dir):
     a = fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1234))
     b = fsmn_vad.run_vad(audio, sess, 0.0, rng=np.random.RandomState(1234), graph=True)
     assert np.array_equal(a.saved, b.saved) and a.timestamps == b.timestamps
+
+
+def test_fp16_io_contract(cuda, wts):
+    """The I/O contract of the reference's fp16-optimised export (FSMN/Inference_FSMN_VAD_ONNX.py:42,157-160): the script keys
+    on `_inputs_meta[1].type` and then feeds float16 caches / threshold / noise level.  The engine keeps fp32-grade arithmetic;
+    outputs are the fp32 graph's rounded to float16."""
+    cfg = W.FsmnConfig()
+    s16 = vadx.FsmnSession(wts, cfg, chunk_len=16000, io_dtype="float16")
+    s32 = vadx.FsmnSession(wts, cfg, chunk_len=16000)
+    assert "float16" in s16._inputs_meta[1].type and "float16" not in s32._inputs_meta[1].type
+    a = synth.synth_streams(1, 16000, seed=3)[:, None, :]
+    rs = np.random.RandomState(0)
+    c16 = [(rs.normal(size=(1, 128, 19, 1)) * 0.3).astype(np.float16) for _ in range(4)]
+    feed16 = {"audio": a, "one_minus_speech_threshold": np.array([1.0], np.float16), "noise_average_dB": np.array([4.0], np.float16)}
+    feed32 = {"audio": a, "one_minus_speech_threshold": np.array([1.0], np.float32), "noise_average_dB": np.array([4.0], np.float32)}
+    for i in range(4):
+        feed16[f"cache_{i}"] = c16[i]
+        feed32[f"cache_{i}"] = c16[i].astype(np.float32)
+    o16, o32 = s16.run(None, feed16), s32.run(None, feed32)
+    assert np.array_equal(o16[0], o32[0]) and o16[0].dtype == np.uint8
+    for i in range(1, 5):
+        assert o16[i].dtype == np.float16 and np.array_equal(o16[i], o32[i].astype(np.float16))
+    assert o16[5].dtype == np.float16 and o16[5] == np.float16(o32[5])
+    with pytest.raises(ValueError):
+        s16.run(None, feed32)

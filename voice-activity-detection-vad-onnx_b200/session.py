@@ -317,7 +317,15 @@ class FsmnSession:
     OUTPUT_NAMES = ["score", "cache_0_out", "cache_1_out", "cache_2_out", "cache_3_out", "noisy_dB"]
 
     def __init__(self, weights: dict, cfg: W.FsmnConfig = W.FsmnConfig(), chunk_len: int = 16000,
-                 tensor_cores: bool = True):
+                 tensor_cores: bool = True, io_dtype: str = "float32"):
+        """io_dtype = "float16" gives the I/O contract of the reference's fp16-optimised export (Optimize_ONNX.py
+        `use_fp16`, `convert_float_to_float16(keep_io_types=False)`): caches, threshold, noise level and noisy_dB travel as
+        float16 and `_inputs_meta[1].type` says so, which is what the inference script keys on (:42,:157-160).  The arithmetic
+        inside stays the fp32-grade engine (the ORT fp16 kernels' own rounding is not reproducible here):
+        results are the fp32 graph's, rounded to float16 at the boundary."""
+        if io_dtype not in ("float32", "float16"):
+            raise ValueError("FsmnSession: io_dtype must be 'float32' or 'float16'")
+        self.io_dtype = np.float16 if io_dtype == "float16" else np.float32
         self.cfg, self.chunk_len = cfg, int(chunk_len)
         if self.chunk_len < cfg.n_fft:
             raise ValueError(f"FsmnSession: chunk_len {chunk_len} is shorter than the {cfg.n_fft}-sample energy frame")
@@ -348,13 +356,14 @@ class FsmnSession:
         self.T = self._e.output_frames(self.chunk_len)
         self.cache_shape = (cfg.proj_dim, (cfg.lorder - 1) * cfg.lstride)
         cs = [1, cfg.proj_dim, (cfg.lorder - 1) * cfg.lstride, 1]
+        ft = "tensor(float16)" if self.io_dtype == np.float16 else "tensor(float)"
         self._inputs_meta = [NodeArg("audio", [1, 1, self.chunk_len], "tensor(int16)")]
-        self._inputs_meta += [NodeArg(f"cache_{i}", cs, "tensor(float)") for i in range(cfg.fsmn_layers)]
-        self._inputs_meta += [NodeArg("one_minus_speech_threshold", [1], "tensor(float)"),
-                              NodeArg("noise_average_dB", [1], "tensor(float)")]
+        self._inputs_meta += [NodeArg(f"cache_{i}", cs, ft) for i in range(cfg.fsmn_layers)]
+        self._inputs_meta += [NodeArg("one_minus_speech_threshold", [1], ft),
+                              NodeArg("noise_average_dB", [1], ft)]
         self._outputs_meta = [NodeArg("score", [self.T], "tensor(uint8)")]
-        self._outputs_meta += [NodeArg(f"cache_{i}_out", cs, "tensor(float)") for i in range(cfg.fsmn_layers)]
-        self._outputs_meta += [NodeArg("noisy_dB", [], "tensor(float)")]
+        self._outputs_meta += [NodeArg(f"cache_{i}_out", cs, ft) for i in range(cfg.fsmn_layers)]
+        self._outputs_meta += [NodeArg("noisy_dB", [], ft)]
         self._thr = 1.0
 
     def get_inputs(self):
@@ -450,13 +459,18 @@ class FsmnSession:
         caches = []
         for i in range(self.cfg.fsmn_layers):
             c = np.asarray(input_feed[f"cache_{i}"])
-            if c.dtype != np.float32 or c.shape != (1,) + self.cache_shape + (1,):
-                raise ValueError(f"InvalidArgument: 'cache_{i}' must be fp32 of shape {(1,) + self.cache_shape + (1,)}")
-            caches.append(torch.from_numpy(np.ascontiguousarray(c[..., 0])).cuda())
+            if c.dtype != self.io_dtype or c.shape != (1,) + self.cache_shape + (1,):
+                raise ValueError(f"InvalidArgument: 'cache_{i}' must be {np.dtype(self.io_dtype).name} of shape "
+                                 f"{(1,) + self.cache_shape + (1,)}")
+            caches.append(torch.from_numpy(np.ascontiguousarray(c[..., 0], dtype=np.float32)).cuda())
+        for k in ("one_minus_speech_threshold", "noise_average_dB"):
+            if np.asarray(input_feed[k]).dtype != self.io_dtype:
+                raise ValueError(f"InvalidArgument: '{k}' must be {np.dtype(self.io_dtype).name}")
         thr = float(np.asarray(input_feed["one_minus_speech_threshold"], np.float32).reshape(-1)[0])
         noise = torch.from_numpy(np.asarray(input_feed["noise_average_dB"], np.float32).reshape(1)).cuda()
         score, new, noisy, _, _ = self.run_batch(torch.from_numpy(a[0]).cuda(), caches, noise, thr)
-        outs = [score[0].cpu().numpy()] + [c.cpu().numpy()[..., None] for c in new] + [noisy[0].cpu().numpy()]
+        outs = ([score[0].cpu().numpy()] + [c.cpu().numpy()[..., None].astype(self.io_dtype, copy=False) for c in new]
+                + [noisy[0].cpu().numpy().astype(self.io_dtype, copy=False)])
         if output_names is None:
             return outs
         return [outs[names.index(n)] for n in output_names]
