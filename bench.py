@@ -287,8 +287,9 @@ def family_workloads(dev, only=None):
         S, stride = 1024, 16000 - 31 * 160
         n = 16000 + 3 * stride
         a = torch.from_numpy(synth.synth_chunks_fast(S, n, seed=11)).to(dev)
-        yield "fsmn", dict(step=lambda: fsmn_vad.run_streams(sess, a, stride), eager=None, audio_s=S * n / 16000, steps=3, warm=3,
-                           config=f"{S} streams/GPU x 4 windows of 16000 samples (stride {stride}), caches + hysteresis on device")
+        yield "fsmn", dict(step=lambda: fsmn_vad.run_streams(sess, a, stride, whole=True), eager=None, audio_s=S * n / 16000, steps=3,
+                           warm=3, config=f"{S} streams/GPU x 4 windows of 16000 samples (stride {stride}), all windows in one forward "
+                                          "(whole-file mode), caches + gate + hysteresis on device")
         del sess, a
     if want("marblenet"):
         # MarbleNet (config 2): 60 s clips, the survey's 256 clips per GPU

@@ -270,6 +270,11 @@ int vadx_fsmn_gate_hysteresis_windows(const float* d_p_sil, const float* d_power
                                       uint8_t* d_saved, int64_t ld_saved, float* d_noise_avg, float snr_threshold,
                                       void* stream);
 
+/* whole-file mode helper: d_out [S*W][n_samples] = the W windows of every recording, window w of stream s starting at
+ * d_in + s*stream_stride + w*window_stride */
+int vadx_gather_windows_i16(const int16_t* d_in, int64_t stream_stride, int64_t n_streams, int n_windows, int64_t window_stride,
+                            int64_t n_samples, int16_t* d_out, void* stream);
+
 /* a14 -- runs of non-silence flags -> (start, end-exclusive) frame pairs per stream
  * (vad_to_timestamps, FSMN/Inference_FSMN_VAD_ONNX.py:124-141). */
 int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags, int64_t n_streams,

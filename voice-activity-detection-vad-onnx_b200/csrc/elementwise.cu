@@ -322,17 +322,18 @@ extern "C" int vadx_prep_audio(const void* d_audio, int in_dtype, int64_t n_stre
                (long long)n_streams, (long long)n_samples, (long long)in_stride, (long long)pad_left,
                (long long)out_stride);
   VADX_REQUIRE(preemph_mode >= 0 && preemph_mode <= 2, "vadx_prep_audio: preemph_mode %d", preemph_mode);
-  VADX_REQUIRE(n_streams <= 65535, "vadx_prep_audio: at most 65535 streams per call (got %lld)", (long long)n_streams);
   if (n_streams == 0) return VADX_OK;
   int chunks = remove_dc ? 1 : (int)std::min<int64_t>(ceil_div(out_stride, 256 * 16), 1024);
-  dim3 grid((unsigned)chunks, (unsigned)n_streams);
   cudaStream_t st = (cudaStream_t)stream;
-  if (in_dtype == VADX_DT_I16)
-    prep_audio_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)d_audio, n_samples, in_stride, scale, remove_dc,
-                                                     preemph_mode, preemph, pad_left, d_out, out_stride);
-  else
-    prep_audio_kernel<float><<<grid, 256, 0, st>>>((const float*)d_audio, n_samples, in_stride, scale, remove_dc,
-                                                   preemph_mode, preemph, pad_left, d_out, out_stride);
+  for (int64_t s0 = 0; s0 < n_streams; s0 += 65535) {            // grid.y carries the stream: 65535 rows per launch
+    dim3 grid((unsigned)chunks, (unsigned)std::min<int64_t>(65535, n_streams - s0));
+    if (in_dtype == VADX_DT_I16)
+      prep_audio_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)d_audio + s0 * in_stride, n_samples, in_stride, scale,
+                                                       remove_dc, preemph_mode, preemph, pad_left, d_out + s0 * out_stride, out_stride);
+    else
+      prep_audio_kernel<float><<<grid, 256, 0, st>>>((const float*)d_audio + s0 * in_stride, n_samples, in_stride, scale, remove_dc,
+                                                     preemph_mode, preemph, pad_left, d_out + s0 * out_stride, out_stride);
+  }
   return after_launch("vadx_prep_audio");
 }
 

@@ -228,6 +228,19 @@ __global__ void __launch_bounds__(128) fsmn_gate_hysteresis_windows_kernel(
   }
 }
 
+// whole-file mode: the W overlapping windows of every recording as dense rows [S*W][L] (int16), so that the batched
+// frontend kernels see ordinary streams
+__global__ void __launch_bounds__(256) gather_windows_i16_kernel(const int16_t* __restrict__ in, int64_t stream_stride,
+                                                                 int64_t n_streams, int W, int64_t window_stride, int64_t L,
+                                                                 int16_t* __restrict__ out) {
+  const int64_t total = n_streams * W * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / L, k = i - row * L;
+    const int64_t s = row / W, w = row - s * W;
+    out[i] = in[s * stream_stride + w * window_stride + k];
+  }
+}
+
 // a14: runs of "not silence" -> (start, end-exclusive) frame pairs
 __global__ void __launch_bounds__(128) runs_to_segments_kernel(const uint8_t* __restrict__ silence_flags, int64_t ld,
                                                                const int32_t* __restrict__ n_flags, int64_t n_streams,
@@ -350,6 +363,18 @@ extern "C" int vadx_fsmn_gate_hysteresis_windows(const float* d_p_sil, const flo
       d_p_sil, d_power_dB, n_windows, n_frames, one_minus_speech_threshold, speech_2_noise_ratio, look_backward, speaking_score,
       silence_score, d_score, d_noisy_dB, d_noise_in, d_silence_state, d_n_saved, d_saved, ld_saved, d_noise_avg, snr_threshold);
   return after_launch("vadx_fsmn_gate_hysteresis_windows");
+}
+
+extern "C" int vadx_gather_windows_i16(const int16_t* d_in, int64_t stream_stride, int64_t n_streams, int n_windows,
+                                       int64_t window_stride, int64_t n_samples, int16_t* d_out, void* stream) {
+  StageTimer _timer(VADX_STAGE_PREP, (cudaStream_t)stream, "gather_windows_i16_kernel", 4.0 * n_streams * n_windows * n_samples);
+  VADX_REQUIRE(d_in && d_out && n_streams >= 0 && n_windows >= 1 && window_stride >= 1 && n_samples >= 1 &&
+                   stream_stride >= n_samples + (int64_t)(n_windows - 1) * window_stride,
+               "vadx_gather_windows_i16: bad argument");
+  if (n_streams == 0) return VADX_OK;
+  gather_windows_i16_kernel<<<grid_for(n_streams * n_windows * n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_in, stream_stride, n_streams, n_windows, window_stride, n_samples, d_out);
+  return after_launch("vadx_gather_windows_i16");
 }
 
 extern "C" int vadx_runs_to_segments(const uint8_t* d_silence_flags, int64_t ld, const int32_t* d_n_flags,

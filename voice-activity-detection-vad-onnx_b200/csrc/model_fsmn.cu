@@ -21,6 +21,7 @@ int vadx_softmax_class0_f32(const float*, int64_t, int64_t, int, float*, void*);
 int vadx_frame_energy_log10_f32(const float*, int64_t, int64_t, int64_t, int, int, int, int, float, float, float*,
                                 void*);
 int vadx_fsmn_gate(const float*, const float*, const float*, float, float, int64_t, int, uint8_t*, float*, void*);
+int vadx_gather_windows_i16(const int16_t*, int64_t, int64_t, int, int64_t, int64_t, int16_t*, void*);
 }
 
 namespace {
@@ -133,6 +134,7 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   float* power_db_ws = ws.take<float>(rows);
   float* mean_ws = ws.take<float>(S);
   int32_t* mean_int_ws = ws.take<int32_t>(S);
+  int16_t* win16 = W > 1 ? ws.take<int16_t>(S * L) : nullptr;       // whole-file mode: the windows as dense int16 rows
   if (need) *need = ws.off;
   if (dry) return VADX_OK;
   if (ws.off > ws_bytes) {
@@ -160,16 +162,16 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
   const bool use_tc = m->scalar("engine.use_tc", 1.0) != 0.0 && rows > kSkinnyMaxRows;
   const int mel_max = (int)(m->find("frontend.mel_w")->numel() / h.n_mels);
 
-  if (W == 1) {
-    VADX_TRY(vadx_prep_audio(in[0], VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,
-                             h.pad_left(), sig, Lp, st));
-  } else {
-    for (int64_t s = 0; s < S_streams; ++s)      // the W windows of one stream are rows `wstride` samples apart
-      VADX_TRY(vadx_prep_audio(static_cast<const int16_t*>(in[0]) + s * sstride, VADX_DT_I16, W, L, wstride, 1.0f, 1,
-                               preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph, h.pad_left(), sig + s * W * Lp, Lp, st));
+  const int16_t* audio = static_cast<const int16_t*>(in[0]);
+  if (W > 1) {
+    // the W windows of every stream become ordinary rows; everything below is the batched single-window path over S*W rows
+    VADX_TRY(vadx_gather_windows_i16(audio, sstride, S_streams, W, wstride, L, win16, st));
+    audio = win16;
   }
-  const uint8_t* stft_img = (use_tc && W == 1) ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
-  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(in[0])) {
+  VADX_TRY(vadx_prep_audio(audio, VADX_DT_I16, S, L, L, 1.0f, 1, preemph > 0.f ? VADX_PREEMPH_KEEP_FIRST : 0, preemph,
+                           h.pad_left(), sig, Lp, st));
+  const uint8_t* stft_img = use_tc ? m->d<uint8_t>("frontend.basis#TC") : nullptr;
+  if (stft_img && (L % 8) == 0 && (h.hop % 8) == 0 && (h.pad_left() % 8) == 0 && aligned16(audio)) {
     // framed DFT on the tensor cores straight from the int16 samples; the mean is removed in the epilogue
     const std::string key = "frontend.dc#" + std::to_string((long long)L);
     const std::string k_lo = key + ".lo", k_hi = key + ".hi";
@@ -186,8 +188,8 @@ int fsmn_run(vadx_model* m, bool dry, const void* const* in, void* const* out, v
       m->scalars[k_lo] = lo;
       m->scalars[k_hi] = hi;
     }
-    VADX_TRY(vadx_stream_mean_i16(static_cast<const int16_t*>(in[0]), L, L, S, mean_ws, mean_int_ws, st));
-    VADX_TRY(vadx_stft_power_tc_i16_ex(static_cast<const int16_t*>(in[0]), L, L, S, T, h.hop, h.n_taps(), stft_img, h.n_bins(),
+    VADX_TRY(vadx_stream_mean_i16(audio, L, L, S, mean_ws, mean_int_ws, st));
+    VADX_TRY(vadx_stft_power_tc_i16_ex(audio, L, L, S, T, h.hop, h.n_taps(), stft_img, h.n_bins(),
                                        power, h.ld_power(), h.pad_left(), mean_ws, mean_int_ws, m->d<float>(key),
                                        (int)m->scalar(k_lo.c_str(), 0.0), (int)m->scalar(k_hi.c_str(), (double)T), 1.0f,
                                        VADX_TC_FMT_BF16, st));

@@ -80,6 +80,7 @@ SIGNATURES = {
     "vadx_reflect_windows_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp]),
     "vadx_silero_lstm_windows_f32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, C.c_float, _vp, _i64, _i32, _i32, _vp]),
     "vadx_stft_mag_compact_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "vadx_gather_windows_i16": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i64, _vp, _vp]),
     "vadx_fsmn_gate_hysteresis_windows": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.c_float, C.c_float, _i32, C.c_double, C.c_double,
                                                     _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, _vp]),
     "vadx_lookahead_hysteresis": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _i32, C.c_double, C.c_double, _i32, _vp, _vp,
