@@ -294,6 +294,8 @@ int vadx_reflect_window_f32(const float* d_x, int64_t in_stride, int64_t n_strea
 int vadx_reflect_windows_f32(const float* d_x, int64_t in_stride, int64_t n_streams, int n_windows, int64_t window_step,
                              int n_in, int pad, float* d_out, void* stream);
 int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream);
+/* y[i] = a * x[i] + b (MarbleNet's fused tail: P(silence) = 1 - P(active) of the two-class softmax head) */
+int vadx_affine_f32(const float* d_x, float a, float b, float* d_y, int64_t n, void* stream);
 int vadx_lstm_cell_f32(const float* d_gates, const float* d_c_in, float* d_h_out, float* d_c_out, float* d_h_relu,
                        int64_t n_streams, int hidden, void* stream);
 

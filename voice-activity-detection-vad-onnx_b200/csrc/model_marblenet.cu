@@ -5,6 +5,7 @@
 // (+folded BN bias, +residual, ReLU)]* -> 2-class softmax head.
 #include "model.hpp"
 
+extern "C" int vadx_affine_f32(const float*, float, float, float*, int64_t, void*);
 extern "C" int vadx_depthwise_conv1d_f32(const float*, int64_t, const float*, int, int, int, int, float*, int64_t,
                                          int64_t, int, int, int, void*);
 
@@ -118,6 +119,35 @@ int marblenet_finalize(vadx_model* m) {
   }
   VADX_TRY(m->upload_linear("decoder.weight", h.n_classes, c_in));
   VADX_TRY(m->upload_raw("decoder.bias", h.n_classes, VADX_DT_F32));
+  // Fused tail: when the last block is a single k = 1 separable block (marblenet_3x2x64: 128 x k1) its depthwise conv is a
+  // per-channel scale that folds into the pointwise weight, and a 2-class softmax head is sigmoid((w1 - w0).y + b1 - b0): the
+  // last pointwise layer and the head then run as ONE tensor-core kernel (vadx_linear_head_tc_f32), its 128-wide output
+  // never leaves the SM.
+  const Block& lb = h.blocks.back();
+  if (h.n_classes == 2 && lb.repeat == 1 && lb.kernel == 1 && lb.stride == 1 && !lb.residual && h.blocks.size() >= 2) {
+    const int cl = h.blocks[h.blocks.size() - 2].filters;                 // input channels of the last block
+    const std::string p = "b" + std::to_string(h.blocks.size() - 1) + ".r0.";
+    const HostTensor* dw = m->find(p + "dw");
+    const HostTensor* pw = m->find(p + "pw");
+    const HostTensor* dec = m->find("decoder.weight");
+    const HostTensor* db = m->find("decoder.bias");
+    if (dw && pw && dec && db && vadx_tc_supported(cl, lb.filters)) {
+      HostTensor f;
+      f.dtype = VADX_DT_F32;
+      f.dims = {lb.filters, cl};
+      f.bytes.resize((size_t)lb.filters * cl * sizeof(float));
+      float* w = reinterpret_cast<float*>(f.bytes.data());
+      for (int o = 0; o < lb.filters; ++o)
+        for (int c = 0; c < cl; ++c) w[(size_t)o * cl + c] = pw->f32()[(size_t)o * cl + c] * dw->f32()[c];
+      m->host["tail.pw_folded"] = std::move(f);
+      VADX_TRY(m->upload_linear("tail.pw_folded", lb.filters, cl));
+      std::vector<float> diff((size_t)lb.filters);
+      for (int o = 0; o < lb.filters; ++o) diff[o] = dec->f32()[(size_t)lb.filters + o] - dec->f32()[o];
+      VADX_TRY(m->upload("tail.head_w", diff.data(), diff.size() * sizeof(float)));
+      m->scalars["derived.tail_head_b"] = (double)(db->f32()[1] - db->f32()[0]);
+      m->scalars["derived.tail_fused"] = 1.0;
+    }
+  }
   return VADX_OK;
 }
 
@@ -214,8 +244,21 @@ int marblenet_run(vadx_model* m, bool dry, const void* const* in, void* const* o
                            rows, n_in, n_out, act, st);
   };
   int c_in = h.feat_in, t = T0;
+  const bool fused_tail = use_tc && S * (int64_t)Tout > kSkinnyMaxRows && m->scalar("derived.tail_fused", 0.0) != 0.0 &&
+                          m->scalar("engine.fuse_tail", 1.0) != 0.0 && m->d<uint8_t>("tail.pw_folded#TC");
   for (size_t bi = 0; bi < h.blocks.size(); ++bi) {
     const Block& k = h.blocks[bi];
+    if (fused_tail && bi + 1 == h.blocks.size()) {
+      // last block + decoder: p_active = sigmoid(head . relu(W' x + b)), p_silence = 1 - p_active
+      const int64_t rows = S * (int64_t)t;
+      float* planes = static_cast<float*>(out[0]);
+      const std::string p = "b" + std::to_string(bi) + ".r0.";
+      VADX_TRY(vadx_linear_head_tc_f32(B[0], c_in, m->d<uint8_t>("tail.pw_folded#TC"), m->d<float>(p + "pw_bias"), rows, c_in,
+                                       k.filters, VADX_ACT_RELU, m->d<float>("tail.head_w"),
+                                       (float)m->scalar("derived.tail_head_b", 0.0), planes + rows, st));
+      VADX_REQUIRE(t == Tout, "marblenet: internal frame-count mismatch (%d vs %d)", t, Tout);
+      return vadx_affine_f32(planes + rows, -1.0f, 1.0f, planes, rows, st);
+    }
     const std::string bp = "b" + std::to_string(bi) + ".";
     if (k.residual)
       VADX_TRY(lin(B[0], c_in, bp + "res", bp + "res_bias", nullptr, B[4], k.filters, S * (int64_t)t, VADX_ACT_NONE));

@@ -25,6 +25,11 @@ __global__ void __launch_bounds__(256) sqrt_kernel(float* __restrict__ p, int64_
     p[i] = sqrtf(p[i]);
 }
 
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float a, float b, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], b);
+}
+
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 // PyTorch LSTMCell gate order (i, f, g, o); state = [h ; c] planes of [S][H]
@@ -238,6 +243,14 @@ extern "C" int vadx_reflect_windows_f32(const float* d_x, int64_t in_stride, int
   reflect_window_kernel<<<grid1d(n_streams * n_windows * (n_in + pad)), 256, 0, (cudaStream_t)stream>>>(
       d_x, in_stride, n_streams, n_windows, window_step, n_in, pad, d_out);
   return after_launch("vadx_reflect_windows_f32");
+}
+
+extern "C" int vadx_affine_f32(const float* d_x, float a, float b, float* d_y, int64_t n, void* stream) {
+  StageTimer _timer(VADX_STAGE_HEAD, (cudaStream_t)stream, "affine_kernel", 8.0 * n);
+  VADX_REQUIRE(d_x && d_y && n >= 0, "vadx_affine_f32: bad argument");
+  if (n == 0) return VADX_OK;
+  affine_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(d_x, a, b, d_y, n);
+  return after_launch("vadx_affine_f32");
 }
 
 extern "C" int vadx_sqrt_inplace_f32(float* d_p, int64_t n, void* stream) {

@@ -77,6 +77,7 @@ SIGNATURES = {
     "vadx_add_transposed_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
     "vadx_lstm_recurrence_supported": (C.c_int, [_i32]),
     "vadx_lstm_recurrence_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "vadx_affine_f32": (C.c_int, [_vp, C.c_float, C.c_float, _vp, _i64, _vp]),
     "vadx_reflect_windows_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _i32, _vp, _vp]),
     "vadx_silero_lstm_windows_f32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, C.c_float, _vp, _i64, _i32, _i32, _vp]),
     "vadx_stft_mag_compact_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
