@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) layernorm_perm_kernel(const float* __rest
 // registers, the two C x CIN weights are broadcast from shared memory, gx / d go to odd-stride shared-memory rows for the two
 // block statistics.  LayerNorm = (v - mean) / (unbiased std + eps) * w + b over the whole [F][.] block, as layernorm_kernel.
 template <int CIN, int C>
-__global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restrict__ x, int F, const float* __restrict__ ln0_w,
+__global__ void __launch_bounds__(160, 4) cfb_front_kernel(const float* __restrict__ x, int F, const float* __restrict__ ln0_w,
                                                           const float* __restrict__ ln0_b, const float* __restrict__ wg,
                                                           const float* __restrict__ bg, const float* __restrict__ wi,
                                                           const float* __restrict__ bi, const float* __restrict__ ln1_w,
@@ -206,35 +206,45 @@ __global__ void __launch_bounds__(160, 3) cfb_front_kernel(const float* __restri
   }
   block_sum2(part, 0.f, 1, r0, r1);
   const float inv0 = 1.0f / (sqrtf(r0 / (D0 - 1.0f)) + eps);
-  // ---- the two C x CIN products of this bin, gating
+  // ---- the two C x CIN products of this bin, gating.  Two passes over ONE register copy of the row (the input product on
+  // the raw row first, its results parked in the thread's shared-memory row; then the row is normalised in place for the gate
+  // product): 40 instead of 80 row registers, one more resident CTA per SM
   float sum_gx = 0.f, sum_d = 0.f;
   if (live) {
-    float lr[CIN];
+#pragma unroll 2
+    for (int o = 0; o < C; ++o) {
+      const float4* i4 = reinterpret_cast<const float4*>(wis + o * CIN);
+      float ai0 = __ldg(bi + o), ai1 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < CIN / 4; ++k4) {
+        const float4 c4 = i4[k4];
+        ai0 = fmaf(c4.y, xr[4 * k4 + 1], fmaf(c4.x, xr[4 * k4], ai0));
+        ai1 = fmaf(c4.w, xr[4 * k4 + 3], fmaf(c4.z, xr[4 * k4 + 2], ai1));
+      }
+      ds[tid * LD + o] = ai0 + ai1;
+    }
     const float4* w0 = reinterpret_cast<const float4*>(ln0_w + (size_t)tid * CIN);
     const float4* b0 = reinterpret_cast<const float4*>(ln0_b + (size_t)tid * CIN);
 #pragma unroll
     for (int k4 = 0; k4 < CIN / 4; ++k4) {
       const float4 wv = __ldg(w0 + k4), bv = __ldg(b0 + k4);
-      lr[4 * k4] = (xr[4 * k4] - mean0) * inv0 * wv.x + bv.x;
-      lr[4 * k4 + 1] = (xr[4 * k4 + 1] - mean0) * inv0 * wv.y + bv.y;
-      lr[4 * k4 + 2] = (xr[4 * k4 + 2] - mean0) * inv0 * wv.z + bv.z;
-      lr[4 * k4 + 3] = (xr[4 * k4 + 3] - mean0) * inv0 * wv.w + bv.w;
+      xr[4 * k4] = (xr[4 * k4] - mean0) * inv0 * wv.x + bv.x;
+      xr[4 * k4 + 1] = (xr[4 * k4 + 1] - mean0) * inv0 * wv.y + bv.y;
+      xr[4 * k4 + 2] = (xr[4 * k4 + 2] - mean0) * inv0 * wv.z + bv.z;
+      xr[4 * k4 + 3] = (xr[4 * k4 + 3] - mean0) * inv0 * wv.w + bv.w;
     }
 #pragma unroll 2
     for (int o = 0; o < C; ++o) {
       const float4* g4 = reinterpret_cast<const float4*>(wgs + o * CIN);
-      const float4* i4 = reinterpret_cast<const float4*>(wis + o * CIN);
-      float ag0 = __ldg(bg + o), ag1 = 0.f, ai0 = __ldg(bi + o), ai1 = 0.f;
+      float ag0 = __ldg(bg + o), ag1 = 0.f;
 #pragma unroll
       for (int k4 = 0; k4 < CIN / 4; ++k4) {
-        const float4 a = g4[k4], c4 = i4[k4];
-        ag0 = fmaf(a.y, lr[4 * k4 + 1], fmaf(a.x, lr[4 * k4], ag0));
-        ag1 = fmaf(a.w, lr[4 * k4 + 3], fmaf(a.z, lr[4 * k4 + 2], ag1));
-        ai0 = fmaf(c4.y, xr[4 * k4 + 1], fmaf(c4.x, xr[4 * k4], ai0));
-        ai1 = fmaf(c4.w, xr[4 * k4 + 3], fmaf(c4.z, xr[4 * k4 + 2], ai1));
+        const float4 a = g4[k4];
+        ag0 = fmaf(a.y, xr[4 * k4 + 1], fmaf(a.x, xr[4 * k4], ag0));
+        ag1 = fmaf(a.w, xr[4 * k4 + 3], fmaf(a.z, xr[4 * k4 + 2], ag1));
       }
       const float g = 1.0f / (1.0f + expf(-(ag0 + ag1)));
-      const float xi = ai0 + ai1;
+      const float xi = ds[tid * LD + o];
       const float gx = g * xi, dd = xi - gx;
       gxs[tid * LD + o] = gx;
       ds[tid * LD + o] = dd;
@@ -466,9 +476,13 @@ __global__ void __launch_bounds__(kRecThreads) lstm_rec_kernel(const LstmRecArgs
     const float4* gt = reinterpret_cast<const float4*>(gq + (int64_t)t * a.g_step);
     // two units per 256-bit load: a lane's row is 52 KB away from its neighbour's, so every load touches 32 different
     // sectors; with 128-bit loads each 32-byte sector was requested twice and L1 (10 % hit rate under ncu) did not keep it
+    float4 nxt[2];
+    ldg256_nc(reinterpret_cast<const float*>(gt), nxt[0], nxt[1]);
     for (int j = 0; j < H; j += 2) {
-      float4 acc2[2];
-      ldg256_nc(reinterpret_cast<const float*>(gt + j), acc2[0], acc2[1]);
+      float4 acc2[2] = {nxt[0], nxt[1]};
+      // the next pair's pre-activations are requested before this pair's arithmetic (the last iteration re-reads pair 0 of
+      // the row: harmless, in bounds)
+      ldg256_nc(reinterpret_cast<const float*>(gt + (j + 2 < H ? j + 2 : 0)), nxt[0], nxt[1]);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         float4 acc = acc2[u];
