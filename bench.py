@@ -55,7 +55,9 @@ def parse():
 def ncu_traffic_bytes(kernel_substr):
     """DRAM bytes per launch of the named kernel from the committed ncu capture (None when absent)."""
     import re
-    p = os.path.join(ROOT, "profiles", "r01_top_kernels.txt")
+    p = os.path.join(ROOT, "profiles", "r02_top_kernels_firered.txt")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_top_kernels.txt")
     if not os.path.exists(p):
         return None
     vals = []
@@ -638,7 +640,7 @@ def run_vadx(args):
         roof["traffic"] = ncu_traffic_bytes({"linear": "linear_tc_kernel", "memory": "fc2_memory_stages_kernel" if fused else "fsmn_memory_bulk_kernel",
                                              "stft": "stft_power_tc_kernel", "mel": "mel_log_kernel"}.get(dom, dom))
         if roof["traffic"] is not None:
-            roof["traffic_source"] = "profiles/r01_top_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches at this bench size)"
+            roof["traffic_source"] = "profiles/r02_top_kernels_firered.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over captured launches at this bench size)"
         if dom in stage_flops:
             tf = stage_flops[dom] * args.steps / (dom_ms * 1e-3) / 1e12
             roof["tensor"] = {"achieved_tflops_fp32_equiv": tf, "mma_products_per_fp32_product": 3 if dom == "linear" else 4,

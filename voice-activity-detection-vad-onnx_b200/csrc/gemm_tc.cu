@@ -50,6 +50,8 @@ struct TcArgs {
                   // 2: the same, but one image set per STREAM of ys_T rows ([stream][N/64][hi | lo], images of ys_img
                   //    bytes = round_up(ys_T, 16) rows): the fused fc2 + memory kernel's operand (block_stages.cu)
   int ys_T, ys_img;
+  int y_bulk;     // y_split == 2 only: the epilogue assembles each warp's 32 rows of a K chunk in shared memory exactly as they lie in
+                  // the images and one lane writes them with bulk copies (shared -> global), 4 KB per copy
   int pf_spread, pf_at;   // pf_at: the K step of the current tile at which the prefetch is issued
   const float* head_w;   // optional fused 1-output head: out = sigmoid(sum_n act(y[n]) * head_w[n] + head_b)
   float head_b;
@@ -75,7 +77,9 @@ static int lin_loader_warps() {
 static bool lw_is16() { return lin_loader_warps() != 8; }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int ACT, int LW, int NB = 3>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
+// YB: the epilogue is the bulk-store writer of per-stream operand stages and nothing else (its own instantiation, so that
+// the register allocation of the general kernel does not change)
+template <int ACT, int LW, int NB = 3, bool YB = false>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
 __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArgs g) {
   constexpr int kTcLoaderWarps = LW, kTcEpiWarp0 = LW, kTcMmaWarp = LW + 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
   uint8_t* a_smem = w_smem + w_bytes;
   float* bias_s = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);
   float* stage_out = bias_s + g.n_pad;  // 4 warps x 32 rows x 36 floats: epilogue transpose buffer
-  float* head_s = stage_out + 4 * 32 * kTcOutLd;  // [n_pad] fused-head weights (zeros when unused)
+  float* head_s = stage_out + (YB ? 4 * 8192 / 4 : 4 * 32 * kTcOutLd);  // [n_pad] fused-head weights (zeros when unused)
   uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + g.n_pad);
   // bars: full[4], empty[4], tmem_full[2], tmem_empty[2], wbar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
@@ -304,7 +308,62 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * g.n_pad);
-      if (g.head_out) {
+      if (YB) {
+        // Per-stream operand stages through BULK stores.  Measured on the 128 -> 256 layer (8192 x 98 rows, tools/block_microbench.py,
+        // VADX_TC_DEBUG): 0.29 ms with the per-lane 16-byte stores of the y_split branch below (each instruction: eight 64-byte
+        // segments in eight different images), 0.175 ms with the stores removed, 0.286 ms with the LOADS removed -- the layer
+        // was bound by its store instructions, not by bytes.  Here a warp lays its 32 rows of one K chunk (hi image rows |
+        // lo image rows, 2 x 4 KB, the chunk swizzle of the IMAGE row) out in shared memory and lane 0 hands each run of
+        // rows that is contiguous in a stream's image to cp.async.bulk (at most two runs: a stream has >= 32 rows).
+        uint8_t* my = reinterpret_cast<uint8_t*>(stage_out) + (size_t)q * 8192;
+        const uint32_t my_s = smem_u32(my);
+        const int64_t grow0 = (int64_t)tile * kTcBM + q * 32;
+        const int64_t s0 = grow0 / g.ys_T;
+        const int t0 = (int)(grow0 - s0 * g.ys_T);
+        const int n_valid = (int)min_i64(32, g.M - grow0);
+        const int n1 = min(n_valid, g.ys_T - t0), n2 = n_valid - n1;     // rows in stream s0 / in stream s0 + 1
+        const int t = lane < n1 ? t0 + lane : lane - n1;                 // this lane's row in its stream's images
+        const size_t stream_bytes = (size_t)(g.N / kTcBK) * 2 * g.ys_img;
+        uint8_t* const img0 = reinterpret_cast<uint8_t*>(g.Y) + (size_t)s0 * stream_bytes + (size_t)t0 * 128;
+        uint8_t* const img1 = reinterpret_cast<uint8_t*>(g.Y) + (size_t)(s0 + 1) * stream_bytes;
+        uint8_t* const row_hi = my + lane * 128;
+        for (int c0 = 0; c0 < g.N && n_valid > 0; c0 += kTcBK) {
+          // the previous chunk's copies must have READ the tile before it is overwritten
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(c0 + 32 * hh), v);
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0 + 32 * hh);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              split2(bias_act<ACT>(v[4 * j], b.x), bias_act<ACT>(v[4 * j + 1], b.y), hi[2 * j], lo[2 * j]);
+              split2(bias_act<ACT>(v[4 * j + 2], b.z), bias_act<ACT>(v[4 * j + 3], b.w), hi[2 * j + 1], lo[2 * j + 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int off = ((4 * hh + j) ^ (t & 7)) << 4;
+              *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              *reinterpret_cast<uint4*>(row_hi + 4096 + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+          fence_proxy_async();   // generic-proxy stores -> visible to the bulk copy (async proxy)
+          __syncwarp();
+          if (lane == 0 && !(g.debug & 1)) {
+            const size_t ci = (size_t)(c0 / kTcBK) * 2 * g.ys_img;
+            bulk_s2g(img0 + ci, my_s, (uint32_t)n1 * 128u);
+            bulk_s2g(img0 + ci + g.ys_img, my_s + 4096u, (uint32_t)n1 * 128u);
+            if (n2 > 0) {
+              bulk_s2g(img1 + ci, my_s + (uint32_t)n1 * 128u, (uint32_t)n2 * 128u);
+              bulk_s2g(img1 + ci + g.ys_img, my_s + 4096u + (uint32_t)n1 * 128u, (uint32_t)n2 * 128u);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (g.head_out) {
         // fused narrow head: the row's N activations never leave the SM
         float acc = 0.f;
         for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
@@ -362,7 +421,8 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr)
             val[itr] = *reinterpret_cast<const uint4*>(my + (itr * 4 + (lane >> 3)) * kTcOutLd + half * 16 + ch * 4);
-          if (g.y_split == 1) {
+          if (g.debug & 1) {
+          } else if (g.y_split == 1) {
             uint8_t* base = yimg + (size_t)(c0 / kTcBK) * kTcStageBytes + (size_t)half * kTcTileBytes;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
@@ -498,6 +558,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
       if (lane == 0) mbar_arrive(tempty_bar(b));
     }
   }
+  if (YB && warp >= kTcEpiWarp0 && warp < kTcMmaWarp && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == kTcMmaWarp) {
@@ -527,13 +588,15 @@ struct TcShape {
   size_t w_bytes, smem_bytes;
   bool ok;
 };
-TcShape tc_shape(int n_in, int n_out) {
+TcShape tc_shape(int n_in, int n_out, bool bulk_out = false);
+TcShape tc_shape(int n_in, int n_out, bool bulk_out) {
   TcShape s{};
   s.n_pad = (int)round_up(n_out, 16);
   s.kc = (int)ceil_div(n_in, kTcBK);
   s.n_k16 = (int)ceil_div(n_in, 16);
   s.w_bytes = (size_t)s.kc * 2 * s.n_pad * 128;
-  const size_t misc = (size_t)s.n_pad * 8 + (size_t)4 * 32 * kTcOutLd * 4 + 13 * 8 + 16;
+  // bias + head vectors, the four epilogue warps' staging tiles (padded 32 x 32 transposes, or 2 x 4 KB image rows), barriers
+  const size_t misc = (size_t)s.n_pad * 8 + (bulk_out ? (size_t)4 * 8192 : (size_t)4 * 32 * kTcOutLd * 4) + 13 * 8 + 16;
   s.ok = s.n_pad <= 256 && n_out > 8;
   if (s.ok) {
     size_t left = kTcSmemBudget > s.w_bytes + misc ? kTcSmemBudget - s.w_bytes - misc : 0;
@@ -629,6 +692,14 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   VADX_REQUIRE(s.ok, "vadx_linear_tc_f32: shape %d -> %d is not supported by the tensor-core path", n_in, n_out);
   VADX_REQUIRE(aligned16(d_wimg), "vadx_linear_tc_f32: weight image must be 16-byte aligned");
   if (n_rows == 0) return VADX_OK;
+  // per-stream stages leave through bulk stores when the wider staging tiles cost no operand stage
+  bool y_bulk = false;
+  if (y_split == 2 && rows_per_stream >= 32 && !x_split && !d_residual && !d_head_out && lin_loader_warps() == 16 &&
+      ((act & 15) == VADX_ACT_NONE || (act & 15) == VADX_ACT_RELU)) {
+    static const int want = ab_env("VADX_LIN_YBULK", 1);
+    const TcShape sb = tc_shape(n_in, n_out, true);
+    if (want && sb.ok && sb.n_stages == s.n_stages) { s = sb; y_bulk = true; }
+  }
   static PerDevice per_device;
   int n_sm = 148;
   VADX_TRY(per_device.ensure(&n_sm, [] {
@@ -636,6 +707,7 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     };
+    opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 3, true>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 3, true>);
     opt_in(linear_tc_kernel<VADX_ACT_NONE, 8>);       opt_in(linear_tc_kernel<VADX_ACT_NONE, 16>); opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_RELU, 8>);       opt_in(linear_tc_kernel<VADX_ACT_RELU, 16>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 8>);    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16>); opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16, 4>);
@@ -667,7 +739,7 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     static const int spread = ab_env("VADX_LIN_PF_SPREAD", 0);
     static const int at = ab_env("VADX_LIN_PF_AT", 0);
     g.pf_at = at == 1 ? s.kc / 2 : (at == 2 ? s.kc - 1 : 0);
-    g.x_split = x_split; g.y_split = y_split;
+    g.x_split = x_split; g.y_split = y_split; g.y_bulk = y_bulk ? 1 : 0;
     g.ys_T = g_ys_T; g.ys_img = (int)round_up(g_ys_T, 16) * 128;
     if (y_split == 2) VADX_REQUIRE(ceil_div(n_rows, (int64_t)std::max(1, g_ys_T)) * (int64_t)(n_out / kTcBK) * 2 * (round_up(g_ys_T, 16) * 128) < (1LL << 32),
                                    "linear_tc: per-stream stages of %lld rows exceed the 32-bit image offsets", (long long)n_rows);
@@ -689,6 +761,11 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     else if (lw == 16) linear_tc_kernel<A, 16><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g); \
     else linear_tc_kernel<A, 16, 4><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);            \
   } while (0)
+  if (y_bulk) {
+    if ((act & 15) == VADX_ACT_RELU) linear_tc_kernel<VADX_ACT_RELU, 16, 3, true><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);
+    else linear_tc_kernel<VADX_ACT_NONE, 16, 3, true><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);
+    return after_launch("vadx_linear_tc_f32");
+  }
   switch (act & 15) {
     case VADX_ACT_NONE: VADX_LIN_LAUNCH(VADX_ACT_NONE); break;
     case VADX_ACT_RELU: VADX_LIN_LAUNCH(VADX_ACT_RELU); break;
