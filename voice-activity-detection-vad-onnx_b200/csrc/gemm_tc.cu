@@ -22,6 +22,8 @@
 // mbarrier ring decouples the loaders from the MMA issuer.  The loaders keep TWO 32 KB stages of
 // global loads in flight per SM (three register buffers per thread): with one stage in flight the
 // kernel sat at Little's-law bandwidth (~32 KB / ~1.3 us per SM = 0.57 of the HBM peak).
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links against libcuda)
+
 #include "tc_ptx.cuh"
 
 namespace vadx {
@@ -77,10 +79,11 @@ static int lin_loader_warps() {
 static bool lw_is16() { return lin_loader_warps() != 8; }
 
 // ------------------------------------------------------------------------------------------ kernel
-// YB: the epilogue is the bulk-store writer of per-stream operand stages and nothing else (its own instantiation, so that
-// the register allocation of the general kernel does not change)
-template <int ACT, int LW, int NB = 3, bool YB = false>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
-__global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArgs g) {
+// YB: the epilogue is ONE bulk-store writer and nothing else (its own instantiations, so that the register allocation of the
+// general kernel does not change): 1 = per-stream operand stages (1-D bulk copies), 2 = fp32 rows through a 2-D tensor map
+// (cp.async.bulk.tensor: 32 x 32 boxes, rows / columns past the end clipped by the copy engine).
+template <int ACT, int LW, int NB = 3, int YB = 0>  // activation code is a compile-time constant: the per-element epilogue must not carry the sigmoid path around
+__global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArgs g, const __grid_constant__ CUtensorMap ymap) {
   constexpr int kTcLoaderWarps = LW, kTcEpiWarp0 = LW, kTcMmaWarp = LW + 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (base is 1024-aligned by the launch: dynamic smem starts at a 1024-aligned offset
@@ -88,9 +91,10 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
   uint8_t* w_smem = smem_raw;
   const int w_bytes = g.kc * 2 * g.n_pad * 128;
   uint8_t* a_smem = w_smem + w_bytes;
-  float* bias_s = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);
-  float* stage_out = bias_s + g.n_pad;  // 4 warps x 32 rows x 36 floats: epilogue transpose buffer
-  float* head_s = stage_out + (YB ? 4 * 8192 / 4 : 4 * 32 * kTcOutLd);  // [n_pad] fused-head weights (zeros when unused)
+  // YB: the staging tiles come first (1024-byte aligned: the tensor-map copies read them 128-byte swizzled)
+  float* stage_out = reinterpret_cast<float*>(a_smem + (size_t)g.n_stages * kTcStageBytes);  // 4 warps x (32 rows x 36 floats | 8 KB)
+  float* bias_s = stage_out + (YB ? 4 * 8192 / 4 : 4 * 32 * kTcOutLd);
+  float* head_s = bias_s + g.n_pad;  // [n_pad] fused-head weights (zeros when unused)
   uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + g.n_pad);
   // bars: full[4], empty[4], tmem_full[2], tmem_empty[2], wbar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp - kTcEpiWarp0;  // TMEM lane quarter this warp may touch (== warp % 4)
+    int buf = 0;                        // YB == 2: staging tile in use
     int it = 0;
     for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -308,7 +313,36 @@ __global__ void __launch_bounds__((LW + 5) * 32, 1) linear_tc_kernel(const TcArg
       const int64_t row = (int64_t)tile * kTcBM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * g.n_pad);
-      if (YB) {
+      if (YB == 2) {
+        // fp32 rows through the tensor map: the warp stages 32 rows x 32 columns (128-byte rows, 16-byte chunks XOR-swizzled
+        // with the row -- conflict-free for row-per-thread stores and exactly the tensor map's SWIZZLE_128B), lane 0 issues
+        // one 2-D bulk store per tile; two tiles alternate so that a store is in flight while the next is assembled.
+        uint8_t* my = reinterpret_cast<uint8_t*>(stage_out) + (size_t)q * 8192;
+        const uint32_t my_s = smem_u32(my);
+        const int row0 = tile * kTcBM + q * 32;
+        for (int c0 = 0; c0 < g.N; c0 += 32, buf ^= 1) {   // (buf runs on across tiles: the wait below allows ONE copy in flight)
+          float v[32];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          if (c0 + 16 < g.n_pad) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = c0 + j < g.n_pad ? bias_act<ACT>(v[j], bias_s[c0 + j]) : 0.f;
+          // the copy issued two rounds ago must have READ this tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          uint8_t* dst = my + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();   // generic-proxy stores -> visible to the bulk copy (async proxy)
+          __syncwarp();
+          if (lane == 0 && row0 < g.M && !(g.debug & 1)) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&ymap), "r"(c0), "r"(row0),
+                         "r"(my_s + (uint32_t)buf * 4096u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (YB == 1) {
         // Per-stream operand stages through BULK stores.  Measured on the 128 -> 256 layer (8192 x 98 rows, tools/block_microbench.py,
         // VADX_TC_DEBUG): 0.29 ms with the per-lane 16-byte stores of the y_split branch below (each instruction: eight 64-byte
         // segments in eight different images), 0.175 ms with the stores removed, 0.286 ms with the LOADS removed -- the layer
@@ -676,6 +710,32 @@ extern "C" int vadx_linear_head_tc_f32(const float* d_x, int64_t ldx, const void
                           head_bias, d_head_out, stream);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (null when the driver does not export it)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static const TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+// fp32 [rows][n_out] with a row pitch of ldy floats as a 2-D tensor: 32 x 32 boxes, 128-byte swizzled in shared memory
+static bool encode_rows_map(CUtensorMap* m, float* d_y, int64_t ldy, int64_t n_rows, int n_out) {
+  const TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n_out, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldy * 4u};
+  const cuuint32_t box[2] = {32u, 32u}, estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
                             const float* d_residual, int64_t ldr, float* d_y, int64_t ldy, int64_t n_rows, int n_in,
                             int n_out, int act, const float* d_head_w, float head_b, float* d_head_out, void* stream,
@@ -700,6 +760,16 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     const TcShape sb = tc_shape(n_in, n_out, true);
     if (want && sb.ok && sb.n_stages == s.n_stages) { s = sb; y_bulk = true; }
   }
+  // plain fp32 rows leave through 2-D tensor-map stores under the same condition
+  alignas(64) CUtensorMap ymap;
+  memset(&ymap, 0, sizeof(ymap));
+  bool y_tma = false;
+  if (!y_split && d_y && !d_residual && !d_head_out && lin_loader_warps() == 16 && (ldy & 3) == 0 && aligned16(d_y) &&
+      n_rows < (1LL << 31) && n_rows > kSkinnyMaxRows) {
+    static const int want = ab_env("VADX_LIN_YTMA", 1);
+    const TcShape sb = tc_shape(n_in, n_out, true);
+    if (want && sb.ok && sb.n_stages == s.n_stages && encode_rows_map(&ymap, d_y, ldy, n_rows, n_out)) { s = sb; y_tma = true; }
+  }
   static PerDevice per_device;
   int n_sm = 148;
   VADX_TRY(per_device.ensure(&n_sm, [] {
@@ -707,7 +777,10 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
     auto opt_in = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
     };
-    opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 3, true>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 3, true>);
+    opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 3, 1>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 3, 1>);
+    opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 3, 2>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 3, 2>);
+    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16, 3, 2>); opt_in(linear_tc_kernel<VADX_ACT_LOG, 16, 3, 2>);
+    opt_in(linear_tc_kernel<VADX_ACT_LOG_CLAMP, 16, 3, 2>);
     opt_in(linear_tc_kernel<VADX_ACT_NONE, 8>);       opt_in(linear_tc_kernel<VADX_ACT_NONE, 16>); opt_in(linear_tc_kernel<VADX_ACT_NONE, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_RELU, 8>);       opt_in(linear_tc_kernel<VADX_ACT_RELU, 16>); opt_in(linear_tc_kernel<VADX_ACT_RELU, 16, 4>);
     opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 8>);    opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16>); opt_in(linear_tc_kernel<VADX_ACT_SIGMOID, 16, 4>);
@@ -755,15 +828,16 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
   g.vec_y = ((ldy & 3) == 0) && aligned16(d_y) && (!d_residual || (((ldr & 3) == 0) && aligned16(d_residual)));
   int grid = (int)std::min<int64_t>(tiles, n_sm);
   const int lw = lin_loader_warps();
-#define VADX_LIN_LAUNCH(A)                                                                                \
-  do {                                                                                                    \
-    if (lw == 8) linear_tc_kernel<A, 8><<<grid, 13 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);        \
-    else if (lw == 16) linear_tc_kernel<A, 16><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g); \
-    else linear_tc_kernel<A, 16, 4><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);            \
+#define VADX_LIN_LAUNCH(A)                                                                                      \
+  do {                                                                                                          \
+    if (y_tma) linear_tc_kernel<A, 16, 3, 2><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap);   \
+    else if (lw == 8) linear_tc_kernel<A, 8><<<grid, 13 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap);   \
+    else if (lw == 16) linear_tc_kernel<A, 16><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap); \
+    else linear_tc_kernel<A, 16, 4><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap);            \
   } while (0)
   if (y_bulk) {
-    if ((act & 15) == VADX_ACT_RELU) linear_tc_kernel<VADX_ACT_RELU, 16, 3, true><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);
-    else linear_tc_kernel<VADX_ACT_NONE, 16, 3, true><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g);
+    if ((act & 15) == VADX_ACT_RELU) linear_tc_kernel<VADX_ACT_RELU, 16, 3, 1><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap);
+    else linear_tc_kernel<VADX_ACT_NONE, 16, 3, 1><<<grid, 21 * 32, s.smem_bytes, (cudaStream_t)stream>>>(g, ymap);
     return after_launch("vadx_linear_tc_f32");
   }
   switch (act & 15) {
