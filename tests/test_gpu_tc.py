@@ -33,6 +33,9 @@ def _run_tc(cuda, x, w, b, r, act):
     (777, 140, 170, 1, False, True),      # odd sizes: K = 140 -> 3 k-chunks, N padded to 176
     (513, 250, 128, 0, False, True),      # K = 250 -> 4 k-chunks (partial last chunk)
     (64, 128, 128, 2, False, True),       # fewer rows than one tile, sigmoid
+    (300000, 64, 80, 1, False, True),     # an ODD number of 32-column store rounds per tile, many tiles per CTA: the two
+                                          # staging tiles of the tensor-map store path alternate ACROSS tiles
+    (40011, 128, 96, 0, False, True),     # three rounds, ragged last tile (rows clipped by the copy engine)
 ])
 def test_linear_tc_matches_fp64(cuda, rows, n_in, n_out, act, res, bias):
     assert lib.load().vadx_tc_supported(n_in, n_out) == 1
@@ -86,6 +89,29 @@ def test_linear_tc_strided_input(cuda, rows, n_in, ldx, col0):
     bound = 1.2e-5 * (x.abs().double() @ w.abs().double().T).max().item() + 1e-6
     assert not torch.isnan(y).any()
     assert err <= bound, (err, bound)
+
+
+def test_linear_tc_strided_output_leaves_neighbours_alone(cuda):
+    """Output rows inside a wider tensor (ldy > n_out, as the K-split / N-split layers of model.hpp write them): the columns
+    beside the layer's own must keep their contents -- the 2-D tensor-map stores clip at n_out, the per-lane path guards."""
+    l = lib.load()
+    rows, n_in, n_out, ldy, col0 = 5003, 128, 80, 256, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((rows, n_in), generator=g)
+    w = torch.randn((n_out, n_in), generator=g) / np.sqrt(n_in)
+    img = torch.from_numpy(lib.pack_weight_tc(w.numpy())).to(cuda)
+    xd = x.to(cuda)
+    wide = torch.full((rows, ldy), 7.0, device=cuda)
+    y = wide[:, col0:]
+    lib.check(l.vadx_linear_tc_f32(xd.data_ptr(), n_in, img.data_ptr(), None, None, 0, y.data_ptr(), ldy, rows, n_in, n_out, 0,
+                                   lib.stream_ptr()))
+    torch.cuda.synchronize()
+    out = wide.cpu()
+    ref = x.double() @ w.double().T
+    err = (out[:, col0:col0 + n_out].double() - ref).abs().max().item()
+    print(f"tc linear into a {ldy}-wide tensor: max abs err {err:.3e}")
+    assert err <= 1.2e-5 * (x.abs().double() @ w.abs().double().T).max().item() + 1e-6
+    assert (out[:, :col0] == 7.0).all() and (out[:, col0 + n_out:] == 7.0).all()
 
 
 @pytest.mark.parametrize("act", [4, 5])

@@ -20,10 +20,10 @@ cap() { # family  dominant-regex  count  others-regex  count
 for fam in "$@"; do
   case $fam in
     firered)        cap firered 'fc2_memory_stages_kernel' 8 'linear_tc_kernel|stft_power_tc_kernel' 11 ;;
-    fsmn)           cap fsmn 'linear_tc_kernel' 20 'stft_power_tc_kernel|lfr_cmvn|fsmn_memory|gather_windows' 5 ;;
+    fsmn)           cap fsmn 'linear_tc_kernel' 12 'stft_power_tc_kernel|lfr_cmvn|fsmn_memory|gather_windows' 5 ;;
     marblenet)      cap marblenet 'stft_power_tc_kernel' 1 'depthwise_conv1d_reg_kernel|linear_tc_kernel' 10 ;;
-    silero)         cap silero 'linear_tc_kernel' 20 'silero_lstm_windows_kernel|stft_mag_compact|reflect_window' 3 ;;
-    dfsmn_aec)      cap dfsmn_aec 'linear_tc_kernel' 80 'lstm_rec_kernel|cfb_front_kernel|layernorm_perm_kernel' 8 ;;
+    silero)         cap silero 'linear_tc_kernel' 12 'silero_lstm_windows_kernel|stft_mag_compact|reflect_window' 3 ;;
+    dfsmn_aec)      cap dfsmn_aec 'linear_tc_kernel' 24 'lstm_rec_kernel|cfb_front_kernel|layernorm_perm_kernel' 8 ;;
     firered_stream) cap firered_stream 'fsmn_memory' 8 'linear_tc_kernel' 6 ;;
   esac
 done
