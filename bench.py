@@ -622,7 +622,7 @@ def run_vadx(args):
         dom_ms, dom_calls = stages[dom]
         stage_share = {k: round(v[0] / total_ms, 4) for k, v in stages.items()}
         kernel_names = {"linear": "linear_tc_kernel (tcgen05, bf16 2-term split)",
-                        "memory": ("fc2_memory_stages_kernel (tcgen05 transposed product + FIR out of TMEM)" if fused
+                        "memory": ("fc2_memory_stages_kernel (tcgen05 transposed product, fp32x2 FIR out of TMEM, bulk-copied operand and residual rings)" if fused
                                    else "fsmn_memory_bulk_kernel (cp.async.bulk ring, fp32x2 FMA)"),
                         "stft": "stft_power_tc_kernel (tcgen05, int16 exact split)", "mel": "mel_log_kernel",
                         "head": "linear_narrow_kernel", "postproc": "postprocess_frames_runs_kernel",
