@@ -768,7 +768,8 @@ static int linear_tc_launch(const float* d_x, int64_t ldx, const void* d_wimg, c
       n_rows < (1LL << 31) && n_rows > kSkinnyMaxRows) {
     static const int want = ab_env("VADX_LIN_YTMA", 1);
     const TcShape sb = tc_shape(n_in, n_out, true);
-    if (want && sb.ok && sb.n_stages == s.n_stages && encode_rows_map(&ymap, d_y, ldy, n_rows, n_out)) { s = sb; y_tma = true; }
+    // (the wider staging tiles may cost the fourth operand stage, never the second or third)
+    if (want && sb.ok && sb.n_stages >= std::min(s.n_stages, 3) && encode_rows_map(&ymap, d_y, ldy, n_rows, n_out)) { s = sb; y_tma = true; }
   }
   static PerDevice per_device;
   int n_sm = 148;
