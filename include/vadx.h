@@ -174,7 +174,10 @@ int vadx_linear_f32(const float* d_x, int64_t ldx, const float* d_wt, int ldw, c
  * vadx_tc_supported: 1 when (n_in, n_out) fits the weights-stationary kernel (n_out in 9..256 and
  * the image + two activation stages fit in shared memory).
  * vadx_pack_weight_tc: h_w is the reference-layout weight [n_out][n_in] on the HOST; call with
- * h_img = NULL to query *img_bytes. */
+ * h_img = NULL to query *img_bytes.
+ * Output rows without a residual input leave through 2-D tensor-map bulk stores (cp.async.bulk.tensor) when ldy % 4 == 0
+ * and d_y is 16-byte aligned; the map is encoded per call (cuTensorMapEncodeTiled via cudaGetDriverEntryPoint; the library
+ * does not link against libcuda) and the per-lane store path is taken when the driver does not export the encoder. */
 int vadx_tc_supported(int n_in, int n_out);
 int vadx_pack_weight_tc(const float* h_w, int n_out, int n_in, void* h_img, size_t img_capacity, size_t* img_bytes);
 int vadx_linear_tc_f32(const float* d_x, int64_t ldx, const void* d_wimg, const float* d_bias,
@@ -215,7 +218,9 @@ int vadx_fsmn_memory_f32(const float* d_p, int64_t ldp, const float* d_wl, int n
  *   vadx_fc2_memory_stages_f32:  p = act(h W2^T + b2) issued transposed (accumulator = p^T in tensor memory),
  *       out = p + FIR_back(p) + FIR_ahead(p) (+ residual); d_residual / d_out [S*T][128]; p never reaches HBM.
  * Supported: n_out(fc2) = 128, n_in(fc2) in {64,128,192,256}, n_frames = 98, 20 + 20 unit-stride taps (a chunk is
- * zero-padded in time by definition, so there is no halo); act NONE or RELU.  d_wimg from vadx_pack_weight_tc. */
+ * zero-padded in time by definition, so there is no halo); act NONE or RELU.  d_wimg from vadx_pack_weight_tc.
+ * d_himg, d_wimg and d_residual must be 16-byte aligned (they are read with bulk copies); d_wl and d_wr are required.
+ * The stages are written with bulk stores (shared -> global) when rows_per_stream >= 32, else with per-lane stores. */
 size_t vadx_fc2_memory_stages_stream_bytes(int n_in, int n_frames);
 int vadx_fc2_memory_stages_supported(int n_in, int n_out, int n_frames, int n_back, int stride_back, int n_ahead,
                                      int stride_ahead);
