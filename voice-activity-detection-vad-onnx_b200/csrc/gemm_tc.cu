@@ -16,12 +16,19 @@
 // pulls its whole stationary operand with a handful of 1-D bulk async copies (cp.async.bulk ->
 // mbarrier complete_tx); activations are converted fp32 -> (hi, lo) bf16 by the loader warps.
 //
-// CTA = 13 warps: 0-7 loaders (global fp32 -> split -> swizzled smem), 8-11 epilogue (TMEM -> regs ->
-// bias/act/residual -> global), 12 = TMEM allocator + single-thread MMA issuer.  Two TMEM
+// CTA = 21 warps: 0-15 loaders (global fp32 -> split -> swizzled smem; 8 in the LW = 8 measurement variant), 16-19
+// epilogue (TMEM -> regs -> bias/act/residual -> global), 20 = TMEM allocator + single-thread MMA issuer.  Two TMEM
 // accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1; a 2-4 deep
 // mbarrier ring decouples the loaders from the MMA issuer.  The loaders keep TWO 32 KB stages of
 // global loads in flight per SM (three register buffers per thread): with one stage in flight the
 // kernel sat at Little's-law bandwidth (~32 KB / ~1.3 us per SM = 0.57 of the HBM peak).
+//
+// Epilogues (template parameter YB; DESIGN.md section 3 "Bulk-store epilogues"): the wide layers were bound by their STORE
+// INSTRUCTIONS, so the two hot output forms leave through the bulk-copy engine -- YB = 1: per-stream operand stages for the
+// fused block tail (block_stages.cu), assembled in shared memory as they lie in the images and written with 1-D
+// cp.async.bulk shared -> global; YB = 2: plain fp32 rows through a 2-D tensor map (cp.async.bulk.tensor, 32 x 32 boxes,
+// edges clipped by the copy engine).  YB = 0 keeps the per-lane paths: residual input, fused head, K-split accumulation,
+// unaligned outputs, and the operand-stage forms the bulk path does not cover.
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links against libcuda)
 
 #include "tc_ptx.cuh"
